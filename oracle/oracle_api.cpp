@@ -1,0 +1,88 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  C entry points (ctypes / bench cpu_baseline) over the
+// C++ restatement in ros.hpp / models.hpp.  Cells are independent; OpenMP loops over them the way
+// a user of the (serial, single-system) reference would loop over INTEGRATE_ADJ calls.
+// Layout: cell-major ("array of systems"): y[cell][N], lambda[cell][NADJ][N] (= Fortran
+// Lambda(N,NADJ) per cell), mu[cell][NADJ][NP], istatus[cell][20], rstatus[cell][20].
+#include <omp.h>
+#include <cstring>
+#include "models.hpp"
+#include "ros.hpp"
+
+using namespace oracle;
+
+enum { MODEL_ROBERTS = 1, MODEL_SMALL_STRATO = 2, MODEL_CBM4 = 3 };
+
+template <class M>
+static void adj_batch(long ncells, int np, int nadj, double* y, double* lambda, double* mu, double tin, double tout,
+                      const double* atol, const double* rtol, const int* icntrl, const double* rcntrl, int* istatus,
+                      double* rstatus, int* ierr, int nthreads) {
+  const int N = M::N;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+  for (long c = 0; c < ncells; ++c) {
+    M mdl;
+    ierr[c] = ros_integrate_adj<M>(mdl, np, nadj, y + c * N, lambda + c * (long)N * nadj,
+                                   (np > 0 && mu) ? mu + c * (long)np * nadj : nullptr, tin, tout, atol, rtol, icntrl,
+                                   rcntrl, istatus + c * 20, rstatus + c * 20);
+  }
+}
+
+template <class M>
+static void fwd_batch(long ncells, double* y, double tin, double tout, const double* atol, const double* rtol,
+                      const int* icntrl, const double* rcntrl, int* istatus, double* rstatus, int* ierr, int nthreads) {
+  const int N = M::N;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+  for (long c = 0; c < ncells; ++c) {
+    M mdl;
+    ierr[c] = ros_integrate<M>(mdl, tin, tout, y + c * N, rtol, atol, icntrl, rcntrl, istatus + c * 20, rstatus + c * 20);
+  }
+}
+
+extern "C" {
+
+int oracle_max_threads() { return omp_get_max_threads(); }
+
+int oracle_model_dims(int model, int* n, int* np) {
+  switch (model) {
+    case MODEL_ROBERTS: *n = Roberts::N; *np = Roberts::NP; return 0;
+    case MODEL_SMALL_STRATO: *n = SmallStrato::N; *np = SmallStrato::NP; return 0;
+    case MODEL_CBM4: *n = Cbm4::N; *np = Cbm4::NP; return 0;
+  }
+  return -1;
+}
+
+int oracle_initial_state(int model, double* y) {
+  switch (model) {
+    case MODEL_ROBERTS: Roberts::initial_state(y); return 0;
+    case MODEL_SMALL_STRATO: SmallStrato::initial_state(y); return 0;
+    case MODEL_CBM4: Cbm4::initial_state(y); return 0;
+  }
+  return -1;
+}
+
+// FWD/ROS INTEGRATE looped over cells
+int oracle_ros_fwd_batch(int model, long ncells, double* y, double tin, double tout, const double* atol,
+                         const double* rtol, const int* icntrl, const double* rcntrl, int* istatus, double* rstatus,
+                         int* ierr, int nthreads) {
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+  switch (model) {
+    case MODEL_ROBERTS: fwd_batch<Roberts>(ncells, y, tin, tout, atol, rtol, icntrl, rcntrl, istatus, rstatus, ierr, nthreads); return 0;
+    case MODEL_SMALL_STRATO: fwd_batch<SmallStrato>(ncells, y, tin, tout, atol, rtol, icntrl, rcntrl, istatus, rstatus, ierr, nthreads); return 0;
+    case MODEL_CBM4: fwd_batch<Cbm4>(ncells, y, tin, tout, atol, rtol, icntrl, rcntrl, istatus, rstatus, ierr, nthreads); return 0;
+  }
+  return -1;
+}
+
+// ADJ/ROS_ADJ INTEGRATE_ADJ looped over cells (mu == NULL or np == 0 -> RosenbrockADJ2)
+int oracle_ros_adj_batch(int model, long ncells, int np, int nadj, double* y, double* lambda, double* mu, double tin,
+                         double tout, const double* atol, const double* rtol, const int* icntrl, const double* rcntrl,
+                         int* istatus, double* rstatus, int* ierr, int nthreads) {
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+  switch (model) {
+    case MODEL_ROBERTS: adj_batch<Roberts>(ncells, np, nadj, y, lambda, mu, tin, tout, atol, rtol, icntrl, rcntrl, istatus, rstatus, ierr, nthreads); return 0;
+    case MODEL_SMALL_STRATO: adj_batch<SmallStrato>(ncells, np, nadj, y, lambda, mu, tin, tout, atol, rtol, icntrl, rcntrl, istatus, rstatus, ierr, nthreads); return 0;
+    case MODEL_CBM4: adj_batch<Cbm4>(ncells, np, nadj, y, lambda, mu, tin, tout, atol, rtol, icntrl, rcntrl, istatus, rstatus, ierr, nthreads); return 0;
+  }
+  return -1;
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (never linked into the product path).
+//
+// Restatement of the third-party dense kernels the reference's FULL_ALGEBRA
+// path links (un-vendored netlib reference BLAS/LAPACK 3.x, see SURVEY.md §8c;
+// call sites ADJ/ROS_ADJ/LS_Solver.F90:41 DGETRF, :50,:52 DGETRS;
+// ADJ/RK_ADJ/LS_Solver.F90:55 ZGETRF, :104,:106 ZGETRS).  For N < 64 netlib
+// DGETRF/ZGETRF run the unblocked DGETF2/ZGETF2 (NB=64 from ILAENV), which is
+// what is restated here, loop order and all:
+//   DGETF2: IDAMAX first-maximal pivot, DSWAP of full rows, reciprocal scaling
+//           when |pivot| >= sfmin, DGER rank-1 update a(i,j) += x(i)*(-y(j)).
+//   DGETRS: DLASWP + DTRSM(L,L,N,U) + DTRSM(L,U,N,N)   for 'N'
+//           DTRSM(L,U,T,N) + DTRSM(L,L,T,U) + DLASWP^-1 for 'T'
+// Matrices are column-major with leading dimension n; pivots are 1-based like
+// LAPACK's IPIV.  Compile with -ffp-contract=off (no FMA) to match the
+// reference's x86-64 SSE2 build.
+#pragma once
+#include <cmath>
+#include <cfloat>
+
+namespace oracle {
+
+// DLAMCH('E') as used by the integrators (ADJ/ROS_ADJ/..:455): relative machine eps = 2^-53
+static inline double dlamch_eps() { return DBL_EPSILON * 0.5; }
+// DLAMCH('S') safe minimum (netlib dlamch: sfmin = tiny, bumped if 1/huge >= tiny)
+static inline double dlamch_sfmin() {
+  double sfmin = DBL_MIN, small = 1.0 / DBL_MAX;
+  if (small >= sfmin) sfmin = small * (1.0 + dlamch_eps());
+  return sfmin;
+}
+
+// returns info (0 ok, j>0: U(j,j) exactly zero, first such j, 1-based)
+static inline int dgetf2(int n, double* a, int* ipiv) {
+  const double sfmin = dlamch_sfmin();
+  int info = 0;
+  for (int j = 0; j < n; ++j) {
+    // IDAMAX over a(j:n-1, j): first index of max |.|
+    int jp = j;
+    double dmax = std::fabs(a[j + n * j]);
+    for (int i = j + 1; i < n; ++i) {
+      double v = std::fabs(a[i + n * j]);
+      if (v > dmax) { dmax = v; jp = i; }
+    }
+    ipiv[j] = jp + 1;
+    if (a[jp + n * j] != 0.0) {
+      if (jp != j)
+        for (int c = 0; c < n; ++c) { double t = a[j + n * c]; a[j + n * c] = a[jp + n * c]; a[jp + n * c] = t; }
+      if (j < n - 1) {
+        if (std::fabs(a[j + n * j]) >= sfmin) {
+          double r = 1.0 / a[j + n * j];
+          for (int i = j + 1; i < n; ++i) a[i + n * j] = r * a[i + n * j];   // DSCAL: da*dx(i)
+        } else {
+          for (int i = j + 1; i < n; ++i) a[i + n * j] = a[i + n * j] / a[j + n * j];
+        }
+      }
+    } else if (info == 0) {
+      info = j + 1;
+    }
+    if (j < n - 1) {
+      // DGER(m-j, n-j, -1, x=a(j+1:,j), y=a(j,j+1:), A=a(j+1:,j+1:))
+      for (int c = j + 1; c < n; ++c) {
+        double yc = a[j + n * c];
+        if (yc != 0.0) {
+          double temp = -1.0 * yc;
+          for (int i = j + 1; i < n; ++i) a[i + n * c] = a[i + n * c] + a[i + n * j] * temp;
+        }
+      }
+    }
+  }
+  return info;
+}
+
+// DGETRS with one right-hand side
+static inline void dgetrs(bool trans, int n, const double* a, const int* ipiv, double* b) {
+  if (!trans) {
+    for (int i = 0; i < n; ++i) {            // DLASWP forward
+      int ip = ipiv[i] - 1;
+      if (ip != i) { double t = b[i]; b[i] = b[ip]; b[ip] = t; }
+    }
+    for (int k = 0; k < n; ++k)              // DTRSM Left Lower NoTrans Unit
+      if (b[k] != 0.0)
+        for (int i = k + 1; i < n; ++i) b[i] = b[i] - b[k] * a[i + n * k];
+    for (int k = n - 1; k >= 0; --k)         // DTRSM Left Upper NoTrans NonUnit
+      if (b[k] != 0.0) {
+        b[k] = b[k] / a[k + n * k];
+        for (int i = 0; i < k; ++i) b[i] = b[i] - b[k] * a[i + n * k];
+      }
+  } else {
+    for (int i = 0; i < n; ++i) {            // DTRSM Left Upper Trans NonUnit
+      double temp = b[i];
+      for (int k = 0; k < i; ++k) temp = temp - a[k + n * i] * b[k];
+      temp = temp / a[i + n * i];
+      b[i] = temp;
+    }
+    for (int i = n - 1; i >= 0; --i) {       // DTRSM Left Lower Trans Unit
+      double temp = b[i];
+      for (int k = i + 1; k < n; ++k) temp = temp - a[k + n * i] * b[k];
+      b[i] = temp;
+    }
+    for (int i = n - 1; i >= 0; --i) {       // DLASWP backward
+      int ip = ipiv[i] - 1;
+      if (ip != i) { double t = b[i]; b[i] = b[ip]; b[ip] = t; }
+    }
+  }
+}
+
+}  // namespace oracle
