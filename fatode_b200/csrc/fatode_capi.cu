@@ -1,0 +1,523 @@
+// fatode_b200 — C-ABI entry points (include/fatode_b200.h), kernels and the host-side wave scheduler.
+//
+// Execution model for INTEGRATE_ADJ over a batch:
+//   cells are processed in waves sized to the trajectory-tape budget in HBM.  Per wave:
+//     1. k_ros_fwd<TAPE=false>  forward sweep, one cell per warp -> y(Tend), ISTATUS, RSTATUS, IERR,
+//                               accepted-step count per cell
+//     2. k_scan_offsets         exclusive prefix sum of the counts -> exact tape offsets
+//     3. k_ros_fwd<TAPE=true>   the same sweep again (bit-identical by construction), writing
+//                               (T,H,Ystage,K) per accepted step at the cell's offset
+//     4. k_ros_adj              backward sweep, persistent warps pulling cells from an atomic queue
+//   then one deterministic two-stage reduction of Mu over cells (k_mu_reduce*).
+// There is no CPU path: every failure to reach the GPU is reported as an error.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/fatode_b200.h"
+#include "fatode_common.cuh"
+#include "ros_options.h"
+#include "model_cbm4.cuh"
+#include "ros_warp_fwd.cuh"
+#include "ros_warp_adj.cuh"
+
+using namespace fatode;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+static thread_local std::string g_err;
+static thread_local fatode_stats g_stats;
+static uint64_t g_tape_budget = 0;
+static int64_t g_wave_cells = 0;
+
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(x)                                                                              \
+  do {                                                                                           \
+    cudaError_t e_ = (x);                                                                        \
+    if (e_ != cudaSuccess) {                                                                     \
+      int code_ = (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? FATODE_ENODEVICE : FATODE_ECUDA; \
+      return fail(code_, std::string(#x) + ": " + cudaGetErrorString(e_));                      \
+    }                                                                                            \
+  } while (0)
+
+extern "C" const char* fatode_last_error(void) { return g_err.c_str(); }
+extern "C" const char* fatode_version(void) { return "fatode_b200 0.1 (sm_100a)"; }
+extern "C" int fatode_set_tape_budget(uint64_t bytes) { g_tape_budget = bytes; return 0; }
+extern "C" int fatode_set_wave_cells(int64_t cells) { g_wave_cells = cells; return 0; }
+extern "C" int fatode_get_last_stats(fatode_stats* out) { if (!out) return FATODE_EINVAL; *out = g_stats; return 0; }
+
+extern "C" void* fatode_alloc_pinned(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { g_err = "cudaHostAlloc failed"; return nullptr; }
+  return p;
+}
+extern "C" void fatode_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" int fatode_model_dims(int model, int* nvar, int* np) {
+  switch (model) {
+    case FATODE_MODEL_ROBERTS: *nvar = 3; *np = 3; return 0;
+    case FATODE_MODEL_SMALL_STRATO: *nvar = 5; *np = 0; return 0;
+    case FATODE_MODEL_CBM4: *nvar = 32; *np = 29; return 0;
+  }
+  return fail(FATODE_EINVAL, "unknown model id");
+}
+
+extern "C" int fatode_model_initial_state(int model, double* y) {
+  if (!y) return fail(FATODE_EINVAL, "y is NULL");
+  switch (model) {
+    case FATODE_MODEL_ROBERTS: y[0] = 1; y[1] = 0; y[2] = 0; return 0;                    // roberts_ros_adj_dr.F90:194-196
+    case FATODE_MODEL_SMALL_STRATO:                                                         // small_strato_dr.F90:50-54
+      y[0] = (double)9.906E+01f; y[1] = (double)6.624E+08f; y[2] = (double)5.326E+11f;
+      y[3] = (double)8.725E+08f; y[4] = (double)2.240E+08f; return 0;
+    case FATODE_MODEL_CBM4: {                                                               // cbm4_ros_adj_dr.F90:233-264
+      static const double v[32] = {
+          3.652686375061191e-02, 3.470772014720235e+11, 2.558736854382598e+03, 3.353179955426548e-23,
+          5.287698343141944e-20, 1.307511063007438e+07, 0.0, 1.985180650951722e+01,
+          3.839565210778183e+08, 2.675425503948970e+08, 1.593461800730453e-24, 1.191924698309334e+12,
+          4.894101892069533e-05, 5.462490511678749e-21, 1.943997577140665e-23, 2.329863421033919e+12,
+          2.106517721289787e-30, 5.518957651363696e+08, 2.633932009302457e-21, 8.118206770655152e+03,
+          3.000632019118241e+10, 0.0, 0.0, 2.687919546821573e+02,
+          2.061185883675469e+12, 1.561906017211229e+10, 3.671987743784878e+07, 9.888485531199334e+08,
+          1.248793414327174e+04, 3.357869003391008e+07, 2.727638922137502e+09, 6.534644475169904e+00};
+      std::memcpy(y, v, sizeof v);
+      return 0;
+    }
+  }
+  return fail(FATODE_EINVAL, "unknown model id");
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+
+constexpr int FWD_WARPS = 4;
+constexpr int ADJ_WARPS = 3;
+
+template <class Model>
+__host__ __device__ constexpr int fwd_ws_doubles() { return Model::WS_DOUBLES + ((Model::NJ + 1) / 2) * 2 + 1024; }
+
+template <class Model, bool TAPE>
+__global__ void __launch_bounds__(FWD_WARPS * 32)
+k_ros_fwd(RosParams rp, typename Model::Const mc, long ncells, const double* __restrict__ y_in, double* __restrict__ y_out,
+          const double* __restrict__ atol, const double* __restrict__ rtol, int* __restrict__ istatus,
+          double* __restrict__ rstatus, int* __restrict__ ierr, int* __restrict__ nacc,
+          const long long* __restrict__ tape_off, double* __restrict__ tape) {
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long cell = (long)blockIdx.x * FWD_WARPS + warp;
+  if (cell >= ncells) return;
+  if (TAPE && ierr[cell] != 1) return;
+  double* ws = smem + (size_t)warp * fwd_ws_doubles<Model>();
+  double* tile = ws + Model::WS_DOUBLES + ((Model::NJ + 1) / 2) * 2;
+  double y = y_in[cell * 32 + lane];
+  const int ti = rp.vector_tol ? lane : 0;
+  FwdResult res;
+  double* tb = nullptr;
+  long cap = 0;
+  if (TAPE) {
+    tb = tape + tape_off[cell] * tape_entry_doubles(rp.S, 32);
+    cap = (long)(tape_off[cell + 1] - tape_off[cell]);
+  }
+  ros_forward_warp<Model, TAPE>(rp, mc, ws, tile, y, atol[ti], rtol[ti], tb, cap, res, lane);
+  if (!TAPE) {
+    y_out[cell * 32 + lane] = y;
+    if (lane < 8) istatus[cell * 20 + lane] = res.istatus[lane];
+    else if (lane < 20) istatus[cell * 20 + lane] = 0;
+    if (lane < 20) {
+      double r = 0.0;
+      if (lane == Ntexit) r = res.texit; else if (lane == Nhexit) r = res.hexit; else if (lane == Nhnew) r = res.hnew;
+      rstatus[cell * 20 + lane] = r;
+    }
+    if (lane == 0) { ierr[cell] = res.ierr; nacc[cell] = res.istatus[Nacc]; }
+  }
+}
+
+// exclusive scan of nacc (only cells with ierr == 1 get tape space); single block
+__global__ void k_scan_offsets(long ncells, const int* __restrict__ nacc, const int* __restrict__ ierr,
+                               long long* __restrict__ off) {
+  __shared__ long long part[1024];
+  __shared__ long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (long base = 0; base < ncells; base += 1024) {
+    long i = base + threadIdx.x;
+    long long v = (i < ncells && ierr[i] == 1) ? nacc[i] : 0;
+    part[threadIdx.x] = v;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+      long long t = (threadIdx.x >= d) ? part[threadIdx.x - d] : 0;
+      __syncthreads();
+      part[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < ncells) off[i] = carry + part[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += part[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) off[ncells] = carry;
+}
+
+template <class Model>
+__global__ void __launch_bounds__(ADJ_WARPS * 32, 1)
+k_ros_adj(RosParams rp, typename Model::Const mc, long ncells, int nadj, int with_mu, const double* __restrict__ tape,
+          const long long* __restrict__ tape_off, const int* __restrict__ ierr, const double* __restrict__ y_final,
+          double* __restrict__ lambda, double* __restrict__ mu, int* __restrict__ istatus,
+          unsigned long long* __restrict__ queue, int smem_per_warp) {
+  extern __shared__ __align__(16) double smem[];
+  typedef AdjSmem<Model> L;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sm = smem + (size_t)warp * smem_per_warp;
+  const int NE = tape_entry_doubles(rp.S, 32);
+  for (;;) {
+    unsigned long long c = 0;
+    if (lane == 0) c = atomicAdd(queue, 1ull);
+    c = __shfl_sync(FATODE_FULL_MASK, c, 0);
+    if (c >= (unsigned long long)ncells) break;
+    if (ierr[c] != 1) continue;
+    const int nsteps = (int)(tape_off[c + 1] - tape_off[c]);
+    const double yf = y_final[c * 32 + lane];
+    ros_adjoint_warp<Model>(rp, mc, sm, tape + tape_off[c] * NE, nsteps, nadj, with_mu != 0, yf, lane);
+    __syncwarp();
+    const double* LAM = sm + L::OFF_LAM;
+    const double* MU = sm + L::OFF_MU;
+    for (int m = 0; m < nadj; ++m) {
+      lambda[((long)c * nadj + m) * 32 + lane] = LAM[lane * 32 + m];
+      if (with_mu && lane < Model::NP) mu[((long)c * nadj + m) * Model::NP + lane] = MU[lane * 32 + m];
+    }
+    if (lane == 0) {   // counters of the backward sweep (ADJ :1257-1267, :1303, :1312, :1381)
+      int* is = istatus + c * 20;
+      is[Nstp] += nsteps;
+      is[Njac] += nsteps * (2 + rp.S + (rp.autonomous ? 0 : 1));
+      is[Ndec] += nsteps;
+      is[Nsol] += nsteps * rp.S * nadj;
+    }
+    __syncwarp();
+  }
+}
+
+// deterministic sum of mu over cells: stage 1 partial sums over fixed cell blocks, stage 2 over blocks
+__global__ void k_mu_reduce1(long ncells, int len, const double* __restrict__ mu, const int* __restrict__ ierr,
+                             double* __restrict__ partial, int cells_per_block) {
+  const long c0 = (long)blockIdx.x * cells_per_block;
+  const long c1 = min(ncells, c0 + cells_per_block);
+  for (int j = threadIdx.x; j < len; j += blockDim.x) {
+    double s = 0.0;
+    for (long c = c0; c < c1; ++c)
+      if (ierr[c] == 1) s += mu[c * len + j];
+    partial[(long)blockIdx.x * len + j] = s;
+  }
+}
+__global__ void k_mu_reduce2(int nblocks, int len, const double* __restrict__ partial, double* __restrict__ out) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= len) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += partial[(long)b * len + j];
+  out[j] = s;
+}
+
+// FP64 peak probe: 8 independent DFMA chains per thread
+__global__ void k_dfma_probe(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" double fatode_measure_fp64_peak(int iters) {
+  if (iters <= 0) iters = 20000;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { g_err = "no CUDA device"; return -1.0; }
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = sms * 8, threads = 256;
+  double* d = nullptr;
+  if (cudaMalloc(&d, sizeof(double) * blocks * threads) != cudaSuccess) { g_err = "cudaMalloc failed"; return -1.0; }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k_dfma_probe<<<blocks, threads>>>(d, iters / 10);   // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    k_dfma_probe<<<blocks, threads>>>(d, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  if (cudaGetLastError() != cudaSuccess) { g_err = "dfma probe failed"; return -1.0; }
+  const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+  return flops / (best * 1e-3) / 1e12;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+
+static int cbm4_constants(const double* params, Cbm4Const& mc) {
+  std::memset(&mc, 0, sizeof mc);
+  mc.temp = params ? params[0] : 298.0;                    // cbm4_ros_adj_dr.F90:268
+  mc.fix = params ? params[1] : (1.25e+8) * 2.55e10;       // :178,202
+  mc.emis = params ? params[2] : 2.0e3;                    // :96-97
+  for (int i = 0; i < 41; ++i)                             // ARR2 (cbm4_Parameters.F90:2389-2392)
+    mc.rc_base[cbm4_dev::ARR_IDX[i]] = cbm4_dev::ARR_A0[i] * std::exp(cbm4_dev::ARR_B0[i] / mc.temp);
+  return 0;
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8); }
+  template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct PhaseTimer {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaStream_t s;
+  explicit PhaseTimer(cudaStream_t st) : s(st) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
+  ~PhaseTimer() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+  void start() { cudaEventRecord(e0, s); }
+  double stop() { cudaEventRecord(e1, s); cudaEventSynchronize(e1); float ms = 0; cudaEventElapsedTime(&ms, e0, e1); return ms; }
+};
+
+static int check_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) return fail(FATODE_ENODEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+// core of INTEGRATE_ADJ on device-resident arrays (cbm4 / warp family)
+template <class Model>
+static int ros_adj_device(const RosParams& rp, const typename Model::Const& mc, int64_t ncells, int nadj, bool with_mu,
+                          bool do_adjoint, double* d_y, double* d_lambda, double* d_mu, const double* d_atol,
+                          const double* d_rtol, int* d_istatus, double* d_rstatus, int* d_ierr, double* d_mu_sum,
+                          cudaStream_t st) {
+  const int NE = tape_entry_doubles(rp.S, 32);
+  const size_t entry_bytes = sizeof(double) * NE;
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const size_t fwd_smem = sizeof(double) * fwd_ws_doubles<Model>() * FWD_WARPS;
+  const int adj_per_warp = AdjSmem<Model>::doubles(rp.S);
+  const size_t adj_smem = sizeof(double) * (size_t)adj_per_warp * ADJ_WARPS;
+  CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd<Model, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
+  CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd<Model, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
+  CUDA_TRY(cudaFuncSetAttribute(k_ros_adj<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem));
+
+  size_t free_b = 0, total_b = 0;
+  CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+  size_t budget = g_tape_budget ? (size_t)g_tape_budget : (size_t)(0.6 * (double)free_b);
+  budget = std::min(budget, (size_t)(0.9 * (double)free_b));
+  if (!do_adjoint) budget = 0;
+  const long long cap_entries = (long long)(budget / entry_bytes);
+
+  int64_t wave = g_wave_cells > 0 ? g_wave_cells : 16384;
+  wave = std::min<int64_t>(wave, ncells);
+  DevBuf b_y0, b_nacc, b_off, b_tape, b_queue;
+  CUDA_TRY(b_y0.alloc(sizeof(double) * 32 * wave));
+  CUDA_TRY(b_nacc.alloc(sizeof(int) * wave));
+  CUDA_TRY(b_off.alloc(sizeof(long long) * (wave + 1)));
+  CUDA_TRY(b_queue.alloc(sizeof(unsigned long long)));
+  if (do_adjoint) CUDA_TRY(b_tape.alloc(budget));
+  PhaseTimer tm(st);
+  std::memset(&g_stats, 0, sizeof g_stats);
+
+  int64_t c0 = 0;
+  std::vector<long long> h_off;
+  while (c0 < ncells) {
+    int64_t n = std::min<int64_t>(wave, ncells - c0);
+    double* y = d_y + c0 * 32;
+    int* ist = d_istatus + c0 * 20;
+    double* rst = d_rstatus + c0 * 20;
+    int* ier = d_ierr + c0;
+    // 1. forward without tape (keeps the initial state for the taped pass)
+    CUDA_TRY(cudaMemcpyAsync(b_y0.p, y, sizeof(double) * 32 * n, cudaMemcpyDeviceToDevice, st));
+    const int fblocks = (int)((n + FWD_WARPS - 1) / FWD_WARPS);
+    tm.start();
+    k_ros_fwd<Model, false><<<fblocks, FWD_WARPS * 32, fwd_smem, st>>>(rp, mc, n, b_y0.as<double>(), y, d_atol, d_rtol, ist,
+                                                                         rst, ier, b_nacc.as<int>(), nullptr, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    g_stats.ms_forward += tm.stop();
+    g_stats.launches++;
+    if (!do_adjoint) { c0 += n; g_stats.waves++; continue; }
+    // 2. tape offsets
+    k_scan_offsets<<<1, 1024, 0, st>>>(n, b_nacc.as<int>(), ier, b_off.as<long long>());
+    CUDA_TRY(cudaGetLastError());
+    g_stats.launches++;
+    h_off.resize(n + 1);
+    CUDA_TRY(cudaMemcpyAsync(h_off.data(), b_off.p, sizeof(long long) * (n + 1), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    int64_t fit = n;
+    if (h_off[n] > cap_entries) {   // keep the prefix of cells whose trajectories fit the tape
+      fit = std::upper_bound(h_off.begin(), h_off.end(), cap_entries) - h_off.begin() - 1;
+      if (fit <= 0) return fail(FATODE_ENOMEM, "trajectory tape of a single cell exceeds the tape budget");
+      wave = std::max<int64_t>(1, fit);   // later waves: what fitted this time
+    }
+    g_stats.tape_bytes_peak = std::max<uint64_t>(g_stats.tape_bytes_peak, (uint64_t)h_off[fit] * entry_bytes);
+    g_stats.accepted_steps += h_off[fit];
+    // 3. forward with tape
+    const int tblocks = (int)((fit + FWD_WARPS - 1) / FWD_WARPS);
+    tm.start();
+    k_ros_fwd<Model, true><<<tblocks, FWD_WARPS * 32, fwd_smem, st>>>(rp, mc, fit, b_y0.as<double>(), nullptr, d_atol, d_rtol,
+                                                                        ist, rst, ier, b_nacc.as<int>(), b_off.as<long long>(),
+                                                                        b_tape.as<double>());
+    CUDA_TRY(cudaGetLastError());
+    g_stats.ms_forward_tape += tm.stop();
+    g_stats.launches++;
+    // 4. backward sweep
+    CUDA_TRY(cudaMemsetAsync(b_queue.p, 0, sizeof(unsigned long long), st));
+    const int ablocks = (int)std::min<int64_t>(sms, (fit + ADJ_WARPS - 1) / ADJ_WARPS);
+    tm.start();
+    k_ros_adj<Model><<<ablocks, ADJ_WARPS * 32, adj_smem, st>>>(rp, mc, fit, nadj, with_mu ? 1 : 0, b_tape.as<double>(),
+                                                                  b_off.as<long long>(), ier, y, d_lambda + c0 * nadj * 32,
+                                                                  with_mu ? d_mu + c0 * nadj * Model::NP : nullptr, ist,
+                                                                  b_queue.as<unsigned long long>(), adj_per_warp);
+    CUDA_TRY(cudaGetLastError());
+    g_stats.ms_adjoint += tm.stop();
+    g_stats.launches++;
+    if (fit < n) {   // cells beyond the prefix: restore their initial state, they run in the next wave
+      CUDA_TRY(cudaMemcpyAsync(y + fit * 32, b_y0.as<double>() + fit * 32, sizeof(double) * 32 * (n - fit),
+                               cudaMemcpyDeviceToDevice, st));
+    }
+    c0 += fit;
+    g_stats.waves++;
+  }
+  // deterministic Mu sum over cells
+  if (do_adjoint && with_mu && d_mu_sum) {
+    const int len = nadj * Model::NP;
+    const int cpb = 256;
+    const int nb = (int)((ncells + cpb - 1) / cpb);
+    DevBuf part;
+    CUDA_TRY(part.alloc(sizeof(double) * (size_t)nb * len));
+    tm.start();
+    k_mu_reduce1<<<nb, 256, 0, st>>>(ncells, len, d_mu, d_ierr, part.as<double>(), cpb);
+    k_mu_reduce2<<<(len + 255) / 256, 256, 0, st>>>(nb, len, part.as<double>(), d_mu_sum);
+    CUDA_TRY(cudaGetLastError());
+    g_stats.ms_other += tm.stop();
+    g_stats.launches += 2;
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+static int check_model_dims(int model, int nvar, int np) {
+  int n = 0, p = 0;
+  if (fatode_model_dims(model, &n, &p) != 0) return FATODE_EINVAL;
+  if (n != nvar) return fail(FATODE_EINVAL, "nvar does not match the registered model");
+  if (np != 0 && np != p) return fail(FATODE_EINVAL, "np does not match the registered model");
+  return 0;
+}
+
+// fills per-cell ierr with a parse error (the reference returns before touching Y)
+static int broadcast_ierr(int64_t ncells, int code, int* istatus, double* rstatus, int* ierr, int mem, cudaStream_t st) {
+  if (mem == FATODE_MEM_HOST) {
+    for (int64_t c = 0; c < ncells; ++c) ierr[c] = code;
+    std::memset(istatus, 0, sizeof(int) * 20 * ncells);
+    std::memset(rstatus, 0, sizeof(double) * 20 * ncells);
+    return 0;
+  }
+  std::vector<int> h(ncells, code);
+  CUDA_TRY(cudaMemcpyAsync(ierr, h.data(), sizeof(int) * ncells, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(istatus, 0, sizeof(int) * 20 * ncells, st));
+  CUDA_TRY(cudaMemsetAsync(rstatus, 0, sizeof(double) * 20 * ncells, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+static int ros_batch_impl(int family, int model, int64_t ncells, int nvar, int np, int nadj, double* y, double* lambda,
+                          double* mu, double tin, double tout, const double* atol, const double* rtol, const int* icntrl_u,
+                          const double* rcntrl_u, int* istatus, double* rstatus, int* ierr, double* mu_sum,
+                          const double* model_params, int mem, void* stream) {
+  g_err.clear();
+  if (ncells < 0 || !y || !atol || !rtol || !istatus || !rstatus || !ierr) return fail(FATODE_EINVAL, "NULL required argument");
+  if (int e = check_model_dims(model, nvar, np)) return e;
+  if (family == FAM_ADJ && (!lambda || nadj < 1)) return fail(FATODE_EINVAL, "lambda is NULL or nadj < 1");
+  if (int e = check_device()) return e;
+  if (ncells == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  RosParams rp;
+  int ic[20];
+  const int perr = ros_parse_options(family, nvar, icntrl_u, rcntrl_u, tin, tout, atol, rtol, rp, ic);
+  bool do_adjoint = false;
+  if (family == FAM_ADJ) {
+    const int adjtype = ic[6] == 0 ? 2 : ic[6];
+    if (perr == 1 && (adjtype == 3 || adjtype == 4))
+      return fail(FATODE_EUNSUPPORTED, "continuous adjoints (ICNTRL(7)=3,4) are outside this engine's scope");
+    if (perr == 1 && ic[7] != 0) return fail(FATODE_EUNSUPPORTED, "ICNTRL(8) (SaveLU) is not implemented by the reference either");
+    do_adjoint = (adjtype == 2);
+    if (do_adjoint && nadj > 32) return fail(FATODE_EUNSUPPORTED, "nadj > 32 per call is not supported yet");
+  }
+  if (perr != 1) return broadcast_ierr(ncells, perr, istatus, rstatus, ierr, mem, st);
+  const bool with_mu = (family == FAM_ADJ) && np > 0 && mu != nullptr;
+  if (model != FATODE_MODEL_CBM4) return fail(FATODE_EUNSUPPORTED, "model not available in this build yet");
+  Cbm4Const mc;
+  cbm4_constants(model_params, mc);
+
+  // stage arrays
+  DevBuf b_atol, b_rtol, b_y, b_lam, b_mu, b_ist, b_rst, b_ierr, b_musum;
+  CUDA_TRY(b_atol.alloc(sizeof(double) * nvar));
+  CUDA_TRY(b_rtol.alloc(sizeof(double) * nvar));
+  CUDA_TRY(cudaMemcpyAsync(b_atol.p, atol, sizeof(double) * nvar, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(b_rtol.p, rtol, sizeof(double) * nvar, cudaMemcpyHostToDevice, st));
+  double *d_y = y, *d_lam = lambda, *d_mu = mu, *d_rst = rstatus, *d_musum = mu_sum;
+  int *d_ist = istatus, *d_ierr = ierr;
+  const size_t ny = sizeof(double) * nvar * ncells, nl = sizeof(double) * (size_t)nvar * nadj * ncells,
+               nm = sizeof(double) * (size_t)np * nadj * ncells;
+  if (mem == FATODE_MEM_HOST) {
+    CUDA_TRY(b_y.alloc(ny));
+    CUDA_TRY(b_ist.alloc(sizeof(int) * 20 * ncells));
+    CUDA_TRY(b_rst.alloc(sizeof(double) * 20 * ncells));
+    CUDA_TRY(b_ierr.alloc(sizeof(int) * ncells));
+    CUDA_TRY(cudaMemcpyAsync(b_y.p, y, ny, cudaMemcpyHostToDevice, st));
+    d_y = b_y.as<double>(); d_ist = b_ist.as<int>(); d_rst = b_rst.as<double>(); d_ierr = b_ierr.as<int>();
+    if (family == FAM_ADJ) {
+      CUDA_TRY(b_lam.alloc(nl));
+      d_lam = b_lam.as<double>();
+      if (with_mu) { CUDA_TRY(b_mu.alloc(nm)); d_mu = b_mu.as<double>(); }
+      if (with_mu && mu_sum) { CUDA_TRY(b_musum.alloc(sizeof(double) * np * nadj)); d_musum = b_musum.as<double>(); }
+    }
+  }
+  int rc = ros_adj_device<Cbm4Warp>(rp, mc, ncells, nadj, with_mu, do_adjoint, d_y, d_lam, d_mu, b_atol.as<double>(),
+                                    b_rtol.as<double>(), d_ist, d_rst, d_ierr, d_musum, st);
+  if (rc != 0) return rc;
+  if (mem == FATODE_MEM_HOST) {
+    CUDA_TRY(cudaMemcpyAsync(y, d_y, ny, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(istatus, d_ist, sizeof(int) * 20 * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(rstatus, d_rst, sizeof(double) * 20 * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ierr, d_ierr, sizeof(int) * ncells, cudaMemcpyDeviceToHost, st));
+    if (family == FAM_ADJ && do_adjoint) {
+      CUDA_TRY(cudaMemcpyAsync(lambda, d_lam, nl, cudaMemcpyDeviceToHost, st));
+      if (with_mu) CUDA_TRY(cudaMemcpyAsync(mu, d_mu, nm, cudaMemcpyDeviceToHost, st));
+      if (with_mu && mu_sum) CUDA_TRY(cudaMemcpyAsync(mu_sum, d_musum, sizeof(double) * np * nadj, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+extern "C" int fatode_ros_integrate_batch(int model, int64_t ncells, int nvar, double* y, double tin, double tout,
+                                          const double* atol, const double* rtol, const int* icntrl_u,
+                                          const double* rcntrl_u, int* istatus, double* rstatus, int* ierr,
+                                          const double* model_params, int mem, void* stream) {
+  return ros_batch_impl(FAM_FWD, model, ncells, nvar, 0, 0, y, nullptr, nullptr, tin, tout, atol, rtol, icntrl_u, rcntrl_u,
+                        istatus, rstatus, ierr, nullptr, model_params, mem, stream);
+}
+
+extern "C" int fatode_ros_integrate_adj_batch(int model, int64_t ncells, int nvar, int np, int nadj, double* y,
+                                              double* lambda, double* mu, double tin, double tout, const double* atol_adj,
+                                              const double* rtol_adj, const double* atol, const double* rtol,
+                                              const int* icntrl_u, const double* rcntrl_u, int* istatus, double* rstatus,
+                                              int* ierr, double* mu_sum, const double* model_params, int mem, void* stream) {
+  (void)atol_adj; (void)rtol_adj;
+  return ros_batch_impl(FAM_ADJ, model, ncells, nvar, np, nadj, y, lambda, mu, tin, tout, atol, rtol, icntrl_u, rcntrl_u,
+                        istatus, rstatus, ierr, mu_sum, model_params, mem, stream);
+}

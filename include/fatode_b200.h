@@ -1,0 +1,120 @@
+/* fatode_b200 — C ABI of the B200-native batched stiff-integration engine.
+ *
+ * Drop-in boundary for FATODE's data-parallel hot path.  Each entry point is the
+ * batched form of one Fortran90 interface of the reference; `ncells` independent systems are
+ * integrated in one call (ncells = 1 reproduces the reference call).  What a Fortran binding
+ * (fatode_b200/fortran/fatode_b200_mod.F90, ISO_C_BINDING) passes here is exactly what the
+ * reference's INTEGRATE* routines receive, except that the EXTERNAL callbacks FUN/JAC/HESSTR_VEC/
+ * JACP/HESSTR_VEC_F_PY/ADJINIT/HESS_VEC are replaced by a registered model id: the shipped example
+ * models are compiled as device functions.
+ *
+ * Array conventions (Fortran order, 0-based description):
+ *   y       [ncells][nvar]              VAR(1:N) of cell c at y + c*nvar                 (in/out)
+ *   lambda  [ncells][nadj][nvar]        Lambda(1:N,1:NADJ) of cell c, column-major        (out)
+ *   mu      [ncells][nadj][np]          Mu(1:NP,1:NADJ) of cell c, column-major           (out)
+ *   atol, rtol [nvar]                   shared by all cells (ATOL(1:N), RTOL(1:N))
+ *   icntrl_u[20], rcntrl_u[20]          ICNTRL_U / RCNTRL_U, may be NULL (all defaults)
+ *   istatus [ncells][20], rstatus [ncells][20], ierr [ncells]   per-cell ISTATUS_U / RSTATUS_U / IERR
+ * `mem` says where those arrays live: FATODE_MEM_HOST (the library stages them through the GPU,
+ * host<->device copies included) or FATODE_MEM_DEVICE (device pointers, results stay resident;
+ * icntrl_u/rcntrl_u/atol/rtol are always host pointers).
+ *
+ * Return value: 0 on success of the call itself (per-cell outcomes are in ierr[]: 1 = success,
+ * negative = the reference's error codes), or a negative FATODE_E* code; fatode_last_error()
+ * returns a message.  There is no CPU fallback: without a usable CUDA device every compute entry
+ * point fails with FATODE_ENODEVICE.
+ */
+#ifndef FATODE_B200_H
+#define FATODE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* model registry (replaces the FUN/JAC/... callback arguments) */
+enum {
+  FATODE_MODEL_ROBERTS = 1,      /* EXAMPLES/roberts/ROBERTS_ROS_ADJ/roberts_ros_adj_dr.F90 : N=3,  NP=3  */
+  FATODE_MODEL_SMALL_STRATO = 2, /* EXAMPLES/small_strato/small_ros{,_adj}/User_Parameters.F90 : N=5, NP=0 */
+  FATODE_MODEL_CBM4 = 3          /* EXAMPLES/cbm4/CBM4_ROS_ADJ/cbm4_Parameters.F90          : N=32, NP=29 */
+};
+
+enum { FATODE_MEM_HOST = 0, FATODE_MEM_DEVICE = 1 };
+
+enum {
+  FATODE_OK = 0,
+  FATODE_EINVAL = -101,    /* bad argument (unknown model, dimension mismatch, NULL required pointer) */
+  FATODE_ENODEVICE = -102, /* no CUDA device / driver */
+  FATODE_ECUDA = -103,     /* CUDA runtime error (message in fatode_last_error) */
+  FATODE_ENOMEM = -104,    /* trajectory tape does not fit in device memory even for one cell */
+  FATODE_EUNSUPPORTED = -105 /* option of the reference outside this engine's scope */
+};
+
+const char* fatode_last_error(void);
+const char* fatode_version(void);
+
+/* dimensions of a registered model: nvar, np (number of parameters for Mu) */
+int fatode_model_dims(int model, int* nvar, int* np);
+/* initial state of the reference's example driver for this model (host array [nvar]) */
+int fatode_model_initial_state(int model, double* y);
+
+/* Optional per-call model constants; NULL = the example driver's values.
+ *  CBM4: params[0] = TEMP (298), params[1] = FIX(1) (1.25e8*2.55e10), params[2] = emission (2e3)
+ *        (cbm4_ros_adj_dr.F90:96-97,202,268).  Other models take none. */
+
+/* INTEGRATE of FWD/ROS (FWD/ROS/ROS_f90_Integrator.F90:32):
+ *   INTEGRATE(TIN,TOUT,N,NNZERO,VAR,RTOL,ATOL,FUN,JAC,ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U,IERR_U)
+ * ICNTRL_U/RCNTRL_U entries override the defaults only when > 0 (:67-72). */
+int fatode_ros_integrate_batch(int model, int64_t ncells, int nvar, double* y, double tin, double tout,
+                               const double* atol, const double* rtol, const int* icntrl_u,
+                               const double* rcntrl_u, int* istatus, double* rstatus, int* ierr,
+                               const double* model_params, int mem, void* stream);
+
+/* INTEGRATE_ADJ of ADJ/ROS_ADJ (ADJ/ROS_ADJ/ROS_ADJ_f90_Integrator.F90:34):
+ *   INTEGRATE_ADJ(NVAR,NP,NADJ,NNZERO,Y,Lambda,Mu,TIN,TOUT,ATOL_adj,RTOL_adj,ATOL,RTOL,FUN,JAC,ADJINIT,
+ *                 HESSTR_VEC,JACP,DRDY,DRDP,HESSTR_VEC_F_PY,HESSTR_VEC_R_PY,HESSTR_VEC_R,
+ *                 ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U,Q,QFUN)
+ * Discrete adjoint (ICNTRL(7) = 0 or 2) or forward only (1).  ICNTRL_U/RCNTRL_U override when >= 0
+ * (:91-96).  mu == NULL or np == 0 selects the Lambda-only mode (RosenbrockADJ2).  ADJINIT is the
+ * model's registered routine.  ATOL_adj/RTOL_adj are accepted for signature parity and unused (the
+ * reference uses them only for the continuous adjoint).  Quadrature arguments (Q, QFUN, DRDY, DRDP,
+ * HESSTR_VEC_R*) and the continuous adjoints (ICNTRL(7) = 3,4) are outside the engine's scope
+ * (FATODE_EUNSUPPORTED).
+ * mu_sum (may be NULL): [nadj][np] sum over all cells of this call with ierr == 1, reduced in a
+ * fixed order on the device (host pointer unless mem == FATODE_MEM_DEVICE); a multi-GPU caller
+ * all-reduces it across ranks. */
+int fatode_ros_integrate_adj_batch(int model, int64_t ncells, int nvar, int np, int nadj, double* y,
+                                   double* lambda, double* mu, double tin, double tout,
+                                   const double* atol_adj, const double* rtol_adj, const double* atol,
+                                   const double* rtol, const int* icntrl_u, const double* rcntrl_u,
+                                   int* istatus, double* rstatus, int* ierr, double* mu_sum,
+                                   const double* model_params, int mem, void* stream);
+
+/* Engine knobs (process-wide): trajectory-tape budget in bytes (0 = 60% of free device memory) and
+ * the number of cells per wave (0 = automatic). */
+int fatode_set_tape_budget(uint64_t bytes);
+int fatode_set_wave_cells(int64_t cells);
+
+/* Per-call telemetry of the last batch call on this thread (kernel launches, waves, device time in
+ * ms of each phase measured with CUDA events on the launch stream, tape bytes). */
+typedef struct {
+  int64_t launches;
+  int64_t waves;
+  double ms_forward, ms_forward_tape, ms_adjoint, ms_other;
+  uint64_t tape_bytes_peak;
+  int64_t accepted_steps, attempts;
+} fatode_stats;
+int fatode_get_last_stats(fatode_stats* out);
+
+/* pinned host memory helpers for callers that want asynchronous staging */
+void* fatode_alloc_pinned(uint64_t bytes);
+void fatode_free_pinned(void* p);
+
+/* FP64 DFMA micro-benchmark on the current device: returns achieved TFLOP/s (<0 on error). */
+double fatode_measure_fp64_peak(int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FATODE_B200_H */

@@ -1,0 +1,43 @@
+#!/usr/bin/env python3
+"""Collects the reference's own golden outputs for the hot path into small fixtures
+(tests/golden/*.json).  The reference tree is not available on the GPU box, so the numbers are
+copied here verbatim (they are run outputs committed upstream, not source code):
+  EXAMPLES/cbm4/CBM4_ROS_ADJ/cbm4_ros_sol.txt          Y(Tend), 32 x E24.16
+  EXAMPLES/cbm4/CBM4_ROS_ADJ/cbm4_output_sens.txt      Lambda(32,32) then Mu(29,32)
+  EXAMPLES/small_strato/small_ros_adj/rkadj_ADJ_results.m   Lambda(5,5) (RosenbrockADJ2, Rodas3)
+  EXAMPLES/small_strato/small_ros/small_strato_dr.F90:23-24  ANS(5) (REAL(4) literals)
+Usage: python tests/golden/make_golden.py [/root/reference]
+"""
+import json
+import os
+import re
+import sys
+
+import numpy as np
+
+REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    d = os.path.join(REF, "EXAMPLES/cbm4/CBM4_ROS_ADJ")
+    y = [float(l) for l in open(os.path.join(d, "cbm4_ros_sol.txt"))]
+    vals = [float(l) for l in open(os.path.join(d, "cbm4_output_sens.txt")) if not l.startswith(("L", "M"))]
+    assert len(y) == 32 and len(vals) == 32 * 32 + 32 * 29
+    json.dump({"source": "EXAMPLES/cbm4/CBM4_ROS_ADJ/{cbm4_ros_sol.txt,cbm4_output_sens.txt}",
+               "y": y, "lambda": vals[:1024], "mu": vals[1024:]},
+              open(os.path.join(HERE, "cbm4_ros_adj.json"), "w"))
+    m = os.path.join(REF, "EXAMPLES/small_strato/small_ros_adj/rkadj_ADJ_results.m")
+    lam = [float(x) for x in open(m).read().split()]
+    assert len(lam) == 25
+    drv = open(os.path.join(REF, "EXAMPLES/small_strato/small_ros/small_strato_dr.F90")).read()
+    mm = re.search(r"ANS\s*=\s*\(/(.*?)/\)", drv, re.S)
+    ans = [float(np.float32(x)) for x in re.sub(r"&", "", mm.group(1)).replace("\n", "").split(",")]
+    assert len(ans) == 5
+    json.dump({"source": "EXAMPLES/small_strato/small_ros_adj/rkadj_ADJ_results.m; small_ros/small_strato_dr.F90:23-24",
+               "lambda": lam, "ans": ans}, open(os.path.join(HERE, "small_strato.json"), "w"))
+    print("wrote fixtures")
+
+
+if __name__ == "__main__":
+    main()

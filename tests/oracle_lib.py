@@ -1,0 +1,87 @@
+"""ctypes view of the CPU oracle (oracle/liboracle.so) — checker only, used by tests."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int)
+MODEL = {"roberts": 1, "small_strato": 2, "cbm4": 3}
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        so = os.path.join(ORACLE_DIR, "liboracle.so")
+        subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
+        L = ctypes.CDLL(so)
+        L.oracle_ros_fwd_batch.argtypes = [ctypes.c_int, ctypes.c_long, _dp, ctypes.c_double, ctypes.c_double, _dp, _dp,
+                                           _ip, _dp, _ip, _dp, _ip, ctypes.c_int]
+        L.oracle_ros_adj_batch.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_int, _dp, _dp, _dp,
+                                           ctypes.c_double, ctypes.c_double, _dp, _dp, _ip, _dp, _ip, _dp, _ip,
+                                           ctypes.c_int]
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+def dims(model):
+    n, p = ctypes.c_int(), ctypes.c_int()
+    lib().oracle_model_dims(MODEL[model], ctypes.byref(n), ctypes.byref(p))
+    return n.value, p.value
+
+
+def initial_state(model):
+    n, _ = dims(model)
+    y = np.zeros(n)
+    lib().oracle_initial_state(MODEL[model], _d(y))
+    return y
+
+
+def _ctrl(icntrl, rcntrl):
+    ic = np.zeros(20, dtype=np.int32) if icntrl is None else np.ascontiguousarray(icntrl, dtype=np.int32)
+    rc = np.zeros(20) if rcntrl is None else np.ascontiguousarray(rcntrl, dtype=np.float64)
+    return ic, rc
+
+
+def ros_fwd(model, y, tin, tout, atol, rtol, icntrl=None, rcntrl=None, nthreads=0):
+    y = np.atleast_2d(np.array(y, dtype=np.float64, order="C"))
+    nc = y.shape[0]
+    ic, rc = _ctrl(icntrl, rcntrl)
+    atol = np.ascontiguousarray(atol, dtype=np.float64)
+    rtol = np.ascontiguousarray(rtol, dtype=np.float64)
+    ist = np.zeros((nc, 20), dtype=np.int32)
+    rst = np.zeros((nc, 20))
+    ierr = np.zeros(nc, dtype=np.int32)
+    lib().oracle_ros_fwd_batch(MODEL[model], nc, _d(y), tin, tout, _d(atol), _d(rtol), _i(ic), _d(rc), _i(ist), _d(rst),
+                               _i(ierr), nthreads)
+    return dict(y=y, istatus=ist, rstatus=rst, ierr=ierr)
+
+
+def ros_adj(model, y, nadj, tin, tout, atol, rtol, icntrl=None, rcntrl=None, with_mu=True, nthreads=0):
+    y = np.atleast_2d(np.array(y, dtype=np.float64, order="C"))
+    nc, n = y.shape
+    _, npar = dims(model)
+    ic, rc = _ctrl(icntrl, rcntrl)
+    atol = np.ascontiguousarray(atol, dtype=np.float64)
+    rtol = np.ascontiguousarray(rtol, dtype=np.float64)
+    ist = np.zeros((nc, 20), dtype=np.int32)
+    rst = np.zeros((nc, 20))
+    ierr = np.zeros(nc, dtype=np.int32)
+    lam = np.zeros((nc, nadj, n))
+    use_mu = with_mu and npar > 0
+    mu = np.zeros((nc, nadj, max(npar, 1)))
+    lib().oracle_ros_adj_batch(MODEL[model], nc, npar if use_mu else 0, nadj, _d(y), _d(lam), _d(mu) if use_mu else None,
+                               tin, tout, _d(atol), _d(rtol), _i(ic), _d(rc), _i(ist), _d(rst), _i(ierr), nthreads)
+    return dict(y=y, istatus=ist, rstatus=rst, ierr=ierr, lambda_=lam, mu=mu[:, :, :npar] if use_mu else None)

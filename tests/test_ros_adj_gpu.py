@@ -1,0 +1,174 @@
+"""GPU parity tests for the headline path: batched CBM-IV ROS_ADJ through the C ABI against the CPU
+oracle on the same inputs.  Bar (BASELINE.json north_star): ISTATUS bit-exact per cell, states and
+sensitivities within 1e-9 relative (normwise per vector)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+F01 = float(np.float32(0.1))
+T0 = 12.0 * 3600.0
+T1 = T0 + 72.0 * 3600.0
+RTOL_PARITY = 1e-9
+
+
+def driver_tols():
+    return np.full(32, F01 * 1.0e-4), np.full(32, F01 * 1.0e-6)
+
+
+def rodas4():
+    ic = np.zeros(20, dtype=np.int32)
+    ic[2] = 5
+    return ic
+
+
+def normwise(a, b, axis=-1, floor=1e-300):
+    return np.max(np.abs(a - b), axis=axis) / np.maximum(np.max(np.abs(b), axis=axis), floor)
+
+
+def check_against_oracle(res, ref, nadj):
+    assert np.array_equal(res.ierr, ref["ierr"])
+    assert np.array_equal(res.istatus, ref["istatus"]), "ISTATUS must be bit-exact"
+    assert np.all(normwise(res.rstatus[:, :3], ref["rstatus"][:, :3]) <= 1e-12)
+    assert np.all(normwise(res.y, ref["y"]) <= RTOL_PARITY)
+    # Lambda / Mu: per cell, per adjoint column, relative to the column's own scale.  Columns whose
+    # reference scale is below 1e-30 are round-off level (species that stay ~0) and are compared
+    # absolutely against the largest column scale of the cell instead.
+    for name, a, b in (("lambda", res.lambda_, ref["lambda_"]), ("mu", res.mu, ref["mu"])):
+        if b is None:
+            continue
+        scale = np.max(np.abs(b), axis=2)                      # [cell, column]
+        err = np.max(np.abs(a - b), axis=2)
+        big = scale > 1e-30
+        assert np.all(err[big] <= RTOL_PARITY * scale[big]), (name, np.max(err[big] / scale[big]))
+
+
+def test_driver_cell_matches_oracle_and_reference_golden():
+    import fatode_b200 as F
+    rtol, atol = driver_tols()
+    y0 = F.initial_state("cbm4")
+    res = F.integrate_adj("cbm4", T0, T1, y0, 32, rtol, atol, icntrl_u=rodas4())
+    ref = O.ros_adj("cbm4", y0, 32, T0, T1, atol, rtol, rodas4(), nthreads=1)
+    check_against_oracle(res, ref, 32)
+    g = json.load(open(os.path.join(G, "cbm4_ros_adj.json")))
+    gy = np.array(g["y"])
+    assert np.max(np.abs(res.y[0] - gy)) <= 1e-10 * np.max(np.abs(gy))
+    glam = np.array(g["lambda"]).reshape(32, 32)
+    cs = np.max(np.abs(glam), axis=1)
+    ok = cs > 1e-30
+    assert np.all((np.max(np.abs(res.lambda_[0] - glam), axis=1) / np.maximum(cs, 1e-300))[ok] <= 1e-8)
+
+
+def test_batch_of_perturbed_cells_matches_oracle():
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    rtol, atol = driver_tols()
+    y0 = perturbed_states(F.initial_state("cbm4"), 96)
+    res = F.integrate_adj("cbm4", T0, T1, y0, 32, rtol, atol, icntrl_u=rodas4(), want_mu_sum=True)
+    ref = O.ros_adj("cbm4", y0, 32, T0, T1, atol, rtol, rodas4())
+    check_against_oracle(res, ref, 32)
+    # deterministic Mu sum = sum over cells (fixed order), compared to a float64 sum of the per-cell results
+    s = res.mu.sum(axis=0)
+    assert np.all(np.abs(res.mu_sum - s) <= 1e-12 * np.abs(res.mu).sum(axis=0) + 1e-300)
+    st = F.last_stats()
+    assert st.launches >= 4 and st.accepted_steps == int(res.istatus[:, 3].sum())
+
+
+def test_parity_tolerance_rtol_1e6():
+    """north_star's stated tolerance setting: RTOL = 1e-6 (ATOL = 1e-8)."""
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    rtol, atol = np.full(32, 1e-6), np.full(32, 1e-8)
+    y0 = perturbed_states(F.initial_state("cbm4"), 24)
+    res = F.integrate_adj("cbm4", T0, T1, y0, 32, rtol, atol, icntrl_u=rodas4())
+    ref = O.ros_adj("cbm4", y0, 32, T0, T1, atol, rtol, rodas4())
+    check_against_oracle(res, ref, 32)
+
+
+def test_lambda_only_mode_and_fewer_columns():
+    """mu = NULL -> RosenbrockADJ2; NADJ < NVAR."""
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    rtol, atol = driver_tols()
+    y0 = perturbed_states(F.initial_state("cbm4"), 8)
+    res = F.integrate_adj("cbm4", T0, T1, y0, 5, rtol, atol, icntrl_u=rodas4(), want_mu=False)
+    ref = O.ros_adj("cbm4", y0, 5, T0, T1, atol, rtol, rodas4(), with_mu=False)
+    check_against_oracle(res, ref, 5)
+    assert res.mu is None
+
+
+def test_other_rosenbrock_methods_and_autonomous_flag():
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    rtol, atol = driver_tols()
+    y0 = perturbed_states(F.initial_state("cbm4"), 4)
+    t1 = T0 + 6 * 3600.0
+    for method in (0, 1, 2, 3, 4):
+        for auto in (0, 1):
+            ic = np.zeros(20, dtype=np.int32)
+            ic[2] = method
+            ic[0] = auto
+            res = F.integrate_adj("cbm4", T0, t1, y0, 32, rtol, atol, icntrl_u=ic)
+            ref = O.ros_adj("cbm4", y0, 32, T0, t1, atol, rtol, ic)
+            check_against_oracle(res, ref, 32)
+
+
+def test_forward_only_family_fwd_ros():
+    """FWD/ROS INTEGRATE: REAL(4) tableau/defaults, no Ndec/Nsol counting."""
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    rtol, atol = driver_tols()
+    y0 = perturbed_states(F.initial_state("cbm4"), 64)
+    for method in (0, 4, 5):
+        ic = np.zeros(20, dtype=np.int32)
+        ic[2] = method
+        res = F.integrate("cbm4", T0, T1, y0, rtol, atol, icntrl_u=ic)
+        ref = O.ros_fwd("cbm4", y0, T0, T1, atol, rtol, ic)
+        assert np.array_equal(res.ierr, ref["ierr"])
+        assert np.array_equal(res.istatus, ref["istatus"])
+        assert np.all(res.istatus[:, 5] == 0) and np.all(res.istatus[:, 6] == 0)
+        assert np.all(normwise(res.y, ref["y"]) <= RTOL_PARITY)
+
+
+def test_error_codes_follow_the_reference():
+    import fatode_b200 as F
+    rtol, atol = driver_tols()
+    y0 = F.initial_state("cbm4")
+    ic = np.zeros(20, dtype=np.int32)
+    ic[2] = 7                                     # unknown method -> IERR -2
+    res = F.integrate_adj("cbm4", T0, T1, y0, 32, rtol, atol, icntrl_u=ic)
+    assert res.ierr[0] == -2 and np.array_equal(res.y[0], y0)
+    ic = rodas4()
+    ic[3] = 10                                    # Max_no_steps = 10 -> IERR -6 after 11 attempts
+    res = F.integrate_adj("cbm4", T0, T1, y0, 32, rtol, atol, icntrl_u=ic)
+    ref = O.ros_adj("cbm4", y0, 32, T0, T1, atol, rtol, ic)
+    assert res.ierr[0] == -6 == ref["ierr"][0]
+    assert np.array_equal(res.istatus, ref["istatus"])
+    bad = atol.copy()
+    bad[3] = 0.0                                  # AbsTol <= 0 -> IERR -5
+    res = F.integrate_adj("cbm4", T0, T1, y0, 32, rtol, bad, icntrl_u=rodas4())
+    assert res.ierr[0] == -5
+
+
+def test_wave_splitting_is_invisible():
+    """A tiny tape budget forces many waves and prefix splitting; results must not change."""
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    rtol, atol = driver_tols()
+    y0 = perturbed_states(F.initial_state("cbm4"), 40)
+    a = F.integrate_adj("cbm4", T0, T1, y0, 32, rtol, atol, icntrl_u=rodas4())
+    F.lib().fatode_set_tape_budget(int(12 * 900 * 3104))      # ~12 cells' worth of tape
+    F.lib().fatode_set_wave_cells(16)
+    try:
+        b = F.integrate_adj("cbm4", T0, T1, y0, 32, rtol, atol, icntrl_u=rodas4())
+        assert F.last_stats().waves >= 3
+    finally:
+        F.lib().fatode_set_tape_budget(0)
+        F.lib().fatode_set_wave_cells(0)
+    for x, y in ((a.y, b.y), (a.lambda_, b.lambda_), (a.mu, b.mu), (a.istatus, b.istatus)):
+        assert np.array_equal(x, y)
