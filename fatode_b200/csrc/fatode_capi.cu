@@ -98,10 +98,10 @@ constexpr int FWD_WARPS = 4;
 constexpr int ADJ_WARPS = 3;
 
 template <class Model>
-__host__ __device__ constexpr int fwd_ws_doubles() { return Model::WS_DOUBLES + ((Model::NJ + 1) / 2) * 2 + 1024; }
+__host__ __device__ constexpr int fwd_ws_doubles() { return FwdSmem<Model>::DOUBLES; }
 
 template <class Model, bool TAPE>
-__global__ void __launch_bounds__(FWD_WARPS * 32)
+__global__ void __launch_bounds__(FWD_WARPS * 32, 3)
 k_ros_fwd(RosParams rp, typename Model::Const mc, long ncells, const double* __restrict__ y_in, double* __restrict__ y_out,
           const double* __restrict__ atol, const double* __restrict__ rtol, int* __restrict__ istatus,
           double* __restrict__ rstatus, int* __restrict__ ierr, int* __restrict__ nacc,
@@ -112,7 +112,6 @@ k_ros_fwd(RosParams rp, typename Model::Const mc, long ncells, const double* __r
   if (cell >= ncells) return;
   if (TAPE && ierr[cell] != 1) return;
   double* ws = smem + (size_t)warp * fwd_ws_doubles<Model>();
-  double* tile = ws + Model::WS_DOUBLES + ((Model::NJ + 1) / 2) * 2;
   double y = y_in[cell * 32 + lane];
   const int ti = rp.vector_tol ? lane : 0;
   FwdResult res;
@@ -122,17 +121,22 @@ k_ros_fwd(RosParams rp, typename Model::Const mc, long ncells, const double* __r
     tb = tape + tape_off[cell] * tape_entry_doubles(rp.S, 32);
     cap = (long)(tape_off[cell + 1] - tape_off[cell]);
   }
-  ros_forward_warp<Model, TAPE>(rp, mc, ws, tile, y, atol[ti], rtol[ti], tb, cap, res, lane);
+  ros_forward_warp<Model, TAPE>(rp, mc, ws, y, atol[ti], rtol[ti], tb, cap, res, lane);
   if (!TAPE) {
     y_out[cell * 32 + lane] = y;
-    if (lane < 8) istatus[cell * 20 + lane] = res.istatus[lane];
-    else if (lane < 20) istatus[cell * 20 + lane] = 0;
+    if (lane < 20) {
+      int v = 0;
+      if (lane == Nfun) v = res.nfun; else if (lane == Njac) v = res.njac; else if (lane == Nstp) v = res.nstp;
+      else if (lane == Nacc) v = res.nacc; else if (lane == Nrej) v = res.nrej; else if (lane == Ndec) v = res.ndec;
+      else if (lane == Nsol) v = res.nsol; else if (lane == Nsng) v = res.nsng;
+      istatus[cell * 20 + lane] = v;
+    }
     if (lane < 20) {
       double r = 0.0;
       if (lane == Ntexit) r = res.texit; else if (lane == Nhexit) r = res.hexit; else if (lane == Nhnew) r = res.hnew;
       rstatus[cell * 20 + lane] = r;
     }
-    if (lane == 0) { ierr[cell] = res.ierr; nacc[cell] = res.istatus[Nacc]; }
+    if (lane == 0) { ierr[cell] = res.ierr; nacc[cell] = res.nacc; }
   }
 }
 
@@ -520,4 +524,73 @@ extern "C" int fatode_ros_integrate_adj_batch(int model, int64_t ncells, int nva
   (void)atol_adj; (void)rtol_adj;
   return ros_batch_impl(FAM_ADJ, model, ncells, nvar, np, nadj, y, lambda, mu, tin, tout, atol, rtol, icntrl_u, rcntrl_u,
                         istatus, rstatus, ierr, mu_sum, model_params, mem, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Unit-level probes (used by tests/): evaluate the device model / warp LU on explicit inputs.
+template <class Model>
+__global__ void k_probe_model(typename Model::Const mc, double t, const double* y, double* f, double* jac_dense,
+                              double* hess) {
+  extern __shared__ __align__(16) double smem[];
+  typedef FwdSmem<Model> L;
+  const int lane = threadIdx.x;
+  double* ws = smem + L::OFF_MODEL;
+  double* jv = smem + L::OFF_JV;
+  double* tile = smem + L::OFF_A;
+  Model::init(ws, mc, lane);
+  Model::set_time(ws, t, lane);
+  Model::set_y(ws, y[lane], lane);
+  f[lane] = Model::fun(ws, mc, lane);
+  Model::jac(ws, jv, lane);
+  Model::template scatter_E<LDA>(jv, 0.0, tile, lane);     // tile = -J (column-major)
+  for (int j = 0; j < 32; ++j) jac_dense[j * 32 + lane] = -tile[j * LDA + lane];
+  Model::hess(ws, ws + Model::OFF_OUT, lane);
+  for (int h = lane; h < Model::NHESS; h += 32) hess[h] = ws[Model::OFF_OUT + h];
+}
+
+__global__ void k_probe_lu(const double* A /*col-major 32x32*/, const double* b, double* lu_out /*row-major logical*/,
+                           int* ipiv_who, double* x, int* info) {
+  __shared__ double tile[32 * LDA];
+  __shared__ int who[32];
+  const int lane = threadIdx.x;
+  for (int j = 0; j < 32; ++j) tile[j * LDA + lane] = A[j * 32 + lane];
+  __syncwarp();
+  int pos;
+  int inf = warp_lu_factor(tile, who, pos, lane);
+  for (int j = 0; j < 32; ++j) lu_out[pos * 32 + j] = tile[j * LDA + lane];
+  ipiv_who[lane] = who[lane];
+  if (lane == 0) *info = inf;
+  x[lane] = warp_lu_solve(tile, who, pos, b[lane], lane);
+}
+
+extern "C" int fatode_probe_cbm4(double t, const double* y, double* f, double* jac_dense, double* hess) {
+  if (int e = check_device()) return e;
+  Cbm4Const mc;
+  cbm4_constants(nullptr, mc);
+  DevBuf by, bf, bj, bh;
+  CUDA_TRY(by.alloc(256)); CUDA_TRY(bf.alloc(256)); CUDA_TRY(bj.alloc(8192)); CUDA_TRY(bh.alloc(8 * 264));
+  CUDA_TRY(cudaMemcpy(by.p, y, 256, cudaMemcpyHostToDevice));
+  const size_t sm = sizeof(double) * fwd_ws_doubles<Cbm4Warp>();
+  k_probe_model<Cbm4Warp><<<1, 32, sm>>>(mc, t, by.as<double>(), bf.as<double>(), bj.as<double>(), bh.as<double>());
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(f, bf.p, 256, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(jac_dense, bj.p, 8192, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(hess, bh.p, 8 * 258, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int fatode_probe_lu32(const double* A, const double* b, double* lu_out, int* who, double* x, int* info) {
+  if (int e = check_device()) return e;
+  DevBuf bA, bb, bl, bw, bx, bi;
+  CUDA_TRY(bA.alloc(8192)); CUDA_TRY(bb.alloc(256)); CUDA_TRY(bl.alloc(8192)); CUDA_TRY(bw.alloc(128)); CUDA_TRY(bx.alloc(256));
+  CUDA_TRY(bi.alloc(4));
+  CUDA_TRY(cudaMemcpy(bA.p, A, 8192, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(bb.p, b, 256, cudaMemcpyHostToDevice));
+  k_probe_lu<<<1, 32>>>(bA.as<double>(), bb.as<double>(), bl.as<double>(), bw.as<int>(), bx.as<double>(), bi.as<int>());
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(lu_out, bl.p, 8192, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(who, bw.p, 128, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(x, bx.p, 256, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(info, bi.p, 4, cudaMemcpyDeviceToHost));
+  return 0;
 }

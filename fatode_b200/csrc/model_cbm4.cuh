@@ -7,10 +7,12 @@
 //                                                               (cbm4_Parameters.F90:196-2392)
 // The mechanism itself comes from gen/cbm4_dev_gen.h (two-level sum-of-products tables, see
 // tools/gen_cbm4_device.py).  FUN and JAC keep the Fortran's operation order with unfused
-// multiplies/adds, so the forward sweep differs from the reference arithmetic only through cos().
+// multiplies/adds; COS comes from portable_math.h (fixed-order, < 1 ulp), so the forward sweep is
+// reproducible bit for bit on the host.
 #pragma once
 #include "fatode_common.cuh"
 #include "gen/cbm4_dev_gen.h"
+#include "portable_math.h"
 
 namespace fatode {
 
@@ -41,7 +43,7 @@ struct Cbm4Warp {
     if (Tlocal >= SunRise && Tlocal <= SunSet) {
       double Ttmp = __ddiv_rn(__dsub_rn(__dsub_rn(__dmul_rn(2.0, Tlocal), SunRise), SunSet), __dsub_rn(SunSet, SunRise));
       if (Ttmp > 0) Ttmp = __dmul_rn(Ttmp, Ttmp); else Ttmp = __dmul_rn(-Ttmp, Ttmp);
-      return __ddiv_rn(__dadd_rn(1.0, cos(__dmul_rn(PI, Ttmp))), 2.0);
+      return __ddiv_rn(__dadd_rn(1.0, fpm::cos_small(__dmul_rn(PI, Ttmp))), 2.0);
     }
     return 0.0;
   }
@@ -84,7 +86,7 @@ struct Cbm4Warp {
   template <int NITER>
   __device__ static void eval_l2(const cbm4_dev::L2* __restrict__ tab, const double* P, double* out, int lane) {
     double acc = 0.0;
-#pragma unroll 4
+#pragma unroll 10
     for (int it = 0; it < NITER; ++it) {
       cbm4_dev::L2 e = tab[it * 32 + lane];
       double term = __dmul_rn(e.sc, P[e.src]);
@@ -107,16 +109,17 @@ struct Cbm4Warp {
     eval_l1<cbm4_dev::JAC_L1_NPAD>(cbm4_dev::JAC_L1_TAB, ws, ws + OFF_P, lane);
     eval_l2<cbm4_dev::JAC_L2_NITER>(cbm4_dev::JAC_L2_TAB, ws + OFF_P, jv, lane);
   }
-  // dense scatter of E = ghinv*I - J into a column-major 32x32 tile (for the LU)
+  // dense scatter of E = ghinv*I - J into a column-major 32x32 tile with leading dimension LD (for the LU)
+  template <int LD>
   __device__ static void scatter_E(const double* jv, double ghinv, double* tile, int lane) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) tile[j * 32 + lane] = (j == lane) ? ghinv : 0.0;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) tile[j * LD + lane] = (j == lane) ? ghinv : 0.0;
     __syncwarp();
     for (int e = lane; e < NJ; e += 32) {
       int r = cbm4_dev::JAC_ROW[e], c = cbm4_dev::JAC_COL[e];
       double v = -jv[e];
       // e(j,j) = -fjac(j,j) + hgamma   (LS_Solver.F90:36-40)
-      tile[c * 32 + r] = (r == c) ? __dadd_rn(v, ghinv) : v;
+      tile[c * LD + r] = (r == c) ? __dadd_rn(v, ghinv) : v;
     }
     __syncwarp();
   }
@@ -134,7 +137,7 @@ struct Cbm4Warp {
     }
     __syncwarp();
     double acc = 0.0;
-#pragma unroll 4
+#pragma unroll
     for (int it = 0; it < cbm4_dev::MAT_L2_NITER; ++it) {
       cbm4_dev::L2 e = cbm4_dev::MAT_L2_TAB[it * 32 + lane];
       double term = hs[e.src] * kb[(int)e.sc];

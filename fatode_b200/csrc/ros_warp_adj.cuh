@@ -124,24 +124,19 @@ __device__ void ros_adjoint_warp(const RosParams& rp, const typename Model::Cons
     Model::jac(ws, JV, lane);
     {
       const double ghinv = __ddiv_rn(1.0, __dmul_rn(__dmul_rn(dDir, H), rp.Gamma[0]));
-      double* tile = W;   // free at this point
-      Model::scatter_E(JV, ghinv, tile, lane);
-      WarpLU lu;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) lu.a[j] = tile[j * 32 + lane];
-      __syncwarp();
-      warp_lu_factor(lu, lane);
-      double* row = LUs + lu.pos * 34;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) row[j] = lu.a[j];
-      WHO[lane] = lu.who;
+      double* tile = W;   // [32][LDA]: W is free between steps
+      Model::template scatter_E<LDA>(JV, ghinv, tile, lane);
+      int pos;
+      warp_lu_factor(tile, WHO, pos, lane);       // same code as the forward sweep -> identical factors
+      // repack for the private phase: logical rows, row-major, ld 34 (lane = column j)
+      for (int r = 0; r < 32; ++r) LUs[r * 34 + lane] = tile[lane * LDA + WHO[r]];
       __syncwarp();
       DINV[lane] = 1.0 / LUs[lane * 34 + lane];
     }
     Model::hess(ws, HS, lane);                   // Hessian(T): rate coefficients only
     if (!rp.autonomous) {                        // dJ/dt (:1379-1382) on the time-dependent entries
       const double Delta = sqrt(rp.roundoff) * fmax(DeltaMin, fabs(T));
-      double* Jd = W + 1024 * ((S > 2) ? 1 : 0);   // scratch
+      double* Jd = W + 2048;                       // scratch (S >= 4) / beyond the tile
       Model::set_time(ws, T + Delta, lane);
       Model::jac(ws, Jd, lane);
       if (lane < Model::NJT) {

@@ -114,6 +114,13 @@ void fatode_free_pinned(void* p);
 /* FP64 DFMA micro-benchmark on the current device: returns achieved TFLOP/s (<0 on error). */
 double fatode_measure_fp64_peak(int iters);
 
+/* Unit-level probes used by the parity tests (one warp, one system).
+ *  fatode_probe_cbm4: f[32] = fun(t,y); jac_dense[32*32] column-major = jac(t,y); hess[258] = Hessian(t)
+ *  fatode_probe_lu32: DGETF2 + DGETRS('N') of a column-major 32x32 matrix on the warp LU;
+ *                     lu_out row-major in pivoted row order, who[k] = original row at position k */
+int fatode_probe_cbm4(double t, const double* y, double* f, double* jac_dense, double* hess);
+int fatode_probe_lu32(const double* A, const double* b, double* lu_out, int* who, double* x, int* info);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,9 +8,16 @@
 #pragma once
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include "gen/cbm4_gen.h"
+#include "portable_math.hpp"
 
 namespace oracle {
+
+// 0: deterministic kernels of portable_math.hpp (default), 1: libm cos/pow (see portable_math.hpp)
+inline int& libm_mode() { static int m = (getenv("ORACLE_LIBM") && atoi(getenv("ORACLE_LIBM")) != 0) ? 1 : 0; return m; }
+static inline double o_cos(double x) { return libm_mode() ? std::cos(x) : oracle_pm::cos_small(x); }
+static inline double o_root(double x, double elo) { return libm_mode() ? std::pow(x, 1.0 / elo) : oracle_pm::root_elo(x, elo); }
 
 #define F4(x) ((double)(x##f))
 
@@ -25,7 +32,7 @@ static inline double update_sun(double T) {
   if (Tlocal >= SunRise && Tlocal <= SunSet) {
     double Ttmp = (2.0 * Tlocal - SunRise - SunSet) / (SunSet - SunRise);
     if (Ttmp > 0) Ttmp = Ttmp * Ttmp; else Ttmp = -Ttmp * Ttmp;
-    return (1.0 + std::cos(PI * Ttmp)) / 2.0;
+    return (1.0 + o_cos(PI * Ttmp)) / 2.0;
   }
   return 0.0;
 }

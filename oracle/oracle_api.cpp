@@ -40,6 +40,7 @@ static void fwd_batch(long ncells, double* y, double tin, double tout, const dou
 extern "C" {
 
 int oracle_max_threads() { return omp_get_max_threads(); }
+int oracle_set_libm(int on) { int old = libm_mode(); libm_mode() = on ? 1 : 0; return old; }
 
 int oracle_model_dims(int model, int* n, int* np) {
   switch (model) {
@@ -86,3 +87,23 @@ int oracle_ros_adj_batch(int model, long ncells, int np, int nadj, double* y, do
 }
 
 }  // extern "C"
+
+// unit-level probes for the parity tests
+extern "C" {
+int oracle_cbm4_fun_jac(double t, const double* y, double* f, double* jac, double* hess) {
+  Cbm4 m;
+  m.fun(t, y, f);
+  m.jac(t, y, jac);
+  m.update(t);
+  cbm4_gen::hessian(y, m.fix, m.rconst, hess);
+  return 0;
+}
+// DGETF2 + DGETRS('N' and 'T'): a is column-major n x n (overwritten by L\U), ipiv 1-based
+int oracle_dgetf2_solve(int n, double* a, int* ipiv, const double* b, double* x_n, double* x_t) {
+  int info = dgetf2(n, a, ipiv);
+  for (int i = 0; i < n; ++i) { x_n[i] = b[i]; x_t[i] = b[i]; }
+  dgetrs(false, n, a, ipiv, x_n);
+  dgetrs(true, n, a, ipiv, x_t);
+  return info;
+}
+}

@@ -21,6 +21,7 @@
 #include <cstring>
 #include <vector>
 #include "ref_lapack.hpp"
+#include "portable_math.hpp"
 #include "gen/ros_tableau_gen.h"
 
 namespace oracle {
@@ -254,7 +255,7 @@ struct Rosenbrock {
           for (int i = 0; i < N; ++i) Yerr[i] = Yerr[i] + e * K[N * (j - 1) + i];
         }
         Err = ros_error_norm(N, Y, Ynew, Yerr, AbsTol, RelTol, cfg.VectorTol);
-        Fac = std::fmin(cfg.FacMax, std::fmax(cfg.FacMin, cfg.FacSafe / std::pow(Err, 1.0 / tb.ELO)));
+        Fac = std::fmin(cfg.FacMax, std::fmax(cfg.FacMin, cfg.FacSafe / o_root(Err, tb.ELO)));
         Hnew = H * Fac;
         ISTATUS[Nstp]++;
         if (Err <= 1.0 || H <= cfg.Hmin) {

@@ -21,9 +21,14 @@ def cbm4_driver_case():
 
 
 def test_cbm4_ros_adj_matches_reference_golden_files():
+    """libm mode (cos/pow from glibc, as the reference binary had): round-off level agreement."""
     g = json.load(open(os.path.join(G, "cbm4_ros_adj.json")))
     c = cbm4_driver_case()
-    r = O.ros_adj("cbm4", O.initial_state("cbm4"), 32, c["tin"], c["tout"], c["atol"], c["rtol"], c["icntrl"], nthreads=1)
+    old = O.lib().oracle_set_libm(1)
+    try:
+        r = O.ros_adj("cbm4", O.initial_state("cbm4"), 32, c["tin"], c["tout"], c["atol"], c["rtol"], c["icntrl"], nthreads=1)
+    finally:
+        O.lib().oracle_set_libm(old)
     assert r["ierr"][0] == 1
     y, lam, mu = r["y"][0], r["lambda_"][0], r["mu"][0]
     gy = np.array(g["y"])
@@ -56,6 +61,25 @@ def test_cbm4_ros_adj_matches_reference_golden_files():
     assert ist[5] == att + A + ist[7]
     assert ist[6] == att * 6 + A * 6 * 32
     assert att >= A + R
+
+
+def test_cbm4_default_mode_agrees_with_golden_at_integration_level():
+    """Default (deterministic cos/root kernels): one ulp in SUN(t) or Err**(1/4) changes the
+    accept/reject sequence of this problem (the error estimate is dominated by cancellation), so the
+    run is a different but equally valid Rodas4 trajectory: Nacc 799 vs 797, state within 1e-8,
+    sensitivities within the integration tolerance."""
+    g = json.load(open(os.path.join(G, "cbm4_ros_adj.json")))
+    c = cbm4_driver_case()
+    assert O.lib().oracle_set_libm(0) == 0
+    r = O.ros_adj("cbm4", O.initial_state("cbm4"), 32, c["tin"], c["tout"], c["atol"], c["rtol"], c["icntrl"], nthreads=1)
+    gy = np.array(g["y"])
+    assert np.max(np.abs(r["y"][0] - gy)) <= 1e-8 * np.max(np.abs(gy))
+    glam = np.array(g["lambda"]).reshape(32, 32)
+    cs = np.max(np.abs(glam), axis=1)
+    ok = cs > 1e-30
+    err = (np.max(np.abs(r["lambda_"][0] - glam), axis=1) / np.maximum(cs, 1e-300))[ok]
+    assert np.all(err <= 1e-4) and np.median(err) <= 1e-6, err
+    assert abs(int(r["istatus"][0][3]) - 797) <= 5
 
 
 def test_small_strato_forward_matches_ANS():
