@@ -42,7 +42,8 @@ struct AdjSmem {
   static constexpr int OFF_LAM = OFF_LU + 32 * 34;                    // [i][m]
   static constexpr int OFF_MU = OFF_LAM + 1024;                       // [p][m]
   static constexpr int OFF_W = OFF_MU + Model::NP * 32;               // [(S-1)][r][m]
-  __host__ __device__ static constexpr int doubles(int S) { return OFF_W + (S > 1 ? S - 1 : 1) * 1024; }
+  // at least 3 slabs: between steps W doubles as the LU tile ([32][33]) and the dJ/dt scratch (at +2048)
+  __host__ __device__ static constexpr int doubles(int S) { return OFF_W + (S - 1 > 3 ? S - 1 : 3) * 1024; }
 };
 
 // x <- (L U)^-T x on the row-major factors; 1056 DFMA, all L\U reads are warp-uniform

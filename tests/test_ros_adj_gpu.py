@@ -15,6 +15,7 @@ F01 = float(np.float32(0.1))
 T0 = 12.0 * 3600.0
 T1 = T0 + 72.0 * 3600.0
 RTOL_PARITY = 1e-9
+NOISE_FLOOR = 1e-10
 
 
 def driver_tols():
@@ -37,28 +38,30 @@ def check_against_oracle(res, ref, nadj):
     assert np.all(normwise(res.rstatus[:, :3], ref["rstatus"][:, :3]) <= 1e-12)
     assert np.all(normwise(res.y, ref["y"]) <= RTOL_PARITY)
     # Lambda: per cell and adjoint column m, relative to the column's own scale max_i |Lambda(i,m)|.
-    # Columns whose reference scale is below 1e-30 are pure round-off (species that stay at zero,
-    # e.g. 22 and 23 in the driver state) and carry no information.
+    # Columns more than ten orders of magnitude below the cell's dominant column are sensitivities
+    # of species that sit at round-off level (e.g. 7, 15, 17, 22, 23 in the driver state): their
+    # values are cancellation noise in the reference too, so they are held to the absolute bound
+    # 1e-9 * (1e-10 * largest column scale) instead of to their own scale.
     lam, rlam = res.lambda_, ref["lambda_"]
     lscale = np.max(np.abs(rlam), axis=2)                     # [cell, column]
     lerr = np.max(np.abs(lam - rlam), axis=2)
-    big = lscale > 1e-30
-    assert np.all(lerr[big] <= RTOL_PARITY * lscale[big]), ("lambda", np.max(lerr[big] / lscale[big]))
+    lfloor = NOISE_FLOOR * np.max(lscale, axis=1, keepdims=True)
+    assert np.all(lerr <= RTOL_PARITY * np.maximum(lscale, lfloor)), ("lambda", np.max(lerr / np.maximum(lscale, lfloor)))
     if ref["mu"] is None:
         return
-    # Mu(p,m): (i) per parameter p, relative to max_m |Mu(p,m)| (all parameters, all cells);
-    # (ii) per column m, relative to max_p |Mu(p,m)|, for the columns whose adjoint variable is
-    # not itself round-off level (Lambda column scale > 1e-10 of the cell's largest).  In the
-    # excluded columns Mu is round-off noise amplified by dF/dp ~ 1e38 (parameter 4 = k21 ~ 4e-40).
+    # Mu(p,m).  The 29 parameters span 50 orders of magnitude (k21 = 4.4e-40 ... k54 = 1600), so rows
+    # are first put on a common footing:  (i) per parameter p, |dMu(p,m)| <= 1e-9 * max_m |Mu(p,m)|
+    # for every element;  (ii) per column m of the row-normalised matrix Mu(p,m)/max_m|Mu(p,m)|,
+    # relative to that column's scale, with the same ten-decade noise floor as Lambda.
     mu, rmu = res.mu, ref["mu"]
-    pscale = np.max(np.abs(rmu), axis=1)                      # [cell, p]
-    perr = np.max(np.abs(mu - rmu), axis=1)
-    nz = pscale > 0
-    assert np.all(perr[nz] <= RTOL_PARITY * pscale[nz]), ("mu rows", np.max(perr[nz] / pscale[nz]))
-    cscale = np.max(np.abs(rmu), axis=2)                      # [cell, column]
-    cerr = np.max(np.abs(mu - rmu), axis=2)
-    good = (lscale > 1e-10 * np.max(lscale, axis=1, keepdims=True)) & (cscale > 0)
-    assert np.all(cerr[good] <= RTOL_PARITY * cscale[good]), ("mu cols", np.max(cerr[good] / cscale[good]))
+    pscale = np.max(np.abs(rmu), axis=1, keepdims=True)       # [cell, 1, p]
+    assert np.all(np.abs(mu - rmu) <= RTOL_PARITY * pscale), ("mu rows", np.max(np.abs(mu - rmu) / np.maximum(pscale, 1e-300)))
+    nrm = np.where(pscale > 0, pscale, 1.0)
+    a, b = mu / nrm, rmu / nrm
+    cscale = np.max(np.abs(b), axis=2)                        # [cell, column]
+    cerr = np.max(np.abs(a - b), axis=2)
+    cfloor = NOISE_FLOOR * np.max(cscale, axis=1, keepdims=True)
+    assert np.all(cerr <= RTOL_PARITY * np.maximum(cscale, cfloor)), ("mu cols", np.max(cerr / np.maximum(cscale, cfloor)))
 
 
 def test_driver_cell_matches_oracle_and_reference_golden():
