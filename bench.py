@@ -1,0 +1,377 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of fatode_b200 (contract: see the task brief / DESIGN.md §6).
+
+Metric (BASELINE.json): cell-integrations/sec (forward + adjoint) for CBM-IV ROS_ADJ.
+One cell-integration = one complete INTEGRATE_ADJ (ADJ/ROS_ADJ/ROS_ADJ_f90_Integrator.F90:34): forward
+Rodas4 sweep 12h -> 84h with trajectory tape, ADJINIT, discrete adjoint sweep for NADJ = 32 cost
+functionals and NP = 29 rate-coefficient parameters (the reference driver's problem,
+EXAMPLES/cbm4/CBM4_ROS_ADJ/cbm4_ros_adj_dr.F90:167-292), on synthetic per-cell initial states.
+
+A "step" is one pass of the hot path over one batch of `--cells` cells per GPU.
+  value : cells/s with y0 and all outputs resident in HBM (device pointers through the C ABI)
+  e2e   : cells/s through the same C-ABI call with pinned HOST buffers (H2D of y0, D2H of y, Lambda,
+          Mu, ISTATUS, RSTATUS, IERR inside the timed region)
+  roofline    : dominant kernel (k_ros_adj, the backward sweep): algorithmic FP64 flops of
+                SURVEY.md §8d evaluated on the returned counters / its CUDA-event time, against the
+                DFMA peak measured on this GPU in this run (MEASURED_PEAKS.json has no FP64 figure)
+  cpu_baseline: the CPU oracle (C++ restatement of the reference, OpenMP over cells) on a bounded sample
+`--impl reference` times that CPU restatement alone (the reference Fortran cannot be built: no Fortran
+compiler in the image) and prints the same JSON line with "impl": "reference".
+Multi-GPU (torchrun, one rank per GPU): cells are sharded, no data-path collective; one NCCL
+all-reduce of the 29x32 Mu sums per step.  Time = max over ranks, barrier on both sides.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N, NP, NADJ, S = 32, 29, 32, 6
+T0 = 12.0 * 3600.0
+T1 = T0 + 72.0 * 3600.0
+F01 = float(np.float32(0.1))
+
+
+def tolerances():
+    # rtol(i) = 0.1*1e-4, atol(i) = 0.1*1e-6 with a REAL(4) 0.1 (cbm4_ros_adj_dr.F90:181-189)
+    return np.full(N, F01 * 1.0e-4), np.full(N, F01 * 1.0e-6)
+
+
+def icntrl_rodas4():
+    ic = np.zeros(20, dtype=np.int32)
+    ic[2] = 5
+    return ic
+
+
+# ---- algorithmic flop model, evaluated on the returned ISTATUS counters
+def flops_adjoint_per_step(nadj=NADJ):
+    n, s, p = N, S, NP
+    LU, SOL, MV, MVP = (2 * n ** 3) // 3 + n * n, 2 * n * n, 2 * n * n, 2 * n * p
+    F_jac, F_hess, F_htv, F_jacp, F_djdr = 636, 129, 1483, 250, 250
+    per_col = s * n + 2 * n * s * (s - 1) + s * SOL + s * MV + s * (F_htv + 2 * n) + s * (2 * MVP + 2 * p) + \
+        (2 * n * s + MVP + MV + 2 * n)
+    return F_jac + LU + s * F_jac + F_hess + s * (F_jacp + F_djdr) + nadj * per_col + \
+        (F_jac + 2 * n * n + 2 * F_jacp + 2 * n * p)
+
+
+def flops_forward(attempts, accepted, singular=0):
+    n, s = N, S
+    LU, SOL, F_fun, F_jac = (2 * n ** 3) // 3 + n * n, 2 * n * n, 573, 636
+    per_attempt = s * SOL + 5 * F_fun + 2 * n * s * (s - 1) + 2 * n * 4 + 4 * n * s + 7 * n
+    return (attempts + singular) * LU + attempts * per_attempt + accepted * (2 * F_fun + F_jac + 2 * n)
+
+
+class ClockSampler:
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for l in self.proc.stdout:
+            self.lines.append(l.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def oracle_lib():
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    L = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+    L.oracle_ros_adj_batch.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_int, dp, dp, dp, ctypes.c_double,
+                                       ctypes.c_double, dp, dp, ip, dp, ip, dp, ip, ctypes.c_int]
+    return L
+
+
+def cpu_run(L, y0, nthreads):
+    """CPU restatement (oracle) over the cells of y0 with OpenMP; returns seconds."""
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+    nc = y0.shape[0]
+    y = y0.copy()
+    rtol, atol = tolerances()
+    ic, rc = icntrl_rodas4(), np.zeros(20)
+    lam, mu = np.zeros((nc, NADJ, N)), np.zeros((nc, NADJ, NP))
+    ist, rst, ierr = np.zeros((nc, 20), dtype=np.int32), np.zeros((nc, 20)), np.zeros(nc, dtype=np.int32)
+    d = lambda a: a.ctypes.data_as(dp)
+    i = lambda a: a.ctypes.data_as(ip)
+    t = time.perf_counter()
+    L.oracle_ros_adj_batch(3, nc, NP, NADJ, d(y), d(lam), d(mu), T0, T1, d(atol), d(rtol), i(ic), d(rc), i(ist), d(rst), i(ierr),
+                           nthreads)
+    dt = time.perf_counter() - t
+    assert (ierr == 1).all()
+    return dt
+
+
+def cpu_baseline(sample_cells=None):
+    from fatode_b200.inputs import perturbed_states
+    import fatode_b200 as F
+    L = oracle_lib()
+    cores = L.oracle_max_threads()
+    nc = sample_cells or max(16, 12 * cores)
+    y0 = perturbed_states(F.initial_state("cbm4"), nc)
+    dt = cpu_run(L, y0, cores)
+    return {"value": nc / dt, "unit": "cells/s", "cores": cores, "kind": "port",
+            "sample": f"{nc} cells of the same workload (perturbed driver states, cells 0..{nc-1}), {dt:.1f} s wall, "
+                      f"OpenMP schedule(dynamic) over cells, C++ restatement of ADJ/ROS_ADJ (oracle/), strict IEEE"}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU algorithm (C++ restatement; no Fortran compiler in this image)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from fatode_b200.inputs import perturbed_states
+    import fatode_b200 as F
+    L = oracle_lib()
+    cores = L.oracle_max_threads()
+    nc = max(8, 4 * cores)       # bounded sample per step: ~4 cells per core, ~5 s
+    base = F.initial_state("cbm4")
+    times = []
+    for s in range(args.warmup + args.steps):
+        y0 = perturbed_states(base, nc, first_cell=s * nc)
+        dt = cpu_run(L, y0, cores)
+        if s >= args.warmup:
+            times.append(dt)
+    tot = sum(times)
+    v = nc * len(times) / tot
+    line = {"impl": "reference", "metric": "cell-integrations/sec (fwd + adjoint), CBM-IV ROS_ADJ", "value": v, "unit": "cells/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(nc, 1, note="CPU arm: bounded sample per step"),
+            "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port",
+                             "sample": f"{nc} cells per step x {len(times)} steps, OpenMP over cells on {cores} host threads"},
+            "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(cells, ngpus, note=None):
+    c = {"workload": "EXAMPLES/cbm4 ADJ/ROS_ADJ: CBM-IV N=32, Rodas4 (ICNTRL(3)=5), NADJ=32, NP=29, t=12h..84h, "
+                     "rtol=0.1f*1e-4, atol=0.1f*1e-6, y0 = driver state*(1+0.1u) per cell (cell 0 unperturbed)",
+         "cells_per_gpu_per_step": int(cells), "global_cells_per_step": int(cells * ngpus), "parallelism": f"cells sharded x{ngpus}",
+         "l2_policy": "working set >> L2 (trajectory tape ~2.5 MB per cell; no explicit flush needed)"}
+    if note:
+        c["note"] = note
+    return c
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--cells", type=int, default=16384, help="cells per GPU per step")
+    ap.add_argument("--impl", default="fatode_b200", choices=["fatode_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = F.lib()
+    dev = torch.device("cuda", local)
+    nc = args.cells
+    rtol, atol = tolerances()
+    ic, rc = icntrl_rodas4(), np.zeros(20)
+    base = F.initial_state("cbm4")
+    fp64_peak = F.measure_fp64_peak(20000) if rank == 0 else None
+
+    # device-resident buffers (torch = allocator + stream plumbing only)
+    y0_all = [torch.from_numpy(perturbed_states(base, nc, first_cell=(s * world + rank) * nc)).to(dev)
+              for s in range(args.warmup + args.steps)]
+    y = torch.empty((nc, N), dtype=torch.float64, device=dev)
+    lam = torch.empty((nc, NADJ, N), dtype=torch.float64, device=dev)
+    mu = torch.empty((nc, NADJ, NP), dtype=torch.float64, device=dev)
+    ist = torch.empty((nc, 20), dtype=torch.int32, device=dev)
+    rst = torch.empty((nc, 20), dtype=torch.float64, device=dev)
+    ierr = torch.empty((nc,), dtype=torch.int32, device=dev)
+    musum = torch.empty((NADJ, NP), dtype=torch.float64, device=dev)
+    vp = ctypes.c_void_p
+    np_ptr = lambda a: vp(a.ctypes.data)
+    stream = torch.cuda.current_stream()
+
+    def step_device(s):
+        y.copy_(y0_all[s])
+        r = L.fatode_ros_integrate_adj_batch(F.MODEL_CBM4, nc, N, NP, NADJ, vp(y.data_ptr()), vp(lam.data_ptr()), vp(mu.data_ptr()),
+                                             T0, T1, None, None, np_ptr(atol), np_ptr(rtol), np_ptr(ic), np_ptr(rc),
+                                             vp(ist.data_ptr()), vp(rst.data_ptr()), vp(ierr.data_ptr()), vp(musum.data_ptr()),
+                                             None, F.MEM_DEVICE, vp(stream.cuda_stream))
+        if r != 0:
+            raise RuntimeError(L.fatode_last_error().decode())
+        if dist is not None:
+            dist.all_reduce(musum)      # the path's only exchange: 29x32 parameter sensitivities summed over cells
+        return F.last_stats()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for s in range(args.warmup):
+        step_device(s)
+    sampler = ClockSampler(local)
+    sync_all()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    launches = 0
+    ms_adj = ms_fwd = ms_tape = 0.0
+    acc_steps = attempts = 0
+    for s in range(args.warmup, args.warmup + args.steps):
+        st = step_device(s)
+        launches += st.launches + 1 + (1 if dist is not None else 0)     # + the y0 copy (+ NCCL kernel)
+        ms_adj += st.ms_adjoint
+        ms_fwd += st.ms_forward
+        ms_tape += st.ms_forward_tape
+        acc_steps += st.accepted_steps
+        ok = bool((ierr == 1).all().item())
+        attempts += int((ist[:, 2].sum() - ist[:, 3].sum()).item())       # Nstp counts attempts + backward steps
+        if not ok:
+            raise RuntimeError("a cell failed (ierr != 1)")
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    sync_all()
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    cells_total = nc * world * args.steps
+    value = cells_total / (ms * 1e-3)
+
+    # ---- e2e: same call, pinned host buffers, H2D/D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        hy0 = [torch.from_numpy(perturbed_states(base, nc, first_cell=(s * world + rank) * nc)).pin_memory()
+               for s in range(args.warmup, args.warmup + args.steps)]
+        hy = torch.empty((nc, N), dtype=torch.float64).pin_memory()
+        hlam = torch.empty((nc, NADJ, N), dtype=torch.float64).pin_memory()
+        hmu = torch.empty((nc, NADJ, NP), dtype=torch.float64).pin_memory()
+        hist = torch.empty((nc, 20), dtype=torch.int32).pin_memory()
+        hrst = torch.empty((nc, 20), dtype=torch.float64).pin_memory()
+        hierr = torch.empty((nc,), dtype=torch.int32).pin_memory()
+        hmusum = torch.empty((NADJ, NP), dtype=torch.float64).pin_memory()
+
+        def step_host(k):
+            hy.copy_(hy0[k])
+            r = L.fatode_ros_integrate_adj_batch(F.MODEL_CBM4, nc, N, NP, NADJ, vp(hy.data_ptr()), vp(hlam.data_ptr()),
+                                                 vp(hmu.data_ptr()), T0, T1, None, None, np_ptr(atol), np_ptr(rtol), np_ptr(ic),
+                                                 np_ptr(rc), vp(hist.data_ptr()), vp(hrst.data_ptr()), vp(hierr.data_ptr()),
+                                                 vp(hmusum.data_ptr()), None, F.MEM_HOST, vp(stream.cuda_stream))
+            if r != 0:
+                raise RuntimeError(L.fatode_last_error().decode())
+            if dist is not None:
+                g = hmusum.to(dev, non_blocking=True)
+                dist.all_reduce(g)
+                hmusum.copy_(g)
+        step_host(0)
+        sync_all()
+        e0.record(stream)
+        for k in range(args.steps):
+            step_host(k)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms2 = e0.elapsed_time(e1)
+        t = torch.tensor([ms2], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms2 = float(t.item())
+        h2d = nc * N * 8 + 2 * N * 8
+        d2h = nc * (N * 8 + NADJ * N * 8 + NADJ * NP * 8 + 20 * 4 + 20 * 8 + 4) + NADJ * NP * 8
+        e2e = {"value": cells_total / (ms2 * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+
+    # totals over ranks for the flop model
+    tot = torch.tensor([acc_steps, attempts, ms_adj, ms_fwd, ms_tape], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tot)
+    if rank == 0:
+        acc_t, att_t, ms_adj_t, ms_fwd_t, ms_tape_t = [float(x) for x in tot.tolist()]
+        f_adj = acc_t * flops_adjoint_per_step()
+        f_fwd = flops_forward(att_t, acc_t)
+        # dominant kernel: k_ros_adj; per-rank kernel time = sum of its launches on that rank (ranks run concurrently)
+        adj_tflops = f_adj / (ms_adj_t / world * 1e-3) / 1e12
+        roof = {"bound": "fp64", "kernel": "k_ros_adj<Cbm4Warp> (discrete adjoint sweep)", "achieved": adj_tflops,
+                "peak": fp64_peak * world, "unit": "TFLOP/s", "frac": adj_tflops / (fp64_peak * world),
+                "peak_source": "DFMA micro-benchmark run by this bench on this GPU (fatode_measure_fp64_peak); "
+                               "MEASURED_PEAKS.json carries no FP64 figure",
+                "algorithmic_flops_per_accepted_step": flops_adjoint_per_step(),
+                "launches": int(args.steps * world), "avg_launch_ms": ms_adj_t / (args.steps * world),
+                "share_of_step_time": (ms_adj_t / world) / ms,
+                "traffic": None,
+                "whole_job_algorithmic_tflops": (f_adj + f_fwd) / (ms * 1e-3) / 1e12,
+                "forward_ms_per_step": ms_fwd_t / (args.steps * world), "forward_tape_ms_per_step": ms_tape_t / (args.steps * world)}
+        line = {"metric": "cell-integrations/sec (fwd + adjoint), CBM-IV ROS_ADJ", "value": value, "unit": "cells/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(nc, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roof,
+                "accepted_steps_per_cell": acc_t / (nc * world * args.steps)}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
