@@ -335,7 +335,7 @@ def main():
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms2 = float(t.item())
-        h2d = nc * N * 8 + 2 * N * 8
+        h2d = nc * (N * 8 + NADJ * N * 8 + NADJ * NP * 8) + 2 * N * 8     # y0 + Lambda/Mu (INOUT in the reference API)
         d2h = nc * (N * 8 + NADJ * N * 8 + NADJ * NP * 8 + 20 * 4 + 20 * 8 + 4) + NADJ * NP * 8
         e2e = {"value": cells_total / (ms2 * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
 

@@ -100,29 +100,39 @@ constexpr int ADJ_WARPS = 3;
 template <class Model>
 __host__ __device__ constexpr int fwd_ws_doubles() { return FwdSmem<Model>::DOUBLES; }
 
-template <class Model, bool TAPE>
+constexpr int IERR_TAPE_OVERFLOW = -1000;   // internal: slab too small, the wave is re-run in exact mode
+
+// MODE 0: no tape, writes y/ISTATUS/RSTATUS/IERR/nacc.   MODE 1: replay with tape at exact offsets (tape_off), no
+// status.   MODE 2: single pass, status + tape into a fixed slab of `slab_cap` entries per cell.
+template <class Model, int MODE>
 __global__ void __launch_bounds__(FWD_WARPS * 32, 3)
 k_ros_fwd(RosParams rp, typename Model::Const mc, long ncells, const double* __restrict__ y_in, double* __restrict__ y_out,
           const double* __restrict__ atol, const double* __restrict__ rtol, int* __restrict__ istatus,
           double* __restrict__ rstatus, int* __restrict__ ierr, int* __restrict__ nacc,
-          const long long* __restrict__ tape_off, double* __restrict__ tape) {
+          const long long* __restrict__ tape_off, double* __restrict__ tape, long slab_cap, int* __restrict__ n_overflow) {
   extern __shared__ __align__(16) double smem[];
+  constexpr bool TAPE = (MODE != 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long cell = (long)blockIdx.x * FWD_WARPS + warp;
   if (cell >= ncells) return;
-  if (TAPE && ierr[cell] != 1) return;
+  if (MODE == 1 && ierr[cell] != 1) return;
   double* ws = smem + (size_t)warp * fwd_ws_doubles<Model>();
   double y = y_in[cell * 32 + lane];
   const int ti = rp.vector_tol ? lane : 0;
   FwdResult res;
   double* tb = nullptr;
   long cap = 0;
-  if (TAPE) {
-    tb = tape + tape_off[cell] * tape_entry_doubles(rp.S, 32);
+  const int NE = tape_entry_doubles(rp.S, 32);
+  if (MODE == 1) {
+    tb = tape + tape_off[cell] * NE;
     cap = (long)(tape_off[cell + 1] - tape_off[cell]);
+  } else if (MODE == 2) {
+    tb = tape + cell * slab_cap * NE;
+    cap = slab_cap;
   }
   ros_forward_warp<Model, TAPE>(rp, mc, ws, y, atol[ti], rtol[ti], tb, cap, res, lane);
-  if (!TAPE) {
+  if (MODE != 1) {
+    const bool overflow = (MODE == 2) && res.ierr == -6 && res.nacc > slab_cap;   // ran out of slab, not of steps
     y_out[cell * 32 + lane] = y;
     if (lane < 20) {
       int v = 0;
@@ -136,7 +146,11 @@ k_ros_fwd(RosParams rp, typename Model::Const mc, long ncells, const double* __r
       if (lane == Ntexit) r = res.texit; else if (lane == Nhexit) r = res.hexit; else if (lane == Nhnew) r = res.hnew;
       rstatus[cell * 20 + lane] = r;
     }
-    if (lane == 0) { ierr[cell] = res.ierr; nacc[cell] = res.nacc; }
+    if (lane == 0) {
+      ierr[cell] = overflow ? IERR_TAPE_OVERFLOW : res.ierr;
+      nacc[cell] = res.nacc;
+      if (overflow) atomicAdd(n_overflow, 1);
+    }
   }
 }
 
@@ -171,7 +185,7 @@ __global__ void __launch_bounds__(ADJ_WARPS * 32, 1)
 k_ros_adj(RosParams rp, typename Model::Const mc, long ncells, int nadj, int with_mu, const double* __restrict__ tape,
           const long long* __restrict__ tape_off, const int* __restrict__ ierr, const double* __restrict__ y_final,
           double* __restrict__ lambda, double* __restrict__ mu, int* __restrict__ istatus,
-          unsigned long long* __restrict__ queue, int smem_per_warp) {
+          unsigned long long* __restrict__ queue, int smem_per_warp, long slab_cap, const int* __restrict__ nacc) {
   extern __shared__ __align__(16) double smem[];
   typedef AdjSmem<Model> L;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -183,9 +197,10 @@ k_ros_adj(RosParams rp, typename Model::Const mc, long ncells, int nadj, int wit
     c = __shfl_sync(FATODE_FULL_MASK, c, 0);
     if (c >= (unsigned long long)ncells) break;
     if (ierr[c] != 1) continue;
-    const int nsteps = (int)(tape_off[c + 1] - tape_off[c]);
+    const long long off = slab_cap > 0 ? (long long)c * slab_cap : tape_off[c];
+    const int nsteps = slab_cap > 0 ? nacc[c] : (int)(tape_off[c + 1] - tape_off[c]);
     const double yf = y_final[c * 32 + lane];
-    ros_adjoint_warp<Model>(rp, mc, sm, tape + tape_off[c] * NE, nsteps, nadj, with_mu != 0, yf, lane);
+    ros_adjoint_warp<Model>(rp, mc, sm, tape + off * NE, nsteps, nadj, with_mu != 0, yf, lane);
     __syncwarp();
     const double* LAM = sm + L::OFF_LAM;
     const double* MU = sm + L::OFF_MU;
@@ -283,6 +298,26 @@ struct DevBuf {
   template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
+// Grow-only device workspace cached across calls (cudaMalloc/cudaFree of a 100 GB tape costs ~100 ms).
+struct CachedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+static thread_local CachedBuf g_tape, g_y0, g_nacc, g_off, g_queue, g_part;
+extern "C" int fatode_release_workspace(void) {
+  g_tape.release(); g_y0.release(); g_nacc.release(); g_off.release(); g_queue.release(); g_part.release();
+  return 0;
+}
+
 struct PhaseTimer {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   cudaStream_t s;
@@ -313,8 +348,9 @@ static int ros_adj_device(const RosParams& rp, const typename Model::Const& mc, 
   const size_t fwd_smem = sizeof(double) * fwd_ws_doubles<Model>() * FWD_WARPS;
   const int adj_per_warp = AdjSmem<Model>::doubles(rp.S);
   const size_t adj_smem = sizeof(double) * (size_t)adj_per_warp * ADJ_WARPS;
-  CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd<Model, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
-  CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd<Model, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
+  CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd<Model, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
+  CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd<Model, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
+  CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd<Model, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
   CUDA_TRY(cudaFuncSetAttribute(k_ros_adj<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem));
 
   size_t free_b = 0, total_b = 0;
@@ -322,77 +358,139 @@ static int ros_adj_device(const RosParams& rp, const typename Model::Const& mc, 
   size_t budget = g_tape_budget ? (size_t)g_tape_budget : (size_t)(0.6 * (double)free_b);
   budget = std::min(budget, (size_t)(0.9 * (double)free_b));
   if (!do_adjoint) budget = 0;
+  if (do_adjoint && g_tape_budget == 0 && g_tape.cap >= entry_bytes * 4096) budget = g_tape.cap;   // reuse the cached tape
   const long long cap_entries = (long long)(budget / entry_bytes);
 
-  int64_t wave = g_wave_cells > 0 ? g_wave_cells : 16384;
-  wave = std::min<int64_t>(wave, ncells);
-  DevBuf b_y0, b_nacc, b_off, b_tape, b_queue;
-  CUDA_TRY(b_y0.alloc(sizeof(double) * 32 * wave));
-  CUDA_TRY(b_nacc.alloc(sizeof(int) * wave));
-  CUDA_TRY(b_off.alloc(sizeof(long long) * (wave + 1)));
-  CUDA_TRY(b_queue.alloc(sizeof(unsigned long long)));
-  if (do_adjoint) CUDA_TRY(b_tape.alloc(budget));
+  const int64_t wave_max = std::min<int64_t>(g_wave_cells > 0 ? g_wave_cells : 32768, ncells);
+  CachedBuf &b_y0 = g_y0, &b_nacc = g_nacc, &b_off = g_off, &b_tape = g_tape, &b_queue = g_queue;
+  CUDA_TRY(b_y0.ensure(sizeof(double) * 32 * wave_max));
+  CUDA_TRY(b_nacc.ensure(sizeof(int) * wave_max));
+  CUDA_TRY(b_off.ensure(sizeof(long long) * (wave_max + 1)));
+  CUDA_TRY(b_queue.ensure(2 * sizeof(unsigned long long)));
+  if (do_adjoint) CUDA_TRY(b_tape.ensure(budget));
+  unsigned long long* d_queue = b_queue.as<unsigned long long>();
+  int* d_novf = reinterpret_cast<int*>(d_queue + 1);
   PhaseTimer tm(st);
   std::memset(&g_stats, 0, sizeof g_stats);
 
-  int64_t c0 = 0;
-  std::vector<long long> h_off;
-  while (c0 < ncells) {
-    int64_t n = std::min<int64_t>(wave, ncells - c0);
+  auto launch_adjoint = [&](int64_t c0, int64_t n, long slab_cap) -> int {
+    CUDA_TRY(cudaMemsetAsync(d_queue, 0, sizeof(unsigned long long), st));
+    const int ablocks = (int)std::min<int64_t>(sms, (n + ADJ_WARPS - 1) / ADJ_WARPS);
+    tm.start();
+    k_ros_adj<Model><<<ablocks, ADJ_WARPS * 32, adj_smem, st>>>(
+        rp, mc, n, nadj, with_mu ? 1 : 0, b_tape.as<double>(), b_off.as<long long>(), d_ierr + c0, d_y + c0 * 32,
+        d_lambda + c0 * nadj * 32, with_mu ? d_mu + c0 * nadj * Model::NP : nullptr, d_istatus + c0 * 20, d_queue,
+        adj_per_warp, slab_cap, b_nacc.as<int>());
+    CUDA_TRY(cudaGetLastError());
+    g_stats.ms_adjoint += tm.stop();
+    g_stats.launches++;
+    return 0;
+  };
+
+  // Exact (two-pass) wave: forward for the counts, prefix-sum offsets, replay with tape, adjoint.
+  // Returns the number of leading cells that were completed (the rest did not fit the tape).
+  auto exact_wave = [&](int64_t c0, int64_t n, int64_t& done, int& max_nacc) -> int {
     double* y = d_y + c0 * 32;
     int* ist = d_istatus + c0 * 20;
     double* rst = d_rstatus + c0 * 20;
     int* ier = d_ierr + c0;
-    // 1. forward without tape (keeps the initial state for the taped pass)
     CUDA_TRY(cudaMemcpyAsync(b_y0.p, y, sizeof(double) * 32 * n, cudaMemcpyDeviceToDevice, st));
     const int fblocks = (int)((n + FWD_WARPS - 1) / FWD_WARPS);
     tm.start();
-    k_ros_fwd<Model, false><<<fblocks, FWD_WARPS * 32, fwd_smem, st>>>(rp, mc, n, b_y0.as<double>(), y, d_atol, d_rtol, ist,
-                                                                         rst, ier, b_nacc.as<int>(), nullptr, nullptr);
+    k_ros_fwd<Model, 0><<<fblocks, FWD_WARPS * 32, fwd_smem, st>>>(rp, mc, n, b_y0.as<double>(), y, d_atol, d_rtol, ist, rst, ier,
+                                                                     b_nacc.as<int>(), nullptr, nullptr, 0, nullptr);
     CUDA_TRY(cudaGetLastError());
     g_stats.ms_forward += tm.stop();
     g_stats.launches++;
-    if (!do_adjoint) { c0 += n; g_stats.waves++; continue; }
-    // 2. tape offsets
+    done = n;
+    if (!do_adjoint) return 0;
     k_scan_offsets<<<1, 1024, 0, st>>>(n, b_nacc.as<int>(), ier, b_off.as<long long>());
     CUDA_TRY(cudaGetLastError());
     g_stats.launches++;
-    h_off.resize(n + 1);
+    std::vector<long long> h_off(n + 1);
+    std::vector<int> h_nacc(n);
     CUDA_TRY(cudaMemcpyAsync(h_off.data(), b_off.p, sizeof(long long) * (n + 1), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_nacc.data(), b_nacc.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     int64_t fit = n;
     if (h_off[n] > cap_entries) {   // keep the prefix of cells whose trajectories fit the tape
       fit = std::upper_bound(h_off.begin(), h_off.end(), cap_entries) - h_off.begin() - 1;
       if (fit <= 0) return fail(FATODE_ENOMEM, "trajectory tape of a single cell exceeds the tape budget");
-      wave = std::max<int64_t>(1, fit);   // later waves: what fitted this time
     }
+    for (int64_t i = 0; i < fit; ++i) max_nacc = std::max(max_nacc, h_nacc[i]);
     g_stats.tape_bytes_peak = std::max<uint64_t>(g_stats.tape_bytes_peak, (uint64_t)h_off[fit] * entry_bytes);
     g_stats.accepted_steps += h_off[fit];
-    // 3. forward with tape
     const int tblocks = (int)((fit + FWD_WARPS - 1) / FWD_WARPS);
     tm.start();
-    k_ros_fwd<Model, true><<<tblocks, FWD_WARPS * 32, fwd_smem, st>>>(rp, mc, fit, b_y0.as<double>(), nullptr, d_atol, d_rtol,
-                                                                        ist, rst, ier, b_nacc.as<int>(), b_off.as<long long>(),
-                                                                        b_tape.as<double>());
+    k_ros_fwd<Model, 1><<<tblocks, FWD_WARPS * 32, fwd_smem, st>>>(rp, mc, fit, b_y0.as<double>(), nullptr, d_atol, d_rtol, ist, rst,
+                                                                     ier, b_nacc.as<int>(), b_off.as<long long>(), b_tape.as<double>(),
+                                                                     0, nullptr);
     CUDA_TRY(cudaGetLastError());
     g_stats.ms_forward_tape += tm.stop();
     g_stats.launches++;
-    // 4. backward sweep
-    CUDA_TRY(cudaMemsetAsync(b_queue.p, 0, sizeof(unsigned long long), st));
-    const int ablocks = (int)std::min<int64_t>(sms, (fit + ADJ_WARPS - 1) / ADJ_WARPS);
-    tm.start();
-    k_ros_adj<Model><<<ablocks, ADJ_WARPS * 32, adj_smem, st>>>(rp, mc, fit, nadj, with_mu ? 1 : 0, b_tape.as<double>(),
-                                                                  b_off.as<long long>(), ier, y, d_lambda + c0 * nadj * 32,
-                                                                  with_mu ? d_mu + c0 * nadj * Model::NP : nullptr, ist,
-                                                                  b_queue.as<unsigned long long>(), adj_per_warp);
-    CUDA_TRY(cudaGetLastError());
-    g_stats.ms_adjoint += tm.stop();
-    g_stats.launches++;
-    if (fit < n) {   // cells beyond the prefix: restore their initial state, they run in the next wave
+    if (int e = launch_adjoint(c0, fit, 0)) return e;
+    if (fit < n)   // cells beyond the prefix: restore their initial state, they run in a later wave
       CUDA_TRY(cudaMemcpyAsync(y + fit * 32, b_y0.as<double>() + fit * 32, sizeof(double) * 32 * (n - fit),
                                cudaMemcpyDeviceToDevice, st));
+    done = fit;
+    return 0;
+  };
+
+  int64_t c0 = 0;
+  int max_nacc = 0;
+  bool have_estimate = false;
+  while (c0 < ncells) {
+    int64_t remaining = ncells - c0;
+    if (!do_adjoint || !have_estimate) {
+      // forward-only call, or first wave: exact mode on a sample to learn the trajectory lengths
+      int64_t n = std::min<int64_t>(do_adjoint ? std::min<int64_t>(wave_max, 2048) : wave_max, remaining);
+      int64_t done = 0;
+      if (int e = exact_wave(c0, n, done, max_nacc)) return e;
+      c0 += done;
+      g_stats.waves++;
+      have_estimate = do_adjoint && max_nacc > 0;
+      continue;
     }
-    c0 += fit;
+    // single-pass waves: fixed slab per cell sized from the longest trajectory seen so far (+30%)
+    const long slab = (long)std::min<long long>((long long)rp.max_no_steps + 1, (long long)(1.3 * max_nacc) + 32);
+    int64_t n = std::min<int64_t>(std::min<int64_t>(wave_max, remaining), cap_entries / slab);
+    if (n < 1) {   // not even one slab fits: fall back to the exact path (it reports ENOMEM if hopeless)
+      int64_t done = 0;
+      if (int e = exact_wave(c0, std::min<int64_t>(remaining, 64), done, max_nacc)) return e;
+      c0 += done;
+      g_stats.waves++;
+      continue;
+    }
+    double* y = d_y + c0 * 32;
+    CUDA_TRY(cudaMemcpyAsync(b_y0.p, y, sizeof(double) * 32 * n, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(d_novf, 0, sizeof(int), st));
+    const int fblocks = (int)((n + FWD_WARPS - 1) / FWD_WARPS);
+    tm.start();
+    k_ros_fwd<Model, 2><<<fblocks, FWD_WARPS * 32, fwd_smem, st>>>(rp, mc, n, b_y0.as<double>(), y, d_atol, d_rtol,
+                                                                     d_istatus + c0 * 20, d_rstatus + c0 * 20, d_ierr + c0,
+                                                                     b_nacc.as<int>(), nullptr, b_tape.as<double>(), slab, d_novf);
+    CUDA_TRY(cudaGetLastError());
+    g_stats.ms_forward += tm.stop();
+    g_stats.launches++;
+    int h_novf = 0;
+    std::vector<int> h_nacc(n);
+    CUDA_TRY(cudaMemcpyAsync(&h_novf, d_novf, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_nacc.data(), b_nacc.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_novf > 0) {   // some trajectory outgrew its slab: redo this wave exactly (rare), with a larger estimate after
+      CUDA_TRY(cudaMemcpyAsync(y, b_y0.p, sizeof(double) * 32 * n, cudaMemcpyDeviceToDevice, st));
+      int64_t done = 0;
+      if (int e = exact_wave(c0, n, done, max_nacc)) return e;
+      c0 += done;
+      g_stats.waves++;
+      continue;
+    }
+    long long steps = 0;
+    for (int64_t i = 0; i < n; ++i) { steps += h_nacc[i]; max_nacc = std::max(max_nacc, h_nacc[i]); }
+    g_stats.accepted_steps += steps;   // (cells with ierr != 1 contribute the steps they made)
+    g_stats.tape_bytes_peak = std::max<uint64_t>(g_stats.tape_bytes_peak, (uint64_t)n * slab * entry_bytes);
+    if (int e = launch_adjoint(c0, n, slab)) return e;
+    c0 += n;
     g_stats.waves++;
   }
   // deterministic Mu sum over cells
@@ -400,8 +498,8 @@ static int ros_adj_device(const RosParams& rp, const typename Model::Const& mc, 
     const int len = nadj * Model::NP;
     const int cpb = 256;
     const int nb = (int)((ncells + cpb - 1) / cpb);
-    DevBuf part;
-    CUDA_TRY(part.alloc(sizeof(double) * (size_t)nb * len));
+    CachedBuf& part = g_part;
+    CUDA_TRY(part.ensure(sizeof(double) * (size_t)nb * len));
     tm.start();
     k_mu_reduce1<<<nb, 256, 0, st>>>(ncells, len, d_mu, d_ierr, part.as<double>(), cpb);
     k_mu_reduce2<<<(len + 255) / 256, 256, 0, st>>>(nb, len, part.as<double>(), d_mu_sum);
@@ -484,9 +582,15 @@ static int ros_batch_impl(int family, int model, int64_t ncells, int nvar, int n
     CUDA_TRY(cudaMemcpyAsync(b_y.p, y, ny, cudaMemcpyHostToDevice, st));
     d_y = b_y.as<double>(); d_ist = b_ist.as<int>(); d_rst = b_rst.as<double>(); d_ierr = b_ierr.as<int>();
     if (family == FAM_ADJ) {
+      // Lambda and Mu are INTENT(INOUT) in the reference: cells whose forward sweep fails keep the caller's values
       CUDA_TRY(b_lam.alloc(nl));
       d_lam = b_lam.as<double>();
-      if (with_mu) { CUDA_TRY(b_mu.alloc(nm)); d_mu = b_mu.as<double>(); }
+      CUDA_TRY(cudaMemcpyAsync(d_lam, lambda, nl, cudaMemcpyHostToDevice, st));
+      if (with_mu) {
+        CUDA_TRY(b_mu.alloc(nm));
+        d_mu = b_mu.as<double>();
+        CUDA_TRY(cudaMemcpyAsync(d_mu, mu, nm, cudaMemcpyHostToDevice, st));
+      }
       if (with_mu && mu_sum) { CUDA_TRY(b_musum.alloc(sizeof(double) * np * nadj)); d_musum = b_musum.as<double>(); }
     }
   }

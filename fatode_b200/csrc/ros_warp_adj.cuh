@@ -150,6 +150,7 @@ __device__ void ros_adjoint_warp(const RosParams& rp, const typename Model::Cons
       __syncwarp();
     }
     const bool ident = __all_sync(FATODE_FULL_MASK, WHO[lane] == lane);
+    const double inv_dH = 1.0 / (dDir * H);
 
     double lacc[32];
 #pragma unroll
@@ -195,7 +196,7 @@ __device__ void ros_adjoint_warp(const RosParams& rp, const typename Model::Cons
       for (int j = 0; j < 5; ++j) {
         const bool on = j < is;
         ca[j] = on ? rp.A[is * (is - 1) / 2 + j] : 0.0;
-        cc[j] = on ? rp.C[is * (is - 1) / 2 + j] / (dDir * H) : 0.0;
+        cc[j] = on ? rp.C[is * (is - 1) / 2 + j] * inv_dH : 0.0;
       }
       Model::jt_mt_rows(JV, MV, x, [&](auto rc, double v, double h) {
         constexpr int r = decltype(rc)::value;

@@ -95,6 +95,8 @@ int fatode_ros_integrate_adj_batch(int model, int64_t ncells, int nvar, int np, 
  * the number of cells per wave (0 = automatic). */
 int fatode_set_tape_budget(uint64_t bytes);
 int fatode_set_wave_cells(int64_t cells);
+/* frees the device workspace (trajectory tape etc.) the engine caches between calls */
+int fatode_release_workspace(void);
 
 /* Per-call telemetry of the last batch call on this thread (kernel launches, waves, device time in
  * ms of each phase measured with CUDA events on the launch stream, tape bytes). */
