@@ -1,0 +1,167 @@
+!~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~
+!  fatode_b200_mod — ISO_C_BINDING shim that keeps FATODE's INTEGRATE / INTEGRATE_ADJ host API and
+!  forwards it to the B200 engine (include/fatode_b200.h).  Source only: the build image has no
+!  Fortran compiler; a maintainer compiles this next to the application and links libfatode_b200.so.
+!
+!  Replaces, for the registered example models:
+!     MODULE ROS_adj_f90_Integrator :: INTEGRATE_ADJ   (ADJ/ROS_ADJ/ROS_ADJ_f90_Integrator.F90:34)
+!     MODULE ROS_f90_Integrator     :: INTEGRATE       (FWD/ROS/ROS_f90_Integrator.F90:32)
+!  Dummy-argument names and order are the reference's, so keyword calls such as
+!     call integrate_adj(tin=tstart, tout=tend, nvar=nvar, nnzero=nnz, np=np, nadj=nadj, y=var, &
+!                        lambda=lambda, mu=mu, ..., fun=fun, jac=jac, ..., icntrl_u=icntrl)
+!  (EXAMPLES/cbm4/CBM4_ROS_ADJ/cbm4_ros_adj_dr.F90:282-287) compile unchanged.  The EXTERNAL callback
+!  arguments are accepted and ignored: the model is selected with fatode_b200_set_model(); the
+!  shipped models (roberts, small_strato, cbm4) run as device functions.
+!  Batched entry points (INTEGRATE_ADJ_BATCH / INTEGRATE_BATCH) take NCELLS systems at once:
+!  Y(NVAR,NCELLS), Lambda(NVAR,NADJ,NCELLS), Mu(NP,NADJ,NCELLS), ISTATUS(20,NCELLS), ... — the
+!  column-major Fortran layout is exactly the C ABI's [cell][nadj][nvar] layout.
+!~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~
+MODULE fatode_b200_mod
+  USE, INTRINSIC :: ISO_C_BINDING
+  IMPLICIT NONE
+  PRIVATE
+  PUBLIC :: INTEGRATE, INTEGRATE_ADJ, INTEGRATE_BATCH, INTEGRATE_ADJ_BATCH, fatode_b200_set_model
+  PUBLIC :: FATODE_MODEL_ROBERTS, FATODE_MODEL_SMALL_STRATO, FATODE_MODEL_CBM4
+
+  INTEGER(C_INT), PARAMETER :: FATODE_MODEL_ROBERTS = 1, FATODE_MODEL_SMALL_STRATO = 2, FATODE_MODEL_CBM4 = 3
+  INTEGER(C_INT), PARAMETER :: FATODE_MEM_HOST = 0
+  INTEGER(C_INT), SAVE :: current_model = FATODE_MODEL_CBM4
+
+  INTERFACE
+    FUNCTION fatode_ros_integrate_batch(model, ncells, nvar, y, tin, tout, atol, rtol, icntrl_u, rcntrl_u, &
+                                        istatus, rstatus, ierr, model_params, mem, stream) BIND(C, NAME='fatode_ros_integrate_batch')
+      IMPORT :: C_INT, C_INT64_T, C_DOUBLE, C_PTR
+      INTEGER(C_INT), VALUE :: model, nvar, mem
+      INTEGER(C_INT64_T), VALUE :: ncells
+      REAL(C_DOUBLE), VALUE :: tin, tout
+      REAL(C_DOUBLE) :: y(*), rstatus(*)
+      REAL(C_DOUBLE), INTENT(IN) :: atol(*), rtol(*)
+      TYPE(C_PTR), VALUE :: icntrl_u, rcntrl_u, model_params, stream
+      INTEGER(C_INT) :: istatus(*), ierr(*)
+      INTEGER(C_INT) :: fatode_ros_integrate_batch
+    END FUNCTION
+    FUNCTION fatode_ros_integrate_adj_batch(model, ncells, nvar, np, nadj, y, lambda, mu, tin, tout, atol_adj, rtol_adj, &
+                                            atol, rtol, icntrl_u, rcntrl_u, istatus, rstatus, ierr, mu_sum, model_params, &
+                                            mem, stream) BIND(C, NAME='fatode_ros_integrate_adj_batch')
+      IMPORT :: C_INT, C_INT64_T, C_DOUBLE, C_PTR
+      INTEGER(C_INT), VALUE :: model, nvar, np, nadj, mem
+      INTEGER(C_INT64_T), VALUE :: ncells
+      REAL(C_DOUBLE), VALUE :: tin, tout
+      REAL(C_DOUBLE) :: y(*), lambda(*), rstatus(*)
+      TYPE(C_PTR), VALUE :: mu, atol_adj, rtol_adj, icntrl_u, rcntrl_u, mu_sum, model_params, stream
+      REAL(C_DOUBLE), INTENT(IN) :: atol(*), rtol(*)
+      INTEGER(C_INT) :: istatus(*), ierr(*)
+      INTEGER(C_INT) :: fatode_ros_integrate_adj_batch
+    END FUNCTION
+  END INTERFACE
+
+CONTAINS
+
+  SUBROUTINE fatode_b200_set_model(model)
+    INTEGER, INTENT(IN) :: model
+    current_model = INT(model, C_INT)
+  END SUBROUTINE
+
+  !~~~> FWD/ROS INTEGRATE, one system (FWD/ROS/ROS_f90_Integrator.F90:32-33)
+  SUBROUTINE INTEGRATE( TIN, TOUT, N, NNZERO, VAR, RTOL, ATOL, FUN, JAC, ICNTRL_U, RCNTRL_U, ISTATUS_U, RSTATUS_U, IERR_U )
+    INTEGER, INTENT(IN) :: N, NNZERO
+    DOUBLE PRECISION, INTENT(INOUT) :: VAR(N)
+    DOUBLE PRECISION, INTENT(IN) :: RTOL(N), ATOL(N), TIN, TOUT
+    EXTERNAL :: FUN, JAC
+    INTEGER, INTENT(IN), OPTIONAL, TARGET :: ICNTRL_U(20)
+    DOUBLE PRECISION, INTENT(IN), OPTIONAL, TARGET :: RCNTRL_U(20)
+    INTEGER, INTENT(OUT), OPTIONAL :: ISTATUS_U(20), IERR_U
+    DOUBLE PRECISION, INTENT(OUT), OPTIONAL :: RSTATUS_U(20)
+    INTEGER(C_INT) :: ist(20), ierr(1), rc
+    REAL(C_DOUBLE) :: rst(20)
+    TYPE(C_PTR) :: pic, prc
+    pic = C_NULL_PTR; prc = C_NULL_PTR
+    IF (PRESENT(ICNTRL_U)) pic = C_LOC(ICNTRL_U)
+    IF (PRESENT(RCNTRL_U)) prc = C_LOC(RCNTRL_U)
+    rc = fatode_ros_integrate_batch(current_model, 1_C_INT64_T, INT(N, C_INT), VAR, TIN, TOUT, ATOL, RTOL, pic, prc, &
+                                    ist, rst, ierr, C_NULL_PTR, FATODE_MEM_HOST, C_NULL_PTR)
+    IF (rc /= 0) ierr(1) = rc
+    IF (PRESENT(ISTATUS_U)) ISTATUS_U(:) = ist(:)
+    IF (PRESENT(RSTATUS_U)) RSTATUS_U(:) = rst(:)
+    IF (PRESENT(IERR_U)) IERR_U = ierr(1)
+  END SUBROUTINE INTEGRATE
+
+  !~~~> ADJ/ROS_ADJ INTEGRATE_ADJ, one system (ADJ/ROS_ADJ/ROS_ADJ_f90_Integrator.F90:34-37)
+  SUBROUTINE INTEGRATE_ADJ( NVAR, NP, NADJ, NNZERO, Y, Lambda, Mu, TIN, TOUT, ATOL_adj, RTOL_adj, ATOL, RTOL, FUN, JAC, &
+                            ADJINIT, HESSTR_VEC, JACP, DRDY, DRDP, HESSTR_VEC_F_PY, HESSTR_VEC_R_PY, HESSTR_VEC_R, &
+                            ICNTRL_U, RCNTRL_U, ISTATUS_U, RSTATUS_U, Q, QFUN )
+    INTEGER, INTENT(IN) :: NVAR, NNZERO, NP, NADJ
+    DOUBLE PRECISION, INTENT(INOUT) :: Y(NVAR), Lambda(NVAR,NADJ)
+    DOUBLE PRECISION, INTENT(INOUT), OPTIONAL, TARGET :: Mu(NP,NADJ)
+    DOUBLE PRECISION, INTENT(INOUT), OPTIONAL :: Q(NADJ)
+    DOUBLE PRECISION, INTENT(IN) :: TIN, TOUT, ATOL_adj(NVAR,NADJ), RTOL_adj(NVAR,NADJ), ATOL(NVAR), RTOL(NVAR)
+    INTEGER, INTENT(IN), OPTIONAL, TARGET :: ICNTRL_U(20)
+    DOUBLE PRECISION, INTENT(IN), OPTIONAL, TARGET :: RCNTRL_U(20)
+    INTEGER, INTENT(OUT), OPTIONAL :: ISTATUS_U(20)
+    DOUBLE PRECISION, INTENT(OUT), OPTIONAL :: RSTATUS_U(20)
+    EXTERNAL FUN, JAC, ADJINIT, HESSTR_VEC
+    EXTERNAL QFUN, JACP, DRDY, DRDP, HESSTR_VEC_F_PY, HESSTR_VEC_R_PY, HESSTR_VEC_R
+    OPTIONAL QFUN, JACP, DRDY, DRDP, HESSTR_VEC_F_PY, HESSTR_VEC_R_PY, HESSTR_VEC_R
+    INTEGER(C_INT) :: ist(20), ierr(1), rc, npc
+    REAL(C_DOUBLE) :: rst(20)
+    TYPE(C_PTR) :: pic, prc, pmu
+    pic = C_NULL_PTR; prc = C_NULL_PTR; pmu = C_NULL_PTR; npc = 0
+    IF (PRESENT(ICNTRL_U)) pic = C_LOC(ICNTRL_U)
+    IF (PRESENT(RCNTRL_U)) prc = C_LOC(RCNTRL_U)
+    ! mode selection of the reference (:100-144): Mu is propagated only with NP>0, Mu, JACP and HESSTR_VEC_F_PY present
+    IF (NP > 0 .AND. PRESENT(Mu) .AND. PRESENT(JACP) .AND. PRESENT(HESSTR_VEC_F_PY)) THEN
+      pmu = C_LOC(Mu); npc = INT(NP, C_INT)
+    END IF
+    IF (PRESENT(Q) .AND. PRESENT(QFUN)) THEN
+      PRINT *, 'fatode_b200: quadrature cost terms (Q, QFUN) are not supported by the batched engine'
+      IF (PRESENT(ISTATUS_U)) ISTATUS_U(:) = 0
+      RETURN
+    END IF
+    rc = fatode_ros_integrate_adj_batch(current_model, 1_C_INT64_T, INT(NVAR, C_INT), npc, INT(NADJ, C_INT), Y, Lambda, pmu, &
+                                        TIN, TOUT, C_NULL_PTR, C_NULL_PTR, ATOL, RTOL, pic, prc, ist, rst, ierr, &
+                                        C_NULL_PTR, C_NULL_PTR, FATODE_MEM_HOST, C_NULL_PTR)
+    IF (rc /= 0) ierr(1) = rc
+    IF (ierr(1) < 0) PRINT *, 'RosenbrockADJ: Unsucessful step at T=', TIN, ' (IERR=', ierr(1), ')'   ! as :146-148
+    IF (PRESENT(ISTATUS_U)) ISTATUS_U(:) = ist(:)
+    IF (PRESENT(RSTATUS_U)) RSTATUS_U(:) = rst(:)
+  END SUBROUTINE INTEGRATE_ADJ
+
+  !~~~> batched forms: NCELLS independent systems in one call
+  SUBROUTINE INTEGRATE_BATCH( NCELLS, TIN, TOUT, N, VAR, RTOL, ATOL, ICNTRL_U, RCNTRL_U, ISTATUS_U, RSTATUS_U, IERR_U )
+    INTEGER, INTENT(IN) :: NCELLS, N
+    DOUBLE PRECISION, INTENT(INOUT) :: VAR(N,NCELLS)
+    DOUBLE PRECISION, INTENT(IN) :: RTOL(N), ATOL(N), TIN, TOUT
+    INTEGER, INTENT(IN), TARGET :: ICNTRL_U(20)
+    DOUBLE PRECISION, INTENT(IN), TARGET :: RCNTRL_U(20)
+    INTEGER, INTENT(OUT) :: ISTATUS_U(20,NCELLS), IERR_U(NCELLS)
+    DOUBLE PRECISION, INTENT(OUT) :: RSTATUS_U(20,NCELLS)
+    INTEGER(C_INT) :: rc
+    rc = fatode_ros_integrate_batch(current_model, INT(NCELLS, C_INT64_T), INT(N, C_INT), VAR, TIN, TOUT, ATOL, RTOL, &
+                                    C_LOC(ICNTRL_U), C_LOC(RCNTRL_U), ISTATUS_U, RSTATUS_U, IERR_U, C_NULL_PTR, &
+                                    FATODE_MEM_HOST, C_NULL_PTR)
+    IF (rc /= 0) IERR_U(:) = rc
+  END SUBROUTINE INTEGRATE_BATCH
+
+  SUBROUTINE INTEGRATE_ADJ_BATCH( NCELLS, NVAR, NP, NADJ, Y, Lambda, Mu, TIN, TOUT, ATOL, RTOL, ICNTRL_U, RCNTRL_U, &
+                                  ISTATUS_U, RSTATUS_U, IERR_U, Mu_sum )
+    INTEGER, INTENT(IN) :: NCELLS, NVAR, NP, NADJ
+    DOUBLE PRECISION, INTENT(INOUT) :: Y(NVAR,NCELLS), Lambda(NVAR,NADJ,NCELLS)
+    DOUBLE PRECISION, INTENT(INOUT), TARGET :: Mu(NP,NADJ,NCELLS)
+    DOUBLE PRECISION, INTENT(IN) :: TIN, TOUT, ATOL(NVAR), RTOL(NVAR)
+    INTEGER, INTENT(IN), TARGET :: ICNTRL_U(20)
+    DOUBLE PRECISION, INTENT(IN), TARGET :: RCNTRL_U(20)
+    INTEGER, INTENT(OUT) :: ISTATUS_U(20,NCELLS), IERR_U(NCELLS)
+    DOUBLE PRECISION, INTENT(OUT) :: RSTATUS_U(20,NCELLS)
+    DOUBLE PRECISION, INTENT(OUT), OPTIONAL, TARGET :: Mu_sum(NP,NADJ)
+    INTEGER(C_INT) :: rc
+    TYPE(C_PTR) :: psum
+    psum = C_NULL_PTR
+    IF (PRESENT(Mu_sum)) psum = C_LOC(Mu_sum)
+    rc = fatode_ros_integrate_adj_batch(current_model, INT(NCELLS, C_INT64_T), INT(NVAR, C_INT), INT(NP, C_INT), &
+                                        INT(NADJ, C_INT), Y, Lambda, C_LOC(Mu), TIN, TOUT, C_NULL_PTR, C_NULL_PTR, ATOL, RTOL, &
+                                        C_LOC(ICNTRL_U), C_LOC(RCNTRL_U), ISTATUS_U, RSTATUS_U, IERR_U, psum, C_NULL_PTR, &
+                                        FATODE_MEM_HOST, C_NULL_PTR)
+    IF (rc /= 0) IERR_U(:) = rc
+  END SUBROUTINE INTEGRATE_ADJ_BATCH
+
+END MODULE fatode_b200_mod
