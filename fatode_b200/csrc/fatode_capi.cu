@@ -25,6 +25,7 @@
 #include "model_cbm4.cuh"
 #include "ros_warp_fwd.cuh"
 #include "ros_warp_adj.cuh"
+#include "ros_warp_adj2.cuh"
 
 using namespace fatode;
 
@@ -219,6 +220,100 @@ k_ros_adj(RosParams rp, typename Model::Const mc, long ncells, int nadj, int wit
   }
 }
 
+
+// Second-generation backward kernel: producer/consumer warp pairs, TMEM-resident running sums (ros_warp_adj2.cuh)
+template <class Model>
+__global__ void __launch_bounds__(ADJ2_THREADS, 1)
+k_ros_adj2(RosParams rp, typename Model::Const mc, long ncells, int nadj, int with_mu, const double* __restrict__ tape,
+           const long long* __restrict__ tape_off, const int* __restrict__ ierr, const double* __restrict__ y_final,
+           double* __restrict__ lambda, double* __restrict__ mu, int* __restrict__ istatus,
+           unsigned long long* __restrict__ queue, long slab_cap, const int* __restrict__ nacc) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ uint32_t tmem_base_s;
+  typedef Adj2Smem<Model> L;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = warp & 3;
+  const bool producer = warp >= 4;
+  if (warp == 0) tmem::alloc512(&tmem_base_s);
+  tmem::fence_before_sync();
+  __syncthreads();
+  tmem::fence_after_sync();
+  const uint32_t tm = tmem_base_s + ((uint32_t)(slot * 32) << 16);
+  double* sm = smem + (size_t)slot * L::DOUBLES;
+  volatile long long* ctrl = reinterpret_cast<volatile long long*>(sm + L::OFF_CTRL);
+  const int S = rp.S;
+  const int NE = tape_entry_doubles(S, 32);
+  if (producer) Model::init(sm + L::OFF_MODEL, mc, lane);
+  for (;;) {
+    if (producer && lane == 0) {
+      long long c = (long long)atomicAdd(queue, 1ull);
+      while (c < ncells && ierr[c] != 1) c = (long long)atomicAdd(queue, 1ull);
+      ctrl[0] = (c < ncells) ? c : -1;
+    }
+    pair_barrier(slot);
+    const long long c = ctrl[0];
+    if (c < 0) break;
+    const long long off = slab_cap > 0 ? c * slab_cap : tape_off[c];
+    const int nsteps = slab_cap > 0 ? nacc[c] : (int)(tape_off[c + 1] - tape_off[c]);
+    const double* ent0 = tape + off * NE;
+    const int n_items = nsteps * S;
+    if (!producer) {   // ADJINIT (model routine): lane = adjoint column m
+      double lam[32], m0[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) lam[i] = Model::adjinit_lambda(i, lane, y_final[c * 32 + i]);
+#pragma unroll
+      for (int p = 0; p < 32; ++p) m0[p] = 0.0;
+      tmem::st32(tm + TM_LAM, lam);
+      tmem::st32(tm + TM_MU, m0);
+      tmem::wait_st();
+    } else if (n_items > 0) {
+      adj2_produce<Model>(rp, sm, ent0 + (long)(nsteps - 1) * NE, S - 1, 0, 0, with_mu != 0, lane);
+    }
+    pair_barrier(slot);
+    for (int t = 0; t < n_items; ++t) {
+      if (!producer) {
+        const int si = t / S;
+        adj2_consume<Model>(rp, sm, S - 1 - (t - si * S), si & 1, t & 1, with_mu != 0, tm);
+      } else if (t + 1 < n_items) {
+        const int t1 = t + 1;
+        const int si = t1 / S;
+        adj2_produce<Model>(rp, sm, ent0 + (long)(nsteps - 1 - si) * NE, S - 1 - (t1 - si * S), si & 1, t1 & 1, with_mu != 0, lane);
+      }
+      pair_barrier(slot);
+    }
+    if (!producer) {   // results: column m of Lambda / Mu is this lane's private vector
+      tmem::wait_st();
+      {
+        double lam[32];
+        tmem::ld32(tm + TM_LAM, lam);   // .sync.aligned: executed by the whole warp, outside any lane-dependent branch
+        if (lane < nadj) {
+          double* dst = lambda + ((long)c * nadj + lane) * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) *reinterpret_cast<double2*>(dst + i) = make_double2(lam[i], lam[i + 1]);
+        }
+      }
+      if (with_mu) {
+        double m0[32];
+        tmem::ld32(tm + TM_MU, m0);
+        if (lane < nadj) {
+          double* dst = mu + ((long)c * nadj + lane) * Model::NP;
+#pragma unroll
+          for (int p = 0; p < Model::NP; ++p) dst[p] = m0[p];
+        }
+      }
+      if (lane == 0) {   // counters of the backward sweep (ADJ :1257-1267, :1303, :1312, :1381)
+        int* is_ = istatus + c * 20;
+        is_[Nstp] += nsteps;
+        is_[Njac] += nsteps * (2 + S + (rp.autonomous ? 0 : 1));
+        is_[Ndec] += nsteps;
+        is_[Nsol] += nsteps * S * nadj;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tmem::dealloc512(tmem_base_s);
+}
+
 // deterministic sum of mu over cells: stage 1 partial sums over fixed cell blocks, stage 2 over blocks
 __global__ void k_mu_reduce1(long ncells, int len, const double* __restrict__ mu, const int* __restrict__ ierr,
                              double* __restrict__ partial, int cells_per_block) {
@@ -373,14 +468,26 @@ static int ros_adj_device(const RosParams& rp, const typename Model::Const& mc, 
   PhaseTimer tm(st);
   std::memset(&g_stats, 0, sizeof g_stats);
 
+  static const int adj_kernel = getenv("FATODE_ADJ_KERNEL") ? atoi(getenv("FATODE_ADJ_KERNEL")) : 2;
+  const size_t adj2_smem = sizeof(double) * (size_t)Adj2Smem<Model>::DOUBLES * ADJ2_SLOTS;
+  if (adj_kernel == 2)
+    CUDA_TRY(cudaFuncSetAttribute(k_ros_adj2<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj2_smem));
   auto launch_adjoint = [&](int64_t c0, int64_t n, long slab_cap) -> int {
     CUDA_TRY(cudaMemsetAsync(d_queue, 0, sizeof(unsigned long long), st));
-    const int ablocks = (int)std::min<int64_t>(sms, (n + ADJ_WARPS - 1) / ADJ_WARPS);
     tm.start();
+    if (adj_kernel == 2 && rp.S >= 2) {
+      const int ablocks = (int)std::min<int64_t>(sms, (n + ADJ2_SLOTS - 1) / ADJ2_SLOTS);
+      k_ros_adj2<Model><<<ablocks, ADJ2_THREADS, adj2_smem, st>>>(
+          rp, mc, n, nadj, with_mu ? 1 : 0, b_tape.as<double>(), b_off.as<long long>(), d_ierr + c0, d_y + c0 * 32,
+          d_lambda + c0 * nadj * 32, with_mu ? d_mu + c0 * nadj * Model::NP : nullptr, d_istatus + c0 * 20, d_queue,
+          slab_cap, b_nacc.as<int>());
+    } else {
+    const int ablocks = (int)std::min<int64_t>(sms, (n + ADJ_WARPS - 1) / ADJ_WARPS);
     k_ros_adj<Model><<<ablocks, ADJ_WARPS * 32, adj_smem, st>>>(
         rp, mc, n, nadj, with_mu ? 1 : 0, b_tape.as<double>(), b_off.as<long long>(), d_ierr + c0, d_y + c0 * 32,
         d_lambda + c0 * nadj * 32, with_mu ? d_mu + c0 * nadj * Model::NP : nullptr, d_istatus + c0 * 20, d_queue,
         adj_per_warp, slab_cap, b_nacc.as<int>());
+    }
     CUDA_TRY(cudaGetLastError());
     g_stats.ms_adjoint += tm.stop();
     g_stats.launches++;

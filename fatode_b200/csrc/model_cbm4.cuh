@@ -172,6 +172,11 @@ struct Cbm4Warp {
   __device__ __forceinline__ static void jt_mt_rows(const double* Jv, const double* Mv, const double (&x)[32], F&& f) {
     cbm4_dev::jt_mt_rows(Jv, Mv, x, f);
   }
+  __device__ __forceinline__ static void jt_vec(const double* Jv, const double (&x)[32], double (&v)[32]) {
+    cbm4_dev::jt_vec(Jv, x, v);
+  }
+  template <class F>
+  __device__ __forceinline__ static void mt_rows(const double* Mv, const double (&x)[32], F&& f) { cbm4_dev::mt_rows(Mv, x, f); }
   template <class F>
   __device__ __forceinline__ static void stoich_cols(const double (&x)[32], F&& f) { cbm4_dev::stoich_cols(x, f); }
   // adjinit (dr.F90:101-117): Lambda = I, Mu = 0

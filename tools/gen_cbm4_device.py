@@ -331,6 +331,32 @@ def main():
         w(f"    f(IC<{r}>(), v, h);")
         w("  }")
     w("}")
+    w("// v = J^T x as a register vector (static indices), and rows of h = M'^T x through a callback")
+    w("__device__ __forceinline__ void jt_vec(const double* __restrict__ Jv, const double (&x)[32], double (&v)[32]) {")
+    je = 0
+    for r in range(N):
+        terms = []
+        while je < NJ and jent[je][1] == r:
+            terms.append((je, jent[je][0]))
+            je += 1
+        # two partial sums per row shorten the dependent FMA chain
+        w(f"  {{ double a0 = 0.0, a1 = 0.0;")
+        for t, (e, k) in enumerate(terms):
+            w(f"    a{t % 2} = fma(Jv[{e}], x[{k}], a{t % 2});")
+        w(f"    v[{r}] = a0 + a1; }}")
+    w("}")
+    w("template <class F> __device__ __forceinline__ void mt_rows(const double* __restrict__ Mv, const double (&x)[32], F&& f) {")
+    me = 0
+    for r in range(N):
+        terms = []
+        while me < NM and mpat[me][1] == r:
+            terms.append((me, mpat[me][0]))
+            me += 1
+        w(f"  {{ double a0 = 0.0, a1 = 0.0;")
+        for t, (e, k) in enumerate(terms):
+            w(f"    a{t % 2} = fma(Mv[{e}], x[{k}], a{t % 2});")
+        w(f"    f(IC<{r}>(), a0 + a1); }}")
+    w("}")
     w("// s_p = sum_r STOICM(r, JCOEFF[p]) * x_r  (column p of the stoichiometric matrix; REAL(4) literals)")
     w("template <class F> __device__ __forceinline__ void stoich_cols(const double (&x)[32], F&& f) {")
     nst = 0
