@@ -7,7 +7,7 @@
 //     2. k_scan_offsets         exclusive prefix sum of the counts -> exact tape offsets
 //     3. k_ros_fwd<TAPE=true>   the same sweep again (bit-identical by construction), writing
 //                               (T,H,Ystage,K) per accepted step at the cell's offset
-//     4. k_ros_adj              backward sweep, persistent warps pulling cells from an atomic queue
+//     4. k_ros_adj2             backward sweep, persistent producer/consumer warp pairs pulling cells from an atomic queue
 //   then one deterministic two-stage reduction of Mu over cells (k_mu_reduce*).
 // There is no CPU path: every failure to reach the GPU is reported as an error.
 #include <cuda_runtime.h>
@@ -96,7 +96,6 @@ extern "C" int fatode_model_initial_state(int model, double* y) {
 // kernels
 
 constexpr int FWD_WARPS = 4;
-constexpr int ADJ_WARPS = 3;
 
 template <class Model>
 __host__ __device__ constexpr int fwd_ws_doubles() { return FwdSmem<Model>::DOUBLES; }
@@ -181,47 +180,7 @@ __global__ void k_scan_offsets(long ncells, const int* __restrict__ nacc, const 
   if (threadIdx.x == 0) off[ncells] = carry;
 }
 
-template <class Model>
-__global__ void __launch_bounds__(ADJ_WARPS * 32, 1)
-k_ros_adj(RosParams rp, typename Model::Const mc, long ncells, int nadj, int with_mu, const double* __restrict__ tape,
-          const long long* __restrict__ tape_off, const int* __restrict__ ierr, const double* __restrict__ y_final,
-          double* __restrict__ lambda, double* __restrict__ mu, int* __restrict__ istatus,
-          unsigned long long* __restrict__ queue, int smem_per_warp, long slab_cap, const int* __restrict__ nacc) {
-  extern __shared__ __align__(16) double smem[];
-  typedef AdjSmem<Model> L;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* sm = smem + (size_t)warp * smem_per_warp;
-  const int NE = tape_entry_doubles(rp.S, 32);
-  for (;;) {
-    unsigned long long c = 0;
-    if (lane == 0) c = atomicAdd(queue, 1ull);
-    c = __shfl_sync(FATODE_FULL_MASK, c, 0);
-    if (c >= (unsigned long long)ncells) break;
-    if (ierr[c] != 1) continue;
-    const long long off = slab_cap > 0 ? (long long)c * slab_cap : tape_off[c];
-    const int nsteps = slab_cap > 0 ? nacc[c] : (int)(tape_off[c + 1] - tape_off[c]);
-    const double yf = y_final[c * 32 + lane];
-    ros_adjoint_warp<Model>(rp, mc, sm, tape + off * NE, nsteps, nadj, with_mu != 0, yf, lane);
-    __syncwarp();
-    const double* LAM = sm + L::OFF_LAM;
-    const double* MU = sm + L::OFF_MU;
-    for (int m = 0; m < nadj; ++m) {
-      lambda[((long)c * nadj + m) * 32 + lane] = LAM[lane * 32 + m];
-      if (with_mu && lane < Model::NP) mu[((long)c * nadj + m) * Model::NP + lane] = MU[lane * 32 + m];
-    }
-    if (lane == 0) {   // counters of the backward sweep (ADJ :1257-1267, :1303, :1312, :1381)
-      int* is = istatus + c * 20;
-      is[Nstp] += nsteps;
-      is[Njac] += nsteps * (2 + rp.S + (rp.autonomous ? 0 : 1));
-      is[Ndec] += nsteps;
-      is[Nsol] += nsteps * rp.S * nadj;
-    }
-    __syncwarp();
-  }
-}
-
-
-// Second-generation backward kernel: producer/consumer warp pairs, TMEM-resident running sums (ros_warp_adj2.cuh)
+// Backward kernel: producer/consumer warp pairs, TMEM-resident running sums (ros_warp_adj2.cuh)
 template <class Model>
 __global__ void __launch_bounds__(ADJ2_THREADS, 1)
 k_ros_adj2(RosParams rp, typename Model::Const mc, long ncells, int nadj, int with_mu, const double* __restrict__ tape,
@@ -441,12 +400,9 @@ static int ros_adj_device(const RosParams& rp, const typename Model::Const& mc, 
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const size_t fwd_smem = sizeof(double) * fwd_ws_doubles<Model>() * FWD_WARPS;
-  const int adj_per_warp = AdjSmem<Model>::doubles(rp.S);
-  const size_t adj_smem = sizeof(double) * (size_t)adj_per_warp * ADJ_WARPS;
   CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd<Model, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
   CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd<Model, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
   CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd<Model, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
-  CUDA_TRY(cudaFuncSetAttribute(k_ros_adj<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem));
 
   size_t free_b = 0, total_b = 0;
   CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
@@ -468,26 +424,16 @@ static int ros_adj_device(const RosParams& rp, const typename Model::Const& mc, 
   PhaseTimer tm(st);
   std::memset(&g_stats, 0, sizeof g_stats);
 
-  static const int adj_kernel = getenv("FATODE_ADJ_KERNEL") ? atoi(getenv("FATODE_ADJ_KERNEL")) : 2;
   const size_t adj2_smem = sizeof(double) * (size_t)Adj2Smem<Model>::DOUBLES * ADJ2_SLOTS;
-  if (adj_kernel == 2)
-    CUDA_TRY(cudaFuncSetAttribute(k_ros_adj2<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj2_smem));
+  CUDA_TRY(cudaFuncSetAttribute(k_ros_adj2<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj2_smem));
   auto launch_adjoint = [&](int64_t c0, int64_t n, long slab_cap) -> int {
     CUDA_TRY(cudaMemsetAsync(d_queue, 0, sizeof(unsigned long long), st));
     tm.start();
-    if (adj_kernel == 2 && rp.S >= 2) {
-      const int ablocks = (int)std::min<int64_t>(sms, (n + ADJ2_SLOTS - 1) / ADJ2_SLOTS);
-      k_ros_adj2<Model><<<ablocks, ADJ2_THREADS, adj2_smem, st>>>(
-          rp, mc, n, nadj, with_mu ? 1 : 0, b_tape.as<double>(), b_off.as<long long>(), d_ierr + c0, d_y + c0 * 32,
-          d_lambda + c0 * nadj * 32, with_mu ? d_mu + c0 * nadj * Model::NP : nullptr, d_istatus + c0 * 20, d_queue,
-          slab_cap, b_nacc.as<int>());
-    } else {
-    const int ablocks = (int)std::min<int64_t>(sms, (n + ADJ_WARPS - 1) / ADJ_WARPS);
-    k_ros_adj<Model><<<ablocks, ADJ_WARPS * 32, adj_smem, st>>>(
+    const int ablocks = (int)std::min<int64_t>(sms, (n + ADJ2_SLOTS - 1) / ADJ2_SLOTS);
+    k_ros_adj2<Model><<<ablocks, ADJ2_THREADS, adj2_smem, st>>>(
         rp, mc, n, nadj, with_mu ? 1 : 0, b_tape.as<double>(), b_off.as<long long>(), d_ierr + c0, d_y + c0 * 32,
         d_lambda + c0 * nadj * 32, with_mu ? d_mu + c0 * nadj * Model::NP : nullptr, d_istatus + c0 * 20, d_queue,
-        adj_per_warp, slab_cap, b_nacc.as<int>());
-    }
+        slab_cap, b_nacc.as<int>());
     CUDA_TRY(cudaGetLastError());
     g_stats.ms_adjoint += tm.stop();
     g_stats.launches++;
@@ -755,8 +701,10 @@ __global__ void k_probe_model(typename Model::Const mc, double t, const double* 
   Model::jac(ws, jv, lane);
   Model::template scatter_E<LDA>(jv, 0.0, tile, lane);     // tile = -J (column-major)
   for (int j = 0; j < 32; ++j) jac_dense[j * 32 + lane] = -tile[j * LDA + lane];
-  Model::hess(ws, ws + Model::OFF_OUT, lane);
-  for (int h = lane; h < Model::NHESS; h += 32) hess[h] = ws[Model::OFF_OUT + h];
+  __syncwarp();
+  double* hs = tile;   // the tile is free again
+  Model::hess(ws, hs, lane);
+  for (int h = lane; h < Model::NHESS; h += 32) hess[h] = hs[h];
 }
 
 __global__ void k_probe_lu(const double* A /*col-major 32x32*/, const double* b, double* lu_out /*row-major logical*/,
@@ -767,11 +715,12 @@ __global__ void k_probe_lu(const double* A /*col-major 32x32*/, const double* b,
   for (int j = 0; j < 32; ++j) tile[j * LDA + lane] = A[j * 32 + lane];
   __syncwarp();
   int pos;
-  int inf = warp_lu_factor(tile, who, pos, lane);
+  LUMasks mk;
+  int inf = warp_lu_factor(tile, who, pos, lane, &mk);
   for (int j = 0; j < 32; ++j) lu_out[pos * 32 + j] = tile[j * LDA + lane];
   ipiv_who[lane] = who[lane];
   if (lane == 0) *info = inf;
-  x[lane] = warp_lu_solve(tile, who, pos, b[lane], lane);
+  x[lane] = warp_lu_solve(tile, who, pos, mk, b[lane], lane);
 }
 
 extern "C" int fatode_probe_cbm4(double t, const double* y, double* f, double* jac_dense, double* hess) {

@@ -30,8 +30,8 @@ struct Cbm4Warp {
   static constexpr int OFF_YB = 0;      // [36]  operands: V(0..31), F(1), 1.0, 2.0
   static constexpr int OFF_RC = 36;     // [84]  rate coefficients at the current time
   static constexpr int OFF_P = 120;     // [160] level-1 products
-  static constexpr int OFF_OUT = 280;   // [288] level-2 results (Vdot / JV / HESS)
-  static constexpr int WS_DOUBLES = 568;
+  static constexpr int OFF_T = 280;     // [354] level-2 products sc*P (+ zero sentinel)
+  static constexpr int WS_DOUBLES = 634;
   typedef Cbm4Const Const;
 
   // Update_SUN, cbm4_Parameters.F90:196-220
@@ -83,15 +83,50 @@ struct Cbm4Warp {
     }
     __syncwarp();
   }
+  // level 2, part 1: all products TERM_k = sc_k * P[src_k], 32 per round (independent -> fully parallel)
+  template <int NTPAD>
+  __device__ static void eval_terms(const cbm4_dev::TermSP* __restrict__ tab, const double* P, double* T, int lane) {
+#pragma unroll
+    for (int b = 0; b < NTPAD; b += 32) {
+      cbm4_dev::TermSP e = tab[b + lane];
+      T[b + lane] = __dmul_rn(e.sc, *reinterpret_cast<const double*>(reinterpret_cast<const char*>(P) + e.off));
+    }
+    if (lane == 0) T[NTPAD] = 0.0;   // sentinel used by padded slots
+    __syncwarp();
+  }
+  // level 2, part 2: ordered sums (the Fortran's textual order).  One output per lane, kept in a register.
   template <int NITER>
-  __device__ static void eval_l2(const cbm4_dev::L2* __restrict__ tab, const double* P, double* out, int lane) {
+  __device__ static double sum_fixed(const ushort4* __restrict__ tab, const double* T, int lane) {
     double acc = 0.0;
-#pragma unroll 10
-    for (int it = 0; it < NITER; ++it) {
-      cbm4_dev::L2 e = tab[it * 32 + lane];
-      double term = __dmul_rn(e.sc, P[e.src]);
-      acc = e.first ? term : __dadd_rn(acc, term);
-      if (e.last) out[e.out] = acc;
+#pragma unroll
+    for (int q = 0; q < NITER / 4; ++q) {
+      const ushort4 w = tab[q * 32 + lane];
+      acc = __dadd_rn(acc, T[w.x]);
+      acc = __dadd_rn(acc, T[w.y]);
+      acc = __dadd_rn(acc, T[w.z]);
+      acc = __dadd_rn(acc, T[w.w]);
+    }
+    return acc;
+  }
+  // several outputs per lane: bit 15 marks the last term of an output; ACCUM adds to out[] instead of storing
+  template <int NITER, bool ACCUM>
+  __device__ static void sum_multi(const ushort4* __restrict__ tab, const unsigned short* __restrict__ outmap, const double* T,
+                                   double* out, int lane) {
+    double acc = 0.0;
+    int n = 0;
+    auto step = [&](unsigned v) {
+      acc = __dadd_rn(acc, T[v & 0x3fffu]);
+      if (v & 0x8000u) {
+        const int o = outmap[n * 32 + lane];
+        if (ACCUM) out[o] += acc; else out[o] = acc;
+        acc = 0.0;
+        ++n;
+      }
+    };
+#pragma unroll
+    for (int q = 0; q < NITER / 4; ++q) {
+      const ushort4 w = tab[q * 32 + lane];
+      step(w.x); step(w.y); step(w.z); step(w.w);
     }
     __syncwarp();
   }
@@ -99,15 +134,20 @@ struct Cbm4Warp {
   // fun (dr.F90:83-98): returns component `lane` of f(t, y); set_time/set_y must have been called
   __device__ static double fun(double* ws, const Const& mc, int lane) {
     eval_l1<cbm4_dev::FUN_L1_NPAD>(cbm4_dev::FUN_L1_TAB, ws, ws + OFF_P, lane);
-    eval_l2<cbm4_dev::FUN_L2_NITER>(cbm4_dev::FUN_L2_TAB, ws + OFF_P, ws + OFF_OUT, lane);
-    double f = ws[OFF_OUT + lane];
+    eval_terms<cbm4_dev::FUN_L2_NTPAD>(cbm4_dev::FUN_L2_TERM, ws + OFF_P, ws + OFF_T, lane);
+    double f = sum_fixed<cbm4_dev::FUN_L2_NITER>(cbm4_dev::FUN_L2_SUM, ws + OFF_T, lane);
+    __syncwarp();
     if (lane == 30 || lane == 25) f = __dadd_rn(f, mc.emis);
     return f;
   }
   // jac (dr.F90:69-80): the 276 structural entries, order (col,row) = cbm4_dev::JAC_COL/JAC_ROW
   __device__ static void jac(double* ws, double* jv, int lane) {
+    static_assert(cbm4_dev::JAC_L2_NG == 2, "generator emitted a different number of JAC groups");
     eval_l1<cbm4_dev::JAC_L1_NPAD>(cbm4_dev::JAC_L1_TAB, ws, ws + OFF_P, lane);
-    eval_l2<cbm4_dev::JAC_L2_NITER>(cbm4_dev::JAC_L2_TAB, ws + OFF_P, jv, lane);
+    eval_terms<cbm4_dev::JAC_L20_NTPAD>(cbm4_dev::JAC_L20_TERM, ws + OFF_P, ws + OFF_T, lane);
+    sum_multi<cbm4_dev::JAC_L20_NITER, false>(cbm4_dev::JAC_L20_SUM, cbm4_dev::JAC_L20_OUT, ws + OFF_T, jv, lane);
+    eval_terms<cbm4_dev::JAC_L21_NTPAD>(cbm4_dev::JAC_L21_TERM, ws + OFF_P, ws + OFF_T, lane);
+    sum_multi<cbm4_dev::JAC_L21_NITER, false>(cbm4_dev::JAC_L21_SUM, cbm4_dev::JAC_L21_OUT, ws + OFF_T, jv, lane);
   }
   // dense scatter of E = ghinv*I - J into a column-major 32x32 tile with leading dimension LD (for the LU)
   template <int LD>
@@ -125,26 +165,36 @@ struct Cbm4Warp {
   }
   // Hessian(T) (:1190-1853): HESS depends on the rate coefficients only (bimolecular mechanism)
   __device__ static void hess(double* ws, double* hs, int lane) {
+    static_assert(cbm4_dev::HES_L2_NG == 1, "generator emitted a different number of HESS groups");
     eval_l1<cbm4_dev::HES_L1_NPAD>(cbm4_dev::HES_L1_TAB, ws, ws + OFF_P, lane);
-    eval_l2<cbm4_dev::HES_L2_NITER>(cbm4_dev::HES_L2_TAB, ws + OFF_P, hs, lane);
+    eval_terms<cbm4_dev::HES_L20_NTPAD>(cbm4_dev::HES_L20_TERM, ws + OFF_P, ws + OFF_T, lane);
+    sum_multi<cbm4_dev::HES_L20_NITER, false>(cbm4_dev::HES_L20_SUM, cbm4_dev::HES_L20_OUT, ws + OFF_T, hs, lane);
   }
   // M'[e] = sum_t HESS[h]*K[c]  +  hg * dJdt[e]   on pattern(M) U time-dependent J entries.
   // (CBM4_HessTR_Vec regrouped: HTU = M^T U1;  non-autonomous term ADJ :1377-1403 folded per stage)
-  __device__ static void build_M(const double* hs, const double* kb, const double* djdt, double hg, double* mv, int lane) {
+  template <int NTPAD>
+  __device__ static void mat_terms(const ushort2* __restrict__ tab, const double* hs, const double* kb, double* T, int lane) {
+#pragma unroll
+    for (int b = 0; b < NTPAD; b += 32) {
+      const ushort2 e = tab[b + lane];
+      T[b + lane] = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(hs) + e.x) *
+                    *reinterpret_cast<const double*>(reinterpret_cast<const char*>(kb) + e.y);
+    }
+    if (lane == 0) T[NTPAD] = 0.0;
+    __syncwarp();
+  }
+  __device__ static void build_M(double* ws, const double* hs, const double* kb, const double* djdt, double hg, double* mv,
+                                 int lane) {
+    static_assert(cbm4_dev::MAT_L2_NG == 2, "generator emitted a different number of M groups");
     for (int e = lane; e < NM; e += 32) {
       int jt = cbm4_dev::MAT_JT[e];
       mv[e] = (jt >= 0) ? hg * djdt[jt] : 0.0;
     }
     __syncwarp();
-    double acc = 0.0;
-#pragma unroll
-    for (int it = 0; it < cbm4_dev::MAT_L2_NITER; ++it) {
-      cbm4_dev::L2 e = cbm4_dev::MAT_L2_TAB[it * 32 + lane];
-      double term = hs[e.src] * kb[(int)e.sc];
-      acc = e.first ? term : acc + term;
-      if (e.last) mv[e.out] += acc;
-    }
-    __syncwarp();
+    mat_terms<cbm4_dev::MAT_L20_NTPAD>(cbm4_dev::MAT_L20_TERM, hs, kb, ws + OFF_T, lane);
+    sum_multi<cbm4_dev::MAT_L20_NITER, true>(cbm4_dev::MAT_L20_SUM, cbm4_dev::MAT_L20_OUT, ws + OFF_T, mv, lane);
+    mat_terms<cbm4_dev::MAT_L21_NTPAD>(cbm4_dev::MAT_L21_TERM, hs, kb, ws + OFF_T, lane);
+    sum_multi<cbm4_dev::MAT_L21_NITER, true>(cbm4_dev::MAT_L21_SUM, cbm4_dev::MAT_L21_OUT, ws + OFF_T, mv, lane);
   }
   // ap[p] = ARP_p(Y_i)  (dFun_dRcoeff :1135-1175)  +  aj_p(Y0, K_i) (dJac_dRcoeff :2330-2380)
   // yb must hold Y_i when arp is evaluated and Y0 when aj is evaluated -> two calls

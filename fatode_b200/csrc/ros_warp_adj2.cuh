@@ -30,8 +30,8 @@ template <class Model>
 struct Adj2Smem {
   // per-slot layout in doubles
   static constexpr int OFF_MODEL = 0;                                   // producer: model scratch (HESS in its L2 area)
-  static constexpr int OFF_HS = Model::OFF_OUT;
-  static constexpr int OFF_DJ = Model::WS_DOUBLES;                      // [32]
+  static constexpr int OFF_HS = Model::WS_DOUBLES;                      // [NHESS] Hessian(T) of the current step
+  static constexpr int OFF_DJ = OFF_HS + ((Model::NHESS + 1) / 2) * 2;  // [32]
   static constexpr int OFF_KB = OFF_DJ + 32;                            // [32]
   static constexpr int OFF_J0 = OFF_KB + 32;                            // [288] J(T,Y0)
   static constexpr int OFF_JD = OFF_J0 + 288;                           // [288] J(T+Delta,Y0)
@@ -114,7 +114,7 @@ __device__ __forceinline__ void adj2_produce(const RosParams& rp, double* sm, co
   if (with_mu) ap += Model::aj(ws, KB, lane);
   STG[L::STG_AP + lane] = ap;
   const double hg = rp.autonomous ? 0.0 : H * rp.Gamma[is];
-  Model::build_M(HS, KB, DJ, hg, STG + L::STG_MV, lane);
+  Model::build_M(ws, HS, KB, DJ, hg, STG + L::STG_MV, lane);
   {
     const bool ident = __all_sync(FATODE_FULL_MASK, WHO[lane] == lane);
     if (lane == 0) {

@@ -40,14 +40,22 @@ __device__ __forceinline__ int warp_argmax_abs(double v, int key, bool active) {
   return __ffs(__ballot_sync(FATODE_FULL_MASK, win)) - 1;
 }
 
+// Column-occupancy masks of the factors: bit k of lnz / unz is set when column k of L (below the diagonal) /
+// of U (above the diagonal) holds a non-zero.  The triangular sweeps skip empty columns — netlib's DTRSM
+// would add exact zeros there — and for CBM-IV about half of U's columns are empty.
+struct LUMasks { unsigned lnz, unz; };
+
 // DGETF2 on the shared-memory tile A (column-major, ld = LDA, lane = physical row).
 // Outputs: pos (per lane), who[0..31] in shared memory; returns INFO (0 or first zero pivot, 1-based).
-__device__ __forceinline__ int warp_lu_factor(double* __restrict__ A, int* __restrict__ who, int& pos, int lane) {
+__device__ __forceinline__ int warp_lu_factor(double* __restrict__ A, int* __restrict__ who, int& pos, int lane,
+                                              LUMasks* masks = nullptr) {
   const double sfmin = DBL_MIN;   // DLAMCH('S') for IEEE double (1/huge < tiny)
   pos = lane;
   int info = 0;
+  unsigned lnz = 0, unz = 0;
   for (int k = 0; k < 32; ++k) {
     const double v = A[k * LDA + lane];
+    if (__ballot_sync(FATODE_FULL_MASK, pos < k && v != 0.0)) unz |= 1u << k;   // column k of U is final here
     const int p = warp_argmax_abs(v, pos, pos >= k);             // physical row of the pivot
     const int pos_p = __shfl_sync(FATODE_FULL_MASK, pos, p);
     const double piv = shfl_d(v, p);
@@ -61,6 +69,7 @@ __device__ __forceinline__ int warp_lu_factor(double* __restrict__ A, int* __res
         if (fabs(piv) >= sfmin) l = __dmul_rn(__ddiv_rn(1.0, piv), v);   // DSCAL by the reciprocal
         else l = __ddiv_rn(v, piv);
         if (below) A[k * LDA + lane] = l;
+        if (__ballot_sync(FATODE_FULL_MASK, below && l != 0.0)) lnz |= 1u << k;
         const double urow = A[lane * LDA + p];                   // lane = column: pivot row entry
         unsigned mask = __ballot_sync(FATODE_FULL_MASK, urow != 0.0 && lane > k);
         while (mask) {                                           // DGER over the non-zero columns
@@ -78,21 +87,25 @@ __device__ __forceinline__ int warp_lu_factor(double* __restrict__ A, int* __res
     }
     __syncwarp();
   }
+  if (masks) { masks->lnz = lnz; masks->unz = unz; }
   return info;
 }
 
 // DGETRS 'N' with one right-hand side; lane i passes b_i and receives x_i
 __device__ __forceinline__ double warp_lu_solve(const double* __restrict__ A, const int* __restrict__ who, int pos,
-                                                double b, int lane) {
+                                                LUMasks mk, double b, int lane) {
   // row interchanges are implicit: lane's b belongs to logical row pos
-  for (int k = 0; k < 31; ++k) {                 // DTRSM Left Lower NoTrans Unit
+  for (unsigned m = mk.lnz; m; m &= m - 1) {     // DTRSM Left Lower NoTrans Unit, non-empty columns ascending
+    const int k = __ffs(m) - 1;
     const double bk = shfl_d(b, who[k]);
     if (bk != 0.0) {
       const double l = A[k * LDA + lane];
       if (pos > k) b = __dsub_rn(b, __dmul_rn(bk, l));
     }
   }
-  for (int k = 31; k >= 0; --k) {                // DTRSM Left Upper NoTrans NonUnit
+  for (unsigned m = mk.unz; m;) {                // DTRSM Left Upper NoTrans NonUnit, non-empty columns descending
+    const int k = 31 - __clz(m);
+    m &= ~(1u << k);
     const int src = who[k];
     double bk = shfl_d(b, src);
     if (bk != 0.0) {
@@ -102,6 +115,8 @@ __device__ __forceinline__ double warp_lu_solve(const double* __restrict__ A, co
       if (pos < k) b = __dsub_rn(b, __dmul_rn(bk, u));
     }
   }
+  // rows whose column of U is empty above the diagonal: nobody consumes x_k, divide them all at once
+  if (!((mk.unz >> pos) & 1u) && b != 0.0) b = __ddiv_rn(b, A[pos * LDA + lane]);
   // unknown r sits in the lane that owns logical row r
   return shfl_d(b, who[lane]);
 }
@@ -144,6 +159,7 @@ __device__ void ros_forward_warp(const RosParams& rp, const typename Model::Cons
   int nfun = 0, njac = 0, nstp = 0, nacc = 0, nrej = 0, ndec = 0, nsol = 0, nsng = 0;
   double Ynew = y, Fcn0, Fcn = 0.0, dFdT = 0.0;
   int pos = lane;
+  LUMasks mk = {0u, 0u};
 
   Model::init(ws, mc, lane);
   double T = rp.tstart;
@@ -188,7 +204,7 @@ __device__ void ros_forward_warp(const RosParams& rp, const typename Model::Cons
         while (Singular) {
           const double ghinv = __ddiv_rn(1.0, __dmul_rn(__dmul_rn(dDir, H), rp.Gamma[0]));
           Model::template scatter_E<LDA>(jv, ghinv, A, lane);
-          const int info = warp_lu_factor(A, who, pos, lane);
+          const int info = warp_lu_factor(A, who, pos, lane, &mk);
           if (count_la) ndec++;
           if (info == 0) {
             Singular = false;
@@ -227,7 +243,7 @@ __device__ void ros_forward_warp(const RosParams& rp, const typename Model::Cons
           const double HG = __dmul_rn(dH, rp.Gamma[is]);
           k = __dadd_rn(k, __dmul_rn(HG, dFdT));
         }
-        k = warp_lu_solve(A, who, pos, k, lane);
+        k = warp_lu_solve(A, who, pos, mk, k, lane);
         if (count_la) nsol++;
         Ks[is * 32 + lane] = k;
       }

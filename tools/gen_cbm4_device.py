@@ -222,7 +222,8 @@ def main():
     w(f"constexpr int NVAR = {N}, NREACT = {NREACT}, NPAR = {NP}, NJ = {NJ}, NM = {NM}, NHESS = 258, NJT = {len(jtime)};")
     w("constexpr int OP_F = 32, OP_ONE = 33, OP_TWO = 34;")
     w("struct L1 { double lit; short rct; unsigned char o1, o2, o3; unsigned char pad[3]; };")
-    w("struct L2 { double sc; short src; short out; unsigned char first, last; unsigned char pad[2]; };")
+    w("constexpr int TERM_BUF = 353;   // products buffer: MAXT + the zero sentinel")
+    w("struct TermSP { double sc; unsigned int off; unsigned int pad; };")
 
     def emit_l1(name, entries):
         ms = sorted(entries.keys())
@@ -238,40 +239,117 @@ def main():
                 w(f"  {{0.0, -1, {OP_ONE}, {OP_ONE}, {OP_ONE}, {{0,0,0}}}},")
         w("};")
 
-    def emit_l2(name, lists):
-        niter, seqs = schedule_l2(lists)
-        w(f"constexpr int {name}_NITER = {niter};")
-        w(f"CBM4_TAB L2 {name}_TAB[{niter} * 32] = {{   // [iter][lane]")
-        for it in range(niter):
+    def emit_l2(name, lists, fixed_lanes=False, mat=False, out_ids=None):
+        """Level 2 as (a) a flat table of products TERM_k = sc_k * P[src_k] evaluated 32 at a time and (b) per
+        lane an ordered list of term indices to add up (the Fortran's textual order), so the sequential part
+        is one shared-memory load and one DADD per term.  fixed_lanes: output e belongs to lane e (FUN: the
+        sum stays in that lane's register).  mat: TERM_k = HS[h_k] * K[c_k] (no literal coefficient)."""
+        terms = []        # (sc, src) or (h, c)
+        per_out = []      # per output: list of term ids, in order
+        for lst in lists:
+            ids = []
+            for (sc, src) in lst:
+                terms.append((sc, src))
+                ids.append(len(terms) - 1)
+            per_out.append(ids)
+        nt = len(terms)
+        ntpad = (nt + 31) // 32 * 32
+        ZERO = ntpad      # T[ntpad] = 0.0 (sentinel for padded slots)
+        seqs = [[] for _ in range(32)]
+        if fixed_lanes:
+            assert len(lists) == 32
+            for e, ids in enumerate(per_out):
+                seqs[e] = [(k, False, e) for k in ids]
+        else:
+            order = sorted(range(len(per_out)), key=lambda e: -len(per_out[e]))
+            load = [0] * 32
+            for e in order:
+                ids = per_out[e]
+                if not ids:
+                    continue
+                lane = min(range(32), key=lambda l: (load[l], l))
+                for t, k in enumerate(ids):
+                    seqs[lane].append((k, t == len(ids) - 1, e))
+                load[lane] += len(ids)
+        niter = max(len(q) for q in seqs)
+        niter4 = (niter + 3) // 4 * 4
+        w(f"constexpr int {name}_NT = {nt}, {name}_NTPAD = {ntpad}, {name}_NITER = {niter4};")
+        if mat:
+            w(f"CBM4_TAB ushort2 {name}_TERM[{ntpad}] = {{   // (HESS index, K index) byte offsets")
+            w("  " + ", ".join(f"{{{8 * int(terms[k][1])}, {8 * int(terms[k][0])}}}" if k < nt else "{0, 0}" for k in range(ntpad)))
+        else:
+            w(f"CBM4_TAB TermSP {name}_TERM[{ntpad}] = {{   // sc, byte offset of the level-1 product")
+            w("  " + ", ".join(f"{{{fx.c_double(terms[k][0])}, {8 * terms[k][1]}, 0}}" if k < nt else "{0.0, 0, 0}"
+                               for k in range(ntpad)))
+        w("};")
+        # ordered sums: ushort per (iter, lane), 4 iterations packed per 64-bit word: [iter/4][lane] as ushort4
+        w(f"CBM4_TAB ushort4 {name}_SUM[{niter4 // 4} * 32] = {{   // term index (low 14 bits) | 0x8000 = last term of an output")
+        rows = []
+        for q4 in range(niter4 // 4):
             row = []
             for lane in range(32):
-                if it < len(seqs[lane]):
-                    sc, src, fi, la, e = seqs[lane][it]
-                    row.append(f"{{{fx.c_double(sc)}, {src}, {e}, {int(fi)}, {int(la)}, {{0,0}}}}")
-                else:
-                    row.append("{0.0, 0, -1, 0, 0, {0,0}}")
-            w("  " + ", ".join(row) + ",")
+                vals = []
+                for it in range(4 * q4, 4 * q4 + 4):
+                    if it < len(seqs[lane]):
+                        k, last, e = seqs[lane][it]
+                        vals.append(k | (0x8000 if (last and not fixed_lanes) else 0))
+                    else:
+                        vals.append(ZERO)
+                row.append("{" + ", ".join(map(str, vals)) + "}")
+            rows.append("  " + ", ".join(row) + ",")
+        w("\n".join(rows))
         w("};")
-        return niter
+        if not fixed_lanes:
+            nout = max(sum(1 for (_, last, _) in q if last) for q in seqs)
+            w(f"constexpr int {name}_NOUT = {nout};")
+            w(f"CBM4_TAB unsigned short {name}_OUT[{nout} * 32] = {{   // n-th output finished by a lane -> output index")
+            for n in range(nout):
+                row = []
+                for lane in range(32):
+                    outs = [e for (_, last, e) in seqs[lane] if last]
+                    row.append(str(out_ids[outs[n]] if out_ids else outs[n]) if n < len(outs) else "0")
+                w("  " + ", ".join(row) + ",")
+            w("};")
+        return niter4
+
+    MAXT = 352   # products buffer (doubles) shared by all evaluators; larger routines run in groups
+
+    def emit_l2_groups(name, lists, mat=False):
+        """split the outputs (kept in order, global output numbering) into groups of <= MAXT terms"""
+        groups, cur, cnt = [], [], 0
+        for e, lst in enumerate(lists):
+            if cnt + len(lst) > MAXT and cur:
+                groups.append(cur)
+                cur, cnt = [], 0
+            cur.append(e)
+            cnt += len(lst)
+        if cur:
+            groups.append(cur)
+        w(f"constexpr int {name}_NG = {len(groups)};")
+        its = []
+        for g, outs in enumerate(groups):
+            sub = [lists[e] for e in outs]
+            its.append(emit_l2(f"{name}{g}", sub, mat=mat, out_ids=outs))
+        return its
 
     stats = {}
     # FUN
     emit_l1("FUN_L1", A)
-    stats["fun_iter"] = emit_l2("FUN_L2", VD)
+    stats["fun_iter"] = emit_l2("FUN_L2", VD, fixed_lanes=True)
     # JAC: outputs numbered in jent order
     emit_l1("JAC_L1", B)
-    stats["jac_iter"] = emit_l2("JAC_L2", [JV[rc] for rc in jent])
+    stats["jac_iter"] = emit_l2_groups("JAC_L2", [JV[rc] for rc in jent])
     w(f"CBM4_TAB unsigned char JAC_ROW[{NJ}] = {{{', '.join(str(rc[0]) for rc in jent)}}};")
     w(f"CBM4_TAB unsigned char JAC_COL[{NJ}] = {{{', '.join(str(rc[1]) for rc in jent)}}};")
     w(f"CBM4_TAB short JAC_TIME[{len(jtime)}] = {{{', '.join(map(str, jtime))}}};   // J entries depending on SUN")
     # HESS
     emit_l1("HES_L1", D2A)
-    stats["hes_iter"] = emit_l2("HES_L2", [HE[h] for h in range(258)])
+    stats["hes_iter"] = emit_l2_groups("HES_L2", [HE[h] for h in range(258)])
     # M' assembly: M'_e = sum_t HESS[h]*K[c]  (+ H*gamma*djdt[jt] if the entry is a time-dependent J entry)
     mlists = []
     for kr in mpat:
         mlists.append([(float(c), h) for (h, c) in M.get(kr, [])])      # sc field carries the K index
-    stats["m_iter"] = emit_l2("MAT_L2", mlists)
+    stats["m_iter"] = emit_l2_groups("MAT_L2", mlists, mat=True)
     jt_of = {jent[i]: n for n, i in enumerate(jtime)}
     w(f"CBM4_TAB short MAT_JT[{NM}] = {{{', '.join(str(jt_of.get(kr, -1)) for kr in mpat)}}};   // index into JAC_TIME or -1")
     # rate coefficients
