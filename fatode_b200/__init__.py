@@ -33,7 +33,8 @@ class FatodeError(RuntimeError):
 class Stats(ctypes.Structure):
     _fields_ = [("launches", ctypes.c_int64), ("waves", ctypes.c_int64), ("ms_forward", ctypes.c_double),
                 ("ms_forward_tape", ctypes.c_double), ("ms_adjoint", ctypes.c_double), ("ms_other", ctypes.c_double),
-                ("tape_bytes_peak", ctypes.c_uint64), ("accepted_steps", ctypes.c_int64), ("attempts", ctypes.c_int64)]
+                ("tape_bytes_peak", ctypes.c_uint64), ("accepted_steps", ctypes.c_int64), ("attempts", ctypes.c_int64),
+                ("cells_general", ctypes.c_int64), ("cells_deferred", ctypes.c_int64)]
 
 
 _lib = None
@@ -56,6 +57,8 @@ def lib():
         L.fatode_free_pinned.argtypes = [ctypes.c_void_p]
         L.fatode_set_tape_budget.argtypes = [ctypes.c_uint64]
         L.fatode_set_wave_cells.argtypes = [ctypes.c_int64]
+        L.fatode_set_path.argtypes = [ctypes.c_int]
+        L.fatode_debug_irregular_every.argtypes = [ctypes.c_int]
         L.fatode_get_last_stats.argtypes = [ctypes.POINTER(Stats)]
         L.fatode_model_dims.argtypes = [ctypes.c_int, _ip, _ip]
         L.fatode_model_initial_state.argtypes = [ctypes.c_int, _dp]

@@ -26,6 +26,8 @@
 #include "ros_warp_fwd.cuh"
 #include "ros_warp_adj.cuh"
 #include "ros_warp_adj2.cuh"
+#include "ros_cell_fwd.cuh"
+#include "ros_cell_adj.cuh"
 
 using namespace fatode;
 
@@ -35,6 +37,8 @@ static thread_local std::string g_err;
 static thread_local fatode_stats g_stats;
 static uint64_t g_tape_budget = 0;
 static int64_t g_wave_cells = 0;
+static int g_path = 0;                    // 0 = per-thread fast path with general fallback, 1 = general kernels only
+static int g_debug_irregular_every = 0;   // test hook: every k-th cell is pushed through the fallback
 
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CUDA_TRY(x)                                                                              \
@@ -50,6 +54,8 @@ extern "C" const char* fatode_last_error(void) { return g_err.c_str(); }
 extern "C" const char* fatode_version(void) { return "fatode_b200 0.1 (sm_100a)"; }
 extern "C" int fatode_set_tape_budget(uint64_t bytes) { g_tape_budget = bytes; return 0; }
 extern "C" int fatode_set_wave_cells(int64_t cells) { g_wave_cells = cells; return 0; }
+extern "C" int fatode_set_path(int mode) { g_path = mode; return 0; }
+extern "C" int fatode_debug_irregular_every(int k) { g_debug_irregular_every = k; return 0; }
 extern "C" int fatode_get_last_stats(fatode_stats* out) { if (!out) return FATODE_EINVAL; *out = g_stats; return 0; }
 
 extern "C" void* fatode_alloc_pinned(uint64_t bytes) {
@@ -100,7 +106,6 @@ constexpr int FWD_WARPS = 4;
 template <class Model>
 __host__ __device__ constexpr int fwd_ws_doubles() { return FwdSmem<Model>::DOUBLES; }
 
-constexpr int IERR_TAPE_OVERFLOW = -1000;   // internal: slab too small, the wave is re-run in exact mode
 
 // MODE 0: no tape, writes y/ISTATUS/RSTATUS/IERR/nacc.   MODE 1: replay with tape at exact offsets (tape_off), no
 // status.   MODE 2: single pass, status + tape into a fixed slab of `slab_cap` entries per cell.
@@ -367,8 +372,10 @@ struct CachedBuf {
   template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
 static thread_local CachedBuf g_tape, g_y0, g_nacc, g_off, g_queue, g_part;
+static thread_local CachedBuf g_ids, g_wnacc, g_wlast, g_prev, g_owner, g_order, g_wierr;   // per-thread path
 extern "C" int fatode_release_workspace(void) {
   g_tape.release(); g_y0.release(); g_nacc.release(); g_off.release(); g_queue.release(); g_part.release();
+  g_ids.release(); g_wnacc.release(); g_wlast.release(); g_prev.release(); g_owner.release(); g_order.release(); g_wierr.release();
   return 0;
 }
 
@@ -388,12 +395,13 @@ static int check_device() {
   return 0;
 }
 
-// core of INTEGRATE_ADJ on device-resident arrays (cbm4 / warp family)
+// GENERAL PATH: core of INTEGRATE / INTEGRATE_ADJ on device-resident arrays with the warp-per-cell kernels
+// (full partial pivoting, singular-matrix retries).  Used for cells the per-thread path hands back and when
+// fatode_set_path(1) asks for it.
 template <class Model>
-static int ros_adj_device(const RosParams& rp, const typename Model::Const& mc, int64_t ncells, int nadj, bool with_mu,
+static int ros_device_general(const RosParams& rp, const typename Model::Const& mc, int64_t ncells, int nadj, bool with_mu,
                           bool do_adjoint, double* d_y, double* d_lambda, double* d_mu, const double* d_atol,
-                          const double* d_rtol, int* d_istatus, double* d_rstatus, int* d_ierr, double* d_mu_sum,
-                          cudaStream_t st) {
+                          const double* d_rtol, int* d_istatus, double* d_rstatus, int* d_ierr, cudaStream_t st) {
   const int NE = tape_entry_doubles(rp.S, 32);
   const size_t entry_bytes = sizeof(double) * NE;
   int dev = 0, sms = 0;
@@ -422,7 +430,6 @@ static int ros_adj_device(const RosParams& rp, const typename Model::Const& mc, 
   unsigned long long* d_queue = b_queue.as<unsigned long long>();
   int* d_novf = reinterpret_cast<int*>(d_queue + 1);
   PhaseTimer tm(st);
-  std::memset(&g_stats, 0, sizeof g_stats);
 
   const size_t adj2_smem = sizeof(double) * (size_t)Adj2Smem<Model>::DOUBLES * ADJ2_SLOTS;
   CUDA_TRY(cudaFuncSetAttribute(k_ros_adj2<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj2_smem));
@@ -546,20 +553,262 @@ static int ros_adj_device(const RosParams& rp, const typename Model::Const& mc, 
     c0 += n;
     g_stats.waves++;
   }
-  // deterministic Mu sum over cells
-  if (do_adjoint && with_mu && d_mu_sum) {
-    const int len = nadj * Model::NP;
-    const int cpb = 256;
-    const int nb = (int)((ncells + cpb - 1) / cpb);
-    CachedBuf& part = g_part;
-    CUDA_TRY(part.ensure(sizeof(double) * (size_t)nb * len));
-    tm.start();
-    k_mu_reduce1<<<nb, 256, 0, st>>>(ncells, len, d_mu, d_ierr, part.as<double>(), cpb);
-    k_mu_reduce2<<<(len + 255) / 256, 256, 0, st>>>(nb, len, part.as<double>(), d_mu_sum);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// deterministic Mu sum over cells (fixed order -> bitwise reproducible)
+static int mu_sum_device(int64_t ncells, int len, const double* d_mu, const int* d_ierr, double* d_mu_sum, cudaStream_t st) {
+  const int cpb = 256;
+  const int nb = (int)((ncells + cpb - 1) / cpb);
+  CachedBuf& part = g_part;
+  CUDA_TRY(part.ensure(sizeof(double) * (size_t)nb * len));
+  PhaseTimer tm(st);
+  tm.start();
+  k_mu_reduce1<<<nb, 256, 0, st>>>(ncells, len, d_mu, d_ierr, part.as<double>(), cpb);
+  k_mu_reduce2<<<(len + 255) / 256, 256, 0, st>>>(nb, len, part.as<double>(), d_mu_sum);
+  CUDA_TRY(cudaGetLastError());
+  g_stats.ms_other += tm.stop();
+  g_stats.launches += 2;
+  return 0;
+}
+
+// gather / scatter of per-cell rows for the cells handed to the general path
+__global__ void k_gather_rows(int n, const int* __restrict__ ids, int row, const double* __restrict__ src, double* __restrict__ dst) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)n * row) return;
+  const long c = i / row, j = i - c * row;
+  dst[i] = src[(long)ids[c] * row + j];
+}
+__global__ void k_scatter_rows(int n, const int* __restrict__ ids, int row, const double* __restrict__ src, double* __restrict__ dst) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)n * row) return;
+  const long c = i / row, j = i - c * row;
+  dst[(long)ids[c] * row + j] = src[i];
+}
+__global__ void k_scatter_rows_i(int n, const int* __restrict__ ids, int row, const int* __restrict__ src, int* __restrict__ dst) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)n * row) return;
+  const long c = i / row, j = i - c * row;
+  dst[(long)ids[c] * row + j] = src[i];
+}
+
+__global__ void k_gather_rows_i(int n, const int* __restrict__ ids, const int* __restrict__ src, int* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[ids[i]];
+}
+
+
+// FAST PATH (models with per-thread code): forward sweep one cell per thread, fat tape from a chunk pool, backward
+// sweep streaming the tape.  Cells that need the general kernels are appended to `general`.
+template <class Cell, class Warp>
+static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, int64_t ncells, int nadj, bool with_mu,
+                           bool do_adjoint, double* d_y, double* d_lambda, double* d_mu, const double* d_atol,
+                           const double* d_rtol, int* d_istatus, double* d_rstatus, int* d_ierr, cudaStream_t st,
+                           std::vector<int>& general) {
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_cbm4_rc, mc.rc_base, sizeof(double) * 81, 0, cudaMemcpyHostToDevice, st));
+  if (do_adjoint) {   // constant Hessian values of the mechanism for k_expand_tape
+    CUDA_TRY(g_part.ensure(sizeof(double) * 512));
+    k_cbm4_hess<<<1, 1, 0, st>>>(mc.fix, g_part.as<double>());
     CUDA_TRY(cudaGetLastError());
-    g_stats.ms_other += tm.stop();
-    g_stats.launches += 2;
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_cbm4_hess, g_part.p, sizeof(double) * 258, 0, cudaMemcpyDeviceToDevice, st));
   }
+  PhaseTimer tm(st);
+  // forward kernel: persistent single-warp blocks, one per SM (188 KB of shared memory each)
+  auto fwd_blocks = [&](int64_t n) { return (unsigned)std::min<int64_t>((n + CELL_LANES - 1) / CELL_LANES, (int64_t)sms); };
+  const size_t cell_smem = CellSmem<Cell>::BYTES;
+  CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd_cell<Cell, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cell_smem));
+  CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd_cell<Cell, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cell_smem));
+  CUDA_TRY(g_queue.ensure(4 * sizeof(unsigned long long)));
+  unsigned long long* d_queue = g_queue.as<unsigned long long>();
+  CellTape tape{nullptr, nullptr, nullptr, nullptr, 0u, nullptr};
+  if (!do_adjoint) {
+    CUDA_TRY(g_wnacc.ensure(sizeof(int) * ncells));
+    CUDA_TRY(cudaMemsetAsync(d_queue, 0, 4 * sizeof(unsigned long long), st));
+    tm.start();
+    k_ros_fwd_cell<Cell, 0><<<fwd_blocks(ncells), CELL_LANES, cell_smem, st>>>(
+        rp, mc, ncells, nullptr, d_y, d_y, d_atol, d_rtol, d_istatus, d_rstatus, d_ierr, g_wnacc.as<int>(), tape, 0,
+        g_debug_irregular_every, d_queue + 2);
+    CUDA_TRY(cudaGetLastError());
+    g_stats.ms_forward += tm.stop();
+    g_stats.launches++;
+    g_stats.waves++;
+    std::vector<int> h_ierr(ncells);
+    CUDA_TRY(cudaMemcpyAsync(h_ierr.data(), d_ierr, sizeof(int) * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int64_t c = 0; c < ncells; ++c)
+      if (h_ierr[c] == IERR_IRREGULAR) general.push_back((int)c);
+    return 0;
+  }
+  // ---- adjoint mode: waves over a chunk pool
+  const int NE = fat_entry_doubles(rp.S);
+  const size_t chunk_bytes = sizeof(double) * (size_t)NE * FT_CHUNK;
+  size_t free_b = 0, total_b = 0;
+  CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+  size_t budget = g_tape_budget ? (size_t)g_tape_budget : (size_t)(0.6 * (double)free_b);
+  budget = std::min(budget, (size_t)(0.9 * (double)free_b));
+  if (g_tape_budget == 0 && g_tape.cap >= chunk_bytes * 64) budget = g_tape.cap;   // reuse the cached tape
+  const unsigned pool_chunks = (unsigned)std::min<size_t>(budget / chunk_bytes, 0x7fffffffu);
+  if (pool_chunks < 1) return fail(FATODE_ENOMEM, "tape budget smaller than one chunk of the trajectory tape");
+  CUDA_TRY(g_tape.ensure((size_t)pool_chunks * chunk_bytes));
+  CUDA_TRY(g_prev.ensure(sizeof(int) * (size_t)pool_chunks));
+  CUDA_TRY(g_owner.ensure(sizeof(int) * (size_t)pool_chunks));
+  unsigned int* d_head = reinterpret_cast<unsigned int*>(d_queue + 1);
+  const size_t adj_smem = sizeof(double) * (size_t)ADJ3_WARP_DOUBLES * ADJ3_WARPS;
+  CUDA_TRY(cudaFuncSetAttribute(k_ros_adj_cell<Warp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem));
+
+  const int64_t wave_max = std::min<int64_t>(g_wave_cells > 0 ? g_wave_cells : (1 << 20), ncells);
+  CUDA_TRY(g_ids.ensure(sizeof(int) * wave_max));
+  CUDA_TRY(g_wnacc.ensure(sizeof(int) * wave_max));
+  CUDA_TRY(g_wlast.ensure(sizeof(int) * wave_max));
+  CUDA_TRY(g_order.ensure(sizeof(int) * wave_max));
+  CUDA_TRY(g_wierr.ensure(sizeof(int) * wave_max));
+  tape.base = g_tape.as<double>();
+  tape.chunk_prev = g_prev.as<int>();
+  tape.chunk_owner = g_owner.as<int>();
+  tape.pool_head = d_head;
+  tape.pool_chunks = pool_chunks;
+  tape.last_chunk = g_wlast.as<int>();
+
+  std::vector<int> pending(ncells), next_pending, ids, h_nacc, h_ierr, order;
+  for (int64_t c = 0; c < ncells; ++c) pending[c] = (int)c;
+  double chunks_per_cell = 0.0;   // running estimate (0 = unknown)
+  size_t pos = 0;
+  while (pos < pending.size() || !next_pending.empty()) {
+    if (pos >= pending.size()) { pending.swap(next_pending); next_pending.clear(); pos = 0; }
+    const int64_t remaining = (int64_t)(pending.size() - pos);
+    int64_t cap = chunks_per_cell > 0.0 ? (int64_t)((double)pool_chunks / (chunks_per_cell * 1.02 + 0.5))
+                                        : std::max<int64_t>(1, std::min<int64_t>(1184, pool_chunks / 64));
+    const int64_t n = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(remaining, wave_max), cap));
+    ids.assign(pending.begin() + pos, pending.begin() + pos + n);
+    pos += n;
+    CUDA_TRY(cudaMemcpyAsync(g_ids.p, ids.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(d_queue, 0, 4 * sizeof(unsigned long long), st));
+    tm.start();
+    k_ros_fwd_cell<Cell, 1><<<fwd_blocks(n), CELL_LANES, cell_smem, st>>>(
+        rp, mc, n, g_ids.as<int>(), d_y, d_y, d_atol, d_rtol, d_istatus, d_rstatus, d_ierr, g_wnacc.as<int>(), tape,
+        with_mu ? 1 : 0, g_debug_irregular_every, d_queue + 2);
+    CUDA_TRY(cudaGetLastError());
+    {
+      const double ms_f = tm.stop();
+      g_stats.ms_forward += ms_f;
+      if (getenv("FATODE_DEBUG_WAVES")) fprintf(stderr, "[wave] forward %.2f ms\n", ms_f);
+    }
+    g_stats.launches++;
+    g_stats.waves++;
+    // per-slot outcome
+    h_nacc.resize(n);
+    h_ierr.resize(n);
+    k_gather_rows_i<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((int)n, g_ids.as<int>(), d_ierr, g_wierr.as<int>());
+    CUDA_TRY(cudaMemcpyAsync(h_ierr.data(), g_wierr.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_nacc.data(), g_wnacc.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    unsigned h_head = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h_head, d_head, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const unsigned chunks_used = std::min(h_head, pool_chunks);
+    int64_t n_ok = 0, n_def = 0;
+    long long steps = 0;
+    order.clear();
+    for (int64_t w = 0; w < n; ++w) {
+      if (h_ierr[w] == IERR_DEFERRED) { next_pending.push_back(ids[w]); ++n_def; }
+      else if (h_ierr[w] == IERR_IRREGULAR) general.push_back(ids[w]);
+      else if (h_ierr[w] == 1) { ++n_ok; steps += h_nacc[w]; order.push_back((int)w); }
+    }
+    g_stats.cells_deferred += n_def;
+    if (n_ok > 0) {
+      chunks_per_cell = std::max(chunks_per_cell, ((double)steps / (double)n_ok) / FT_CHUNK + 0.5);
+      g_stats.accepted_steps += steps;
+      g_stats.tape_bytes_peak = std::max<uint64_t>(g_stats.tape_bytes_peak, (uint64_t)(steps + n_ok * FT_CHUNK / 2) * NE * 8);
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h_nacc[a] > h_nacc[b]; });
+      CUDA_TRY(cudaMemcpyAsync(g_order.p, order.data(), sizeof(int) * n_ok, cudaMemcpyHostToDevice, st));
+      tm.start();
+      {   // per-stage blocks of the tape: one thread per (step, stage)
+        const long items = (long)chunks_used * FT_CHUNK * rp.S;
+        k_expand_tape<Cell><<<(unsigned)((items + 127) / 128), 128, 0, st>>>(
+            rp, mc, chunks_used, g_owner.as<int>(), g_ids.as<int>(), d_ierr, g_wnacc.as<int>(), g_wlast.as<int>(),
+            g_tape.as<double>(), with_mu ? 1 : 0);
+        CUDA_TRY(cudaGetLastError());
+        const double ms_x = tm.stop();
+        g_stats.ms_forward_tape += ms_x;
+        g_stats.launches++;
+        if (getenv("FATODE_DEBUG_WAVES")) fprintf(stderr, "[wave] cells %ld ok %ld deferred %ld chunks %u expand %.2f ms\n", (long)n, (long)n_ok, (long)n_def, chunks_used, ms_x);
+      }
+      tm.start();
+      const int ablocks = (int)std::min<int64_t>(sms, (n_ok + ADJ3_WARPS - 1) / ADJ3_WARPS);
+      k_ros_adj_cell<Warp><<<ablocks, ADJ3_WARPS * 32, adj_smem, st>>>(
+          rp, n_ok, g_ids.as<int>(), g_wnacc.as<int>(), g_wlast.as<int>(), g_tape.as<double>(), g_prev.as<int>(), d_ierr,
+          d_y, d_lambda, with_mu ? d_mu : nullptr, d_istatus, d_queue, g_order.as<int>(), nadj, with_mu ? 1 : 0);
+      CUDA_TRY(cudaGetLastError());
+      const double ms_a = tm.stop();
+      g_stats.ms_adjoint += ms_a;
+      g_stats.launches++;
+      if (getenv("FATODE_DEBUG_WAVES")) fprintf(stderr, "[wave] adjoint %.2f ms\n", ms_a);
+    } else if (n_def == n) {
+      if (n == 1) return fail(FATODE_ENOMEM, "trajectory tape of a single cell exceeds the tape budget");
+      chunks_per_cell = std::max(2.0 * chunks_per_cell, (double)pool_chunks / std::max<int64_t>(1, n / 2));
+    }
+  }
+  return 0;
+}
+
+// dispatcher: fast path where the model has one, then the general path for what is left
+template <class Cell, class Warp>
+static int ros_device(const RosParams& rp, const typename Warp::Const& mc, int64_t ncells, int nadj, bool with_mu,
+                      bool do_adjoint, double* d_y, double* d_lambda, double* d_mu, const double* d_atol, const double* d_rtol,
+                      int* d_istatus, double* d_rstatus, int* d_ierr, double* d_mu_sum, cudaStream_t st) {
+  std::memset(&g_stats, 0, sizeof g_stats);
+  if (g_path == 1) {
+    if (int e = ros_device_general<Warp>(rp, mc, ncells, nadj, with_mu, do_adjoint, d_y, d_lambda, d_mu, d_atol, d_rtol,
+                                         d_istatus, d_rstatus, d_ierr, st)) return e;
+    g_stats.cells_general = ncells;
+  } else {
+    std::vector<int> general;
+    if (int e = ros_device_fast<Cell, Warp>(rp, mc, ncells, nadj, with_mu, do_adjoint, d_y, d_lambda, d_mu, d_atol, d_rtol,
+                                            d_istatus, d_rstatus, d_ierr, st, general)) return e;
+    const int m = (int)general.size();
+    g_stats.cells_general = m;
+    if (m > 0) {   // hand-back: compact copies of the rows, general kernels, scatter
+      std::sort(general.begin(), general.end());
+      const int N = Warp::N, NP = Warp::NP;
+      DevBuf b_ids, b_y, b_lam, b_mu, b_ist, b_rst, b_ierr;
+      CUDA_TRY(b_ids.alloc(sizeof(int) * m));
+      CUDA_TRY(b_y.alloc(sizeof(double) * N * m));
+      CUDA_TRY(b_ist.alloc(sizeof(int) * 20 * m));
+      CUDA_TRY(b_rst.alloc(sizeof(double) * 20 * m));
+      CUDA_TRY(b_ierr.alloc(sizeof(int) * m));
+      CUDA_TRY(cudaMemcpyAsync(b_ids.p, general.data(), sizeof(int) * m, cudaMemcpyHostToDevice, st));
+      auto blocks = [](long n) { return (unsigned)((n + 255) / 256); };
+      k_gather_rows<<<blocks((long)m * N), 256, 0, st>>>(m, b_ids.as<int>(), N, d_y, b_y.as<double>());
+      if (do_adjoint) {
+        CUDA_TRY(b_lam.alloc(sizeof(double) * (size_t)N * nadj * m));
+        k_gather_rows<<<blocks((long)m * N * nadj), 256, 0, st>>>(m, b_ids.as<int>(), N * nadj, d_lambda, b_lam.as<double>());
+        if (with_mu) {
+          CUDA_TRY(b_mu.alloc(sizeof(double) * (size_t)NP * nadj * m));
+          k_gather_rows<<<blocks((long)m * NP * nadj), 256, 0, st>>>(m, b_ids.as<int>(), NP * nadj, d_mu, b_mu.as<double>());
+        }
+      }
+      CUDA_TRY(cudaGetLastError());
+      if (int e = ros_device_general<Warp>(rp, mc, m, nadj, with_mu, do_adjoint, b_y.as<double>(), b_lam.as<double>(),
+                                           b_mu.as<double>(), d_atol, d_rtol, b_ist.as<int>(), b_rst.as<double>(),
+                                           b_ierr.as<int>(), st)) return e;
+      k_scatter_rows<<<blocks((long)m * N), 256, 0, st>>>(m, b_ids.as<int>(), N, b_y.as<double>(), d_y);
+      k_scatter_rows<<<blocks((long)m * 20), 256, 0, st>>>(m, b_ids.as<int>(), 20, b_rst.as<double>(), d_rstatus);
+      k_scatter_rows_i<<<blocks((long)m * 20), 256, 0, st>>>(m, b_ids.as<int>(), 20, b_ist.as<int>(), d_istatus);
+      k_scatter_rows_i<<<blocks((long)m), 256, 0, st>>>(m, b_ids.as<int>(), 1, b_ierr.as<int>(), d_ierr);
+      if (do_adjoint) {
+        k_scatter_rows<<<blocks((long)m * N * nadj), 256, 0, st>>>(m, b_ids.as<int>(), N * nadj, b_lam.as<double>(), d_lambda);
+        if (with_mu)
+          k_scatter_rows<<<blocks((long)m * NP * nadj), 256, 0, st>>>(m, b_ids.as<int>(), NP * nadj, b_mu.as<double>(), d_mu);
+      }
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaStreamSynchronize(st));
+    }
+  }
+  if (do_adjoint && with_mu && d_mu_sum)
+    if (int e = mu_sum_device(ncells, nadj * Warp::NP, d_mu, d_ierr, d_mu_sum, st)) return e;
   CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
 }
@@ -647,8 +896,8 @@ static int ros_batch_impl(int family, int model, int64_t ncells, int nvar, int n
       if (with_mu && mu_sum) { CUDA_TRY(b_musum.alloc(sizeof(double) * np * nadj)); d_musum = b_musum.as<double>(); }
     }
   }
-  int rc = ros_adj_device<Cbm4Warp>(rp, mc, ncells, nadj, with_mu, do_adjoint, d_y, d_lam, d_mu, b_atol.as<double>(),
-                                    b_rtol.as<double>(), d_ist, d_rst, d_ierr, d_musum, st);
+  int rc = ros_device<Cbm4Cell, Cbm4Warp>(rp, mc, ncells, nadj, with_mu, do_adjoint, d_y, d_lam, d_mu, b_atol.as<double>(),
+                                          b_rtol.as<double>(), d_ist, d_rst, d_ierr, d_musum, st);
   if (rc != 0) return rc;
   if (mem == FATODE_MEM_HOST) {
     CUDA_TRY(cudaMemcpyAsync(y, d_y, ny, cudaMemcpyDeviceToHost, st));

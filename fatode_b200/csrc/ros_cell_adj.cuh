@@ -1,0 +1,342 @@
+// Discrete Rosenbrock adjoint, backward sweep over the FAT tape written by k_ros_fwd_cell (ros_cell_fwd.cuh).
+//
+// Mathematics and regrouping against ros_DadjInt (ADJ/ROS_ADJ/ROS_ADJ_f90_Integrator.F90:1177-1441) are those of
+// ros_warp_adj2.cuh: lane m of a warp owns adjoint column m of one cell (the NADJ columns never couple,
+// :1285-1317) with its 32-vector in registers and its running sums W_1..W_5, Lambda, the Lambda increment and Mu
+// in TENSOR MEMORY (256 doubles per lane).  What changed: everything that does not depend on the adjoint
+// variables — the L\U factors of the step, J(T_i,Y_i), M'_i = Hess x K_i + h*gamma_i*dJ/dt and a_p per stage —
+// now arrives precomputed on the tape, so there are no producer warps; each warp streams its cell's tape through
+// two double-buffered shared-memory slots with 1-D bulk TMA copies (cp.async.bulk + mbarrier complete_tx) issued
+// one work item (= one stage of one step) ahead, and the transposed solve runs on the static sparse pattern
+// (335 FMA instead of 1056, cbm4_cell::lut_solve).
+//
+// One CTA of 4 warps per SM (TMEM: 4 x 32 lanes x 512 columns), cells pulled from an atomic queue.
+#pragma once
+#include "fatode_common.cuh"
+#include "ros_cell_fwd.cuh"
+#include "ros_warp_adj2.cuh"   // TMEM column map (TM_W, TM_LAM, TM_MU, TM_LACC) shared with the general kernel
+#include "tmem.cuh"
+
+namespace fatode {
+
+constexpr int ADJ3_WARPS = 4;
+constexpr int ADJ3_WARP_DOUBLES = 2 * FT_STEP_COPY + 2 * FT_STAGE + 8;   // step blocks, stage blocks, 4 mbarriers (+pad)
+
+namespace mbar {
+__device__ __forceinline__ uint32_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void init(void* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(saddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void expect_tx(void* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(saddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(saddr(dst)),
+               "l"(src), "r"(bytes), "r"(saddr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void wait(void* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(saddr(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+}  // namespace mbar
+
+// k_expand_tape: fills the per-stage blocks of the fat tape from what the forward sweep recorded (T, H, Y(T), K_1..K_S):
+//   JV = J(T_i, Y_i) values (:1311), MV = M'_i = Hess(T,Y) x K_i + h*gamma_i*dJ/dt (:1330, :1379-1403),
+//   AP = a_p = dF/dp reactant product at Y_i + (dJ/dp x K_i) at Y (:1348, :1363).
+// None of it depends on the adjoint variables, every (step, stage) is independent: one thread per item, millions of
+// threads per wave, so the straight-line model code runs at full occupancy instead of inside the latency-bound
+// forward loop.  Thread layout: item = ((chunk * FT_CHUNK + slot) * S + stage).
+// once per call: Hessian(T) of the mechanism into a staging buffer (copied to c_cbm4_hess by the host)
+__global__ void k_cbm4_hess(double fix, double* __restrict__ out) {
+  double y[32], ph[cbm4_cell::NPHOTO];
+  for (int i = 0; i < 32; ++i) y[i] = 0.0;
+  for (int i = 0; i < cbm4_cell::NPHOTO; ++i) ph[i] = 0.0;
+  cbm4_cell::hess_values<1>(y, fix, ph, out);
+}
+
+template <class Cell>
+__global__ void __launch_bounds__(128, 3)
+k_expand_tape(RosParams rp, typename Cell::Const mc, unsigned nchunks, const int* __restrict__ chunk_owner,
+              const int* __restrict__ ids, const int* __restrict__ ierr, const int* __restrict__ nacc,
+              const int* __restrict__ last_chunk, double* __restrict__ tape, int with_mu) {
+  constexpr int N = Cell::N;
+  const int S = rp.S;
+  const long item = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int is = (int)(item % S);
+  const long t = item / S;
+  const int q = (int)(t % FT_CHUNK);
+  const long c = t / FT_CHUNK;
+  if (c >= (long)nchunks) return;
+  const int w = chunk_owner[c];
+  if (ierr[ids ? ids[w] : w] != 1) return;
+  const int cnt = (c == last_chunk[w]) ? ((nacc[w] - 1) % FT_CHUNK) + 1 : FT_CHUNK;
+  if (q >= cnt) return;
+  double* e = tape + ((size_t)c * FT_CHUNK + q) * fat_entry_doubles(S);
+  const double T = e[0], H = e[1];
+  const double dDir = (rp.tend >= rp.tstart) ? 1.0 : -1.0;
+  double Y0[N], Yi[N], Ki[N], DJ[cbm4_cell::NJT], JT0[cbm4_cell::NJT], PHT[Cell::NPH], PHS[Cell::NPH];
+#pragma unroll 8
+  for (int i = 0; i < N; i += 2) {
+    const double2 a = *reinterpret_cast<const double2*>(e + FT_Y0 + i);
+    Y0[i] = a.x; Y0[i + 1] = a.y;
+    const double2 b = *reinterpret_cast<const double2*>(e + FT_K + is * N + i);
+    Ki[i] = b.x; Ki[i + 1] = b.y;
+  }
+  // Y_i as the forward sweep formed it: refreshed only at stages with ros_NewF (stale otherwise, :1015-1018)
+  int sr = is;
+  while (sr > 0 && !rp.NewF[sr]) --sr;
+#pragma unroll 8
+  for (int i = 0; i < N; ++i) Yi[i] = Y0[i];
+  for (int j = 0; j < sr; ++j) {
+    const double a = rp.A[sr * (sr - 1) / 2 + j];
+    if (a != 0.0) {
+      const double* kj = e + FT_K + j * N;
+#pragma unroll 8
+      for (int i = 0; i < N; ++i) Yi[i] = __dadd_rn(Yi[i], __dmul_rn(a, kj[i]));
+    }
+  }
+  if (!rp.autonomous) {
+    Cell::photo(T, PHT);   // dJ/dt by the reference's forward difference (:1379-1382), DeltaMin of ros_DadjInt :1212
+    const double Delta = sqrt(rp.roundoff) * fmax(1.0e-5, fabs(T));
+    Cell::photo(T + Delta, PHS);
+    cbm4_cell::jac_time<1>(Y0, mc.fix, PHT, JT0);
+    cbm4_cell::jac_time<1>(Y0, mc.fix, PHS, DJ);
+    const double rd = 1.0 / Delta;
+#pragma unroll
+    for (int n = 0; n < cbm4_cell::NJT; ++n) DJ[n] = (DJ[n] - JT0[n]) * rd;
+  } else {
+#pragma unroll
+    for (int n = 0; n < cbm4_cell::NJT; ++n) DJ[n] = 0.0;
+  }
+  double* sb = e + FT_STEP + is * FT_STAGE;
+  Cell::photo(T + rp.Alpha[is] * dDir * H, PHS);
+  cbm4_cell::jac_values<1>(Yi, mc.fix, PHS, sb + FT_JV);
+  cbm4_cell::build_M<1>(Ki, DJ, rp.autonomous ? 0.0 : H * rp.Gamma[is], sb + FT_MV);
+  if (with_mu) cbm4_cell::param_terms<1>(Yi, Y0, mc.fix, Ki, sb + FT_AP);
+  else
+    for (int p = 0; p < 30; ++p) sb[FT_AP + p] = 0.0;
+}
+
+template <class Model, int HALF>
+__device__ __forceinline__ void adj3_lambda_half(const double* __restrict__ MV, const double (&x)[32], const double (&v)[32],
+                                                 bool first, bool last, uint32_t tm) {
+  double acc[16];
+  if (!first) tmem::ld16(tm + TM_LACC + 32 * HALF, acc);
+  Model::mt_rows(MV, x, [&](auto rc, double h) {
+    constexpr int r = decltype(rc)::value;
+    if constexpr (r / 16 == HALF) {
+      const double t = v[r] + h;
+      acc[r - 16 * HALF] = first ? t : (acc[r - 16 * HALF] + t);
+    }
+  });
+  if (last) {
+    double lam[16];
+    tmem::ld16(tm + TM_LAM + 32 * HALF, lam);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) lam[r] += acc[r];
+    tmem::st16(tm + TM_LAM + 32 * HALF, lam);
+  } else {
+    tmem::st16(tm + TM_LACC + 32 * HALF, acc);
+  }
+}
+
+// one work item: stage `is` of the step whose per-step block is `SB`, stage block `STG`
+template <class Model>
+__device__ __forceinline__ void adj3_consume(const RosParams& rp, const double* __restrict__ SB, const double* __restrict__ STG,
+                                             int is, bool with_mu, uint32_t tm) {
+  const int S = rp.S;
+  const double* lu = SB + FT_HDR;
+  const double* dinv = SB + FT_HDR + FT_LU;
+  const double* JV = STG + FT_JV;
+  const double* MV = STG + FT_MV;
+  const double* AP = STG + FT_AP;
+  const double dDir = (rp.tend >= rp.tstart) ? 1.0 : -1.0;
+  const double H = SB[1];
+  const unsigned swaps = (unsigned)SB[2];
+  const bool first = (is == S - 1);
+  const double mi = rp.M[is];
+
+  double x[32];
+  {   // x = m_i * lambda + W_i      (:1285-1300; W_i already holds sum_j a_ji V_j + c_ji/h U_j)
+    tmem::wait_st();
+    tmem::ld32(tm + TM_LAM, x);
+    if (!first) {
+      double w[16];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tmem::ld16(tm + TM_W + 64 * is + 32 * c, w);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[16 * c + r] = fma(mi, x[16 * c + r], w[r]);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 32; ++r) x[r] = mi * x[r];
+    }
+  }
+  cbm4_cell::lut_solve(lu, dinv, swaps, x);   // LSS_Solve(Transp, U_i(m)) (:1301-1304) on the forward sweep's factors
+  double v[32];
+  Model::jt_vec(JV, x, v);                    // V_i = J(T_i,Y_i)^T U_i  (:1315)
+  // running sums for the earlier stages j < is: W_j (+)= a_ij V_i + c_ij/h U_i   (:1292-1300)
+  {
+    const double inv_dH = 1.0 / (dDir * H);
+    for (int j = 0; j < is; ++j) {
+      const double ca = rp.A[is * (is - 1) / 2 + j];
+      const double cc = rp.C[is * (is - 1) / 2 + j] * inv_dH;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        double w[16];
+        if (!first) tmem::ld16(tm + TM_W + 64 * j + 32 * c, w);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const double t = fma(ca, v[16 * c + r], cc * x[16 * c + r]);
+          w[r] = first ? t : (w[r] + t);
+        }
+        tmem::st16(tm + TM_W + 64 * j + 32 * c, w);
+      }
+    }
+  }
+  // Lambda increment: LACC (+)= V_i + M'^T U_i     (:1328-1332 and the dJ/dt term :1402-1403); at the last stage of
+  // the step Lambda += increment (:1324-1339 run after the stage loop).  Two halves of 16 rows bound the register use.
+  adj3_lambda_half<Model, 0>(MV, x, v, first, is == 0, tm);
+  adj3_lambda_half<Model, 1>(MV, x, v, first, is == 0, tm);
+  if (with_mu) {   // Mu += a_p * (S^T U_i)_p     (:1352-1365)
+    double mu[32];
+    tmem::ld32(tm + TM_MU, mu);
+    Model::stoich_cols(x, [&](auto pc, double s) {
+      constexpr int p = decltype(pc)::value;
+      mu[p] = fma(AP[p], s, mu[p]);
+    });
+    tmem::st32(tm + TM_MU, mu);
+  }
+}
+
+// ids[w]: cell of wave slot w; nacc[w], last_chunk[w]: its tape; order[]: processing order of the slots.
+// Only slots with ierr[cell] == 1 are processed.
+template <class Model>
+__global__ void __launch_bounds__(ADJ3_WARPS * 32, 1)
+k_ros_adj_cell(RosParams rp, long nwave, const int* __restrict__ ids, const int* __restrict__ nacc,
+               const int* __restrict__ last_chunk, const double* __restrict__ tape, const int* __restrict__ chunk_prev,
+               const int* __restrict__ ierr, const double* __restrict__ y_final, double* __restrict__ lambda,
+               double* __restrict__ mu, int* __restrict__ istatus, unsigned long long* __restrict__ queue,
+               const int* __restrict__ order, int nadj, int with_mu) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sm = smem + (size_t)warp * ADJ3_WARP_DOUBLES;
+  double* SBUF = sm;                                   // [2][FT_STEP_COPY]
+  double* GBUF = sm + 2 * FT_STEP_COPY;                // [2][FT_STAGE]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + 2 * FT_STEP_COPY + 2 * FT_STAGE);   // [0,1] step, [2,3] stage
+  if (warp == 0) tmem::alloc512(&tmem_base_s);
+  if (lane == 0) {
+    for (int b = 0; b < 4; ++b) mbar::init(bars + b, 1);
+    mbar::fence_init();
+  }
+  tmem::fence_before_sync();
+  __syncthreads();
+  tmem::fence_after_sync();
+  const uint32_t tm = tmem_base_s + ((uint32_t)(warp * 32) << 16);
+  const int S = rp.S;
+  const int NE = fat_entry_doubles(S);
+  uint32_t ph_step0 = 0u, ph_step1 = 0u, ph_stage0 = 0u, ph_stage1 = 0u;   // phase parity per barrier (warp-uniform)
+
+  for (;;) {
+    unsigned long long q = 0;
+    if (lane == 0) q = atomicAdd(queue, 1ull);
+    q = __shfl_sync(FATODE_FULL_MASK, q, 0);
+    if (q >= (unsigned long long)nwave) break;
+    if (order) q = (unsigned long long)order[q];   // longest trajectories first
+    const long cell = ids ? ids[q] : (long)q;
+    if (ierr[cell] != 1) continue;
+    const int nsteps = nacc[q];
+    const int n_items = nsteps * S;
+    {   // ADJINIT (model routine): lane = adjoint column m
+      double lam[32], m0[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) lam[i] = Model::adjinit_lambda(i, lane, y_final[cell * 32 + i]);
+#pragma unroll
+      for (int p = 0; p < 32; ++p) m0[p] = 0.0;
+      tmem::st32(tm + TM_LAM, lam);
+      tmem::st32(tm + TM_MU, m0);
+      tmem::wait_st();
+    }
+    // prefetch cursor: walks the chunk list backwards, one work item ahead of the computation
+    int pf_chunk = last_chunk[q];
+    int pf_step = nsteps - 1;                      // forward-order index of the step the cursor is in
+    auto issue = [&](int t) {                      // executed by lane 0
+      const int si = t / S, is = S - 1 - (t - si * S);
+      const double* ent = tape + ((size_t)pf_chunk * FT_CHUNK + (pf_step % FT_CHUNK)) * NE;
+      if (is == S - 1) {
+        mbar::expect_tx(bars + (si & 1), FT_STEP_COPY * 8);
+        mbar::bulk_g2s(SBUF + (si & 1) * FT_STEP_COPY, ent, FT_STEP_COPY * 8, bars + (si & 1));
+      }
+      mbar::expect_tx(bars + 2 + (t & 1), FT_STAGE * 8);
+      mbar::bulk_g2s(GBUF + (t & 1) * FT_STAGE, ent + FT_STEP + is * FT_STAGE, FT_STAGE * 8, bars + 2 + (t & 1));
+    };
+    auto advance = [&](int t) {                    // cursor moves from item t to item t + 1 (all lanes, uniform)
+      if ((t + 1) % S == 0) {
+        if (pf_step % FT_CHUNK == 0) pf_chunk = chunk_prev[pf_chunk];
+        --pf_step;
+      }
+    };
+    if (n_items > 0 && lane == 0) issue(0);
+    for (int t = 0; t < n_items; ++t) {
+      const int si = t / S, is = S - 1 - (t - si * S);
+      __syncwarp();                                // every lane is done with the buffers item t + 1 will overwrite
+      if (t + 1 < n_items) {
+        advance(t);
+        if (lane == 0) issue(t + 1);
+      }
+      if (is == S - 1) {
+        if (si & 1) { mbar::wait(bars + 1, ph_step1); ph_step1 ^= 1u; }
+        else { mbar::wait(bars + 0, ph_step0); ph_step0 ^= 1u; }
+      }
+      if (t & 1) { mbar::wait(bars + 3, ph_stage1); ph_stage1 ^= 1u; }
+      else { mbar::wait(bars + 2, ph_stage0); ph_stage0 ^= 1u; }
+      adj3_consume<Model>(rp, SBUF + (si & 1) * FT_STEP_COPY, GBUF + (t & 1) * FT_STAGE, is, with_mu != 0, tm);
+    }
+    // results: column m of Lambda / Mu is this lane's private vector
+    tmem::wait_st();
+    {
+      double lam[32];
+      tmem::ld32(tm + TM_LAM, lam);   // .sync.aligned: executed by the whole warp, outside any lane-dependent branch
+      if (lane < nadj) {
+        double* dst = lambda + ((long)cell * nadj + lane) * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) *reinterpret_cast<double2*>(dst + i) = make_double2(lam[i], lam[i + 1]);
+      }
+    }
+    if (with_mu) {
+      double m0[32];
+      tmem::ld32(tm + TM_MU, m0);
+      if (lane < nadj) {
+        double* dst = mu + ((long)cell * nadj + lane) * Model::NP;
+#pragma unroll
+        for (int p = 0; p < Model::NP; ++p) dst[p] = m0[p];
+      }
+    }
+    if (lane == 0) {   // counters of the backward sweep (ADJ :1257-1267, :1303, :1312, :1381)
+      int* is_ = istatus + cell * 20;
+      is_[Nstp] += nsteps;
+      is_[Njac] += nsteps * (2 + S + (rp.autonomous ? 0 : 1));
+      is_[Ndec] += nsteps;
+      is_[Nsol] += nsteps * S * nadj;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 0) tmem::dealloc512(tmem_base_s);
+}
+
+}  // namespace fatode

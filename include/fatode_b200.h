@@ -95,6 +95,12 @@ int fatode_ros_integrate_adj_batch(int model, int64_t ncells, int nvar, int np, 
  * the number of cells per wave (0 = automatic). */
 int fatode_set_tape_budget(uint64_t bytes);
 int fatode_set_wave_cells(int64_t cells);
+/* Execution path: 0 (default) = per-thread kernels (one cell per thread, static-pattern LU) with automatic
+ * hand-back of irregular cells to the general kernels; 1 = general warp-per-cell kernels only.  Both give
+ * identical forward bits.  fatode_debug_irregular_every(k > 0) is a test hook that pushes every k-th cell
+ * through the hand-back. */
+int fatode_set_path(int mode);
+int fatode_debug_irregular_every(int k);
 /* frees the device workspace (trajectory tape etc.) the engine caches between calls */
 int fatode_release_workspace(void);
 
@@ -106,6 +112,8 @@ typedef struct {
   double ms_forward, ms_forward_tape, ms_adjoint, ms_other;
   uint64_t tape_bytes_peak;
   int64_t accepted_steps, attempts;
+  int64_t cells_general;  /* cells integrated by the general (warp-per-cell, full pivoting) kernels */
+  int64_t cells_deferred; /* cells re-queued because the tape pool of their wave was exhausted */
 } fatode_stats;
 int fatode_get_last_stats(fatode_stats* out);
 

@@ -183,7 +183,7 @@ def test_wave_splitting_is_invisible():
     rtol, atol = driver_tols()
     y0 = perturbed_states(F.initial_state("cbm4"), 40)
     a = F.integrate_adj("cbm4", T0, T1, y0, 32, rtol, atol, icntrl_u=rodas4())
-    F.lib().fatode_set_tape_budget(int(12 * 900 * 3104))      # ~12 cells' worth of tape
+    F.lib().fatode_set_tape_budget(int(12 * 900 * 30336))     # ~12 cells' worth of (fat) tape
     F.lib().fatode_set_wave_cells(16)
     try:
         b = F.integrate_adj("cbm4", T0, T1, y0, 32, rtol, atol, icntrl_u=rodas4())
@@ -193,3 +193,48 @@ def test_wave_splitting_is_invisible():
         F.lib().fatode_set_wave_cells(0)
     for x, y in ((a.y, b.y), (a.lambda_, b.lambda_), (a.mu, b.mu), (a.istatus, b.istatus)):
         assert np.array_equal(x, y)
+
+
+def test_per_thread_and_general_paths_agree():
+    """The one-cell-per-thread kernels (static-pattern LU) and the general warp-per-cell kernels (full pivoting)
+    must give identical forward bits; sensitivities agree to rounding (different summation grouping)."""
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    rtol, atol = driver_tols()
+    y0 = perturbed_states(F.initial_state("cbm4"), 48)
+    fast = F.integrate_adj("cbm4", T0, T1, y0, 32, rtol, atol, icntrl_u=rodas4(), want_mu_sum=True)
+    assert F.last_stats().cells_general == 0
+    F.lib().fatode_set_path(1)
+    try:
+        gen = F.integrate_adj("cbm4", T0, T1, y0, 32, rtol, atol, icntrl_u=rodas4(), want_mu_sum=True)
+        assert F.last_stats().cells_general == 48
+    finally:
+        F.lib().fatode_set_path(0)
+    for a, b in ((fast.y, gen.y), (fast.istatus, gen.istatus), (fast.rstatus, gen.rstatus), (fast.ierr, gen.ierr)):
+        assert np.array_equal(a, b)
+    check_against_oracle(fast, dict(y=gen.y, istatus=gen.istatus, rstatus=gen.rstatus, ierr=gen.ierr, lambda_=gen.lambda_,
+                                    mu=gen.mu), 32)
+
+
+def test_hand_back_of_irregular_cells():
+    """Cells the per-thread kernel gives up on (test hook: every 3rd cell) are integrated by the general kernels;
+    the merged result must not depend on who integrated what."""
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    rtol, atol = driver_tols()
+    y0 = perturbed_states(F.initial_state("cbm4"), 20)
+    t1 = T0 + 12 * 3600.0
+    a = F.integrate_adj("cbm4", T0, t1, y0, 32, rtol, atol, icntrl_u=rodas4(), want_mu_sum=True)
+    fa = F.integrate("cbm4", T0, t1, y0, rtol, atol)
+    F.lib().fatode_debug_irregular_every(3)
+    try:
+        b = F.integrate_adj("cbm4", T0, t1, y0, 32, rtol, atol, icntrl_u=rodas4(), want_mu_sum=True)
+        assert F.last_stats().cells_general == 7
+        fb = F.integrate("cbm4", T0, t1, y0, rtol, atol)
+        assert F.last_stats().cells_general == 7
+    finally:
+        F.lib().fatode_debug_irregular_every(0)
+    for x, y in ((a.y, b.y), (a.istatus, b.istatus), (a.rstatus, b.rstatus), (fa.y, fb.y), (fa.istatus, fb.istatus)):
+        assert np.array_equal(x, y)
+    check_against_oracle(b, dict(y=a.y, istatus=a.istatus, rstatus=a.rstatus, ierr=a.ierr, lambda_=a.lambda_, mu=a.mu), 32)
+    assert np.all(np.abs(a.mu_sum - b.mu_sum) <= 1e-9 * np.abs(a.mu).sum(axis=0) + 1e-300)

@@ -1,0 +1,392 @@
+#!/usr/bin/env python3
+"""Generate fatode_b200/csrc/gen/cbm4_cell_gen.h — CBM-IV as straight-line per-thread code
+("one cell per thread" forward sweep; PRODUCT side, no oracle code involved).
+
+The reference's KPP module (EXAMPLES/cbm4/CBM4_ROS_ADJ/cbm4_Parameters.F90) is restated statement by
+statement with Fortran's evaluation order and REAL(4) literal rounding, so FUN and
+JAC are bit-identical to the reference arithmetic when compiled without FMA contraction.
+
+Linear algebra: the reference factorises E = 1/(h*gamma) I - J with netlib DGETF2 (partial pivoting).
+Along CBM-IV trajectories the pivot sequence is almost static: over 6.7e5 factorisations of perturbed
+cells only four interchanges ever occur (column 12 with row 19, 18 with 27, 21 with 26, 26 with 27;
+0-based).  The generated `lu_factor` is DGETF2 restricted to exactly those candidate interchanges:
+  * the symbolic pattern is the union over all 2^4 interchange outcomes (in "position" space, rows are
+    physically exchanged like DSWAP does), 367 of 1024 entries, 884 multiply-adds;
+  * at every column the IDAMAX decision is re-derived from the data; an unforeseen pivot, a pivot below
+    DLAMCH('S') or a zero pivot returns non-zero and the caller hands the cell to the general
+    (warp-per-cell, full pivoting) kernel;
+  * operations on structural zeros of the actual variant add exact zeros, so the factors and the
+    DGETRS('N') substitutions are bit-identical to netlib's (DGER/DTRSM skip exact zeros).
+`lu_solve` is DGETRS('N') on that pattern (true divisions by the diagonal, like DTRSM).
+
+Adjoint-side helpers (values the backward sweep needs per stage; not bit-critical): jac_values,
+jac_time, hess_values, build_M, param_terms.
+
+The header compiles for the device (nvcc -fmad=false) and for the host (g++ -ffp-contract=off; used by
+tests/test_cell_codegen.py to check the generated LU/solve against the oracle's DGETF2/DGETRS bit for bit).
+Usage: python tools/gen_cbm4_cell.py [reference_root]
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import f90expr as fx  # noqa: E402
+import gen_cbm4_device as gd  # noqa: E402
+
+REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+SRC = os.path.join(REF, "EXAMPLES/cbm4/CBM4_ROS_ADJ/cbm4_Parameters.F90")
+N = 32
+SWAPS = [(12, 19), (18, 27), (21, 26), (26, 27)]   # allowed DGETF2 interchanges (column, partner row), 0-based
+
+
+def symbolic(jpat):
+    """Union-pattern symbolic DGETF2 with the candidate interchanges.  Returns the final pattern and the
+    per-column work lists (cand, swap columns, rows, cols) in elimination order."""
+    P = [[False] * N for _ in range(N)]
+    for (r, c) in jpat:
+        P[r][c] = True
+    for i in range(N):
+        P[i][i] = True
+    steps = []
+    for k in range(N):
+        cand = [i for i in range(k, N) if P[i][k]]
+        sw = [p for (kk, p) in SWAPS if kk == k]
+        assert len(sw) <= 1
+        swcols = None
+        if sw:
+            p = sw[0]
+            assert p in cand, (k, p, cand)
+            swcols = [c for c in range(N) if P[k][c] or P[p][c]]
+            for c in swcols:
+                P[k][c] = P[p][c] = True
+        rows = [i for i in range(k + 1, N) if P[i][k]]
+        cols = [c for c in range(k + 1, N) if P[k][c]]
+        for i in rows:
+            for c in cols:
+                P[i][c] = True
+        steps.append(dict(k=k, cand=cand, p=sw[0] if sw else None, swcols=swcols, rows=rows, cols=cols))
+    return P, steps
+
+
+def emit_paired(w, name, exprs):
+    """out[e] = expr_e, stored two at a time (16-byte stores: the outputs go straight to the tape in HBM)"""
+    n = len(exprs)
+    for e in range(0, n - 1, 2):
+        w(f"  {{ const double a = {exprs[e]}; const double b = {exprs[e + 1]};")
+        w(f"    *reinterpret_cast<double2*>({name} + {e}) = make_double2(a, b); }}")
+    if n % 2:
+        w(f"  {name}[{n - 1}] = {exprs[n - 1]};")
+
+
+def main():
+    text = open(SRC).read()
+    mech = gd.parse_mechanism(text)
+    body = lambda nm: fx.parse_assignments(fx.routine_body(text, nm))
+    photo_idx = sorted(mech.photo)          # reaction indices (0-based) with RCONST = c*SUN
+    ph_of = {r: k for k, r in enumerate(photo_idx)}
+
+    def ref(name, idx):
+        if name == "RCT":
+            r = idx[0] - 1
+            return f"PH[{ph_of[r]}]" if r in ph_of else f"CBM4_CELL_RC({r})"
+        if name == "F":
+            assert idx == (1,)
+            return "F"
+        if name in ("V", "VDOT", "HESS"):              # thread-private vectors: stride SV (shared-memory slots)
+            return f"{name}[{idx[0]-1} * SV]"
+        if name in ("A", "B", "D2A"):                   # routine-local temporaries (registers)
+            return f"{name}[{idx[0]-1}]"
+        raise ValueError((name, idx))
+
+    jent = mech.jent                       # (row, col) of the 276 Jacobian entries, by column then row
+    jpos = {rc: e for e, rc in enumerate(jent)}
+    P, steps = symbolic(jent)
+    idx = {}
+    for i in range(N):
+        for c in range(N):
+            if P[i][c]:
+                idx[(i, c)] = len(idx)
+    NLU = len(idx)
+    rowptr = []
+    for i in range(N):
+        rowptr.append(min(v for (r, c), v in idx.items() if r == i))
+    rowptr.append(NLU)
+    diag = [idx[(i, i)] for i in range(N)]
+    nupd = sum(len(s["rows"]) * len(s["cols"]) for s in steps)
+
+    o = []
+    w = o.append
+    w("// GENERATED by tools/gen_cbm4_cell.py from the reference's CBM-IV mechanism")
+    w("// (EXAMPLES/cbm4/CBM4_ROS_ADJ/cbm4_Parameters.F90) — do not edit.  PRODUCT side:")
+    w("// straight-line per-thread code (one cell per thread) + DGETF2/DGETRS on the static union pattern.")
+    w("// The includer defines CBM4_CELL_FN / CBM4_CELL_INL (function qualifiers) and CBM4_CELL_RC(r) (time-independent rate")
+    w("// coefficient r), CBM4_CELL_HESS(h) (the constant Hessian values) and, on the host, a double2 type with")
+    w("// make_double2; compile without FMA contraction.")
+    w("#pragma once")
+    w("#include <math.h>")
+    w("#include <float.h>")
+    w("namespace cbm4_cell {")
+    w(f"constexpr int NVAR = {N}, NLU = {NLU}, NLU_UPDATES = {nupd}, NJ = {len(jent)}, NM = {mech.NM}, NHESS = 258, "
+      f"NJT = {len(mech.jtime)}, NPHOTO = {len(photo_idx)}, NPAR = {gd.NP};")
+    w(f"// allowed interchanges: bit b of `swaps` = column {[k for k, _ in SWAPS]} exchanged with row {[p for _, p in SWAPS]}")
+    w(f"constexpr int NSWAP = {len(SWAPS)};")
+    w(f"constexpr int SWAP_COL[{len(SWAPS)}] = {{{', '.join(str(k) for k, _ in SWAPS)}}};")
+    w(f"constexpr int SWAP_ROW[{len(SWAPS)}] = {{{', '.join(str(p) for _, p in SWAPS)}}};")
+    w(f"// row-major storage of the union pattern: entries of row i are LU_ROWPTR[i]..LU_ROWPTR[i+1]-1, columns LU_COL[]")
+    w(f"constexpr int LU_ROWPTR[{N + 1}] = {{{', '.join(map(str, rowptr))}}};")
+    cols_flat = [c for (i, c), v in sorted(idx.items(), key=lambda kv: kv[1])]
+    w(f"constexpr unsigned char LU_COL[{NLU}] = {{{', '.join(map(str, cols_flat))}}};")
+    w(f"constexpr int LU_DIAG[{N}] = {{{', '.join(map(str, diag))}}};")
+    w(f"constexpr int PHOTO_IDX[{len(photo_idx)}] = {{{', '.join(map(str, photo_idx))}}};")
+    w(f"constexpr double PHOTO_C[{len(photo_idx)}] = {{{', '.join(fx.c_double(mech.photo[r]) for r in photo_idx)}}};")
+    w("")
+
+    # ------------------------------------------------------------------ FUN
+    w("// CBM4_FUN (:320-449): VDOT = f(V) with RCT = (constants, PH = photolysis rates at the current time)")
+    w("template <int SV> CBM4_CELL_FN void fun(const double* __restrict__ V, const double F, const double* __restrict__ PH, "
+      "double* __restrict__ VDOT) {")
+    w("  double A[81];")
+    for a in body("CBM4_FUN"):
+        w(f"  {ref(a.lhs.name, a.lhs.idx)} = {fx.emit_c(a.rhs, ref)};")
+    w("}")
+    w("")
+
+    # ------------------------------------------------------------------ E = ghinv*I - J on the union pattern
+    jac = body("CBM4_JAC")
+    w("// CBM4_JAC (:451-1016) fused with lss_decomp's  e = -fjac; e(j,j) = e(j,j) + 1/(h*gamma)  (LS_Solver.F90:36-40):")
+    w("// writes E on the union pattern (fill positions = 0)")
+    w("template <int SV> CBM4_CELL_FN void build_E(const double* __restrict__ V, const double F, const double* __restrict__ PH, "
+      "const double ghinv, double* __restrict__ lu) {")
+    w("  double B[138];")
+    written = set()
+    for a in jac:
+        if a.lhs.name == "B":
+            w(f"  B[{a.lhs.idx[0]-1}] = {fx.emit_c(a.rhs, ref)};")
+    for a in jac:
+        if a.lhs.name == "JV":
+            r, c = a.lhs.idx[0] - 1, a.lhs.idx[1] - 1
+            e = f"(-{fx.emit_c(a.rhs, ref)})"
+            if r == c:
+                e = f"({e} + ghinv)"
+            w(f"  lu[{idx[(r, c)]} * SV] = {e};")
+            written.add((r, c))
+    assert len(written) == len(jent)
+    for (r, c), v in sorted(idx.items(), key=lambda kv: kv[1]):
+        if (r, c) not in written:
+            w(f"  lu[{v} * SV] = 0.0;")
+    w("}")
+    w("")
+
+    # ------------------------------------------------------------------ DGETF2 on the union pattern
+    w("// |x| as an ordered integer (IEEE doubles of equal sign order like their bit patterns)")
+    w("CBM4_CELL_INL unsigned long long absbits(double x) {")
+    w("#ifdef __CUDA_ARCH__")
+    w("  return (unsigned long long)__double_as_longlong(x) & 0x7fffffffffffffffull;")
+    w("#else")
+    w("  unsigned long long u; __builtin_memcpy(&u, &x, 8); return u & 0x7fffffffffffffffull;")
+    w("#endif")
+    w("}")
+    w("// DGETF2 restricted to the candidate interchanges.  lu: E in, L\\U out (row-major union pattern, rows in")
+    w("// pivoted order like LAPACK's in-place result).  dinv[k] = 1/U(k,k).  swaps: bit b set = interchange b taken.")
+    w("// Returns 0 when netlib's DGETF2 would have made exactly these choices with pivots >= DLAMCH('S'); non-zero")
+    w("// otherwise (unforeseen pivot row / tiny or zero pivot): the factors are then meaningless.")
+    w("template <int SV> CBM4_CELL_FN int lu_factor(double* __restrict__ lu, double* __restrict__ dinv, unsigned& swaps) {")
+    w("  int bad = 0;")
+    w("  unsigned sw = 0u;")
+    for s in steps:
+        k = s["k"]
+        cand = s["cand"]
+        w(f"  {{  // column {k}")
+        if s["p"] is not None:
+            p = s["p"]
+            b = [i for i, (kk, _) in enumerate(SWAPS) if kk == k][0]
+            w(f"    unsigned long long dmax = absbits(lu[{idx[(k, k)]} * SV]); int jp = {k};")
+            for i in cand[1:]:
+                w(f"    {{ const unsigned long long v = absbits(lu[{idx[(i, k)]} * SV]); if (v > dmax) {{ dmax = v; jp = {i}; }} }}")
+            w(f"    const bool take = (jp == {p});")
+            w(f"    bad |= (jp != {k}) & (jp != {p});")
+            w(f"    if (take) {{")
+            w(f"      sw |= {1 << b}u;")
+            for c in s["swcols"]:
+                w(f"      {{ const double t = lu[{idx[(k, c)]} * SV]; lu[{idx[(k, c)]} * SV] = lu[{idx[(p, c)]} * SV]; lu[{idx[(p, c)]} * SV] = t; }}")
+            w("    }")
+        elif len(cand) > 1:
+            w(f"    const unsigned long long d = absbits(lu[{idx[(k, k)]} * SV]);")
+            terms = " | ".join(f"(absbits(lu[{idx[(i, k)]} * SV]) > d)" for i in cand[1:])
+            w(f"    bad |= {terms};")
+        w(f"    const double piv = lu[{idx[(k, k)]} * SV];")
+        w(f"    bad |= !(fabs(piv) >= DBL_MIN);")
+        w(f"    const double r = 1.0 / piv;")
+        w(f"    dinv[{k} * SV] = r;")
+        if k < N - 1:
+            for i in s["rows"]:
+                w(f"    const double l{i} = r * lu[{idx[(i, k)]} * SV]; lu[{idx[(i, k)]} * SV] = l{i};")
+            for c in s["cols"]:
+                w(f"    {{ const double t = -lu[{idx[(k, c)]} * SV];")
+                for i in s["rows"]:
+                    w(f"      lu[{idx[(i, c)]} * SV] = lu[{idx[(i, c)]} * SV] + l{i} * t;")
+                w("    }")
+        w("  }")
+    w("  swaps = sw;")
+    w("  return bad;")
+    w("}")
+    w("")
+
+    # ------------------------------------------------------------------ DGETRS('N')
+    w("// DGETRS('N'), one right-hand side, on the factors of lu_factor: DLASWP, DTRSM(L,L,N,U), DTRSM(L,U,N,N)")
+    w("template <int SV> CBM4_CELL_FN void lu_solve(const double* __restrict__ lu, const unsigned swaps, double* __restrict__ b) {")
+    for bi, (k, p) in enumerate(SWAPS):
+        w(f"  if (swaps & {1 << bi}u) {{ const double t = b[{k} * SV]; b[{k} * SV] = b[{p} * SV]; b[{p} * SV] = t; }}")
+    for k in range(N - 1):
+        rows = [i for i in range(k + 1, N) if P[i][k]]
+        if not rows:
+            continue
+        w(f"  {{ const double bk = b[{k} * SV];")
+        for i in rows:
+            w(f"    b[{i} * SV] = b[{i} * SV] - bk * lu[{idx[(i, k)]} * SV];")
+        w("  }")
+    for k in range(N - 1, -1, -1):
+        rows = [i for i in range(k) if P[i][k]]
+        w(f"  {{ const double bk = b[{k} * SV] / lu[{idx[(k, k)]} * SV]; b[{k} * SV] = bk;")
+        for i in rows:
+            w(f"    b[{i} * SV] = b[{i} * SV] - bk * lu[{idx[(i, k)]} * SV];")
+        w("  }")
+    w("}")
+    w("")
+
+    # ------------------------------------------------------------------ DGETRS('T') for the backward sweep
+    w("// x <- (P L U)^-T x with the vector in registers (backward sweep: lane = adjoint column; lu/dinv are per-cell")
+    w("// arrays read with warp-uniform addresses).  U^T and L^T substitutions in axpy form, then the interchanges in")
+    w("// reverse order (DGETRS('T'): DTRSM(L,U,T,N), DTRSM(L,L,T,U), DLASWP(-1)).  Uses fma and 1/U(k,k): agrees with")
+    w("// netlib to rounding, not bitwise.")
+    w("CBM4_CELL_INL void lut_solve(const double* __restrict__ lu, const double* __restrict__ dinv, const unsigned swaps, "
+      "double (&x)[32]) {")
+    nf = 0
+    for k in range(N):
+        cols = [c for c in range(k + 1, N) if P[k][c]]
+        w(f"  {{ const double wk = x[{k}] * dinv[{k}]; x[{k}] = wk;")
+        for c in cols:
+            w(f"    x[{c}] = fma(-lu[{idx[(k, c)]}], wk, x[{c}]);")
+            nf += 1
+        w("  }")
+    for k in range(N - 1, 0, -1):
+        cols = [c for c in range(k) if P[k][c]]
+        if not cols:
+            continue
+        w(f"  {{ const double zk = x[{k}];")
+        for c in cols:
+            w(f"    x[{c}] = fma(-lu[{idx[(k, c)]}], zk, x[{c}]);")
+            nf += 1
+        w("  }")
+    for bi in range(len(SWAPS) - 1, -1, -1):
+        k, p_ = SWAPS[bi]
+        w(f"  if (swaps & {1 << bi}u) {{ const double t = x[{k}]; x[{k}] = x[{p_}]; x[{p_}] = t; }}")
+    w("}")
+    w(f"constexpr int LUT_SOLVE_FMA = {nf};")
+    w("")
+    # ------------------------------------------------------------------ adjoint-side helpers
+    w("// J(T,Y) values in the entry order of cbm4_dev::JAC_ROW/JAC_COL (by column, then row)")
+    w("template <int SV> CBM4_CELL_FN void jac_values(const double* __restrict__ V, const double F, const double* __restrict__ PH, "
+      "double* __restrict__ JV) {")
+    w("  double B[138];")
+    for a in jac:
+        if a.lhs.name == "B":
+            w(f"  B[{a.lhs.idx[0]-1}] = {fx.emit_c(a.rhs, ref)};")
+    jexpr = [None] * len(jent)
+    for a in jac:
+        if a.lhs.name == "JV":
+            r, c = a.lhs.idx[0] - 1, a.lhs.idx[1] - 1
+            jexpr[jpos[(r, c)]] = fx.emit_c(a.rhs, ref)
+    emit_paired(w, "JV", jexpr)
+    w("}")
+    # time-dependent entries only
+    tset = {jent[i]: n for n, i in enumerate(mech.jtime)}
+    need_b = set()
+
+    def refs_of(e, name, acc):
+        if isinstance(e, fx.Ref):
+            if e.name == name:
+                acc.add(e.idx[0] - 1)
+        elif isinstance(e, fx.Neg):
+            refs_of(e.a, name, acc)
+        elif isinstance(e, fx.Bin):
+            refs_of(e.a, name, acc)
+            refs_of(e.b, name, acc)
+    for a in jac:
+        if a.lhs.name == "JV" and (a.lhs.idx[0] - 1, a.lhs.idx[1] - 1) in tset:
+            refs_of(a.rhs, "B", need_b)
+    w("// the NJT entries of J that depend on time (through a photolysis rate), same arithmetic as jac_values;")
+    w("// JT[n] is entry cbm4_dev::JAC_TIME[n]")
+    w("template <int SV> CBM4_CELL_FN void jac_time(const double* __restrict__ V, const double F, const double* __restrict__ PH, "
+      "double* __restrict__ JT) {")
+    w("  double B[138];")
+    for a in jac:
+        if a.lhs.name == "B" and (a.lhs.idx[0] - 1) in need_b:
+            w(f"  B[{a.lhs.idx[0]-1}] = {fx.emit_c(a.rhs, ref)};")
+    for a in jac:
+        if a.lhs.name == "JV":
+            rc = (a.lhs.idx[0] - 1, a.lhs.idx[1] - 1)
+            if rc in tset:
+                w(f"  JT[{tset[rc]}] = {fx.emit_c(a.rhs, ref)};")
+    w("}")
+    w("// Hessian (:1190-1853)")
+    w("template <int SV> CBM4_CELL_FN void hess_values(const double* __restrict__ V, const double F, const double* __restrict__ PH, "
+      "double* __restrict__ HESS) {")
+    w("  double D2A[59];")
+    for a in body("Hessian"):
+        w(f"  {ref(a.lhs.name, a.lhs.idx)} = {fx.emit_c(a.rhs, ref)};")
+    w("}")
+    w("// M'[e] = sum_t HESS[h]*K[c] (CBM4_HessTR_Vec :1869-2023 regrouped as the sparse matrix (Hess x K))")
+    w("//         + hg * dJdt[n] on the time-dependent Jacobian entries; entry order = cbm4_dev's MV order.")
+    w("// CBM-IV is at most bimolecular: HESS depends on the rate coefficients only (no V, no SUN), i.e. it is a per-call")
+    w("// constant vector that the includer provides as CBM4_CELL_HESS(h) (filled once from hess_values).")
+    w("template <int SV> CBM4_CELL_FN void build_M(const double* __restrict__ K, "
+      "const double* __restrict__ DJ, const double hg, double* __restrict__ MV) {")
+    jt_of = {jent[i]: n for n, i in enumerate(mech.jtime)}
+    mexpr = []
+    for e, kr in enumerate(mech.mpat):
+        terms = mech.M.get(kr, [])
+        sx = None
+        for (h, c) in terms:
+            t = f"CBM4_CELL_HESS({h}) * K[{c} * SV]"
+            sx = t if sx is None else f"({sx} + {t})"
+        if kr in jt_of:
+            t = f"hg * DJ[{jt_of[kr]}]"
+            sx = t if sx is None else f"({t} + {sx})"
+        mexpr.append(sx if sx is not None else "0.0")
+    emit_paired(w, "MV", mexpr)
+    w("}")
+    w("// AP[p] = ARP_p(Y_i) (dFun_dRcoeff :1135-1175) + sum_t JVRP_t(Y0)*K[col_t] (dJac_dRcoeff :2330-2380), p = 0..28")
+
+    def l1_expr(ent, vec):
+        lit, rct, ops = ent
+        assert rct < 0
+        e = fx.c_double(lit)
+        for op in ops:
+            if op == gd.OP_ONE:
+                continue
+            e = f"({e} * {'F' if op == gd.OP_F else ('2.0' if op == gd.OP_TWO else f'{vec}[{op} * SV]')})"
+        return e
+    w("template <int SV> CBM4_CELL_FN void param_terms(const double* __restrict__ YI, const double* __restrict__ Y0, const double F, "
+      "const double* __restrict__ K, double* __restrict__ AP) {")
+    pexpr = []
+    for p in range(gd.NP):
+        j = gd.JCOEFF[p]
+        e = l1_expr(mech.ARP[j - 1], "YI")
+        for k in range(mech.CROW[j - 1] - 1, mech.CROW[j] - 1):
+            e = f"({e} + {l1_expr(mech.JVRP[k], 'Y0')} * K[{mech.ICOL[k] - 1} * SV])"
+        pexpr.append(e)
+    pexpr.append("0.0")   # pad to an even count (AP has 30 slots)
+    emit_paired(w, "AP", pexpr)
+    w("}")
+    w("}  // namespace cbm4_cell")
+
+    outdir = os.path.join(HERE, "..", "fatode_b200", "csrc", "gen")
+    open(os.path.join(outdir, "cbm4_cell_gen.h"), "w").write("\n".join(o) + "\n")
+    nl = sum(1 for (i, c) in idx if c < i)
+    print(f"NLU={NLU} (L {nl}, U {NLU - nl - N}) updates={nupd} lines={len(o)}")
+
+
+if __name__ == "__main__":
+    main()

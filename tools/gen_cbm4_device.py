@@ -119,8 +119,10 @@ def schedule_l2(l2_lists):
 
 
 # ---------------------------------------------------------------- main
-def main():
-    text = open(SRC).read()
+def parse_mechanism(text):
+    """Reads the KPP module text into the two-level sum-of-products description (shared by the warp and the
+    per-thread generators).  Returns a namespace with A, VD, B, JV, jent, D2A, HE, M, mpat, jtime, photo, arr,
+    ARP, JVRP, CROW, ICOL, CCOL, IROW, st, NJ, NM."""
     body = lambda nm: fx.parse_assignments(fx.routine_body(text, nm))
 
     # ---- rate coefficients (Update_RCONST)
@@ -206,6 +208,37 @@ def main():
             if x:
                 st.append(-fx.parse_number(x[1:]).value if x.startswith("-") else fx.parse_number(x).value)
     assert len(st) == 329
+
+    import types
+    return types.SimpleNamespace(**{k: v for k, v in locals().items() if k not in ("text", "body", "tab", "terms")})
+
+
+def main():
+    text = open(SRC).read()
+    mech = parse_mechanism(text)
+    arr = mech.arr
+    photo = mech.photo
+    A = mech.A
+    VD = mech.VD
+    B = mech.B
+    JV = mech.JV
+    bpos = mech.bpos
+    jent = mech.jent
+    NJ = mech.NJ
+    D2A = mech.D2A
+    HE = mech.HE
+    M = mech.M
+    photoB = mech.photoB
+    jtime = mech.jtime
+    mpat = mech.mpat
+    NM = mech.NM
+    ARP = mech.ARP
+    JVRP = mech.JVRP
+    CROW = mech.CROW
+    ICOL = mech.ICOL
+    CCOL = mech.CCOL
+    IROW = mech.IROW
+    st = mech.st
 
     o = []
     w = o.append
