@@ -726,8 +726,7 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
       CUDA_TRY(cudaMemcpyAsync(g_order.p, order.data(), sizeof(int) * n_ok, cudaMemcpyHostToDevice, st));
       tm.start();
       {   // per-stage blocks of the tape: one thread per (step, stage)
-        const long items = (long)chunks_used * FT_CHUNK * rp.S;
-        k_expand_tape<Cell><<<(unsigned)((items + 127) / 128), 128, 0, st>>>(
+        k_expand_tape<Cell><<<chunks_used, FT_CHUNK * rp.S, 0, st>>>(
             rp, mc, chunks_used, g_owner.as<int>(), g_ids.as<int>(), d_ierr, g_wnacc.as<int>(), g_wlast.as<int>(),
             g_tape.as<double>(), with_mu ? 1 : 0);
         CUDA_TRY(cudaGetLastError());

@@ -52,12 +52,12 @@ __device__ __forceinline__ void wait(void* bar, uint32_t parity) {
 }
 }  // namespace mbar
 
-// k_expand_tape: fills the per-stage blocks of the fat tape from what the forward sweep recorded (T, H, Y(T), K_1..K_S):
+// k_expand_tape: fills the per-stage blocks of the fat tape from what the forward sweep recorded (T, H, Ystage, K_1..K_S):
 //   JV = J(T_i, Y_i) values (:1311), MV = M'_i = Hess(T,Y) x K_i + h*gamma_i*dJ/dt (:1330, :1379-1403),
 //   AP = a_p = dF/dp reactant product at Y_i + (dJ/dp x K_i) at Y (:1348, :1363).
 // None of it depends on the adjoint variables, every (step, stage) is independent: one thread per item, millions of
 // threads per wave, so the straight-line model code runs at full occupancy instead of inside the latency-bound
-// forward loop.  Thread layout: item = ((chunk * FT_CHUNK + slot) * S + stage).
+// forward loop.
 // once per call: Hessian(T) of the mechanism into a staging buffer (copied to c_cbm4_hess by the host)
 __global__ void k_cbm4_hess(double fix, double* __restrict__ out) {
   double y[32], ph[cbm4_cell::NPHOTO];
@@ -66,44 +66,49 @@ __global__ void k_cbm4_hess(double fix, double* __restrict__ out) {
   cbm4_cell::hess_values<1>(y, fix, ph, out);
 }
 
+constexpr int XP_ROW = 226;   // shared-memory row of one step's inputs (Y0 + K = 224 doubles, +2: conflict-free across steps)
 template <class Cell>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(FT_CHUNK * 6, 4)
 k_expand_tape(RosParams rp, typename Cell::Const mc, unsigned nchunks, const int* __restrict__ chunk_owner,
               const int* __restrict__ ids, const int* __restrict__ ierr, const int* __restrict__ nacc,
               const int* __restrict__ last_chunk, double* __restrict__ tape, int with_mu) {
+  // one block per tape chunk (FT_CHUNK steps x S stages = one thread per item); the steps' inputs are staged through
+  // shared memory with coalesced loads, the outputs go straight to the tape
+  __shared__ __align__(16) double in_s[FT_CHUNK * XP_ROW];
   constexpr int N = Cell::N;
   const int S = rp.S;
-  const long item = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int is = (int)(item % S);
-  const long t = item / S;
-  const int q = (int)(t % FT_CHUNK);
-  const long c = t / FT_CHUNK;
-  if (c >= (long)nchunks) return;
+  const long c = blockIdx.x;
   const int w = chunk_owner[c];
   if (ierr[ids ? ids[w] : w] != 1) return;
   const int cnt = (c == last_chunk[w]) ? ((nacc[w] - 1) % FT_CHUNK) + 1 : FT_CHUNK;
+  const int NE = fat_entry_doubles(S);
+  double* chunk = tape + (size_t)c * FT_CHUNK * NE;
+  const int row2 = (N + S * N) / 2;   // double2 per step
+  for (int idx = threadIdx.x; idx < cnt * row2; idx += blockDim.x) {
+    const int q = idx / row2, o = idx - q * row2;
+    *reinterpret_cast<double2*>(in_s + q * XP_ROW + 2 * o) = *reinterpret_cast<const double2*>(chunk + (size_t)q * NE + FT_Y0 + 2 * o);
+  }
+  __syncthreads();
+  const int q = threadIdx.x / S, is = threadIdx.x - q * S;
   if (q >= cnt) return;
-  double* e = tape + ((size_t)c * FT_CHUNK + q) * fat_entry_doubles(S);
+  double* e = chunk + (size_t)q * NE;
   const double T = e[0], H = e[1];
   const double dDir = (rp.tend >= rp.tstart) ? 1.0 : -1.0;
+  const double* in = in_s + q * XP_ROW;      // [Y0(32)][K(S x 32)]
   double Y0[N], Yi[N], Ki[N], DJ[cbm4_cell::NJT], JT0[cbm4_cell::NJT], PHT[Cell::NPH], PHS[Cell::NPH];
-#pragma unroll 8
-  for (int i = 0; i < N; i += 2) {
-    const double2 a = *reinterpret_cast<const double2*>(e + FT_Y0 + i);
-    Y0[i] = a.x; Y0[i + 1] = a.y;
-    const double2 b = *reinterpret_cast<const double2*>(e + FT_K + is * N + i);
-    Ki[i] = b.x; Ki[i + 1] = b.y;
-  }
-  // Y_i as the forward sweep formed it: refreshed only at stages with ros_NewF (stale otherwise, :1015-1018)
+#pragma unroll
+  for (int i = 0; i < N; ++i) { Y0[i] = in[i]; Ki[i] = in[N + is * N + i]; }
+  // Y_i as the forward sweep formed it (same operations, same order): refreshed only at stages with ros_NewF,
+  // stale otherwise (:1015-1018)
   int sr = is;
   while (sr > 0 && !rp.NewF[sr]) --sr;
-#pragma unroll 8
+#pragma unroll
   for (int i = 0; i < N; ++i) Yi[i] = Y0[i];
   for (int j = 0; j < sr; ++j) {
     const double a = rp.A[sr * (sr - 1) / 2 + j];
     if (a != 0.0) {
-      const double* kj = e + FT_K + j * N;
-#pragma unroll 8
+      const double* kj = in + N + j * N;
+#pragma unroll
       for (int i = 0; i < N; ++i) Yi[i] = __dadd_rn(Yi[i], __dmul_rn(a, kj[i]));
     }
   }
@@ -126,7 +131,7 @@ k_expand_tape(RosParams rp, typename Cell::Const mc, unsigned nchunks, const int
   cbm4_cell::build_M<1>(Ki, DJ, rp.autonomous ? 0.0 : H * rp.Gamma[is], sb + FT_MV);
   if (with_mu) cbm4_cell::param_terms<1>(Yi, Y0, mc.fix, Ki, sb + FT_AP);
   else
-    for (int p = 0; p < 30; ++p) sb[FT_AP + p] = 0.0;
+    for (int p = 0; p < 32; p += 4) st_global_256(sb + FT_AP + p, 0.0, 0.0, 0.0, 0.0);
 }
 
 template <class Model, int HALF>

@@ -31,6 +31,11 @@
 
 namespace fatode {
 
+// 32-byte store (one full DRAM sector) to 32-byte aligned global memory: STG.256
+__device__ __forceinline__ void st_global_256(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 __constant__ double c_cbm4_rc[81];     // RCONST with the time-independent entries (set per call by the host)
 __constant__ double c_cbm4_hess[258];  // Hessian values: rate coefficients only for this mechanism (set per call)
 
@@ -40,6 +45,7 @@ __constant__ double c_cbm4_hess[258];  // Hessian values: rate coefficients only
 #define CBM4_CELL_INL __device__ __forceinline__
 #define CBM4_CELL_RC(r) fatode::c_cbm4_rc[r]
 #define CBM4_CELL_HESS(h) fatode::c_cbm4_hess[h]
+#define CBM4_CELL_ST4(p, a, b, c, d) fatode::st_global_256(p, a, b, c, d)
 #include "gen/cbm4_cell_gen.h"
 
 namespace fatode {
@@ -56,11 +62,12 @@ constexpr int FT_STEP_COPY = FT_HDR + FT_LU + FT_DINV;     // what the backward 
 constexpr int FT_Y0 = FT_STEP_COPY;                         // Y(T) [32]   } inputs of k_expand_tape
 constexpr int FT_K = FT_Y0 + 32;                            // K [S][32]   }
 constexpr int FT_STEP = FT_K + 6 * 32;                      // forward-written part of an entry: 632 doubles
-constexpr int FT_JV = 0, FT_MV = 276, FT_AP = 534;          // inside a stage block
-constexpr int FT_STAGE = 564;                               // 4512 B (multiple of 16)
+constexpr int FT_JV = 0, FT_MV = 276, FT_AP = 536;          // inside a stage block (each part 32-byte aligned, zero padded)
+constexpr int FT_STAGE = 568;                               // 4544 B (multiple of 32)
 constexpr int FT_CHUNK = 16;                                // accepted steps per chunk
 __host__ __device__ inline int fat_entry_doubles(int S) { return FT_STEP + S * FT_STAGE; }
-static_assert(cbm4_cell::NLU <= FT_LU && cbm4_cell::NJ == FT_MV && cbm4_cell::NJ + cbm4_cell::NM == FT_AP, "tape layout");
+static_assert(cbm4_cell::NLU <= FT_LU && cbm4_cell::NJ == FT_MV && cbm4_cell::NJ + cbm4_cell::NM <= FT_AP && FT_AP % 4 == 0 &&
+              FT_STAGE % 4 == 0 && FT_STEP % 4 == 0 && FT_MV % 4 == 0, "tape layout");
 
 struct Cbm4Cell {
   static constexpr int N = 32, NP = 29, NLU = cbm4_cell::NLU, NPH = cbm4_cell::NPHOTO;
@@ -267,7 +274,6 @@ k_ros_fwd_cell(RosParams rp, typename Model::Const mc, long nwave, const int* __
         nacc++;
         if (MODE == 1) {
           // ---- ros_DPush, fat form
-          const int NE = fat_entry_doubles(S);
           const int slot = (nacc - 1) % FT_CHUNK;
           if (slot == 0) {
             const unsigned c = atomicAdd(tape.pool_head, 1u);
@@ -276,23 +282,27 @@ k_ros_fwd_cell(RosParams rp, typename Model::Const mc, long nwave, const int* __
             tape.chunk_owner[c] = (int)w;
             cur_chunk = (int)c;
           }
-          double* e = tape.base + ((size_t)cur_chunk * FT_CHUNK + slot) * NE;
-          e[0] = T; e[1] = H; e[2] = (double)swaps; e[3] = 0.0;
+          double* e = tape.base + ((size_t)cur_chunk * FT_CHUNK + slot) * fat_entry_doubles(S);
+          st_global_256(e, T, H, (double)swaps, 0.0);
           double* el = e + FT_HDR;
-#pragma unroll 8
-          for (int q = 0; q < Model::NLU - 1; q += 2) *reinterpret_cast<double2*>(el + q) = make_double2(lu[q * SV], lu[(q + 1) * SV]);
-          el[Model::NLU - 1] = lu[(Model::NLU - 1) * SV];
-#pragma unroll 8
-          for (int q = 0; q < N; q += 2)
-            *reinterpret_cast<double2*>(e + FT_HDR + FT_LU + q) = make_double2(dinv[q * SV], dinv[(q + 1) * SV]);
+#pragma unroll 4
+          for (int q = 0; q + 3 < Model::NLU; q += 4) st_global_256(el + q, lu[q * SV], lu[(q + 1) * SV], lu[(q + 2) * SV], lu[(q + 3) * SV]);
+          {
+            constexpr int q = (Model::NLU / 4) * 4;   // tail (NLU = 367: three values + pad)
+            st_global_256(el + q, q < Model::NLU ? lu[q * SV] : 0.0, q + 1 < Model::NLU ? lu[(q + 1) * SV] : 0.0,
+                          q + 2 < Model::NLU ? lu[(q + 2) * SV] : 0.0, 0.0);
+          }
+#pragma unroll 4
+          for (int q = 0; q < N; q += 4)
+            st_global_256(e + FT_HDR + FT_LU + q, dinv[q * SV], dinv[(q + 1) * SV], dinv[(q + 2) * SV], dinv[(q + 3) * SV]);
           // Y(T) and the stage vectors K: k_expand_tape derives the per-stage blocks from them
-#pragma unroll 8
-          for (int q = 0; q < N; q += 2) *reinterpret_cast<double2*>(e + FT_Y0 + q) = make_double2(y[q * SV], y[(q + 1) * SV]);
+#pragma unroll 4
+          for (int q = 0; q < N; q += 4) st_global_256(e + FT_Y0 + q, y[q * SV], y[(q + 1) * SV], y[(q + 2) * SV], y[(q + 3) * SV]);
           for (int j = 0; j < S; ++j) {
             const double* kj = K + j * N * SV;
-#pragma unroll 8
-            for (int q = 0; q < N; q += 2)
-              *reinterpret_cast<double2*>(e + FT_K + j * N + q) = make_double2(kj[q * SV], kj[(q + 1) * SV]);
+#pragma unroll 4
+            for (int q = 0; q < N; q += 4)
+              st_global_256(e + FT_K + j * N + q, kj[q * SV], kj[(q + 1) * SV], kj[(q + 2) * SV], kj[(q + 3) * SV]);
           }
         }
 #pragma unroll 8

@@ -10,12 +10,11 @@
 #include <cmath>
 
 static double g_rc[81], g_hess[258];
-struct double2 { double x, y; };
-static inline double2 make_double2(double a, double b) { double2 r; r.x = a; r.y = b; return r; }
 #define CBM4_CELL_FN static inline
 #define CBM4_CELL_INL static inline
 #define CBM4_CELL_RC(r) g_rc[r]
 #define CBM4_CELL_HESS(h) g_hess[h]
+#define CBM4_CELL_ST4(p, a, b, c, d) do { (p)[0] = (a); (p)[1] = (b); (p)[2] = (c); (p)[3] = (d); } while (0)
 #include "../fatode_b200/csrc/gen/cbm4_cell_gen.h"
 
 static long n_lu = 0, n_lu_bad = 0, n_irregular = 0, n_solve = 0, n_solve_bad = 0, n_swaps[4] = {0, 0, 0, 0};
@@ -140,7 +139,7 @@ int main(int argc, char** argv) {
       ++n_fun;
       for (int i = 0; i < 32; ++i) if (!same(f_ref[i], f_new[i])) { ++bad_fun; break; }
       m.jac(t, y, jac);
-      double lu[cbm4_cell::NLU], jv[cbm4_cell::NJ];
+      double lu[cbm4_cell::NLU], jv[cbm4_cell::NJ + 4];
       const double ghinv = 1.0 / (37.0 * 0.25);
       cbm4_cell::build_E<1>(y, m.fix[0], PH, ghinv, lu);
       for (int i = 0; i < 32; ++i)

@@ -70,13 +70,15 @@ def symbolic(jpat):
 
 
 def emit_paired(w, name, exprs):
-    """out[e] = expr_e, stored two at a time (16-byte stores: the outputs go straight to the tape in HBM)"""
-    n = len(exprs)
-    for e in range(0, n - 1, 2):
-        w(f"  {{ const double a = {exprs[e]}; const double b = {exprs[e + 1]};")
-        w(f"    *reinterpret_cast<double2*>({name} + {e}) = make_double2(a, b); }}")
-    if n % 2:
-        w(f"  {name}[{n - 1}] = {exprs[n - 1]};")
+    """out[e] = expr_e, stored four at a time with one 32-byte store (a full DRAM sector: the outputs go straight to the
+    tape in HBM, partial-sector writes would cost a read-modify-write there).  The list is zero-padded to a multiple
+    of four; CBM4_CELL_ST4(ptr, a, b, c, d) is provided by the includer."""
+    ex = list(exprs)
+    while len(ex) % 4:
+        ex.append("0.0")
+    for e in range(0, len(ex), 4):
+        w(f"  {{ const double a = {ex[e]}; const double b = {ex[e + 1]}; const double c = {ex[e + 2]}; const double d = {ex[e + 3]};")
+        w(f"    CBM4_CELL_ST4({name} + {e}, a, b, c, d); }}")
 
 
 def main():
@@ -121,8 +123,8 @@ def main():
     w("// (EXAMPLES/cbm4/CBM4_ROS_ADJ/cbm4_Parameters.F90) — do not edit.  PRODUCT side:")
     w("// straight-line per-thread code (one cell per thread) + DGETF2/DGETRS on the static union pattern.")
     w("// The includer defines CBM4_CELL_FN / CBM4_CELL_INL (function qualifiers) and CBM4_CELL_RC(r) (time-independent rate")
-    w("// coefficient r), CBM4_CELL_HESS(h) (the constant Hessian values) and, on the host, a double2 type with")
-    w("// make_double2; compile without FMA contraction.")
+    w("// coefficient r), CBM4_CELL_HESS(h) (the constant Hessian values) and CBM4_CELL_ST4(p, a, b, c, d) (store four")
+    w("// consecutive doubles at the 32-byte aligned p); compile without FMA contraction.")
     w("#pragma once")
     w("#include <math.h>")
     w("#include <float.h>")
@@ -377,7 +379,6 @@ def main():
         for k in range(mech.CROW[j - 1] - 1, mech.CROW[j] - 1):
             e = f"({e} + {l1_expr(mech.JVRP[k], 'Y0')} * K[{mech.ICOL[k] - 1} * SV])"
         pexpr.append(e)
-    pexpr.append("0.0")   # pad to an even count (AP has 30 slots)
     emit_paired(w, "AP", pexpr)
     w("}")
     w("}  // namespace cbm4_cell")
