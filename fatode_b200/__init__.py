@@ -58,6 +58,7 @@ def lib():
         L.fatode_set_tape_budget.argtypes = [ctypes.c_uint64]
         L.fatode_set_wave_cells.argtypes = [ctypes.c_int64]
         L.fatode_set_path.argtypes = [ctypes.c_int]
+        L.fatode_set_pipeline.argtypes = [ctypes.c_int]
         L.fatode_debug_irregular_every.argtypes = [ctypes.c_int]
         L.fatode_get_last_stats.argtypes = [ctypes.POINTER(Stats)]
         L.fatode_model_dims.argtypes = [ctypes.c_int, _ip, _ip]

@@ -38,6 +38,7 @@ static thread_local fatode_stats g_stats;
 static uint64_t g_tape_budget = 0;
 static int64_t g_wave_cells = 0;
 static int g_path = 0;                    // 0 = per-thread fast path with general fallback, 1 = general kernels only
+static int g_pipeline = 0;                // 0 = phases back to back (default), 1/2 = forward of the next wave overlapped
 static int g_debug_irregular_every = 0;   // test hook: every k-th cell is pushed through the fallback
 
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -55,6 +56,7 @@ extern "C" const char* fatode_version(void) { return "fatode_b200 0.1 (sm_100a)"
 extern "C" int fatode_set_tape_budget(uint64_t bytes) { g_tape_budget = bytes; return 0; }
 extern "C" int fatode_set_wave_cells(int64_t cells) { g_wave_cells = cells; return 0; }
 extern "C" int fatode_set_path(int mode) { g_path = mode; return 0; }
+extern "C" int fatode_set_pipeline(int mode) { g_pipeline = mode; return 0; }
 extern "C" int fatode_debug_irregular_every(int k) { g_debug_irregular_every = k; return 0; }
 extern "C" int fatode_get_last_stats(fatode_stats* out) { if (!out) return FATODE_EINVAL; *out = g_stats; return 0; }
 
@@ -373,9 +375,11 @@ struct CachedBuf {
 };
 static thread_local CachedBuf g_tape, g_y0, g_nacc, g_off, g_queue, g_part;
 static thread_local CachedBuf g_ids, g_wnacc, g_wlast, g_prev, g_owner, g_order, g_wierr;   // per-thread path
+static void release_pipeline_workspace();
 extern "C" int fatode_release_workspace(void) {
   g_tape.release(); g_y0.release(); g_nacc.release(); g_off.release(); g_queue.release(); g_part.release();
   g_ids.release(); g_wnacc.release(); g_wlast.release(); g_prev.release(); g_owner.release(); g_order.release(); g_wierr.release();
+  release_pipeline_workspace();
   return 0;
 }
 
@@ -599,8 +603,48 @@ __global__ void k_gather_rows_i(int n, const int* __restrict__ ids, const int* _
 }
 
 
-// FAST PATH (models with per-thread code): forward sweep one cell per thread, fat tape from a chunk pool, backward
-// sweep streaming the tape.  Cells that need the general kernels are appended to `general`.
+// FAST PATH (models with per-thread code).
+//   forward-only calls: k_ros_fwd_cell<MODE 0> over all cells.
+//   adjoint calls: a three-stream software pipeline over WAVES of cells and BATCHES inside a wave
+//     sF: k_ros_fwd_cell<MODE 1> of wave k+1  -> step entries (T, H, L\U, Y, K) in a chunk pool (two pools, ping-pong)
+//     sX: k_expand_tape of batch g+1          -> per-stage operands (J_i, M'_i, a_p) in a "fat" buffer (two buffers)
+//     sA: k_ros_adj_cell of batch g           -> Lambda, Mu
+//   The forward kernel occupies one warp and 153 KB of shared memory per SM, the backward kernel four warps, 62 KB and
+//   the tensor memory, so both are resident on every SM at the same time and the latency-bound forward sweep of the
+//   next wave hides behind the backward sweep of the current one.  Cells that need the general kernels are appended
+//   to `general`; cells that found their pool exhausted are re-queued.
+struct StreamSet {
+  cudaStream_t sF = nullptr, sX = nullptr, sA = nullptr;
+  cudaEvent_t comp_free[2] = {nullptr, nullptr}, fat_free[2] = {nullptr, nullptr}, expand_done[2] = {nullptr, nullptr};
+  cudaEvent_t join = nullptr, doneF = nullptr, doneX = nullptr, doneA = nullptr, tables_ready = nullptr;
+  cudaError_t init() {
+    if (sF) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&sF, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithFlags(&sX, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithFlags(&sA, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    cudaEvent_t* all[] = {&comp_free[0], &comp_free[1], &fat_free[0], &fat_free[1], &expand_done[0], &expand_done[1],
+                          &join, &doneF, &doneX, &doneA, &tables_ready};
+    for (cudaEvent_t* ev : all)
+      if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    return cudaSuccess;
+  }
+};
+static thread_local StreamSet g_ss;
+static thread_local CachedBuf g_comp[2], g_fat[2], g_cprev[2], g_cowner[2], g_cseq[2], g_wids[2], g_wnacc2[2], g_wlast2[2],
+    g_border[2], g_bfatoff[2], g_wbatch[2], g_ctr;
+
+static void release_pipeline_workspace() {
+  for (int i = 0; i < 2; ++i) {
+    g_comp[i].release(); g_fat[i].release(); g_cprev[i].release(); g_cowner[i].release(); g_cseq[i].release();
+    g_wids[i].release(); g_wnacc2[i].release(); g_wlast2[i].release(); g_border[i].release(); g_bfatoff[i].release();
+    g_wbatch[i].release();
+  }
+  g_ctr.release();
+}
+
+struct TimedLaunch { cudaEvent_t a, b; int phase; };
+
 template <class Cell, class Warp>
 static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, int64_t ncells, int nadj, bool with_mu,
                            bool do_adjoint, double* d_y, double* d_lambda, double* d_mu, const double* d_atol,
@@ -610,28 +654,21 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_cbm4_rc, mc.rc_base, sizeof(double) * 81, 0, cudaMemcpyHostToDevice, st));
-  if (do_adjoint) {   // constant Hessian values of the mechanism for k_expand_tape
-    CUDA_TRY(g_part.ensure(sizeof(double) * 512));
-    k_cbm4_hess<<<1, 1, 0, st>>>(mc.fix, g_part.as<double>());
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyToSymbolAsync(c_cbm4_hess, g_part.p, sizeof(double) * 258, 0, cudaMemcpyDeviceToDevice, st));
-  }
-  PhaseTimer tm(st);
-  // forward kernel: persistent single-warp blocks, one per SM (188 KB of shared memory each)
-  auto fwd_blocks = [&](int64_t n) { return (unsigned)std::min<int64_t>((n + CELL_LANES - 1) / CELL_LANES, (int64_t)sms); };
-  const size_t cell_smem = CellSmem<Cell>::BYTES;
-  CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd_cell<Cell, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cell_smem));
-  CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd_cell<Cell, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cell_smem));
-  CUDA_TRY(g_queue.ensure(4 * sizeof(unsigned long long)));
-  unsigned long long* d_queue = g_queue.as<unsigned long long>();
-  CellTape tape{nullptr, nullptr, nullptr, nullptr, 0u, nullptr};
+  CUDA_TRY(g_ctr.ensure(16 * sizeof(unsigned long long)));
+  unsigned long long* d_ctr = g_ctr.as<unsigned long long>();   // [0,1] forward queues, [2,3] pool heads, [4,5] backward queues
+  CellTape tape{nullptr, nullptr, nullptr, nullptr, nullptr, 0u, nullptr};
   if (!do_adjoint) {
+    constexpr int LANES = CELL_LANES_SOLO;
+    const size_t cell_smem = CellSmem<Cell, LANES>::BYTES;
+    CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd_cell<Cell, 0, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cell_smem));
     CUDA_TRY(g_wnacc.ensure(sizeof(int) * ncells));
-    CUDA_TRY(cudaMemsetAsync(d_queue, 0, 4 * sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(d_ctr, 0, 16 * sizeof(unsigned long long), st));
+    PhaseTimer tm(st);
     tm.start();
-    k_ros_fwd_cell<Cell, 0><<<fwd_blocks(ncells), CELL_LANES, cell_smem, st>>>(
-        rp, mc, ncells, nullptr, d_y, d_y, d_atol, d_rtol, d_istatus, d_rstatus, d_ierr, g_wnacc.as<int>(), tape, 0,
-        g_debug_irregular_every, d_queue + 2);
+    const unsigned blocks = (unsigned)std::min<int64_t>((ncells + LANES - 1) / LANES, (int64_t)sms);
+    k_ros_fwd_cell<Cell, 0, LANES><<<blocks, 32, cell_smem, st>>>(rp, mc, ncells, nullptr, d_y, d_y, d_atol, d_rtol, d_istatus,
+                                                                  d_rstatus, d_ierr, g_wnacc.as<int>(), tape, 0,
+                                                                  g_debug_irregular_every, d_ctr);
     CUDA_TRY(cudaGetLastError());
     g_stats.ms_forward += tm.stop();
     g_stats.launches++;
@@ -643,72 +680,157 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
       if (h_ierr[c] == IERR_IRREGULAR) general.push_back((int)c);
     return 0;
   }
-  // ---- adjoint mode: waves over a chunk pool
-  const int NE = fat_entry_doubles(rp.S);
-  const size_t chunk_bytes = sizeof(double) * (size_t)NE * FT_CHUNK;
-  size_t free_b = 0, total_b = 0;
-  CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-  size_t budget = g_tape_budget ? (size_t)g_tape_budget : (size_t)(0.6 * (double)free_b);
-  budget = std::min(budget, (size_t)(0.9 * (double)free_b));
-  if (g_tape_budget == 0 && g_tape.cap >= chunk_bytes * 64) budget = g_tape.cap;   // reuse the cached tape
-  const unsigned pool_chunks = (unsigned)std::min<size_t>(budget / chunk_bytes, 0x7fffffffu);
-  if (pool_chunks < 1) return fail(FATODE_ENOMEM, "tape budget smaller than one chunk of the trajectory tape");
-  CUDA_TRY(g_tape.ensure((size_t)pool_chunks * chunk_bytes));
-  CUDA_TRY(g_prev.ensure(sizeof(int) * (size_t)pool_chunks));
-  CUDA_TRY(g_owner.ensure(sizeof(int) * (size_t)pool_chunks));
-  unsigned int* d_head = reinterpret_cast<unsigned int*>(d_queue + 1);
-  const size_t adj_smem = sizeof(double) * (size_t)ADJ3_WARP_DOUBLES * ADJ3_WARPS;
-  CUDA_TRY(cudaFuncSetAttribute(k_ros_adj_cell<Warp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem));
 
-  const int64_t wave_max = std::min<int64_t>(g_wave_cells > 0 ? g_wave_cells : (1 << 20), ncells);
-  CUDA_TRY(g_ids.ensure(sizeof(int) * wave_max));
-  CUDA_TRY(g_wnacc.ensure(sizeof(int) * wave_max));
-  CUDA_TRY(g_wlast.ensure(sizeof(int) * wave_max));
-  CUDA_TRY(g_order.ensure(sizeof(int) * wave_max));
+  // ---- adjoint mode
+  // Pipeline mode 0 (default): forward, expand and backward kernels of a wave run back to back, each with the whole
+  // GPU (forward: 32 cells per SM).  Modes 1/2 overlap the forward sweep of wave k+1 (26 cells per SM, so that a CTA of
+  // the backward kernel fits beside it) with the backward sweep of wave k on separate streams and double-buffered
+  // storage; measured on B200 the co-resident kernels slow each other down by more than the overlap gains (the
+  // forward kernel's 190 KB of straight-line code evicts the backward kernel's from the instruction cache), so it is
+  // kept as an option (fatode_set_pipeline) rather than the default.
+  const int pmode = getenv("FATODE_PIPELINE") ? atoi(getenv("FATODE_PIPELINE")) : g_pipeline;
+  const int nbuf = pmode > 0 ? 2 : 1;
+  const int LANES = pmode > 0 ? CELL_LANES_SHARED : CELL_LANES_SOLO;
+  const int S = rp.S;
+  const size_t cell_smem = pmode > 0 ? CellSmem<Cell, CELL_LANES_SHARED>::BYTES : CellSmem<Cell, CELL_LANES_SOLO>::BYTES;
+  const size_t adj_smem = sizeof(double) * (size_t)ADJ3_WARP_DOUBLES * ADJ3_WARPS;
+  CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd_cell<Cell, 1, CELL_LANES_SHARED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)CellSmem<Cell, CELL_LANES_SHARED>::BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd_cell<Cell, 1, CELL_LANES_SOLO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)CellSmem<Cell, CELL_LANES_SOLO>::BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(k_ros_adj_cell<Warp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem));
+  CUDA_TRY(g_ss.init());
+  StreamSet ss = g_ss;
+  if (pmode <= 1) ss.sX = ss.sF;
+  if (pmode <= 0) ss.sA = ss.sF;
+  {   // constant Hessian values of the mechanism for k_expand_tape
+    CUDA_TRY(g_part.ensure(sizeof(double) * 512));
+    k_cbm4_hess<<<1, 1, 0, st>>>(mc.fix, g_part.as<double>());
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_cbm4_hess, g_part.p, sizeof(double) * 258, 0, cudaMemcpyDeviceToDevice, st));
+  }
+  // memory plan: chunk pool(s) of step entries and fat buffer(s): 22 % + 78 % of the budget, or 2 x (14 % + 36 %)
+  // when the pipeline double-buffers them
+  const size_t chunk_bytes = sizeof(double) * (size_t)FT_STEP * FT_CHUNK;
+  const size_t fat_step_bytes = sizeof(double) * (size_t)fat_step_doubles(S);
+  size_t budget;
+  if (g_tape_budget) budget = (size_t)g_tape_budget;
+  else if (g_comp[0].cap >= chunk_bytes * 64 && g_fat[0].cap >= fat_step_bytes * 64 && (nbuf == 1 || g_comp[1].cap == g_comp[0].cap) &&
+           (nbuf == 2 || g_comp[1].cap == 0))
+    budget = 0;   // reuse the cached buffers
+  else {
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    free_b += g_comp[0].cap + g_comp[1].cap + g_fat[0].cap + g_fat[1].cap;
+    budget = (size_t)(0.6 * (double)free_b);
+  }
+  const size_t comp_bytes = budget ? (size_t)((nbuf == 2 ? 0.14 : 0.22) * (double)budget) : g_comp[0].cap;
+  const size_t fat_bytes = budget ? (size_t)((nbuf == 2 ? 0.36 : 0.78) * (double)budget) : g_fat[0].cap;
+  const unsigned pool_chunks = (unsigned)std::min<size_t>(comp_bytes / chunk_bytes, 0x7fffffffu);
+  const long long fat_steps_cap = (long long)(fat_bytes / fat_step_bytes);
+  if (pool_chunks < 1 || fat_steps_cap < 1) return fail(FATODE_ENOMEM, "tape budget smaller than one chunk of the trajectory tape");
+  if (budget) {
+    for (int i = 0; i < 2; ++i) { g_comp[i].release(); g_fat[i].release(); }   // re-plan (budget or mode changed)
+  }
+  const int64_t wave_max = std::min<int64_t>(g_wave_cells > 0 ? g_wave_cells : (int64_t)sms * LANES, ncells);
+  for (int i = 0; i < nbuf; ++i) {
+    CUDA_TRY(g_comp[i].ensure((size_t)pool_chunks * chunk_bytes));
+    CUDA_TRY(g_fat[i].ensure((size_t)fat_steps_cap * fat_step_bytes));
+    CUDA_TRY(g_cprev[i].ensure(sizeof(int) * (size_t)pool_chunks));
+    CUDA_TRY(g_cowner[i].ensure(sizeof(int) * (size_t)pool_chunks));
+    CUDA_TRY(g_cseq[i].ensure(sizeof(int) * (size_t)pool_chunks));
+    CUDA_TRY(g_wids[i].ensure(sizeof(int) * wave_max));
+    CUDA_TRY(g_wnacc2[i].ensure(sizeof(int) * wave_max));
+    CUDA_TRY(g_wlast2[i].ensure(sizeof(int) * wave_max));
+    CUDA_TRY(g_border[i].ensure(sizeof(int) * wave_max));
+    CUDA_TRY(g_bfatoff[i].ensure(sizeof(long long) * wave_max));
+    CUDA_TRY(g_wbatch[i].ensure(sizeof(int) * wave_max));
+  }
   CUDA_TRY(g_wierr.ensure(sizeof(int) * wave_max));
-  tape.base = g_tape.as<double>();
-  tape.chunk_prev = g_prev.as<int>();
-  tape.chunk_owner = g_owner.as<int>();
-  tape.pool_head = d_head;
-  tape.pool_chunks = pool_chunks;
-  tape.last_chunk = g_wlast.as<int>();
+
+  // the side streams start after whatever precedes this call on the caller's stream
+  CUDA_TRY(cudaEventRecord(ss.join, st));
+  CUDA_TRY(cudaStreamWaitEvent(ss.sF, ss.join, 0));
+  CUDA_TRY(cudaStreamWaitEvent(ss.sX, ss.join, 0));
+  CUDA_TRY(cudaStreamWaitEvent(ss.sA, ss.join, 0));
+
+  std::vector<TimedLaunch> timed;
+  auto t_begin = [&](cudaStream_t s, int phase) -> int {
+    TimedLaunch t{nullptr, nullptr, phase};
+    CUDA_TRY(cudaEventCreate(&t.a));
+    CUDA_TRY(cudaEventCreate(&t.b));
+    CUDA_TRY(cudaEventRecord(t.a, s));
+    timed.push_back(t);
+    return 0;
+  };
+  auto t_end = [&](cudaStream_t s) -> int { CUDA_TRY(cudaEventRecord(timed.back().b, s)); return 0; };
+  const bool dbg = getenv("FATODE_DEBUG_WAVES") != nullptr;
 
   std::vector<int> pending(ncells), next_pending, ids, h_nacc, h_ierr, order;
+  std::vector<long long> h_fatoff;
+  std::vector<int> h_batch;
   for (int64_t c = 0; c < ncells; ++c) pending[c] = (int)c;
   double chunks_per_cell = 0.0;   // running estimate (0 = unknown)
   size_t pos = 0;
+  int k = 0, g = 0;
+  bool comp_used[2] = {false, false}, fat_used[2] = {false, false};
+  int rc_fail = 0;
   while (pos < pending.size() || !next_pending.empty()) {
     if (pos >= pending.size()) { pending.swap(next_pending); next_pending.clear(); pos = 0; }
+    const int p = (nbuf == 2) ? (k & 1) : 0;
     const int64_t remaining = (int64_t)(pending.size() - pos);
-    int64_t cap = chunks_per_cell > 0.0 ? (int64_t)((double)pool_chunks / (chunks_per_cell * 1.02 + 0.5))
-                                        : std::max<int64_t>(1, std::min<int64_t>(1184, pool_chunks / 64));
+    // wave size: what the chunk pool holds; a batch = what one fat buffer holds; both rounded down to a multiple of the
+    // backward kernel's cell slots (4 per SM) so that the last round of cells of every batch is a full one
+    const int64_t slots = (int64_t)sms * ADJ3_WARPS;
+    int64_t cap, batch_cells = 0;
+    if (chunks_per_cell > 0.0) {
+      cap = (int64_t)((double)pool_chunks / (chunks_per_cell * 1.02 + 0.5));
+      batch_cells = (int64_t)((double)fat_steps_cap / (chunks_per_cell * FT_CHUNK * 1.02));
+      if (batch_cells >= slots) batch_cells = batch_cells / slots * slots;
+      batch_cells = std::max<int64_t>(batch_cells, 1);
+      if (cap >= slots) cap = cap / slots * slots;
+    } else {
+      cap = std::max<int64_t>(1, std::min<int64_t>(2 * slots, pool_chunks / 64));
+    }
     const int64_t n = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(remaining, wave_max), cap));
     ids.assign(pending.begin() + pos, pending.begin() + pos + n);
     pos += n;
-    CUDA_TRY(cudaMemcpyAsync(g_ids.p, ids.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemsetAsync(d_queue, 0, 4 * sizeof(unsigned long long), st));
-    tm.start();
-    k_ros_fwd_cell<Cell, 1><<<fwd_blocks(n), CELL_LANES, cell_smem, st>>>(
-        rp, mc, n, g_ids.as<int>(), d_y, d_y, d_atol, d_rtol, d_istatus, d_rstatus, d_ierr, g_wnacc.as<int>(), tape,
-        with_mu ? 1 : 0, g_debug_irregular_every, d_queue + 2);
+    // ---- forward sweep of wave k into pool p (waits until the backward sweep of wave k-2 has released it)
+    if (comp_used[p]) CUDA_TRY(cudaStreamWaitEvent(ss.sF, ss.comp_free[p], 0));
+    CUDA_TRY(cudaMemcpyAsync(g_wids[p].p, ids.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ss.sF));
+    CUDA_TRY(cudaMemsetAsync(d_ctr + p, 0, sizeof(unsigned long long), ss.sF));
+    CUDA_TRY(cudaMemsetAsync(d_ctr + 2 + p, 0, sizeof(unsigned long long), ss.sF));
+    tape.base = g_comp[p].as<double>();
+    tape.chunk_prev = g_cprev[p].as<int>();
+    tape.chunk_owner = g_cowner[p].as<int>();
+    tape.chunk_seq = g_cseq[p].as<int>();
+    tape.pool_head = reinterpret_cast<unsigned int*>(d_ctr + 2 + p);
+    tape.pool_chunks = pool_chunks;
+    tape.last_chunk = g_wlast2[p].as<int>();
+    if (int e = t_begin(ss.sF, 0)) return e;
+    const unsigned fblocks = (unsigned)std::min<int64_t>((n + LANES - 1) / LANES, (int64_t)sms);
+    if (pmode > 0)
+      k_ros_fwd_cell<Cell, 1, CELL_LANES_SHARED><<<fblocks, 32, cell_smem, ss.sF>>>(
+          rp, mc, n, g_wids[p].as<int>(), d_y, d_y, d_atol, d_rtol, d_istatus, d_rstatus, d_ierr, g_wnacc2[p].as<int>(), tape,
+          with_mu ? 1 : 0, g_debug_irregular_every, d_ctr + p);
+    else
+      k_ros_fwd_cell<Cell, 1, CELL_LANES_SOLO><<<fblocks, 32, cell_smem, ss.sF>>>(
+          rp, mc, n, g_wids[p].as<int>(), d_y, d_y, d_atol, d_rtol, d_istatus, d_rstatus, d_ierr, g_wnacc2[p].as<int>(), tape,
+          with_mu ? 1 : 0, g_debug_irregular_every, d_ctr + p);
     CUDA_TRY(cudaGetLastError());
-    {
-      const double ms_f = tm.stop();
-      g_stats.ms_forward += ms_f;
-      if (getenv("FATODE_DEBUG_WAVES")) fprintf(stderr, "[wave] forward %.2f ms\n", ms_f);
-    }
+    if (int e = t_end(ss.sF)) return e;
     g_stats.launches++;
     g_stats.waves++;
-    // per-slot outcome
+    // per-slot outcome (the host waits for this wave's forward sweep only; earlier waves keep the GPU busy meanwhile)
     h_nacc.resize(n);
     h_ierr.resize(n);
-    k_gather_rows_i<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((int)n, g_ids.as<int>(), d_ierr, g_wierr.as<int>());
-    CUDA_TRY(cudaMemcpyAsync(h_ierr.data(), g_wierr.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(h_nacc.data(), g_wnacc.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
-    unsigned h_head = 0;
-    CUDA_TRY(cudaMemcpyAsync(&h_head, d_head, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    const unsigned chunks_used = std::min(h_head, pool_chunks);
+    k_gather_rows_i<<<(unsigned)((n + 255) / 256), 256, 0, ss.sF>>>((int)n, g_wids[p].as<int>(), d_ierr, g_wierr.as<int>());
+    CUDA_TRY(cudaMemcpyAsync(h_ierr.data(), g_wierr.p, sizeof(int) * n, cudaMemcpyDeviceToHost, ss.sF));
+    CUDA_TRY(cudaMemcpyAsync(h_nacc.data(), g_wnacc2[p].p, sizeof(int) * n, cudaMemcpyDeviceToHost, ss.sF));
+    unsigned long long h_head = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h_head, d_ctr + 2 + p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ss.sF));
+    CUDA_TRY(cudaStreamSynchronize(ss.sF));
+    const unsigned chunks_used = (unsigned)std::min<unsigned long long>(h_head & 0xffffffffull, pool_chunks);
     int64_t n_ok = 0, n_def = 0;
     long long steps = 0;
     order.clear();
@@ -718,39 +840,97 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
       else if (h_ierr[w] == 1) { ++n_ok; steps += h_nacc[w]; order.push_back((int)w); }
     }
     g_stats.cells_deferred += n_def;
+    if (dbg) fprintf(stderr, "[wave %d] cells %ld ok %ld deferred %ld chunks %u/%u\n", k, (long)n, (long)n_ok, (long)n_def, chunks_used, pool_chunks);
+    if (n_ok == 0 && n_def == n) {
+      if (n == 1) { rc_fail = fail(FATODE_ENOMEM, "trajectory tape of a single cell exceeds the tape budget"); break; }
+      chunks_per_cell = std::max(2.0 * chunks_per_cell, (double)pool_chunks / std::max<int64_t>(1, n / 2));
+    }
     if (n_ok > 0) {
       chunks_per_cell = std::max(chunks_per_cell, ((double)steps / (double)n_ok) / FT_CHUNK + 0.5);
       g_stats.accepted_steps += steps;
-      g_stats.tape_bytes_peak = std::max<uint64_t>(g_stats.tape_bytes_peak, (uint64_t)(steps + n_ok * FT_CHUNK / 2) * NE * 8);
-      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h_nacc[a] > h_nacc[b]; });
-      CUDA_TRY(cudaMemcpyAsync(g_order.p, order.data(), sizeof(int) * n_ok, cudaMemcpyHostToDevice, st));
-      tm.start();
-      {   // per-stage blocks of the tape: one thread per (step, stage)
-        k_expand_tape<Cell><<<chunks_used, FT_CHUNK * rp.S, 0, st>>>(
-            rp, mc, chunks_used, g_owner.as<int>(), g_ids.as<int>(), d_ierr, g_wnacc.as<int>(), g_wlast.as<int>(),
-            g_tape.as<double>(), with_mu ? 1 : 0);
-        CUDA_TRY(cudaGetLastError());
-        const double ms_x = tm.stop();
-        g_stats.ms_forward_tape += ms_x;
-        g_stats.launches++;
-        if (getenv("FATODE_DEBUG_WAVES")) fprintf(stderr, "[wave] cells %ld ok %ld deferred %ld chunks %u expand %.2f ms\n", (long)n, (long)n_ok, (long)n_def, chunks_used, ms_x);
+      g_stats.tape_bytes_peak = std::max<uint64_t>(g_stats.tape_bytes_peak, (uint64_t)chunks_used * chunk_bytes + (uint64_t)std::min<long long>(steps, fat_steps_cap) * fat_step_bytes);
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h_nacc[a] > h_nacc[b]; });   // longest first
+      // ---- batches of this wave (as many cells as one fat buffer holds): per-wave tables first, uploaded on sF (idle
+      // now, so the pageable copies do not stall the host), then per batch expand (sX) -> backward sweep (sA)
+      struct Batch { size_t o0, o1; long long steps; };
+      std::vector<Batch> batches;
+      h_fatoff.assign(n, -1);
+      h_batch.assign(n, -1);
+      {
+        size_t o = 0;
+        while (o < order.size()) {
+          Batch bt{o, o, 0};
+          while (o < order.size() && bt.steps + h_nacc[order[o]] <= fat_steps_cap &&
+                 (batch_cells <= 0 || (int64_t)(o - bt.o0) < batch_cells)) {
+            h_fatoff[order[o]] = bt.steps;
+            h_batch[order[o]] = (int)batches.size();
+            bt.steps += h_nacc[order[o]];
+            ++o;
+          }
+          bt.o1 = o;
+          if (bt.o1 == bt.o0) { rc_fail = fail(FATODE_ENOMEM, "trajectory tape of a single cell exceeds the tape budget"); break; }
+          batches.push_back(bt);
+        }
       }
-      tm.start();
-      const int ablocks = (int)std::min<int64_t>(sms, (n_ok + ADJ3_WARPS - 1) / ADJ3_WARPS);
-      k_ros_adj_cell<Warp><<<ablocks, ADJ3_WARPS * 32, adj_smem, st>>>(
-          rp, n_ok, g_ids.as<int>(), g_wnacc.as<int>(), g_wlast.as<int>(), g_tape.as<double>(), g_prev.as<int>(), d_ierr,
-          d_y, d_lambda, with_mu ? d_mu : nullptr, d_istatus, d_queue, g_order.as<int>(), nadj, with_mu ? 1 : 0);
-      CUDA_TRY(cudaGetLastError());
-      const double ms_a = tm.stop();
-      g_stats.ms_adjoint += ms_a;
-      g_stats.launches++;
-      if (getenv("FATODE_DEBUG_WAVES")) fprintf(stderr, "[wave] adjoint %.2f ms\n", ms_a);
-    } else if (n_def == n) {
-      if (n == 1) return fail(FATODE_ENOMEM, "trajectory tape of a single cell exceeds the tape budget");
-      chunks_per_cell = std::max(2.0 * chunks_per_cell, (double)pool_chunks / std::max<int64_t>(1, n / 2));
+      if (rc_fail) break;
+      CUDA_TRY(cudaMemcpyAsync(g_border[p].p, order.data(), sizeof(int) * n_ok, cudaMemcpyHostToDevice, ss.sF));
+      CUDA_TRY(cudaMemcpyAsync(g_bfatoff[p].p, h_fatoff.data(), sizeof(long long) * n, cudaMemcpyHostToDevice, ss.sF));
+      CUDA_TRY(cudaMemcpyAsync(g_wbatch[p].p, h_batch.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ss.sF));
+      CUDA_TRY(cudaEventRecord(ss.tables_ready, ss.sF));
+      CUDA_TRY(cudaStreamWaitEvent(ss.sX, ss.tables_ready, 0));
+      for (size_t bi = 0; bi < batches.size(); ++bi) {
+        const Batch& bt = batches[bi];
+        const int f = (nbuf == 2) ? (g & 1) : 0;
+        const int64_t nb = (int64_t)(bt.o1 - bt.o0);
+        if (fat_used[f]) CUDA_TRY(cudaStreamWaitEvent(ss.sX, ss.fat_free[f], 0));
+        if (int e = t_begin(ss.sX, 1)) return e;
+        k_expand_tape<Cell><<<chunks_used, FT_CHUNK * S, 0, ss.sX>>>(
+            rp, mc, chunks_used, g_cowner[p].as<int>(), g_cseq[p].as<int>(), g_wids[p].as<int>(), d_ierr, g_wnacc2[p].as<int>(),
+            g_wlast2[p].as<int>(), g_comp[p].as<double>(), g_fat[f].as<double>(), g_bfatoff[p].as<long long>(),
+            g_wbatch[p].as<int>(), (int)bi, with_mu ? 1 : 0);
+        CUDA_TRY(cudaGetLastError());
+        if (int e = t_end(ss.sX)) return e;
+        CUDA_TRY(cudaEventRecord(ss.expand_done[f], ss.sX));
+        CUDA_TRY(cudaStreamWaitEvent(ss.sA, ss.expand_done[f], 0));
+        CUDA_TRY(cudaMemsetAsync(d_ctr + 4 + f, 0, sizeof(unsigned long long), ss.sA));
+        if (int e = t_begin(ss.sA, 2)) return e;
+        const int ablocks = (int)std::min<int64_t>(sms, (nb + ADJ3_WARPS - 1) / ADJ3_WARPS);
+        k_ros_adj_cell<Warp><<<ablocks, ADJ3_WARPS * 32, adj_smem, ss.sA>>>(
+            rp, nb, g_wids[p].as<int>(), g_wnacc2[p].as<int>(), g_wlast2[p].as<int>(), g_comp[p].as<double>(), g_cprev[p].as<int>(),
+            g_fat[f].as<double>(), g_bfatoff[p].as<long long>(), d_ierr, d_y, d_lambda, with_mu ? d_mu : nullptr, d_istatus,
+            d_ctr + 4 + f, g_border[p].as<int>() + bt.o0, nadj, with_mu ? 1 : 0);
+        CUDA_TRY(cudaGetLastError());
+        if (int e = t_end(ss.sA)) return e;
+        CUDA_TRY(cudaEventRecord(ss.fat_free[f], ss.sA));
+        fat_used[f] = true;
+        g_stats.launches += 2;
+        if (dbg) fprintf(stderr, "[wave %d] batch %d: %ld cells, %lld steps\n", k, g, (long)nb, bt.steps);
+        ++g;
+      }
+      if (rc_fail) break;
     }
+    CUDA_TRY(cudaEventRecord(ss.comp_free[p], ss.sA));
+    comp_used[p] = true;
+    ++k;
   }
-  return 0;
+  // join: the caller's stream continues after all three side streams
+  CUDA_TRY(cudaEventRecord(ss.doneF, ss.sF));
+  CUDA_TRY(cudaEventRecord(ss.doneX, ss.sX));
+  CUDA_TRY(cudaEventRecord(ss.doneA, ss.sA));
+  CUDA_TRY(cudaStreamWaitEvent(st, ss.doneF, 0));
+  CUDA_TRY(cudaStreamWaitEvent(st, ss.doneX, 0));
+  CUDA_TRY(cudaStreamWaitEvent(st, ss.doneA, 0));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  for (TimedLaunch& t : timed) {   // device time per phase (the phases overlap; their sum exceeds the elapsed time)
+    float ms = 0.f;
+    if (t.b && cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+      if (t.phase == 0) g_stats.ms_forward += ms; else if (t.phase == 1) g_stats.ms_forward_tape += ms; else g_stats.ms_adjoint += ms;
+      if (dbg) fprintf(stderr, "[timing] phase %d %.2f ms\n", t.phase, ms);
+    }
+    cudaEventDestroy(t.a);
+    if (t.b) cudaEventDestroy(t.b);
+  }
+  return rc_fail;
 }
 
 // dispatcher: fast path where the model has one, then the general path for what is left

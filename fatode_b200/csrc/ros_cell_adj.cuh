@@ -70,8 +70,10 @@ constexpr int XP_ROW = 226;   // shared-memory row of one step's inputs (Y0 + K 
 template <class Cell>
 __global__ void __launch_bounds__(FT_CHUNK * 6, 4)
 k_expand_tape(RosParams rp, typename Cell::Const mc, unsigned nchunks, const int* __restrict__ chunk_owner,
-              const int* __restrict__ ids, const int* __restrict__ ierr, const int* __restrict__ nacc,
-              const int* __restrict__ last_chunk, double* __restrict__ tape, int with_mu) {
+              const int* __restrict__ chunk_seq, const int* __restrict__ ids, const int* __restrict__ ierr,
+              const int* __restrict__ nacc, const int* __restrict__ last_chunk, const double* __restrict__ tape,
+              double* __restrict__ fat, const long long* __restrict__ fat_off, const int* __restrict__ batch_of,
+              int batch, int with_mu) {
   // one block per tape chunk (FT_CHUNK steps x S stages = one thread per item); the steps' inputs are staged through
   // shared memory with coalesced loads, the outputs go straight to the tape
   __shared__ __align__(16) double in_s[FT_CHUNK * XP_ROW];
@@ -79,10 +81,11 @@ k_expand_tape(RosParams rp, typename Cell::Const mc, unsigned nchunks, const int
   const int S = rp.S;
   const long c = blockIdx.x;
   const int w = chunk_owner[c];
-  if (ierr[ids ? ids[w] : w] != 1) return;
+  if (batch_of[w] != batch || ierr[ids ? ids[w] : w] != 1) return;   // cells of other batches / unfinished cells
+  const long long fo = fat_off[w];            // first stage block of this cell in its batch's fat buffer
   const int cnt = (c == last_chunk[w]) ? ((nacc[w] - 1) % FT_CHUNK) + 1 : FT_CHUNK;
-  const int NE = fat_entry_doubles(S);
-  double* chunk = tape + (size_t)c * FT_CHUNK * NE;
+  constexpr int NE = FT_STEP;
+  const double* chunk = tape + (size_t)c * FT_CHUNK * NE;
   const int row2 = (N + S * N) / 2;   // double2 per step
   for (int idx = threadIdx.x; idx < cnt * row2; idx += blockDim.x) {
     const int q = idx / row2, o = idx - q * row2;
@@ -91,7 +94,7 @@ k_expand_tape(RosParams rp, typename Cell::Const mc, unsigned nchunks, const int
   __syncthreads();
   const int q = threadIdx.x / S, is = threadIdx.x - q * S;
   if (q >= cnt) return;
-  double* e = chunk + (size_t)q * NE;
+  const double* e = chunk + (size_t)q * NE;
   const double T = e[0], H = e[1];
   const double dDir = (rp.tend >= rp.tstart) ? 1.0 : -1.0;
   const double* in = in_s + q * XP_ROW;      // [Y0(32)][K(S x 32)]
@@ -125,7 +128,7 @@ k_expand_tape(RosParams rp, typename Cell::Const mc, unsigned nchunks, const int
 #pragma unroll
     for (int n = 0; n < cbm4_cell::NJT; ++n) DJ[n] = 0.0;
   }
-  double* sb = e + FT_STEP + is * FT_STAGE;
+  double* sb = fat + ((size_t)(fo + (long long)chunk_seq[c] * FT_CHUNK + q) * S + is) * FT_STAGE;
   Cell::photo(T + rp.Alpha[is] * dDir * H, PHS);
   cbm4_cell::jac_values<1>(Yi, mc.fix, PHS, sb + FT_JV);
   cbm4_cell::build_M<1>(Ki, DJ, rp.autonomous ? 0.0 : H * rp.Gamma[is], sb + FT_MV);
@@ -233,6 +236,7 @@ template <class Model>
 __global__ void __launch_bounds__(ADJ3_WARPS * 32, 1)
 k_ros_adj_cell(RosParams rp, long nwave, const int* __restrict__ ids, const int* __restrict__ nacc,
                const int* __restrict__ last_chunk, const double* __restrict__ tape, const int* __restrict__ chunk_prev,
+               const double* __restrict__ fat, const long long* __restrict__ fat_off,
                const int* __restrict__ ierr, const double* __restrict__ y_final, double* __restrict__ lambda,
                double* __restrict__ mu, int* __restrict__ istatus, unsigned long long* __restrict__ queue,
                const int* __restrict__ order, int nadj, int with_mu) {
@@ -253,7 +257,6 @@ k_ros_adj_cell(RosParams rp, long nwave, const int* __restrict__ ids, const int*
   tmem::fence_after_sync();
   const uint32_t tm = tmem_base_s + ((uint32_t)(warp * 32) << 16);
   const int S = rp.S;
-  const int NE = fat_entry_doubles(S);
   uint32_t ph_step0 = 0u, ph_step1 = 0u, ph_stage0 = 0u, ph_stage1 = 0u;   // phase parity per barrier (warp-uniform)
 
   for (;;) {
@@ -279,15 +282,16 @@ k_ros_adj_cell(RosParams rp, long nwave, const int* __restrict__ ids, const int*
     // prefetch cursor: walks the chunk list backwards, one work item ahead of the computation
     int pf_chunk = last_chunk[q];
     int pf_step = nsteps - 1;                      // forward-order index of the step the cursor is in
+    const double* fat_cell = fat + (size_t)fat_off[q] * S * FT_STAGE;
     auto issue = [&](int t) {                      // executed by lane 0
       const int si = t / S, is = S - 1 - (t - si * S);
-      const double* ent = tape + ((size_t)pf_chunk * FT_CHUNK + (pf_step % FT_CHUNK)) * NE;
+      const double* ent = tape + ((size_t)pf_chunk * FT_CHUNK + (pf_step % FT_CHUNK)) * FT_STEP;
       if (is == S - 1) {
         mbar::expect_tx(bars + (si & 1), FT_STEP_COPY * 8);
         mbar::bulk_g2s(SBUF + (si & 1) * FT_STEP_COPY, ent, FT_STEP_COPY * 8, bars + (si & 1));
       }
       mbar::expect_tx(bars + 2 + (t & 1), FT_STAGE * 8);
-      mbar::bulk_g2s(GBUF + (t & 1) * FT_STAGE, ent + FT_STEP + is * FT_STAGE, FT_STAGE * 8, bars + 2 + (t & 1));
+      mbar::bulk_g2s(GBUF + (t & 1) * FT_STAGE, fat_cell + ((size_t)pf_step * S + is) * FT_STAGE, FT_STAGE * 8, bars + 2 + (t & 1));
     };
     auto advance = [&](int t) {                    // cursor moves from item t to item t + 1 (all lanes, uniform)
       if ((t + 1) % S == 0) {

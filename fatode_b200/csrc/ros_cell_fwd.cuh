@@ -19,11 +19,12 @@
 // step-halving retry of ros_PrepareMatrix leaves this kernel with IERR_IRREGULAR and is integrated by the general
 // warp-per-cell kernel (full pivoting) instead; the two paths give identical bits.
 //
-// Adjoint mode writes a "fat" tape: per accepted step the sparse L\U factors (reused by the backward sweep —
-// the reference refactorises the same matrix, :1261-1267) and, per stage, the values the backward sweep needs
-// that do not depend on the adjoint variables: J(T_i,Y_i), M'_i = Hess x K_i + h*gamma_i*dJ/dt, a_p.
-// Tape space comes from a chunk pool (CHUNK accepted steps per chunk, linked backwards), so no per-cell slab
-// has to be guessed; a cell that finds the pool empty is deferred to the next wave (IERR_DEFERRED).
+// Adjoint mode writes the trajectory tape: per accepted step T, H, the sparse L\U factors (reused by the backward
+// sweep — the reference refactorises the same matrix, :1261-1267), Y(T) and the stage vectors K.  Tape space comes
+// from a chunk pool (FT_CHUNK accepted steps per chunk, linked backwards), so no per-cell slab has to be guessed; a
+// cell that finds the pool empty is deferred to the next wave (IERR_DEFERRED).  k_expand_tape (ros_cell_adj.cuh)
+// later derives from (Y, K) the per-stage operands of the backward sweep that do not depend on the adjoint
+// variables — J(T_i,Y_i), M'_i = Hess x K_i + h*gamma_i*dJ/dt, a_p — into the "fat" stage blocks.
 #pragma once
 #include "fatode_common.cuh"
 #include "model_cbm4.cuh"
@@ -65,7 +66,7 @@ constexpr int FT_STEP = FT_K + 6 * 32;                      // forward-written p
 constexpr int FT_JV = 0, FT_MV = 276, FT_AP = 536;          // inside a stage block (each part 32-byte aligned, zero padded)
 constexpr int FT_STAGE = 568;                               // 4544 B (multiple of 32)
 constexpr int FT_CHUNK = 16;                                // accepted steps per chunk
-__host__ __device__ inline int fat_entry_doubles(int S) { return FT_STEP + S * FT_STAGE; }
+__host__ __device__ inline int fat_step_doubles(int S) { return S * FT_STAGE; }   // stage blocks of one accepted step
 static_assert(cbm4_cell::NLU <= FT_LU && cbm4_cell::NJ == FT_MV && cbm4_cell::NJ + cbm4_cell::NM <= FT_AP && FT_AP % 4 == 0 &&
               FT_STAGE % 4 == 0 && FT_STEP % 4 == 0 && FT_MV % 4 == 0, "tape layout");
 
@@ -86,39 +87,43 @@ struct Cbm4Cell {
 };
 
 struct CellTape {
-  double* base;                 // chunk pool
+  double* base;                 // chunk pool of step entries (FT_STEP doubles per accepted step)
   int* chunk_prev;              // [pool_chunks] backward links
   int* chunk_owner;             // [pool_chunks] wave slot that owns the chunk
+  int* chunk_seq;               // [pool_chunks] position of the chunk in its cell's trajectory (0, 1, ...)
   unsigned int* pool_head;      // next free chunk
   unsigned int pool_chunks;
   int* last_chunk;              // [cells of the wave]
 };
 
-// Per-thread storage: the hot arrays live in SHARED memory, element e of a thread's array at base[e * CELL_LANES]
-// (consecutive lanes -> consecutive doubles: conflict-free), 751 doubles = 6 KB per cell, 188 KB per block of 32
-// cells, hence one block (= one warp) per SM.  Thread-local memory only holds routine temporaries and spills.
-constexpr int CELL_LANES = 32;
-template <class Model>
+// Per-thread storage: the hot arrays live in SHARED memory, element e of a thread's array at base[e * LANES]
+// (consecutive lanes -> consecutive doubles: conflict-free), 751 doubles = 6 KB per cell.  One block (= one warp, LANES
+// of its 32 threads active) per SM: 188 KB with 32 cells; 26 cells (153 KB) leave room for a CTA of the backward
+// kernel on the same SM, which is how the forward sweep of the next wave hides behind the backward sweep of this one.
+// Thread-local memory only holds routine temporaries and spills.
+constexpr int CELL_LANES_SOLO = 32, CELL_LANES_SHARED = 26;
+template <class Model, int LANES>
 struct CellSmem {
   static constexpr int OFF_Y = 0, OFF_F0 = 32, OFF_DF = 64, OFF_YN = 96, OFF_FC = 128, OFF_DINV = 160, OFF_K = 192,
                        OFF_LU = 192 + 6 * 32, DOUBLES = OFF_LU + Model::NLU;
-  static constexpr size_t BYTES = sizeof(double) * DOUBLES * CELL_LANES;
+  static constexpr size_t BYTES = sizeof(double) * DOUBLES * LANES;
 };
 
 // MODE 0: forward only.  MODE 1: forward + fat tape (adjoint mode).
 // Persistent kernel: every LANE pulls its next cell from an atomic queue as soon as its current one is done
 // (slot w of the wave = cell ids[w], or cell w when ids == nullptr), so there is no max-over-lanes tail inside a
 // warp.
-template <class Model, int MODE>
-__global__ void __launch_bounds__(CELL_LANES, 1)
+template <class Model, int MODE, int LANES>
+__global__ void __launch_bounds__(32, 1)
 k_ros_fwd_cell(RosParams rp, typename Model::Const mc, long nwave, const int* __restrict__ ids, const double* __restrict__ y_in,
                double* __restrict__ y_out, const double* __restrict__ atol_g, const double* __restrict__ rtol_g,
                int* __restrict__ istatus, double* __restrict__ rstatus, int* __restrict__ ierr_out, int* __restrict__ nacc_out,
                CellTape tape, int with_mu, int debug_irregular_every, unsigned long long* __restrict__ queue) {
   extern __shared__ __align__(16) double cell_smem[];
   constexpr int N = Model::N;
-  constexpr int SV = CELL_LANES;
-  typedef CellSmem<Model> L;
+  constexpr int SV = LANES;
+  typedef CellSmem<Model, LANES> L;
+  if (threadIdx.x >= LANES) return;
   const int S = rp.S;
   const bool adj = (rp.family == FAM_ADJ);
   const bool count_la = (rp.family != FAM_FWD);
@@ -280,9 +285,10 @@ k_ros_fwd_cell(RosParams rp, typename Model::Const mc, long nwave, const int* __
             if (c >= tape.pool_chunks) { ierr = IERR_DEFERRED; break; }
             tape.chunk_prev[c] = cur_chunk;
             tape.chunk_owner[c] = (int)w;
+            tape.chunk_seq[c] = (nacc - 1) / FT_CHUNK;
             cur_chunk = (int)c;
           }
-          double* e = tape.base + ((size_t)cur_chunk * FT_CHUNK + slot) * fat_entry_doubles(S);
+          double* e = tape.base + ((size_t)cur_chunk * FT_CHUNK + slot) * FT_STEP;
           st_global_256(e, T, H, (double)swaps, 0.0);
           double* el = e + FT_HDR;
 #pragma unroll 4

@@ -100,6 +100,10 @@ int fatode_set_wave_cells(int64_t cells);
  * identical forward bits.  fatode_debug_irregular_every(k > 0) is a test hook that pushes every k-th cell
  * through the hand-back. */
 int fatode_set_path(int mode);
+/* 0 (default): the forward, expand and backward kernels of a wave run back to back; 1, 2: the forward sweep of the
+ * next wave is overlapped with the backward sweep of the current one on separate streams (double-buffered tape).
+ * Results are identical in all modes. */
+int fatode_set_pipeline(int mode);
 int fatode_debug_irregular_every(int k);
 /* frees the device workspace (trajectory tape etc.) the engine caches between calls */
 int fatode_release_workspace(void);
