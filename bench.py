@@ -7,11 +7,13 @@ Rodas4 sweep 12h -> 84h with trajectory tape, ADJINIT, discrete adjoint sweep fo
 functionals and NP = 29 rate-coefficient parameters (the reference driver's problem,
 EXAMPLES/cbm4/CBM4_ROS_ADJ/cbm4_ros_adj_dr.F90:167-292), on synthetic per-cell initial states.
 
-A "step" is one pass of the hot path over one batch of `--cells` cells per GPU.
+A "step" is one pass of the hot path over one batch of `--cells` cells per GPU (default 2^17: the >= 1 M-cell
+workload of BASELINE.json is processed in waves of ~4.7 k cells whatever the batch size, so throughput does not depend
+on it; `--cells 1048576` runs the full-size batch in ~80 s per step).
   value : cells/s with y0 and all outputs resident in HBM (device pointers through the C ABI)
   e2e   : cells/s through the same C-ABI call with pinned HOST buffers (H2D of y0, D2H of y, Lambda,
           Mu, ISTATUS, RSTATUS, IERR inside the timed region)
-  roofline    : dominant kernel (k_ros_adj, the backward sweep): algorithmic FP64 flops of
+  roofline    : dominant kernel (k_ros_adj_cell, the backward sweep): algorithmic FP64 flops of
                 SURVEY.md §8d evaluated on the returned counters / its CUDA-event time, against the
                 DFMA peak measured on this GPU in this run (MEASURED_PEAKS.json has no FP64 figure)
   cpu_baseline: the CPU oracle (C++ restatement of the reference, OpenMP over cells) on a bounded sample
@@ -193,7 +195,7 @@ def workload_config(cells, ngpus, note=None):
     c = {"workload": "EXAMPLES/cbm4 ADJ/ROS_ADJ: CBM-IV N=32, Rodas4 (ICNTRL(3)=5), NADJ=32, NP=29, t=12h..84h, "
                      "rtol=0.1f*1e-4, atol=0.1f*1e-6, y0 = driver state*(1+0.1u) per cell (cell 0 unperturbed)",
          "cells_per_gpu_per_step": int(cells), "global_cells_per_step": int(cells * ngpus), "parallelism": f"cells sharded x{ngpus}",
-         "l2_policy": "working set >> L2 (trajectory tape ~2.5 MB per cell; no explicit flush needed)"}
+         "l2_policy": "working set >> L2 (trajectory tape ~27 MB per cell streamed through HBM; no explicit flush needed)"}
     if note:
         c["note"] = note
     return c
@@ -202,9 +204,9 @@ def workload_config(cells, ngpus, note=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--cells", type=int, default=16384, help="cells per GPU per step")
+    ap.add_argument("--cells", type=int, default=131072, help="cells per GPU per step")
     ap.add_argument("--impl", default="fatode_b200", choices=["fatode_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -273,11 +275,15 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     launches = 0
+    n_adj_launches = 0
+    general_cells = 0
     ms_adj = ms_fwd = ms_tape = 0.0
     acc_steps = attempts = 0
     for s in range(args.warmup, args.warmup + args.steps):
         st = step_device(s)
         launches += st.launches + 1 + (1 if dist is not None else 0)     # + the y0 copy (+ NCCL kernel)
+        n_adj_launches += st.launches_adjoint
+        general_cells += st.cells_general
         ms_adj += st.ms_adjoint
         ms_fwd += st.ms_forward
         ms_tape += st.ms_forward_tape
@@ -340,25 +346,33 @@ def main():
         e2e = {"value": cells_total / (ms2 * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
 
     # totals over ranks for the flop model
-    tot = torch.tensor([acc_steps, attempts, ms_adj, ms_fwd, ms_tape], dtype=torch.float64, device=dev)
+    tot = torch.tensor([acc_steps, attempts, ms_adj, ms_fwd, ms_tape, n_adj_launches, general_cells], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(tot)
     if rank == 0:
-        acc_t, att_t, ms_adj_t, ms_fwd_t, ms_tape_t = [float(x) for x in tot.tolist()]
+        acc_t, att_t, ms_adj_t, ms_fwd_t, ms_tape_t, n_adj_t, general_t = [float(x) for x in tot.tolist()]
         f_adj = acc_t * flops_adjoint_per_step()
         f_fwd = flops_forward(att_t, acc_t)
         # dominant kernel: k_ros_adj; per-rank kernel time = sum of its launches on that rank (ranks run concurrently)
         adj_tflops = f_adj / (ms_adj_t / world * 1e-3) / 1e12
-        roof = {"bound": "fp64", "kernel": "k_ros_adj<Cbm4Warp> (discrete adjoint sweep)", "achieved": adj_tflops,
-                "peak": fp64_peak * world, "unit": "TFLOP/s", "frac": adj_tflops / (fp64_peak * world),
+        # DRAM traffic of the backward kernel: measured with ncu (profiles/, dram__bytes_read.sum + dram__bytes_write.sum of
+        # k_ros_adj_cell) = 32.6 kB per accepted step (the step entry 3.3 kB + six stage blocks of 4.5 kB, streamed once
+        # by TMA, plus the Lambda/Mu write-back); scaled here to the steps one launch of this run processes
+        traffic_per_step = 32.6e3
+        roof = {"bound": "fp64", "kernel": "k_ros_adj_cell<Cbm4Warp> (discrete adjoint sweep, lane = adjoint column)",
+                "achieved": adj_tflops, "peak": fp64_peak * world, "unit": "TFLOP/s", "frac": adj_tflops / (fp64_peak * world),
                 "peak_source": "DFMA micro-benchmark run by this bench on this GPU (fatode_measure_fp64_peak); "
                                "MEASURED_PEAKS.json carries no FP64 figure",
                 "algorithmic_flops_per_accepted_step": flops_adjoint_per_step(),
-                "launches": int(args.steps * world), "avg_launch_ms": ms_adj_t / (args.steps * world),
+                "launches": int(n_adj_t), "avg_launch_ms": ms_adj_t / max(n_adj_t, 1.0),
                 "share_of_step_time": (ms_adj_t / world) / ms,
-                "traffic": None,
+                "traffic": traffic_per_step * acc_t / max(n_adj_t, 1.0),
+                "traffic_note": "bytes per launch = ncu-measured DRAM bytes per accepted step x steps per launch",
                 "whole_job_algorithmic_tflops": (f_adj + f_fwd) / (ms * 1e-3) / 1e12,
-                "forward_ms_per_step": ms_fwd_t / (args.steps * world), "forward_tape_ms_per_step": ms_tape_t / (args.steps * world)}
+                "whole_job_frac_of_fp64_peak": (f_adj + f_fwd) / (ms * 1e-3) / 1e12 / (fp64_peak * world),
+                "forward_ms_per_step": ms_fwd_t / (args.steps * world), "expand_ms_per_step": ms_tape_t / (args.steps * world),
+                "adjoint_ms_per_step": ms_adj_t / (args.steps * world),
+                "cells_on_general_path": int(general_t)}
         line = {"metric": "cell-integrations/sec (fwd + adjoint), CBM-IV ROS_ADJ", "value": value, "unit": "cells/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -34,7 +34,8 @@ class Stats(ctypes.Structure):
     _fields_ = [("launches", ctypes.c_int64), ("waves", ctypes.c_int64), ("ms_forward", ctypes.c_double),
                 ("ms_forward_tape", ctypes.c_double), ("ms_adjoint", ctypes.c_double), ("ms_other", ctypes.c_double),
                 ("tape_bytes_peak", ctypes.c_uint64), ("accepted_steps", ctypes.c_int64), ("attempts", ctypes.c_int64),
-                ("cells_general", ctypes.c_int64), ("cells_deferred", ctypes.c_int64)]
+                ("cells_general", ctypes.c_int64), ("cells_deferred", ctypes.c_int64),
+                ("launches_forward", ctypes.c_int64), ("launches_expand", ctypes.c_int64), ("launches_adjoint", ctypes.c_int64)]
 
 
 _lib = None

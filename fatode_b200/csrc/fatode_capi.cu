@@ -448,6 +448,7 @@ static int ros_device_general(const RosParams& rp, const typename Model::Const& 
     CUDA_TRY(cudaGetLastError());
     g_stats.ms_adjoint += tm.stop();
     g_stats.launches++;
+    g_stats.launches_adjoint++;
     return 0;
   };
 
@@ -466,6 +467,7 @@ static int ros_device_general(const RosParams& rp, const typename Model::Const& 
     CUDA_TRY(cudaGetLastError());
     g_stats.ms_forward += tm.stop();
     g_stats.launches++;
+    g_stats.launches_forward++;
     done = n;
     if (!do_adjoint) return 0;
     k_scan_offsets<<<1, 1024, 0, st>>>(n, b_nacc.as<int>(), ier, b_off.as<long long>());
@@ -492,6 +494,7 @@ static int ros_device_general(const RosParams& rp, const typename Model::Const& 
     CUDA_TRY(cudaGetLastError());
     g_stats.ms_forward_tape += tm.stop();
     g_stats.launches++;
+    g_stats.launches_expand++;
     if (int e = launch_adjoint(c0, fit, 0)) return e;
     if (fit < n)   // cells beyond the prefix: restore their initial state, they run in a later wave
       CUDA_TRY(cudaMemcpyAsync(y + fit * 32, b_y0.as<double>() + fit * 32, sizeof(double) * 32 * (n - fit),
@@ -536,6 +539,7 @@ static int ros_device_general(const RosParams& rp, const typename Model::Const& 
     CUDA_TRY(cudaGetLastError());
     g_stats.ms_forward += tm.stop();
     g_stats.launches++;
+    g_stats.launches_forward++;
     int h_novf = 0;
     std::vector<int> h_nacc(n);
     CUDA_TRY(cudaMemcpyAsync(&h_novf, d_novf, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -672,6 +676,7 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
     CUDA_TRY(cudaGetLastError());
     g_stats.ms_forward += tm.stop();
     g_stats.launches++;
+    g_stats.launches_forward++;
     g_stats.waves++;
     std::vector<int> h_ierr(ncells);
     CUDA_TRY(cudaMemcpyAsync(h_ierr.data(), d_ierr, sizeof(int) * ncells, cudaMemcpyDeviceToHost, st));
@@ -693,7 +698,7 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
   const int LANES = pmode > 0 ? CELL_LANES_SHARED : CELL_LANES_SOLO;
   const int S = rp.S;
   const size_t cell_smem = pmode > 0 ? CellSmem<Cell, CELL_LANES_SHARED>::BYTES : CellSmem<Cell, CELL_LANES_SOLO>::BYTES;
-  const size_t adj_smem = sizeof(double) * (size_t)ADJ3_WARP_DOUBLES * ADJ3_WARPS;
+  const size_t adj_smem = sizeof(double) * ((size_t)ADJ3_WARP_DOUBLES * ADJ3_WARPS + (size_t)ADJ3_PRIV_DOUBLES * (ADJ3_WARPS - 4));
   CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd_cell<Cell, 1, CELL_LANES_SHARED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)CellSmem<Cell, CELL_LANES_SHARED>::BYTES));
   CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd_cell<Cell, 1, CELL_LANES_SOLO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -820,6 +825,7 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
     CUDA_TRY(cudaGetLastError());
     if (int e = t_end(ss.sF)) return e;
     g_stats.launches++;
+    g_stats.launches_forward++;
     g_stats.waves++;
     // per-slot outcome (the host waits for this wave's forward sweep only; earlier waves keep the GPU busy meanwhile)
     h_nacc.resize(n);
@@ -895,15 +901,17 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
         CUDA_TRY(cudaMemsetAsync(d_ctr + 4 + f, 0, sizeof(unsigned long long), ss.sA));
         if (int e = t_begin(ss.sA, 2)) return e;
         const int ablocks = (int)std::min<int64_t>(sms, (nb + ADJ3_WARPS - 1) / ADJ3_WARPS);
-        k_ros_adj_cell<Warp><<<ablocks, ADJ3_WARPS * 32, adj_smem, ss.sA>>>(
-            rp, nb, g_wids[p].as<int>(), g_wnacc2[p].as<int>(), g_wlast2[p].as<int>(), g_comp[p].as<double>(), g_cprev[p].as<int>(),
-            g_fat[f].as<double>(), g_bfatoff[p].as<long long>(), d_ierr, d_y, d_lambda, with_mu ? d_mu : nullptr, d_istatus,
-            d_ctr + 4 + f, g_border[p].as<int>() + bt.o0, nadj, with_mu ? 1 : 0);
+        AdjArgs aa{nb, g_wids[p].as<int>(), g_wnacc2[p].as<int>(), g_wlast2[p].as<int>(), g_comp[p].as<double>(), g_cprev[p].as<int>(),
+                   g_fat[f].as<double>(), g_bfatoff[p].as<long long>(), d_ierr, d_y, d_lambda, with_mu ? d_mu : nullptr, d_istatus,
+                   d_ctr + 4 + f, g_border[p].as<int>() + bt.o0, nadj, with_mu ? 1 : 0};
+        k_ros_adj_cell<Warp><<<ablocks, ADJ3_WARPS * 32, adj_smem, ss.sA>>>(rp, aa);
         CUDA_TRY(cudaGetLastError());
         if (int e = t_end(ss.sA)) return e;
         CUDA_TRY(cudaEventRecord(ss.fat_free[f], ss.sA));
         fat_used[f] = true;
         g_stats.launches += 2;
+        g_stats.launches_expand++;
+        g_stats.launches_adjoint++;
         if (dbg) fprintf(stderr, "[wave %d] batch %d: %ld cells, %lld steps\n", k, g, (long)nb, bt.steps);
         ++g;
       }

@@ -10,7 +10,9 @@
 // one work item (= one stage of one step) ahead, and the transposed solve runs on the static sparse pattern
 // (335 FMA instead of 1056, cbm4_cell::lut_solve).
 //
-// One CTA of 4 warps per SM (TMEM: 4 x 32 lanes x 512 columns), cells pulled from an atomic queue.
+// One CTA per SM: warps 0..3 keep their private state in tensor memory (4 x 32 lanes x 512 columns); further warps
+// (ADJ3_WARPS > 4) would keep it in shared memory — measured on B200: 4 warps 1464 ms, 5 warps 1659 ms, 6 warps
+// 1617 ms per 32768 cells, so four it is.  Cells are pulled from an atomic queue.
 #pragma once
 #include "fatode_common.cuh"
 #include "ros_cell_fwd.cuh"
@@ -19,7 +21,7 @@
 
 namespace fatode {
 
-constexpr int ADJ3_WARPS = 4;
+constexpr int ADJ3_WARPS = 4;          // cells in flight per SM (4: all private state in tensor memory; 5 and 6 measured slower)
 constexpr int ADJ3_WARP_DOUBLES = 2 * FT_STEP_COPY + 2 * FT_STAGE + 8;   // step blocks, stage blocks, 4 mbarriers (+pad)
 
 namespace mbar {
@@ -137,11 +139,45 @@ k_expand_tape(RosParams rp, typename Cell::Const mc, unsigned nchunks, const int
     for (int p = 0; p < 32; p += 4) st_global_256(sb + FT_AP + p, 0.0, 0.0, 0.0, 0.0);
 }
 
-template <class Model, int HALF>
+// ---- private per-lane state of a backward warp: 256 doubles (W_1..W_5, Lambda, Mu, Lambda increment), addressed in
+// 32-bit "columns" like tensor memory (double d = columns 2d, 2d+1).  Warps 0..3 of a CTA keep it in TENSOR MEMORY
+// (their 32-lane quarter, all 512 columns); that is all the tensor memory an SM has, so any further warp keeps the same
+// layout in SHARED memory ([double][lane], conflict-free).
+struct PrivTmem {
+  uint32_t tm;
+  __device__ __forceinline__ void ld16(uint32_t col, double (&d)[16]) const { tmem::ld16(tm + col, d); }
+  __device__ __forceinline__ void ld32(uint32_t col, double (&d)[32]) const { tmem::ld32(tm + col, d); }
+  __device__ __forceinline__ void st16(uint32_t col, const double (&d)[16]) const { tmem::st16(tm + col, d); }
+  __device__ __forceinline__ void st32(uint32_t col, const double (&d)[32]) const { tmem::st32(tm + col, d); }
+  __device__ __forceinline__ void wait_st() const { tmem::wait_st(); }
+};
+struct PrivSmem {
+  double* b;   // this lane's column: double d at b[d * 32]
+  __device__ __forceinline__ void ld16(uint32_t col, double (&d)[16]) const {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) d[r] = b[((col >> 1) + r) * 32];
+  }
+  __device__ __forceinline__ void ld32(uint32_t col, double (&d)[32]) const {
+#pragma unroll
+    for (int r = 0; r < 32; ++r) d[r] = b[((col >> 1) + r) * 32];
+  }
+  __device__ __forceinline__ void st16(uint32_t col, const double (&d)[16]) const {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) b[((col >> 1) + r) * 32] = d[r];
+  }
+  __device__ __forceinline__ void st32(uint32_t col, const double (&d)[32]) const {
+#pragma unroll
+    for (int r = 0; r < 32; ++r) b[((col >> 1) + r) * 32] = d[r];
+  }
+  __device__ __forceinline__ void wait_st() const {}
+};
+constexpr int ADJ3_PRIV_DOUBLES = 256 * 32;   // shared-memory private state of one warp
+
+template <class Model, int HALF, class Priv>
 __device__ __forceinline__ void adj3_lambda_half(const double* __restrict__ MV, const double (&x)[32], const double (&v)[32],
-                                                 bool first, bool last, uint32_t tm) {
+                                                 bool first, bool last, const Priv& pv) {
   double acc[16];
-  if (!first) tmem::ld16(tm + TM_LACC + 32 * HALF, acc);
+  if (!first) pv.ld16(TM_LACC + 32 * HALF, acc);
   Model::mt_rows(MV, x, [&](auto rc, double h) {
     constexpr int r = decltype(rc)::value;
     if constexpr (r / 16 == HALF) {
@@ -151,19 +187,19 @@ __device__ __forceinline__ void adj3_lambda_half(const double* __restrict__ MV, 
   });
   if (last) {
     double lam[16];
-    tmem::ld16(tm + TM_LAM + 32 * HALF, lam);
+    pv.ld16(TM_LAM + 32 * HALF, lam);
 #pragma unroll
     for (int r = 0; r < 16; ++r) lam[r] += acc[r];
-    tmem::st16(tm + TM_LAM + 32 * HALF, lam);
+    pv.st16(TM_LAM + 32 * HALF, lam);
   } else {
-    tmem::st16(tm + TM_LACC + 32 * HALF, acc);
+    pv.st16(TM_LACC + 32 * HALF, acc);
   }
 }
 
 // one work item: stage `is` of the step whose per-step block is `SB`, stage block `STG`
-template <class Model>
+template <class Model, class Priv>
 __device__ __forceinline__ void adj3_consume(const RosParams& rp, const double* __restrict__ SB, const double* __restrict__ STG,
-                                             int is, bool with_mu, uint32_t tm) {
+                                             int is, bool with_mu, const Priv& pv) {
   const int S = rp.S;
   const double* lu = SB + FT_HDR;
   const double* dinv = SB + FT_HDR + FT_LU;
@@ -178,13 +214,13 @@ __device__ __forceinline__ void adj3_consume(const RosParams& rp, const double* 
 
   double x[32];
   {   // x = m_i * lambda + W_i      (:1285-1300; W_i already holds sum_j a_ji V_j + c_ji/h U_j)
-    tmem::wait_st();
-    tmem::ld32(tm + TM_LAM, x);
+    pv.wait_st();
+    pv.ld32(TM_LAM, x);
     if (!first) {
       double w[16];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        tmem::ld16(tm + TM_W + 64 * is + 32 * c, w);
+        pv.ld16(TM_W + 64 * is + 32 * c, w);
 #pragma unroll
         for (int r = 0; r < 16; ++r) x[16 * c + r] = fma(mi, x[16 * c + r], w[r]);
       }
@@ -205,87 +241,74 @@ __device__ __forceinline__ void adj3_consume(const RosParams& rp, const double* 
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         double w[16];
-        if (!first) tmem::ld16(tm + TM_W + 64 * j + 32 * c, w);
+        if (!first) pv.ld16(TM_W + 64 * j + 32 * c, w);
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
           const double t = fma(ca, v[16 * c + r], cc * x[16 * c + r]);
           w[r] = first ? t : (w[r] + t);
         }
-        tmem::st16(tm + TM_W + 64 * j + 32 * c, w);
+        pv.st16(TM_W + 64 * j + 32 * c, w);
       }
     }
   }
   // Lambda increment: LACC (+)= V_i + M'^T U_i     (:1328-1332 and the dJ/dt term :1402-1403); at the last stage of
   // the step Lambda += increment (:1324-1339 run after the stage loop).  Two halves of 16 rows bound the register use.
-  adj3_lambda_half<Model, 0>(MV, x, v, first, is == 0, tm);
-  adj3_lambda_half<Model, 1>(MV, x, v, first, is == 0, tm);
+  adj3_lambda_half<Model, 0>(MV, x, v, first, is == 0, pv);
+  adj3_lambda_half<Model, 1>(MV, x, v, first, is == 0, pv);
   if (with_mu) {   // Mu += a_p * (S^T U_i)_p     (:1352-1365)
     double mu[32];
-    tmem::ld32(tm + TM_MU, mu);
+    pv.ld32(TM_MU, mu);
     Model::stoich_cols(x, [&](auto pc, double s) {
       constexpr int p = decltype(pc)::value;
       mu[p] = fma(AP[p], s, mu[p]);
     });
-    tmem::st32(tm + TM_MU, mu);
+    pv.st32(TM_MU, mu);
   }
 }
 
-// ids[w]: cell of wave slot w; nacc[w], last_chunk[w]: its tape; order[]: processing order of the slots.
-// Only slots with ierr[cell] == 1 are processed.
-template <class Model>
-__global__ void __launch_bounds__(ADJ3_WARPS * 32, 1)
-k_ros_adj_cell(RosParams rp, long nwave, const int* __restrict__ ids, const int* __restrict__ nacc,
-               const int* __restrict__ last_chunk, const double* __restrict__ tape, const int* __restrict__ chunk_prev,
-               const double* __restrict__ fat, const long long* __restrict__ fat_off,
-               const int* __restrict__ ierr, const double* __restrict__ y_final, double* __restrict__ lambda,
-               double* __restrict__ mu, int* __restrict__ istatus, unsigned long long* __restrict__ queue,
-               const int* __restrict__ order, int nadj, int with_mu) {
-  extern __shared__ __align__(16) double smem[];
-  __shared__ uint32_t tmem_base_s;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* sm = smem + (size_t)warp * ADJ3_WARP_DOUBLES;
+struct AdjArgs {
+  long nwave;
+  const int* ids; const int* nacc; const int* last_chunk; const double* tape; const int* chunk_prev; const double* fat;
+  const long long* fat_off; const int* ierr; const double* y_final; double* lambda; double* mu; int* istatus;
+  unsigned long long* queue; const int* order; int nadj; int with_mu;
+};
+
+// the cell loop of one backward warp
+template <class Model, class Priv>
+__device__ __forceinline__ void adj3_warp_loop(const RosParams& rp, const AdjArgs& a, double* sm, const Priv& pv, int lane) {
   double* SBUF = sm;                                   // [2][FT_STEP_COPY]
   double* GBUF = sm + 2 * FT_STEP_COPY;                // [2][FT_STAGE]
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + 2 * FT_STEP_COPY + 2 * FT_STAGE);   // [0,1] step, [2,3] stage
-  if (warp == 0) tmem::alloc512(&tmem_base_s);
-  if (lane == 0) {
-    for (int b = 0; b < 4; ++b) mbar::init(bars + b, 1);
-    mbar::fence_init();
-  }
-  tmem::fence_before_sync();
-  __syncthreads();
-  tmem::fence_after_sync();
-  const uint32_t tm = tmem_base_s + ((uint32_t)(warp * 32) << 16);
   const int S = rp.S;
+  const bool with_mu = a.with_mu != 0;
   uint32_t ph_step0 = 0u, ph_step1 = 0u, ph_stage0 = 0u, ph_stage1 = 0u;   // phase parity per barrier (warp-uniform)
-
   for (;;) {
     unsigned long long q = 0;
-    if (lane == 0) q = atomicAdd(queue, 1ull);
+    if (lane == 0) q = atomicAdd(a.queue, 1ull);
     q = __shfl_sync(FATODE_FULL_MASK, q, 0);
-    if (q >= (unsigned long long)nwave) break;
-    if (order) q = (unsigned long long)order[q];   // longest trajectories first
-    const long cell = ids ? ids[q] : (long)q;
-    if (ierr[cell] != 1) continue;
-    const int nsteps = nacc[q];
+    if (q >= (unsigned long long)a.nwave) break;
+    if (a.order) q = (unsigned long long)a.order[q];   // longest trajectories first
+    const long cell = a.ids ? a.ids[q] : (long)q;
+    if (a.ierr[cell] != 1) continue;
+    const int nsteps = a.nacc[q];
     const int n_items = nsteps * S;
     {   // ADJINIT (model routine): lane = adjoint column m
       double lam[32], m0[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) lam[i] = Model::adjinit_lambda(i, lane, y_final[cell * 32 + i]);
+      for (int i = 0; i < 32; ++i) lam[i] = Model::adjinit_lambda(i, lane, a.y_final[cell * 32 + i]);
 #pragma unroll
       for (int p = 0; p < 32; ++p) m0[p] = 0.0;
-      tmem::st32(tm + TM_LAM, lam);
-      tmem::st32(tm + TM_MU, m0);
-      tmem::wait_st();
+      pv.st32(TM_LAM, lam);
+      pv.st32(TM_MU, m0);
+      pv.wait_st();
     }
     // prefetch cursor: walks the chunk list backwards, one work item ahead of the computation
-    int pf_chunk = last_chunk[q];
+    int pf_chunk = a.last_chunk[q];
     int pf_step = nsteps - 1;                      // forward-order index of the step the cursor is in
-    const double* fat_cell = fat + (size_t)fat_off[q] * S * FT_STAGE;
+    const double* fat_cell = a.fat + (size_t)a.fat_off[q] * S * FT_STAGE;
     auto issue = [&](int t) {                      // executed by lane 0
       const int si = t / S, is = S - 1 - (t - si * S);
-      const double* ent = tape + ((size_t)pf_chunk * FT_CHUNK + (pf_step % FT_CHUNK)) * FT_STEP;
+      const double* ent = a.tape + ((size_t)pf_chunk * FT_CHUNK + (pf_step % FT_CHUNK)) * FT_STEP;
       if (is == S - 1) {
         mbar::expect_tx(bars + (si & 1), FT_STEP_COPY * 8);
         mbar::bulk_g2s(SBUF + (si & 1) * FT_STEP_COPY, ent, FT_STEP_COPY * 8, bars + (si & 1));
@@ -295,7 +318,7 @@ k_ros_adj_cell(RosParams rp, long nwave, const int* __restrict__ ids, const int*
     };
     auto advance = [&](int t) {                    // cursor moves from item t to item t + 1 (all lanes, uniform)
       if ((t + 1) % S == 0) {
-        if (pf_step % FT_CHUNK == 0) pf_chunk = chunk_prev[pf_chunk];
+        if (pf_step % FT_CHUNK == 0) pf_chunk = a.chunk_prev[pf_chunk];
         --pf_step;
       }
     };
@@ -313,37 +336,66 @@ k_ros_adj_cell(RosParams rp, long nwave, const int* __restrict__ ids, const int*
       }
       if (t & 1) { mbar::wait(bars + 3, ph_stage1); ph_stage1 ^= 1u; }
       else { mbar::wait(bars + 2, ph_stage0); ph_stage0 ^= 1u; }
-      adj3_consume<Model>(rp, SBUF + (si & 1) * FT_STEP_COPY, GBUF + (t & 1) * FT_STAGE, is, with_mu != 0, tm);
+      adj3_consume<Model, Priv>(rp, SBUF + (si & 1) * FT_STEP_COPY, GBUF + (t & 1) * FT_STAGE, is, with_mu, pv);
     }
     // results: column m of Lambda / Mu is this lane's private vector
-    tmem::wait_st();
+    pv.wait_st();
     {
       double lam[32];
-      tmem::ld32(tm + TM_LAM, lam);   // .sync.aligned: executed by the whole warp, outside any lane-dependent branch
-      if (lane < nadj) {
-        double* dst = lambda + ((long)cell * nadj + lane) * 32;
+      pv.ld32(TM_LAM, lam);   // warp-collective for tensor memory: executed by the whole warp, outside any lane-dependent branch
+      if (lane < a.nadj) {
+        double* dst = a.lambda + ((long)cell * a.nadj + lane) * 32;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) *reinterpret_cast<double2*>(dst + i) = make_double2(lam[i], lam[i + 1]);
       }
     }
     if (with_mu) {
       double m0[32];
-      tmem::ld32(tm + TM_MU, m0);
-      if (lane < nadj) {
-        double* dst = mu + ((long)cell * nadj + lane) * Model::NP;
+      pv.ld32(TM_MU, m0);
+      if (lane < a.nadj) {
+        double* dst = a.mu + ((long)cell * a.nadj + lane) * Model::NP;
 #pragma unroll
         for (int p = 0; p < Model::NP; ++p) dst[p] = m0[p];
       }
     }
     if (lane == 0) {   // counters of the backward sweep (ADJ :1257-1267, :1303, :1312, :1381)
-      int* is_ = istatus + cell * 20;
+      int* is_ = a.istatus + cell * 20;
       is_[Nstp] += nsteps;
       is_[Njac] += nsteps * (2 + S + (rp.autonomous ? 0 : 1));
       is_[Ndec] += nsteps;
-      is_[Nsol] += nsteps * S * nadj;
+      is_[Nsol] += nsteps * S * a.nadj;
     }
     __syncwarp();
   }
+}
+
+// ids[w]: cell of wave slot w; nacc[w], last_chunk[w]: its tape; order[]: processing order of the slots.
+// Only slots with ierr[cell] == 1 are processed.  Dynamic shared memory: ADJ3_WARPS stream buffers, then the private
+// state of the warps beyond the four that tensor memory serves.
+template <class Model>
+__global__ void __launch_bounds__(ADJ3_WARPS * 32, 1)
+k_ros_adj_cell(RosParams rp, AdjArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sm = smem + (size_t)warp * ADJ3_WARP_DOUBLES;
+  if (warp == 0) tmem::alloc512(&tmem_base_s);
+  if (lane == 0) {
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + 2 * FT_STEP_COPY + 2 * FT_STAGE);
+    for (int b = 0; b < 4; ++b) mbar::init(bars + b, 1);
+    mbar::fence_init();
+  }
+  tmem::fence_before_sync();
+  __syncthreads();
+  tmem::fence_after_sync();
+  if (warp < 4) {
+    PrivTmem pv{tmem_base_s + ((uint32_t)(warp * 32) << 16)};
+    adj3_warp_loop<Model, PrivTmem>(rp, a, sm, pv, lane);
+  } else if constexpr (ADJ3_WARPS > 4) {
+    PrivSmem pv{smem + (size_t)ADJ3_WARPS * ADJ3_WARP_DOUBLES + (size_t)(warp - 4) * ADJ3_PRIV_DOUBLES + lane};
+    adj3_warp_loop<Model, PrivSmem>(rp, a, sm, pv, lane);
+  }
+  tmem::fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem::dealloc512(tmem_base_s);
 }

@@ -109,7 +109,9 @@ int fatode_debug_irregular_every(int k);
 int fatode_release_workspace(void);
 
 /* Per-call telemetry of the last batch call on this thread (kernel launches, waves, device time in
- * ms of each phase measured with CUDA events on the launch stream, tape bytes). */
+ * ms of each phase measured with CUDA events on the launch stream, tape bytes).  ms_forward: forward
+ * sweeps; ms_forward_tape: tape replay (general path) / k_expand_tape (per-thread path); ms_adjoint:
+ * backward sweeps. */
 typedef struct {
   int64_t launches;
   int64_t waves;
@@ -118,6 +120,7 @@ typedef struct {
   int64_t accepted_steps, attempts;
   int64_t cells_general;  /* cells integrated by the general (warp-per-cell, full pivoting) kernels */
   int64_t cells_deferred; /* cells re-queued because the tape pool of their wave was exhausted */
+  int64_t launches_forward, launches_expand, launches_adjoint; /* kernel launches behind ms_forward(+_tape), ms_adjoint */
 } fatode_stats;
 int fatode_get_last_stats(fatode_stats* out);
 

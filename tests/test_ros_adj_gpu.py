@@ -238,3 +238,26 @@ def test_hand_back_of_irregular_cells():
         assert np.array_equal(x, y)
     check_against_oracle(b, dict(y=a.y, istatus=a.istatus, rstatus=a.rstatus, ierr=a.ierr, lambda_=a.lambda_, mu=a.mu), 32)
     assert np.all(np.abs(a.mu_sum - b.mu_sum) <= 1e-9 * np.abs(a.mu).sum(axis=0) + 1e-300)
+
+
+def test_pipeline_modes_give_identical_results():
+    """fatode_set_pipeline(2) overlaps the forward sweep of the next wave with the backward sweep of the current one on
+    separate streams (double-buffered tape); scheduling must not change a single bit.  Small waves force several of them."""
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    rtol, atol = driver_tols()
+    y0 = perturbed_states(F.initial_state("cbm4"), 64)
+    t1 = T0 + 24 * 3600.0
+    F.lib().fatode_set_wave_cells(24)
+    try:
+        a = F.integrate_adj("cbm4", T0, t1, y0, 32, rtol, atol, icntrl_u=rodas4(), want_mu_sum=True)
+        assert F.last_stats().waves >= 3
+        F.lib().fatode_set_pipeline(2)
+        b = F.integrate_adj("cbm4", T0, t1, y0, 32, rtol, atol, icntrl_u=rodas4(), want_mu_sum=True)
+        assert F.last_stats().waves >= 3
+    finally:
+        F.lib().fatode_set_pipeline(0)
+        F.lib().fatode_set_wave_cells(0)
+    for x, y in ((a.y, b.y), (a.istatus, b.istatus), (a.rstatus, b.rstatus), (a.lambda_, b.lambda_), (a.mu, b.mu),
+                 (a.mu_sum, b.mu_sum)):
+        assert np.array_equal(x, y)
