@@ -356,9 +356,9 @@ def main():
         # dominant kernel: k_ros_adj; per-rank kernel time = sum of its launches on that rank (ranks run concurrently)
         adj_tflops = f_adj / (ms_adj_t / world * 1e-3) / 1e12
         # DRAM traffic of the backward kernel: measured with ncu (profiles/, dram__bytes_read.sum + dram__bytes_write.sum of
-        # k_ros_adj_cell) = 32.6 kB per accepted step (the step entry 3.3 kB + six stage blocks of 4.5 kB, streamed once
+        # k_ros_adj_cell) = 28.4 kB per accepted step (the step entry 3.3 kB + six stage blocks of 4.5 kB, streamed once
         # by TMA, plus the Lambda/Mu write-back); scaled here to the steps one launch of this run processes
-        traffic_per_step = 32.6e3
+        traffic_per_step = 28.4e3
         roof = {"bound": "fp64", "kernel": "k_ros_adj_cell<Cbm4Warp> (discrete adjoint sweep, lane = adjoint column)",
                 "achieved": adj_tflops, "peak": fp64_peak * world, "unit": "TFLOP/s", "frac": adj_tflops / (fp64_peak * world),
                 "peak_source": "DFMA micro-benchmark run by this bench on this GPU (fatode_measure_fp64_peak); "
