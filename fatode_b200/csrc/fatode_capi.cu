@@ -28,6 +28,7 @@
 #include "ros_warp_adj2.cuh"
 #include "ros_cell_fwd.cuh"
 #include "ros_cell_adj.cuh"
+#include "model_small_cell.cuh"
 
 using namespace fatode;
 
@@ -941,6 +942,39 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
   return rc_fail;
 }
 
+// Small models (roberts, small_strato): forward sweep only, one system per thread, everything inside one kernel
+// (dense DGETF2 with full partial pivoting and the singular-matrix retry per thread; no hand-back needed).
+template <class Cell>
+static int ros_device_small(const RosParams& rp, const typename Cell::Const& mc, int64_t ncells, double* d_y,
+                            const double* d_atol, const double* d_rtol, int* d_istatus, double* d_rstatus, int* d_ierr,
+                            cudaStream_t st) {
+  std::memset(&g_stats, 0, sizeof g_stats);
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  constexpr int LANES = 32;
+  const size_t smem = CellSmem<Cell, LANES>::BYTES;
+  CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd_cell<Cell, 0, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(g_ctr.ensure(16 * sizeof(unsigned long long)));
+  CUDA_TRY(g_wnacc.ensure(sizeof(int) * ncells));
+  CUDA_TRY(cudaMemsetAsync(g_ctr.p, 0, 16 * sizeof(unsigned long long), st));
+  int per_sm = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ros_fwd_cell<Cell, 0, LANES>, 32, smem));
+  const unsigned blocks = (unsigned)std::min<int64_t>((ncells + LANES - 1) / LANES, (int64_t)sms * std::max(per_sm, 1));
+  CellTape tape{nullptr, nullptr, nullptr, nullptr, nullptr, 0u, nullptr};
+  PhaseTimer tm(st);
+  tm.start();
+  k_ros_fwd_cell<Cell, 0, LANES><<<blocks, 32, smem, st>>>(rp, mc, ncells, nullptr, d_y, d_y, d_atol, d_rtol, d_istatus, d_rstatus,
+                                                            d_ierr, g_wnacc.as<int>(), tape, 0, 0, g_ctr.as<unsigned long long>());
+  CUDA_TRY(cudaGetLastError());
+  g_stats.ms_forward += tm.stop();
+  g_stats.launches++;
+  g_stats.launches_forward++;
+  g_stats.waves++;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
 // dispatcher: fast path where the model has one, then the general path for what is left
 template <class Cell, class Warp>
 static int ros_device(const RosParams& rp, const typename Warp::Const& mc, int64_t ncells, int nadj, bool with_mu,
@@ -1049,9 +1083,13 @@ static int ros_batch_impl(int family, int model, int64_t ncells, int nvar, int n
   }
   if (perr != 1) return broadcast_ierr(ncells, perr, istatus, rstatus, ierr, mem, st);
   const bool with_mu = (family == FAM_ADJ) && np > 0 && mu != nullptr;
-  if (model != FATODE_MODEL_CBM4) return fail(FATODE_EUNSUPPORTED, "model not available in this build yet");
+  if (model != FATODE_MODEL_CBM4 && do_adjoint)
+    return fail(FATODE_EUNSUPPORTED, "the discrete adjoint is available for the cbm4 model only in this build");
   Cbm4Const mc;
   cbm4_constants(model_params, mc);
+  SmallConst sc;
+  sc.fix[0] = model_params ? model_params[0] : (double)8.120E+16f * (double)1.0f;   // small_strato_dr.F90:55-56 (REAL(4) literals)
+  sc.fix[1] = model_params ? model_params[1] : (double)1.697E+16f * (double)1.0f;
 
   // stage arrays
   DevBuf b_atol, b_rtol, b_y, b_lam, b_mu, b_ist, b_rst, b_ierr, b_musum;
@@ -1083,8 +1121,14 @@ static int ros_batch_impl(int family, int model, int64_t ncells, int nvar, int n
       if (with_mu && mu_sum) { CUDA_TRY(b_musum.alloc(sizeof(double) * np * nadj)); d_musum = b_musum.as<double>(); }
     }
   }
-  int rc = ros_device<Cbm4Cell, Cbm4Warp>(rp, mc, ncells, nadj, with_mu, do_adjoint, d_y, d_lam, d_mu, b_atol.as<double>(),
-                                          b_rtol.as<double>(), d_ist, d_rst, d_ierr, d_musum, st);
+  int rc;
+  if (model == FATODE_MODEL_CBM4)
+    rc = ros_device<Cbm4Cell, Cbm4Warp>(rp, mc, ncells, nadj, with_mu, do_adjoint, d_y, d_lam, d_mu, b_atol.as<double>(),
+                                        b_rtol.as<double>(), d_ist, d_rst, d_ierr, d_musum, st);
+  else if (model == FATODE_MODEL_SMALL_STRATO)
+    rc = ros_device_small<SmallStratoCell>(rp, sc, ncells, d_y, b_atol.as<double>(), b_rtol.as<double>(), d_ist, d_rst, d_ierr, st);
+  else
+    rc = ros_device_small<RobertsCell>(rp, sc, ncells, d_y, b_atol.as<double>(), b_rtol.as<double>(), d_ist, d_rst, d_ierr, st);
   if (rc != 0) return rc;
   if (mem == FATODE_MEM_HOST) {
     CUDA_TRY(cudaMemcpyAsync(y, d_y, ny, cudaMemcpyDeviceToHost, st));

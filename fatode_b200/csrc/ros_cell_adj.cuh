@@ -118,9 +118,9 @@ k_expand_tape(RosParams rp, typename Cell::Const mc, unsigned nchunks, const int
     }
   }
   if (!rp.autonomous) {
-    Cell::photo(T, PHT);   // dJ/dt by the reference's forward difference (:1379-1382), DeltaMin of ros_DadjInt :1212
+    Cell::photo(T, mc, PHT);   // dJ/dt by the reference's forward difference (:1379-1382), DeltaMin of ros_DadjInt :1212
     const double Delta = sqrt(rp.roundoff) * fmax(1.0e-5, fabs(T));
-    Cell::photo(T + Delta, PHS);
+    Cell::photo(T + Delta, mc, PHS);
     cbm4_cell::jac_time<1>(Y0, mc.fix, PHT, JT0);
     cbm4_cell::jac_time<1>(Y0, mc.fix, PHS, DJ);
     const double rd = 1.0 / Delta;
@@ -131,7 +131,7 @@ k_expand_tape(RosParams rp, typename Cell::Const mc, unsigned nchunks, const int
     for (int n = 0; n < cbm4_cell::NJT; ++n) DJ[n] = 0.0;
   }
   double* sb = fat + ((size_t)(fo + (long long)chunk_seq[c] * FT_CHUNK + q) * S + is) * FT_STAGE;
-  Cell::photo(T + rp.Alpha[is] * dDir * H, PHS);
+  Cell::photo(T + rp.Alpha[is] * dDir * H, mc, PHS);
   cbm4_cell::jac_values<1>(Yi, mc.fix, PHS, sb + FT_JV);
   cbm4_cell::build_M<1>(Ki, DJ, rp.autonomous ? 0.0 : H * rp.Gamma[is], sb + FT_MV);
   if (with_mu) cbm4_cell::param_terms<1>(Yi, Y0, mc.fix, Ki, sb + FT_AP);

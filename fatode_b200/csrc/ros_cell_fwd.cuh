@@ -70,10 +70,31 @@ __host__ __device__ inline int fat_step_doubles(int S) { return S * FT_STAGE; } 
 static_assert(cbm4_cell::NLU <= FT_LU && cbm4_cell::NJ == FT_MV && cbm4_cell::NJ + cbm4_cell::NM <= FT_AP && FT_AP % 4 == 0 &&
               FT_STAGE % 4 == 0 && FT_STEP % 4 == 0 && FT_MV % 4 == 0, "tape layout");
 
+// ---- model policy of the per-thread kernels -----------------------------------------------------------------------
+//   N, NLU (doubles of the factor storage), NPH (doubles of the time-dependent context), Const
+//   photo(t, mc, PH)            time-dependent rate data at time t
+//   fun<SV>(y, PH, mc, f)       f = FUN(t, y)
+//   build_E<SV>(y, PH, mc, ghinv, lu)   E = ghinv*I - JAC(t, y) in the model's factor storage
+//   lu_factor<SV>(lu, dinv, swaps) -> LU_OK | LU_SINGULAR (zero pivot: ros_PrepareMatrix halves H) | LU_IRREGULAR
+//   lu_solve<SV>(lu, swaps, b)  DGETRS('N')
+// All arrays are thread-private with element stride SV.
+enum { LU_OK = 0, LU_SINGULAR = 1, LU_IRREGULAR = 2 };
+
 struct Cbm4Cell {
   static constexpr int N = 32, NP = 29, NLU = cbm4_cell::NLU, NPH = cbm4_cell::NPHOTO;
+  static constexpr bool HAS_GENERAL_PATH = true;   // irregular cells are handed to the warp-per-cell kernels
   typedef Cbm4Const Const;
-  __device__ static void photo(double t, double* PH) {       // Update_SUN + photolysis part of Update_RCONST
+  template <int SV>
+  __device__ static void build_E(const double* y, const double* PH, const Const& mc, double ghinv, double* lu) {
+    cbm4_cell::build_E<SV>(y, mc.fix, PH, ghinv, lu);
+  }
+  template <int SV>
+  __device__ static int lu_factor(double* lu, double* dinv, unsigned& swaps) {
+    return cbm4_cell::lu_factor<SV>(lu, dinv, swaps) ? LU_IRREGULAR : LU_OK;   // singular matrices included
+  }
+  template <int SV>
+  __device__ static void lu_solve(const double* lu, unsigned swaps, double* b) { cbm4_cell::lu_solve<SV>(lu, swaps, b); }
+  __device__ static void photo(double t, const Const&, double* PH) {       // Update_SUN + photolysis part of Update_RCONST
     const double s = Cbm4Warp::sun(t);
 #pragma unroll
     for (int k = 0; k < NPH; ++k) PH[k] = __dmul_rn(cbm4_dev::PHOTO_C[k], s);   // same order as cbm4_cell::PHOTO_IDX
@@ -104,8 +125,9 @@ struct CellTape {
 constexpr int CELL_LANES_SOLO = 32, CELL_LANES_SHARED = 26;
 template <class Model, int LANES>
 struct CellSmem {
-  static constexpr int OFF_Y = 0, OFF_F0 = 32, OFF_DF = 64, OFF_YN = 96, OFF_FC = 128, OFF_DINV = 160, OFF_K = 192,
-                       OFF_LU = 192 + 6 * 32, DOUBLES = OFF_LU + Model::NLU;
+  static constexpr int N_ = Model::N;
+  static constexpr int OFF_Y = 0, OFF_F0 = N_, OFF_DF = 2 * N_, OFF_YN = 3 * N_, OFF_FC = 4 * N_, OFF_DINV = 5 * N_, OFF_K = 6 * N_,
+                       OFF_LU = 12 * N_, DOUBLES = OFF_LU + Model::NLU;
   static constexpr size_t BYTES = sizeof(double) * DOUBLES * LANES;
 };
 
@@ -179,13 +201,13 @@ k_ros_fwd_cell(RosParams rp, typename Model::Const mc, long nwave, const int* __
         if (__dadd_rn(T, __dmul_rn(rp.tenth, H)) == T || H <= Roundoff) { ierr = -7; break; }
         if (adj) hexit = H;
         H = fmin(H, fabs(__dsub_rn(Tend, T)));
-        Model::photo(T, PHT);
+        Model::photo(T, mc, PHT);
         Model::template fun<SV>(y, PHT, mc, Fcn0);
         nfun++;
         njac++;                                   // J(T,Y) itself is evaluated inside build_E (same operands)
         if (!rp.autonomous) {                     // ros_FunTimeDerivative
           const double Delta = __dmul_rn(sqrt(Roundoff), fmax(rp.deltamin_fd, fabs(T)));
-          Model::photo(__dadd_rn(T, Delta), PHS);
+          Model::photo(__dadd_rn(T, Delta), mc, PHS);
           Model::template fun<SV>(y, PHS, mc, dFdT);
           nfun++;
           const double rd = __ddiv_rn(1.0, Delta);
@@ -194,13 +216,22 @@ k_ros_fwd_cell(RosParams rp, typename Model::Const mc, long nwave, const int* __
         }
         need_setup = false;
       }
-      // ---- one attempt: ros_PrepareMatrix, the stages, the error estimate (:940-1136)
+      // ---- one attempt: ros_PrepareMatrix (:1894-1948), the stages, the error estimate (:940-1136)
       {
-        const double ghinv = __ddiv_rn(1.0, __dmul_rn(__dmul_rn(dDir, H), rp.Gamma[0]));
-        cbm4_cell::build_E<SV>(y, mc.fix, PHT, ghinv, lu);
-        const int bad = cbm4_cell::lu_factor<SV>(lu, dinv, swaps);
-        if (count_la) ndec++;
-        if (bad) { ierr = IERR_IRREGULAR; break; }
+        int Nconsecutive = 0;
+        int code;
+        for (;;) {
+          const double ghinv = __ddiv_rn(1.0, __dmul_rn(__dmul_rn(dDir, H), rp.Gamma[0]));
+          Model::template build_E<SV>(y, PHT, mc, ghinv, lu);
+          code = Model::template lu_factor<SV>(lu, dinv, swaps);
+          if (count_la) ndec++;
+          if (code != LU_SINGULAR) break;
+          nsng++;
+          if (++Nconsecutive > 5) break;
+          H = __dmul_rn(H, 0.5);
+        }
+        if (code == LU_IRREGULAR) { ierr = IERR_IRREGULAR; break; }
+        if (code == LU_SINGULAR) { ierr = -8; break; }
       }
       const double dH = __dmul_rn(dDir, H);
       for (int is = 0; is < S; ++is) {
@@ -222,7 +253,7 @@ k_ros_fwd_cell(RosParams rp, typename Model::Const mc, long nwave, const int* __
             Ynew[i * SV] = v;
           }
           const double Tau = __dadd_rn(T, __dmul_rn(__dmul_rn(rp.Alpha[is], dDir), H));
-          Model::photo(Tau, PHS);
+          Model::photo(Tau, mc, PHS);
           Model::template fun<SV>(Ynew, PHS, mc, Fcn);
           nfun++;
         }
@@ -242,7 +273,7 @@ k_ros_fwd_cell(RosParams rp, typename Model::Const mc, long nwave, const int* __
             k[i * SV] = v;
           }
         }
-        cbm4_cell::lu_solve<SV>(lu, swaps, k);
+        Model::template lu_solve<SV>(lu, swaps, k);
         if (count_la) nsol++;
       }
       // new solution, error estimate, ros_ErrorNorm (sequential sum i = 1..N)
@@ -291,6 +322,7 @@ k_ros_fwd_cell(RosParams rp, typename Model::Const mc, long nwave, const int* __
           double* e = tape.base + ((size_t)cur_chunk * FT_CHUNK + slot) * FT_STEP;
           st_global_256(e, T, H, (double)swaps, 0.0);
           double* el = e + FT_HDR;
+          static_assert(MODE == 0 || Model::N == 32, "the tape layout is the 32-species one");
 #pragma unroll 4
           for (int q = 0; q + 3 < Model::NLU; q += 4) st_global_256(el + q, lu[q * SV], lu[(q + 1) * SV], lu[(q + 2) * SV], lu[(q + 3) * SV]);
           {
