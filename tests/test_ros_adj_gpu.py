@@ -261,3 +261,61 @@ def test_pipeline_modes_give_identical_results():
     for x, y in ((a.y, b.y), (a.istatus, b.istatus), (a.rstatus, b.rstatus), (a.lambda_, b.lambda_), (a.mu, b.mu),
                  (a.mu_sum, b.mu_sum)):
         assert np.array_equal(x, y)
+
+
+def test_full_size_batch_properties():
+    """BASELINE config 2 at full size: 2^20 CBM-IV cells, ROS_ADJ Rodas4, NADJ = 32, NP = 29 on one GPU, device-resident
+    through the C ABI (FATODE_MEM_DEVICE).  Size-independent properties:
+      * every cell succeeds; the ISTATUS closed forms of SURVEY.md §8a hold for every cell;
+      * the second half of the batch repeats the first half: equal inputs give equal bits wherever they are scheduled
+        (different waves, batches, lanes);
+      * mu_sum equals the sum of the per-cell Mu; a strided sample agrees with the oracle (1e-9)."""
+    import ctypes
+    import torch
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    n, nadj, npar, S = 1 << 20, 32, 29, 6
+    rtol, atol = driver_tols()
+    ic, rc = rodas4(), np.zeros(20)
+    dev = torch.device("cuda", 0)
+    half = perturbed_states(F.initial_state("cbm4"), n // 2)
+    y0 = torch.from_numpy(np.concatenate([half, half])).to(dev)
+    y = y0.clone()
+    lam = torch.zeros((n, nadj, 32), dtype=torch.float64, device=dev)
+    mu = torch.zeros((n, nadj, npar), dtype=torch.float64, device=dev)
+    ist = torch.zeros((n, 20), dtype=torch.int32, device=dev)
+    rst = torch.zeros((n, 20), dtype=torch.float64, device=dev)
+    ierr = torch.zeros((n,), dtype=torch.int32, device=dev)
+    musum = torch.zeros((nadj, npar), dtype=torch.float64, device=dev)
+    vp = ctypes.c_void_p
+    p = lambda a: vp(a.ctypes.data)
+    r = F.lib().fatode_ros_integrate_adj_batch(F.MODEL_CBM4, n, 32, npar, nadj, vp(y.data_ptr()), vp(lam.data_ptr()), vp(mu.data_ptr()),
+                                               T0, T1, None, None, p(atol), p(rtol), p(ic), p(rc), vp(ist.data_ptr()),
+                                               vp(rst.data_ptr()), vp(ierr.data_ptr()), vp(musum.data_ptr()), None, F.MEM_DEVICE,
+                                               vp(torch.cuda.current_stream().cuda_stream))
+    assert r == 0, F.lib().fatode_last_error().decode()
+    torch.cuda.synchronize()
+    st = F.last_stats()
+    assert bool((ierr == 1).all()) and st.cells_general == 0
+    # ISTATUS closed forms (discrete adjoint, non-autonomous): A accepted, att attempts
+    I = ist.cpu().numpy().astype(np.int64)
+    A, R = I[:, 3], I[:, 4]
+    att = I[:, 2] - A
+    assert np.all(att >= A + R) and np.all(I[:, 0] == 2 * A + 5 * att) and np.all(I[:, 1] == A + A * (2 + S + 1))
+    assert np.all(I[:, 5] == att + I[:, 7] + A) and np.all(I[:, 6] == att * S + A * S * nadj) and np.all(I[:, 7] == 0)
+    assert st.accepted_steps == int(A.sum())
+    h = n // 2
+    for t in (y, lam, mu, ist, rst):
+        assert torch.equal(t[:h], t[h:])
+    s = mu.sum(dim=0)
+    assert torch.all((musum - s).abs() <= 1e-9 * mu.abs().sum(dim=0) + 1e-300)
+    idx = np.arange(1, h, 8191 * 8 + 5)[:8]
+    ref = O.ros_adj("cbm4", y0[idx].cpu().numpy(), nadj, T0, T1, atol, rtol, ic)
+    import types
+    res = types.SimpleNamespace(y=y[idx].cpu().numpy(), istatus=ist[idx].cpu().numpy(), rstatus=rst[idx].cpu().numpy(),
+                                ierr=ierr[idx].cpu().numpy(), lambda_=lam[idx].cpu().numpy(), mu=mu[idx].cpu().numpy())
+    check_against_oracle(res, ref, nadj)
+    assert np.array_equal(res.y, ref["y"])
+    dt = (st.ms_forward + st.ms_forward_tape + st.ms_adjoint) * 1e-3
+    print(f"2^20 cells: forward {st.ms_forward:.0f} ms, expand {st.ms_forward_tape:.0f} ms, backward {st.ms_adjoint:.0f} ms "
+          f"-> {n / dt:.0f} cells/s (device time), {st.waves} waves")
