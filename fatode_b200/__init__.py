@@ -70,6 +70,9 @@ def lib():
         L.fatode_ros_integrate_adj_batch.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                                      ctypes.c_int, vp, vp, vp, ctypes.c_double, ctypes.c_double,
                                                      vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        L.fatode_ros_integrate_tlm_batch.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, vp, vp,
+                                                     ctypes.c_double, ctypes.c_double, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                                     ctypes.c_int, vp]
         _lib = L
     return _lib
 
@@ -125,6 +128,7 @@ class Result:
     lambda_: np.ndarray | None = None   # [ncells, NADJ, N]  = Lambda(N,NADJ) per cell (Fortran order)
     mu: np.ndarray | None = None        # [ncells, NADJ, NP] = Mu(NP,NADJ) per cell
     mu_sum: np.ndarray | None = None    # [NADJ, NP] deterministic sum over cells
+    y_tlm: np.ndarray | None = None     # [ncells, NTLM, N] = Y_tlm(N,NTLM) per cell
 
 
 def integrate(model, tin, tout, var, rtol, atol, icntrl_u=None, rcntrl_u=None, model_params=None) -> Result:
@@ -168,6 +172,29 @@ def integrate_adj(model, tin, tout, y, nadj, rtol, atol, np_=None, icntrl_u=None
                                                 _ptr(rc), _ptr(ist), _ptr(rst), _ptr(ierr), _ptr(mus), _ptr(mp),
                                                 MEM_HOST, None))
     return Result(yy, ist, rst, ierr, lam, mu, mus)
+
+
+def integrate_tlm(model, tin, tout, y, y_tlm, rtol, atol, icntrl_u=None, rcntrl_u=None, atol_tlm=None, rtol_tlm=None,
+                  model_params=None) -> Result:
+    """Batched TLM/ROS_TLM INTEGRATE_TLM (TLM/ROS_TLM/ROS_TLM_f90_Integrator.F90:35). y: [ncells, N]; y_tlm: [ncells, NTLM, N]."""
+    mid = model_id(model)
+    yy = np.atleast_2d(np.array(y, dtype=np.float64, order="C"))
+    nc, n = yy.shape
+    yt = np.array(y_tlm, dtype=np.float64, order="C").reshape(nc, -1, n)
+    ntlm = yt.shape[1]
+    rtol = np.ascontiguousarray(rtol, dtype=np.float64)
+    atol = np.ascontiguousarray(atol, dtype=np.float64)
+    ic, rc = _ctrl(icntrl_u, rcntrl_u)
+    at = None if atol_tlm is None else np.ascontiguousarray(atol_tlm, dtype=np.float64)
+    rt = None if rtol_tlm is None else np.ascontiguousarray(rtol_tlm, dtype=np.float64)
+    ist = np.zeros((nc, 20), dtype=np.int32)
+    rst = np.zeros((nc, 20))
+    ierr = np.zeros(nc, dtype=np.int32)
+    mp = None if model_params is None else np.ascontiguousarray(model_params, dtype=np.float64)
+    _check(lib().fatode_ros_integrate_tlm_batch(mid, nc, n, ntlm, _ptr(yy), _ptr(yt), float(tin), float(tout), _ptr(at), _ptr(rt),
+                                                _ptr(atol), _ptr(rtol), _ptr(ic), _ptr(rc), _ptr(ist), _ptr(rst), _ptr(ierr),
+                                                _ptr(mp), MEM_HOST, None))
+    return Result(yy, ist, rst, ierr, y_tlm=yt)
 
 
 def measure_fp64_peak(iters=20000) -> float:

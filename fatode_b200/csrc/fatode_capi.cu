@@ -637,13 +637,13 @@ struct StreamSet {
 };
 static thread_local StreamSet g_ss;
 static thread_local CachedBuf g_comp[2], g_fat[2], g_cprev[2], g_cowner[2], g_cseq[2], g_wids[2], g_wnacc2[2], g_wlast2[2],
-    g_border[2], g_bfatoff[2], g_wbatch[2], g_ctr;
+    g_border[2], g_bfatoff[2], g_wbatch[2], g_cnext[2], g_wfirst[2], g_ctr;
 
 static void release_pipeline_workspace() {
   for (int i = 0; i < 2; ++i) {
     g_comp[i].release(); g_fat[i].release(); g_cprev[i].release(); g_cowner[i].release(); g_cseq[i].release();
     g_wids[i].release(); g_wnacc2[i].release(); g_wlast2[i].release(); g_border[i].release(); g_bfatoff[i].release();
-    g_wbatch[i].release();
+    g_wbatch[i].release(); g_cnext[i].release(); g_wfirst[i].release();
   }
   g_ctr.release();
 }
@@ -654,14 +654,16 @@ template <class Cell, class Warp>
 static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, int64_t ncells, int nadj, bool with_mu,
                            bool do_adjoint, double* d_y, double* d_lambda, double* d_mu, const double* d_atol,
                            const double* d_rtol, int* d_istatus, double* d_rstatus, int* d_ierr, cudaStream_t st,
-                           std::vector<int>& general) {
+                           std::vector<int>& general, bool tlm_sweep = false) {
+  // tlm_sweep: the second sweep is the tangent-linear one (forward order, d_lambda = Y_tlm, nadj = NTLM) instead of the
+  // discrete adjoint; everything else (waves, batches, tape, expand) is shared
   int dev = 0, sms = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_cbm4_rc, mc.rc_base, sizeof(double) * 81, 0, cudaMemcpyHostToDevice, st));
   CUDA_TRY(g_ctr.ensure(16 * sizeof(unsigned long long)));
   unsigned long long* d_ctr = g_ctr.as<unsigned long long>();   // [0,1] forward queues, [2,3] pool heads, [4,5] backward queues
-  CellTape tape{nullptr, nullptr, nullptr, nullptr, nullptr, 0u, nullptr};
+  CellTape tape{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0u, nullptr};
   if (!do_adjoint) {
     constexpr int LANES = CELL_LANES_SOLO;
     const size_t cell_smem = CellSmem<Cell, LANES>::BYTES;
@@ -705,6 +707,7 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
   CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd_cell<Cell, 1, CELL_LANES_SOLO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)CellSmem<Cell, CELL_LANES_SOLO>::BYTES));
   CUDA_TRY(cudaFuncSetAttribute(k_ros_adj_cell<Warp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem));
+  CUDA_TRY(cudaFuncSetAttribute(k_ros_tlm_cell<Warp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem));
   CUDA_TRY(g_ss.init());
   StreamSet ss = g_ss;
   if (pmode <= 1) ss.sX = ss.sF;
@@ -751,6 +754,10 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
     CUDA_TRY(g_border[i].ensure(sizeof(int) * wave_max));
     CUDA_TRY(g_bfatoff[i].ensure(sizeof(long long) * wave_max));
     CUDA_TRY(g_wbatch[i].ensure(sizeof(int) * wave_max));
+    if (tlm_sweep) {
+      CUDA_TRY(g_cnext[i].ensure(sizeof(int) * (size_t)pool_chunks));
+      CUDA_TRY(g_wfirst[i].ensure(sizeof(int) * wave_max));
+    }
   }
   CUDA_TRY(g_wierr.ensure(sizeof(int) * wave_max));
 
@@ -810,6 +817,8 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
     tape.chunk_prev = g_cprev[p].as<int>();
     tape.chunk_owner = g_cowner[p].as<int>();
     tape.chunk_seq = g_cseq[p].as<int>();
+    tape.chunk_next = tlm_sweep ? g_cnext[p].as<int>() : nullptr;
+    tape.first_chunk = tlm_sweep ? g_wfirst[p].as<int>() : nullptr;
     tape.pool_head = reinterpret_cast<unsigned int*>(d_ctr + 2 + p);
     tape.pool_chunks = pool_chunks;
     tape.last_chunk = g_wlast2[p].as<int>();
@@ -844,7 +853,7 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
     for (int64_t w = 0; w < n; ++w) {
       if (h_ierr[w] == IERR_DEFERRED) { next_pending.push_back(ids[w]); ++n_def; }
       else if (h_ierr[w] == IERR_IRREGULAR) general.push_back(ids[w]);
-      else if (h_ierr[w] == 1) { ++n_ok; steps += h_nacc[w]; order.push_back((int)w); }
+      else if (h_ierr[w] == 1 || (tlm_sweep && h_ierr[w] < 0 && h_ierr[w] > -100)) { ++n_ok; steps += h_nacc[w]; order.push_back((int)w); }
     }
     g_stats.cells_deferred += n_def;
     if (dbg) fprintf(stderr, "[wave %d] cells %ld ok %ld deferred %ld chunks %u/%u\n", k, (long)n, (long)n_ok, (long)n_def, chunks_used, pool_chunks);
@@ -894,7 +903,7 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
         k_expand_tape<Cell><<<chunks_used, FT_CHUNK * S, 0, ss.sX>>>(
             rp, mc, chunks_used, g_cowner[p].as<int>(), g_cseq[p].as<int>(), g_wids[p].as<int>(), d_ierr, g_wnacc2[p].as<int>(),
             g_wlast2[p].as<int>(), g_comp[p].as<double>(), g_fat[f].as<double>(), g_bfatoff[p].as<long long>(),
-            g_wbatch[p].as<int>(), (int)bi, with_mu ? 1 : 0);
+            g_wbatch[p].as<int>(), (int)bi, tlm_sweep ? 2 : (with_mu ? 1 : 0));
         CUDA_TRY(cudaGetLastError());
         if (int e = t_end(ss.sX)) return e;
         CUDA_TRY(cudaEventRecord(ss.expand_done[f], ss.sX));
@@ -902,10 +911,17 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
         CUDA_TRY(cudaMemsetAsync(d_ctr + 4 + f, 0, sizeof(unsigned long long), ss.sA));
         if (int e = t_begin(ss.sA, 2)) return e;
         const int ablocks = (int)std::min<int64_t>(sms, (nb + ADJ3_WARPS - 1) / ADJ3_WARPS);
-        AdjArgs aa{nb, g_wids[p].as<int>(), g_wnacc2[p].as<int>(), g_wlast2[p].as<int>(), g_comp[p].as<double>(), g_cprev[p].as<int>(),
-                   g_fat[f].as<double>(), g_bfatoff[p].as<long long>(), d_ierr, d_y, d_lambda, with_mu ? d_mu : nullptr, d_istatus,
-                   d_ctr + 4 + f, g_border[p].as<int>() + bt.o0, nadj, with_mu ? 1 : 0};
-        k_ros_adj_cell<Warp><<<ablocks, ADJ3_WARPS * 32, adj_smem, ss.sA>>>(rp, aa);
+        if (tlm_sweep) {
+          TlmArgs ta{nb, g_wids[p].as<int>(), g_wnacc2[p].as<int>(), g_wfirst[p].as<int>(), g_comp[p].as<double>(), g_cnext[p].as<int>(),
+                     g_fat[f].as<double>(), g_bfatoff[p].as<long long>(), d_ierr, d_lambda, d_istatus, d_ctr + 4 + f,
+                     g_border[p].as<int>() + bt.o0, nadj};
+          k_ros_tlm_cell<Warp><<<ablocks, ADJ3_WARPS * 32, adj_smem, ss.sA>>>(rp, ta);
+        } else {
+          AdjArgs aa{nb, g_wids[p].as<int>(), g_wnacc2[p].as<int>(), g_wlast2[p].as<int>(), g_comp[p].as<double>(), g_cprev[p].as<int>(),
+                     g_fat[f].as<double>(), g_bfatoff[p].as<long long>(), d_ierr, d_y, d_lambda, with_mu ? d_mu : nullptr, d_istatus,
+                     d_ctr + 4 + f, g_border[p].as<int>() + bt.o0, nadj, with_mu ? 1 : 0};
+          k_ros_adj_cell<Warp><<<ablocks, ADJ3_WARPS * 32, adj_smem, ss.sA>>>(rp, aa);
+        }
         CUDA_TRY(cudaGetLastError());
         if (int e = t_end(ss.sA)) return e;
         CUDA_TRY(cudaEventRecord(ss.fat_free[f], ss.sA));
@@ -961,7 +977,7 @@ static int ros_device_small(const RosParams& rp, const typename Cell::Const& mc,
   int per_sm = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ros_fwd_cell<Cell, 0, LANES>, 32, smem));
   const unsigned blocks = (unsigned)std::min<int64_t>((ncells + LANES - 1) / LANES, (int64_t)sms * std::max(per_sm, 1));
-  CellTape tape{nullptr, nullptr, nullptr, nullptr, nullptr, 0u, nullptr};
+  CellTape tape{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0u, nullptr};
   PhaseTimer tm(st);
   tm.start();
   k_ros_fwd_cell<Cell, 0, LANES><<<blocks, 32, smem, st>>>(rp, mc, ncells, nullptr, d_y, d_y, d_atol, d_rtol, d_istatus, d_rstatus,
@@ -971,6 +987,29 @@ static int ros_device_small(const RosParams& rp, const typename Cell::Const& mc,
   g_stats.launches++;
   g_stats.launches_forward++;
   g_stats.waves++;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// INTEGRATE_TLM (forward error control): state sweep + tangent-linear sweep on the per-thread path.  There is no general
+// TLM kernel yet: a cell the static-pattern LU cannot take keeps IERR = FATODE_IERR_TLM_IRREGULAR (-20) and its Y / Y_tlm
+// untouched (never observed for the shipped inputs).
+template <class Cell, class Warp>
+static int ros_tlm_device(const RosParams& rp, const typename Warp::Const& mc, int64_t ncells, int ntlm, double* d_y, double* d_ytlm,
+                          const double* d_atol, const double* d_rtol, int* d_istatus, double* d_rstatus, int* d_ierr,
+                          cudaStream_t st) {
+  std::memset(&g_stats, 0, sizeof g_stats);
+  std::vector<int> general;
+  if (int e = ros_device_fast<Cell, Warp>(rp, mc, ncells, ntlm, false, true, d_y, d_ytlm, nullptr, d_atol, d_rtol, d_istatus,
+                                          d_rstatus, d_ierr, st, general, /*tlm_sweep=*/true)) return e;
+  g_stats.cells_general = (int64_t)general.size();
+  if (!general.empty()) {
+    std::vector<int> h(ncells);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), d_ierr, sizeof(int) * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int c : general) h[c] = -20;
+    CUDA_TRY(cudaMemcpyAsync(d_ierr, h.data(), sizeof(int) * ncells, cudaMemcpyHostToDevice, st));
+  }
   CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
 }
@@ -1066,6 +1105,7 @@ static int ros_batch_impl(int family, int model, int64_t ncells, int nvar, int n
   if (ncells < 0 || !y || !atol || !rtol || !istatus || !rstatus || !ierr) return fail(FATODE_EINVAL, "NULL required argument");
   if (int e = check_model_dims(model, nvar, np)) return e;
   if (family == FAM_ADJ && (!lambda || nadj < 1)) return fail(FATODE_EINVAL, "lambda is NULL or nadj < 1");
+  if (family == FAM_TLM && (!lambda || nadj < 1)) return fail(FATODE_EINVAL, "y_tlm is NULL or ntlm < 1");
   if (int e = check_device()) return e;
   if (ncells == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1080,6 +1120,14 @@ static int ros_batch_impl(int family, int model, int64_t ncells, int nvar, int n
     if (perr == 1 && ic[7] != 0) return fail(FATODE_EUNSUPPORTED, "ICNTRL(8) (SaveLU) is not implemented by the reference either");
     do_adjoint = (adjtype == 2);
     if (do_adjoint && nadj > 32) return fail(FATODE_EUNSUPPORTED, "nadj > 32 per call is not supported yet");
+  }
+  const bool do_tlm = (family == FAM_TLM);
+  if (do_tlm) {
+    if (perr == 1 && ic[11] != 0)
+      return fail(FATODE_EUNSUPPORTED, "ROS_TLM with TLM truncation-error control (ICNTRL(12) != 0, the preset when ICNTRL_U is "
+                                       "absent) is not built yet: pass ICNTRL_U with ICNTRL_U(12) = 0");
+    if (nadj > 32) return fail(FATODE_EUNSUPPORTED, "ntlm > 32 per call is not supported yet");
+    if (model != FATODE_MODEL_CBM4) return fail(FATODE_EUNSUPPORTED, "INTEGRATE_TLM is available for the cbm4 model only in this build");
   }
   if (perr != 1) return broadcast_ierr(ncells, perr, istatus, rstatus, ierr, mem, st);
   const bool with_mu = (family == FAM_ADJ) && np > 0 && mu != nullptr;
@@ -1108,7 +1156,7 @@ static int ros_batch_impl(int family, int model, int64_t ncells, int nvar, int n
     CUDA_TRY(b_ierr.alloc(sizeof(int) * ncells));
     CUDA_TRY(cudaMemcpyAsync(b_y.p, y, ny, cudaMemcpyHostToDevice, st));
     d_y = b_y.as<double>(); d_ist = b_ist.as<int>(); d_rst = b_rst.as<double>(); d_ierr = b_ierr.as<int>();
-    if (family == FAM_ADJ) {
+    if (family == FAM_ADJ || do_tlm) {
       // Lambda and Mu are INTENT(INOUT) in the reference: cells whose forward sweep fails keep the caller's values
       CUDA_TRY(b_lam.alloc(nl));
       d_lam = b_lam.as<double>();
@@ -1122,7 +1170,10 @@ static int ros_batch_impl(int family, int model, int64_t ncells, int nvar, int n
     }
   }
   int rc;
-  if (model == FATODE_MODEL_CBM4)
+  if (do_tlm)
+    rc = ros_tlm_device<Cbm4Cell, Cbm4Warp>(rp, mc, ncells, nadj, d_y, d_lam, b_atol.as<double>(), b_rtol.as<double>(), d_ist, d_rst,
+                                            d_ierr, st);
+  else if (model == FATODE_MODEL_CBM4)
     rc = ros_device<Cbm4Cell, Cbm4Warp>(rp, mc, ncells, nadj, with_mu, do_adjoint, d_y, d_lam, d_mu, b_atol.as<double>(),
                                         b_rtol.as<double>(), d_ist, d_rst, d_ierr, d_musum, st);
   else if (model == FATODE_MODEL_SMALL_STRATO)
@@ -1135,6 +1186,7 @@ static int ros_batch_impl(int family, int model, int64_t ncells, int nvar, int n
     CUDA_TRY(cudaMemcpyAsync(istatus, d_ist, sizeof(int) * 20 * ncells, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(rstatus, d_rst, sizeof(double) * 20 * ncells, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(ierr, d_ierr, sizeof(int) * ncells, cudaMemcpyDeviceToHost, st));
+    if (do_tlm) CUDA_TRY(cudaMemcpyAsync(lambda, d_lam, nl, cudaMemcpyDeviceToHost, st));
     if (family == FAM_ADJ && do_adjoint) {
       CUDA_TRY(cudaMemcpyAsync(lambda, d_lam, nl, cudaMemcpyDeviceToHost, st));
       if (with_mu) CUDA_TRY(cudaMemcpyAsync(mu, d_mu, nm, cudaMemcpyDeviceToHost, st));
@@ -1161,6 +1213,15 @@ extern "C" int fatode_ros_integrate_adj_batch(int model, int64_t ncells, int nva
   (void)atol_adj; (void)rtol_adj;
   return ros_batch_impl(FAM_ADJ, model, ncells, nvar, np, nadj, y, lambda, mu, tin, tout, atol, rtol, icntrl_u, rcntrl_u,
                         istatus, rstatus, ierr, mu_sum, model_params, mem, stream);
+}
+
+extern "C" int fatode_ros_integrate_tlm_batch(int model, int64_t ncells, int nvar, int ntlm, double* y, double* y_tlm, double tin,
+                                              double tout, const double* atol_tlm, const double* rtol_tlm, const double* atol,
+                                              const double* rtol, const int* icntrl_u, const double* rcntrl_u, int* istatus,
+                                              double* rstatus, int* ierr, const double* model_params, int mem, void* stream) {
+  (void)atol_tlm; (void)rtol_tlm;   // used by the reference only when ICNTRL(12) != 0 (TLM truncation-error control)
+  return ros_batch_impl(FAM_TLM, model, ncells, nvar, 0, ntlm, y, y_tlm, nullptr, tin, tout, atol, rtol, icntrl_u, rcntrl_u,
+                        istatus, rstatus, ierr, nullptr, model_params, mem, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

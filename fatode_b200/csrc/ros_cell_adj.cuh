@@ -68,6 +68,10 @@ __global__ void k_cbm4_hess(double fix, double* __restrict__ out) {
   cbm4_cell::hess_values<1>(y, fix, ph, out);
 }
 
+// which cells of a wave take part in the second sweep: successful ones; for the tangent-linear sweep also the cells whose
+// state sweep ended with one of the reference's error codes (ros_TLM_Int has advanced Y_tlm up to that point)
+__device__ __forceinline__ bool sweep_takes_cell(int ierr, bool tlm) { return ierr == 1 || (tlm && ierr < 0 && ierr > -100); }
+
 constexpr int XP_ROW = 226;   // shared-memory row of one step's inputs (Y0 + K = 224 doubles, +2: conflict-free across steps)
 template <class Cell>
 __global__ void __launch_bounds__(FT_CHUNK * 6, 4)
@@ -75,7 +79,7 @@ k_expand_tape(RosParams rp, typename Cell::Const mc, unsigned nchunks, const int
               const int* __restrict__ chunk_seq, const int* __restrict__ ids, const int* __restrict__ ierr,
               const int* __restrict__ nacc, const int* __restrict__ last_chunk, const double* __restrict__ tape,
               double* __restrict__ fat, const long long* __restrict__ fat_off, const int* __restrict__ batch_of,
-              int batch, int with_mu) {
+              int batch, int mode) {   // mode 0: no a_p, 1: a_p (adjoint with Mu), 2: tangent-linear sweep (hg = 0, dJ/dt in the AP slot)
   // one block per tape chunk (FT_CHUNK steps x S stages = one thread per item); the steps' inputs are staged through
   // shared memory with coalesced loads, the outputs go straight to the tape
   __shared__ __align__(16) double in_s[FT_CHUNK * XP_ROW];
@@ -83,9 +87,9 @@ k_expand_tape(RosParams rp, typename Cell::Const mc, unsigned nchunks, const int
   const int S = rp.S;
   const long c = blockIdx.x;
   const int w = chunk_owner[c];
-  if (batch_of[w] != batch || ierr[ids ? ids[w] : w] != 1) return;   // cells of other batches / unfinished cells
+  if (batch_of[w] != batch || !sweep_takes_cell(ierr[ids ? ids[w] : w], mode == 2)) return;   // other batches / unfinished cells
   const long long fo = fat_off[w];            // first stage block of this cell in its batch's fat buffer
-  const int cnt = (c == last_chunk[w]) ? ((nacc[w] - 1) % FT_CHUNK) + 1 : FT_CHUNK;
+  const int cnt = (c == last_chunk[w]) ? min(((nacc[w] - 1) % FT_CHUNK) + 1, nacc[w]) : FT_CHUNK;
   constexpr int NE = FT_STEP;
   const double* chunk = tape + (size_t)c * FT_CHUNK * NE;
   const int row2 = (N + S * N) / 2;   // double2 per step
@@ -133,9 +137,15 @@ k_expand_tape(RosParams rp, typename Cell::Const mc, unsigned nchunks, const int
   double* sb = fat + ((size_t)(fo + (long long)chunk_seq[c] * FT_CHUNK + q) * S + is) * FT_STAGE;
   Cell::photo(T + rp.Alpha[is] * dDir * H, mc, PHS);
   cbm4_cell::jac_values<1>(Yi, mc.fix, PHS, sb + FT_JV);
-  cbm4_cell::build_M<1>(Ki, DJ, rp.autonomous ? 0.0 : H * rp.Gamma[is], sb + FT_MV);
-  if (with_mu) cbm4_cell::param_terms<1>(Yi, Y0, mc.fix, Ki, sb + FT_AP);
-  else
+  cbm4_cell::build_M<1>(Ki, DJ, (rp.autonomous || mode == 2) ? 0.0 : H * rp.Gamma[is], sb + FT_MV);
+  if (mode == 1) cbm4_cell::param_terms<1>(Yi, Y0, mc.fix, Ki, sb + FT_AP);
+  else if (mode == 2) {   // the tangent-linear sweep applies dJ/dt to the stage vector itself (LSS_Mul_Jac2, TLM :620)
+    static_assert(cbm4_cell::NJT <= 32, "dJ/dt entries fit the AP slot");
+#pragma unroll
+    for (int p = 0; p < 32; p += 4)
+      st_global_256(sb + FT_AP + p, p < cbm4_cell::NJT ? DJ[p] : 0.0, p + 1 < cbm4_cell::NJT ? DJ[p + 1] : 0.0,
+                    p + 2 < cbm4_cell::NJT ? DJ[p + 2] : 0.0, p + 3 < cbm4_cell::NJT ? DJ[p + 3] : 0.0);
+  } else
     for (int p = 0; p < 32; p += 4) st_global_256(sb + FT_AP + p, 0.0, 0.0, 0.0, 0.0);
 }
 
@@ -394,6 +404,197 @@ k_ros_adj_cell(RosParams rp, AdjArgs a) {
   } else if constexpr (ADJ3_WARPS > 4) {
     PrivSmem pv{smem + (size_t)ADJ3_WARPS * ADJ3_WARP_DOUBLES + (size_t)(warp - 4) * ADJ3_PRIV_DOUBLES + lane};
     adj3_warp_loop<Model, PrivSmem>(rp, a, sm, pv, lane);
+  }
+  tmem::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem::dealloc512(tmem_base_s);
+}
+
+
+// =====================================================================================================================
+// Tangent linear model, ROS_TLM with forward error control (ICNTRL(12) = 0): ros_TLM_Int
+// (TLM/ROS_TLM/ROS_TLM_f90_Integrator.F90:462-707) split into the state sweep (k_ros_fwd_cell, identical step sequence
+// because the TLM does not enter the error estimate) and this sweep over the tape in FORWARD order.
+// Lane m of a warp owns column m of Y_tlm of one cell.  Private per-lane state in tensor memory: K_tlm[6][32]
+// (columns 0..383), the stage function Fcn_tlm (384..447) and Y_tlm itself (448..511).  Per stage i:
+//   Ynew = Y_tlm (+ sum_j a_ij K_tlm_j at ros_NewF stages);  Fcn_tlm = J(T_i,Y_i) Ynew                        (:588-604)
+//   k = Fcn_tlm + sum_j c_ij/(dir h) K_tlm_j + h gamma_i (dJ/dt) Ynew + Hess_Vec(K_i, Y_tlm);  k <- E^-1 k     (:606-633)
+// and after the stages Y_tlm += sum_j m_j K_tlm_j (:642-648).  The operands J_i, Hess x K_i, dJ/dt come from
+// k_expand_tape (mode 2), the L\U factors from the forward sweep.
+constexpr uint32_t TMT_K = 0, TMT_F = 384, TMT_Y = 448;
+
+template <class Model>
+__device__ __forceinline__ void tlm_consume(const RosParams& rp, const double* __restrict__ SB, const double* __restrict__ STG,
+                                            int is, const PrivTmem& pv) {
+  const int S = rp.S;
+  const double* lu = SB + FT_HDR;
+  const double* dinv = SB + FT_HDR + FT_LU;
+  const double* JV = STG + FT_JV;
+  const double* MV = STG + FT_MV;
+  const double* DJ = STG + FT_AP;
+  const double dDir = (rp.tend >= rp.tstart) ? 1.0 : -1.0;
+  const double H = SB[1];
+  const unsigned swaps = (unsigned)SB[2];
+  pv.wait_st();
+  double yn[32], k[32];
+  pv.ld32(TMT_Y, yn);
+  if (is == 0 || rp.NewF[is]) {
+    for (int j = 0; j < is; ++j) {
+      const double a = rp.A[is * (is - 1) / 2 + j];
+      if (a != 0.0) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          double w[16];
+          pv.ld16(TMT_K + 64 * j + 32 * c, w);
+#pragma unroll
+          for (int r = 0; r < 16; ++r) yn[16 * c + r] = fma(a, w[r], yn[16 * c + r]);
+        }
+      }
+    }
+    cbm4_cell::j_vec(JV, yn, k);          // Fcn_tlm = J(T_i, Y_i) Ynew_tlm
+    pv.st32(TMT_F, k);
+  } else {
+    pv.ld32(TMT_F, k);                    // stage without a new function evaluation: previous Fcn_tlm, Ynew = Y_tlm
+  }
+  {
+    const double inv_dH = 1.0 / (dDir * H);
+    for (int j = 0; j < is; ++j) {
+      const double hc = rp.C[is * (is - 1) / 2 + j] * inv_dH;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        double w[16];
+        pv.ld16(TMT_K + 64 * j + 32 * c, w);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) k[16 * c + r] = fma(hc, w[r], k[16 * c + r]);
+      }
+    }
+  }
+  if (!rp.autonomous && rp.Gamma[is] != 0.0) cbm4_cell::dj_vec_add(DJ, dDir * H * rp.Gamma[is], yn, k);
+  pv.ld32(TMT_Y, yn);                     // Hess_Vec(T, Y, K_i, Y_tlm): the step's Y_tlm, not the stage vector
+  cbm4_cell::m_vec_add(MV, yn, k);
+  cbm4_cell::lun_solve(lu, dinv, swaps, k);
+  pv.st32(TMT_K + 64 * is, k);
+  if (is == S - 1) {                      // new solution (:642-648)
+    pv.wait_st();
+    for (int j = 0; j < S; ++j) {
+      const double m = rp.M[j];
+      if (m != 0.0) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          double w[16];
+          pv.ld16(TMT_K + 64 * j + 32 * c, w);
+#pragma unroll
+          for (int r = 0; r < 16; ++r) yn[16 * c + r] = fma(m, w[r], yn[16 * c + r]);
+        }
+      }
+    }
+    pv.st32(TMT_Y, yn);
+  }
+}
+
+struct TlmArgs {
+  long nwave;
+  const int* ids; const int* nacc; const int* first_chunk; const double* tape; const int* chunk_next; const double* fat;
+  const long long* fat_off; const int* ierr; double* y_tlm; int* istatus; unsigned long long* queue; const int* order; int ntlm;
+};
+
+template <class Model>
+__global__ void __launch_bounds__(ADJ3_WARPS * 32, 1)
+k_ros_tlm_cell(RosParams rp, TlmArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sm = smem + (size_t)warp * ADJ3_WARP_DOUBLES;
+  double* SBUF = sm;
+  double* GBUF = sm + 2 * FT_STEP_COPY;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + 2 * FT_STEP_COPY + 2 * FT_STAGE);
+  if (warp == 0) tmem::alloc512(&tmem_base_s);
+  if (lane == 0) {
+    for (int b = 0; b < 4; ++b) mbar::init(bars + b, 1);
+    mbar::fence_init();
+  }
+  tmem::fence_before_sync();
+  __syncthreads();
+  tmem::fence_after_sync();
+  const PrivTmem pv{tmem_base_s + ((uint32_t)(warp * 32) << 16)};
+  const int S = rp.S;
+  uint32_t ph_step0 = 0u, ph_step1 = 0u, ph_stage0 = 0u, ph_stage1 = 0u;
+  for (;;) {
+    unsigned long long q = 0;
+    if (lane == 0) q = atomicAdd(a.queue, 1ull);
+    q = __shfl_sync(FATODE_FULL_MASK, q, 0);
+    if (q >= (unsigned long long)a.nwave) break;
+    if (a.order) q = (unsigned long long)a.order[q];
+    const long cell = a.ids ? a.ids[q] : (long)q;
+    if (!sweep_takes_cell(a.ierr[cell], true)) continue;
+    const int nsteps = a.nacc[q];
+    const int n_items = nsteps * S;
+    double* ycol = a.y_tlm + ((long)cell * a.ntlm + (lane < a.ntlm ? lane : 0)) * 32;
+    {   // Y_tlm(:, m) of the caller
+      double y0[32];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(ycol + i);
+        y0[i] = lane < a.ntlm ? v.x : 0.0;
+        y0[i + 1] = lane < a.ntlm ? v.y : 0.0;
+      }
+      pv.st32(TMT_Y, y0);
+      pv.wait_st();
+    }
+    int pf_chunk = a.first_chunk[q];
+    int pf_step = 0;
+    const double* fat_cell = a.fat + (size_t)a.fat_off[q] * S * FT_STAGE;
+    auto issue = [&](int t) {                      // executed by lane 0
+      const int si = t / S, is = t - si * S;
+      const double* ent = a.tape + ((size_t)pf_chunk * FT_CHUNK + (pf_step % FT_CHUNK)) * FT_STEP;
+      if (is == 0) {
+        mbar::expect_tx(bars + (si & 1), FT_STEP_COPY * 8);
+        mbar::bulk_g2s(SBUF + (si & 1) * FT_STEP_COPY, ent, FT_STEP_COPY * 8, bars + (si & 1));
+      }
+      mbar::expect_tx(bars + 2 + (t & 1), FT_STAGE * 8);
+      mbar::bulk_g2s(GBUF + (t & 1) * FT_STAGE, fat_cell + ((size_t)pf_step * S + is) * FT_STAGE, FT_STAGE * 8, bars + 2 + (t & 1));
+    };
+    auto advance = [&](int t) {                    // cursor moves from item t to item t + 1 (all lanes, uniform)
+      if ((t + 1) % S == 0) {
+        ++pf_step;
+        if (pf_step % FT_CHUNK == 0) pf_chunk = a.chunk_next[pf_chunk];
+      }
+    };
+    if (n_items > 0 && lane == 0) issue(0);
+    for (int t = 0; t < n_items; ++t) {
+      const int si = t / S, is = t - si * S;
+      __syncwarp();
+      if (t + 1 < n_items) {
+        advance(t);
+        if (lane == 0) issue(t + 1);
+      }
+      if (is == 0) {
+        if (si & 1) { mbar::wait(bars + 1, ph_step1); ph_step1 ^= 1u; }
+        else { mbar::wait(bars + 0, ph_step0); ph_step0 ^= 1u; }
+      }
+      if (t & 1) { mbar::wait(bars + 3, ph_stage1); ph_stage1 ^= 1u; }
+      else { mbar::wait(bars + 2, ph_stage0); ph_stage0 ^= 1u; }
+      tlm_consume<Model>(rp, SBUF + (si & 1) * FT_STEP_COPY, GBUF + (t & 1) * FT_STAGE, is, pv);
+    }
+    pv.wait_st();
+    {
+      double y1[32];
+      pv.ld32(TMT_Y, y1);
+      if (lane < a.ntlm) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) *reinterpret_cast<double2*>(ycol + i) = make_double2(y1[i], y1[i + 1]);
+      }
+    }
+    if (lane == 0) {   // counters of ros_TLM_Int on top of the state sweep's (:543-562, 600-601, 625-632)
+      int* is_ = a.istatus + cell * 20;
+      int n_newf = 0;
+      for (int s = 1; s < S; ++s) n_newf += rp.NewF[s] ? 1 : 0;
+      // the state sweep counted one Jacobian per step set-up and one solve per stage: LSS_Jac2 doubles the former when
+      // non-autonomous, LSS_Jac1 adds one per new-function stage of every attempt, every TLM column adds a solve
+      is_[Njac] = is_[Njac] * (rp.autonomous ? 1 : 2) + is_[Nstp] * n_newf;
+      is_[Nsol] = is_[Nsol] * (1 + a.ntlm);
+    }
+    __syncwarp();
   }
   tmem::fence_before_sync();
   __syncthreads();

@@ -112,6 +112,8 @@ struct CellTape {
   int* chunk_prev;              // [pool_chunks] backward links
   int* chunk_owner;             // [pool_chunks] wave slot that owns the chunk
   int* chunk_seq;               // [pool_chunks] position of the chunk in its cell's trajectory (0, 1, ...)
+  int* chunk_next;              // [pool_chunks] forward links (tangent-linear sweep); may be nullptr
+  int* first_chunk;             // [cells of the wave]; may be nullptr
   unsigned int* pool_head;      // next free chunk
   unsigned int pool_chunks;
   int* last_chunk;              // [cells of the wave]
@@ -317,6 +319,9 @@ k_ros_fwd_cell(RosParams rp, typename Model::Const mc, long nwave, const int* __
             tape.chunk_prev[c] = cur_chunk;
             tape.chunk_owner[c] = (int)w;
             tape.chunk_seq[c] = (nacc - 1) / FT_CHUNK;
+            if (tape.chunk_next) {
+              if (cur_chunk >= 0) tape.chunk_next[cur_chunk] = (int)c; else tape.first_chunk[w] = (int)c;
+            }
             cur_chunk = (int)c;
           }
           double* e = tape.base + ((size_t)cur_chunk * FT_CHUNK + slot) * FT_STEP;

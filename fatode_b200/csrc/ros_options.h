@@ -21,7 +21,9 @@ inline int ros_parse_options(int family, int N, const int* icntrl_u, const doubl
   double rc[20];
   std::memset(ic, 0, sizeof ic);
   std::memset(rc, 0, sizeof rc);
-  if (family == FAM_TLM) { ic[2] = 5; ic[11] = 1; }   // ROS_TLM presets (TLM :70-72); RCNTRL(3)=STEPMIN handled by caller
+  // ROS_TLM presets (TLM :70-74): ICNTRL(2) = 1 (scalar tolerances!), (3) = 5, (12) = 1; RCNTRL(3) = STEPMIN is a SAVEd
+  // variable carrying the last step size to the NEXT call — every system of a batch is a first call (0)
+  if (family == FAM_TLM) { ic[1] = 1; ic[2] = 5; ic[11] = 1; }
   for (int i = 0; i < 20; ++i) {
     if (icntrl_u) { if (family == FAM_FWD ? icntrl_u[i] > 0 : icntrl_u[i] >= 0) ic[i] = icntrl_u[i]; }
     if (rcntrl_u) { if (family == FAM_FWD ? rcntrl_u[i] > 0 : rcntrl_u[i] >= 0) rc[i] = rcntrl_u[i]; }

@@ -91,6 +91,22 @@ int fatode_ros_integrate_adj_batch(int model, int64_t ncells, int nvar, int np, 
                                    int* istatus, double* rstatus, int* ierr, double* mu_sum,
                                    const double* model_params, int mem, void* stream);
 
+/* INTEGRATE_TLM of TLM/ROS_TLM (TLM/ROS_TLM/ROS_TLM_f90_Integrator.F90:35):
+ *   INTEGRATE_TLM(N,NTLM,NNZERO,Y,Y_tlm,TIN,TOUT,ATOL_tlm,RTOL_tlm,ATOL,RTOL,FUN,JAC,HESS_VEC,
+ *                 ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U)
+ * y_tlm [ncells][ntlm][nvar] = Y_tlm(1:N,1:NTLM) of cell c, column-major (in: sensitivities at TIN, out: at TOUT).
+ * ICNTRL_U/RCNTRL_U override the presets (ICNTRL(2)=1, (3)=5, (12)=1) when >= 0 (:77-82).  Built: forward error
+ * control, ICNTRL(12) = 0, i.e. any call that passes ICNTRL_U with entry 12 zero; the TLM truncation-error control
+ * (ICNTRL(12) != 0, the preset when icntrl_u == NULL) returns FATODE_EUNSUPPORTED.  ATOL_tlm/RTOL_tlm are used by the
+ * reference only in that mode.  RCNTRL(3) = STEPMIN (a SAVEd variable of the reference that carries the last step size
+ * over to the next call) is 0 for every cell.  ntlm <= 32, cbm4 only; HESS_VEC is the model's registered routine.
+ * A cell whose state sweep ends with an error code returns Y and Y_tlm as of its last accepted step, as the reference. */
+int fatode_ros_integrate_tlm_batch(int model, int64_t ncells, int nvar, int ntlm, double* y, double* y_tlm,
+                                   double tin, double tout, const double* atol_tlm, const double* rtol_tlm,
+                                   const double* atol, const double* rtol, const int* icntrl_u,
+                                   const double* rcntrl_u, int* istatus, double* rstatus, int* ierr,
+                                   const double* model_params, int mem, void* stream);
+
 /* Engine knobs (process-wide): trajectory-tape budget in bytes (0 = 60% of free device memory) and
  * the number of cells per wave (0 = automatic). */
 int fatode_set_tape_budget(uint64_t bytes);

@@ -86,6 +86,13 @@ struct Cbm4 {
     cbm4_gen::hessian(y, fix, rconst, hess);
     cbm4_gen::hesstr_vec(hess, u, v, htv);
   }
+  // HESS_VEC callback of INTEGRATE_TLM: hv = (f_yy x u) . v  (no cbm4 TLM driver upstream; see gen_cbm4.py)
+  void hess_vec(double t, const double* y, const double* u, const double* v, double* hv) {
+    double hess[cbm4_gen::NHESS];
+    update(t);
+    cbm4_gen::hessian(y, fix, rconst, hess);
+    cbm4_gen::hess_vec(hess, u, v, hv);
+  }
   // dFun_dRcoeff: cbm4_Parameters.F90:1135-1175
   void dfun_drcoeff(const double* v, double* dfdr) {
     double arp[81];

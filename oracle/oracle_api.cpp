@@ -86,6 +86,24 @@ int oracle_ros_adj_batch(int model, long ncells, int np, int nadj, double* y, do
   return -1;
 }
 
+// INTEGRATE_TLM of TLM/ROS_TLM looped over cells (cbm4 only: the model needs a HESS_VEC callback).
+// y_tlm[cell][NTLM][N] = Y_tlm(N,NTLM) per cell; atol_tlm/rtol_tlm [NTLM][N] shared by the batch (may be NULL when
+// ICNTRL(12) = 0).  icntrl == NULL means "ICNTRL_U not present" (the presets apply).
+int oracle_ros_tlm_batch(int model, long ncells, int ntlm, double* y, double* y_tlm, double tin, double tout,
+                         const double* atol_tlm, const double* rtol_tlm, const double* atol, const double* rtol,
+                         const int* icntrl, const double* rcntrl, int* istatus, double* rstatus, int* ierr, int nthreads) {
+  if (model != MODEL_CBM4) return -1;
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+  const int N = Cbm4::N;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+  for (long c = 0; c < ncells; ++c) {
+    Cbm4 mdl;
+    ierr[c] = ros_integrate_tlm<Cbm4>(mdl, ntlm, y + c * N, y_tlm + c * (long)N * ntlm, tin, tout, atol_tlm, rtol_tlm, atol, rtol,
+                                      icntrl, rcntrl, istatus + c * 20, rstatus + c * 20);
+  }
+  return 0;
+}
+
 }  // extern "C"
 
 // unit-level probes for the parity tests

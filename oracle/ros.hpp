@@ -409,6 +409,148 @@ struct Rosenbrock {
     }
     return 1;
   }
+
+  // ros_TLM_Int: TLM/ROS_TLM/ROS_TLM_f90_Integrator.F90:462-707 (forward + tangent linear model in one sweep).
+  // Y_tlm(N,NTLM) column-major.  TLMtruncErr: ICNTRL(12) != 0 (ros_ErrorNorm_tlm :745-769).
+  int tlm(double* Y, int NTLM, double* Y_tlm, double Tstart, double Tend, const double* AbsTol, const double* RelTol,
+          const double* AbsTol_tlm, const double* RelTol_tlm, bool TLMtruncErr) {
+    const RosTableauData& tb = cfg.tab;
+    const int S = tb.S;
+    double Ynew[N], Fcn0[N], Fcn[N], dFdT[N], Yerr[N], Tmp[N];
+    std::vector<double> K(N * S), Ynew_tlm((size_t)N * NTLM), Fcn0_tlm((size_t)N * NTLM), Fcn_tlm((size_t)N * NTLM),
+        K_tlm((size_t)N * S * NTLM), Yerr_tlm((size_t)N * NTLM);
+    double H, Hnew, HC, HG, Fac, Tau, Err;
+    const double DeltaMin = 1.0e-5;   // :500
+    bool RejectLastH = false, RejectMoreH = false;
+    const double Roundoff = cfg.Roundoff;
+    const int LD = N * S;
+    double T = Tstart;
+    RSTATUS[Nhexit] = 0.0;
+    H = std::fmin(std::fmax(std::fabs(cfg.Hmin), std::fabs(cfg.Hstart)), std::fabs(cfg.Hmax));
+    if (std::fabs(H) <= 10.0 * Roundoff) H = DeltaMin;
+    const int Direction = (Tend >= Tstart) ? +1 : -1;
+    H = Direction * H;
+    while ((Direction > 0 && (T - Tend) + Roundoff <= 0.0) || (Direction < 0 && (Tend - T) + Roundoff <= 0.0)) {
+      if (ISTATUS[Nstp] > cfg.Max_no_steps) return -6;
+      if ((T + 0.1 * H) == T || H <= Roundoff) return -7;
+      H = std::fmin(H, std::fabs(Tend - T));
+      mdl.fun(T, Y, Fcn0);
+      ISTATUS[Nfun]++;
+      mdl.jac(T, Y, lss.fjac);                                      // LSS_Jac :543
+      ISTATUS[Njac]++;
+      for (int m = 0; m < NTLM; ++m) lss.mul_jac(&Fcn0_tlm[(size_t)N * m], &Y_tlm[(size_t)N * m]);   // :551-553
+      if (!cfg.Autonomous) {
+        fun_time_derivative(T, Y, Fcn0, dFdT);                       // :557
+        double Delta = std::sqrt(Roundoff) * std::fmax(DeltaMin, std::fabs(T));
+        mdl.jac(T + Delta, Y, lss.djdt);                             // LSS_Jac2 :559
+        ISTATUS[Njac]++;
+        lss.jac_time_derivative(Delta);                              // :561
+      }
+      for (;;) {   // UntilAccepted
+        if (prepare_matrix(H, Direction, tb.Gamma[0], true)) return -8;
+        for (int istage = 1; istage <= S; ++istage) {
+          const int ioffset = N * (istage - 1);
+          for (int i = 0; i < N; ++i) Ynew[i] = Y[i];
+          for (size_t i = 0; i < (size_t)N * NTLM; ++i) Ynew_tlm[i] = Y_tlm[i];
+          if (istage == 1) {
+            for (int i = 0; i < N; ++i) Fcn[i] = Fcn0[i];
+            for (size_t i = 0; i < (size_t)N * NTLM; ++i) Fcn_tlm[i] = Fcn0_tlm[i];
+          } else if (tb.NewF[istage - 1]) {
+            for (int j = 1; j <= istage - 1; ++j) {
+              const double a = tb.A[(istage - 1) * (istage - 2) / 2 + j - 1];
+              for (int i = 0; i < N; ++i) Ynew[i] = Ynew[i] + a * K[N * (j - 1) + i];
+              for (int m = 0; m < NTLM; ++m)
+                for (int i = 0; i < N; ++i)
+                  Ynew_tlm[(size_t)N * m + i] = Ynew_tlm[(size_t)N * m + i] + a * K_tlm[(size_t)LD * m + N * (j - 1) + i];
+            }
+            Tau = T + tb.Alpha[istage - 1] * Direction * H;
+            mdl.fun(Tau, Ynew, Fcn);
+            ISTATUS[Nfun]++;
+            mdl.jac(Tau, Ynew, lss.fjac1);                           // LSS_Jac1 :600
+            ISTATUS[Njac]++;
+            for (int m = 0; m < NTLM; ++m) lss.mul_jac1(&Fcn_tlm[(size_t)N * m], &Ynew_tlm[(size_t)N * m]);
+          }
+          for (int i = 0; i < N; ++i) K[ioffset + i] = Fcn[i];
+          for (int m = 0; m < NTLM; ++m)
+            for (int i = 0; i < N; ++i) K_tlm[(size_t)LD * m + ioffset + i] = Fcn_tlm[(size_t)N * m + i];
+          for (int j = 1; j <= istage - 1; ++j) {
+            HC = tb.C[(istage - 1) * (istage - 2) / 2 + j - 1] / (Direction * H);
+            for (int i = 0; i < N; ++i) K[ioffset + i] = K[ioffset + i] + HC * K[N * (j - 1) + i];
+            for (int m = 0; m < NTLM; ++m)
+              for (int i = 0; i < N; ++i)
+                K_tlm[(size_t)LD * m + ioffset + i] = K_tlm[(size_t)LD * m + ioffset + i] + HC * K_tlm[(size_t)LD * m + N * (j - 1) + i];
+          }
+          if (!cfg.Autonomous && tb.Gamma[istage - 1] != 0.0) {
+            HG = Direction * H * tb.Gamma[istage - 1];
+            for (int i = 0; i < N; ++i) K[ioffset + i] = K[ioffset + i] + HG * dFdT[i];
+            for (int m = 0; m < NTLM; ++m) {
+              lss.mul_djdt(Tmp, &Ynew_tlm[(size_t)N * m]);             // LSS_Mul_Jac2 :620
+              for (int i = 0; i < N; ++i) K_tlm[(size_t)LD * m + ioffset + i] = K_tlm[(size_t)LD * m + ioffset + i] + HG * Tmp[i];
+            }
+          }
+          lss.solve(false, &K[ioffset]);
+          ISTATUS[Nsol]++;
+          for (int m = 0; m < NTLM; ++m) {
+            mdl.hess_vec(T, Y, &K[ioffset], &Y_tlm[(size_t)N * m], Tmp);   // :628
+            for (int i = 0; i < N; ++i) K_tlm[(size_t)LD * m + ioffset + i] = K_tlm[(size_t)LD * m + ioffset + i] + 1.0 * Tmp[i];
+            lss.solve(false, &K_tlm[(size_t)LD * m + ioffset]);
+            ISTATUS[Nsol]++;
+          }
+        }
+        for (int i = 0; i < N; ++i) Ynew[i] = Y[i];
+        for (int j = 1; j <= S; ++j)
+          for (int i = 0; i < N; ++i) Ynew[i] = Ynew[i] + tb.M[j - 1] * K[N * (j - 1) + i];
+        for (int m = 0; m < NTLM; ++m) {
+          for (int i = 0; i < N; ++i) Ynew_tlm[(size_t)N * m + i] = Y_tlm[(size_t)N * m + i];
+          for (int j = 1; j <= S; ++j)
+            for (int i = 0; i < N; ++i)
+              Ynew_tlm[(size_t)N * m + i] = Ynew_tlm[(size_t)N * m + i] + tb.M[j - 1] * K_tlm[(size_t)LD * m + N * (j - 1) + i];
+        }
+        for (int i = 0; i < N; ++i) Yerr[i] = 0.0;
+        for (int j = 1; j <= S; ++j)
+          for (int i = 0; i < N; ++i) Yerr[i] = Yerr[i] + tb.E[j - 1] * K[N * (j - 1) + i];
+        Err = ros_error_norm(N, Y, Ynew, Yerr, AbsTol, RelTol, cfg.VectorTol);
+        if (TLMtruncErr) {
+          for (size_t i = 0; i < (size_t)N * NTLM; ++i) Yerr_tlm[i] = 0.0;
+          for (int m = 0; m < NTLM; ++m)
+            for (int j = 1; j <= S; ++j)
+              for (int i = 0; i < N; ++i)
+                Yerr_tlm[(size_t)N * m + i] = Yerr_tlm[(size_t)N * m + i] + tb.E[j - 1] * K_tlm[(size_t)LD * m + N * (j - 1) + i];
+          for (int m = 0; m < NTLM; ++m) {                            // ros_ErrorNorm_tlm :745-769
+            const double t = ros_error_norm(N, &Y_tlm[(size_t)N * m], &Ynew_tlm[(size_t)N * m], &Yerr_tlm[(size_t)N * m],
+                                            &AbsTol_tlm[(size_t)N * m], &RelTol_tlm[(size_t)N * m], cfg.VectorTol);
+            Err = std::fmax(Err, t);
+          }
+          Err = std::fmax(Err, 1.0e-10);
+        }
+        Fac = std::fmin(cfg.FacMax, std::fmax(cfg.FacMin, cfg.FacSafe / o_root(Err, tb.ELO)));
+        Hnew = H * Fac;
+        ISTATUS[Nstp]++;
+        if (Err <= 1.0 || H <= cfg.Hmin) {
+          ISTATUS[Nacc]++;
+          for (int i = 0; i < N; ++i) Y[i] = Ynew[i];
+          for (size_t i = 0; i < (size_t)N * NTLM; ++i) Y_tlm[i] = Ynew_tlm[i];
+          T = T + Direction * H;
+          Hnew = std::fmax(cfg.Hmin, std::fmin(Hnew, cfg.Hmax));
+          if (RejectLastH) Hnew = std::fmin(Hnew, H);
+          RSTATUS[Nhexit] = H;
+          RSTATUS[Nhnew] = Hnew;
+          RSTATUS[Ntexit] = T;
+          RejectLastH = false;
+          RejectMoreH = false;
+          H = Hnew;
+          break;
+        } else {
+          if (RejectMoreH) Hnew = H * cfg.FacRej;
+          RejectMoreH = RejectLastH;
+          RejectLastH = true;
+          H = Hnew;
+          if (ISTATUS[Nacc] >= 1) ISTATUS[Nrej]++;
+        }
+      }
+    }
+    return 1;
+  }
 };
 
 // ---------------------------------------------------------------------------
@@ -451,6 +593,26 @@ int ros_integrate_adj(Model& mdl, int NP, int NADJ, double* Y, double* Lambda, d
     mdl.adjinit(NADJ, TOUT, Y, Lambda, with_mu ? Mu : nullptr);          // :579
     if (AdjointType == 2) IERR = r.adjoint(NADJ, NP, Lambda, with_mu ? Mu : nullptr, TIN, TOUT);
   }
+  if (ISTATUS_U) for (int i = 0; i < 20; ++i) ISTATUS_U[i] = r.ISTATUS[i];
+  if (RSTATUS_U) for (int i = 0; i < 20; ++i) RSTATUS_U[i] = r.RSTATUS[i];
+  return IERR;
+}
+
+// INTEGRATE_TLM of TLM/ROS_TLM (:35-98): presets ICNTRL(1)=0, (2)=1, (3)=5, (12)=1, RCNTRL(3)=STEPMIN (a SAVEd
+// variable that carries the last step size over to the NEXT call, :63,74,93; restated as its initial value 0: every
+// system of a batch is a first call); user values override when >= 0.  ROS_TLM has no IERR_U; the code is returned.
+template <class Model>
+int ros_integrate_tlm(Model& mdl, int NTLM, double* Y, double* Y_tlm, double TIN, double TOUT, const double* ATOL_tlm,
+                      const double* RTOL_tlm, const double* ATOL, const double* RTOL, const int* ICNTRL_U,
+                      const double* RCNTRL_U, int* ISTATUS_U, double* RSTATUS_U) {
+  int ICNTRL[20] = {0};
+  double RCNTRL[20] = {0};
+  ICNTRL[1] = 1; ICNTRL[2] = 5; ICNTRL[11] = 1;
+  if (ICNTRL_U) for (int i = 0; i < 20; ++i) if (ICNTRL_U[i] >= 0) ICNTRL[i] = ICNTRL_U[i];
+  if (RCNTRL_U) for (int i = 0; i < 20; ++i) if (RCNTRL_U[i] >= 0) RCNTRL[i] = RCNTRL_U[i];
+  Rosenbrock<Model> r(mdl);
+  int IERR = ros_parse(ROS_TLM, Model::N, ICNTRL, RCNTRL, TIN, TOUT, ATOL, RTOL, r.cfg);
+  if (IERR == 1) IERR = r.tlm(Y, NTLM, Y_tlm, TIN, TOUT, ATOL, RTOL, ATOL_tlm, RTOL_tlm, ICNTRL[11] != 0);
   if (ISTATUS_U) for (int i = 0; i < 20; ++i) ISTATUS_U[i] = r.ISTATUS[i];
   if (RSTATUS_U) for (int i = 0; i < 20; ++i) RSTATUS_U[i] = r.RSTATUS[i];
   return IERR;

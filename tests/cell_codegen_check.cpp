@@ -85,6 +85,13 @@ static inline int dgetf2(int n, double* a, int* ipiv) {
     double sc = 0.0, er = 0.0;
     for (int i = 0; i < 32; ++i) { sc = std::fmax(sc, std::fabs(xr[i])); er = std::fmax(er, std::fabs(xr[i] - xn[i])); }
     max_terr = std::fmax(max_terr, er / sc);
+    // non-transposed register solve of the tangent-linear sweep against DGETRS('N')
+    for (int i = 0; i < 32; ++i) xr[i] = xn[i] = std::cos(0.5 + i * 0.61 + (double)(n_lu % 89));
+    dgetrs_oracle(false, n, a, ipiv, xr);
+    lun_solve(cur_lu, dinv, cur_swaps, xn);
+    sc = 0.0; er = 0.0;
+    for (int i = 0; i < 32; ++i) { sc = std::fmax(sc, std::fabs(xr[i])); er = std::fmax(er, std::fabs(xr[i] - xn[i])); }
+    max_terr = std::fmax(max_terr, er / sc);
   }
   return info;
 }

@@ -381,6 +381,63 @@ def main():
         pexpr.append(e)
     emit_paired(w, "AP", pexpr)
     w("}")
+    # ------------------------------------------------------------------ tangent-linear sweep (lane = TLM column)
+    w("")
+    w("// ---- operators of the tangent-linear sweep (ros_TLM_Int, TLM/ROS_TLM/ROS_TLM_f90_Integrator.F90:551-633): the same")
+    w("// per-stage operands as the backward sweep, applied NON-transposed to a register vector.")
+    w("// out = J x  (LSS_Mul_Jac / LSS_Mul_Jac1), Jv in the JAC_ROW/JAC_COL entry order")
+    w("CBM4_CELL_INL void j_vec(const double* __restrict__ Jv, const double (&x)[32], double (&out)[32]) {")
+    for r in range(N):
+        ents = [(e, rc[1]) for e, rc in enumerate(jent) if rc[0] == r]
+        w("  { double a0 = 0.0, a1 = 0.0;")
+        for t, (e, c) in enumerate(ents):
+            w(f"    a{t % 2} = fma(Jv[{e}], x[{c}], a{t % 2});")
+        w(f"    out[{r}] = a0 + a1; }}")
+    w("}")
+    w("// out += (Hess x K) x  (Hess_Vec(K, x): the matrix M of build_M with hg = 0, applied non-transposed), Mv in MV order")
+    w("CBM4_CELL_INL void m_vec_add(const double* __restrict__ Mv, const double (&x)[32], double (&out)[32]) {")
+    for k in range(N):
+        ents = [(e, kr[1]) for e, kr in enumerate(mech.mpat) if kr[0] == k]
+        if not ents:
+            continue
+        w("  { double a0 = 0.0, a1 = 0.0;")
+        for t, (e, r) in enumerate(ents):
+            w(f"    a{t % 2} = fma(Mv[{e}], x[{r}], a{t % 2});")
+        w(f"    out[{k}] += a0 + a1; }}")
+    w("}")
+    w("// out += hg * (dJ/dt) x  on the NJT time-dependent Jacobian entries (LSS_Mul_Jac2), Dj[n] = d/dt of entry JAC_TIME[n]")
+    w("CBM4_CELL_INL void dj_vec_add(const double* __restrict__ Dj, const double hg, const double (&x)[32], double (&out)[32]) {")
+    byrow = {}
+    for n, i in enumerate(mech.jtime):
+        r, c = jent[i]
+        byrow.setdefault(r, []).append((n, c))
+    for r, ents in sorted(byrow.items()):
+        e = None
+        for (n, c) in ents:
+            t = f"Dj[{n}] * x[{c}]"
+            e = t if e is None else f"fma(Dj[{n}], x[{c}], {e})"
+        w(f"  out[{r}] = fma(hg, {e}, out[{r}]);")
+    w("}")
+    w("// x <- (P L U)^-1 x with the vector in registers: DGETRS('N') on the static pattern with fma and 1/U(k,k)")
+    w("CBM4_CELL_INL void lun_solve(const double* __restrict__ lu, const double* __restrict__ dinv, const unsigned swaps, "
+      "double (&x)[32]) {")
+    for bi, (k, p_) in enumerate(SWAPS):
+        w(f"  if (swaps & {1 << bi}u) {{ const double t = x[{k}]; x[{k}] = x[{p_}]; x[{p_}] = t; }}")
+    for k in range(N - 1):
+        rows = [i for i in range(k + 1, N) if P[i][k]]
+        if not rows:
+            continue
+        w(f"  {{ const double bk = x[{k}];")
+        for i in rows:
+            w(f"    x[{i}] = fma(-lu[{idx[(i, k)]}], bk, x[{i}]);")
+        w("  }")
+    for k in range(N - 1, -1, -1):
+        rows = [i for i in range(k) if P[i][k]]
+        w(f"  {{ const double bk = x[{k}] * dinv[{k}]; x[{k}] = bk;")
+        for i in rows:
+            w(f"    x[{i}] = fma(-lu[{idx[(i, k)]}], bk, x[{i}]);")
+        w("  }")
+    w("}")
     w("}  // namespace cbm4_cell")
 
     outdir = os.path.join(HERE, "..", "fatode_b200", "csrc", "gen")
