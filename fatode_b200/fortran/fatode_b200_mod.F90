@@ -6,6 +6,7 @@
 !  Replaces, for the registered example models:
 !     MODULE ROS_adj_f90_Integrator :: INTEGRATE_ADJ   (ADJ/ROS_ADJ/ROS_ADJ_f90_Integrator.F90:34)
 !     MODULE ROS_f90_Integrator     :: INTEGRATE       (FWD/ROS/ROS_f90_Integrator.F90:32)
+!     MODULE ROS_tlm_f90_Integrator :: INTEGRATE_TLM   (TLM/ROS_TLM/ROS_TLM_f90_Integrator.F90:35)
 !  Dummy-argument names and order are the reference's, so keyword calls such as
 !     call integrate_adj(tin=tstart, tout=tend, nvar=nvar, nnzero=nnz, np=np, nadj=nadj, y=var, &
 !                        lambda=lambda, mu=mu, ..., fun=fun, jac=jac, ..., icntrl_u=icntrl)
@@ -20,7 +21,7 @@ MODULE fatode_b200_mod
   USE, INTRINSIC :: ISO_C_BINDING
   IMPLICIT NONE
   PRIVATE
-  PUBLIC :: INTEGRATE, INTEGRATE_ADJ, INTEGRATE_BATCH, INTEGRATE_ADJ_BATCH, fatode_b200_set_model
+  PUBLIC :: INTEGRATE, INTEGRATE_ADJ, INTEGRATE_TLM, INTEGRATE_BATCH, INTEGRATE_ADJ_BATCH, fatode_b200_set_model
   PUBLIC :: FATODE_MODEL_ROBERTS, FATODE_MODEL_SMALL_STRATO, FATODE_MODEL_CBM4
 
   INTEGER(C_INT), PARAMETER :: FATODE_MODEL_ROBERTS = 1, FATODE_MODEL_SMALL_STRATO = 2, FATODE_MODEL_CBM4 = 3
@@ -52,6 +53,19 @@ MODULE fatode_b200_mod
       REAL(C_DOUBLE), INTENT(IN) :: atol(*), rtol(*)
       INTEGER(C_INT) :: istatus(*), ierr(*)
       INTEGER(C_INT) :: fatode_ros_integrate_adj_batch
+    END FUNCTION
+    FUNCTION fatode_ros_integrate_tlm_batch(model, ncells, nvar, ntlm, y, y_tlm, tin, tout, atol_tlm, rtol_tlm, atol, rtol, &
+                                            icntrl_u, rcntrl_u, istatus, rstatus, ierr, model_params, mem, stream) &
+                                            BIND(C, NAME='fatode_ros_integrate_tlm_batch')
+      IMPORT :: C_INT, C_INT64_T, C_DOUBLE, C_PTR
+      INTEGER(C_INT), VALUE :: model, nvar, ntlm, mem
+      INTEGER(C_INT64_T), VALUE :: ncells
+      REAL(C_DOUBLE), VALUE :: tin, tout
+      REAL(C_DOUBLE) :: y(*), y_tlm(*), rstatus(*)
+      TYPE(C_PTR), VALUE :: atol_tlm, rtol_tlm, icntrl_u, rcntrl_u, model_params, stream
+      REAL(C_DOUBLE), INTENT(IN) :: atol(*), rtol(*)
+      INTEGER(C_INT) :: istatus(*), ierr(*)
+      INTEGER(C_INT) :: fatode_ros_integrate_tlm_batch
     END FUNCTION
   END INTERFACE
 
@@ -125,6 +139,37 @@ CONTAINS
     IF (PRESENT(ISTATUS_U)) ISTATUS_U(:) = ist(:)
     IF (PRESENT(RSTATUS_U)) RSTATUS_U(:) = rst(:)
   END SUBROUTINE INTEGRATE_ADJ
+
+  !~~~> TLM/ROS_TLM INTEGRATE_TLM, one system (TLM/ROS_TLM/ROS_TLM_f90_Integrator.F90:35-36).  The engine implements the
+  !     forward-error-control mode, ICNTRL_U(12) = 0; ROS_TLM has no IERR_U (failures are printed, :86-89).
+  SUBROUTINE INTEGRATE_TLM( N, NTLM, NNZERO, Y, Y_tlm, TIN, TOUT, ATOL_tlm, RTOL_tlm, ATOL, RTOL, FUN, JAC, HESS_VEC, &
+                            ICNTRL_U, RCNTRL_U, ISTATUS_U, RSTATUS_U )
+    INTEGER, INTENT(IN) :: N, NNZERO, NTLM
+    DOUBLE PRECISION, INTENT(INOUT) :: Y(N), Y_tlm(N,NTLM)
+    DOUBLE PRECISION, INTENT(IN) :: TIN, TOUT
+    DOUBLE PRECISION, INTENT(IN), OPTIONAL, TARGET :: RTOL_tlm(N,NTLM), ATOL_tlm(N,NTLM)
+    DOUBLE PRECISION, INTENT(IN) :: ATOL(N), RTOL(N)
+    EXTERNAL :: FUN, JAC, HESS_VEC
+    INTEGER, INTENT(IN), OPTIONAL, TARGET :: ICNTRL_U(20)
+    DOUBLE PRECISION, INTENT(IN), OPTIONAL, TARGET :: RCNTRL_U(20)
+    INTEGER, INTENT(OUT), OPTIONAL :: ISTATUS_U(20)
+    DOUBLE PRECISION, INTENT(OUT), OPTIONAL :: RSTATUS_U(20)
+    INTEGER(C_INT) :: ist(20), ierr(1), rc
+    REAL(C_DOUBLE) :: rst(20)
+    TYPE(C_PTR) :: pic, prc, pat, prt
+    pic = C_NULL_PTR; prc = C_NULL_PTR; pat = C_NULL_PTR; prt = C_NULL_PTR
+    IF (PRESENT(ICNTRL_U)) pic = C_LOC(ICNTRL_U)
+    IF (PRESENT(RCNTRL_U)) prc = C_LOC(RCNTRL_U)
+    IF (PRESENT(ATOL_tlm)) pat = C_LOC(ATOL_tlm)
+    IF (PRESENT(RTOL_tlm)) prt = C_LOC(RTOL_tlm)
+    ist = 0; rst = 0.0d0; ierr = 0
+    rc = fatode_ros_integrate_tlm_batch(current_model, 1_C_INT64_T, INT(N, C_INT), INT(NTLM, C_INT), Y, Y_tlm, TIN, TOUT, &
+                                        pat, prt, ATOL, RTOL, pic, prc, ist, rst, ierr, C_NULL_PTR, FATODE_MEM_HOST, C_NULL_PTR)
+    IF (rc /= 0) ierr(1) = rc
+    IF (ierr(1) < 0) PRINT *, 'Rosenbrock: Unsucessful step at T=', TIN, ' (IERR=', ierr(1), ')'   ! as :86-89
+    IF (PRESENT(ISTATUS_U)) ISTATUS_U(:) = ist(:)
+    IF (PRESENT(RSTATUS_U)) RSTATUS_U(:) = rst(:)
+  END SUBROUTINE INTEGRATE_TLM
 
   !~~~> batched forms: NCELLS independent systems in one call
   SUBROUTINE INTEGRATE_BATCH( NCELLS, TIN, TOUT, N, VAR, RTOL, ATOL, ICNTRL_U, RCNTRL_U, ISTATUS_U, RSTATUS_U, IERR_U )
