@@ -29,6 +29,7 @@
 #include "ros_cell_fwd.cuh"
 #include "ros_cell_adj.cuh"
 #include "model_small_cell.cuh"
+#include "sdirk_cell_fwd.cuh"
 
 using namespace fatode;
 
@@ -1222,6 +1223,89 @@ extern "C" int fatode_ros_integrate_tlm_batch(int model, int64_t ncells, int nva
   (void)atol_tlm; (void)rtol_tlm;   // used by the reference only when ICNTRL(12) != 0 (TLM truncation-error control)
   return ros_batch_impl(FAM_TLM, model, ncells, nvar, 0, ntlm, y, y_tlm, nullptr, tin, tout, atol, rtol, icntrl_u, rcntrl_u,
                         istatus, rstatus, ierr, nullptr, model_params, mem, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FWD/SDIRK INTEGRATE: one system per thread for all three models
+template <class Cell>
+static int sdirk_device(const SdirkParams& sp, const typename Cell::Const& mc, int64_t ncells, double* d_y, const double* d_atol,
+                        const double* d_rtol, int* d_istatus, double* d_rstatus, int* d_ierr, cudaStream_t st) {
+  std::memset(&g_stats, 0, sizeof g_stats);
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  constexpr int LANES = 32;
+  const size_t smem = SdirkSmem<Cell, LANES>::BYTES;
+  CUDA_TRY(cudaFuncSetAttribute(k_sdirk_fwd_cell<Cell, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(g_ctr.ensure(16 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemsetAsync(g_ctr.p, 0, 16 * sizeof(unsigned long long), st));
+  int per_sm = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sdirk_fwd_cell<Cell, LANES>, 32, smem));
+  const unsigned blocks = (unsigned)std::min<int64_t>((ncells + LANES - 1) / LANES, (int64_t)sms * std::max(per_sm, 1));
+  PhaseTimer tm(st);
+  tm.start();
+  k_sdirk_fwd_cell<Cell, LANES><<<blocks, 32, smem, st>>>(sp, mc, ncells, d_y, d_y, d_atol, d_rtol, d_istatus, d_rstatus, d_ierr,
+                                                          g_ctr.as<unsigned long long>());
+  CUDA_TRY(cudaGetLastError());
+  g_stats.ms_forward += tm.stop();
+  g_stats.launches++;
+  g_stats.launches_forward++;
+  g_stats.waves++;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int fatode_sdirk_integrate_batch(int model, int64_t ncells, int nvar, double* y, double tin, double tout,
+                                            const double* atol, const double* rtol, const int* icntrl_u, const double* rcntrl_u,
+                                            int* istatus, double* rstatus, int* ierr, const double* model_params, int mem,
+                                            void* stream) {
+  g_err.clear();
+  if (ncells < 0 || !y || !atol || !rtol || !istatus || !rstatus || !ierr) return fail(FATODE_EINVAL, "NULL required argument");
+  if (int e = check_model_dims(model, nvar, 0)) return e;
+  if (int e = check_device()) return e;
+  if (ncells == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SdirkParams sp;
+  const int perr = sdirk_parse_options(nvar, icntrl_u, rcntrl_u, tin, tout, atol, rtol, sp);
+  if (perr < 0) return broadcast_ierr(ncells, perr, istatus, rstatus, ierr, mem, st);
+  Cbm4Const mc;
+  cbm4_constants(model_params, mc);
+  SmallConst sc;
+  sc.fix[0] = model_params ? model_params[0] : (double)8.120E+16f * (double)1.0f;
+  sc.fix[1] = model_params ? model_params[1] : (double)1.697E+16f * (double)1.0f;
+  DevBuf b_atol, b_rtol, b_y, b_ist, b_rst, b_ierr;
+  CUDA_TRY(b_atol.alloc(sizeof(double) * nvar));
+  CUDA_TRY(b_rtol.alloc(sizeof(double) * nvar));
+  CUDA_TRY(cudaMemcpyAsync(b_atol.p, atol, sizeof(double) * nvar, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(b_rtol.p, rtol, sizeof(double) * nvar, cudaMemcpyHostToDevice, st));
+  double *d_y = y, *d_rst = rstatus;
+  int *d_ist = istatus, *d_ierr = ierr;
+  const size_t ny = sizeof(double) * nvar * ncells;
+  if (mem == FATODE_MEM_HOST) {
+    CUDA_TRY(b_y.alloc(ny));
+    CUDA_TRY(b_ist.alloc(sizeof(int) * 20 * ncells));
+    CUDA_TRY(b_rst.alloc(sizeof(double) * 20 * ncells));
+    CUDA_TRY(b_ierr.alloc(sizeof(int) * ncells));
+    CUDA_TRY(cudaMemcpyAsync(b_y.p, y, ny, cudaMemcpyHostToDevice, st));
+    d_y = b_y.as<double>(); d_ist = b_ist.as<int>(); d_rst = b_rst.as<double>(); d_ierr = b_ierr.as<int>();
+  }
+  if (model == FATODE_MODEL_CBM4) CUDA_TRY(cudaMemcpyToSymbolAsync(c_cbm4_rc, mc.rc_base, sizeof(double) * 81, 0, cudaMemcpyHostToDevice, st));
+  int rc;
+  if (model == FATODE_MODEL_CBM4)
+    rc = sdirk_device<Cbm4Cell>(sp, mc, ncells, d_y, b_atol.as<double>(), b_rtol.as<double>(), d_ist, d_rst, d_ierr, st);
+  else if (model == FATODE_MODEL_SMALL_STRATO)
+    rc = sdirk_device<SmallStratoCell>(sp, sc, ncells, d_y, b_atol.as<double>(), b_rtol.as<double>(), d_ist, d_rst, d_ierr, st);
+  else
+    rc = sdirk_device<RobertsCell>(sp, sc, ncells, d_y, b_atol.as<double>(), b_rtol.as<double>(), d_ist, d_rst, d_ierr, st);
+  if (rc != 0) return rc;
+  if (mem == FATODE_MEM_HOST) {
+    CUDA_TRY(cudaMemcpyAsync(y, d_y, ny, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(istatus, d_ist, sizeof(int) * 20 * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(rstatus, d_rst, sizeof(double) * 20 * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ierr, d_ierr, sizeof(int) * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -107,6 +107,18 @@ int fatode_ros_integrate_tlm_batch(int model, int64_t ncells, int nvar, int ntlm
                                    const double* rcntrl_u, int* istatus, double* rstatus, int* ierr,
                                    const double* model_params, int mem, void* stream);
 
+/* INTEGRATE of FWD/SDIRK (FWD/SDIRK/SDIRK_f90_Integrator.F90:25):
+ *   INTEGRATE(TIN,TOUT,N,NNZERO,VAR,RTOL,ATOL,FUN,JAC,ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U,Ierr_U)
+ * Singly diagonally implicit Runge-Kutta methods (ICNTRL(3) = 1..5: Sdirk2a, 2b, 3a, 4a (default), 4b) with simplified
+ * Newton iterations; ICNTRL_U/RCNTRL_U override the defaults only when > 0 (:57-64); RCNTRL(8..11) = ThetaMin,
+ * NewtonTol, Qmin, Qmax, ICNTRL(5) = NewtonMaxit, ICNTRL(6) = zero starting values for Newton.  Models: cbm4,
+ * small_strato, roberts.  Per-cell IERR: 1, or the reference's -1..-8; for cbm4 additionally -20 when a system asks for
+ * a pivot sequence outside the static LU pattern (no general SDIRK kernel yet; not observed for the shipped inputs). */
+int fatode_sdirk_integrate_batch(int model, int64_t ncells, int nvar, double* y, double tin, double tout,
+                                 const double* atol, const double* rtol, const int* icntrl_u,
+                                 const double* rcntrl_u, int* istatus, double* rstatus, int* ierr,
+                                 const double* model_params, int mem, void* stream);
+
 /* Engine knobs (process-wide): trajectory-tape budget in bytes (0 = 60% of free device memory) and
  * the number of cells per wave (0 = automatic). */
 int fatode_set_tape_budget(uint64_t bytes);

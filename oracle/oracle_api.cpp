@@ -7,6 +7,7 @@
 #include <cstring>
 #include "models.hpp"
 #include "ros.hpp"
+#include "sdirk.hpp"
 
 using namespace oracle;
 
@@ -100,6 +101,22 @@ int oracle_ros_tlm_batch(int model, long ncells, int ntlm, double* y, double* y_
     Cbm4 mdl;
     ierr[c] = ros_integrate_tlm<Cbm4>(mdl, ntlm, y + c * N, y_tlm + c * (long)N * ntlm, tin, tout, atol_tlm, rtol_tlm, atol, rtol,
                                       icntrl, rcntrl, istatus + c * 20, rstatus + c * 20);
+  }
+  return 0;
+}
+
+// FWD/SDIRK INTEGRATE looped over cells
+int oracle_sdirk_fwd_batch(int model, long ncells, double* y, double tin, double tout, const double* atol, const double* rtol,
+                           const int* icntrl, const double* rcntrl, int* istatus, double* rstatus, int* ierr, int nthreads) {
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+  for (long c = 0; c < ncells; ++c) {
+    switch (model) {
+      case MODEL_ROBERTS: { Roberts m; ierr[c] = sdirk_integrate<Roberts>(m, tin, tout, y + c * Roberts::N, rtol, atol, icntrl, rcntrl, istatus + c * 20, rstatus + c * 20); break; }
+      case MODEL_SMALL_STRATO: { SmallStrato m; ierr[c] = sdirk_integrate<SmallStrato>(m, tin, tout, y + c * SmallStrato::N, rtol, atol, icntrl, rcntrl, istatus + c * 20, rstatus + c * 20); break; }
+      case MODEL_CBM4: { Cbm4 m; ierr[c] = sdirk_integrate<Cbm4>(m, tin, tout, y + c * Cbm4::N, rtol, atol, icntrl, rcntrl, istatus + c * 20, rstatus + c * 20); break; }
+      default: ierr[c] = -100;
+    }
   }
   return 0;
 }

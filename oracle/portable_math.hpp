@@ -97,4 +97,29 @@ FPM_HD double root_elo(double x, double elo) {
   return pow(x, 1.0 / elo);   // not reached by the shipped tableaux
 }
 
+
+// x**(-1/k) for a small positive integer-valued k: the SDIRK step controller's Err**(-1/rkELO) (rkELO = 2, 4) and the
+// Newton-failure factor Qnewton**(-1/k), k = 1 + NewtonMaxit - NewtonIter, Qnewton in [1,10]
+// (FWD/SDIRK/SDIRK_f90_Integrator.F90:548, 587).  Fixed-order IEEE operations only (host == device bits): roots by
+// sqrt / the cbrt kernel where k allows, otherwise Newton's iteration on y**(-k) = x from the Bernoulli seed
+// 1/(1+(x-1)/k) (monotone from below until the correction reaches round-off level; a few ulp).
+FPM_HD double pow_neg_inv(double x, double k) {
+  if (k == 1.0) return 1.0 / x;
+  if (k == 2.0) return 1.0 / sqrt(x);
+  if (k == 4.0) return 1.0 / sqrt(sqrt(x));
+  if (k == 8.0) return 1.0 / sqrt(sqrt(sqrt(x)));
+  if (k == 3.0) return 1.0 / root_elo(x, 3.0);
+  if (k == 6.0) return 1.0 / sqrt(root_elo(x, 3.0));
+  const int n = (int)k;
+  double y = 1.0 / (1.0 + (x - 1.0) / k);
+  for (int it = 0; it < 400; ++it) {
+    double p = y, q = 1.0;          // y**n by square-and-multiply
+    for (unsigned m = (unsigned)n; m; m >>= 1) { if (m & 1u) q = q * p; p = p * p; }
+    const double d = (1.0 - x * q) / k;   // relative Newton correction: positive and decreasing until round-off level
+    if (!(d > 4.0e-16)) break;
+    y = y * (1.0 + d);
+  }
+  return y;
+}
+
 }  // namespace oracle_pm

@@ -6,6 +6,7 @@ copied here verbatim (they are run outputs committed upstream, not source code):
   EXAMPLES/cbm4/CBM4_ROS_ADJ/cbm4_output_sens.txt      Lambda(32,32) then Mu(29,32)
   EXAMPLES/small_strato/small_ros_adj/rkadj_ADJ_results.m   Lambda(5,5) (RosenbrockADJ2, Rodas3)
   EXAMPLES/small_strato/small_ros/small_strato_dr.F90:23-24  ANS(5) (REAL(4) literals)
+  EXAMPLES/cbm4/CBM4_SDIRK/cbm4_sdirk_sol.txt          Y(Tend), 32 x E24.16 (FWD/SDIRK, Sdirk4a, rtol 1e-6, atol 1e-8)
 Usage: python tests/golden/make_golden.py [/root/reference]
 """
 import json
@@ -36,6 +37,9 @@ def main():
     assert len(ans) == 5
     json.dump({"source": "EXAMPLES/small_strato/small_ros_adj/rkadj_ADJ_results.m; small_ros/small_strato_dr.F90:23-24",
                "lambda": lam, "ans": ans}, open(os.path.join(HERE, "small_strato.json"), "w"))
+    ys = [float(l) for l in open(os.path.join(REF, "EXAMPLES/cbm4/CBM4_SDIRK/cbm4_sdirk_sol.txt"))]
+    assert len(ys) == 32
+    json.dump({"source": "EXAMPLES/cbm4/CBM4_SDIRK/cbm4_sdirk_sol.txt", "y": ys}, open(os.path.join(HERE, "cbm4_sdirk.json"), "w"))
     print("wrote fixtures")
 
 

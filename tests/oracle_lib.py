@@ -24,6 +24,8 @@ def lib():
         L.oracle_ros_adj_batch.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_int, _dp, _dp, _dp,
                                            ctypes.c_double, ctypes.c_double, _dp, _dp, _ip, _dp, _ip, _dp, _ip,
                                            ctypes.c_int]
+        L.oracle_sdirk_fwd_batch.argtypes = [ctypes.c_int, ctypes.c_long, _dp, ctypes.c_double, ctypes.c_double, _dp, _dp,
+                                             _ip, _dp, _ip, _dp, _ip, ctypes.c_int]
         L.oracle_ros_tlm_batch.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_int, _dp, _dp, ctypes.c_double, ctypes.c_double,
                                            _dp, _dp, _dp, _dp, _ip, _dp, _ip, _dp, _ip, ctypes.c_int]
         _lib = L
@@ -109,3 +111,18 @@ def ros_tlm(model, y, y_tlm, tin, tout, atol, rtol, icntrl=None, rcntrl=None, at
                                    _i(ist), _d(rst), _i(ierr), nthreads)
     assert r == 0
     return dict(y=y, y_tlm=yt, istatus=ist, rstatus=rst, ierr=ierr)
+
+
+def sdirk_fwd(model, y, tin, tout, atol, rtol, icntrl=None, rcntrl=None, nthreads=0):
+    """FWD/SDIRK INTEGRATE looped over cells."""
+    y = np.atleast_2d(np.array(y, dtype=np.float64, order="C"))
+    nc = y.shape[0]
+    ic, rc = _ctrl(icntrl, rcntrl)
+    atol = np.ascontiguousarray(atol, dtype=np.float64)
+    rtol = np.ascontiguousarray(rtol, dtype=np.float64)
+    ist = np.zeros((nc, 20), dtype=np.int32)
+    rst = np.zeros((nc, 20))
+    ierr = np.zeros(nc, dtype=np.int32)
+    lib().oracle_sdirk_fwd_batch(MODEL[model], nc, _d(y), tin, tout, _d(atol), _d(rtol), _i(ic), _d(rc), _i(ist), _d(rst),
+                                 _i(ierr), nthreads)
+    return dict(y=y, istatus=ist, rstatus=rst, ierr=ierr)
