@@ -201,6 +201,71 @@ def workload_config(cells, ngpus, note=None):
     return c
 
 
+def run_side_workload(args):
+    """Side measurements (1 GPU, host buffers through the C ABI): BASELINE config 1 (small_strato FWD/ROS, 2^20 cells) and the
+    ROS_TLM / FWD/SDIRK entry points on CBM-IV, each next to the CPU oracle on a bounded sample."""
+    import torch  # noqa: F401  (initialises CUDA the same way the main arm does)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fatode_b200 as F
+    import oracle_lib as O
+    from fatode_b200.inputs import perturbed_states
+    w = args.workload
+    if w == "small_strato_fwd":
+        nc = args.cells if args.cells != 131072 else (1 << 20)
+        rtol, atol = np.full(5, 1.0e-1), np.full(5, 1.0)
+        for _ in range(5):                      # tolerances of the driver's fifth sweep (small_strato_dr.F90:27-38)
+            rtol, atol = F01 * rtol, F01 * atol
+        t0, t1 = T0, T0 + 30 * 24 * 3600.0
+        y0 = perturbed_states(F.initial_state("small_strato"), nc)
+        run = lambda y: F.integrate("small_strato", t0, t1, y, rtol, atol)
+        cpu = lambda y: O.ros_fwd("small_strato", y, t0, t1, atol, rtol)
+        desc = "EXAMPLES/small_strato FWD/ROS (Ros4, REAL(4) tableau), N=5, 12h..30d, rtol 1e-6 atol 1e-5 (REAL(4) 0.1 products)"
+        ncpu = 256
+    elif w == "cbm4_ros_tlm":
+        nc = args.cells if args.cells != 131072 else 32768
+        rtol, atol = tolerances()
+        ic = icntrl_rodas4()
+        y0 = perturbed_states(F.initial_state("cbm4"), nc)
+        eye = np.eye(32)
+        run = lambda y: F.integrate_tlm("cbm4", T0, T1, y, np.broadcast_to(eye, (y.shape[0], 32, 32)).copy(), rtol, atol, icntrl_u=ic)
+        cpu = lambda y: O.ros_tlm("cbm4", y, np.broadcast_to(eye, (y.shape[0], 32, 32)).copy(), T0, T1, atol, rtol, ic)
+        desc = "EXAMPLES/cbm4 TLM/ROS_TLM: Rodas4, NTLM=32, Y_tlm(t0)=I, ICNTRL(12)=0, 12h..84h, driver tolerances of ROS_ADJ"
+        ncpu = 32
+    else:
+        nc = args.cells if args.cells != 131072 else 18944
+        rtol, atol = np.full(N, F01 * 1.0e-5), np.full(N, F01 * 1.0e-7)
+        y0 = perturbed_states(F.initial_state("cbm4"), nc)
+        run = lambda y: F.integrate_sdirk("cbm4", T0, T1, y, rtol, atol)
+        cpu = lambda y: O.sdirk_fwd("cbm4", y, T0, T1, atol, rtol)
+        desc = "EXAMPLES/cbm4 FWD/SDIRK: Sdirk4a, 12h..84h, rtol 0.1f*1e-5, atol 0.1f*1e-7 (cbm4_sdirk_dr.F90)"
+        ncpu = 128
+    for _ in range(max(args.warmup, 1)):
+        run(y0[: max(nc // 8, 64)])
+    times, dev_ms = [], []
+    for _ in range(args.steps):
+        t = time.perf_counter()
+        r = run(y0)
+        times.append(time.perf_counter() - t)
+        st = F.last_stats()
+        dev_ms.append(st.ms_forward + st.ms_forward_tape + st.ms_adjoint)
+        assert (r.ierr == 1).all()
+    t = time.perf_counter()
+    ref = cpu(y0[:ncpu])
+    tc = time.perf_counter() - t
+    same = bool(np.array_equal(ref["y"], r.y[:ncpu]) and np.array_equal(ref["istatus"], r.istatus[:ncpu]))
+    cores = O.lib().oracle_max_threads()
+    line = {"metric": "cell-integrations/sec, " + w, "value": nc / (np.mean(dev_ms) * 1e-3), "unit": "cells/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(dev_ms)), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "cells_per_gpu_per_step": int(nc), "note": "side measurement, not the driver's metric; "
+                       "value = CUDA-event kernel time, e2e = wall clock of the C-ABI call with pageable host buffers"},
+            "e2e": {"value": nc / float(np.mean(times)), "unit": "cells/s"},
+            "cpu_baseline": {"value": ncpu / tc, "unit": "cells/s", "cores": cores, "kind": "port",
+                             "sample": f"{ncpu} cells, {tc:.1f} s, OpenMP over cells"},
+            "bitwise_equal_to_oracle_on_sample": same}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -210,7 +275,12 @@ def main():
     ap.add_argument("--impl", default="fatode_b200", choices=["fatode_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="cbm4_ros_adj", choices=["cbm4_ros_adj", "small_strato_fwd", "cbm4_ros_tlm", "cbm4_sdirk"],
+                    help="cbm4_ros_adj = the headline metric (default); the others are side measurements of the other "
+                         "BASELINE configs / entry points (single GPU, one JSON line each, not the driver's metric)")
     args = ap.parse_args()
+    if args.workload != "cbm4_ros_adj":
+        return run_side_workload(args)
     if args.impl == "reference":
         return run_reference_arm(args)
 
