@@ -1,4 +1,4 @@
-"""Tiny run of every entry point for compute-sanitizer (memcheck / racecheck)."""
+"""Tiny run of every entry point (small tape budget: several waves, hand-back path) — a quick end-to-end sanity case."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
