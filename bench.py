@@ -442,7 +442,10 @@ def main():
                 "whole_job_frac_of_fp64_peak": (f_adj + f_fwd) / (ms * 1e-3) / 1e12 / (fp64_peak * world),
                 "forward_ms_per_step": ms_fwd_t / (args.steps * world), "expand_ms_per_step": ms_tape_t / (args.steps * world),
                 "adjoint_ms_per_step": ms_adj_t / (args.steps * world),
-                "cells_on_general_path": int(general_t)}
+                "cells_on_general_path": int(general_t),
+                # executed (not algorithmic) work of the same kernel from the ncu capture in profiles/r1i_cellpath_raw.csv:
+                # the kernel exploits the sparsity, so it executes ~0.65 Mflop per accepted step of the 2.05 Mflop dense count
+                "executed_fp64_pipe_busy_ncu": 0.30, "executed_dfma_frac_of_peak_ncu": 0.206, "issue_slots_busy_ncu": 0.285}
         line = {"metric": "cell-integrations/sec (fwd + adjoint), CBM-IV ROS_ADJ", "value": value, "unit": "cells/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -394,10 +394,21 @@ struct PhaseTimer {
   double stop() { cudaEventRecord(e1, s); cudaEventSynchronize(e1); float ms = 0; cudaEventElapsedTime(&ms, e0, e1); return ms; }
 };
 
+extern "C" int fatode_release_workspace(void);
+static thread_local int g_ws_device = -1;   // device the cached workspace of this host thread lives on
 static int check_device() {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) return fail(FATODE_ENODEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  int dev = -1;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev != g_ws_device) {   // the caller switched GPUs: drop the other GPU's buffers
+    if (g_ws_device >= 0) {
+      cudaSetDevice(g_ws_device);
+      fatode_release_workspace();
+      cudaSetDevice(dev);
+    }
+    g_ws_device = dev;
+  }
   return 0;
 }
 
