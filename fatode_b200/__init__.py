@@ -72,6 +72,7 @@ def lib():
                                                      vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
         L.fatode_sdirk_integrate_batch.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int, vp, ctypes.c_double,
                                                    ctypes.c_double, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        L.fatode_rk_integrate_batch.argtypes = L.fatode_sdirk_integrate_batch.argtypes
         L.fatode_ros_integrate_tlm_batch.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, vp, vp,
                                                      ctypes.c_double, ctypes.c_double, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                                      ctypes.c_int, vp]
@@ -164,6 +165,23 @@ def integrate_sdirk(model, tin, tout, var, rtol, atol, icntrl_u=None, rcntrl_u=N
     mp = None if model_params is None else np.ascontiguousarray(model_params, dtype=np.float64)
     _check(lib().fatode_sdirk_integrate_batch(mid, nc, n, _ptr(y), float(tin), float(tout), _ptr(atol), _ptr(rtol),
                                               _ptr(ic), _ptr(rc), _ptr(ist), _ptr(rst), _ptr(ierr), _ptr(mp), MEM_HOST, None))
+    return Result(y, ist, rst, ierr)
+
+
+def integrate_rk(model, tin, tout, var, rtol, atol, icntrl_u=None, rcntrl_u=None, model_params=None) -> Result:
+    """Batched FWD/RK INTEGRATE (FWD/RK/RK_f90_Integrator.F90:32). var: [ncells, N] or [N]."""
+    mid = model_id(model)
+    y = np.atleast_2d(np.array(var, dtype=np.float64, order="C"))
+    nc, n = y.shape
+    rtol = np.ascontiguousarray(rtol, dtype=np.float64)
+    atol = np.ascontiguousarray(atol, dtype=np.float64)
+    ic, rc = _ctrl(icntrl_u, rcntrl_u)
+    ist = np.zeros((nc, 20), dtype=np.int32)
+    rst = np.zeros((nc, 20))
+    ierr = np.zeros(nc, dtype=np.int32)
+    mp = None if model_params is None else np.ascontiguousarray(model_params, dtype=np.float64)
+    _check(lib().fatode_rk_integrate_batch(mid, nc, n, _ptr(y), float(tin), float(tout), _ptr(atol), _ptr(rtol),
+                                           _ptr(ic), _ptr(rc), _ptr(ist), _ptr(rst), _ptr(ierr), _ptr(mp), MEM_HOST, None))
     return Result(y, ist, rst, ierr)
 
 

@@ -30,6 +30,7 @@
 #include "ros_cell_adj.cuh"
 #include "model_small_cell.cuh"
 #include "sdirk_cell_fwd.cuh"
+#include "rk_cell_fwd.cuh"
 
 using namespace fatode;
 
@@ -1237,26 +1238,29 @@ extern "C" int fatode_ros_integrate_tlm_batch(int model, int64_t ncells, int nva
 }
 
 // ------------------------------------------------------------------------------------------------
-// FWD/SDIRK INTEGRATE: one system per thread for all three models
-template <class Cell>
-static int sdirk_device(const SdirkParams& sp, const typename Cell::Const& mc, int64_t ncells, double* d_y, const double* d_atol,
-                        const double* d_rtol, int* d_istatus, double* d_rstatus, int* d_ierr, cudaStream_t st) {
+// FWD/SDIRK and FWD/RK INTEGRATE: one system per thread for all three models
+template <class Params, class Const>
+using CellFwdKernel = void (*)(Params, Const, long, const double*, double*, const double*, const double*, int*, double*, int*,
+                               unsigned long long*);
+
+template <class Params, class Const>
+static int cellfwd_launch(CellFwdKernel<Params, Const> kern, size_t smem, int lanes, const Params& prm, const Const& mc,
+                          int64_t ncells, double* d_y, const double* d_atol, const double* d_rtol, int* d_istatus,
+                          double* d_rstatus, int* d_ierr, cudaStream_t st) {
   std::memset(&g_stats, 0, sizeof g_stats);
   int dev = 0, sms = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  constexpr int LANES = 32;
-  const size_t smem = SdirkSmem<Cell, LANES>::BYTES;
-  CUDA_TRY(cudaFuncSetAttribute(k_sdirk_fwd_cell<Cell, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUDA_TRY(g_ctr.ensure(16 * sizeof(unsigned long long)));
   CUDA_TRY(cudaMemsetAsync(g_ctr.p, 0, 16 * sizeof(unsigned long long), st));
   int per_sm = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sdirk_fwd_cell<Cell, LANES>, 32, smem));
-  const unsigned blocks = (unsigned)std::min<int64_t>((ncells + LANES - 1) / LANES, (int64_t)sms * std::max(per_sm, 1));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
+  const unsigned blocks = (unsigned)std::min<int64_t>((ncells + lanes - 1) / lanes, (int64_t)sms * std::max(per_sm, 1));
   PhaseTimer tm(st);
   tm.start();
-  k_sdirk_fwd_cell<Cell, LANES><<<blocks, 32, smem, st>>>(sp, mc, ncells, d_y, d_y, d_atol, d_rtol, d_istatus, d_rstatus, d_ierr,
-                                                          g_ctr.as<unsigned long long>());
+  kern<<<blocks, 32, smem, st>>>(prm, mc, (long)ncells, d_y, d_y, d_atol, d_rtol, d_istatus, d_rstatus, d_ierr,
+                                 g_ctr.as<unsigned long long>());
   CUDA_TRY(cudaGetLastError());
   g_stats.ms_forward += tm.stop();
   g_stats.launches++;
@@ -1266,10 +1270,12 @@ static int sdirk_device(const SdirkParams& sp, const typename Cell::Const& mc, i
   return 0;
 }
 
-extern "C" int fatode_sdirk_integrate_batch(int model, int64_t ncells, int nvar, double* y, double tin, double tout,
-                                            const double* atol, const double* rtol, const int* icntrl_u, const double* rcntrl_u,
-                                            int* istatus, double* rstatus, int* ierr, const double* model_params, int mem,
-                                            void* stream) {
+enum { IMPL_SDIRK = 0, IMPL_RK = 1 };
+constexpr int RK_LANES_CBM4 = 16;   // 13.4 KB of shared memory per system (three factor planes + 17 vectors)
+
+static int implicit_integrate_batch(int family, int model, int64_t ncells, int nvar, double* y, double tin, double tout,
+                                    const double* atol, const double* rtol, const int* icntrl_u, const double* rcntrl_u,
+                                    int* istatus, double* rstatus, int* ierr, const double* model_params, int mem, void* stream) {
   g_err.clear();
   if (ncells < 0 || !y || !atol || !rtol || !istatus || !rstatus || !ierr) return fail(FATODE_EINVAL, "NULL required argument");
   if (int e = check_model_dims(model, nvar, 0)) return e;
@@ -1277,7 +1283,9 @@ extern "C" int fatode_sdirk_integrate_batch(int model, int64_t ncells, int nvar,
   if (ncells == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   SdirkParams sp;
-  const int perr = sdirk_parse_options(nvar, icntrl_u, rcntrl_u, tin, tout, atol, rtol, sp);
+  RkParams rp;
+  const int perr = (family == IMPL_SDIRK) ? sdirk_parse_options(nvar, icntrl_u, rcntrl_u, tin, tout, atol, rtol, sp)
+                                          : rk_parse_options(nvar, icntrl_u, rcntrl_u, tin, tout, atol, rtol, rp);
   if (perr < 0) return broadcast_ierr(ncells, perr, istatus, rstatus, ierr, mem, st);
   Cbm4Const mc;
   cbm4_constants(model_params, mc);
@@ -1301,13 +1309,23 @@ extern "C" int fatode_sdirk_integrate_batch(int model, int64_t ncells, int nvar,
     d_y = b_y.as<double>(); d_ist = b_ist.as<int>(); d_rst = b_rst.as<double>(); d_ierr = b_ierr.as<int>();
   }
   if (model == FATODE_MODEL_CBM4) CUDA_TRY(cudaMemcpyToSymbolAsync(c_cbm4_rc, mc.rc_base, sizeof(double) * 81, 0, cudaMemcpyHostToDevice, st));
+  const double *da = b_atol.as<double>(), *dr = b_rtol.as<double>();
   int rc;
-  if (model == FATODE_MODEL_CBM4)
-    rc = sdirk_device<Cbm4Cell>(sp, mc, ncells, d_y, b_atol.as<double>(), b_rtol.as<double>(), d_ist, d_rst, d_ierr, st);
-  else if (model == FATODE_MODEL_SMALL_STRATO)
-    rc = sdirk_device<SmallStratoCell>(sp, sc, ncells, d_y, b_atol.as<double>(), b_rtol.as<double>(), d_ist, d_rst, d_ierr, st);
-  else
-    rc = sdirk_device<RobertsCell>(sp, sc, ncells, d_y, b_atol.as<double>(), b_rtol.as<double>(), d_ist, d_rst, d_ierr, st);
+  if (family == IMPL_SDIRK) {
+    if (model == FATODE_MODEL_CBM4)
+      rc = cellfwd_launch<SdirkParams, Cbm4Const>(k_sdirk_fwd_cell<Cbm4Cell, 32>, SdirkSmem<Cbm4Cell, 32>::BYTES, 32, sp, mc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st);
+    else if (model == FATODE_MODEL_SMALL_STRATO)
+      rc = cellfwd_launch<SdirkParams, SmallConst>(k_sdirk_fwd_cell<SmallStratoCell, 32>, SdirkSmem<SmallStratoCell, 32>::BYTES, 32, sp, sc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st);
+    else
+      rc = cellfwd_launch<SdirkParams, SmallConst>(k_sdirk_fwd_cell<RobertsCell, 32>, SdirkSmem<RobertsCell, 32>::BYTES, 32, sp, sc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st);
+  } else {
+    if (model == FATODE_MODEL_CBM4)
+      rc = cellfwd_launch<RkParams, Cbm4Const>(k_rk_fwd_cell<Cbm4Cell, RK_LANES_CBM4>, RkSmem<Cbm4Cell, RK_LANES_CBM4>::BYTES, RK_LANES_CBM4, rp, mc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st);
+    else if (model == FATODE_MODEL_SMALL_STRATO)
+      rc = cellfwd_launch<RkParams, SmallConst>(k_rk_fwd_cell<SmallStratoCell, 32>, RkSmem<SmallStratoCell, 32>::BYTES, 32, rp, sc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st);
+    else
+      rc = cellfwd_launch<RkParams, SmallConst>(k_rk_fwd_cell<RobertsCell, 32>, RkSmem<RobertsCell, 32>::BYTES, 32, rp, sc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st);
+  }
   if (rc != 0) return rc;
   if (mem == FATODE_MEM_HOST) {
     CUDA_TRY(cudaMemcpyAsync(y, d_y, ny, cudaMemcpyDeviceToHost, st));
@@ -1317,6 +1335,22 @@ extern "C" int fatode_sdirk_integrate_batch(int model, int64_t ncells, int nvar,
     CUDA_TRY(cudaStreamSynchronize(st));
   }
   return 0;
+}
+
+extern "C" int fatode_sdirk_integrate_batch(int model, int64_t ncells, int nvar, double* y, double tin, double tout,
+                                            const double* atol, const double* rtol, const int* icntrl_u, const double* rcntrl_u,
+                                            int* istatus, double* rstatus, int* ierr, const double* model_params, int mem,
+                                            void* stream) {
+  return implicit_integrate_batch(IMPL_SDIRK, model, ncells, nvar, y, tin, tout, atol, rtol, icntrl_u, rcntrl_u, istatus, rstatus,
+                                  ierr, model_params, mem, stream);
+}
+
+extern "C" int fatode_rk_integrate_batch(int model, int64_t ncells, int nvar, double* y, double tin, double tout,
+                                         const double* atol, const double* rtol, const int* icntrl_u, const double* rcntrl_u,
+                                         int* istatus, double* rstatus, int* ierr, const double* model_params, int mem,
+                                         void* stream) {
+  return implicit_integrate_batch(IMPL_RK, model, ncells, nvar, y, tin, tout, atol, rtol, icntrl_u, rcntrl_u, istatus, rstatus,
+                                  ierr, model_params, mem, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

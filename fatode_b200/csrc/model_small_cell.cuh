@@ -102,6 +102,137 @@ __device__ __forceinline__ void dense_lu_solve(const double* a, unsigned swaps, 
   }
 }
 
+// ---- COMPLEX*16 counterparts (FWD/RK/LS_Solver.F90:22-52): ZGETF2 / ZGETRS('N') on two planes ar/ai, netlib loop order,
+// four-multiplication products and range-reduced (Smith) quotients as gfortran emits them (oracle/ref_lapack.hpp cdiv)
+__device__ __forceinline__ void zdiv_dev(double a, double b, double c, double e, double& qr, double& qi) {
+  if (fabs(c) < fabs(e)) {
+    const double ratio = __ddiv_rn(c, e), div = __dadd_rn(__dmul_rn(c, ratio), e);
+    qr = __ddiv_rn(__dadd_rn(__dmul_rn(a, ratio), b), div);
+    qi = __ddiv_rn(__dsub_rn(__dmul_rn(b, ratio), a), div);
+  } else {
+    const double ratio = __ddiv_rn(e, c), div = __dadd_rn(__dmul_rn(e, ratio), c);
+    qr = __ddiv_rn(__dadd_rn(__dmul_rn(b, ratio), a), div);
+    qi = __ddiv_rn(__dsub_rn(b, __dmul_rn(a, ratio)), div);
+  }
+}
+template <int N, int SV>
+__device__ __forceinline__ int dense_zlu_factor(double* ar, double* ai, unsigned& swaps) {
+  unsigned piv = 0u;
+  int info = 0;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    int jp = j;
+    double dmax = __dadd_rn(fabs(ar[(j + N * j) * SV]), fabs(ai[(j + N * j) * SV]));
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      const double v = __dadd_rn(fabs(ar[(i + N * j) * SV]), fabs(ai[(i + N * j) * SV]));
+      if (v > dmax) { dmax = v; jp = i; }
+    }
+    piv |= (unsigned)jp << (4 * j);
+    if (ar[(jp + N * j) * SV] != 0.0 || ai[(jp + N * j) * SV] != 0.0) {
+      if (jp != j) {
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+          const double tr = ar[(j + N * c) * SV], ti = ai[(j + N * c) * SV];
+          ar[(j + N * c) * SV] = ar[(jp + N * c) * SV]; ai[(j + N * c) * SV] = ai[(jp + N * c) * SV];
+          ar[(jp + N * c) * SV] = tr; ai[(jp + N * c) * SV] = ti;
+        }
+      }
+      if (j < N - 1) {
+        const double pr = ar[(j + N * j) * SV], pi = ai[(j + N * j) * SV];
+        if (hypot(pr, pi) >= DBL_MIN) {
+          double rr, ri;
+          zdiv_dev(1.0, 0.0, pr, pi, rr, ri);
+#pragma unroll
+          for (int i = j + 1; i < N; ++i) {
+            const double xr = ar[(i + N * j) * SV], xi = ai[(i + N * j) * SV];
+            ar[(i + N * j) * SV] = __dsub_rn(__dmul_rn(rr, xr), __dmul_rn(ri, xi));
+            ai[(i + N * j) * SV] = __dadd_rn(__dmul_rn(rr, xi), __dmul_rn(ri, xr));
+          }
+        } else {
+#pragma unroll
+          for (int i = j + 1; i < N; ++i) {
+            double qr, qi;
+            zdiv_dev(ar[(i + N * j) * SV], ai[(i + N * j) * SV], pr, pi, qr, qi);
+            ar[(i + N * j) * SV] = qr; ai[(i + N * j) * SV] = qi;
+          }
+        }
+      }
+    } else if (info == 0) {
+      info = j + 1;
+    }
+    if (j < N - 1) {
+#pragma unroll
+      for (int c = j + 1; c < N; ++c) {
+        const double yr = ar[(j + N * c) * SV], yi = ai[(j + N * c) * SV];
+        if (yr != 0.0 || yi != 0.0) {
+          const double tr = __dsub_rn(__dmul_rn(-1.0, yr), __dmul_rn(0.0, yi)), ti = __dadd_rn(__dmul_rn(-1.0, yi), __dmul_rn(0.0, yr));
+#pragma unroll
+          for (int i = j + 1; i < N; ++i) {
+            const double xr = ar[(i + N * j) * SV], xi = ai[(i + N * j) * SV];
+            ar[(i + N * c) * SV] = __dadd_rn(ar[(i + N * c) * SV], __dsub_rn(__dmul_rn(xr, tr), __dmul_rn(xi, ti)));
+            ai[(i + N * c) * SV] = __dadd_rn(ai[(i + N * c) * SV], __dadd_rn(__dmul_rn(xr, ti), __dmul_rn(xi, tr)));
+          }
+        }
+      }
+    }
+  }
+  swaps = piv;
+  return info == 0 ? LU_OK : LU_SINGULAR;
+}
+template <int N, int SV>
+__device__ __forceinline__ void dense_zlu_solve(const double* ar, const double* ai, unsigned swaps, double* br, double* bi) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int ip = (swaps >> (4 * i)) & 15;
+    if (ip != i) {
+      const double tr = br[i * SV], ti = bi[i * SV];
+      br[i * SV] = br[ip * SV]; bi[i * SV] = bi[ip * SV];
+      br[ip * SV] = tr; bi[ip * SV] = ti;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const double kr = br[k * SV], ki = bi[k * SV];
+    if (kr != 0.0 || ki != 0.0) {
+#pragma unroll
+      for (int i = k + 1; i < N; ++i) {
+        const double xr = ar[(i + N * k) * SV], xi = ai[(i + N * k) * SV];
+        br[i * SV] = __dsub_rn(br[i * SV], __dsub_rn(__dmul_rn(kr, xr), __dmul_rn(ki, xi)));
+        bi[i * SV] = __dsub_rn(bi[i * SV], __dadd_rn(__dmul_rn(kr, xi), __dmul_rn(ki, xr)));
+      }
+    }
+  }
+#pragma unroll
+  for (int k = N - 1; k >= 0; --k) {
+    if (br[k * SV] != 0.0 || bi[k * SV] != 0.0) {
+      double kr, ki;
+      zdiv_dev(br[k * SV], bi[k * SV], ar[(k + N * k) * SV], ai[(k + N * k) * SV], kr, ki);
+      br[k * SV] = kr; bi[k * SV] = ki;
+#pragma unroll
+      for (int i = 0; i < k; ++i) {
+        const double xr = ar[(i + N * k) * SV], xi = ai[(i + N * k) * SV];
+        br[i * SV] = __dsub_rn(br[i * SV], __dsub_rn(__dmul_rn(kr, xr), __dmul_rn(ki, xi)));
+        bi[i * SV] = __dsub_rn(bi[i * SV], __dadd_rn(__dmul_rn(kr, xi), __dmul_rn(ki, xr)));
+      }
+    }
+  }
+}
+// dense policies: complex matrix from build_E (real plane, shift a) + imaginary plane (b on the diagonal)
+#define FATODE_DENSE_COMPLEX_POLICY()                                                                                             \
+  template <int SV>                                                                                                               \
+  __device__ static void build_EZ(const double* y, const double* PH, const Const& mc, double a, double b, double* zr, double* zi) { \
+    build_E<SV>(y, PH, mc, a, zr);                                                                                                \
+    _Pragma("unroll") for (int j = 0; j < N; ++j)                                                                                 \
+      _Pragma("unroll") for (int i = 0; i < N; ++i) zi[(i + N * j) * SV] = (i == j) ? b : 0.0;                                    \
+  }                                                                                                                               \
+  template <int SV>                                                                                                               \
+  __device__ static int zlu_factor(double* zr, double* zi, unsigned& swaps) { return dense_zlu_factor<N, SV>(zr, zi, swaps); }    \
+  template <int SV>                                                                                                               \
+  __device__ static void zlu_solve(const double* zr, const double* zi, unsigned swaps, double* br, double* bi) {                  \
+    dense_zlu_solve<N, SV>(zr, zi, swaps, br, bi);                                                                                \
+  }
+
 #define FATODE_F4(x) ((double)(x##f))
 
 struct SmallConst {
@@ -197,6 +328,7 @@ struct SmallStratoCell {
   __device__ static int lu_factor(double* lu, double* dinv, unsigned& swaps) { return dense_lu_factor<N, SV>(lu, dinv, swaps); }
   template <int SV>
   __device__ static void lu_solve(const double* lu, unsigned swaps, double* b) { dense_lu_solve<N, SV>(lu, swaps, b); }
+  FATODE_DENSE_COMPLEX_POLICY()
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -243,6 +375,7 @@ struct RobertsCell {
   __device__ static int lu_factor(double* lu, double* dinv, unsigned& swaps) { return dense_lu_factor<N, SV>(lu, dinv, swaps); }
   template <int SV>
   __device__ static void lu_solve(const double* lu, unsigned swaps, double* b) { dense_lu_solve<N, SV>(lu, swaps, b); }
+  FATODE_DENSE_COMPLEX_POLICY()
 };
 
 }  // namespace fatode

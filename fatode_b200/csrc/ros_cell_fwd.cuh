@@ -77,6 +77,7 @@ static_assert(cbm4_cell::NLU <= FT_LU && cbm4_cell::NJ == FT_MV && cbm4_cell::NJ
 //   build_E<SV>(y, PH, mc, ghinv, lu)   E = ghinv*I - JAC(t, y) in the model's factor storage
 //   lu_factor<SV>(lu, dinv, swaps) -> LU_OK | LU_SINGULAR (zero pivot: ros_PrepareMatrix halves H) | LU_IRREGULAR
 //   lu_solve<SV>(lu, swaps, b)  DGETRS('N')
+//   build_EZ / zlu_factor / zlu_solve: the same for the complex matrix -J + (a + i b) I (ZGETF2 / ZGETRS('N'), two planes)
 // All arrays are thread-private with element stride SV.
 enum { LU_OK = 0, LU_SINGULAR = 1, LU_IRREGULAR = 2 };
 
@@ -94,6 +95,20 @@ struct Cbm4Cell {
   }
   template <int SV>
   __device__ static void lu_solve(const double* lu, unsigned swaps, double* b) { cbm4_cell::lu_solve<SV>(lu, swaps, b); }
+  // complex matrix -J + (a + i b) I of the implicit Runge-Kutta families in two planes (FWD/RK/LS_Solver.F90:22-32)
+  template <int SV>
+  __device__ static void build_EZ(const double* y, const double* PH, const Const& mc, double a, double b, double* zr, double* zi) {
+    cbm4_cell::build_E<SV>(y, mc.fix, PH, a, zr);
+    cbm4_cell::zimag_init<SV>(zi, b);
+  }
+  template <int SV>
+  __device__ static int zlu_factor(double* zr, double* zi, unsigned& swaps) {
+    return cbm4_cell::zlu_factor<SV>(zr, zi, swaps) ? LU_IRREGULAR : LU_OK;
+  }
+  template <int SV>
+  __device__ static void zlu_solve(const double* zr, const double* zi, unsigned swaps, double* br, double* bi) {
+    cbm4_cell::zlu_solve<SV>(zr, zi, swaps, br, bi);
+  }
   __device__ static void photo(double t, const Const&, double* PH) {       // Update_SUN + photolysis part of Update_RCONST
     const double s = Cbm4Warp::sun(t);
 #pragma unroll

@@ -119,6 +119,21 @@ int fatode_sdirk_integrate_batch(int model, int64_t ncells, int nvar, double* y,
                                  const double* rcntrl_u, int* istatus, double* rstatus, int* ierr,
                                  const double* model_params, int mem, void* stream);
 
+/* INTEGRATE of FWD/RK (FWD/RK/RK_f90_Integrator.F90:32):
+ *   INTEGRATE(TIN,TOUT,N,NNZERO,VAR,RTOL,ATOL,FUN,JAC,ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U,IERR_U)
+ * Fully implicit 3-stage Runge-Kutta methods with simplified Newton iterations on the transformed (one real + one complex)
+ * system: ICNTRL(3) = 1 Radau-2A, 0/2 Lobatto-3C (the default), 3 Gauss, 4 Radau-1A, 5 Lobatto-3A.  INTEGRATE presets
+ * ICNTRL(5) = 8 (NewtonMaxit) and ICNTRL(10) = 1 (embedded SDIRK error estimator); ICNTRL_U/RCNTRL_U override only when
+ * > 0 (:67-74).  ICNTRL(6) = 1: zero starting values, ICNTRL(11) = 1: classic instead of Gustafsson controller,
+ * RCNTRL(8..11) = ThetaMin, NewtonTol, Qmin, Qmax.  ISTATUS as the reference counts it (the three FUN calls per Newton
+ * iteration are not counted, a real+complex decomposition counts once, RK_Solve counts twice).  Models: cbm4,
+ * small_strato, roberts.  Per-cell IERR: 1, or the reference's -1..-13; for cbm4 additionally -20 when a system asks for
+ * a pivot sequence outside the static LU pattern (no general RK kernel yet; seen for rtol >= 1e-5). */
+int fatode_rk_integrate_batch(int model, int64_t ncells, int nvar, double* y, double tin, double tout,
+                              const double* atol, const double* rtol, const int* icntrl_u,
+                              const double* rcntrl_u, int* istatus, double* rstatus, int* ierr,
+                              const double* model_params, int mem, void* stream);
+
 /* Engine knobs (process-wide): trajectory-tape budget in bytes (0 = 60% of free device memory) and
  * the number of cells per wave (0 = automatic). */
 int fatode_set_tape_budget(uint64_t bytes);

@@ -8,6 +8,7 @@
 #include "models.hpp"
 #include "ros.hpp"
 #include "sdirk.hpp"
+#include "rk.hpp"
 
 using namespace oracle;
 
@@ -121,10 +122,36 @@ int oracle_sdirk_fwd_batch(int model, long ncells, double* y, double tin, double
   return 0;
 }
 
+// FWD/RK INTEGRATE looped over cells.  raw != 0 bypasses INTEGRATE's presets (calls RungeKutta with the arrays as given).
+// stats (optional, 2 longs per cell): out[0] = bit mask of DGETF2 row interchanges jp != j that occurred anywhere is not
+// tracked here; see oracle_rk_pivot_census for the pivot statistics used by the code generator.
+int oracle_rk_fwd_batch(int model, long ncells, double* y, double tin, double tout, const double* atol, const double* rtol,
+                        const int* icntrl, const double* rcntrl, int* istatus, double* rstatus, int* ierr, int raw, int nthreads) {
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+  for (long c = 0; c < ncells; ++c) {
+    switch (model) {
+      case MODEL_ROBERTS: { Roberts m; ierr[c] = rk_integrate<Roberts>(m, tin, tout, y + c * Roberts::N, rtol, atol, icntrl, rcntrl, istatus + c * 20, rstatus + c * 20, raw != 0); break; }
+      case MODEL_SMALL_STRATO: { SmallStrato m; ierr[c] = rk_integrate<SmallStrato>(m, tin, tout, y + c * SmallStrato::N, rtol, atol, icntrl, rcntrl, istatus + c * 20, rstatus + c * 20, raw != 0); break; }
+      case MODEL_CBM4: { Cbm4 m; ierr[c] = rk_integrate<Cbm4>(m, tin, tout, y + c * Cbm4::N, rtol, atol, icntrl, rcntrl, istatus + c * 20, rstatus + c * 20, raw != 0); break; }
+      default: ierr[c] = -100;
+    }
+  }
+  return 0;
+}
+
 }  // extern "C"
 
 // unit-level probes for the parity tests
 extern "C" {
+// interchange census (see ref_lapack.hpp): copies the 32x32 count tables [column][pivot row], optionally clearing them
+int oracle_pivot_census(long* d, long* z, int reset) {
+  PivotCensus& c = pivot_census();
+  if (d) std::memcpy(d, c.d, sizeof c.d);
+  if (z) std::memcpy(z, c.z, sizeof c.z);
+  if (reset) std::memset(&c, 0, sizeof c);
+  return 0;
+}
 int oracle_cbm4_fun_jac(double t, const double* y, double* f, double* jac, double* hess) {
   Cbm4 m;
   m.fun(t, y, f);

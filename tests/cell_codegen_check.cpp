@@ -28,9 +28,17 @@ static bool same(double a, double b) { return a == b || (std::isnan(a) && std::i
 // wrap the oracle's LAPACK restatement
 #define dgetf2 dgetf2_oracle
 #define dgetrs dgetrs_oracle
+#define zgetf2 zgetf2_oracle
+#define zgetrs_n zgetrs_n_oracle
 #include "../oracle/ref_lapack.hpp"
 #undef dgetf2
 #undef dgetrs
+#undef zgetf2
+#undef zgetrs_n
+static long n_zlu = 0, n_zlu_bad = 0, n_zirregular = 0, n_zsolve = 0, n_zsolve_bad = 0;
+static double cur_zr[cbm4_cell::NLU], cur_zi[cbm4_cell::NLU];
+static unsigned cur_zswaps = 0;
+static bool cur_zok = false;
 namespace oracle {
 static inline int dgetf2(int n, double* a, int* ipiv) {
   using namespace cbm4_cell;
@@ -104,9 +112,61 @@ static inline void dgetrs(bool trans, int n, const double* a, const int* ipiv, d
   ++n_solve;
   for (int i = 0; i < 32; ++i) if (!same(x[i], b[i])) { ++n_solve_bad; break; }
 }
+// ZGETF2 / ZGETRS('N') of the implicit Runge-Kutta families through cbm4_cell::zlu_factor / zlu_solve
+static inline int zgetf2(int n, cplx* a, int* ipiv) {
+  using namespace cbm4_cell;
+  bool inpat[32][32];
+  std::memset(inpat, 0, sizeof inpat);
+  for (int i = 0; i < 32; ++i)
+    for (int e = LU_ROWPTR[i]; e < LU_ROWPTR[i + 1]; ++e) {
+      inpat[i][LU_COL[e]] = true; cur_zr[e] = a[i + 32 * LU_COL[e]].re; cur_zi[e] = a[i + 32 * LU_COL[e]].im;
+    }
+  int info = zgetf2_oracle(n, a, ipiv);
+  int bad = zlu_factor<1>(cur_zr, cur_zi, cur_zswaps);
+  ++n_zlu;
+  bool regular = (info == 0);
+  unsigned exp_sw = 0;
+  for (int k = 0; k < 32; ++k)
+    if (ipiv[k] != k + 1) {
+      bool ok = false;
+      for (int b = 0; b < NSWAP; ++b)
+        if (SWAP_COL[b] == k && SWAP_ROW[b] == ipiv[k] - 1) { ok = true; exp_sw |= 1u << b; }
+      if (!ok) regular = false;
+    }
+  cur_zok = (bad == 0);
+  if (!regular) {
+    ++n_zirregular;
+    if (bad == 0) { ++n_zlu_bad; std::printf("zlu_factor accepted an irregular pivot sequence\n"); }
+    return info;
+  }
+  if (bad != 0) { ++n_zlu_bad; std::printf("zlu_factor rejected a regular factorisation (zlu %ld)\n", n_zlu); return info; }
+  if (cur_zswaps != exp_sw) { ++n_zlu_bad; std::printf("complex swap flags %u != %u\n", cur_zswaps, exp_sw); return info; }
+  int nbad = 0;
+  for (int i = 0; i < 32; ++i)
+    for (int c = 0; c < 32; ++c) {
+      const cplx ref = a[i + 32 * c];
+      if (inpat[i][c]) {
+        int e = -1;
+        for (int q = LU_ROWPTR[i]; q < LU_ROWPTR[i + 1]; ++q) if (LU_COL[q] == c) e = q;
+        if (!same(cur_zr[e], ref.re) || !same(cur_zi[e], ref.im)) ++nbad;
+      } else if (ref.re != 0.0 || ref.im != 0.0) ++nbad;
+    }
+  if (nbad) { ++n_zlu_bad; std::printf("ZLU %ld: %d entries differ\n", n_zlu, nbad); }
+  return info;
+}
+static inline void zgetrs_n(int n, const cplx* a, const int* ipiv, cplx* b) {
+  if (!cur_zok) { zgetrs_n_oracle(n, a, ipiv, b); return; }
+  double xr[32], xi[32];
+  for (int i = 0; i < 32; ++i) { xr[i] = b[i].re; xi[i] = b[i].im; }
+  zgetrs_n_oracle(n, a, ipiv, b);
+  cbm4_cell::zlu_solve<1>(cur_zr, cur_zi, cur_zswaps, xr, xi);
+  ++n_zsolve;
+  for (int i = 0; i < 32; ++i) if (!same(xr[i], b[i].re) || !same(xi[i], b[i].im)) { ++n_zsolve_bad; break; }
+}
 }  // namespace oracle
 #include "../oracle/models.hpp"
 #include "../oracle/ros.hpp"
+#include "../oracle/rk.hpp"
 using namespace oracle;
 
 static uint64_t splitmix(uint64_t x) {
@@ -166,7 +226,15 @@ int main(int argc, char** argv) {
     int is[20];
     double rs[20];
     int e;
-    if (family_adj) {
+    if (family_adj == 2) {
+      // FWD/RK (real + complex factorisations): ICNTRL(3) cycles through the five methods
+      int icr[20] = {0};
+      const int meth[5] = {1, 2, 3, 4, 5};
+      icr[2] = meth[c % 5];
+      double rt[32], at[32];
+      for (int i = 0; i < 32; ++i) { rt[i] = F01 * 1e-5; at[i] = F01 * 1e-7; }
+      e = rk_integrate<Cbm4>(m, 43200.0, 43200.0 + hours * 3600.0, y, rt, at, icr, rc, is, rs);
+    } else if (family_adj) {
       // ADJ-family forward sweep (DOUBLE PRECISION tableau), adjoint skipped: ICNTRL(7)=1 is "no adjoint"
       double lam[32 * 1];
       std::memset(lam, 0, sizeof lam);
@@ -180,5 +248,9 @@ int main(int argc, char** argv) {
   std::printf("cells %d LUs %ld irregular %ld lu_mismatch %ld solves %ld solve_mismatch %ld fun_checks %ld fun_mismatch %ld swaps %ld %ld %ld %ld max_transposed_solve_err %.2e\n",
               ncells, n_lu, n_irregular, n_lu_bad, n_solve, n_solve_bad, n_fun, bad_fun, n_swaps[0], n_swaps[1], n_swaps[2],
               n_swaps[3], max_terr);
-  return (n_lu_bad || n_solve_bad || bad_fun || !(max_terr < 1e-9)) ? 1 : 0;
+  if (family_adj == 2)
+    std::printf("complex: LUs %ld irregular %ld lu_mismatch %ld solves %ld solve_mismatch %ld\n", n_zlu, n_zirregular, n_zlu_bad,
+                n_zsolve, n_zsolve_bad);
+  if (family_adj == 2 && (n_zlu == 0 || n_zsolve == 0)) return 4;
+  return (n_lu_bad || n_solve_bad || bad_fun || !(max_terr < 1e-9) || n_zlu_bad || n_zsolve_bad) ? 1 : 0;
 }

@@ -7,6 +7,7 @@ copied here verbatim (they are run outputs committed upstream, not source code):
   EXAMPLES/small_strato/small_ros_adj/rkadj_ADJ_results.m   Lambda(5,5) (RosenbrockADJ2, Rodas3)
   EXAMPLES/small_strato/small_ros/small_strato_dr.F90:23-24  ANS(5) (REAL(4) literals)
   EXAMPLES/cbm4/CBM4_SDIRK/cbm4_sdirk_sol.txt          Y(Tend), 32 x E24.16 (FWD/SDIRK, Sdirk4a, rtol 1e-6, atol 1e-8)
+  EXAMPLES/cbm4/CBM4_RK/cbm4_rk_sol.txt                Y(Tend), 32 x E24.16 (FWD/RK, Radau-2A, rtol 1e-6, atol 1e-8)
 Usage: python tests/golden/make_golden.py [/root/reference]
 """
 import json
@@ -40,6 +41,9 @@ def main():
     ys = [float(l) for l in open(os.path.join(REF, "EXAMPLES/cbm4/CBM4_SDIRK/cbm4_sdirk_sol.txt"))]
     assert len(ys) == 32
     json.dump({"source": "EXAMPLES/cbm4/CBM4_SDIRK/cbm4_sdirk_sol.txt", "y": ys}, open(os.path.join(HERE, "cbm4_sdirk.json"), "w"))
+    yr = [float(l) for l in open(os.path.join(REF, "EXAMPLES/cbm4/CBM4_RK/cbm4_rk_sol.txt"))]
+    assert len(yr) == 32
+    json.dump({"source": "EXAMPLES/cbm4/CBM4_RK/cbm4_rk_sol.txt", "y": yr}, open(os.path.join(HERE, "cbm4_rk.json"), "w"))
     print("wrote fixtures")
 
 

@@ -24,6 +24,8 @@ def lib():
         L.oracle_ros_adj_batch.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_int, _dp, _dp, _dp,
                                            ctypes.c_double, ctypes.c_double, _dp, _dp, _ip, _dp, _ip, _dp, _ip,
                                            ctypes.c_int]
+        L.oracle_rk_fwd_batch.argtypes = [ctypes.c_int, ctypes.c_long, _dp, ctypes.c_double, ctypes.c_double, _dp, _dp,
+                                          _ip, _dp, _ip, _dp, _ip, ctypes.c_int, ctypes.c_int]
         L.oracle_sdirk_fwd_batch.argtypes = [ctypes.c_int, ctypes.c_long, _dp, ctypes.c_double, ctypes.c_double, _dp, _dp,
                                              _ip, _dp, _ip, _dp, _ip, ctypes.c_int]
         L.oracle_ros_tlm_batch.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_int, _dp, _dp, ctypes.c_double, ctypes.c_double,
@@ -125,4 +127,19 @@ def sdirk_fwd(model, y, tin, tout, atol, rtol, icntrl=None, rcntrl=None, nthread
     ierr = np.zeros(nc, dtype=np.int32)
     lib().oracle_sdirk_fwd_batch(MODEL[model], nc, _d(y), tin, tout, _d(atol), _d(rtol), _i(ic), _d(rc), _i(ist), _d(rst),
                                  _i(ierr), nthreads)
+    return dict(y=y, istatus=ist, rstatus=rst, ierr=ierr)
+
+
+def rk_fwd(model, y, tin, tout, atol, rtol, icntrl=None, rcntrl=None, raw=False, nthreads=0):
+    """FWD/RK INTEGRATE looped over cells (raw=True: RungeKutta called directly, no INTEGRATE presets)."""
+    y = np.atleast_2d(np.array(y, dtype=np.float64, order="C"))
+    nc = y.shape[0]
+    ic, rc = _ctrl(icntrl, rcntrl)
+    atol = np.ascontiguousarray(atol, dtype=np.float64)
+    rtol = np.ascontiguousarray(rtol, dtype=np.float64)
+    ist = np.zeros((nc, 20), dtype=np.int32)
+    rst = np.zeros((nc, 20))
+    ierr = np.zeros(nc, dtype=np.int32)
+    lib().oracle_rk_fwd_batch(MODEL[model], nc, _d(y), tin, tout, _d(atol), _d(rtol), _i(ic), _d(rc), _i(ist), _d(rst),
+                              _i(ierr), 1 if raw else 0, nthreads)
     return dict(y=y, istatus=ist, rstatus=rst, ierr=ierr)

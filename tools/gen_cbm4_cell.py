@@ -257,6 +257,100 @@ def main():
     w("}")
     w("")
 
+    # ------------------------------------------------------------------ ZGETF2 / ZGETRS('N') on the same pattern
+    w("// ---- COMPLEX*16 factorisation of the implicit Runge-Kutta families (FWD/RK/LS_Solver.F90:22-52): the matrix")
+    w("// -J + (alpha + i beta) I lives in two planes zr/zi on the union pattern.  netlib ZGETF2 restricted to the candidate")
+    w("// interchanges: IZAMAX on |re|+|im| (first maximum), ZSCAL by the reciprocal ONE/pivot, ZGERU update")
+    w("// a(i,c) += l(i)*(-y(c)); products in the plain four-multiplication form, quotients in the range-reduced (Smith)")
+    w("// form gfortran emits under -fcx-fortran-rules.  Agrees with the reference bit for bit except for the sign of zeros.")
+    w("// imaginary plane of  -J + (alpha + i beta) I  on the union pattern: beta on the diagonal, zero elsewhere")
+    w("template <int SV> CBM4_CELL_FN void zimag_init(double* __restrict__ zi, const double beta) {")
+    dset = set(diag)
+    for e in range(NLU):
+        w(f"  zi[{e} * SV] = {'beta' if e in dset else '0.0'};")
+    w("}")
+    w("CBM4_CELL_INL void zdiv(const double a, const double b, const double c, const double e, double& qr, double& qi) {")
+    w("  if (fabs(c) < fabs(e)) {")
+    w("    const double ratio = c / e, div = c * ratio + e;")
+    w("    qr = (a * ratio + b) / div; qi = (b * ratio - a) / div;")
+    w("  } else {")
+    w("    const double ratio = e / c, div = e * ratio + c;")
+    w("    qr = (b * ratio + a) / div; qi = (b - a * ratio) / div;")
+    w("  }")
+    w("}")
+    w("template <int SV> CBM4_CELL_FN int zlu_factor(double* __restrict__ zr, double* __restrict__ zi, unsigned& swaps) {")
+    w("  int bad = 0;")
+    w("  unsigned sw = 0u;")
+    cabs1 = lambda e: f"(fabs(zr[{e} * SV]) + fabs(zi[{e} * SV]))"
+    for s_ in steps:
+        k = s_["k"]
+        cand = s_["cand"]
+        w(f"  {{  // column {k}")
+        if s_["p"] is not None:
+            p_ = s_["p"]
+            b = [i for i, (kk, _) in enumerate(SWAPS) if kk == k][0]
+            w(f"    double dmax = {cabs1(idx[(k, k)])}; int jp = {k};")
+            for i in cand[1:]:
+                w(f"    {{ const double v = {cabs1(idx[(i, k)])}; if (v > dmax) {{ dmax = v; jp = {i}; }} }}")
+            w(f"    const bool take = (jp == {p_});")
+            w(f"    bad |= (jp != {k}) & (jp != {p_});")
+            w(f"    if (take) {{")
+            w(f"      sw |= {1 << b}u;")
+            for c in s_["swcols"]:
+                a_, b_ = idx[(k, c)], idx[(p_, c)]
+                w(f"      {{ const double tr = zr[{a_} * SV], ti = zi[{a_} * SV]; zr[{a_} * SV] = zr[{b_} * SV]; zi[{a_} * SV] = zi[{b_} * SV]; "
+                  f"zr[{b_} * SV] = tr; zi[{b_} * SV] = ti; }}")
+            w("    }")
+        elif len(cand) > 1:
+            w(f"    const double d = {cabs1(idx[(k, k)])};")
+            terms = " | ".join(f"({cabs1(idx[(i, k)])} > d)" for i in cand[1:])
+            w(f"    bad |= {terms};")
+        w(f"    const double pr = zr[{idx[(k, k)]} * SV], pi = zi[{idx[(k, k)]} * SV];")
+        w(f"    bad |= !(fabs(pr) + fabs(pi) >= 4.0 * DBL_MIN);")
+        if k < N - 1 and s_["rows"]:
+            w(f"    double rr, ri; zdiv(1.0, 0.0, pr, pi, rr, ri);")
+            for i in s_["rows"]:
+                e = idx[(i, k)]
+                w(f"    const double lr{i} = rr * zr[{e} * SV] - ri * zi[{e} * SV], li{i} = rr * zi[{e} * SV] + ri * zr[{e} * SV]; "
+                  f"zr[{e} * SV] = lr{i}; zi[{e} * SV] = li{i};")
+            for c in s_["cols"]:
+                e = idx[(k, c)]
+                w(f"    {{ const double tr = -zr[{e} * SV], ti = -zi[{e} * SV];")
+                for i in s_["rows"]:
+                    q = idx[(i, c)]
+                    w(f"      zr[{q} * SV] = zr[{q} * SV] + (lr{i} * tr - li{i} * ti); zi[{q} * SV] = zi[{q} * SV] + (lr{i} * ti + li{i} * tr);")
+                w("    }")
+        w("  }")
+    w("  swaps = sw;")
+    w("  return bad;")
+    w("}")
+    w("")
+    w("// ZGETRS('N'), one right-hand side (br + i bi): ZLASWP, ZTRSM(L,L,N,U), ZTRSM(L,U,N,N)")
+    w("template <int SV> CBM4_CELL_FN void zlu_solve(const double* __restrict__ zr, const double* __restrict__ zi, const unsigned swaps, "
+      "double* __restrict__ br, double* __restrict__ bi) {")
+    for b, (k, p_) in enumerate(SWAPS):
+        w(f"  if (swaps & {1 << b}u) {{ const double tr = br[{k} * SV], ti = bi[{k} * SV]; br[{k} * SV] = br[{p_} * SV]; bi[{k} * SV] = bi[{p_} * SV]; "
+          f"br[{p_} * SV] = tr; bi[{p_} * SV] = ti; }}")
+    for k in range(N - 1):
+        rows = [i for i in range(k + 1, N) if P[i][k]]
+        if not rows:
+            continue
+        w(f"  {{ const double kr = br[{k} * SV], ki = bi[{k} * SV];")
+        for i in rows:
+            e = idx[(i, k)]
+            w(f"    br[{i} * SV] = br[{i} * SV] - (kr * zr[{e} * SV] - ki * zi[{e} * SV]); bi[{i} * SV] = bi[{i} * SV] - (kr * zi[{e} * SV] + ki * zr[{e} * SV]);")
+        w("  }")
+    for k in range(N - 1, -1, -1):
+        rows = [i for i in range(k) if P[i][k]]
+        d = idx[(k, k)]
+        w(f"  {{ double kr, ki; zdiv(br[{k} * SV], bi[{k} * SV], zr[{d} * SV], zi[{d} * SV], kr, ki); br[{k} * SV] = kr; bi[{k} * SV] = ki;")
+        for i in rows:
+            e = idx[(i, k)]
+            w(f"    br[{i} * SV] = br[{i} * SV] - (kr * zr[{e} * SV] - ki * zi[{e} * SV]); bi[{i} * SV] = bi[{i} * SV] - (kr * zi[{e} * SV] + ki * zr[{e} * SV]);")
+        w("  }")
+    w("}")
+    w("")
+
     # ------------------------------------------------------------------ DGETRS('T') for the backward sweep
     w("// x <- (P L U)^-T x with the vector in registers (backward sweep: lane = adjoint column; lu/dinv are per-cell")
     w("// arrays read with warp-uniform addresses).  U^T and L^T substitutions in axpy form, then the interchanges in")
