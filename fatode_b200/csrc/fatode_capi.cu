@@ -31,6 +31,7 @@
 #include "model_small_cell.cuh"
 #include "sdirk_cell_fwd.cuh"
 #include "rk_cell_fwd.cuh"
+#include "model_cbm4_dense_cell.cuh"
 
 using namespace fatode;
 
@@ -1241,13 +1242,12 @@ extern "C" int fatode_ros_integrate_tlm_batch(int model, int64_t ncells, int nva
 // FWD/SDIRK and FWD/RK INTEGRATE: one system per thread for all three models
 template <class Params, class Const>
 using CellFwdKernel = void (*)(Params, Const, long, const double*, double*, const double*, const double*, int*, double*, int*,
-                               unsigned long long*);
+                               unsigned long long*, const int*);
 
 template <class Params, class Const>
 static int cellfwd_launch(CellFwdKernel<Params, Const> kern, size_t smem, int lanes, const Params& prm, const Const& mc,
                           int64_t ncells, double* d_y, const double* d_atol, const double* d_rtol, int* d_istatus,
-                          double* d_rstatus, int* d_ierr, cudaStream_t st) {
-  std::memset(&g_stats, 0, sizeof g_stats);
+                          double* d_rstatus, int* d_ierr, cudaStream_t st, const int* d_cell_ids = nullptr) {
   int dev = 0, sms = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1260,7 +1260,7 @@ static int cellfwd_launch(CellFwdKernel<Params, Const> kern, size_t smem, int la
   PhaseTimer tm(st);
   tm.start();
   kern<<<blocks, 32, smem, st>>>(prm, mc, (long)ncells, d_y, d_y, d_atol, d_rtol, d_istatus, d_rstatus, d_ierr,
-                                 g_ctr.as<unsigned long long>());
+                                 g_ctr.as<unsigned long long>(), d_cell_ids);
   CUDA_TRY(cudaGetLastError());
   g_stats.ms_forward += tm.stop();
   g_stats.launches++;
@@ -1272,6 +1272,7 @@ static int cellfwd_launch(CellFwdKernel<Params, Const> kern, size_t smem, int la
 
 enum { IMPL_SDIRK = 0, IMPL_RK = 1 };
 constexpr int RK_LANES_CBM4 = 16;   // 13.4 KB of shared memory per system (three factor planes + 17 vectors)
+constexpr int RK_LANES_DENSE = 7, SDIRK_LANES_DENSE = 16;   // general-pivoting second pass (dense 32 x 32 planes)
 
 static int implicit_integrate_batch(int family, int model, int64_t ncells, int nvar, double* y, double tin, double tout,
                                     const double* atol, const double* rtol, const int* icntrl_u, const double* rcntrl_u,
@@ -1310,6 +1311,7 @@ static int implicit_integrate_batch(int family, int model, int64_t ncells, int n
   }
   if (model == FATODE_MODEL_CBM4) CUDA_TRY(cudaMemcpyToSymbolAsync(c_cbm4_rc, mc.rc_base, sizeof(double) * 81, 0, cudaMemcpyHostToDevice, st));
   const double *da = b_atol.as<double>(), *dr = b_rtol.as<double>();
+  std::memset(&g_stats, 0, sizeof g_stats);
   int rc;
   if (family == IMPL_SDIRK) {
     if (model == FATODE_MODEL_CBM4)
@@ -1327,6 +1329,29 @@ static int implicit_integrate_batch(int family, int model, int64_t ncells, int n
       rc = cellfwd_launch<RkParams, SmallConst>(k_rk_fwd_cell<RobertsCell, 32>, RkSmem<RobertsCell, 32>::BYTES, 32, rp, sc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st);
   }
   if (rc != 0) return rc;
+  if (model == FATODE_MODEL_CBM4) {
+    // second pass: systems that left the static pivot pattern kept their initial state; integrate them again with
+    // general partial pivoting (same arithmetic as the reference for every pivot sequence, singular retries included)
+    std::vector<int> h_ierr((size_t)ncells), ids;
+    CUDA_TRY(cudaMemcpyAsync(h_ierr.data(), d_ierr, sizeof(int) * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int64_t c = 0; c < ncells; ++c)
+      if (h_ierr[(size_t)c] == RK_IERR_IRREGULAR) ids.push_back((int)c);
+    static_assert(RK_IERR_IRREGULAR == SDIRK_IERR_IRREGULAR, "one hand-back code for both implicit families");
+    if (!ids.empty()) {
+      DevBuf b_ids;
+      CUDA_TRY(b_ids.alloc(sizeof(int) * ids.size()));
+      CUDA_TRY(cudaMemcpyAsync(b_ids.p, ids.data(), sizeof(int) * ids.size(), cudaMemcpyHostToDevice, st));
+      if (family == IMPL_SDIRK)
+        rc = cellfwd_launch<SdirkParams, Cbm4Const>(k_sdirk_fwd_cell<Cbm4DenseCell, SDIRK_LANES_DENSE>, SdirkSmem<Cbm4DenseCell, SDIRK_LANES_DENSE>::BYTES,
+                                                   SDIRK_LANES_DENSE, sp, mc, (int64_t)ids.size(), d_y, da, dr, d_ist, d_rst, d_ierr, st, b_ids.as<int>());
+      else
+        rc = cellfwd_launch<RkParams, Cbm4Const>(k_rk_fwd_cell<Cbm4DenseCell, RK_LANES_DENSE>, RkSmem<Cbm4DenseCell, RK_LANES_DENSE>::BYTES,
+                                                RK_LANES_DENSE, rp, mc, (int64_t)ids.size(), d_y, da, dr, d_ist, d_rst, d_ierr, st, b_ids.as<int>());
+      if (rc != 0) return rc;
+      g_stats.cells_general = (int64_t)ids.size();
+    }
+  }
   if (mem == FATODE_MEM_HOST) {
     CUDA_TRY(cudaMemcpyAsync(y, d_y, ny, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(istatus, d_ist, sizeof(int) * 20 * ncells, cudaMemcpyDeviceToHost, st));

@@ -16,8 +16,9 @@
 // INTEGRATE presets ICNTRL(10) = 1, so the error estimate is always the embedded SDIRK stage (:604-683); the classic
 // estimator (RK_ErrorEstimate) cannot be selected through this interface and is not built.
 // The CBM-IV policy factorises both matrices with the generated static-pattern DGETF2 / ZGETF2; a system that needs any
-// other pivot sequence ends with IERR = RK_IERR_IRREGULAR (there is no general RK kernel yet).  The dense small-model
-// policies handle every case themselves.
+// other pivot sequence ends with IERR = RK_IERR_IRREGULAR, keeps its initial state and is integrated again by the host
+// with the general-pivoting policy Cbm4DenseCell (cell_ids lists those systems).  The dense small-model policies handle
+// every case themselves.
 #pragma once
 #include "fatode_common.cuh"
 #include "ros_cell_fwd.cuh"
@@ -52,7 +53,8 @@ template <class Model, int LANES>
 __global__ void __launch_bounds__(32, 1)
 k_rk_fwd_cell(RkParams rp, typename Model::Const mc, long ncells, const double* __restrict__ y_in, double* __restrict__ y_out,
               const double* __restrict__ atol_g, const double* __restrict__ rtol_g, int* __restrict__ istatus,
-              double* __restrict__ rstatus, int* __restrict__ ierr_out, unsigned long long* __restrict__ queue) {
+              double* __restrict__ rstatus, int* __restrict__ ierr_out, unsigned long long* __restrict__ queue,
+              const int* __restrict__ cell_ids) {
   extern __shared__ __align__(16) double cell_smem[];
   constexpr int N = Model::N;
   constexpr int SV = LANES;
@@ -103,8 +105,9 @@ k_rk_fwd_cell(RkParams rp, typename Model::Const mc, long ncells, const double* 
   };
 
   for (;;) {
-    const long cell = (long)atomicAdd(queue, 1ull);
-    if (cell >= ncells) break;
+    const long slot = (long)atomicAdd(queue, 1ull);
+    if (slot >= ncells) break;
+    const long cell = cell_ids ? (long)cell_ids[slot] : slot;   // second pass: the systems the first pass handed back
 #pragma unroll 4
     for (int i = 0; i < N; ++i) Y[i * SV] = y_in[cell * N + i];
     int nfun = 0, njac = 0, nstp = 0, nacc = 0, nrej = 0, ndec = 0, nsol = 0, nsng = 0;
@@ -412,8 +415,10 @@ k_rk_fwd_cell(RkParams rp, typename Model::Const mc, long ncells, const double* 
     }
     // ---- results
     ierr_out[cell] = ierr;
+    if (ierr != RK_IERR_IRREGULAR) {   // a handed-back system keeps its initial state for the general-pivoting pass
 #pragma unroll 4
-    for (int i = 0; i < N; ++i) y_out[cell * N + i] = Y[i * SV];
+      for (int i = 0; i < N; ++i) y_out[cell * N + i] = Y[i * SV];
+    }
     int* is_ = istatus + cell * 20;
     for (int q = 0; q < 20; ++q) is_[q] = 0;
     is_[Nfun] = nfun; is_[Njac] = njac; is_[Nstp] = nstp; is_[Nacc] = nacc; is_[Nrej] = nrej;

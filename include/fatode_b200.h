@@ -112,8 +112,8 @@ int fatode_ros_integrate_tlm_batch(int model, int64_t ncells, int nvar, int ntlm
  * Singly diagonally implicit Runge-Kutta methods (ICNTRL(3) = 1..5: Sdirk2a, 2b, 3a, 4a (default), 4b) with simplified
  * Newton iterations; ICNTRL_U/RCNTRL_U override the defaults only when > 0 (:57-64); RCNTRL(8..11) = ThetaMin,
  * NewtonTol, Qmin, Qmax, ICNTRL(5) = NewtonMaxit, ICNTRL(6) = zero starting values for Newton.  Models: cbm4,
- * small_strato, roberts.  Per-cell IERR: 1, or the reference's -1..-8; for cbm4 additionally -20 when a system asks for
- * a pivot sequence outside the static LU pattern (no general SDIRK kernel yet; not observed for the shipped inputs). */
+ * small_strato, roberts.  Per-cell IERR: 1, or the reference's -1..-8.  cbm4 systems whose factorisations leave the static
+ * pivot pattern are integrated a second time with general partial pivoting (fatode_stats.cells_general counts them). */
 int fatode_sdirk_integrate_batch(int model, int64_t ncells, int nvar, double* y, double tin, double tout,
                                  const double* atol, const double* rtol, const int* icntrl_u,
                                  const double* rcntrl_u, int* istatus, double* rstatus, int* ierr,
@@ -127,8 +127,9 @@ int fatode_sdirk_integrate_batch(int model, int64_t ncells, int nvar, double* y,
  * > 0 (:67-74).  ICNTRL(6) = 1: zero starting values, ICNTRL(11) = 1: classic instead of Gustafsson controller,
  * RCNTRL(8..11) = ThetaMin, NewtonTol, Qmin, Qmax.  ISTATUS as the reference counts it (the three FUN calls per Newton
  * iteration are not counted, a real+complex decomposition counts once, RK_Solve counts twice).  Models: cbm4,
- * small_strato, roberts.  Per-cell IERR: 1, or the reference's -1..-13; for cbm4 additionally -20 when a system asks for
- * a pivot sequence outside the static LU pattern (no general RK kernel yet; seen for rtol >= 1e-5). */
+ * small_strato, roberts.  Per-cell IERR: 1, or the reference's -1..-13.  cbm4 systems whose factorisations leave the static
+ * pivot pattern (seen for rtol >= 1e-5) are integrated a second time with general partial pivoting
+ * (fatode_stats.cells_general counts them). */
 int fatode_rk_integrate_batch(int model, int64_t ncells, int nvar, double* y, double tin, double tout,
                               const double* atol, const double* rtol, const int* icntrl_u,
                               const double* rcntrl_u, int* istatus, double* rstatus, int* ierr,

@@ -128,3 +128,22 @@ def test_rk_methods_options_and_small_models():
     ic = np.zeros(20, dtype=np.int32)
     ic[2] = 9
     assert (F.integrate_rk("cbm4", T0, t1, y0, rtol, atol, icntrl_u=ic).ierr == -13).all()
+
+
+@pytest.mark.gpu
+def test_general_pivoting_second_pass_rk_and_sdirk():
+    """At loose tolerances some CBM-IV systems need interchanges outside the static pattern (e.g. column 26 with row 28):
+    the first pass hands them back and the dense general-pivoting pass must reproduce the oracle bit for bit."""
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    rtol, atol = np.full(32, F01 * 1.0e-4), np.full(32, F01 * 1.0e-6)
+    y0 = perturbed_states(F.initial_state("cbm4"), 192)
+    res = F.integrate_rk("cbm4", T0, T1, y0, rtol, atol, icntrl_u=radau())
+    st = F.last_stats()
+    assert 0 < st.cells_general < 192, "this case is known to need the second pass for a few systems"
+    assert_bitwise(res, O.rk_fwd("cbm4", y0, T0, T1, atol, rtol, radau()))
+    assert (res.ierr == 1).all()
+    rtol, atol = np.full(32, 1.0e-3), np.full(32, 1.0e-5)
+    res = F.integrate_sdirk("cbm4", T0, T1, y0, rtol, atol)
+    assert_bitwise(res, O.sdirk_fwd("cbm4", y0, T0, T1, atol, rtol))
+    print("SDIRK systems on the general-pivoting pass:", F.last_stats().cells_general)

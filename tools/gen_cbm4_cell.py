@@ -180,6 +180,29 @@ def main():
     w("}")
     w("")
 
+    # ------------------------------------------------------------------ dense E for the full-pivoting fallback
+    w("// Same as build_E but on a dense column-major 32 x 32 matrix, element (r,c) at E[(r + 32*c) * SV] (structural zeros")
+    w("// written as 0.0): input of the general DGETF2 / ZGETF2 of the implicit families' fallback policy.")
+    w("template <int SV> CBM4_CELL_FN void build_E_dense(const double* __restrict__ V, const double F, const double* __restrict__ PH, "
+      "const double ghinv, double* __restrict__ E) {")
+    w("  double B[138];")
+    for a in jac:
+        if a.lhs.name == "B":
+            w(f"  B[{a.lhs.idx[0]-1}] = {fx.emit_c(a.rhs, ref)};")
+    w("  for (int q = 0; q < 1024; ++q) E[q * SV] = 0.0;")
+    dense_written = set()
+    for a in jac:
+        if a.lhs.name == "JV":
+            r, c = a.lhs.idx[0] - 1, a.lhs.idx[1] - 1
+            e = f"(-{fx.emit_c(a.rhs, ref)})"
+            if r == c:
+                e = f"({e} + ghinv)"
+            w(f"  E[{r + 32 * c} * SV] = {e};")
+            dense_written.add((r, c))
+    for i in range(N):
+        assert (i, i) in dense_written
+    w("}")
+    w("")
     # ------------------------------------------------------------------ DGETF2 on the union pattern
     w("// |x| as an ordered integer (IEEE doubles of equal sign order like their bit patterns)")
     w("CBM4_CELL_INL unsigned long long absbits(double x) {")
