@@ -7,6 +7,10 @@
 !     MODULE ROS_adj_f90_Integrator :: INTEGRATE_ADJ   (ADJ/ROS_ADJ/ROS_ADJ_f90_Integrator.F90:34)
 !     MODULE ROS_f90_Integrator     :: INTEGRATE       (FWD/ROS/ROS_f90_Integrator.F90:32)
 !     MODULE ROS_tlm_f90_Integrator :: INTEGRATE_TLM   (TLM/ROS_TLM/ROS_TLM_f90_Integrator.F90:35)
+!     MODULE SDIRK_f90_Integrator   :: INTEGRATE       (FWD/SDIRK/SDIRK_f90_Integrator.F90:25)   after fatode_b200_set_family(FATODE_FAMILY_SDIRK)
+!     MODULE RK_f90_Integrator      :: INTEGRATE       (FWD/RK/RK_f90_Integrator.F90:32)         after fatode_b200_set_family(FATODE_FAMILY_RK)
+!  (upstream the forward families are separate modules that all export INTEGRATE with the same argument list; the
+!  application picks one with its USE line, here with fatode_b200_set_family)
 !  Dummy-argument names and order are the reference's, so keyword calls such as
 !     call integrate_adj(tin=tstart, tout=tend, nvar=nvar, nnzero=nnz, np=np, nadj=nadj, y=var, &
 !                        lambda=lambda, mu=mu, ..., fun=fun, jac=jac, ..., icntrl_u=icntrl)
@@ -22,11 +26,14 @@ MODULE fatode_b200_mod
   IMPLICIT NONE
   PRIVATE
   PUBLIC :: INTEGRATE, INTEGRATE_ADJ, INTEGRATE_TLM, INTEGRATE_BATCH, INTEGRATE_ADJ_BATCH, fatode_b200_set_model
+  PUBLIC :: fatode_b200_set_family, FATODE_FAMILY_ROS, FATODE_FAMILY_SDIRK, FATODE_FAMILY_RK
   PUBLIC :: FATODE_MODEL_ROBERTS, FATODE_MODEL_SMALL_STRATO, FATODE_MODEL_CBM4
 
   INTEGER(C_INT), PARAMETER :: FATODE_MODEL_ROBERTS = 1, FATODE_MODEL_SMALL_STRATO = 2, FATODE_MODEL_CBM4 = 3
   INTEGER(C_INT), PARAMETER :: FATODE_MEM_HOST = 0
+  INTEGER, PARAMETER :: FATODE_FAMILY_ROS = 0, FATODE_FAMILY_SDIRK = 1, FATODE_FAMILY_RK = 2
   INTEGER(C_INT), SAVE :: current_model = FATODE_MODEL_CBM4
+  INTEGER, SAVE :: current_family = FATODE_FAMILY_ROS
 
   INTERFACE
     FUNCTION fatode_ros_integrate_batch(model, ncells, nvar, y, tin, tout, atol, rtol, icntrl_u, rcntrl_u, &
@@ -40,6 +47,30 @@ MODULE fatode_b200_mod
       TYPE(C_PTR), VALUE :: icntrl_u, rcntrl_u, model_params, stream
       INTEGER(C_INT) :: istatus(*), ierr(*)
       INTEGER(C_INT) :: fatode_ros_integrate_batch
+    END FUNCTION
+    FUNCTION fatode_sdirk_integrate_batch(model, ncells, nvar, y, tin, tout, atol, rtol, icntrl_u, rcntrl_u, &
+                                        istatus, rstatus, ierr, model_params, mem, stream) BIND(C, NAME='fatode_sdirk_integrate_batch')
+      IMPORT :: C_INT, C_INT64_T, C_DOUBLE, C_PTR
+      INTEGER(C_INT), VALUE :: model, nvar, mem
+      INTEGER(C_INT64_T), VALUE :: ncells
+      REAL(C_DOUBLE), VALUE :: tin, tout
+      REAL(C_DOUBLE) :: y(*), rstatus(*)
+      REAL(C_DOUBLE), INTENT(IN) :: atol(*), rtol(*)
+      TYPE(C_PTR), VALUE :: icntrl_u, rcntrl_u, model_params, stream
+      INTEGER(C_INT) :: istatus(*), ierr(*)
+      INTEGER(C_INT) :: fatode_sdirk_integrate_batch
+    END FUNCTION
+    FUNCTION fatode_rk_integrate_batch(model, ncells, nvar, y, tin, tout, atol, rtol, icntrl_u, rcntrl_u, &
+                                        istatus, rstatus, ierr, model_params, mem, stream) BIND(C, NAME='fatode_rk_integrate_batch')
+      IMPORT :: C_INT, C_INT64_T, C_DOUBLE, C_PTR
+      INTEGER(C_INT), VALUE :: model, nvar, mem
+      INTEGER(C_INT64_T), VALUE :: ncells
+      REAL(C_DOUBLE), VALUE :: tin, tout
+      REAL(C_DOUBLE) :: y(*), rstatus(*)
+      REAL(C_DOUBLE), INTENT(IN) :: atol(*), rtol(*)
+      TYPE(C_PTR), VALUE :: icntrl_u, rcntrl_u, model_params, stream
+      INTEGER(C_INT) :: istatus(*), ierr(*)
+      INTEGER(C_INT) :: fatode_rk_integrate_batch
     END FUNCTION
     FUNCTION fatode_ros_integrate_adj_batch(model, ncells, nvar, np, nadj, y, lambda, mu, tin, tout, atol_adj, rtol_adj, &
                                             atol, rtol, icntrl_u, rcntrl_u, istatus, rstatus, ierr, mu_sum, model_params, &
@@ -76,7 +107,13 @@ CONTAINS
     current_model = INT(model, C_INT)
   END SUBROUTINE
 
-  !~~~> FWD/ROS INTEGRATE, one system (FWD/ROS/ROS_f90_Integrator.F90:32-33)
+  SUBROUTINE fatode_b200_set_family(family)
+    INTEGER, INTENT(IN) :: family
+    current_family = family
+  END SUBROUTINE
+
+  !~~~> FWD/ROS, FWD/SDIRK or FWD/RK INTEGRATE, one system (FWD/ROS/ROS_f90_Integrator.F90:32-33,
+  !     FWD/SDIRK/SDIRK_f90_Integrator.F90:25-26, FWD/RK/RK_f90_Integrator.F90:32-33: identical argument lists)
   SUBROUTINE INTEGRATE( TIN, TOUT, N, NNZERO, VAR, RTOL, ATOL, FUN, JAC, ICNTRL_U, RCNTRL_U, ISTATUS_U, RSTATUS_U, IERR_U )
     INTEGER, INTENT(IN) :: N, NNZERO
     DOUBLE PRECISION, INTENT(INOUT) :: VAR(N)
@@ -92,8 +129,17 @@ CONTAINS
     pic = C_NULL_PTR; prc = C_NULL_PTR
     IF (PRESENT(ICNTRL_U)) pic = C_LOC(ICNTRL_U)
     IF (PRESENT(RCNTRL_U)) prc = C_LOC(RCNTRL_U)
-    rc = fatode_ros_integrate_batch(current_model, 1_C_INT64_T, INT(N, C_INT), VAR, TIN, TOUT, ATOL, RTOL, pic, prc, &
-                                    ist, rst, ierr, C_NULL_PTR, FATODE_MEM_HOST, C_NULL_PTR)
+    SELECT CASE (current_family)
+    CASE (FATODE_FAMILY_SDIRK)
+      rc = fatode_sdirk_integrate_batch(current_model, 1_C_INT64_T, INT(N, C_INT), VAR, TIN, TOUT, ATOL, RTOL, pic, prc, &
+                                        ist, rst, ierr, C_NULL_PTR, FATODE_MEM_HOST, C_NULL_PTR)
+    CASE (FATODE_FAMILY_RK)
+      rc = fatode_rk_integrate_batch(current_model, 1_C_INT64_T, INT(N, C_INT), VAR, TIN, TOUT, ATOL, RTOL, pic, prc, &
+                                     ist, rst, ierr, C_NULL_PTR, FATODE_MEM_HOST, C_NULL_PTR)
+    CASE DEFAULT
+      rc = fatode_ros_integrate_batch(current_model, 1_C_INT64_T, INT(N, C_INT), VAR, TIN, TOUT, ATOL, RTOL, pic, prc, &
+                                      ist, rst, ierr, C_NULL_PTR, FATODE_MEM_HOST, C_NULL_PTR)
+    END SELECT
     IF (rc /= 0) ierr(1) = rc
     IF (PRESENT(ISTATUS_U)) ISTATUS_U(:) = ist(:)
     IF (PRESENT(RSTATUS_U)) RSTATUS_U(:) = rst(:)
