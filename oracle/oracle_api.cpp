@@ -9,6 +9,7 @@
 #include "ros.hpp"
 #include "sdirk.hpp"
 #include "rk.hpp"
+#include "rk_adj.hpp"
 
 using namespace oracle;
 
@@ -25,6 +26,20 @@ static void adj_batch(long ncells, int np, int nadj, double* y, double* lambda, 
     ierr[c] = ros_integrate_adj<M>(mdl, np, nadj, y + c * N, lambda + c * (long)N * nadj,
                                    (np > 0 && mu) ? mu + c * (long)np * nadj : nullptr, tin, tout, atol, rtol, icntrl,
                                    rcntrl, istatus + c * 20, rstatus + c * 20);
+  }
+}
+
+template <class M>
+static void rk_adj_batch(long ncells, int np, int nadj, double* y, double* lambda, double* mu, double tin, double tout,
+                         const double* atol, const double* rtol, const int* icntrl, const double* rcntrl, int* istatus,
+                         double* rstatus, int* ierr, int nthreads) {
+  const int N = M::N;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+  for (long c = 0; c < ncells; ++c) {
+    M mdl;
+    ierr[c] = rk_adj_integrate<M>(mdl, np, nadj, y + c * N, lambda + c * (long)N * nadj,
+                                  (np > 0 && mu) ? mu + c * (long)np * nadj : nullptr, tin, tout, atol, rtol, icntrl,
+                                  rcntrl, istatus + c * 20, rstatus + c * 20);
   }
 }
 
@@ -84,6 +99,19 @@ int oracle_ros_adj_batch(int model, long ncells, int np, int nadj, double* y, do
     case MODEL_ROBERTS: adj_batch<Roberts>(ncells, np, nadj, y, lambda, mu, tin, tout, atol, rtol, icntrl, rcntrl, istatus, rstatus, ierr, nthreads); return 0;
     case MODEL_SMALL_STRATO: adj_batch<SmallStrato>(ncells, np, nadj, y, lambda, mu, tin, tout, atol, rtol, icntrl, rcntrl, istatus, rstatus, ierr, nthreads); return 0;
     case MODEL_CBM4: adj_batch<Cbm4>(ncells, np, nadj, y, lambda, mu, tin, tout, atol, rtol, icntrl, rcntrl, istatus, rstatus, ierr, nthreads); return 0;
+  }
+  return -1;
+}
+
+// INTEGRATE_ADJ of ADJ/RK_ADJ looped over cells (same layouts as oracle_ros_adj_batch)
+int oracle_rk_adj_batch(int model, long ncells, int np, int nadj, double* y, double* lambda, double* mu, double tin,
+                        double tout, const double* atol, const double* rtol, const int* icntrl, const double* rcntrl,
+                        int* istatus, double* rstatus, int* ierr, int nthreads) {
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+  switch (model) {
+    case MODEL_ROBERTS: rk_adj_batch<Roberts>(ncells, np, nadj, y, lambda, mu, tin, tout, atol, rtol, icntrl, rcntrl, istatus, rstatus, ierr, nthreads); return 0;
+    case MODEL_SMALL_STRATO: rk_adj_batch<SmallStrato>(ncells, np, nadj, y, lambda, mu, tin, tout, atol, rtol, icntrl, rcntrl, istatus, rstatus, ierr, nthreads); return 0;
+    case MODEL_CBM4: rk_adj_batch<Cbm4>(ncells, np, nadj, y, lambda, mu, tin, tout, atol, rtol, icntrl, rcntrl, istatus, rstatus, ierr, nthreads); return 0;
   }
   return -1;
 }

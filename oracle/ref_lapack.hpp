@@ -192,4 +192,24 @@ static inline void zgetrs_n(int n, const cplx* a, const int* ipiv, cplx* b) {
     }
 }
 
+// ZGETRS('T') with one right-hand side: ZTRSM(L,U,T,N) + ZTRSM(L,L,T,U) + ZLASWP(-1); plain transpose, no conjugation
+static inline void zgetrs_t(int n, const cplx* a, const int* ipiv, cplx* b) {
+  const cplx one = {1.0, 0.0};
+  for (int i = 0; i < n; ++i) {
+    cplx temp = cmul(one, b[i]);
+    for (int k = 0; k < i; ++k) temp = csub(temp, cmul(a[k + n * i], b[k]));
+    temp = cdiv(temp, a[i + n * i]);
+    b[i] = temp;
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    cplx temp = cmul(one, b[i]);
+    for (int k = i + 1; k < n; ++k) temp = csub(temp, cmul(a[k + n * i], b[k]));
+    b[i] = temp;
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    int ip = ipiv[i] - 1;
+    if (ip != i) { cplx t = b[i]; b[i] = b[ip]; b[ip] = t; }
+  }
+}
+
 }  // namespace oracle

@@ -30,11 +30,14 @@ static bool same(double a, double b) { return a == b || (std::isnan(a) && std::i
 #define dgetrs dgetrs_oracle
 #define zgetf2 zgetf2_oracle
 #define zgetrs_n zgetrs_n_oracle
+#define zgetrs_t zgetrs_t_oracle
 #include "../oracle/ref_lapack.hpp"
 #undef dgetf2
 #undef dgetrs
 #undef zgetf2
 #undef zgetrs_n
+#undef zgetrs_t
+static double max_zterr = 0.0;
 static long n_zlu = 0, n_zlu_bad = 0, n_zirregular = 0, n_zsolve = 0, n_zsolve_bad = 0;
 static double cur_zr[cbm4_cell::NLU], cur_zi[cbm4_cell::NLU];
 static unsigned cur_zswaps = 0;
@@ -152,8 +155,27 @@ static inline int zgetf2(int n, cplx* a, int* ipiv) {
       } else if (ref.re != 0.0 || ref.im != 0.0) ++nbad;
     }
   if (nbad) { ++n_zlu_bad; std::printf("ZLU %ld: %d entries differ\n", n_zlu, nbad); }
+  if ((n_zlu & 15) == 0) {   // transposed complex solve of the RK adjoint sweep against ZGETRS('T'), to rounding
+    cplx xr_[32];
+    double xr[32], xi[32], zdr[32], zdi[32];
+    for (int i = 0; i < 32; ++i) {
+      xr[i] = std::sin(1.0 + i * 0.37 + (double)(n_zlu % 97)); xi[i] = std::cos(0.3 + i * 0.91 + (double)(n_zlu % 53));
+      xr_[i] = cplx{xr[i], xi[i]};
+      const cplx d = cdiv(cplx{1.0, 0.0}, a[i + 32 * i]);
+      zdr[i] = d.re; zdi[i] = d.im;
+    }
+    zgetrs_t_oracle(n, a, ipiv, xr_);
+    zlut_solve(cur_zr, cur_zi, zdr, zdi, cur_zswaps, xr, xi);
+    double sc = 0.0, er = 0.0;
+    for (int i = 0; i < 32; ++i) {
+      sc = std::fmax(sc, std::fabs(xr_[i].re) + std::fabs(xr_[i].im));
+      er = std::fmax(er, std::fabs(xr_[i].re - xr[i]) + std::fabs(xr_[i].im - xi[i]));
+    }
+    max_zterr = std::fmax(max_zterr, er / sc);
+  }
   return info;
 }
+static inline void zgetrs_t(int n, const cplx* a, const int* ipiv, cplx* b) { zgetrs_t_oracle(n, a, ipiv, b); }
 static inline void zgetrs_n(int n, const cplx* a, const int* ipiv, cplx* b) {
   if (!cur_zok) { zgetrs_n_oracle(n, a, ipiv, b); return; }
   double xr[32], xi[32];
@@ -217,6 +239,18 @@ int main(int argc, char** argv) {
           if (!same(ref, lu[e])) { ++bad_fun; }
         }
       cbm4_cell::jac_values<1>(y, m.fix[0], PH, jv);
+      {   // J^T x of the RK adjoint sweep against the dense product
+        double x[32], out[32];
+        for (int i = 0; i < 32; ++i) x[i] = std::sin(0.7 + 1.3 * i + q);
+        cbm4_cell::jt_vec(jv, x, out);
+        double sc = 0.0, er = 0.0;
+        for (int cidx = 0; cidx < 32; ++cidx) {
+          double sref = 0.0;
+          for (int r = 0; r < 32; ++r) sref += jac[r + 32 * cidx] * x[r];
+          sc = std::fmax(sc, std::fabs(sref)); er = std::fmax(er, std::fabs(sref - out[cidx]));
+        }
+        if (!(er <= 1e-12 * sc)) ++bad_fun;
+      }
       // entry order: by column then row over the structural non-zeros of CBM4_JAC
       double hs_ref[258], hs_new[258];
       cbm4_gen::hessian(y, m.fix, m.rconst, hs_ref);
@@ -249,8 +283,9 @@ int main(int argc, char** argv) {
               ncells, n_lu, n_irregular, n_lu_bad, n_solve, n_solve_bad, n_fun, bad_fun, n_swaps[0], n_swaps[1], n_swaps[2],
               n_swaps[3], max_terr);
   if (family_adj == 2)
-    std::printf("complex: LUs %ld irregular %ld lu_mismatch %ld solves %ld solve_mismatch %ld\n", n_zlu, n_zirregular, n_zlu_bad,
-                n_zsolve, n_zsolve_bad);
+    std::printf("complex: LUs %ld irregular %ld lu_mismatch %ld solves %ld solve_mismatch %ld max_transposed_err %.2e\n", n_zlu,
+                n_zirregular, n_zlu_bad, n_zsolve, n_zsolve_bad, max_zterr);
+  if (family_adj == 2 && !(max_zterr < 1e-9)) return 5;
   if (family_adj == 2 && (n_zlu == 0 || n_zsolve == 0)) return 4;
   return (n_lu_bad || n_solve_bad || bad_fun || !(max_terr < 1e-9) || n_zlu_bad || n_zsolve_bad) ? 1 : 0;
 }

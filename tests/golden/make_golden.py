@@ -8,6 +8,7 @@ copied here verbatim (they are run outputs committed upstream, not source code):
   EXAMPLES/small_strato/small_ros/small_strato_dr.F90:23-24  ANS(5) (REAL(4) literals)
   EXAMPLES/cbm4/CBM4_SDIRK/cbm4_sdirk_sol.txt          Y(Tend), 32 x E24.16 (FWD/SDIRK, Sdirk4a, rtol 1e-6, atol 1e-8)
   EXAMPLES/cbm4/CBM4_RK/cbm4_rk_sol.txt                Y(Tend), 32 x E24.16 (FWD/RK, Radau-2A, rtol 1e-6, atol 1e-8)
+  EXAMPLES/cbm4/CBM4_RK_ADJ/{cbm4_rk_sol.txt,cbm4_output_sens.txt}   ADJ/RK_ADJ Radau-2A: Y(Tend), Lambda(32,32), Mu(29,32)
 Usage: python tests/golden/make_golden.py [/root/reference]
 """
 import json
@@ -44,6 +45,13 @@ def main():
     yr = [float(l) for l in open(os.path.join(REF, "EXAMPLES/cbm4/CBM4_RK/cbm4_rk_sol.txt"))]
     assert len(yr) == 32
     json.dump({"source": "EXAMPLES/cbm4/CBM4_RK/cbm4_rk_sol.txt", "y": yr}, open(os.path.join(HERE, "cbm4_rk.json"), "w"))
+    d = os.path.join(REF, "EXAMPLES/cbm4/CBM4_RK_ADJ")
+    y = [float(l) for l in open(os.path.join(d, "cbm4_rk_sol.txt"))]
+    vals = [float(l) for l in open(os.path.join(d, "cbm4_output_sens.txt")) if not l.startswith(("L", "M"))]
+    assert len(y) == 32 and len(vals) == 32 * 32 + 32 * 29
+    json.dump({"source": "EXAMPLES/cbm4/CBM4_RK_ADJ/{cbm4_rk_sol.txt,cbm4_output_sens.txt}",
+               "y": y, "lambda": vals[:1024], "mu": vals[1024:]},
+              open(os.path.join(HERE, "cbm4_rk_adj.json"), "w"))
     print("wrote fixtures")
 
 

@@ -1,0 +1,80 @@
+"""ADJ/RK_ADJ (adjoint part): discrete adjoint of the 3-stage implicit Runge-Kutta methods.
+CPU: the oracle restatement (oracle/rk_adj.hpp) against the reference's golden files
+EXAMPLES/cbm4/CBM4_RK_ADJ/{cbm4_rk_sol.txt, cbm4_output_sens.txt} (driver cbm4_rk_adj_dr.F90: Radau-2A, rtol = 0.1*1e-5,
+atol = 0.1*1e-7, NADJ = 32, NP = 29, 12 h .. 84 h).  No combination of estimator / controller / starting values of the
+shipped integrator reproduces that run's step sequence (the files predate it), so the pin is at the level of two valid
+runs: state 2e-8, dominant sensitivity columns 1e-7.  GPU: forward sweep bit-identical, Lambda/Mu within 1e-9."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+F01 = float(np.float32(0.1))
+T0 = 12.0 * 3600.0
+T1 = T0 + 72.0 * 3600.0
+
+
+def driver_tols():
+    return np.full(32, F01 * 1.0e-5), np.full(32, F01 * 1.0e-7)
+
+
+def radau():
+    ic = np.zeros(20, dtype=np.int32)
+    ic[2] = 1
+    return ic
+
+
+def test_oracle_against_reference_golden_files_and_counters():
+    g = json.load(open(os.path.join(G, "cbm4_rk_adj.json")))
+    gy, glam, gmu = np.array(g["y"]), np.array(g["lambda"]).reshape(32, 32), np.array(g["mu"]).reshape(32, 29)
+    rtol, atol = driver_tols()
+    r = O.rk_adj("cbm4", O.initial_state("cbm4"), 32, T0, T1, atol, rtol, radau(), nthreads=1)
+    assert r["ierr"][0] == 1
+    y, lam, mu = r["y"][0], r["lambda_"][0], r["mu"][0]
+    assert np.max(np.abs(y - gy)) <= 1e-7 * np.max(np.abs(gy))                 # observed 3.4e-9
+    cs = np.max(np.abs(glam), axis=1)
+    err = np.max(np.abs(lam - glam), axis=1) / np.maximum(cs, 1e-300)
+    dominant = cs > 1e-6                         # columns within six decades of the largest one
+    assert dominant.sum() >= 18 and np.all(err[dominant] <= 1e-5) and np.median(err[dominant]) <= 1e-7, err
+    rs = np.max(np.abs(gmu), axis=0)
+    rerr = np.max(np.abs(mu - gmu), axis=0) / rs
+    noise = {15, 21, 22, 23, 24, 25, 26}         # parameters that multiply identically-zero species (as for ROS_ADJ)
+    good = [p for p in range(29) if p not in noise]
+    assert np.all(rerr[good] <= 1e-5), rerr      # observed <= 3e-7
+    # counters: forward passes F (incl. Newton failures), accepted A, backward adds per step Njac 4, Ndec 1,
+    # Nstp 1 and Nsol 2 * sweeps * NADJ with sweeps = min(8, max(NewIt + 2, 7))
+    I = r["istatus"][0]
+    fwd = O.rk_adj("cbm4", O.initial_state("cbm4"), 32, T0, T1, atol, rtol, np.array([0, 0, 1, 0, 0, 0, 0, 0, 1] + [0] * 11, dtype=np.int32),
+                   nthreads=1)                   # ICNTRL(9) = 1: forward sweep only
+    Fw = fwd["istatus"][0]
+    A = I[3]
+    assert np.array_equal(fwd["y"][0], y) and Fw[3] == A and Fw[4] == I[4] and Fw[0] == I[0] and Fw[7] == I[7]
+    assert I[1] == Fw[1] + 4 * A and I[5] == Fw[5] + A and I[2] == Fw[2] + A
+    per_step = (I[6] - Fw[6]) / (64.0 * A)
+    assert 7.0 <= per_step <= 8.0
+    # the adjoint of another family agrees to integration accuracy on the dominant columns (independent check)
+    ic5 = np.zeros(20, dtype=np.int32)
+    ic5[2] = 5
+    q = O.ros_adj("cbm4", O.initial_state("cbm4"), 32, T0, T1, atol, rtol, ic5, nthreads=1)
+    ql = q["lambda_"][0]
+    cq = np.max(np.abs(ql), axis=1)
+    e2 = np.max(np.abs(lam - ql), axis=1) / np.maximum(cq, 1e-300)
+    assert np.all(e2[cq > 1e-3] <= 1e-4), e2
+
+
+def test_oracle_options():
+    rtol, atol = driver_tols()
+    y0 = O.initial_state("cbm4")
+    ic = radau()
+    ic[6] = 2                                     # direct 3N x 3N solve: not restated
+    assert O.rk_adj("cbm4", y0, 2, T0, T0 + 600.0, atol, rtol, ic)["ierr"][0] == -100
+    ic = radau()
+    ic[2] = 5                                     # no Lobatto-3A in RK_ADJ
+    assert O.rk_adj("cbm4", y0, 2, T0, T0 + 600.0, atol, rtol, ic)["ierr"][0] == -13
+    ic = radau()
+    ic[8] = 3                                     # continuous adjoints are not implemented upstream either
+    assert O.rk_adj("cbm4", y0, 2, T0, T0 + 600.0, atol, rtol, ic)["ierr"][0] == -9

@@ -498,6 +498,48 @@ def main():
         pexpr.append(e)
     emit_paired(w, "AP", pexpr)
     w("}")
+    # ------------------------------------------------------------------ Runge-Kutta adjoint helpers
+    w("")
+    w("// ---- operators of the Runge-Kutta discrete adjoint (rk_DadjInt, ADJ/RK_ADJ/RK_ADJ_f90_Integrator.F90:1229-1524)")
+    w("// AP[p] = ARP_p(Y): reactant product of reaction JCOEFF[p]; column p of JACP is AP[p] * STOICM(:, JCOEFF[p])")
+    w("// (dFun_dRcoeff, cbm4_Parameters.F90:1121-1161)")
+    w("template <int SV> CBM4_CELL_FN void arp_values(const double* __restrict__ YI, const double F, double* __restrict__ AP) {")
+    pexpr = [l1_expr(mech.ARP[gd.JCOEFF[p] - 1], "YI") for p in range(gd.NP)]
+    emit_paired(w, "AP", pexpr)
+    w("}")
+    w("// out = J^T x  (LSS_Mul_Jactr1..3), Jv in the JAC_ROW/JAC_COL entry order")
+    w("CBM4_CELL_INL void jt_vec(const double* __restrict__ Jv, const double (&x)[32], double (&out)[32]) {")
+    for c in range(N):
+        ents = [(e, rc[0]) for e, rc in enumerate(jent) if rc[1] == c]
+        w("  { double a0 = 0.0, a1 = 0.0;")
+        for t, (e, r) in enumerate(ents):
+            w(f"    a{t % 2} = fma(Jv[{e}], x[{r}], a{t % 2});")
+        w(f"    out[{c}] = a0 + a1; }}")
+    w("}")
+    w("// (xr + i xi) <- (P L U)^-T (xr + i xi) for the complex factors of zlu_factor (ZGETRS('T'): plain transpose).")
+    w("// zdr + i zdi = 1/U(k,k).  Same structure as lut_solve; fma arithmetic, agrees with netlib to rounding.")
+    w("CBM4_CELL_INL void zlut_solve(const double* __restrict__ zr, const double* __restrict__ zi, const double* __restrict__ zdr, "
+      "const double* __restrict__ zdi, const unsigned swaps, double (&xr)[32], double (&xi)[32]) {")
+    for k in range(N):
+        cols = [c for c in range(k + 1, N) if P[k][c]]
+        w(f"  {{ const double wr = fma(xr[{k}], zdr[{k}], -(xi[{k}] * zdi[{k}])), wi = fma(xr[{k}], zdi[{k}], xi[{k}] * zdr[{k}]); xr[{k}] = wr; xi[{k}] = wi;")
+        for c in cols:
+            e = idx[(k, c)]
+            w(f"    xr[{c}] = fma(-zr[{e}], wr, fma(zi[{e}], wi, xr[{c}])); xi[{c}] = fma(-zr[{e}], wi, fma(-zi[{e}], wr, xi[{c}]));")
+        w("  }")
+    for k in range(N - 1, 0, -1):
+        cols = [c for c in range(k) if P[k][c]]
+        if not cols:
+            continue
+        w(f"  {{ const double wr = xr[{k}], wi = xi[{k}];")
+        for c in cols:
+            e = idx[(k, c)]
+            w(f"    xr[{c}] = fma(-zr[{e}], wr, fma(zi[{e}], wi, xr[{c}])); xi[{c}] = fma(-zr[{e}], wi, fma(-zi[{e}], wr, xi[{c}]));")
+        w("  }")
+    for bi in range(len(SWAPS) - 1, -1, -1):
+        k, p_ = SWAPS[bi]
+        w(f"  if (swaps & {1 << bi}u) {{ double t = xr[{k}]; xr[{k}] = xr[{p_}]; xr[{p_}] = t; t = xi[{k}]; xi[{k}] = xi[{p_}]; xi[{p_}] = t; }}")
+    w("}")
     # ------------------------------------------------------------------ tangent-linear sweep (lane = TLM column)
     w("")
     w("// ---- operators of the tangent-linear sweep (ros_TLM_Int, TLM/ROS_TLM/ROS_TLM_f90_Integrator.F90:551-633): the same")
