@@ -32,6 +32,7 @@
 #include "sdirk_cell_fwd.cuh"
 #include "rk_cell_fwd.cuh"
 #include "model_cbm4_dense_cell.cuh"
+#include "rk_cell_adj.cuh"
 
 using namespace fatode;
 
@@ -380,10 +381,12 @@ struct CachedBuf {
 static thread_local CachedBuf g_tape, g_y0, g_nacc, g_off, g_queue, g_part;
 static thread_local CachedBuf g_ids, g_wnacc, g_wlast, g_prev, g_owner, g_order, g_wierr;   // per-thread path
 static void release_pipeline_workspace();
+static void release_rk_workspace();
 extern "C" int fatode_release_workspace(void) {
   g_tape.release(); g_y0.release(); g_nacc.release(); g_off.release(); g_queue.release(); g_part.release();
   g_ids.release(); g_wnacc.release(); g_wlast.release(); g_prev.release(); g_owner.release(); g_order.release(); g_wierr.release();
   release_pipeline_workspace();
+  release_rk_workspace();
   return 0;
 }
 
@@ -1240,14 +1243,14 @@ extern "C" int fatode_ros_integrate_tlm_batch(int model, int64_t ncells, int nva
 
 // ------------------------------------------------------------------------------------------------
 // FWD/SDIRK and FWD/RK INTEGRATE: one system per thread for all three models
-template <class Params, class Const>
+template <class Params, class Const, class... Extra>
 using CellFwdKernel = void (*)(Params, Const, long, const double*, double*, const double*, const double*, int*, double*, int*,
-                               unsigned long long*, const int*);
+                               unsigned long long*, const int*, Extra...);
 
-template <class Params, class Const>
-static int cellfwd_launch(CellFwdKernel<Params, Const> kern, size_t smem, int lanes, const Params& prm, const Const& mc,
+template <class Params, class Const, class... Extra>
+static int cellfwd_launch(CellFwdKernel<Params, Const, Extra...> kern, size_t smem, int lanes, const Params& prm, const Const& mc,
                           int64_t ncells, double* d_y, const double* d_atol, const double* d_rtol, int* d_istatus,
-                          double* d_rstatus, int* d_ierr, cudaStream_t st, const int* d_cell_ids = nullptr) {
+                          double* d_rstatus, int* d_ierr, cudaStream_t st, const int* d_cell_ids, Extra... extra) {
   int dev = 0, sms = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1260,7 +1263,7 @@ static int cellfwd_launch(CellFwdKernel<Params, Const> kern, size_t smem, int la
   PhaseTimer tm(st);
   tm.start();
   kern<<<blocks, 32, smem, st>>>(prm, mc, (long)ncells, d_y, d_y, d_atol, d_rtol, d_istatus, d_rstatus, d_ierr,
-                                 g_ctr.as<unsigned long long>(), d_cell_ids);
+                                 g_ctr.as<unsigned long long>(), d_cell_ids, extra...);
   CUDA_TRY(cudaGetLastError());
   g_stats.ms_forward += tm.stop();
   g_stats.launches++;
@@ -1315,18 +1318,18 @@ static int implicit_integrate_batch(int family, int model, int64_t ncells, int n
   int rc;
   if (family == IMPL_SDIRK) {
     if (model == FATODE_MODEL_CBM4)
-      rc = cellfwd_launch<SdirkParams, Cbm4Const>(k_sdirk_fwd_cell<Cbm4Cell, 32>, SdirkSmem<Cbm4Cell, 32>::BYTES, 32, sp, mc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st);
+      rc = cellfwd_launch<SdirkParams, Cbm4Const>(k_sdirk_fwd_cell<Cbm4Cell, 32>, SdirkSmem<Cbm4Cell, 32>::BYTES, 32, sp, mc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st, nullptr);
     else if (model == FATODE_MODEL_SMALL_STRATO)
-      rc = cellfwd_launch<SdirkParams, SmallConst>(k_sdirk_fwd_cell<SmallStratoCell, 32>, SdirkSmem<SmallStratoCell, 32>::BYTES, 32, sp, sc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st);
+      rc = cellfwd_launch<SdirkParams, SmallConst>(k_sdirk_fwd_cell<SmallStratoCell, 32>, SdirkSmem<SmallStratoCell, 32>::BYTES, 32, sp, sc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st, nullptr);
     else
-      rc = cellfwd_launch<SdirkParams, SmallConst>(k_sdirk_fwd_cell<RobertsCell, 32>, SdirkSmem<RobertsCell, 32>::BYTES, 32, sp, sc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st);
+      rc = cellfwd_launch<SdirkParams, SmallConst>(k_sdirk_fwd_cell<RobertsCell, 32>, SdirkSmem<RobertsCell, 32>::BYTES, 32, sp, sc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st, nullptr);
   } else {
     if (model == FATODE_MODEL_CBM4)
-      rc = cellfwd_launch<RkParams, Cbm4Const>(k_rk_fwd_cell<Cbm4Cell, RK_LANES_CBM4>, RkSmem<Cbm4Cell, RK_LANES_CBM4>::BYTES, RK_LANES_CBM4, rp, mc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st);
+      rc = cellfwd_launch<RkParams, Cbm4Const, double*, int>(k_rk_fwd_cell<Cbm4Cell, RK_LANES_CBM4>, RkSmem<Cbm4Cell, RK_LANES_CBM4>::BYTES, RK_LANES_CBM4, rp, mc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st, nullptr, (double*)nullptr, 0);
     else if (model == FATODE_MODEL_SMALL_STRATO)
-      rc = cellfwd_launch<RkParams, SmallConst>(k_rk_fwd_cell<SmallStratoCell, 32>, RkSmem<SmallStratoCell, 32>::BYTES, 32, rp, sc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st);
+      rc = cellfwd_launch<RkParams, SmallConst, double*, int>(k_rk_fwd_cell<SmallStratoCell, 32>, RkSmem<SmallStratoCell, 32>::BYTES, 32, rp, sc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st, nullptr, (double*)nullptr, 0);
     else
-      rc = cellfwd_launch<RkParams, SmallConst>(k_rk_fwd_cell<RobertsCell, 32>, RkSmem<RobertsCell, 32>::BYTES, 32, rp, sc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st);
+      rc = cellfwd_launch<RkParams, SmallConst, double*, int>(k_rk_fwd_cell<RobertsCell, 32>, RkSmem<RobertsCell, 32>::BYTES, 32, rp, sc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st, nullptr, (double*)nullptr, 0);
   }
   if (rc != 0) return rc;
   if (model == FATODE_MODEL_CBM4) {
@@ -1346,8 +1349,8 @@ static int implicit_integrate_batch(int family, int model, int64_t ncells, int n
         rc = cellfwd_launch<SdirkParams, Cbm4Const>(k_sdirk_fwd_cell<Cbm4DenseCell, SDIRK_LANES_DENSE>, SdirkSmem<Cbm4DenseCell, SDIRK_LANES_DENSE>::BYTES,
                                                    SDIRK_LANES_DENSE, sp, mc, (int64_t)ids.size(), d_y, da, dr, d_ist, d_rst, d_ierr, st, b_ids.as<int>());
       else
-        rc = cellfwd_launch<RkParams, Cbm4Const>(k_rk_fwd_cell<Cbm4DenseCell, RK_LANES_DENSE>, RkSmem<Cbm4DenseCell, RK_LANES_DENSE>::BYTES,
-                                                RK_LANES_DENSE, rp, mc, (int64_t)ids.size(), d_y, da, dr, d_ist, d_rst, d_ierr, st, b_ids.as<int>());
+        rc = cellfwd_launch<RkParams, Cbm4Const, double*, int>(k_rk_fwd_cell<Cbm4DenseCell, RK_LANES_DENSE>, RkSmem<Cbm4DenseCell, RK_LANES_DENSE>::BYTES,
+                                                RK_LANES_DENSE, rp, mc, (int64_t)ids.size(), d_y, da, dr, d_ist, d_rst, d_ierr, st, b_ids.as<int>(), (double*)nullptr, 0);
       if (rc != 0) return rc;
       g_stats.cells_general = (int64_t)ids.size();
     }
@@ -1376,6 +1379,216 @@ extern "C" int fatode_rk_integrate_batch(int model, int64_t ncells, int nvar, do
                                          void* stream) {
   return implicit_integrate_batch(IMPL_RK, model, ncells, nvar, y, tin, tout, atol, rtol, icntrl_u, rcntrl_u, istatus, rstatus,
                                   ierr, model_params, mem, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ADJ/RK_ADJ INTEGRATE_ADJ for CBM-IV: taping forward sweep (one system per thread), per-step preparation (one thread per
+// accepted step), backward sweep (one warp per system, lane = adjoint column).  rk_cell_adj.cuh.
+static thread_local CachedBuf g_rk_tape, g_rk_fat, g_rk_idx, g_rk_stat;
+static void release_rk_workspace() { g_rk_tape.release(); g_rk_fat.release(); g_rk_idx.release(); g_rk_stat.release(); }
+
+__global__ void k_rk_gather_status(int n, const int* __restrict__ ids, const int* __restrict__ ierr, const int* __restrict__ istatus,
+                                   int* __restrict__ out) {   // out[2 i] = ierr, out[2 i + 1] = Nacc
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = ids[i];
+  out[2 * i] = ierr[c];
+  out[2 * i + 1] = istatus[(size_t)c * 20 + Nacc];
+}
+
+// One group of systems (ids) through forward + backward.  Systems that overflow their tape slot are appended to `overflow`.
+static int rk_adj_group(const RkParams& rp, const Cbm4Const& mc, const std::vector<int>& ids, int cap, int nadj, bool with_mu,
+                        int np, bool do_adjoint, size_t fat_budget, double* d_y, double* d_lam, double* d_mu, const double* d_atol,
+                        const double* d_rtol, int* d_ist, double* d_rst, int* d_ierr, cudaStream_t st, int sms,
+                        std::vector<int>& overflow) {
+  const int n = (int)ids.size();
+  if (n == 0) return 0;
+  // index buffer: [ids n][slot n][cell n] ints, then [rec_off n + 1] long long
+  const size_t idx_bytes = sizeof(int) * (size_t)n * 3 + 16 + sizeof(long long) * (size_t)(n + 1);
+  CUDA_TRY(g_rk_idx.ensure(idx_bytes));
+  int* d_ids = g_rk_idx.as<int>();
+  int* d_slot = d_ids + n;
+  int* d_cell = d_slot + n;
+  long long* d_off = reinterpret_cast<long long*>(reinterpret_cast<char*>(g_rk_idx.p) + ((sizeof(int) * (size_t)n * 3 + 15) / 16) * 16);
+  CUDA_TRY(cudaMemcpyAsync(d_ids, ids.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  if (do_adjoint) CUDA_TRY(g_rk_tape.ensure(sizeof(double) * (size_t)n * cap * RK_REC));
+  if (int e = cellfwd_launch<RkParams, Cbm4Const, double*, int>(k_rk_fwd_cell<Cbm4Cell, RK_LANES_CBM4, true>, RkSmem<Cbm4Cell, RK_LANES_CBM4>::BYTES,
+                                                               RK_LANES_CBM4, rp, mc, n, d_y, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, d_ids,
+                                                               do_adjoint ? g_rk_tape.as<double>() : (double*)nullptr, cap))
+    return e;
+  if (!do_adjoint) return 0;
+  CUDA_TRY(g_rk_stat.ensure(sizeof(int) * 2 * (size_t)n));
+  k_rk_gather_status<<<(n + 255) / 256, 256, 0, st>>>(n, d_ids, d_ierr, d_ist, g_rk_stat.as<int>());
+  std::vector<int> h_stat(2 * (size_t)n);
+  CUDA_TRY(cudaMemcpyAsync(h_stat.data(), g_rk_stat.p, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  // backward sweep in batches that fit the record budget
+  const size_t rec_bytes = sizeof(double) * RA_REC;
+  std::vector<int> b_slot, b_cell;
+  std::vector<long long> b_off;
+  auto flush = [&]() -> int {
+    const int nb = (int)b_slot.size();
+    if (nb == 0) return 0;
+    const long long nrec = b_off.back();
+    CUDA_TRY(g_rk_fat.ensure((size_t)std::max<long long>(nrec, 1) * rec_bytes));
+    CUDA_TRY(cudaMemcpyAsync(d_slot, b_slot.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_cell, b_cell.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_off, b_off.data(), sizeof(long long) * (nb + 1), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(g_ctr.p, 0, 16 * sizeof(unsigned long long), st));
+    PhaseTimer tm(st);
+    if (nrec > 0) {
+      RkAdjPrepArgs pa{(long)nrec, nb, d_off, d_slot, g_rk_tape.as<double>(), cap, g_rk_fat.as<double>()};
+      const size_t psm = sizeof(double) * (size_t)(3 * cbm4_cell::NLU + 3 * 32) * RA_PREP_LANES;
+      CUDA_TRY(cudaFuncSetAttribute(k_rk_adj_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+      const unsigned pblocks = (unsigned)std::min<long long>((nrec + RA_PREP_LANES - 1) / RA_PREP_LANES, (long long)sms);
+      tm.start();
+      k_rk_adj_prep<<<pblocks, 32, psm, st>>>(rp, mc, pa);
+      CUDA_TRY(cudaGetLastError());
+      g_stats.ms_forward_tape += tm.stop();
+      g_stats.launches++; g_stats.launches_expand++;
+    }
+    RkAdjArgs aa{nb, d_off, d_cell, g_rk_fat.as<double>(), d_lam, d_mu, d_ist, g_ctr.as<unsigned long long>(), nadj, with_mu ? 1 : 0, np};
+    CUDA_TRY(cudaFuncSetAttribute(k_rk_adj_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RK_ADJ_SMEM));
+    const unsigned ablocks = (unsigned)std::min<int>(nb, 2 * sms);
+    tm.start();
+    k_rk_adj_cell<<<ablocks, 32, RK_ADJ_SMEM, st>>>(rp, aa);
+    CUDA_TRY(cudaGetLastError());
+    g_stats.ms_adjoint += tm.stop();
+    g_stats.launches++; g_stats.launches_adjoint++;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    b_slot.clear(); b_cell.clear(); b_off.clear();
+    return 0;
+  };
+  for (int i = 0; i < n; ++i) {
+    const int code = h_stat[2 * (size_t)i], nacc = h_stat[2 * (size_t)i + 1];
+    if (code == IERR_TAPE_OVERFLOW) { overflow.push_back(ids[i]); continue; }
+    if (code != 1) continue;                       // failed forward sweep: no adjoint (the reference returns)
+    if (b_off.empty()) b_off.push_back(0);
+    if (!b_slot.empty() && (size_t)(b_off.back() + nacc) * rec_bytes > fat_budget)
+      if (int e = flush()) return e;
+    if (b_off.empty()) b_off.push_back(0);
+    b_slot.push_back(i);
+    b_cell.push_back(ids[i]);
+    b_off.push_back(b_off.back() + nacc);
+    g_stats.accepted_steps += nacc;
+  }
+  return flush();
+}
+
+static int rk_adj_device(const RkParams& rp, const Cbm4Const& mc, int64_t ncells, int nadj, bool with_mu, int np, bool do_adjoint,
+                         double* d_y, double* d_lam, double* d_mu, const double* d_atol, const double* d_rtol, int* d_ist,
+                         double* d_rst, int* d_ierr, double* d_mu_sum, cudaStream_t st) {
+  std::memset(&g_stats, 0, sizeof g_stats);
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  size_t free_b = 0, total_b = 0;
+  CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+  free_b += g_rk_tape.cap + g_rk_fat.cap;
+  const size_t budget = g_tape_budget ? (size_t)g_tape_budget : (size_t)(0.6 * (double)free_b);
+  const int cap = std::min(rp.max_no_steps, 1024);
+  int64_t wave = g_wave_cells > 0 ? g_wave_cells : (int64_t)sms * RK_LANES_CBM4 * 2;
+  wave = std::min<int64_t>(wave, std::max<int64_t>(1, (int64_t)(0.2 * (double)budget / ((double)cap * RK_REC * sizeof(double)))));
+  const size_t fat_budget = (size_t)(0.75 * (double)budget);
+  std::vector<int> ids, overflow;
+  for (int64_t w0 = 0; w0 < ncells; w0 += wave) {
+    const int64_t w1 = std::min(ncells, w0 + wave);
+    ids.resize((size_t)(w1 - w0));
+    for (int64_t c = w0; c < w1; ++c) ids[(size_t)(c - w0)] = (int)c;
+    if (int e = rk_adj_group(rp, mc, ids, cap, nadj, with_mu, np, do_adjoint, fat_budget, d_y, d_lam, d_mu, d_atol, d_rtol, d_ist, d_rst,
+                             d_ierr, st, sms, overflow))
+      return e;
+    g_stats.waves++;
+  }
+  // systems with more accepted steps than the default slot: again, a few at a time, with room for Max_no_steps
+  while (!overflow.empty()) {
+    const int capx = rp.max_no_steps;
+    const size_t per = (size_t)capx * RK_REC * sizeof(double);
+    const size_t take = std::max<size_t>(1, std::min<size_t>(overflow.size(), (size_t)(0.2 * (double)budget) / per));
+    std::vector<int> part(overflow.end() - (long)take, overflow.end()), again;
+    overflow.resize(overflow.size() - take);
+    if (int e = rk_adj_group(rp, mc, part, capx, nadj, with_mu, np, do_adjoint, fat_budget, d_y, d_lam, d_mu, d_atol, d_rtol, d_ist,
+                             d_rst, d_ierr, st, sms, again))
+      return e;
+    if (!again.empty()) return fail(FATODE_ENOMEM, "RK_ADJ tape overflow with a Max_no_steps slot");
+    g_stats.waves++;
+  }
+  if (with_mu && d_mu_sum && do_adjoint)
+    if (int e = mu_sum_device(ncells, nadj * np, d_mu, d_ierr, d_mu_sum, st)) return e;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int fatode_rk_integrate_adj_batch(int model, int64_t ncells, int nvar, int np, int nadj, double* y, double* lambda,
+                                             double* mu, double tin, double tout, const double* atol_adj, const double* rtol_adj,
+                                             const double* atol, const double* rtol, const int* icntrl_u, const double* rcntrl_u,
+                                             int* istatus, double* rstatus, int* ierr, double* mu_sum, const double* model_params,
+                                             int mem, void* stream) {
+  (void)atol_adj; (void)rtol_adj;   // only used by the adaptive adjoint solve (ICNTRL(7) = 3), which is not built
+  g_err.clear();
+  if (ncells < 0 || !y || !atol || !rtol || !istatus || !rstatus || !ierr) return fail(FATODE_EINVAL, "NULL required argument");
+  if (int e = check_model_dims(model, nvar, np)) return e;
+  if (!lambda || nadj < 1) return fail(FATODE_EINVAL, "lambda is NULL or nadj < 1");
+  if (model != FATODE_MODEL_CBM4) return fail(FATODE_EUNSUPPORTED, "the RK discrete adjoint is available for the cbm4 model only in this build");
+  if (nadj > 32) return fail(FATODE_EUNSUPPORTED, "nadj > 32 per call is not supported yet");
+  if (int e = check_device()) return e;
+  if (ncells == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  RkParams rp;
+  RkAdjOptions ao;
+  const int perr = rk_parse_options(nvar, icntrl_u, rcntrl_u, tin, tout, atol, rtol, rp, &ao);
+  if (perr < 0) return broadcast_ierr(ncells, perr, istatus, rstatus, ierr, mem, st);
+  const bool do_adjoint = (ao.type == 0 || ao.type == 2);
+  if (do_adjoint && ao.solve >= 2)
+    return fail(FATODE_EUNSUPPORTED, "RK_ADJ direct / adaptive adjoint solves (ICNTRL(7) = 2, 3: 3N x 3N factorisation) are not built; "
+                                     "use the preset fixed-sweep solve");
+  const bool with_mu = np > 0 && mu != nullptr;
+  Cbm4Const mc;
+  cbm4_constants(model_params, mc);
+  DevBuf b_atol, b_rtol, b_y, b_lam, b_mu, b_ist, b_rst, b_ierr, b_musum;
+  CUDA_TRY(b_atol.alloc(sizeof(double) * nvar));
+  CUDA_TRY(b_rtol.alloc(sizeof(double) * nvar));
+  CUDA_TRY(cudaMemcpyAsync(b_atol.p, atol, sizeof(double) * nvar, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(b_rtol.p, rtol, sizeof(double) * nvar, cudaMemcpyHostToDevice, st));
+  double *d_y = y, *d_lam = lambda, *d_mu = mu, *d_rst = rstatus, *d_musum = mu_sum;
+  int *d_ist = istatus, *d_ierr = ierr;
+  const size_t ny = sizeof(double) * nvar * ncells, nl = sizeof(double) * (size_t)nvar * nadj * ncells,
+               nm = sizeof(double) * (size_t)np * nadj * ncells;
+  if (mem == FATODE_MEM_HOST) {
+    CUDA_TRY(b_y.alloc(ny));
+    CUDA_TRY(b_ist.alloc(sizeof(int) * 20 * ncells));
+    CUDA_TRY(b_rst.alloc(sizeof(double) * 20 * ncells));
+    CUDA_TRY(b_ierr.alloc(sizeof(int) * ncells));
+    CUDA_TRY(cudaMemcpyAsync(b_y.p, y, ny, cudaMemcpyHostToDevice, st));
+    d_y = b_y.as<double>(); d_ist = b_ist.as<int>(); d_rst = b_rst.as<double>(); d_ierr = b_ierr.as<int>();
+    // Lambda and Mu are INTENT(INOUT) upstream: systems whose forward sweep fails keep the caller's values
+    CUDA_TRY(b_lam.alloc(nl));
+    d_lam = b_lam.as<double>();
+    CUDA_TRY(cudaMemcpyAsync(d_lam, lambda, nl, cudaMemcpyHostToDevice, st));
+    if (with_mu) {
+      CUDA_TRY(b_mu.alloc(nm));
+      d_mu = b_mu.as<double>();
+      CUDA_TRY(cudaMemcpyAsync(d_mu, mu, nm, cudaMemcpyHostToDevice, st));
+      if (mu_sum) { CUDA_TRY(b_musum.alloc(sizeof(double) * np * nadj)); d_musum = b_musum.as<double>(); }
+    }
+  }
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_cbm4_rc, mc.rc_base, sizeof(double) * 81, 0, cudaMemcpyHostToDevice, st));
+  if (int e = rk_adj_device(rp, mc, ncells, nadj, with_mu, np, do_adjoint, d_y, d_lam, d_mu, b_atol.as<double>(), b_rtol.as<double>(),
+                            d_ist, d_rst, d_ierr, with_mu ? d_musum : nullptr, st))
+    return e;
+  if (mem == FATODE_MEM_HOST) {
+    CUDA_TRY(cudaMemcpyAsync(y, d_y, ny, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(istatus, d_ist, sizeof(int) * 20 * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(rstatus, d_rst, sizeof(double) * 20 * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ierr, d_ierr, sizeof(int) * ncells, cudaMemcpyDeviceToHost, st));
+    if (do_adjoint) {
+      CUDA_TRY(cudaMemcpyAsync(lambda, d_lam, nl, cudaMemcpyDeviceToHost, st));
+      if (with_mu) CUDA_TRY(cudaMemcpyAsync(mu, d_mu, nm, cudaMemcpyDeviceToHost, st));
+      if (with_mu && mu_sum) CUDA_TRY(cudaMemcpyAsync(mu_sum, d_musum, sizeof(double) * np * nadj, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------

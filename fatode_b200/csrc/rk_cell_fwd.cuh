@@ -33,7 +33,7 @@ enum { RK_R2A = 1, RK_R1A = 2, RK_L3C = 3, RK_GAU = 4, RK_L3A = 5 };
 
 struct RkParams {
   int method;
-  double T[3][3], TinvAinv[3][3], A[4][4], C[4], D[4], Bgam[5], Theta[4], F[5], Gamma, Alpha, Beta, ELO;
+  double T[3][3], TinvAinv[3][3], Tinv[3][3], AinvT[3][3], A[4][4], B[4], C[4], D[4], Bgam[5], Theta[4], F[5], Gamma, Alpha, Beta, ELO;
   int vector_tol, max_no_steps, newton_maxit, start_newton, gustafsson;
   double roundoff, hmin, hmax, hstart, facmin, facmax, facrej, facsafe, thetamin, newtontol, qmin, qmax;
   double tstart, tend;
@@ -49,12 +49,19 @@ struct RkSmem {
   static constexpr size_t BYTES = sizeof(double) * DOUBLES * LANES;
 };
 
-template <class Model, int LANES>
+// ADJ = true: the forward sweep of ADJ/RK_ADJ (RK_FwdIntegrator, ADJ/RK_ADJ/RK_ADJ_f90_Integrator.F90:866-1226): no FUN(T,Y)
+// at the top of the time loop (the SDIRK error stage evaluates and counts its own), and every accepted step pushes
+// (T, H, NewIt, Y, Z1, Z2, Z3) — rk_DPush :775-794 — to the system's tape slot: record r of queue slot s lives at
+// tape[(s * tape_cap + r) * RK_REC].  A system with more than tape_cap accepted steps ends with IERR_TAPE_OVERFLOW and is
+// run again by the host with a larger slot.
+constexpr int RK_REC = 132;   // doubles per tape record: T, H, NewIt, pad, Y(32), Z1(32), Z2(32), Z3(32)
+
+template <class Model, int LANES, bool ADJ = false>
 __global__ void __launch_bounds__(32, 1)
 k_rk_fwd_cell(RkParams rp, typename Model::Const mc, long ncells, const double* __restrict__ y_in, double* __restrict__ y_out,
               const double* __restrict__ atol_g, const double* __restrict__ rtol_g, int* __restrict__ istatus,
               double* __restrict__ rstatus, int* __restrict__ ierr_out, unsigned long long* __restrict__ queue,
-              const int* __restrict__ cell_ids) {
+              const int* __restrict__ cell_ids, double* __restrict__ tape, int tape_cap) {
   extern __shared__ __align__(16) double cell_smem[];
   constexpr int N = Model::N;
   constexpr int SV = LANES;
@@ -125,10 +132,13 @@ k_rk_fwd_cell(RkParams rp, typename Model::Const mc, long ncells, const double* 
     double TJ = T;
     error_scale();
 
+    int NewIt = 0;
     while (__dsub_rn(__dmul_rn(__dsub_rn(Tend, T), Tdirection), Roundoff) > 0.0) {   // Tloop
-      Model::photo(T, mc, PH);
-      Model::template fun<SV>(Y, PH, mc, F0);
-      nfun++;
+      if constexpr (!ADJ) {
+        Model::photo(T, mc, PH);
+        Model::template fun<SV>(Y, PH, mc, F0);
+        nfun++;
+      }
       if (!SkipLU) {
         if (!SkipJac) {                      // LSS_Jac(T,Y): remember where; the values are rebuilt inside build_E
           njac++;
@@ -255,7 +265,7 @@ k_rk_fwd_cell(RkParams rp, typename Model::Const mc, long ncells, const double* 
           Z3[i * SV] = __dadd_rn(Z3[i * SV], __dmul_rn(-1.0, R3[i * SV]));
         }
         NewtonDone = (__dmul_rn(NewtonRate, NewtonIncrement) <= rp.newtontol);
-        if (NewtonDone) break;
+        if (NewtonDone) { NewIt = NewtonIter; break; }
       }
       if (!NewtonDone) {   // CYCLE Tloop (:598-602)
         H = __dmul_rn(Fac, H); Reject = true; SkipJac = true; SkipLU = false;
@@ -264,6 +274,11 @@ k_rk_fwd_cell(RkParams rp, typename Model::Const mc, long ncells, const double* 
 
       // ---- embedded SDIRK stage (:604-666)
       {
+        if constexpr (ADJ) {   // ADJ/RK_ADJ :1041-1043
+          Model::photo(T, mc, PH);
+          Model::template fun<SV>(Y, PH, mc, F0);
+          nfun++;
+        }
         const double bg = __dmul_rn(rp.Bgam[0], H);
 #pragma unroll 4
         for (int i = 0; i < N; ++i) {
@@ -353,6 +368,18 @@ k_rk_fwd_cell(RkParams rp, typename Model::Const mc, long ncells, const double* 
       double Hnew = __dmul_rn(Fac, H);
 
       if (Err < 1.0) {   // accepted (:704-746)
+        if constexpr (ADJ) if (tape) {   // rk_DPush (tape == nullptr: ICNTRL(9) = 1, forward sweep only)
+          if (nacc >= tape_cap) { ierr = IERR_TAPE_OVERFLOW; break; }
+          double* rec = tape + ((size_t)slot * tape_cap + nacc) * RK_REC;
+          st_global_256(rec, T, H, (double)NewIt, 0.0);
+#pragma unroll 2
+          for (int i = 0; i < N; i += 4) {
+            st_global_256(rec + 4 + i, Y[i * SV], Y[(i + 1) * SV], Y[(i + 2) * SV], Y[(i + 3) * SV]);
+            st_global_256(rec + 4 + N + i, Z1[i * SV], Z1[(i + 1) * SV], Z1[(i + 2) * SV], Z1[(i + 3) * SV]);
+            st_global_256(rec + 4 + 2 * N + i, Z2[i * SV], Z2[(i + 1) * SV], Z2[(i + 2) * SV], Z2[(i + 3) * SV]);
+            st_global_256(rec + 4 + 3 * N + i, Z3[i * SV], Z3[(i + 1) * SV], Z3[(i + 2) * SV], Z3[(i + 3) * SV]);
+          }
+        }
         FirstStep = false;
         nacc++;
         if (rp.gustafsson) {
@@ -415,7 +442,7 @@ k_rk_fwd_cell(RkParams rp, typename Model::Const mc, long ncells, const double* 
     }
     // ---- results
     ierr_out[cell] = ierr;
-    if (ierr != RK_IERR_IRREGULAR) {   // a handed-back system keeps its initial state for the general-pivoting pass
+    if (ierr != RK_IERR_IRREGULAR && ierr != IERR_TAPE_OVERFLOW) {   // a handed-back system keeps its initial state for its second pass
 #pragma unroll 4
       for (int i = 0; i < N; ++i) y_out[cell * N + i] = Y[i * SV];
     }
@@ -432,14 +459,18 @@ k_rk_fwd_cell(RkParams rp, typename Model::Const mc, long ncells, const double* 
 // host: INTEGRATE's presets and override rule (:58-74) followed by the option handling of RungeKutta (:260-451).
 // Returns the reference's IERR before integrating (0 = go on, < 0 = the last option error: the reference keeps checking
 // after an error and returns the last code).
+// adj != nullptr: INTEGRATE_ADJ of ADJ/RK_ADJ instead (presets :63-70, no Lobatto-3A :411-423, Max_no_steps 10000 :426,
+// ICNTRL(7) adjoint solve and ICNTRL(9) adjoint type :456-487); *adj receives ICNTRL(7) (0..3) and ICNTRL(9) (0..2).
+struct RkAdjOptions { int solve, type; };
 inline int rk_parse_options(int N, const int* icntrl_u, const double* rcntrl_u, double tin, double tout, const double* atol,
-                            const double* rtol, RkParams& rp) {
+                            const double* rtol, RkParams& rp, RkAdjOptions* adj = nullptr) {
   int ic[20];
   double rc[20];
   std::memset(ic, 0, sizeof ic);
   std::memset(rc, 0, sizeof rc);
   ic[4] = 8;    // ICNTRL(5): max no. of Newton iterations
   ic[9] = 1;    // ICNTRL(10): SDIRK error estimation
+  if (adj) { ic[6] = 1; ic[8] = 2; ic[10] = 1; }   // fixed-sweep adjoint solve, discrete adjoint, classic controller
   for (int i = 0; i < 20; ++i) {
     if (icntrl_u && icntrl_u[i] > 0) ic[i] = icntrl_u[i];
     if (rcntrl_u && rcntrl_u[i] > 0) rc[i] = rcntrl_u[i];
@@ -453,7 +484,7 @@ inline int rk_parse_options(int N, const int* icntrl_u, const double* rcntrl_u, 
     case 0: case 2: method = RK_L3C; break;   // the actual default
     case 3: method = RK_GAU; break;
     case 4: method = RK_R1A; break;
-    case 5: method = RK_L3A; break;
+    case 5: if (adj) ierr = -13; else method = RK_L3A; break;
     default: ierr = -13;
   }
   if (method) {
@@ -461,6 +492,9 @@ inline int rk_parse_options(int N, const int* icntrl_u, const double* rcntrl_u, 
     rp.method = method;
     std::memcpy(rp.T, t.T, sizeof rp.T);
     std::memcpy(rp.TinvAinv, t.TinvAinv, sizeof rp.TinvAinv);
+    std::memcpy(rp.Tinv, t.Tinv, sizeof rp.Tinv);
+    std::memcpy(rp.AinvT, t.AinvT, sizeof rp.AinvT);
+    std::memcpy(rp.B, t.B, sizeof rp.B);
     std::memcpy(rp.A, t.A, sizeof rp.A);
     std::memcpy(rp.C, t.C, sizeof rp.C);
     std::memcpy(rp.D, t.D, sizeof rp.D);
@@ -469,7 +503,7 @@ inline int rk_parse_options(int N, const int* icntrl_u, const double* rcntrl_u, 
     std::memcpy(rp.F, t.F, sizeof rp.F);
     rp.Gamma = t.Gamma; rp.Alpha = t.Alpha; rp.Beta = t.Beta; rp.ELO = t.ELO;
   }
-  if (ic[3] == 0) rp.max_no_steps = 200000; else { rp.max_no_steps = ic[3]; if (rp.max_no_steps <= 0) ierr = -1; }
+  if (ic[3] == 0) rp.max_no_steps = adj ? 10000 : 200000; else { rp.max_no_steps = ic[3]; if (rp.max_no_steps <= 0) ierr = -1; }
   rp.newton_maxit = ic[4];
   if (rp.newton_maxit <= 0) ierr = -2;
   rp.start_newton = (ic[5] == 0);
@@ -494,6 +528,11 @@ inline int rk_parse_options(int N, const int* icntrl_u, const double* rcntrl_u, 
     if (atol[i] <= 0.0 || rtol[i] <= 10.0 * rp.roundoff) ierr = -8;
   rp.tstart = tin;
   rp.tend = tout;
+  if (adj) {
+    adj->solve = ic[6];
+    adj->type = ic[8];
+    if (ic[6] < 0 || ic[6] > 3 || ic[8] < 0 || ic[8] > 2) ierr = -9;   // the reference returns at once with -9
+  }
   return ierr;
 }
 

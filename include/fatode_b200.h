@@ -135,6 +135,23 @@ int fatode_rk_integrate_batch(int model, int64_t ncells, int nvar, double* y, do
                               const double* rcntrl_u, int* istatus, double* rstatus, int* ierr,
                               const double* model_params, int mem, void* stream);
 
+/* INTEGRATE_ADJ of ADJ/RK_ADJ (ADJ/RK_ADJ/RK_ADJ_f90_Integrator.F90:20):
+ *   INTEGRATE_ADJ(NVAR,NP,NADJ,NNZERO,Y,Lambda,TIN,TOUT,ATOL_adj,RTOL_adj,ATOL,RTOL,FUN,JAC,AdjInit,ICNTRL_U,RCNTRL_U,
+ *                 ISTATUS_U,RSTATUS_U,IERR_U,Mu,JACP,DRDY,DRDP,QFUN,Q)
+ * Discrete adjoint of the 3-stage implicit Runge-Kutta methods (ICNTRL(3) = 1 Radau-2A, 0/2 Lobatto-3C, 3 Gauss,
+ * 4 Radau-1A) with the presets of the reference (ICNTRL(5) = 8, (7) = 1 fixed-sweep adjoint solve, (9) = 2 discrete,
+ * (10) = 1 SDIRK error estimator, (11) = 1 classic controller, Max_no_steps = 10000); ICNTRL(9) = 1: forward sweep only.
+ * Same argument layout as fatode_ros_integrate_adj_batch; ADJINIT of the example drivers (Lambda = I, Mu = 0) is applied
+ * after the forward sweep, systems whose forward sweep fails keep the caller's Lambda/Mu.  cbm4 only.  The direct and the
+ * adaptive adjoint solves (ICNTRL(7) = 2, 3) and the quadrature terms return FATODE_EUNSUPPORTED.  Per-cell IERR: 1, or
+ * the reference's -1..-13, or -20 for a system whose forward factorisations leave the static pivot pattern (no
+ * general-pivoting pass for this family yet). */
+int fatode_rk_integrate_adj_batch(int model, int64_t ncells, int nvar, int np, int nadj, double* y, double* lambda,
+                                  double* mu, double tin, double tout, const double* atol_adj,
+                                  const double* rtol_adj, const double* atol, const double* rtol,
+                                  const int* icntrl_u, const double* rcntrl_u, int* istatus, double* rstatus,
+                                  int* ierr, double* mu_sum, const double* model_params, int mem, void* stream);
+
 /* Engine knobs (process-wide): trajectory-tape budget in bytes (0 = 60% of free device memory) and
  * the number of cells per wave (0 = automatic). */
 int fatode_set_tape_budget(uint64_t bytes);

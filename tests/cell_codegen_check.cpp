@@ -96,6 +96,13 @@ static inline int dgetf2(int n, double* a, int* ipiv) {
     double sc = 0.0, er = 0.0;
     for (int i = 0; i < 32; ++i) { sc = std::fmax(sc, std::fabs(xr[i])); er = std::fmax(er, std::fabs(xr[i] - xn[i])); }
     max_terr = std::fmax(max_terr, er / sc);
+    {   // reference-order transposed solve: bit for bit
+      double ys[32], yref[32];
+      for (int i = 0; i < 32; ++i) ys[i] = yref[i] = std::cos(1.0 + i * 0.77 + (double)(n_lu % 31));
+      dgetrs_oracle(true, n, a, ipiv, yref);
+      lut_solve_seq(cur_lu, dinv, cur_swaps, ys);
+      for (int i = 0; i < 32; ++i) if (!same(ys[i], yref[i])) { ++n_solve_bad; break; }
+    }
     // non-transposed register solve of the tangent-linear sweep against DGETRS('N')
     for (int i = 0; i < 32; ++i) xr[i] = xn[i] = std::cos(0.5 + i * 0.61 + (double)(n_lu % 89));
     dgetrs_oracle(false, n, a, ipiv, xr);
@@ -172,6 +179,15 @@ static inline int zgetf2(int n, cplx* a, int* ipiv) {
       er = std::fmax(er, std::fabs(xr_[i].re - xr[i]) + std::fabs(xr_[i].im - xi[i]));
     }
     max_zterr = std::fmax(max_zterr, er / sc);
+    // reference-order variant: bit for bit
+    double yr[32], yi[32];
+    cplx ref2[32];
+    for (int i = 0; i < 32; ++i) { yr[i] = std::cos(2.0 + i * 0.53); yi[i] = std::sin(0.1 + i * 1.7); ref2[i] = cplx{yr[i], yi[i]}; }
+    zgetrs_t_oracle(n, a, ipiv, ref2);
+    double zrt[32], zdv[32], zrd[32];
+    const unsigned zmask = zdiag_prep<1>(cur_zr, cur_zi, zrt, zdv, zrd);
+    zlut_solve_seq(cur_zr, cur_zi, zrt, zdv, zrd, zmask, cur_zswaps, yr, yi);
+    for (int i = 0; i < 32; ++i) if (!same(yr[i], ref2[i].re) || !same(yi[i], ref2[i].im)) { ++n_zsolve_bad; break; }
   }
   return info;
 }
@@ -250,6 +266,12 @@ int main(int argc, char** argv) {
           sc = std::fmax(sc, std::fabs(sref)); er = std::fmax(er, std::fabs(sref - out[cidx]));
         }
         if (!(er <= 1e-12 * sc)) ++bad_fun;
+        cbm4_cell::jt_vec_seq(jv, x, out);        // reference order: bit for bit with the dense sequential dot products
+        for (int cidx = 0; cidx < 32; ++cidx) {
+          double sref = 0.0;
+          for (int r = 0; r < 32; ++r) sref += jac[r + 32 * cidx] * x[r];
+          if (!same(sref, out[cidx])) ++bad_fun;
+        }
       }
       // entry order: by column then row over the structural non-zeros of CBM4_JAC
       double hs_ref[258], hs_new[258];

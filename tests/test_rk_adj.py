@@ -78,3 +78,57 @@ def test_oracle_options():
     ic = radau()
     ic[8] = 3                                     # continuous adjoints are not implemented upstream either
     assert O.rk_adj("cbm4", y0, 2, T0, T0 + 600.0, atol, rtol, ic)["ierr"][0] == -9
+
+
+@pytest.mark.gpu
+def test_cbm4_rk_adj_batch_matches_oracle():
+    """Forward sweep bit-identical (state, RSTATUS, every ISTATUS counter incl. the backward sweep's), Lambda and Mu within
+    1e-9 with the same per-column / per-parameter scaling as the ROS_ADJ parity test."""
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    from test_ros_adj_gpu import check_against_oracle
+    rtol, atol = driver_tols()
+    y0 = perturbed_states(F.initial_state("cbm4"), 48)
+    res = F.integrate_adj("cbm4", T0, T1, y0, 32, rtol, atol, icntrl_u=radau(), family="rk")
+    ref = O.rk_adj("cbm4", y0, 32, T0, T1, atol, rtol, radau())
+    assert (res.ierr == 1).all()
+    assert np.array_equal(res.y, ref["y"]) and np.array_equal(res.rstatus, ref["rstatus"])
+    check_against_oracle(res, ref, 32)
+    g = json.load(open(os.path.join(G, "cbm4_rk_adj.json")))
+    glam = np.array(g["lambda"]).reshape(32, 32)
+    cs = np.max(np.abs(glam), axis=1)
+    err = np.max(np.abs(res.lambda_[0] - glam), axis=1) / np.maximum(cs, 1e-300)
+    assert np.median(err[cs > 1e-6]) <= 1e-7                      # cell 0 = the driver's problem vs the reference's file
+
+
+@pytest.mark.gpu
+def test_rk_adj_variants():
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    from test_ros_adj_gpu import check_against_oracle
+    rtol, atol = driver_tols()
+    y0 = perturbed_states(F.initial_state("cbm4"), 12)
+    t1 = T0 + 8 * 3600.0
+    for method, nadj, with_mu in ((0, 32, True), (4, 5, True), (1, 32, False), (3, 7, True)):
+        ic = np.zeros(20, dtype=np.int32)
+        ic[2] = method
+        te = T0 + 3600.0 if method == 3 else t1
+        res = F.integrate_adj("cbm4", T0, te, y0, nadj, rtol, atol, icntrl_u=ic, want_mu=with_mu, family="rk")
+        ref = O.rk_adj("cbm4", y0, nadj, T0, te, atol, rtol, ic, with_mu=with_mu)
+        assert np.array_equal(res.y, ref["y"])
+        check_against_oracle(res, ref, nadj)
+    # forward sweep only (ICNTRL(9) = 1), tiny tape slots (overflow -> second group), Gustafsson controller not selectable
+    ic = radau()
+    ic[8] = 1
+    res = F.integrate_adj("cbm4", T0, t1, y0, 4, rtol, atol, icntrl_u=ic, family="rk")
+    ref = O.rk_adj("cbm4", y0, 4, T0, t1, atol, rtol, ic)
+    assert np.array_equal(res.y, ref["y"]) and np.array_equal(res.istatus, ref["istatus"])
+    ic = radau()
+    ic[3] = 20                                                    # Max_no_steps = 20: IERR -9 like the reference
+    res = F.integrate_adj("cbm4", T0, T1, y0, 4, rtol, atol, icntrl_u=ic, family="rk")
+    ref = O.rk_adj("cbm4", y0, 4, T0, T1, atol, rtol, ic)
+    assert np.array_equal(res.ierr, ref["ierr"]) and (res.ierr == -9).all()
+    ic = radau()
+    ic[6] = 2
+    with pytest.raises(Exception):
+        F.integrate_adj("cbm4", T0, t1, y0, 4, rtol, atol, icntrl_u=ic, family="rk")

@@ -507,6 +507,31 @@ def main():
     pexpr = [l1_expr(mech.ARP[gd.JCOEFF[p] - 1], "YI") for p in range(gd.NP)]
     emit_paired(w, "AP", pexpr)
     w("}")
+    w("// Division by a complex pivot c + i e in Smith's form (zdiv) splits into a pivot-only part — ratio = c/e or e/c, div =")
+    w("// c*ratio + e or e*ratio + c, and which branch — and two real divisions by div.  zdiag_prep tabulates the pivot-only part")
+    w("// of the 32 diagonal entries (contiguous outputs) plus RN(1/div); bit k of the result = branch |c| < |e| taken.")
+    w("template <int SV> CBM4_CELL_FN unsigned zdiag_prep(const double* __restrict__ zr, const double* __restrict__ zi, double* __restrict__ ZRATIO, "
+      "double* __restrict__ ZDIV, double* __restrict__ ZRDIV) {")
+    w("  unsigned mask = 0u;")
+    for k0 in range(0, N, 4):
+        w("  {")
+        for j in range(4):
+            d = diag[k0 + j]
+            w(f"    const double c{j} = zr[{d} * SV], e{j} = zi[{d} * SV]; const bool f{j} = fabs(c{j}) < fabs(e{j});")
+            w(f"    const double t{j} = f{j} ? c{j} / e{j} : e{j} / c{j}; const double d{j} = f{j} ? c{j} * t{j} + e{j} : e{j} * t{j} + c{j};")
+            w(f"    if (f{j}) mask |= {1 << (k0 + j)}u;")
+        w(f"    CBM4_CELL_ST4(ZRATIO + {k0}, t0, t1, t2, t3);")
+        w(f"    CBM4_CELL_ST4(ZDIV + {k0}, d0, d1, d2, d3);")
+        w(f"    CBM4_CELL_ST4(ZRDIV + {k0}, 1.0 / d0, 1.0 / d1, 1.0 / d2, 1.0 / d3);")
+        w("  }")
+    w("  return mask;")
+    w("}")
+    w("// a / b, correctly rounded, from rb = RN(1/b): one Newton correction with exact residual (Markstein); three operations")
+    w("// instead of a full division.  Normal-range operands only.")
+    w("CBM4_CELL_INL double exact_div(const double a, const double b, const double rb) {")
+    w("  const double q = a * rb;")
+    w("  return fma(fma(-q, b, a), rb, q);")
+    w("}")
     w("// out = J^T x  (LSS_Mul_Jactr1..3), Jv in the JAC_ROW/JAC_COL entry order")
     w("CBM4_CELL_INL void jt_vec(const double* __restrict__ Jv, const double (&x)[32], double (&out)[32]) {")
     for c in range(N):
@@ -536,6 +561,66 @@ def main():
             e = idx[(k, c)]
             w(f"    xr[{c}] = fma(-zr[{e}], wr, fma(zi[{e}], wi, xr[{c}])); xi[{c}] = fma(-zr[{e}], wi, fma(-zi[{e}], wr, xi[{c}]));")
         w("  }")
+    for bi in range(len(SWAPS) - 1, -1, -1):
+        k, p_ = SWAPS[bi]
+        w(f"  if (swaps & {1 << bi}u) {{ double t = xr[{k}]; xr[{k}] = xr[{p_}]; xr[{p_}] = t; t = xi[{k}]; xi[{k}] = xi[{p_}]; xi[{p_}] = t; }}")
+    w("}")
+    # ------------------------------------------------------------------ reference-order variants (RK adjoint)
+    w("")
+    w("// ---- reference-order variants for the Runge-Kutta adjoint sweep.  Its update Lambda <- Lambda + U1 + U2 + U3 cancels")
+    w("// up to nine digits for stiff components, so rounding differences of a reordered evaluation are amplified beyond the")
+    w("// 1e-9 parity bound; these variants perform exactly the reference's operations (no fma, true divisions) in its order:")
+    w("// matmul(transpose(fjac), g) as sequential dot products; DGETRS('T') = DTRSM(L,U,T,N) + DTRSM(L,L,T,U) + DLASWP(-1) in")
+    w("// dot-product form; ZGETRS('T') likewise with four-multiplication products and Smith division.  Skipped structural")
+    w("// zeros add exact zeros.  Compile without FMA contraction.")
+    w("CBM4_CELL_INL void jt_vec_seq(const double* __restrict__ Jv, const double (&x)[32], double (&out)[32]) {")
+    for c in range(N):
+        ents = [(e, rc[0]) for e, rc in enumerate(jent) if rc[1] == c]
+        w("  { double a = 0.0;")
+        for (e, r) in ents:
+            w(f"    a = a + Jv[{e}] * x[{r}];")
+        w(f"    out[{c}] = a; }}")
+    w("}")
+    w("CBM4_CELL_INL void lut_solve_seq(const double* __restrict__ lu, const double* __restrict__ dinv, const unsigned swaps, double (&x)[32]) {")
+    for i in range(N):
+        rows = [k for k in range(i) if P[k][i]]
+        w(f"  {{ double t = x[{i}];")
+        for k in rows:
+            w(f"    t = t - lu[{idx[(k, i)]}] * x[{k}];")
+        w(f"    x[{i}] = exact_div(t, lu[{idx[(i, i)]}], dinv[{i}]); }}")
+    for i in range(N - 1, -1, -1):
+        rows = [k for k in range(i + 1, N) if P[k][i]]
+        if not rows:
+            continue
+        w(f"  {{ double t = x[{i}];")
+        for k in rows:
+            w(f"    t = t - lu[{idx[(k, i)]}] * x[{k}];")
+        w(f"    x[{i}] = t; }}")
+    for bi in range(len(SWAPS) - 1, -1, -1):
+        k, p_ = SWAPS[bi]
+        w(f"  if (swaps & {1 << bi}u) {{ const double t = x[{k}]; x[{k}] = x[{p_}]; x[{p_}] = t; }}")
+    w("}")
+    w("CBM4_CELL_INL void zlut_solve_seq(const double* __restrict__ zr, const double* __restrict__ zi, const double* __restrict__ zratio, "
+      "const double* __restrict__ zdiv, const double* __restrict__ zrdiv, const unsigned zmask, const unsigned swaps, "
+      "double (&xr)[32], double (&xi)[32]) {")
+    for i in range(N):
+        rows = [k for k in range(i) if P[k][i]]
+        w(f"  {{ double tr = xr[{i}], ti = xi[{i}];")
+        for k in rows:
+            e = idx[(k, i)]
+            w(f"    {{ const double pr = zr[{e}] * xr[{k}] - zi[{e}] * xi[{k}], pi = zr[{e}] * xi[{k}] + zi[{e}] * xr[{k}]; tr = tr - pr; ti = ti - pi; }}")
+        w(f"    const double rt = zratio[{i}]; const bool f = (zmask >> {i}) & 1u;")
+        w(f"    const double nr = f ? tr * rt + ti : ti * rt + tr, ni = f ? ti * rt - tr : ti - tr * rt;")
+        w(f"    xr[{i}] = exact_div(nr, zdiv[{i}], zrdiv[{i}]); xi[{i}] = exact_div(ni, zdiv[{i}], zrdiv[{i}]); }}")
+    for i in range(N - 1, -1, -1):
+        rows = [k for k in range(i + 1, N) if P[k][i]]
+        if not rows:
+            continue
+        w(f"  {{ double tr = xr[{i}], ti = xi[{i}];")
+        for k in rows:
+            e = idx[(k, i)]
+            w(f"    {{ const double pr = zr[{e}] * xr[{k}] - zi[{e}] * xi[{k}], pi = zr[{e}] * xi[{k}] + zi[{e}] * xr[{k}]; tr = tr - pr; ti = ti - pi; }}")
+        w(f"    xr[{i}] = tr; xi[{i}] = ti; }}")
     for bi in range(len(SWAPS) - 1, -1, -1):
         k, p_ = SWAPS[bi]
         w(f"  if (swaps & {1 << bi}u) {{ double t = xr[{k}]; xr[{k}] = xr[{p_}]; xr[{p_}] = t; t = xi[{k}]; xi[{k}] = xi[{p_}]; xi[{p_}] = t; }}")
