@@ -231,6 +231,17 @@ def run_side_workload(args):
         cpu = lambda y: O.ros_tlm("cbm4", y, np.broadcast_to(eye, (y.shape[0], 32, 32)).copy(), T0, T1, atol, rtol, ic)
         desc = "EXAMPLES/cbm4 TLM/ROS_TLM: Rodas4, NTLM=32, Y_tlm(t0)=I, ICNTRL(12)=0, 12h..84h, driver tolerances of ROS_ADJ"
         ncpu = 32
+    elif w == "cbm4_rk_adj":
+        nc = args.cells if args.cells != 131072 else 9472
+        rtol, atol = np.full(N, F01 * 1.0e-5), np.full(N, F01 * 1.0e-7)
+        ic = np.zeros(20, dtype=np.int32)
+        ic[2] = 1
+        y0 = perturbed_states(F.initial_state("cbm4"), nc)
+        run = lambda y: F.integrate_adj("cbm4", T0, T1, y, 32, rtol, atol, icntrl_u=ic, family="rk")
+        cpu = lambda y: O.rk_adj("cbm4", y, 32, T0, T1, atol, rtol, ic)
+        desc = ("EXAMPLES/cbm4 ADJ/RK_ADJ: Radau-2A (ICNTRL(3)=1), NADJ=32, NP=29, fixed-sweep discrete adjoint, 12h..84h, "
+                "rtol 0.1f*1e-5, atol 0.1f*1e-7 (cbm4_rk_adj_dr.F90)")
+        ncpu = 32
     elif w == "cbm4_rk":
         nc = args.cells if args.cells != 131072 else 18944
         rtol, atol = np.full(N, F01 * 1.0e-5), np.full(N, F01 * 1.0e-7)
@@ -285,7 +296,7 @@ def main():
     ap.add_argument("--impl", default="fatode_b200", choices=["fatode_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="cbm4_ros_adj", choices=["cbm4_ros_adj", "small_strato_fwd", "cbm4_ros_tlm", "cbm4_sdirk", "cbm4_rk"],
+    ap.add_argument("--workload", default="cbm4_ros_adj", choices=["cbm4_ros_adj", "small_strato_fwd", "cbm4_ros_tlm", "cbm4_sdirk", "cbm4_rk", "cbm4_rk_adj"],
                     help="cbm4_ros_adj = the headline metric (default); the others are side measurements of the other "
                          "BASELINE configs / entry points (single GPU, one JSON line each, not the driver's metric)")
     args = ap.parse_args()

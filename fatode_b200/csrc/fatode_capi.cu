@@ -1385,6 +1385,8 @@ extern "C" int fatode_rk_integrate_batch(int model, int64_t ncells, int nvar, do
 // ADJ/RK_ADJ INTEGRATE_ADJ for CBM-IV: taping forward sweep (one system per thread), per-step preparation (one thread per
 // accepted step), backward sweep (one warp per system, lane = adjoint column).  rk_cell_adj.cuh.
 static thread_local CachedBuf g_rk_tape, g_rk_fat, g_rk_idx, g_rk_stat;
+static int g_rk_tape_slot = 0;   // accepted steps per system in the first pass (0 = 1024)
+extern "C" int fatode_set_rk_tape_slot(int steps) { g_rk_tape_slot = steps; return 0; }
 static void release_rk_workspace() { g_rk_tape.release(); g_rk_fat.release(); g_rk_idx.release(); g_rk_stat.release(); }
 
 __global__ void k_rk_gather_status(int n, const int* __restrict__ ids, const int* __restrict__ ierr, const int* __restrict__ istatus,
@@ -1486,7 +1488,7 @@ static int rk_adj_device(const RkParams& rp, const Cbm4Const& mc, int64_t ncells
   CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
   free_b += g_rk_tape.cap + g_rk_fat.cap;
   const size_t budget = g_tape_budget ? (size_t)g_tape_budget : (size_t)(0.6 * (double)free_b);
-  const int cap = std::min(rp.max_no_steps, 1024);
+  const int cap = std::min(rp.max_no_steps, g_rk_tape_slot > 0 ? g_rk_tape_slot : 1024);
   int64_t wave = g_wave_cells > 0 ? g_wave_cells : (int64_t)sms * RK_LANES_CBM4 * 2;
   wave = std::min<int64_t>(wave, std::max<int64_t>(1, (int64_t)(0.2 * (double)budget / ((double)cap * RK_REC * sizeof(double)))));
   const size_t fat_budget = (size_t)(0.75 * (double)budget);

@@ -9,6 +9,7 @@
 !     MODULE ROS_tlm_f90_Integrator :: INTEGRATE_TLM   (TLM/ROS_TLM/ROS_TLM_f90_Integrator.F90:35)
 !     MODULE SDIRK_f90_Integrator   :: INTEGRATE       (FWD/SDIRK/SDIRK_f90_Integrator.F90:25)   after fatode_b200_set_family(FATODE_FAMILY_SDIRK)
 !     MODULE RK_f90_Integrator      :: INTEGRATE       (FWD/RK/RK_f90_Integrator.F90:32)         after fatode_b200_set_family(FATODE_FAMILY_RK)
+!     MODULE RK_adj_f90_Integrator  :: INTEGRATE_ADJ   (ADJ/RK_ADJ/RK_ADJ_f90_Integrator.F90:20) after fatode_b200_set_family(FATODE_FAMILY_RK)
 !  (upstream the forward families are separate modules that all export INTEGRATE with the same argument list; the
 !  application picks one with its USE line, here with fatode_b200_set_family)
 !  Dummy-argument names and order are the reference's, so keyword calls such as
@@ -85,6 +86,19 @@ MODULE fatode_b200_mod
       INTEGER(C_INT) :: istatus(*), ierr(*)
       INTEGER(C_INT) :: fatode_ros_integrate_adj_batch
     END FUNCTION
+    FUNCTION fatode_rk_integrate_adj_batch(model, ncells, nvar, np, nadj, y, lambda, mu, tin, tout, atol_adj, rtol_adj, &
+                                            atol, rtol, icntrl_u, rcntrl_u, istatus, rstatus, ierr, mu_sum, model_params, &
+                                            mem, stream) BIND(C, NAME='fatode_rk_integrate_adj_batch')
+      IMPORT :: C_INT, C_INT64_T, C_DOUBLE, C_PTR
+      INTEGER(C_INT), VALUE :: model, nvar, np, nadj, mem
+      INTEGER(C_INT64_T), VALUE :: ncells
+      REAL(C_DOUBLE), VALUE :: tin, tout
+      REAL(C_DOUBLE) :: y(*), lambda(*), rstatus(*)
+      TYPE(C_PTR), VALUE :: mu, atol_adj, rtol_adj, icntrl_u, rcntrl_u, mu_sum, model_params, stream
+      REAL(C_DOUBLE), INTENT(IN) :: atol(*), rtol(*)
+      INTEGER(C_INT) :: istatus(*), ierr(*)
+      INTEGER(C_INT) :: fatode_rk_integrate_adj_batch
+    END FUNCTION
     FUNCTION fatode_ros_integrate_tlm_batch(model, ncells, nvar, ntlm, y, y_tlm, tin, tout, atol_tlm, rtol_tlm, atol, rtol, &
                                             icntrl_u, rcntrl_u, istatus, rstatus, ierr, model_params, mem, stream) &
                                             BIND(C, NAME='fatode_ros_integrate_tlm_batch')
@@ -147,9 +161,13 @@ CONTAINS
   END SUBROUTINE INTEGRATE
 
   !~~~> ADJ/ROS_ADJ INTEGRATE_ADJ, one system (ADJ/ROS_ADJ/ROS_ADJ_f90_Integrator.F90:34-37)
+  !     With fatode_b200_set_family(FATODE_FAMILY_RK) the same routine stands in for ADJ/RK_ADJ's INTEGRATE_ADJ
+  !     (ADJ/RK_ADJ/RK_ADJ_f90_Integrator.F90:20-23): its dummy arguments are a subset of these names (no Hessian
+  !     callbacks, plus IERR_U), so the keyword call of cbm4_rk_adj_dr.F90:231-235 compiles unchanged; only the positional
+  !     order differs upstream.
   SUBROUTINE INTEGRATE_ADJ( NVAR, NP, NADJ, NNZERO, Y, Lambda, Mu, TIN, TOUT, ATOL_adj, RTOL_adj, ATOL, RTOL, FUN, JAC, &
                             ADJINIT, HESSTR_VEC, JACP, DRDY, DRDP, HESSTR_VEC_F_PY, HESSTR_VEC_R_PY, HESSTR_VEC_R, &
-                            ICNTRL_U, RCNTRL_U, ISTATUS_U, RSTATUS_U, Q, QFUN )
+                            ICNTRL_U, RCNTRL_U, ISTATUS_U, RSTATUS_U, Q, QFUN, IERR_U )
     INTEGER, INTENT(IN) :: NVAR, NNZERO, NP, NADJ
     DOUBLE PRECISION, INTENT(INOUT) :: Y(NVAR), Lambda(NVAR,NADJ)
     DOUBLE PRECISION, INTENT(INOUT), OPTIONAL, TARGET :: Mu(NP,NADJ)
@@ -157,11 +175,11 @@ CONTAINS
     DOUBLE PRECISION, INTENT(IN) :: TIN, TOUT, ATOL_adj(NVAR,NADJ), RTOL_adj(NVAR,NADJ), ATOL(NVAR), RTOL(NVAR)
     INTEGER, INTENT(IN), OPTIONAL, TARGET :: ICNTRL_U(20)
     DOUBLE PRECISION, INTENT(IN), OPTIONAL, TARGET :: RCNTRL_U(20)
-    INTEGER, INTENT(OUT), OPTIONAL :: ISTATUS_U(20)
+    INTEGER, INTENT(OUT), OPTIONAL :: ISTATUS_U(20), IERR_U
     DOUBLE PRECISION, INTENT(OUT), OPTIONAL :: RSTATUS_U(20)
     EXTERNAL FUN, JAC, ADJINIT, HESSTR_VEC
     EXTERNAL QFUN, JACP, DRDY, DRDP, HESSTR_VEC_F_PY, HESSTR_VEC_R_PY, HESSTR_VEC_R
-    OPTIONAL QFUN, JACP, DRDY, DRDP, HESSTR_VEC_F_PY, HESSTR_VEC_R_PY, HESSTR_VEC_R
+    OPTIONAL HESSTR_VEC, QFUN, JACP, DRDY, DRDP, HESSTR_VEC_F_PY, HESSTR_VEC_R_PY, HESSTR_VEC_R
     INTEGER(C_INT) :: ist(20), ierr(1), rc, npc
     REAL(C_DOUBLE) :: rst(20)
     TYPE(C_PTR) :: pic, prc, pmu
@@ -169,7 +187,7 @@ CONTAINS
     IF (PRESENT(ICNTRL_U)) pic = C_LOC(ICNTRL_U)
     IF (PRESENT(RCNTRL_U)) prc = C_LOC(RCNTRL_U)
     ! mode selection of the reference (:100-144): Mu is propagated only with NP>0, Mu, JACP and HESSTR_VEC_F_PY present
-    IF (NP > 0 .AND. PRESENT(Mu) .AND. PRESENT(JACP) .AND. PRESENT(HESSTR_VEC_F_PY)) THEN
+    IF (NP > 0 .AND. PRESENT(Mu) .AND. PRESENT(JACP) .AND. (PRESENT(HESSTR_VEC_F_PY) .OR. current_family == FATODE_FAMILY_RK)) THEN
       pmu = C_LOC(Mu); npc = INT(NP, C_INT)
     END IF
     IF (PRESENT(Q) .AND. PRESENT(QFUN)) THEN
@@ -177,11 +195,20 @@ CONTAINS
       IF (PRESENT(ISTATUS_U)) ISTATUS_U(:) = 0
       RETURN
     END IF
-    rc = fatode_ros_integrate_adj_batch(current_model, 1_C_INT64_T, INT(NVAR, C_INT), npc, INT(NADJ, C_INT), Y, Lambda, pmu, &
-                                        TIN, TOUT, C_NULL_PTR, C_NULL_PTR, ATOL, RTOL, pic, prc, ist, rst, ierr, &
-                                        C_NULL_PTR, C_NULL_PTR, FATODE_MEM_HOST, C_NULL_PTR)
-    IF (rc /= 0) ierr(1) = rc
-    IF (ierr(1) < 0) PRINT *, 'RosenbrockADJ: Unsucessful step at T=', TIN, ' (IERR=', ierr(1), ')'   ! as :146-148
+    IF (current_family == FATODE_FAMILY_RK) THEN
+      rc = fatode_rk_integrate_adj_batch(current_model, 1_C_INT64_T, INT(NVAR, C_INT), npc, INT(NADJ, C_INT), Y, Lambda, pmu, &
+                                         TIN, TOUT, C_NULL_PTR, C_NULL_PTR, ATOL, RTOL, pic, prc, ist, rst, ierr, &
+                                         C_NULL_PTR, C_NULL_PTR, FATODE_MEM_HOST, C_NULL_PTR)
+      IF (rc /= 0) ierr(1) = rc
+      IF (ierr(1) < 0) PRINT *, 'Runge-Kutta-ADJ: Unsuccessful exit at T=', TIN, ' (IERR=', ierr(1), ')'   ! RK_ADJ :135-137
+    ELSE
+      rc = fatode_ros_integrate_adj_batch(current_model, 1_C_INT64_T, INT(NVAR, C_INT), npc, INT(NADJ, C_INT), Y, Lambda, pmu, &
+                                          TIN, TOUT, C_NULL_PTR, C_NULL_PTR, ATOL, RTOL, pic, prc, ist, rst, ierr, &
+                                          C_NULL_PTR, C_NULL_PTR, FATODE_MEM_HOST, C_NULL_PTR)
+      IF (rc /= 0) ierr(1) = rc
+      IF (ierr(1) < 0) PRINT *, 'RosenbrockADJ: Unsucessful step at T=', TIN, ' (IERR=', ierr(1), ')'   ! as :146-148
+    END IF
+    IF (PRESENT(IERR_U)) IERR_U = ierr(1)
     IF (PRESENT(ISTATUS_U)) ISTATUS_U(:) = ist(:)
     IF (PRESENT(RSTATUS_U)) RSTATUS_U(:) = rst(:)
   END SUBROUTINE INTEGRATE_ADJ

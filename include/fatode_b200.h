@@ -155,6 +155,9 @@ int fatode_rk_integrate_adj_batch(int model, int64_t ncells, int nvar, int np, i
 /* Engine knobs (process-wide): trajectory-tape budget in bytes (0 = 60% of free device memory) and
  * the number of cells per wave (0 = automatic). */
 int fatode_set_tape_budget(uint64_t bytes);
+/* RK_ADJ: accepted steps per system the first pass reserves tape for (0 = 1024); systems with more steps are integrated
+ * again with a Max_no_steps slot.  Results do not depend on it. */
+int fatode_set_rk_tape_slot(int steps);
 int fatode_set_wave_cells(int64_t cells);
 /* Execution path: 0 (default) = per-thread kernels (one cell per thread, static-pattern LU) with automatic
  * hand-back of irregular cells to the general kernels; 1 = general warp-per-cell kernels only.  Both give

@@ -132,3 +132,34 @@ def test_rk_adj_variants():
     ic[6] = 2
     with pytest.raises(Exception):
         F.integrate_adj("cbm4", T0, t1, y0, 4, rtol, atol, icntrl_u=ic, family="rk")
+
+
+@pytest.mark.gpu
+def test_rk_adj_waves_batches_and_tape_overflow_are_invisible():
+    import ctypes
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    rtol, atol = driver_tols()
+    y0 = perturbed_states(F.initial_state("cbm4"), 40)
+    t1 = T0 + 30 * 3600.0
+    base = F.integrate_adj("cbm4", T0, t1, y0, 32, rtol, atol, icntrl_u=radau(), family="rk")
+    L = F.lib()
+    L.fatode_set_rk_tape_slot.argtypes = [ctypes.c_int]
+    L.fatode_set_tape_budget.argtypes = [ctypes.c_uint64]
+    L.fatode_set_wave_cells.argtypes = [ctypes.c_int64]
+    try:
+        L.fatode_set_wave_cells(7)                    # six waves
+        L.fatode_set_tape_budget(1 << 30)             # ~0.75 GB of records per backward batch
+        L.fatode_set_rk_tape_slot(100)                # most systems overflow their slot and take the second pass
+        res = F.integrate_adj("cbm4", T0, t1, y0, 32, rtol, atol, icntrl_u=radau(), family="rk")
+        st = F.last_stats()
+    finally:
+        L.fatode_set_wave_cells(0)
+        L.fatode_set_tape_budget(0)
+        L.fatode_set_rk_tape_slot(0)
+        L.fatode_release_workspace()
+    assert st.waves > 6
+    assert (base.istatus[:, 3] > 100).any()
+    for a, b in ((res.y, base.y), (res.istatus, base.istatus), (res.rstatus, base.rstatus), (res.lambda_, base.lambda_),
+                 (res.mu, base.mu), (res.ierr, base.ierr)):
+        assert np.array_equal(a, b)
