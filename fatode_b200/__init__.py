@@ -77,6 +77,8 @@ def lib():
         L.fatode_ros_integrate_tlm_batch.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, vp, vp,
                                                      ctypes.c_double, ctypes.c_double, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                                      ctypes.c_int, vp]
+        L.fatode_sdirk_integrate_tlm_batch.argtypes = L.fatode_ros_integrate_tlm_batch.argtypes
+        L.fatode_set_sdirk_tape_slot.argtypes = [ctypes.c_int]
         _lib = L
     return _lib
 
@@ -215,8 +217,9 @@ def integrate_adj(model, tin, tout, y, nadj, rtol, atol, np_=None, icntrl_u=None
 
 
 def integrate_tlm(model, tin, tout, y, y_tlm, rtol, atol, icntrl_u=None, rcntrl_u=None, atol_tlm=None, rtol_tlm=None,
-                  model_params=None) -> Result:
-    """Batched TLM/ROS_TLM INTEGRATE_TLM (TLM/ROS_TLM/ROS_TLM_f90_Integrator.F90:35). y: [ncells, N]; y_tlm: [ncells, NTLM, N]."""
+                  model_params=None, family="ros") -> Result:
+    """Batched INTEGRATE_TLM: family="ros" TLM/ROS_TLM (TLM/ROS_TLM/ROS_TLM_f90_Integrator.F90:35), family="sdirk"
+    TLM/SDIRK_TLM (TLM/SDIRK_TLM/SDIRK_TLM_f90_Integrator.F90:31). y: [ncells, N]; y_tlm: [ncells, NTLM, N]."""
     mid = model_id(model)
     yy = np.atleast_2d(np.array(y, dtype=np.float64, order="C"))
     nc, n = yy.shape
@@ -231,9 +234,9 @@ def integrate_tlm(model, tin, tout, y, y_tlm, rtol, atol, icntrl_u=None, rcntrl_
     rst = np.zeros((nc, 20))
     ierr = np.zeros(nc, dtype=np.int32)
     mp = None if model_params is None else np.ascontiguousarray(model_params, dtype=np.float64)
-    _check(lib().fatode_ros_integrate_tlm_batch(mid, nc, n, ntlm, _ptr(yy), _ptr(yt), float(tin), float(tout), _ptr(at), _ptr(rt),
-                                                _ptr(atol), _ptr(rtol), _ptr(ic), _ptr(rc), _ptr(ist), _ptr(rst), _ptr(ierr),
-                                                _ptr(mp), MEM_HOST, None))
+    entry = lib().fatode_sdirk_integrate_tlm_batch if family == "sdirk" else lib().fatode_ros_integrate_tlm_batch
+    _check(entry(mid, nc, n, ntlm, _ptr(yy), _ptr(yt), float(tin), float(tout), _ptr(at), _ptr(rt),
+                 _ptr(atol), _ptr(rtol), _ptr(ic), _ptr(rc), _ptr(ist), _ptr(rst), _ptr(ierr), _ptr(mp), MEM_HOST, None))
     return Result(yy, ist, rst, ierr, y_tlm=yt)
 
 

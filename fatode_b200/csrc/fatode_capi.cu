@@ -30,6 +30,7 @@
 #include "ros_cell_adj.cuh"
 #include "model_small_cell.cuh"
 #include "sdirk_cell_fwd.cuh"
+#include "sdirk_cell_tlm.cuh"
 #include "rk_cell_fwd.cuh"
 #include "model_cbm4_dense_cell.cuh"
 #include "rk_cell_adj.cuh"
@@ -382,11 +383,13 @@ static thread_local CachedBuf g_tape, g_y0, g_nacc, g_off, g_queue, g_part;
 static thread_local CachedBuf g_ids, g_wnacc, g_wlast, g_prev, g_owner, g_order, g_wierr;   // per-thread path
 static void release_pipeline_workspace();
 static void release_rk_workspace();
+static void release_sdirk_workspace();
 extern "C" int fatode_release_workspace(void) {
   g_tape.release(); g_y0.release(); g_nacc.release(); g_off.release(); g_queue.release(); g_part.release();
   g_ids.release(); g_wnacc.release(); g_wlast.release(); g_prev.release(); g_owner.release(); g_order.release(); g_wierr.release();
   release_pipeline_workspace();
   release_rk_workspace();
+  release_sdirk_workspace();
   return 0;
 }
 
@@ -1318,11 +1321,11 @@ static int implicit_integrate_batch(int family, int model, int64_t ncells, int n
   int rc;
   if (family == IMPL_SDIRK) {
     if (model == FATODE_MODEL_CBM4)
-      rc = cellfwd_launch<SdirkParams, Cbm4Const>(k_sdirk_fwd_cell<Cbm4Cell, 32>, SdirkSmem<Cbm4Cell, 32>::BYTES, 32, sp, mc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st, nullptr);
+      rc = cellfwd_launch<SdirkParams, Cbm4Const, double*, int, int>(k_sdirk_fwd_cell<Cbm4Cell, 32>, SdirkSmem<Cbm4Cell, 32>::BYTES, 32, sp, mc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st, nullptr, (double*)nullptr, 0, 0);
     else if (model == FATODE_MODEL_SMALL_STRATO)
-      rc = cellfwd_launch<SdirkParams, SmallConst>(k_sdirk_fwd_cell<SmallStratoCell, 32>, SdirkSmem<SmallStratoCell, 32>::BYTES, 32, sp, sc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st, nullptr);
+      rc = cellfwd_launch<SdirkParams, SmallConst, double*, int, int>(k_sdirk_fwd_cell<SmallStratoCell, 32>, SdirkSmem<SmallStratoCell, 32>::BYTES, 32, sp, sc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st, nullptr, (double*)nullptr, 0, 0);
     else
-      rc = cellfwd_launch<SdirkParams, SmallConst>(k_sdirk_fwd_cell<RobertsCell, 32>, SdirkSmem<RobertsCell, 32>::BYTES, 32, sp, sc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st, nullptr);
+      rc = cellfwd_launch<SdirkParams, SmallConst, double*, int, int>(k_sdirk_fwd_cell<RobertsCell, 32>, SdirkSmem<RobertsCell, 32>::BYTES, 32, sp, sc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st, nullptr, (double*)nullptr, 0, 0);
   } else {
     if (model == FATODE_MODEL_CBM4)
       rc = cellfwd_launch<RkParams, Cbm4Const, double*, int>(k_rk_fwd_cell<Cbm4Cell, RK_LANES_CBM4>, RkSmem<Cbm4Cell, RK_LANES_CBM4>::BYTES, RK_LANES_CBM4, rp, mc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st, nullptr, (double*)nullptr, 0);
@@ -1346,8 +1349,8 @@ static int implicit_integrate_batch(int family, int model, int64_t ncells, int n
       CUDA_TRY(b_ids.alloc(sizeof(int) * ids.size()));
       CUDA_TRY(cudaMemcpyAsync(b_ids.p, ids.data(), sizeof(int) * ids.size(), cudaMemcpyHostToDevice, st));
       if (family == IMPL_SDIRK)
-        rc = cellfwd_launch<SdirkParams, Cbm4Const>(k_sdirk_fwd_cell<Cbm4DenseCell, SDIRK_LANES_DENSE>, SdirkSmem<Cbm4DenseCell, SDIRK_LANES_DENSE>::BYTES,
-                                                   SDIRK_LANES_DENSE, sp, mc, (int64_t)ids.size(), d_y, da, dr, d_ist, d_rst, d_ierr, st, b_ids.as<int>());
+        rc = cellfwd_launch<SdirkParams, Cbm4Const, double*, int, int>(k_sdirk_fwd_cell<Cbm4DenseCell, SDIRK_LANES_DENSE>, SdirkSmem<Cbm4DenseCell, SDIRK_LANES_DENSE>::BYTES,
+                                                   SDIRK_LANES_DENSE, sp, mc, (int64_t)ids.size(), d_y, da, dr, d_ist, d_rst, d_ierr, st, b_ids.as<int>(), (double*)nullptr, 0, 0);
       else
         rc = cellfwd_launch<RkParams, Cbm4Const, double*, int>(k_rk_fwd_cell<Cbm4DenseCell, RK_LANES_DENSE>, RkSmem<Cbm4DenseCell, RK_LANES_DENSE>::BYTES,
                                                 RK_LANES_DENSE, rp, mc, (int64_t)ids.size(), d_y, da, dr, d_ist, d_rst, d_ierr, st, b_ids.as<int>(), (double*)nullptr, 0);
@@ -1488,7 +1491,7 @@ static int rk_adj_device(const RkParams& rp, const Cbm4Const& mc, int64_t ncells
   CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
   free_b += g_rk_tape.cap + g_rk_fat.cap;
   const size_t budget = g_tape_budget ? (size_t)g_tape_budget : (size_t)(0.6 * (double)free_b);
-  const int cap = std::min(rp.max_no_steps, g_rk_tape_slot > 0 ? g_rk_tape_slot : 1024);
+  const int cap = std::min(rp.max_no_steps + 1, g_rk_tape_slot > 0 ? g_rk_tape_slot : 1024);   // Nstp > Max_no_steps stops: one more may be accepted
   int64_t wave = g_wave_cells > 0 ? g_wave_cells : (int64_t)sms * RK_LANES_CBM4 * 2;
   wave = std::min<int64_t>(wave, std::max<int64_t>(1, (int64_t)(0.2 * (double)budget / ((double)cap * RK_REC * sizeof(double)))));
   const size_t fat_budget = (size_t)(0.75 * (double)budget);
@@ -1504,7 +1507,7 @@ static int rk_adj_device(const RkParams& rp, const Cbm4Const& mc, int64_t ncells
   }
   // systems with more accepted steps than the default slot: again, a few at a time, with room for Max_no_steps
   while (!overflow.empty()) {
-    const int capx = rp.max_no_steps;
+    const int capx = rp.max_no_steps + 1;
     const size_t per = (size_t)capx * RK_REC * sizeof(double);
     const size_t take = std::max<size_t>(1, std::min<size_t>(overflow.size(), (size_t)(0.2 * (double)budget) / per));
     std::vector<int> part(overflow.end() - (long)take, overflow.end()), again;
@@ -1588,6 +1591,190 @@ extern "C" int fatode_rk_integrate_adj_batch(int model, int64_t ncells, int nvar
       if (with_mu) CUDA_TRY(cudaMemcpyAsync(mu, d_mu, nm, cudaMemcpyDeviceToHost, st));
       if (with_mu && mu_sum) CUDA_TRY(cudaMemcpyAsync(mu_sum, d_musum, sizeof(double) * np * nadj, cudaMemcpyDeviceToHost, st));
     }
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TLM/SDIRK_TLM INTEGRATE_TLM for CBM-IV: taping state sweep (one system per thread), per-step preparation (one thread per
+// accepted step), column sweep (one warp per system, lane = TLM column).  sdirk_cell_tlm.cuh.
+static thread_local CachedBuf g_sd_tape, g_sd_fat, g_sd_idx, g_sd_stat;
+static int g_sdirk_tape_slot = 0;   // accepted steps per system in the first pass (0 = 4608)
+extern "C" int fatode_set_sdirk_tape_slot(int steps) { g_sdirk_tape_slot = steps; return 0; }
+static void release_sdirk_workspace() { g_sd_tape.release(); g_sd_fat.release(); g_sd_idx.release(); g_sd_stat.release(); }
+
+// One group of systems (ids) through the state sweep and the column sweep.  Systems that overflow their tape slot are
+// appended to `overflow`.  A system whose state sweep fails keeps Y_tlm as of its last accepted step, like the reference.
+static int sdirk_tlm_group(const SdirkParams& sp, const Cbm4Const& mc, const std::vector<int>& ids, int cap, int ntlm, size_t fat_budget,
+                           double* d_y, double* d_ytlm, const double* d_atol, const double* d_rtol, int* d_ist, double* d_rst,
+                           int* d_ierr, cudaStream_t st, int sms, std::vector<int>& overflow) {
+  const int n = (int)ids.size();
+  if (n == 0) return 0;
+  const size_t idx_bytes = sizeof(int) * (size_t)n * 3 + 16 + sizeof(long long) * (size_t)(n + 1);
+  CUDA_TRY(g_sd_idx.ensure(idx_bytes));
+  int* d_ids = g_sd_idx.as<int>();
+  int* d_slot = d_ids + n;
+  int* d_cell = d_slot + n;
+  long long* d_off = reinterpret_cast<long long*>(reinterpret_cast<char*>(g_sd_idx.p) + ((sizeof(int) * (size_t)n * 3 + 15) / 16) * 16);
+  CUDA_TRY(cudaMemcpyAsync(d_ids, ids.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(g_sd_tape.ensure(sizeof(double) * (size_t)n * cap * SD_REC));
+  if (int e = cellfwd_launch<SdirkParams, Cbm4Const, double*, int, int>(k_sdirk_fwd_cell<Cbm4Cell, 32, true>, SdirkSmem<Cbm4Cell, 32>::BYTES, 32,
+                                                                       sp, mc, n, d_y, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, d_ids,
+                                                                       g_sd_tape.as<double>(), cap, ntlm))
+    return e;
+  CUDA_TRY(g_sd_stat.ensure(sizeof(int) * 2 * (size_t)n));
+  k_rk_gather_status<<<(n + 255) / 256, 256, 0, st>>>(n, d_ids, d_ierr, d_ist, g_sd_stat.as<int>());
+  std::vector<int> h_stat(2 * (size_t)n);
+  CUDA_TRY(cudaMemcpyAsync(h_stat.data(), g_sd_stat.p, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const size_t rec_bytes = sizeof(double) * ST_REC;
+  std::vector<int> b_slot, b_cell;
+  std::vector<long long> b_off;
+  auto flush = [&]() -> int {
+    const int nb = (int)b_slot.size();
+    if (nb == 0) return 0;
+    const long long nrec = b_off.back();
+    CUDA_TRY(g_sd_fat.ensure((size_t)std::max<long long>(nrec, 1) * rec_bytes));
+    CUDA_TRY(cudaMemcpyAsync(d_slot, b_slot.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_cell, b_cell.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_off, b_off.data(), sizeof(long long) * (nb + 1), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(g_ctr.p, 0, 16 * sizeof(unsigned long long), st));
+    PhaseTimer tm(st);
+    if (nrec > 0) {
+      SdirkTlmPrepArgs pa{(long)nrec, nb, d_off, d_slot, g_sd_tape.as<double>(), cap, g_sd_fat.as<double>()};
+      const size_t psm = sizeof(double) * (size_t)(cbm4_cell::NLU + 3 * 32) * ST_PREP_LANES;
+      CUDA_TRY(cudaFuncSetAttribute(k_sdirk_tlm_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+      int per_sm = 1;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sdirk_tlm_prep, 32, psm));
+      const unsigned pblocks = (unsigned)std::min<long long>((nrec + ST_PREP_LANES - 1) / ST_PREP_LANES, (long long)sms * std::max(per_sm, 1));
+      tm.start();
+      k_sdirk_tlm_prep<<<pblocks, 32, psm, st>>>(sp, mc, pa);
+      CUDA_TRY(cudaGetLastError());
+      g_stats.ms_forward_tape += tm.stop();
+      g_stats.launches++; g_stats.launches_expand++;
+      SdirkTlmArgs aa{nb, d_off, d_cell, g_sd_fat.as<double>(), d_ytlm, g_ctr.as<unsigned long long>(), ntlm};
+      CUDA_TRY(cudaFuncSetAttribute(k_sdirk_tlm_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDIRK_TLM_SMEM));
+      const unsigned ablocks = (unsigned)std::min<int>(nb, 2 * sms);
+      tm.start();
+      k_sdirk_tlm_cell<<<ablocks, 32, SDIRK_TLM_SMEM, st>>>(sp, aa);
+      CUDA_TRY(cudaGetLastError());
+      g_stats.ms_adjoint += tm.stop();
+      g_stats.launches++; g_stats.launches_adjoint++;
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    b_slot.clear(); b_cell.clear(); b_off.clear();
+    return 0;
+  };
+  for (int i = 0; i < n; ++i) {
+    const int code = h_stat[2 * (size_t)i], nacc = h_stat[2 * (size_t)i + 1];
+    if (code == IERR_TAPE_OVERFLOW) { overflow.push_back(ids[i]); continue; }
+    if (code == SDIRK_IERR_IRREGULAR || nacc <= 0) continue;   // handed back / nothing accepted: the columns stay as given
+    if (b_off.empty()) b_off.push_back(0);
+    if (!b_slot.empty() && (size_t)(b_off.back() + nacc) * rec_bytes > fat_budget)
+      if (int e = flush()) return e;
+    if (b_off.empty()) b_off.push_back(0);
+    b_slot.push_back(i);
+    b_cell.push_back(ids[i]);
+    b_off.push_back(b_off.back() + nacc);
+    g_stats.accepted_steps += nacc;
+  }
+  return flush();
+}
+
+static int sdirk_tlm_device(const SdirkParams& sp, const Cbm4Const& mc, int64_t ncells, int ntlm, double* d_y, double* d_ytlm,
+                            const double* d_atol, const double* d_rtol, int* d_ist, double* d_rst, int* d_ierr, cudaStream_t st) {
+  std::memset(&g_stats, 0, sizeof g_stats);
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  size_t free_b = 0, total_b = 0;
+  CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+  free_b += g_sd_tape.cap + g_sd_fat.cap;
+  const size_t budget = g_tape_budget ? (size_t)g_tape_budget : (size_t)(0.6 * (double)free_b);
+  const int cap = std::min(sp.max_no_steps + 1, g_sdirk_tape_slot > 0 ? g_sdirk_tape_slot : 4608);   // Nstp > Max_no_steps stops: one more may be accepted
+  int64_t wave = g_wave_cells > 0 ? g_wave_cells : (int64_t)sms * 32 * 2;
+  wave = std::min<int64_t>(wave, std::max<int64_t>(1, (int64_t)(0.35 * (double)budget / ((double)cap * SD_REC * sizeof(double)))));
+  const size_t fat_budget = (size_t)(0.6 * (double)budget);
+  std::vector<int> ids, overflow;
+  for (int64_t w0 = 0; w0 < ncells; w0 += wave) {
+    const int64_t w1 = std::min(ncells, w0 + wave);
+    ids.resize((size_t)(w1 - w0));
+    for (int64_t c = w0; c < w1; ++c) ids[(size_t)(c - w0)] = (int)c;
+    if (int e = sdirk_tlm_group(sp, mc, ids, cap, ntlm, fat_budget, d_y, d_ytlm, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, sms, overflow))
+      return e;
+    g_stats.waves++;
+  }
+  while (!overflow.empty()) {   // more accepted steps than the default slot: again with room for Max_no_steps
+    const int capx = sp.max_no_steps + 1;
+    const size_t per = (size_t)capx * SD_REC * sizeof(double);
+    const size_t take = std::max<size_t>(1, std::min<size_t>(overflow.size(), (size_t)(0.35 * (double)budget) / per));
+    std::vector<int> part(overflow.end() - (long)take, overflow.end()), again;
+    overflow.resize(overflow.size() - take);
+    if (int e = sdirk_tlm_group(sp, mc, part, capx, ntlm, fat_budget, d_y, d_ytlm, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, sms, again))
+      return e;
+    if (!again.empty()) return fail(FATODE_ENOMEM, "SDIRK_TLM tape overflow with a Max_no_steps slot");
+    g_stats.waves++;
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int fatode_sdirk_integrate_tlm_batch(int model, int64_t ncells, int nvar, int ntlm, double* y, double* y_tlm, double tin,
+                                                double tout, const double* atol_tlm, const double* rtol_tlm, const double* atol,
+                                                const double* rtol, const int* icntrl_u, const double* rcntrl_u, int* istatus,
+                                                double* rstatus, int* ierr, const double* model_params, int mem, void* stream) {
+  (void)atol_tlm; (void)rtol_tlm;   // only read with ICNTRL(9) / ICNTRL(12), which are not built
+  g_err.clear();
+  if (ncells < 0 || !y || !y_tlm || !atol || !rtol || !istatus || !rstatus || !ierr) return fail(FATODE_EINVAL, "NULL required argument");
+  if (int e = check_model_dims(model, nvar, 0)) return e;
+  if (ntlm < 1) return fail(FATODE_EINVAL, "ntlm < 1");
+  if (model != FATODE_MODEL_CBM4) return fail(FATODE_EUNSUPPORTED, "the SDIRK tangent linear model is available for the cbm4 model only in this build");
+  if (ntlm > 32) return fail(FATODE_EUNSUPPORTED, "ntlm > 32 per call is not supported yet");
+  if (int e = check_device()) return e;
+  if (ncells == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // INTEGRATE_TLM presets ICNTRL(5) = 8 before the `> 0` override (TLM/SDIRK_TLM/SDIRK_TLM_f90_Integrator.F90:60-70)
+  int ic[20];
+  std::memset(ic, 0, sizeof ic);
+  ic[4] = 8;
+  if (icntrl_u) for (int i = 0; i < 20; ++i) if (icntrl_u[i] > 0) ic[i] = icntrl_u[i];
+  SdirkParams sp;
+  int tlm_opt[3] = {0, 0, 0};
+  const int perr = sdirk_parse_options(nvar, ic, rcntrl_u, tin, tout, atol, rtol, sp, tlm_opt);
+  if (perr < 0) return broadcast_ierr(ncells, perr, istatus, rstatus, ierr, mem, st);
+  if (tlm_opt[0] == 1) return fail(FATODE_EUNSUPPORTED, "SDIRK_TLM direct TLM solve (ICNTRL(7) = 1) is not built; use the preset modified Newton");
+  if (tlm_opt[1] != 0 || tlm_opt[2] != 0)
+    return fail(FATODE_EUNSUPPORTED, "SDIRK_TLM with the columns in the Newton / truncation error control (ICNTRL(9), ICNTRL(12)) is not built");
+  Cbm4Const mc;
+  cbm4_constants(model_params, mc);
+  DevBuf b_atol, b_rtol, b_y, b_yt, b_ist, b_rst, b_ierr;
+  CUDA_TRY(b_atol.alloc(sizeof(double) * nvar));
+  CUDA_TRY(b_rtol.alloc(sizeof(double) * nvar));
+  CUDA_TRY(cudaMemcpyAsync(b_atol.p, atol, sizeof(double) * nvar, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(b_rtol.p, rtol, sizeof(double) * nvar, cudaMemcpyHostToDevice, st));
+  double *d_y = y, *d_yt = y_tlm, *d_rst = rstatus;
+  int *d_ist = istatus, *d_ierr = ierr;
+  const size_t ny = sizeof(double) * nvar * ncells, nt = sizeof(double) * (size_t)nvar * ntlm * ncells;
+  if (mem == FATODE_MEM_HOST) {
+    CUDA_TRY(b_y.alloc(ny));
+    CUDA_TRY(b_yt.alloc(nt));
+    CUDA_TRY(b_ist.alloc(sizeof(int) * 20 * ncells));
+    CUDA_TRY(b_rst.alloc(sizeof(double) * 20 * ncells));
+    CUDA_TRY(b_ierr.alloc(sizeof(int) * ncells));
+    CUDA_TRY(cudaMemcpyAsync(b_y.p, y, ny, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b_yt.p, y_tlm, nt, cudaMemcpyHostToDevice, st));
+    d_y = b_y.as<double>(); d_yt = b_yt.as<double>(); d_ist = b_ist.as<int>(); d_rst = b_rst.as<double>(); d_ierr = b_ierr.as<int>();
+  }
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_cbm4_rc, mc.rc_base, sizeof(double) * 81, 0, cudaMemcpyHostToDevice, st));
+  if (int e = sdirk_tlm_device(sp, mc, ncells, ntlm, d_y, d_yt, b_atol.as<double>(), b_rtol.as<double>(), d_ist, d_rst, d_ierr, st))
+    return e;
+  if (mem == FATODE_MEM_HOST) {
+    CUDA_TRY(cudaMemcpyAsync(y, d_y, ny, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(y_tlm, d_yt, nt, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(istatus, d_ist, sizeof(int) * 20 * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(rstatus, d_rst, sizeof(double) * 20 * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ierr, d_ierr, sizeof(int) * ncells, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
   }
   return 0;

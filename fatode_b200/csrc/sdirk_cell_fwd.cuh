@@ -50,12 +50,20 @@ __device__ __forceinline__ double sdirk_powi(double x, int m) {   // gfortran's 
   return m < 0 ? __ddiv_rn(1.0, y) : y;
 }
 
-template <class Model, int LANES>
+// TLM = true: the state part of TLM/SDIRK_TLM (SDIRK_IntegratorTLM, TLM/SDIRK_TLM/SDIRK_TLM_f90_Integrator.F90:474-911) in
+// its preset mode, where the tangent-linear columns do not influence the step control: the LU is never reused across
+// steps (:879), every completed stage counts one more Jacobian (:701-702) and the NTLM * min(saveNiter, NewtonMaxit) solves
+// of its fixed-count TLM iterations (:727, :769 — rejected attempts included), and every accepted step pushes
+// (T, H, saveNiter of the stages, Y, Z_1..Z_S) to the system's tape slot: record r of queue slot s lives at
+// tape[(s * tape_cap + r) * SD_REC].  The columns themselves are propagated afterwards (sdirk_cell_tlm.cuh).
+constexpr int SD_REC = 196;   // T, H, packed saveNiter (4 bits per stage), pad, Y(32), Z(5 x 32)
+
+template <class Model, int LANES, bool TLM = false>
 __global__ void __launch_bounds__(32, 1)
 k_sdirk_fwd_cell(SdirkParams sp, typename Model::Const mc, long ncells, const double* __restrict__ y_in, double* __restrict__ y_out,
                  const double* __restrict__ atol_g, const double* __restrict__ rtol_g, int* __restrict__ istatus,
                  double* __restrict__ rstatus, int* __restrict__ ierr_out, unsigned long long* __restrict__ queue,
-                 const int* __restrict__ cell_ids) {
+                 const int* __restrict__ cell_ids, double* __restrict__ tape, int tape_cap, int ntlm) {
   extern __shared__ __align__(16) double cell_smem[];
   constexpr int N = Model::N;
   constexpr int SV = LANES;
@@ -149,6 +157,7 @@ k_sdirk_fwd_cell(SdirkParams sp, typename Model::Const mc, long ncells, const do
       if (__dadd_rn(T, __dmul_rn(0.1, H)) == T || fabs(H) <= Roundoff) { ierr = -7; break; }
       bool newton_failed = false;
       double Fac = 0.5;
+      unsigned save_pack = 0u;
       for (int istage = 0; istage < S; ++istage) {
         double* Zi = Z + istage * N * SV;
 #pragma unroll 4
@@ -199,7 +208,15 @@ k_sdirk_fwd_cell(SdirkParams sp, typename Model::Const mc, long ncells, const do
 #pragma unroll 4
           for (int i = 0; i < N; ++i) Zi[i * SV] = __dadd_rn(Zi[i * SV], RHS[i * SV]);
           NewtonDone = (__dmul_rn(NewtonRate, NewtonIncrement) <= sp.newtontol);
-          if (NewtonDone) break;
+          if (NewtonDone) {
+            if constexpr (TLM) {   // saveNiter = NewtonIter + 1 (:603); the TLM loop runs min(saveNiter, NewtonMaxit) iterations
+              const int it = min(NewtonIter + 1, sp.newton_maxit);
+              save_pack |= (unsigned)it << (4 * istage);
+              njac++;
+              nsol += ntlm * it;
+            }
+            break;
+          }
         }
         if (!NewtonDone) { newton_failed = true; break; }
       }
@@ -227,6 +244,20 @@ k_sdirk_fwd_cell(SdirkParams sp, typename Model::Const mc, long ncells, const do
       F2 = fmax(sp.facmin, fmin(sp.facmax, F2));
       double Hnew = __dmul_rn(H, F2);
       if (Err < 1.0) {   // accept (:594-631)
+        if constexpr (TLM) if (tape) {
+          if (nacc >= tape_cap) { ierr = IERR_TAPE_OVERFLOW; break; }
+          double* rec = tape + ((size_t)slot * tape_cap + nacc) * SD_REC;
+          st_global_256(rec, T, H, (double)save_pack, (double)S);
+#pragma unroll 2
+          for (int i = 0; i < N; i += 4)
+            st_global_256(rec + 4 + i, Y[i * SV], Y[(i + 1) * SV], Y[(i + 2) * SV], Y[(i + 3) * SV]);
+          for (int s2 = 0; s2 < S; ++s2) {
+            const double* Zs = Z + s2 * N * SV;
+#pragma unroll 2
+            for (int i = 0; i < N; i += 4)
+              st_global_256(rec + 4 + N + s2 * N + i, Zs[i * SV], Zs[(i + 1) * SV], Zs[(i + 2) * SV], Zs[(i + 3) * SV]);
+          }
+        }
         FirstStep = false;
         nacc++;
         T = __dadd_rn(T, H);
@@ -247,7 +278,7 @@ k_sdirk_fwd_cell(SdirkParams sp, typename Model::Const mc, long ncells, const do
           H = __dsub_rn(Tfinal, T);
         } else {
           const double Hratio = __ddiv_rn(Hnew, H);
-          SkipLU = (Theta <= sp.thetamin) && (Hratio >= sp.qmin) && (Hratio <= sp.qmax);
+          SkipLU = !TLM && (Theta <= sp.thetamin) && (Hratio >= sp.qmin) && (Hratio <= sp.qmax);   // TLM: never (:879)
           if (!SkipLU) H = Hnew;
         }
         SkipJac = false;
@@ -259,7 +290,7 @@ k_sdirk_fwd_cell(SdirkParams sp, typename Model::Const mc, long ncells, const do
     }
     // ---- results
     ierr_out[cell] = ierr;
-    if (ierr != SDIRK_IERR_IRREGULAR) {   // a handed-back system keeps its initial state for the general-pivoting pass
+    if (ierr != SDIRK_IERR_IRREGULAR && ierr != IERR_TAPE_OVERFLOW) {   // a handed-back system keeps its initial state
 #pragma unroll 4
       for (int i = 0; i < N; ++i) y_out[cell * N + i] = Y[i * SV];
     }
@@ -275,8 +306,10 @@ k_sdirk_fwd_cell(SdirkParams sp, typename Model::Const mc, long ncells, const do
 
 // host: option handling of SDIRK (:236-417).  Returns the reference's Ierr before integrating (0 = go on, < 0 = the
 // last option error: the reference keeps parsing after an error and returns the last code)
+// tlm != nullptr: INTEGRATE_TLM of TLM/SDIRK_TLM (same presets; an unknown ICNTRL(3) selects Sdirk2a there, :262-275);
+// tlm[0..2] receive ICNTRL(7) (DirectTLM), ICNTRL(9) (TLMNewtonEst), ICNTRL(12) (TLMtruncErr).
 inline int sdirk_parse_options(int N, const int* icntrl_u, const double* rcntrl_u, double tin, double tout, const double* atol,
-                               const double* rtol, SdirkParams& sp) {
+                               const double* rtol, SdirkParams& sp, int* tlm = nullptr) {
   int ic[20];
   double rc[20];
   std::memset(ic, 0, sizeof ic);
@@ -295,6 +328,10 @@ inline int sdirk_parse_options(int N, const int* icntrl_u, const double* rcntrl_
     case 3: method = 3; break;
     case 5: method = 5; break;
     default: method = 4;   // 0, 4 and anything else: Sdirk4a (:262-275)
+  }
+  if (tlm) {
+    if (ic[2] < 0 || ic[2] > 5) method = 1;
+    tlm[0] = ic[6]; tlm[1] = ic[8]; tlm[2] = ic[11];
   }
   const SdirkTableauData& t = SDIRK_TABLEAU[method - 1];
   sp.S = t.S; sp.Gamma = t.Gamma; sp.ELO = t.ELO;

@@ -119,6 +119,22 @@ int fatode_sdirk_integrate_batch(int model, int64_t ncells, int nvar, double* y,
                                  const double* rcntrl_u, int* istatus, double* rstatus, int* ierr,
                                  const double* model_params, int mem, void* stream);
 
+/* INTEGRATE_TLM of TLM/SDIRK_TLM (TLM/SDIRK_TLM/SDIRK_TLM_f90_Integrator.F90:31):
+ *   INTEGRATE_TLM(N,NTLM,NNZERO,Y,Y_TLM,TIN,TOUT,ATOL_TLM,RTOL_TLM,ATOL,RTOL,FUN,JAC,
+ *                 ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U,IERR_U)
+ * y_tlm [ncells][ntlm][nvar] as for ROS_TLM.  Presets: ICNTRL(5) = 8 Newton iterations, everything else 0; user values
+ * override when > 0 (:60-77); an ICNTRL(3) outside 0..5 selects Sdirk2a in this family (:262-275).  Built: the preset
+ * mode — modified-Newton TLM (ICNTRL(7) = 0) with the iteration count of the state stage, columns outside the step
+ * control (ICNTRL(9) = ICNTRL(12) = 0); ICNTRL(7) = 1, ICNTRL(9) != 0 and ICNTRL(12) != 0 return FATODE_EUNSUPPORTED.
+ * ntlm <= 32, cbm4 only.  Per-cell IERR: 1, the reference's -1..-8, or -20 for a system whose factorisations leave the
+ * static pivot pattern (its Y and Y_tlm are returned unchanged).  A cell whose state sweep fails returns Y and Y_tlm as of
+ * its last accepted step, as the reference. */
+int fatode_sdirk_integrate_tlm_batch(int model, int64_t ncells, int nvar, int ntlm, double* y, double* y_tlm,
+                                     double tin, double tout, const double* atol_tlm, const double* rtol_tlm,
+                                     const double* atol, const double* rtol, const int* icntrl_u,
+                                     const double* rcntrl_u, int* istatus, double* rstatus, int* ierr,
+                                     const double* model_params, int mem, void* stream);
+
 /* INTEGRATE of FWD/RK (FWD/RK/RK_f90_Integrator.F90:32):
  *   INTEGRATE(TIN,TOUT,N,NNZERO,VAR,RTOL,ATOL,FUN,JAC,ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U,IERR_U)
  * Fully implicit 3-stage Runge-Kutta methods with simplified Newton iterations on the transformed (one real + one complex)
@@ -158,6 +174,8 @@ int fatode_set_tape_budget(uint64_t bytes);
 /* RK_ADJ: accepted steps per system the first pass reserves tape for (0 = 1024); systems with more steps are integrated
  * again with a Max_no_steps slot.  Results do not depend on it. */
 int fatode_set_rk_tape_slot(int steps);
+/* SDIRK_TLM: the same knob for the state sweep's tape (0 = 4608 accepted steps per system). */
+int fatode_set_sdirk_tape_slot(int steps);
 int fatode_set_wave_cells(int64_t cells);
 /* Execution path: 0 (default) = per-thread kernels (one cell per thread, static-pattern LU) with automatic
  * hand-back of irregular cells to the general kernels; 1 = general warp-per-cell kernels only.  Both give

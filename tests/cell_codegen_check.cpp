@@ -103,6 +103,13 @@ static inline int dgetf2(int n, double* a, int* ipiv) {
       lut_solve_seq(cur_lu, dinv, cur_swaps, ys);
       for (int i = 0; i < 32; ++i) if (!same(ys[i], yref[i])) { ++n_solve_bad; break; }
     }
+    {   // reference-order non-transposed register solve: bit for bit
+      double ys[32], yref[32];
+      for (int i = 0; i < 32; ++i) ys[i] = yref[i] = std::sin(2.0 + i * 0.41 + (double)(n_lu % 29));
+      dgetrs_oracle(false, n, a, ipiv, yref);
+      lun_solve_seq(cur_lu, dinv, cur_swaps, ys);
+      for (int i = 0; i < 32; ++i) if (!same(ys[i], yref[i])) { ++n_solve_bad; break; }
+    }
     // non-transposed register solve of the tangent-linear sweep against DGETRS('N')
     for (int i = 0; i < 32; ++i) xr[i] = xn[i] = std::cos(0.5 + i * 0.61 + (double)(n_lu % 89));
     dgetrs_oracle(false, n, a, ipiv, xr);
@@ -266,6 +273,12 @@ int main(int argc, char** argv) {
           sc = std::fmax(sc, std::fabs(sref)); er = std::fmax(er, std::fabs(sref - out[cidx]));
         }
         if (!(er <= 1e-12 * sc)) ++bad_fun;
+        cbm4_cell::j_vec_seq(jv, x, out);         // matmul(fjac1, g) in column-sweep order = sequential row sums
+        for (int r = 0; r < 32; ++r) {
+          double sref = 0.0;
+          for (int cidx = 0; cidx < 32; ++cidx) sref += jac[r + 32 * cidx] * x[cidx];
+          if (!same(sref, out[r])) ++bad_fun;
+        }
         cbm4_cell::jt_vec_seq(jv, x, out);        // reference order: bit for bit with the dense sequential dot products
         for (int cidx = 0; cidx < 32; ++cidx) {
           double sref = 0.0;

@@ -31,6 +31,7 @@ def lib():
                                              _ip, _dp, _ip, _dp, _ip, ctypes.c_int]
         L.oracle_ros_tlm_batch.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_int, _dp, _dp, ctypes.c_double, ctypes.c_double,
                                            _dp, _dp, _dp, _dp, _ip, _dp, _ip, _dp, _ip, ctypes.c_int]
+        L.oracle_sdirk_tlm_batch.argtypes = L.oracle_ros_tlm_batch.argtypes
         _lib = L
     return _lib
 
@@ -163,3 +164,24 @@ def rk_adj(model, y, nadj, tin, tout, atol, rtol, icntrl=None, rcntrl=None, with
     lib().oracle_rk_adj_batch(MODEL[model], nc, npar if use_mu else 0, nadj, _d(y), _d(lam), _d(mu) if use_mu else None,
                               tin, tout, _d(atol), _d(rtol), _i(ic), _d(rc), _i(ist), _d(rst), _i(ierr), nthreads)
     return dict(y=y, istatus=ist, rstatus=rst, ierr=ierr, lambda_=lam, mu=mu[:, :, :npar] if use_mu else None)
+
+
+def sdirk_tlm(model, y, y_tlm, tin, tout, atol, rtol, icntrl=None, rcntrl=None, atol_tlm=None, rtol_tlm=None, nthreads=0):
+    """INTEGRATE_TLM (TLM/SDIRK_TLM); y_tlm: [ncells, NTLM, N]."""
+    y = np.atleast_2d(np.array(y, dtype=np.float64, order="C"))
+    nc, n = y.shape
+    yt = np.array(y_tlm, dtype=np.float64, order="C").reshape(nc, -1, n)
+    ntlm = yt.shape[1]
+    ic, rc = _ctrl(icntrl, rcntrl)
+    atol = np.ascontiguousarray(atol, dtype=np.float64)
+    rtol = np.ascontiguousarray(rtol, dtype=np.float64)
+    at = None if atol_tlm is None else np.ascontiguousarray(atol_tlm, dtype=np.float64)
+    rt = None if rtol_tlm is None else np.ascontiguousarray(rtol_tlm, dtype=np.float64)
+    ist = np.zeros((nc, 20), dtype=np.int32)
+    rst = np.zeros((nc, 20))
+    ierr = np.zeros(nc, dtype=np.int32)
+    r = lib().oracle_sdirk_tlm_batch(MODEL[model], nc, ntlm, _d(y), _d(yt), tin, tout, None if at is None else _d(at),
+                                     None if rt is None else _d(rt), _d(atol), _d(rtol), _i(ic), _d(rc), _i(ist), _d(rst),
+                                     _i(ierr), nthreads)
+    assert r == 0
+    return dict(y=y, y_tlm=yt, istatus=ist, rstatus=rst, ierr=ierr)

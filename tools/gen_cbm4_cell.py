@@ -625,6 +625,36 @@ def main():
         k, p_ = SWAPS[bi]
         w(f"  if (swaps & {1 << bi}u) {{ double t = xr[{k}]; xr[{k}] = xr[{p_}]; xr[{p_}] = t; t = xi[{k}]; xi[{k}] = xi[{p_}]; xi[{p_}] = t; }}")
     w("}")
+    # ------------------------------------------------------------------ reference-order variants (SDIRK TLM)
+    w("// reference-order operators of the SDIRK tangent-linear sweep (same reason as above: Y_tlm <- Y_tlm + sum d_i Z_tlm_i")
+    w("// cancels for stiff components): matmul(fjac1, g) as sequential row sums, DGETRS('N') = DLASWP + DTRSM(L,L,N,U) +")
+    w("// DTRSM(L,U,N,N) in netlib's column-sweep order with the quotient by U(k,k) through exact_div (dinv = RN(1/U(k,k))).")
+    w("CBM4_CELL_INL void j_vec_seq(const double* __restrict__ Jv, const double (&x)[32], double (&out)[32]) {")
+    for r in range(N):
+        ents = sorted([(rc[1], e) for e, rc in enumerate(jent) if rc[0] == r])
+        w("  { double a = 0.0;")
+        for (c, e) in ents:
+            w(f"    a = a + Jv[{e}] * x[{c}];")
+        w(f"    out[{r}] = a; }}")
+    w("}")
+    w("CBM4_CELL_INL void lun_solve_seq(const double* __restrict__ lu, const double* __restrict__ dinv, const unsigned swaps, double (&b)[32]) {")
+    for bi, (k, p_) in enumerate(SWAPS):
+        w(f"  if (swaps & {1 << bi}u) {{ const double t = b[{k}]; b[{k}] = b[{p_}]; b[{p_}] = t; }}")
+    for k in range(N - 1):
+        rows = [i for i in range(k + 1, N) if P[i][k]]
+        if not rows:
+            continue
+        w(f"  {{ const double bk = b[{k}];")
+        for i in rows:
+            w(f"    b[{i}] = b[{i}] - bk * lu[{idx[(i, k)]}];")
+        w("  }")
+    for k in range(N - 1, -1, -1):
+        rows = [i for i in range(k) if P[i][k]]
+        w(f"  {{ const double bk = exact_div(b[{k}], lu[{idx[(k, k)]}], dinv[{k}]); b[{k}] = bk;")
+        for i in rows:
+            w(f"    b[{i}] = b[{i}] - bk * lu[{idx[(i, k)]}];")
+        w("  }")
+    w("}")
     # ------------------------------------------------------------------ tangent-linear sweep (lane = TLM column)
     w("")
     w("// ---- operators of the tangent-linear sweep (ros_TLM_Int, TLM/ROS_TLM/ROS_TLM_f90_Integrator.F90:551-633): the same")
