@@ -18,8 +18,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfatode_b200.so")
 
-MODEL_ROBERTS, MODEL_SMALL_STRATO, MODEL_CBM4 = 1, 2, 3
-MODELS = {"roberts": MODEL_ROBERTS, "small_strato": MODEL_SMALL_STRATO, "cbm4": MODEL_CBM4}
+MODEL_ROBERTS, MODEL_SMALL_STRATO, MODEL_CBM4, MODEL_SWE = 1, 2, 3, 4
+MODELS = {"roberts": MODEL_ROBERTS, "small_strato": MODEL_SMALL_STRATO, "cbm4": MODEL_CBM4, "swe": MODEL_SWE}
 MEM_HOST, MEM_DEVICE = 0, 1
 
 _dp = ctypes.POINTER(ctypes.c_double)
@@ -79,6 +79,9 @@ def lib():
                                                      ctypes.c_int, vp]
         L.fatode_sdirk_integrate_tlm_batch.argtypes = L.fatode_ros_integrate_tlm_batch.argtypes
         L.fatode_set_sdirk_tape_slot.argtypes = [ctypes.c_int]
+        L.fatode_erk_integrate_batch.argtypes = L.fatode_sdirk_integrate_batch.argtypes
+        L.fatode_erk_integrate_tlm_batch.argtypes = L.fatode_ros_integrate_tlm_batch.argtypes
+        L.fatode_swe_initial_state.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_double, _dp]
         _lib = L
     return _lib
 
@@ -186,6 +189,38 @@ def integrate_rk(model, tin, tout, var, rtol, atol, icntrl_u=None, rcntrl_u=None
     _check(lib().fatode_rk_integrate_batch(mid, nc, n, _ptr(y), float(tin), float(tout), _ptr(atol), _ptr(rtol),
                                            _ptr(ic), _ptr(rc), _ptr(ist), _ptr(rst), _ptr(ierr), _ptr(mp), MEM_HOST, None))
     return Result(y, ist, rst, ierr)
+
+
+def integrate_erk(model, tin, tout, var, rtol, atol, icntrl_u=None, rcntrl_u=None, var_tlm=None, atol_tlm=None, rtol_tlm=None) -> Result:
+    """Batched FWD/ERK INTEGRATE (FWD/ERK/ERK_f90_Integrator.F90:28) or, with var_tlm [ncells, NTLM, N], TLM/ERK_TLM
+    INTEGRATE_TLM (TLM/ERK_TLM/ERK_TLM_f90_Integrator.F90:28). var: [ncells, N] or [N]; model "swe"."""
+    mid = model_id(model)
+    y = np.atleast_2d(np.array(var, dtype=np.float64, order="C"))
+    nc, n = y.shape
+    rtol = np.ascontiguousarray(rtol, dtype=np.float64)
+    atol = np.ascontiguousarray(atol, dtype=np.float64)
+    ic, rc = _ctrl(icntrl_u, rcntrl_u)
+    ist = np.zeros((nc, 20), dtype=np.int32)
+    rst = np.zeros((nc, 20))
+    ierr = np.zeros(nc, dtype=np.int32)
+    if var_tlm is None:
+        _check(lib().fatode_erk_integrate_batch(mid, nc, n, _ptr(y), float(tin), float(tout), _ptr(atol), _ptr(rtol),
+                                                _ptr(ic), _ptr(rc), _ptr(ist), _ptr(rst), _ptr(ierr), None, MEM_HOST, None))
+        return Result(y, ist, rst, ierr)
+    yt = np.array(var_tlm, dtype=np.float64, order="C").reshape(nc, -1, n)
+    at = None if atol_tlm is None else np.ascontiguousarray(atol_tlm, dtype=np.float64)
+    rt = None if rtol_tlm is None else np.ascontiguousarray(rtol_tlm, dtype=np.float64)
+    _check(lib().fatode_erk_integrate_tlm_batch(mid, nc, n, yt.shape[1], _ptr(y), _ptr(yt), float(tin), float(tout), _ptr(at),
+                                                _ptr(rt), _ptr(atol), _ptr(rtol), _ptr(ic), _ptr(rc), _ptr(ist), _ptr(rst),
+                                                _ptr(ierr), None, MEM_HOST, None))
+    return Result(y, ist, rst, ierr, y_tlm=yt)
+
+
+def swe_initial_state(amplitude=30.0, u0=2.0, v0=2.0) -> np.ndarray:
+    """Gaussian bump of the shallow-water drivers (EXAMPLES/swe/SWE_ERK/swe2D_erk_dr.F90:100-103), grid2vec order."""
+    y = np.zeros(4800)
+    _check(lib().fatode_swe_initial_state(float(amplitude), float(u0), float(v0), y.ctypes.data_as(_dp)))
+    return y
 
 
 def integrate_adj(model, tin, tout, y, nadj, rtol, atol, np_=None, icntrl_u=None, rcntrl_u=None, want_mu=True,

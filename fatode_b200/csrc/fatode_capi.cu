@@ -31,6 +31,7 @@
 #include "model_small_cell.cuh"
 #include "sdirk_cell_fwd.cuh"
 #include "sdirk_cell_tlm.cuh"
+#include "erk_swe.cuh"
 #include "rk_cell_fwd.cuh"
 #include "model_cbm4_dense_cell.cuh"
 #include "rk_cell_adj.cuh"
@@ -78,6 +79,7 @@ extern "C" int fatode_model_dims(int model, int* nvar, int* np) {
     case FATODE_MODEL_ROBERTS: *nvar = 3; *np = 3; return 0;
     case FATODE_MODEL_SMALL_STRATO: *nvar = 5; *np = 0; return 0;
     case FATODE_MODEL_CBM4: *nvar = 32; *np = 29; return 0;
+    case FATODE_MODEL_SWE: *nvar = SWE_N; *np = 0; return 0;
   }
   return fail(FATODE_EINVAL, "unknown model id");
 }
@@ -103,7 +105,24 @@ extern "C" int fatode_model_initial_state(int model, double* y) {
       return 0;
     }
   }
+  if (model == FATODE_MODEL_SWE) return fatode_swe_initial_state(30.0, 2.0, 2.0, y);   // swe2D_erk_dr.F90:100-103
   return fail(FATODE_EINVAL, "unknown model id");
+}
+
+// initializeGaussianGrid(A) (EXAMPLES/swe/SWE_ERK/swe2D_upwind.F90:86-126) + constant velocities + grid2vec (:267-289):
+// y[k * 1600 + (i - 3) * 40 + (j - 3)] = U(k, i, j), h = 100 + A exp(-x_j^2 - y_i^2)
+extern "C" int fatode_swe_initial_state(double amplitude, double u0, double v0, double* y) {
+  if (!y) return fail(FATODE_EINVAL, "y is NULL");
+  const double dx = (3.0 - (-3.0)) / (SWE_MX - 1.0);
+  for (int i = 3; i <= SWE_MX + 2; ++i)
+    for (int j = 3; j <= SWE_MX + 2; ++j) {
+      const double xj = -3.0 + (j - 2) * dx, yi = -3.0 + (i - 2) * dx;
+      const int c = (i - 3) * SWE_MX + (j - 3);
+      y[c] = amplitude * std::exp(-xj * xj - yi * yi) + 100.0;
+      y[SWE_CELLS + c] = u0;
+      y[2 * SWE_CELLS + c] = v0;
+    }
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -384,12 +403,14 @@ static thread_local CachedBuf g_ids, g_wnacc, g_wlast, g_prev, g_owner, g_order,
 static void release_pipeline_workspace();
 static void release_rk_workspace();
 static void release_sdirk_workspace();
+static void release_erk_workspace();
 extern "C" int fatode_release_workspace(void) {
   g_tape.release(); g_y0.release(); g_nacc.release(); g_off.release(); g_queue.release(); g_part.release();
   g_ids.release(); g_wnacc.release(); g_wlast.release(); g_prev.release(); g_owner.release(); g_order.release(); g_wierr.release();
   release_pipeline_workspace();
   release_rk_workspace();
   release_sdirk_workspace();
+  release_erk_workspace();
   return 0;
 }
 
@@ -1093,9 +1114,12 @@ static int ros_device(const RosParams& rp, const typename Warp::Const& mc, int64
   return 0;
 }
 
-static int check_model_dims(int model, int nvar, int np) {
+static int check_model_dims(int model, int nvar, int np, bool explicit_family = false) {
   int n = 0, p = 0;
   if (fatode_model_dims(model, &n, &p) != 0) return FATODE_EINVAL;
+  if ((model == FATODE_MODEL_SWE) != explicit_family)
+    return fail(FATODE_EUNSUPPORTED, explicit_family ? "the explicit Runge-Kutta entry points are built for the swe model only"
+                                                     : "the swe model is available through the explicit Runge-Kutta entry points only");
   if (n != nvar) return fail(FATODE_EINVAL, "nvar does not match the registered model");
   if (np != 0 && np != p) return fail(FATODE_EINVAL, "np does not match the registered model");
   return 0;
@@ -1778,6 +1802,102 @@ extern "C" int fatode_sdirk_integrate_tlm_batch(int model, int64_t ncells, int n
     CUDA_TRY(cudaStreamSynchronize(st));
   }
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FWD/ERK INTEGRATE and TLM/ERK_TLM INTEGRATE_TLM on the shallow-water ensemble: one member per CTA (erk_swe.cuh)
+static thread_local CachedBuf g_erk_scratch;
+static void release_erk_workspace() { g_erk_scratch.release(); }
+
+static int erk_batch_impl(bool tlm, int model, int64_t ncells, int nvar, int ntlm, double* y, double* y_tlm, double tin, double tout,
+                          const double* atol, const double* rtol, const int* icntrl_u, const double* rcntrl_u, int* istatus,
+                          double* rstatus, int* ierr, int mem, void* stream) {
+  g_err.clear();
+  if (ncells < 0 || !y || !atol || !rtol || !istatus || !rstatus || !ierr) return fail(FATODE_EINVAL, "NULL required argument");
+  if (tlm && (!y_tlm || ntlm < 1)) return fail(FATODE_EINVAL, "y_tlm is NULL or ntlm < 1");
+  if (int e = check_model_dims(model, nvar, 0, true)) return e;
+  if (int e = check_device()) return e;
+  if (ncells == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ErkParams ep;
+  int tlm_opt[2] = {0, 0};
+  const int perr = erk_parse_options(nvar, icntrl_u, rcntrl_u, tin, tout, atol, rtol, ep, tlm ? tlm_opt : nullptr);
+  if (perr < 0) return broadcast_ierr(ncells, perr, istatus, rstatus, ierr, mem, st);
+  if (tlm && tlm_opt[0] != 0)
+    return fail(FATODE_EUNSUPPORTED, "ERK_TLM with a dense Jacobian (ICNTRL(5) /= 0: a 4800 x 4800 JAC + MATMUL per stage) is not built; "
+                                     "use the preset finite-difference Jacobian-vector products");
+  if (tlm && tlm_opt[1] != 0) return fail(FATODE_EUNSUPPORTED, "ERK_TLM truncation-error control (ICNTRL(12) /= 0) is not built");
+  const int ntl = tlm ? ntlm : 0;
+  const int ntol = ep.vector_tol ? nvar : 1;
+  DevBuf b_atol, b_rtol, b_y, b_yt, b_ist, b_rst, b_ierr;
+  CUDA_TRY(b_atol.alloc(sizeof(double) * ntol));
+  CUDA_TRY(b_rtol.alloc(sizeof(double) * ntol));
+  CUDA_TRY(cudaMemcpyAsync(b_atol.p, atol, sizeof(double) * ntol, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(b_rtol.p, rtol, sizeof(double) * ntol, cudaMemcpyHostToDevice, st));
+  double *d_y = y, *d_yt = y_tlm, *d_rst = rstatus;
+  int *d_ist = istatus, *d_ierr = ierr;
+  const size_t ny = sizeof(double) * (size_t)nvar * ncells, nt = ny * (size_t)ntl;
+  if (mem == FATODE_MEM_HOST) {
+    CUDA_TRY(b_y.alloc(ny));
+    CUDA_TRY(b_ist.alloc(sizeof(int) * 20 * ncells));
+    CUDA_TRY(b_rst.alloc(sizeof(double) * 20 * ncells));
+    CUDA_TRY(b_ierr.alloc(sizeof(int) * ncells));
+    CUDA_TRY(cudaMemcpyAsync(b_y.p, y, ny, cudaMemcpyHostToDevice, st));
+    d_y = b_y.as<double>(); d_ist = b_ist.as<int>(); d_rst = b_rst.as<double>(); d_ierr = b_ierr.as<int>();
+    if (tlm) {
+      CUDA_TRY(b_yt.alloc(nt));
+      CUDA_TRY(cudaMemcpyAsync(b_yt.p, y_tlm, nt, cudaMemcpyHostToDevice, st));
+      d_yt = b_yt.as<double>();
+    }
+  }
+  std::memset(&g_stats, 0, sizeof g_stats);
+  int dev = 0, sms = 0, per_sm = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  auto kern = tlm ? k_erk_swe<true> : k_erk_swe<false>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ERK_SMEM));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ERK_THREADS, ERK_SMEM));
+  const unsigned blocks = (unsigned)std::min<int64_t>(ncells, (int64_t)sms * std::max(per_sm, 1));
+  CUDA_TRY(g_erk_scratch.ensure(sizeof(double) * (size_t)blocks * ep.S * SWE_N * (1 + ntl)));
+  CUDA_TRY(g_ctr.ensure(16 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemsetAsync(g_ctr.p, 0, 16 * sizeof(unsigned long long), st));
+  ErkArgs ea{(long)ncells, d_y, d_y, d_yt, b_atol.as<double>(), b_rtol.as<double>(), d_ist, d_rst, d_ierr,
+             g_ctr.as<unsigned long long>(), g_erk_scratch.as<double>(), ntl};
+  PhaseTimer tm(st);
+  tm.start();
+  kern<<<blocks, ERK_THREADS, ERK_SMEM, st>>>(ep, ea);
+  CUDA_TRY(cudaGetLastError());
+  g_stats.ms_forward += tm.stop();
+  g_stats.launches++;
+  g_stats.launches_forward++;
+  g_stats.waves++;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (mem == FATODE_MEM_HOST) {
+    CUDA_TRY(cudaMemcpyAsync(y, d_y, ny, cudaMemcpyDeviceToHost, st));
+    if (tlm) CUDA_TRY(cudaMemcpyAsync(y_tlm, d_yt, nt, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(istatus, d_ist, sizeof(int) * 20 * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(rstatus, d_rst, sizeof(double) * 20 * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ierr, d_ierr, sizeof(int) * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+extern "C" int fatode_erk_integrate_batch(int model, int64_t ncells, int nvar, double* y, double tin, double tout, const double* atol,
+                                          const double* rtol, const int* icntrl_u, const double* rcntrl_u, int* istatus,
+                                          double* rstatus, int* ierr, const double* model_params, int mem, void* stream) {
+  (void)model_params;
+  return erk_batch_impl(false, model, ncells, nvar, 0, y, nullptr, tin, tout, atol, rtol, icntrl_u, rcntrl_u, istatus, rstatus, ierr,
+                        mem, stream);
+}
+
+extern "C" int fatode_erk_integrate_tlm_batch(int model, int64_t ncells, int nvar, int ntlm, double* y, double* y_tlm, double tin,
+                                              double tout, const double* atol_tlm, const double* rtol_tlm, const double* atol,
+                                              const double* rtol, const int* icntrl_u, const double* rcntrl_u, int* istatus,
+                                              double* rstatus, int* ierr, const double* model_params, int mem, void* stream) {
+  (void)atol_tlm; (void)rtol_tlm; (void)model_params;   // the TLM tolerances are only read with ICNTRL(12) /= 0
+  return erk_batch_impl(true, model, ncells, nvar, ntlm, y, y_tlm, tin, tout, atol, rtol, icntrl_u, rcntrl_u, istatus, rstatus, ierr,
+                        mem, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -10,6 +10,7 @@
 !     MODULE SDIRK_f90_Integrator   :: INTEGRATE       (FWD/SDIRK/SDIRK_f90_Integrator.F90:25)   after fatode_b200_set_family(FATODE_FAMILY_SDIRK)
 !     MODULE RK_f90_Integrator      :: INTEGRATE       (FWD/RK/RK_f90_Integrator.F90:32)         after fatode_b200_set_family(FATODE_FAMILY_RK)
 !     MODULE RK_adj_f90_Integrator  :: INTEGRATE_ADJ   (ADJ/RK_ADJ/RK_ADJ_f90_Integrator.F90:20) after fatode_b200_set_family(FATODE_FAMILY_RK)
+!     MODULE SDIRK_TLM_f90_Integrator :: INTEGRATE_TLM (TLM/SDIRK_TLM/SDIRK_TLM_f90_Integrator.F90:31) after fatode_b200_set_family(FATODE_FAMILY_SDIRK)
 !  (upstream the forward families are separate modules that all export INTEGRATE with the same argument list; the
 !  application picks one with its USE line, here with fatode_b200_set_family)
 !  Dummy-argument names and order are the reference's, so keyword calls such as
@@ -111,6 +112,19 @@ MODULE fatode_b200_mod
       REAL(C_DOUBLE), INTENT(IN) :: atol(*), rtol(*)
       INTEGER(C_INT) :: istatus(*), ierr(*)
       INTEGER(C_INT) :: fatode_ros_integrate_tlm_batch
+    END FUNCTION
+    FUNCTION fatode_sdirk_integrate_tlm_batch(model, ncells, nvar, ntlm, y, y_tlm, tin, tout, atol_tlm, rtol_tlm, atol, rtol, &
+                                              icntrl_u, rcntrl_u, istatus, rstatus, ierr, model_params, mem, stream) &
+                                              BIND(C, NAME='fatode_sdirk_integrate_tlm_batch')
+      IMPORT :: C_INT, C_INT64_T, C_DOUBLE, C_PTR
+      INTEGER(C_INT), VALUE :: model, nvar, ntlm, mem
+      INTEGER(C_INT64_T), VALUE :: ncells
+      REAL(C_DOUBLE), VALUE :: tin, tout
+      REAL(C_DOUBLE) :: y(*), y_tlm(*), rstatus(*)
+      TYPE(C_PTR), VALUE :: atol_tlm, rtol_tlm, icntrl_u, rcntrl_u, model_params, stream
+      REAL(C_DOUBLE), INTENT(IN) :: atol(*), rtol(*)
+      INTEGER(C_INT) :: istatus(*), ierr(*)
+      INTEGER(C_INT) :: fatode_sdirk_integrate_tlm_batch
     END FUNCTION
   END INTERFACE
 
@@ -215,18 +229,23 @@ CONTAINS
 
   !~~~> TLM/ROS_TLM INTEGRATE_TLM, one system (TLM/ROS_TLM/ROS_TLM_f90_Integrator.F90:35-36).  The engine implements the
   !     forward-error-control mode, ICNTRL_U(12) = 0; ROS_TLM has no IERR_U (failures are printed, :86-89).
+  !     With fatode_b200_set_family(FATODE_FAMILY_SDIRK) the same routine stands in for TLM/SDIRK_TLM's INTEGRATE_TLM
+  !     (TLM/SDIRK_TLM/SDIRK_TLM_f90_Integrator.F90:31-32: no HESS_VEC, IERR_U last); both keyword sets compile unchanged.
   SUBROUTINE INTEGRATE_TLM( N, NTLM, NNZERO, Y, Y_tlm, TIN, TOUT, ATOL_tlm, RTOL_tlm, ATOL, RTOL, FUN, JAC, HESS_VEC, &
-                            ICNTRL_U, RCNTRL_U, ISTATUS_U, RSTATUS_U )
+                            ICNTRL_U, RCNTRL_U, ISTATUS_U, RSTATUS_U, IERR_U )
     INTEGER, INTENT(IN) :: N, NNZERO, NTLM
     DOUBLE PRECISION, INTENT(INOUT) :: Y(N), Y_tlm(N,NTLM)
     DOUBLE PRECISION, INTENT(IN) :: TIN, TOUT
     DOUBLE PRECISION, INTENT(IN), OPTIONAL, TARGET :: RTOL_tlm(N,NTLM), ATOL_tlm(N,NTLM)
     DOUBLE PRECISION, INTENT(IN) :: ATOL(N), RTOL(N)
-    EXTERNAL :: FUN, JAC, HESS_VEC
+    EXTERNAL :: FUN, JAC
+    EXTERNAL :: HESS_VEC
+    OPTIONAL :: HESS_VEC
     INTEGER, INTENT(IN), OPTIONAL, TARGET :: ICNTRL_U(20)
     DOUBLE PRECISION, INTENT(IN), OPTIONAL, TARGET :: RCNTRL_U(20)
     INTEGER, INTENT(OUT), OPTIONAL :: ISTATUS_U(20)
     DOUBLE PRECISION, INTENT(OUT), OPTIONAL :: RSTATUS_U(20)
+    INTEGER, INTENT(OUT), OPTIONAL :: IERR_U
     INTEGER(C_INT) :: ist(20), ierr(1), rc
     REAL(C_DOUBLE) :: rst(20)
     TYPE(C_PTR) :: pic, prc, pat, prt
@@ -236,10 +255,18 @@ CONTAINS
     IF (PRESENT(ATOL_tlm)) pat = C_LOC(ATOL_tlm)
     IF (PRESENT(RTOL_tlm)) prt = C_LOC(RTOL_tlm)
     ist = 0; rst = 0.0d0; ierr = 0
-    rc = fatode_ros_integrate_tlm_batch(current_model, 1_C_INT64_T, INT(N, C_INT), INT(NTLM, C_INT), Y, Y_tlm, TIN, TOUT, &
-                                        pat, prt, ATOL, RTOL, pic, prc, ist, rst, ierr, C_NULL_PTR, FATODE_MEM_HOST, C_NULL_PTR)
-    IF (rc /= 0) ierr(1) = rc
-    IF (ierr(1) < 0) PRINT *, 'Rosenbrock: Unsucessful step at T=', TIN, ' (IERR=', ierr(1), ')'   ! as :86-89
+    IF (current_family == FATODE_FAMILY_SDIRK) THEN
+      rc = fatode_sdirk_integrate_tlm_batch(current_model, 1_C_INT64_T, INT(N, C_INT), INT(NTLM, C_INT), Y, Y_tlm, TIN, TOUT, &
+                                            pat, prt, ATOL, RTOL, pic, prc, ist, rst, ierr, C_NULL_PTR, FATODE_MEM_HOST, C_NULL_PTR)
+      IF (rc /= 0) ierr(1) = rc
+      IF (ierr(1) < 0) PRINT *, 'SDIRK-TLM: Unsuccessful exit at T=', TIN, ' (IERR=', ierr(1), ')'   ! as :94-96
+    ELSE
+      rc = fatode_ros_integrate_tlm_batch(current_model, 1_C_INT64_T, INT(N, C_INT), INT(NTLM, C_INT), Y, Y_tlm, TIN, TOUT, &
+                                          pat, prt, ATOL, RTOL, pic, prc, ist, rst, ierr, C_NULL_PTR, FATODE_MEM_HOST, C_NULL_PTR)
+      IF (rc /= 0) ierr(1) = rc
+      IF (ierr(1) < 0) PRINT *, 'Rosenbrock: Unsucessful step at T=', TIN, ' (IERR=', ierr(1), ')'   ! as :86-89
+    END IF
+    IF (PRESENT(IERR_U)) IERR_U = ierr(1)
     IF (PRESENT(ISTATUS_U)) ISTATUS_U(:) = ist(:)
     IF (PRESENT(RSTATUS_U)) RSTATUS_U(:) = rst(:)
   END SUBROUTINE INTEGRATE_TLM

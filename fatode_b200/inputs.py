@@ -34,3 +34,17 @@ def perturbed_states(base: np.ndarray, ncells: int, first_cell: int = 0, amp: fl
         out[...] = y
         return out
     return y
+
+
+def swe_members(nmembers: int, first_member: int = 0, amp: float = 0.1, seed: int = SEED, amplitude: float = 30.0) -> np.ndarray:
+    """[nmembers, 4800] shallow-water ensemble: the driver's Gaussian bump with amplitude
+    a * (1 + amp * u) per member, u from the same counter-based generator; member 0 keeps the driver's a = 30."""
+    import fatode_b200 as F
+    with np.errstate(over="ignore"):
+        mem = np.arange(first_member, first_member + nmembers, dtype=np.uint64)
+        key = _splitmix64(np.uint64(seed) + _splitmix64(mem * np.uint64(1000003) + np.uint64(4800)))
+    u = 2.0 * ((key >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)) - 1.0
+    a = amplitude * (1.0 + amp * u)
+    if first_member == 0 and nmembers > 0:
+        a[0] = amplitude
+    return np.stack([F.swe_initial_state(float(x)) for x in a]) if nmembers > 0 else np.zeros((0, 4800))

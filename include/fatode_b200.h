@@ -37,7 +37,8 @@ extern "C" {
 enum {
   FATODE_MODEL_ROBERTS = 1,      /* EXAMPLES/roberts/ROBERTS_ROS_ADJ/roberts_ros_adj_dr.F90 : N=3,  NP=3  */
   FATODE_MODEL_SMALL_STRATO = 2, /* EXAMPLES/small_strato/small_ros{,_adj}/User_Parameters.F90 : N=5, NP=0 */
-  FATODE_MODEL_CBM4 = 3          /* EXAMPLES/cbm4/CBM4_ROS_ADJ/cbm4_Parameters.F90          : N=32, NP=29 */
+  FATODE_MODEL_CBM4 = 3,         /* EXAMPLES/cbm4/CBM4_ROS_ADJ/cbm4_Parameters.F90          : N=32, NP=29 */
+  FATODE_MODEL_SWE = 4           /* EXAMPLES/swe/SWE_ERK/swe2D_upwind.F90 (40 x 40 grid)    : N=4800, NP=0; ERK entry points only */
 };
 
 enum { FATODE_MEM_HOST = 0, FATODE_MEM_DEVICE = 1 };
@@ -134,6 +135,34 @@ int fatode_sdirk_integrate_tlm_batch(int model, int64_t ncells, int nvar, int nt
                                      const double* atol, const double* rtol, const int* icntrl_u,
                                      const double* rcntrl_u, int* istatus, double* rstatus, int* ierr,
                                      const double* model_params, int mem, void* stream);
+
+/* INTEGRATE of FWD/ERK (FWD/ERK/ERK_f90_Integrator.F90:28):
+ *   INTEGRATE(TIN,TOUT,NVAR,VAR,RTOL,ATOL,FUN,ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U,Ierr_U)   (no NNZERO, no JAC)
+ * Explicit Runge-Kutta pairs, ICNTRL(3) = 1 Erk23, 2 Erk3_Heun, 3 Erk43, 0/4 Dopri5 (default), 5 Verner, 6 Dopri853; user
+ * values override the defaults when > 0 (:56-61).  Built for the shallow-water ensemble (model FATODE_MODEL_SWE, one member
+ * per system, y [ncells][4800] in the reference's grid2vec order).  Per-member IERR: 1 or the reference's -1..-7.
+ * ISTATUS: Nfun = S * Nstp, Njac = Ndec = Nsol = Nsng = 0. */
+int fatode_erk_integrate_batch(int model, int64_t ncells, int nvar, double* y, double tin, double tout,
+                               const double* atol, const double* rtol, const int* icntrl_u,
+                               const double* rcntrl_u, int* istatus, double* rstatus, int* ierr,
+                               const double* model_params, int mem, void* stream);
+
+/* INTEGRATE_TLM of TLM/ERK_TLM (TLM/ERK_TLM/ERK_TLM_f90_Integrator.F90:28):
+ *   INTEGRATE_TLM(TIN,TOUT,NVAR,NTLM,VAR,VAR_TLM,ATOL_TLM,RTOL_TLM,ATOL,RTOL,FUN,JAC,
+ *                 ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U,IERR_U)
+ * (the C ABI keeps the argument order of the other TLM entry points).  Built: the preset mode, ICNTRL(5) = 0 — Jacobian-vector
+ * products by forward finite differences (FDJACV :1071-1097, increment RCNTRL(12) or sqrt(max(RTOL(1), eps))), one extra
+ * FUN per column per stage, Nfun = S * (1 + NTLM) * Nstp — and ICNTRL(12) = 0; the dense-Jacobian mode and the TLM
+ * truncation-error control return FATODE_EUNSUPPORTED.  y_tlm [ncells][ntlm][4800]. */
+int fatode_erk_integrate_tlm_batch(int model, int64_t ncells, int nvar, int ntlm, double* y, double* y_tlm,
+                                   double tin, double tout, const double* atol_tlm, const double* rtol_tlm,
+                                   const double* atol, const double* rtol, const int* icntrl_u,
+                                   const double* rcntrl_u, int* istatus, double* rstatus, int* ierr,
+                                   const double* model_params, int mem, void* stream);
+
+/* Initial state of the shallow-water drivers: Gaussian bump of the given amplitude on h = 100, constant velocities
+ * (initializeGaussianGrid, EXAMPLES/swe/SWE_ERK/swe2D_upwind.F90:86-126; swe2D_erk_dr.F90:100-103 uses 30, 2, 2). */
+int fatode_swe_initial_state(double amplitude, double u0, double v0, double* y);
 
 /* INTEGRATE of FWD/RK (FWD/RK/RK_f90_Integrator.F90:32):
  *   INTEGRATE(TIN,TOUT,N,NNZERO,VAR,RTOL,ATOL,FUN,JAC,ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U,IERR_U)

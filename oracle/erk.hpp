@@ -1,0 +1,347 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (never linked into the product path).
+//
+// CPU restatement of the reference's explicit Runge-Kutta family and of the shallow-water example it is shipped with:
+//   FWD/ERK/ERK_f90_Integrator.F90            INTEGRATE :28-90 (the `> 0` override rule), ERK (option parsing) :92-362,
+//                                             ERK_Integrator :364-503, ERK_ErrorScale :507-522, ERK_ErrorNorm :526-537,
+//                                             coefficient sets :580-923 (gen/erk_tableau_gen.h)
+//   TLM/ERK_TLM/ERK_TLM_f90_Integrator.F90    INTEGRATE_TLM :28-93, ERKTLM options :95-389 (ICNTRL(5) = 0: finite-difference
+//                                             Jacobian-vector products; ICNTRL(12): TLM truncation error; RCNTRL(12):
+//                                             FDincrement), ERK_IntegratorTLM :391-576, ERK_ErrorNorm_TLM :613-626,
+//                                             FDJACV :1071-1097 (forward difference; it perturbs the stage vector in place,
+//                                             so with NTLM > 1 the perturbations of earlier columns stay in it)
+//   EXAMPLES/swe/SWE_ERK/swe2D_upwind.F90     module constants :11-32, initializeGaussianGrid :86-126, grid2vec :267-289,
+//                                             vec2grid :292-315, compute_F :318-567 (third-order upwind flux splitting,
+//                                             periodic halo); FUN = vec2grid -> compute_F -> grid2vec
+//                                             (EXAMPLES/swe/SWE_ERK/swe2D_erk_dr.F90:2-14)
+// Not restated: the dense-Jacobian TLM mode (ICNTRL(5) /= 0: a full 4800 x 4800 JAC + MATMUL per stage, compute_JacF
+// :570-2128) returns -100.
+// Statement order and BLAS call order follow the Fortran (DAXPY with a zero factor returns at once, as netlib's does);
+// compile with -ffp-contract=off.  Err**(-1/rkELO) goes through o_pow_neg_inv (portable kernel by default, libm pow in
+// ORACLE_LIBM mode).
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "sdirk.hpp"
+#include "gen/erk_tableau_gen.h"
+
+namespace oracle {
+
+// ---- shallow-water model (swe2Dxy_Parameters + compute_F)
+struct Swe {
+  static constexpr int Mx = 40, My = 40, CELLS = Mx * My, N = 3 * CELLS;
+  static constexpr int GX = Mx + 4, GY = My + 4;
+  static constexpr double gAcc = 9.80616;
+  static double dx() { return (3.0 - (-3.0)) / (Mx - 1.0); }
+  static double dy() { return (3.0 - (-3.0)) / (My - 1.0); }
+  std::vector<double> U, F;   // (3, Mx+4, My+4) column-major: U(k,i,j) at k + 3*(i + GX*j), 0-based
+  Swe() : U((size_t)3 * GX * GY, 0.0), F((size_t)3 * GX * GY, 0.0) {}
+  static inline int at(int k, int i, int j) { return k + 3 * (i + GX * j); }   // 0-based k, i, j
+
+  // initializeGaussianGrid :86-126 followed by the drivers' u = v = const (swe2D_erk_dr.F90:100-103) and grid2vec
+  static void initial_state(double A, double u0, double v0, double* vec) {
+    std::vector<double> g((size_t)3 * GX * GY, 0.0), x(GX, 0.0), y(GY, 0.0);
+    for (int i = 3; i <= Mx + 2; ++i) x[i - 1] = -3.0 + (i - 2) * dx();
+    for (int j = 3; j <= My + 2; ++j) y[j - 1] = -3.0 + (j - 2) * dy();
+    for (int j = 3; j <= My + 2; ++j)
+      for (int i = 3; i <= Mx + 2; ++i) g[at(0, i - 1, j - 1)] = A * std::exp(-x[j - 1] * x[j - 1] - y[i - 1] * y[i - 1]);
+    for (int j = 0; j < GY; ++j)
+      for (int i = 0; i < GX; ++i) {
+        g[at(0, i, j)] = g[at(0, i, j)] + 100.0;
+        g[at(1, i, j)] = u0;
+        g[at(2, i, j)] = v0;
+      }
+    grid2vec(g.data(), vec);
+  }
+  static void grid2vec(const double* g, double* vec) {   // :267-289
+    int indx = 0;
+    for (int k = 0; k < 3; ++k)
+      for (int i = 3; i <= Mx + 2; ++i)
+        for (int j = 3; j <= My + 2; ++j) vec[indx++] = g[at(k, i - 1, j - 1)];
+  }
+  static void vec2grid(const double* vec, double* g) {   // :292-315
+    for (size_t q = 0; q < (size_t)3 * GX * GY; ++q) g[q] = 0.0;
+    int indx = 0;
+    for (int k = 0; k < 3; ++k)
+      for (int i = 3; i <= Mx + 2; ++i)
+        for (int j = 3; j <= My + 2; ++j) g[at(k, i - 1, j - 1)] = vec[indx++];
+  }
+  static inline void mv3(const double (&M)[3][3], const double* d, double* out) {   // tmpMV loops
+    for (int i1 = 0; i1 < 3; ++i1) {
+      out[i1] = 0.0;
+      for (int j1 = 0; j1 < 3; ++j1) out[i1] = out[i1] + M[i1][j1] * d[j1];
+    }
+  }
+  void compute_F() {   // :318-567 (1-based i, j below; u(k,i,j) is 1-based in all three indices)
+    double* Ug = U.data();
+    auto u = [&](int k, int i, int j) -> double& { return Ug[at(k - 1, i - 1, j - 1)]; };
+    for (int k = 1; k <= 3; ++k) {
+      for (int j = 3; j <= My + 2; ++j) {
+        u(k, 2, j) = u(k, Mx + 2, j);
+        u(k, 1, j) = u(k, Mx + 1, j);
+        u(k, Mx + 3, j) = u(k, 3, j);
+        u(k, Mx + 4, j) = u(k, 4, j);
+      }
+      for (int i = 3; i <= Mx + 2; ++i) {
+        u(k, i, 2) = u(k, i, My + 2);
+        u(k, i, 1) = u(k, i, My + 1);
+        u(k, i, My + 3) = u(k, i, 3);
+        u(k, i, My + 4) = u(k, i, 4);
+      }
+    }
+    const double g = gAcc, ddx = dx(), ddy = dy();
+    for (int j = 3; j <= My + 2; ++j)
+      for (int i = 3; i <= Mx + 2; ++i) {
+        double eigf[3], eigg[3], Fu1[3][3] = {{0}}, Fu2[3][3] = {{0}}, Fu3[3][3] = {{0}}, Gu1[3][3] = {{0}}, Gu2[3][3] = {{0}},
+                                 Gu3[3][3] = {{0}};
+        double dUdxMinus[3], dUdxPlus[3], dUdyMinus[3], dUdyPlus[3], tmpF[3], tmpG[3], tmpMV[3];
+        eigf[0] = u(2, i, j) / u(1, i, j);
+        eigf[1] = u(2, i, j) / u(1, i, j) - std::sqrt(gAcc * u(1, i, j));
+        eigf[2] = u(2, i, j) / u(1, i, j) + std::sqrt(gAcc * u(1, i, j));
+        const double hc = u(1, i, j), uc = u(2, i, j) / u(1, i, j), vc = u(3, i, j) / u(1, i, j);
+        Fu1[2][0] = -vc;
+        Fu1[2][2] = 1.0;
+        double isqrt = 1.0 / std::sqrt(g * hc);
+        Fu2[0][0] = 0.5 * (1.0 + uc * isqrt);
+        Fu2[0][1] = -0.5 * isqrt;
+        Fu2[1][0] = 0.5 * (uc * uc - g * hc) * isqrt;
+        Fu2[1][1] = 0.5 - 0.5 * uc * isqrt;
+        Fu2[2][0] = 0.5 * (1.0 + uc * isqrt) * vc;
+        Fu2[2][1] = -0.5 * vc * isqrt;
+        Fu3[0][0] = 0.5 - 0.5 * uc * isqrt;
+        Fu3[0][1] = 0.5 * isqrt;
+        Fu3[1][0] = 0.5 * (g * hc - uc * uc) * isqrt;
+        Fu3[1][1] = 0.5 * (1.0 + uc * isqrt);
+        Fu3[2][0] = 0.5 * (1.0 - uc * isqrt) * vc;
+        Fu3[2][1] = 0.5 * vc * isqrt;
+        for (int k = 1; k <= 3; ++k) {
+          dUdxMinus[k - 1] = (-u(k, i + 2, j) + 6.0 * u(k, i + 1, j) - 3.0 * u(k, i, j) - 2.0 * u(k, i - 1, j)) / (6.0 * ddx);
+          dUdxPlus[k - 1] = (2.0 * u(k, i + 1, j) + 3.0 * u(k, i, j) - 6.0 * u(k, i - 1, j) + u(k, i - 2, j)) / (6.0 * ddx);
+        }
+        mv3(Fu1, eigf[0] >= 0.0 ? dUdxPlus : dUdxMinus, tmpMV);
+        for (int k = 0; k < 3; ++k) tmpF[k] = eigf[0] * tmpMV[k];
+        mv3(Fu2, eigf[1] >= 0.0 ? dUdxPlus : dUdxMinus, tmpMV);
+        for (int k = 0; k < 3; ++k) tmpF[k] = tmpF[k] + eigf[1] * tmpMV[k];
+        mv3(Fu3, eigf[2] >= 0.0 ? dUdxPlus : dUdxMinus, tmpMV);
+        for (int k = 0; k < 3; ++k) tmpF[k] = tmpF[k] + eigf[2] * tmpMV[k];
+        eigg[0] = u(3, i, j) / u(1, i, j);
+        eigg[1] = u(3, i, j) / u(1, i, j) - std::sqrt(gAcc * u(1, i, j));
+        eigg[2] = u(3, i, j) / u(1, i, j) + std::sqrt(gAcc * u(1, i, j));
+        Gu1[1][0] = -uc;
+        Gu1[1][1] = 1.0;
+        isqrt = 1.0 / std::sqrt(g * hc);
+        Gu2[0][0] = 0.5 * (1.0 + vc * isqrt);
+        Gu2[0][2] = -0.5 * isqrt;
+        Gu2[1][0] = 0.5 * uc * (1.0 + vc * isqrt);
+        Gu2[1][2] = -0.5 * uc * isqrt;
+        Gu2[2][0] = 0.5 * (vc * vc - g * hc) * isqrt;
+        Gu2[2][2] = 0.5 - 0.5 * vc * isqrt;
+        Gu3[0][0] = 0.5 * (1.0 - vc * isqrt);
+        Gu3[0][2] = 0.5 * isqrt;
+        Gu3[1][0] = 0.5 * uc * (1.0 - vc * isqrt);
+        Gu3[1][2] = 0.5 * uc * isqrt;
+        Gu3[2][0] = 0.5 * (-vc * vc + g * hc) * isqrt;
+        Gu3[2][2] = 0.5 + 0.5 * vc * isqrt;
+        for (int k = 1; k <= 3; ++k) {
+          dUdyMinus[k - 1] = (-u(k, i, j + 2) + 6.0 * u(k, i, j + 1) - 3.0 * u(k, i, j) - 2.0 * u(k, i, j - 1)) / (6.0 * ddy);
+          dUdyPlus[k - 1] = (2.0 * u(k, i, j + 1) + 3.0 * u(k, i, j) - 6.0 * u(k, i, j - 1) + u(k, i, j - 2)) / (6.0 * ddy);
+        }
+        mv3(Gu1, eigg[0] >= 0.0 ? dUdyPlus : dUdyMinus, tmpMV);
+        for (int k = 0; k < 3; ++k) tmpG[k] = eigg[0] * tmpMV[k];
+        mv3(Gu2, eigg[1] >= 0.0 ? dUdyPlus : dUdyMinus, tmpMV);
+        for (int k = 0; k < 3; ++k) tmpG[k] = tmpG[k] + eigg[1] * tmpMV[k];
+        mv3(Gu3, eigg[2] >= 0.0 ? dUdyPlus : dUdyMinus, tmpMV);
+        for (int k = 0; k < 3; ++k) tmpG[k] = tmpG[k] + eigg[2] * tmpMV[k];
+        for (int k = 0; k < 3; ++k) F[at(k, i - 1, j - 1)] = -tmpF[k] - tmpG[k];
+      }
+  }
+  void fun(double /*t*/, const double* y, double* p) {   // swe2D_erk_dr.F90:2-14
+    vec2grid(y, U.data());
+    compute_F();
+    grid2vec(F.data(), p);
+  }
+};
+
+struct ErkConfig {
+  ErkTableauData tab;
+  int ITOL, Max_no_steps;
+  bool FDAprox = true, TLMtruncErr = false;
+  double Roundoff, Hmin, Hmax, Hstart, FacMin, FacMax, FacRej, FacSafe, Qmin, Qmax, FDincrement;
+};
+
+// ERK :229-358 / ERKTLM :238-389.  Returns Ierr (0 = fine; the reference keeps parsing after an option error).
+static inline int erk_parse(int N, const int* ICNTRL, const double* RCNTRL, double Tinitial, double Tfinal, const double* AbsTol,
+                            const double* RelTol, bool tlm, ErkConfig& c) {
+  int Ierr = 0;
+  c.ITOL = (ICNTRL[1] == 0) ? 1 : 0;
+  int method = 4;
+  switch (ICNTRL[2]) {
+    case 1: method = 1; break;
+    case 2: method = 2; break;
+    case 3: method = 3; break;
+    case 5: method = 5; break;
+    case 6: method = 6; break;
+    default: method = 4;   // 0, 4 and CASE DEFAULT: Dopri5
+  }
+  c.tab = ERK_TABLEAU[method - 1];
+  if (ICNTRL[3] == 0) c.Max_no_steps = 10000;
+  else if (ICNTRL[3] > 0) c.Max_no_steps = ICNTRL[3];
+  else { c.Max_no_steps = 0; Ierr = -1; }
+  if (tlm) {
+    c.FDAprox = (ICNTRL[4] == 0);
+    c.TLMtruncErr = (ICNTRL[11] != 0);
+  }
+  c.Roundoff = 1.1102230246251565e-16;   // DLAMCH('E')
+  if (RCNTRL[0] == 0.0) c.Hmin = 0.0; else if (RCNTRL[0] > 0.0) c.Hmin = RCNTRL[0]; else { c.Hmin = 0.0; Ierr = -3; }
+  const double span = std::fabs(Tfinal - Tinitial);
+  if (RCNTRL[1] == 0.0) c.Hmax = span; else if (RCNTRL[1] > 0.0) c.Hmax = std::fmin(std::fabs(RCNTRL[1]), span); else { c.Hmax = span; Ierr = -3; }
+  if (RCNTRL[2] == 0.0) c.Hstart = std::fmax(c.Hmin, c.Roundoff);
+  else if (RCNTRL[2] > 0.0) c.Hstart = std::fmin(std::fabs(RCNTRL[2]), span);
+  else { c.Hstart = 0.0; Ierr = -3; }
+  if (RCNTRL[3] == 0.0) c.FacMin = (double)0.2f; else if (RCNTRL[3] > 0.0) c.FacMin = RCNTRL[3]; else { c.FacMin = 0.0; Ierr = -4; }
+  if (RCNTRL[4] == 0.0) c.FacMax = (double)10.0f; else if (RCNTRL[4] > 0.0) c.FacMax = RCNTRL[4]; else { c.FacMax = 0.0; Ierr = -4; }
+  if (RCNTRL[5] == 0.0) c.FacRej = (double)0.1f; else if (RCNTRL[5] > 0.0) c.FacRej = RCNTRL[5]; else { c.FacRej = 0.0; Ierr = -4; }
+  if (RCNTRL[6] == 0.0) c.FacSafe = (double)0.9f; else if (RCNTRL[6] > 0.0) c.FacSafe = RCNTRL[6]; else { c.FacSafe = 0.0; Ierr = -4; }
+  c.Qmin = (RCNTRL[9] == 0.0) ? 1.0 : RCNTRL[9];
+  c.Qmax = (RCNTRL[10] == 0.0) ? 1.2 : RCNTRL[10];
+  c.FDincrement = (RCNTRL[11] == 0.0) ? std::sqrt(std::fmax(RelTol[0], c.Roundoff)) : RCNTRL[11];
+  if (c.ITOL == 0) {
+    if (AbsTol[0] <= 0.0 || RelTol[0] <= 10.0 * c.Roundoff) Ierr = -5;
+  } else {
+    for (int i = 0; i < N; ++i)
+      if (AbsTol[i] <= 0.0 || RelTol[i] <= 10.0 * c.Roundoff) Ierr = -5;
+  }
+  return Ierr;
+}
+
+template <class Model>
+struct Erk {
+  static constexpr int N = Model::N;
+  Model& mdl;
+  ErkConfig cfg;
+  int ISTATUS[20];
+  double RSTATUS[20];
+  explicit Erk(Model& m) : mdl(m) { std::memset(ISTATUS, 0, sizeof ISTATUS); std::memset(RSTATUS, 0, sizeof RSTATUS); }
+
+  static void daxpy(int n, double a, const double* x, double* y) {
+    if (a == 0.0) return;
+    for (int i = 0; i < n; ++i) y[i] = y[i] + a * x[i];
+  }
+  void error_scale(const double* AbsTol, const double* RelTol, const double* Y, double* SCAL) const {
+    for (int i = 0; i < N; ++i)
+      SCAL[i] = (cfg.ITOL == 0) ? 1.0 / (AbsTol[0] + RelTol[0] * std::fabs(Y[i])) : 1.0 / (AbsTol[i] + RelTol[i] * std::fabs(Y[i]));
+  }
+  static double error_norm(const double* Y, const double* SCAL) {
+    double Err = 0.0;
+    for (int i = 0; i < N; ++i) { const double q = Y[i] * SCAL[i]; Err = Err + q * q; }
+    return std::fmax(std::sqrt(Err / (double)N), 1.0e-10);
+  }
+
+  // ERK_Integrator (NTLM = 0) / ERK_IntegratorTLM (FD mode).  Y_TLM (N, NTLM) column-major.
+  int integrate(int NTLM, double* Y, double* Y_TLM, double Tinitial, double Tfinal, const double* AbsTol, const double* RelTol,
+                const double* AbsTol_TLM, const double* RelTol_TLM) {
+    const ErkTableauData& tb = cfg.tab;
+    const int S = tb.S;
+    std::vector<double> K((size_t)N * S), TMP(N), SCAL(N), S_TLM(N), SCAL_TLM(N), K_TLM((size_t)N * S * std::max(NTLM, 1)),
+        Yerr_TLM((size_t)N * std::max(NTLM, 1));
+    auto Kt = [&](int istage, int itlm) { return K_TLM.data() + ((size_t)itlm * S + istage) * N; };
+    const double Roundoff = cfg.Roundoff;
+    double T = Tinitial;
+    const double Tdirection = (Tfinal - Tinitial) >= 0.0 ? 1.0 : -1.0;
+    double H = std::fmax(std::fabs(cfg.Hmin), std::fabs(cfg.Hstart));
+    if (std::fabs(H) <= 10.0 * Roundoff) H = 1.0e-6;
+    H = std::fmin(std::fabs(H), cfg.Hmax);
+    H = std::copysign(H, Tdirection);
+    bool Reject = false, FirstStep = true;
+    error_scale(AbsTol, RelTol, Y, SCAL.data());
+    while ((Tfinal - T) * Tdirection - Roundoff > 0.0) {
+      if (ISTATUS[Nstp] > cfg.Max_no_steps) return -6;
+      if ((T + 0.1 * H == T) || (std::fabs(H) <= Roundoff)) return -7;
+      for (int istage = 1; istage <= S; ++istage) {
+        double* Ki = K.data() + (size_t)(istage - 1) * N;
+        for (int i = 0; i < N; ++i) Ki[i] = 0.0;
+        for (int i = 0; i < N; ++i) TMP[i] = 0.0;
+        for (int j = 1; j <= istage - 1; ++j) daxpy(N, H * tb.A[istage - 1][j - 1], K.data() + (size_t)(j - 1) * N, TMP.data());
+        daxpy(N, 1.0, Y, TMP.data());
+        mdl.fun(T + tb.C[istage - 1] * H, TMP.data(), Ki);
+        ISTATUS[Nfun]++;
+        for (int itlm = 0; itlm < NTLM; ++itlm) {
+          for (int i = 0; i < N; ++i) S_TLM[i] = Y_TLM[(size_t)itlm * N + i];
+          for (int j = 1; j <= istage - 1; ++j) daxpy(N, H * tb.A[istage - 1][j - 1], Kt(j - 1, itlm), S_TLM.data());
+          // FDJACV(N, T + c H, TMP, S_TLM, K(:,istage), K_TLM(:,istage,itlm)) :1071-1097
+          double* Kc = Kt(istage - 1, itlm);
+          daxpy(N, cfg.FDincrement, S_TLM.data(), TMP.data());
+          mdl.fun(T + tb.C[istage - 1] * H, TMP.data(), Kc);
+          ISTATUS[Nfun]++;
+          daxpy(N, -1.0, Ki, Kc);
+          { const double a = 1.0 / cfg.FDincrement; for (int i = 0; i < N; ++i) Kc[i] = a * Kc[i]; }
+        }
+      }
+      ISTATUS[Nstp]++;
+      for (int i = 0; i < N; ++i) TMP[i] = 0.0;
+      for (int i = 1; i <= S; ++i)
+        if (tb.E[i - 1] != 0.0) daxpy(N, H * tb.E[i - 1], K.data() + (size_t)(i - 1) * N, TMP.data());
+      double Err = error_norm(TMP.data(), SCAL.data());
+      if (NTLM > 0 && cfg.TLMtruncErr) {
+        for (size_t q = 0; q < (size_t)N * NTLM; ++q) Yerr_TLM[q] = 0.0;
+        for (int itlm = 0; itlm < NTLM; ++itlm)
+          for (int j = 1; j <= S; ++j)
+            if (tb.E[j - 1] != 0.0) daxpy(N, H * tb.E[j - 1], Kt(j - 1, itlm), Yerr_TLM.data() + (size_t)itlm * N);
+        for (int itlm = 0; itlm < NTLM; ++itlm) {   // ERK_ErrorNorm_TLM: scaled by the error vector itself (:619-624)
+          const double* Ye = Yerr_TLM.data() + (size_t)itlm * N;
+          for (int i = 0; i < N; ++i)
+            SCAL_TLM[i] = (cfg.ITOL == 0) ? 1.0 / (AbsTol_TLM[(size_t)itlm * N] + RelTol_TLM[(size_t)itlm * N] * std::fabs(Ye[i]))
+                                          : 1.0 / (AbsTol_TLM[(size_t)itlm * N + i] + RelTol_TLM[(size_t)itlm * N + i] * std::fabs(Ye[i]));
+          Err = std::fmax(Err, error_norm(Ye, SCAL_TLM.data()));
+        }
+      }
+      double Fac = cfg.FacSafe * o_pow_neg_inv(Err, tb.ELO);
+      Fac = std::fmax(cfg.FacMin, std::fmin(cfg.FacMax, Fac));
+      double Hnew = H * Fac;
+      if (Err < 1.0) {
+        FirstStep = false;
+        ISTATUS[Nacc]++;
+        T = T + H;
+        for (int i = 1; i <= S; ++i) {
+          if (tb.B[i - 1] != 0.0) daxpy(N, H * tb.B[i - 1], K.data() + (size_t)(i - 1) * N, Y);
+          for (int itlm = 0; itlm < NTLM; ++itlm) daxpy(N, H * tb.B[i - 1], Kt(i - 1, itlm), Y_TLM + (size_t)itlm * N);
+        }
+        error_scale(AbsTol, RelTol, Y, SCAL.data());
+        Hnew = Tdirection * std::fmin(std::fabs(Hnew), cfg.Hmax);
+        RSTATUS[Ntexit] = T;
+        RSTATUS[Nhexit] = H;
+        RSTATUS[Nhnew] = Hnew;
+        if (Reject) Hnew = Tdirection * std::fmin(std::fabs(Hnew), std::fabs(H));
+        Reject = false;
+        if ((T + Hnew / cfg.Qmin - Tfinal) * Tdirection > 0.0) H = Tfinal - T;
+        else H = Hnew;
+      } else {
+        if (FirstStep || Reject) H = cfg.FacRej * H; else H = Hnew;
+        Reject = true;
+        if (ISTATUS[Nacc] >= 1) ISTATUS[Nrej]++;
+      }
+    }
+    return 1;
+  }
+};
+
+// INTEGRATE of FWD/ERK (NTLM = 0, Y_TLM = NULL) and INTEGRATE_TLM of TLM/ERK_TLM
+template <class Model>
+int erk_integrate(Model& mdl, int NTLM, double* Y, double* Y_TLM, double TIN, double TOUT, const double* ATOL_TLM, const double* RTOL_TLM,
+                  const double* ATOL, const double* RTOL, const int* ICNTRL_U, const double* RCNTRL_U, int* ISTATUS_U, double* RSTATUS_U) {
+  int ICNTRL[20] = {0};
+  double RCNTRL[20] = {0};
+  if (ICNTRL_U) for (int i = 0; i < 20; ++i) if (ICNTRL_U[i] > 0) ICNTRL[i] = ICNTRL_U[i];
+  if (RCNTRL_U) for (int i = 0; i < 20; ++i) if (RCNTRL_U[i] > 0) RCNTRL[i] = RCNTRL_U[i];
+  Erk<Model> s(mdl);
+  const bool tlm = NTLM > 0;
+  int Ierr = erk_parse(Model::N, ICNTRL, RCNTRL, TIN, TOUT, ATOL, RTOL, tlm, s.cfg);
+  if (Ierr >= 0 && tlm && !s.cfg.FDAprox) Ierr = -100;   // dense-Jacobian TLM mode: not restated
+  if (Ierr >= 0 && tlm && s.cfg.TLMtruncErr && (!ATOL_TLM || !RTOL_TLM)) Ierr = -100;
+  if (Ierr >= 0) Ierr = s.integrate(NTLM, Y, Y_TLM, TIN, TOUT, ATOL, RTOL, ATOL_TLM, RTOL_TLM);
+  if (ISTATUS_U) for (int i = 0; i < 20; ++i) ISTATUS_U[i] = s.ISTATUS[i];
+  if (RSTATUS_U) for (int i = 0; i < 20; ++i) RSTATUS_U[i] = s.RSTATUS[i];
+  return Ierr;
+}
+
+}  // namespace oracle

@@ -11,10 +11,11 @@
 #include "rk.hpp"
 #include "rk_adj.hpp"
 #include "sdirk_tlm.hpp"
+#include "erk.hpp"
 
 using namespace oracle;
 
-enum { MODEL_ROBERTS = 1, MODEL_SMALL_STRATO = 2, MODEL_CBM4 = 3 };
+enum { MODEL_ROBERTS = 1, MODEL_SMALL_STRATO = 2, MODEL_CBM4 = 3, MODEL_SWE = 4 };
 
 template <class M>
 static void adj_batch(long ncells, int np, int nadj, double* y, double* lambda, double* mu, double tin, double tout,
@@ -151,6 +152,26 @@ int oracle_sdirk_tlm_batch(int model, long ncells, int ntlm, double* y, double* 
   }
   return 0;
 }
+
+// INTEGRATE of FWD/ERK (ntlm = 0, y_tlm = NULL) / INTEGRATE_TLM of TLM/ERK_TLM looped over systems; model 4 = the
+// shallow-water example (N = 4800): y[member][N], y_tlm[member][NTLM][N]
+int oracle_erk_batch(int model, long ncells, int ntlm, double* y, double* y_tlm, double tin, double tout, const double* atol_tlm,
+                     const double* rtol_tlm, const double* atol, const double* rtol, const int* icntrl, const double* rcntrl,
+                     int* istatus, double* rstatus, int* ierr, int nthreads) {
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+  for (long c = 0; c < ncells; ++c) {
+    switch (model) {
+      case MODEL_SWE: { Swe m; ierr[c] = erk_integrate<Swe>(m, ntlm, y + c * Swe::N, y_tlm ? y_tlm + c * (long)Swe::N * ntlm : nullptr, tin, tout, atol_tlm, rtol_tlm, atol, rtol, icntrl, rcntrl, istatus + c * 20, rstatus + c * 20); break; }
+      case MODEL_SMALL_STRATO: { SmallStrato m; ierr[c] = erk_integrate<SmallStrato>(m, ntlm, y + c * SmallStrato::N, y_tlm ? y_tlm + c * (long)SmallStrato::N * ntlm : nullptr, tin, tout, atol_tlm, rtol_tlm, atol, rtol, icntrl, rcntrl, istatus + c * 20, rstatus + c * 20); break; }
+      default: ierr[c] = -100;
+    }
+  }
+  return 0;
+}
+// initializeGaussianGrid(A) + u = u0, v = v0 + grid2vec (EXAMPLES/swe/SWE_ERK/swe2D_erk_dr.F90:100-103)
+int oracle_swe_initial_state(double A, double u0, double v0, double* vec) { Swe::initial_state(A, u0, v0, vec); return 0; }
+int oracle_swe_fun(const double* y, double* p) { Swe m; m.fun(0.0, y, p); return 0; }
 
 // FWD/SDIRK INTEGRATE looped over cells
 int oracle_sdirk_fwd_batch(int model, long ncells, double* y, double tin, double tout, const double* atol, const double* rtol,

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int)
-MODEL = {"roberts": 1, "small_strato": 2, "cbm4": 3}
+MODEL = {"roberts": 1, "small_strato": 2, "cbm4": 3, "swe": 4}
 _lib = None
 
 
@@ -32,6 +32,9 @@ def lib():
         L.oracle_ros_tlm_batch.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_int, _dp, _dp, ctypes.c_double, ctypes.c_double,
                                            _dp, _dp, _dp, _dp, _ip, _dp, _ip, _dp, _ip, ctypes.c_int]
         L.oracle_sdirk_tlm_batch.argtypes = L.oracle_ros_tlm_batch.argtypes
+        L.oracle_erk_batch.argtypes = L.oracle_ros_tlm_batch.argtypes
+        L.oracle_swe_initial_state.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_double, _dp]
+        L.oracle_swe_fun.argtypes = [_dp, _dp]
         _lib = L
     return _lib
 
@@ -183,5 +186,43 @@ def sdirk_tlm(model, y, y_tlm, tin, tout, atol, rtol, icntrl=None, rcntrl=None, 
     r = lib().oracle_sdirk_tlm_batch(MODEL[model], nc, ntlm, _d(y), _d(yt), tin, tout, None if at is None else _d(at),
                                      None if rt is None else _d(rt), _d(atol), _d(rtol), _i(ic), _d(rc), _i(ist), _d(rst),
                                      _i(ierr), nthreads)
+    assert r == 0
+    return dict(y=y, y_tlm=yt, istatus=ist, rstatus=rst, ierr=ierr)
+
+
+SWE_N = 4800
+
+
+def swe_initial_state(amplitude=30.0, u0=2.0, v0=2.0):
+    """Gaussian bump of the SWE drivers (EXAMPLES/swe/SWE_ERK/swe2D_erk_dr.F90:100-103)."""
+    y = np.zeros(SWE_N)
+    lib().oracle_swe_initial_state(float(amplitude), float(u0), float(v0), _d(y))
+    return y
+
+
+def swe_fun(y):
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    p = np.zeros(SWE_N)
+    lib().oracle_swe_fun(_d(y), _d(p))
+    return p
+
+
+def erk(model, y, tin, tout, atol, rtol, icntrl=None, rcntrl=None, y_tlm=None, atol_tlm=None, rtol_tlm=None, nthreads=0):
+    """INTEGRATE (FWD/ERK) or, with y_tlm [ncells, NTLM, N], INTEGRATE_TLM (TLM/ERK_TLM, finite-difference mode)."""
+    y = np.atleast_2d(np.array(y, dtype=np.float64, order="C"))
+    nc, n = y.shape
+    yt = None if y_tlm is None else np.array(y_tlm, dtype=np.float64, order="C").reshape(nc, -1, n)
+    ntlm = 0 if yt is None else yt.shape[1]
+    ic, rc = _ctrl(icntrl, rcntrl)
+    atol = np.ascontiguousarray(atol, dtype=np.float64)
+    rtol = np.ascontiguousarray(rtol, dtype=np.float64)
+    at = None if atol_tlm is None else np.ascontiguousarray(atol_tlm, dtype=np.float64)
+    rt = None if rtol_tlm is None else np.ascontiguousarray(rtol_tlm, dtype=np.float64)
+    ist = np.zeros((nc, 20), dtype=np.int32)
+    rst = np.zeros((nc, 20))
+    ierr = np.zeros(nc, dtype=np.int32)
+    r = lib().oracle_erk_batch(MODEL[model], nc, ntlm, _d(y), None if yt is None else _d(yt), tin, tout,
+                               None if at is None else _d(at), None if rt is None else _d(rt), _d(atol), _d(rtol), _i(ic), _d(rc),
+                               _i(ist), _d(rst), _i(ierr), nthreads)
     assert r == 0
     return dict(y=y, y_tlm=yt, istatus=ist, rstatus=rst, ierr=ierr)
