@@ -242,6 +242,37 @@ def run_side_workload(args):
         desc = ("EXAMPLES/cbm4 ADJ/RK_ADJ: Radau-2A (ICNTRL(3)=1), NADJ=32, NP=29, fixed-sweep discrete adjoint, 12h..84h, "
                 "rtol 0.1f*1e-5, atol 0.1f*1e-7 (cbm4_rk_adj_dr.F90)")
         ncpu = 32
+    elif w == "cbm4_sdirk_tlm":
+        nc = args.cells if args.cells != 131072 else 9472
+        rtol, atol = tolerances()
+        y0 = perturbed_states(F.initial_state("cbm4"), nc)
+        eye = np.eye(32)
+        run = lambda y: F.integrate_tlm("cbm4", T0, T1, y, np.broadcast_to(eye, (y.shape[0], 32, 32)).copy(), rtol, atol, family="sdirk")
+        cpu = lambda y: O.sdirk_tlm("cbm4", y, np.broadcast_to(eye, (y.shape[0], 32, 32)).copy(), T0, T1, atol, rtol)
+        desc = ("EXAMPLES/cbm4 TLM/SDIRK_TLM: Sdirk4a, NTLM=32, Y_tlm(t0)=I, modified-Newton TLM (presets), 12h..84h, "
+                "driver tolerances of ROS_ADJ (BASELINE config 4)")
+        ncpu = 32
+    elif w in ("swe_erk", "swe_erk_tlm"):
+        from fatode_b200.inputs import swe_members
+        tlm = w == "swe_erk_tlm"
+        nc = args.cells if args.cells != 131072 else (16384 if tlm else 65536)
+        dt = float(np.float32(2.1573758800627289e-003))
+        tol = np.full(4800, 1.0e-4)
+        t1 = (5 if tlm else 50) * dt
+        y0 = swe_members(nc)
+        e1 = np.zeros((1, 4800))
+        e1[0, 0] = 1.0
+        if tlm:
+            run = lambda y: F.integrate_erk("swe", 0.0, t1, y, tol, tol, var_tlm=np.broadcast_to(e1, (y.shape[0], 1, 4800)).copy())
+            cpu = lambda y: O.erk("swe", y, 0.0, t1, tol, tol, y_tlm=np.broadcast_to(e1, (y.shape[0], 1, 4800)).copy())
+            desc = ("EXAMPLES/swe TLM/ERK_TLM: Dopri5, NTLM=1, Y_tlm=e_1, finite-difference Jacobian-vector products, t=0..5 dt, "
+                    "rtol=atol=1e-4, Gaussian bump a=30(1+0.1u) per member (BASELINE config 5)")
+        else:
+            run = lambda y: F.integrate_erk("swe", 0.0, t1, y, tol, tol)
+            cpu = lambda y: O.erk("swe", y, 0.0, t1, tol, tol)
+            desc = ("EXAMPLES/swe FWD/ERK: Dopri5, 40x40 grid (N=4800), t=0..50 dt, rtol=atol=1e-4, Gaussian bump a=30(1+0.1u) per "
+                    "member (BASELINE config 5)")
+        ncpu = 128
     elif w == "cbm4_rk":
         nc = args.cells if args.cells != 131072 else 18944
         rtol, atol = np.full(N, F01 * 1.0e-5), np.full(N, F01 * 1.0e-7)
@@ -284,6 +315,14 @@ def run_side_workload(args):
             "cpu_baseline": {"value": ncpu / tc, "unit": "cells/s", "cores": cores, "kind": "port",
                              "sample": f"{ncpu} cells, {tc:.1f} s, OpenMP over cells"},
             "bitwise_equal_to_oracle_on_sample": same}
+    if w.startswith("swe_"):
+        # ~0.51 Mflop per FUN (1600 grid cells x ~320 flop) + 2 flop per component per stage-sum term
+        nfun = float(r.istatus[:, 0].sum())
+        line["unit"] = line["e2e"]["unit"] = line["cpu_baseline"]["unit"] = "members/s"
+        line["fun_evaluations_per_s"] = nfun / (np.mean(dev_ms) * 1e-3)
+        line["algorithmic_tflops"] = nfun * 0.51e6 / (np.mean(dev_ms) * 1e-3) / 1e12
+        line["config"]["layout"] = ("one member per CTA: Y and the stage vector in shared memory, K_1..K_S in an L2-resident per-CTA "
+                                    "scratch; HBM traffic = Y in + Y out (76.8 kB per member)")
     print(json.dumps(line), flush=True)
 
 
@@ -296,7 +335,7 @@ def main():
     ap.add_argument("--impl", default="fatode_b200", choices=["fatode_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="cbm4_ros_adj", choices=["cbm4_ros_adj", "small_strato_fwd", "cbm4_ros_tlm", "cbm4_sdirk", "cbm4_rk", "cbm4_rk_adj"],
+    ap.add_argument("--workload", default="cbm4_ros_adj", choices=["cbm4_ros_adj", "small_strato_fwd", "cbm4_ros_tlm", "cbm4_sdirk", "cbm4_rk", "cbm4_rk_adj", "cbm4_sdirk_tlm", "swe_erk", "swe_erk_tlm"],
                     help="cbm4_ros_adj = the headline metric (default); the others are side measurements of the other "
                          "BASELINE configs / entry points (single GPU, one JSON line each, not the driver's metric)")
     args = ap.parse_args()

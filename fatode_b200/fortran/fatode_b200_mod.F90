@@ -11,6 +11,8 @@
 !     MODULE RK_f90_Integrator      :: INTEGRATE       (FWD/RK/RK_f90_Integrator.F90:32)         after fatode_b200_set_family(FATODE_FAMILY_RK)
 !     MODULE RK_adj_f90_Integrator  :: INTEGRATE_ADJ   (ADJ/RK_ADJ/RK_ADJ_f90_Integrator.F90:20) after fatode_b200_set_family(FATODE_FAMILY_RK)
 !     MODULE SDIRK_TLM_f90_Integrator :: INTEGRATE_TLM (TLM/SDIRK_TLM/SDIRK_TLM_f90_Integrator.F90:31) after fatode_b200_set_family(FATODE_FAMILY_SDIRK)
+!     MODULE ERK_f90_Integrator     :: INTEGRATE       (FWD/ERK/ERK_f90_Integrator.F90:28)       as INTEGRATE_ERK (rename on the USE line)
+!     MODULE ERK_TLM_f90_Integrator :: INTEGRATE_TLM   (TLM/ERK_TLM/ERK_TLM_f90_Integrator.F90:28) as INTEGRATE_ERK_TLM
 !  (upstream the forward families are separate modules that all export INTEGRATE with the same argument list; the
 !  application picks one with its USE line, here with fatode_b200_set_family)
 !  Dummy-argument names and order are the reference's, so keyword calls such as
@@ -28,10 +30,11 @@ MODULE fatode_b200_mod
   IMPLICIT NONE
   PRIVATE
   PUBLIC :: INTEGRATE, INTEGRATE_ADJ, INTEGRATE_TLM, INTEGRATE_BATCH, INTEGRATE_ADJ_BATCH, fatode_b200_set_model
+  PUBLIC :: INTEGRATE_ERK, INTEGRATE_ERK_TLM
   PUBLIC :: fatode_b200_set_family, FATODE_FAMILY_ROS, FATODE_FAMILY_SDIRK, FATODE_FAMILY_RK
-  PUBLIC :: FATODE_MODEL_ROBERTS, FATODE_MODEL_SMALL_STRATO, FATODE_MODEL_CBM4
+  PUBLIC :: FATODE_MODEL_ROBERTS, FATODE_MODEL_SMALL_STRATO, FATODE_MODEL_CBM4, FATODE_MODEL_SWE
 
-  INTEGER(C_INT), PARAMETER :: FATODE_MODEL_ROBERTS = 1, FATODE_MODEL_SMALL_STRATO = 2, FATODE_MODEL_CBM4 = 3
+  INTEGER(C_INT), PARAMETER :: FATODE_MODEL_ROBERTS = 1, FATODE_MODEL_SMALL_STRATO = 2, FATODE_MODEL_CBM4 = 3, FATODE_MODEL_SWE = 4
   INTEGER(C_INT), PARAMETER :: FATODE_MEM_HOST = 0
   INTEGER, PARAMETER :: FATODE_FAMILY_ROS = 0, FATODE_FAMILY_SDIRK = 1, FATODE_FAMILY_RK = 2
   INTEGER(C_INT), SAVE :: current_model = FATODE_MODEL_CBM4
@@ -61,6 +64,31 @@ MODULE fatode_b200_mod
       TYPE(C_PTR), VALUE :: icntrl_u, rcntrl_u, model_params, stream
       INTEGER(C_INT) :: istatus(*), ierr(*)
       INTEGER(C_INT) :: fatode_sdirk_integrate_batch
+    END FUNCTION
+    FUNCTION fatode_erk_integrate_batch(model, ncells, nvar, y, tin, tout, atol, rtol, icntrl_u, rcntrl_u, &
+                                        istatus, rstatus, ierr, model_params, mem, stream) BIND(C, NAME='fatode_erk_integrate_batch')
+      IMPORT :: C_INT, C_INT64_T, C_DOUBLE, C_PTR
+      INTEGER(C_INT), VALUE :: model, nvar, mem
+      INTEGER(C_INT64_T), VALUE :: ncells
+      REAL(C_DOUBLE), VALUE :: tin, tout
+      REAL(C_DOUBLE) :: y(*), rstatus(*)
+      REAL(C_DOUBLE), INTENT(IN) :: atol(*), rtol(*)
+      TYPE(C_PTR), VALUE :: icntrl_u, rcntrl_u, model_params, stream
+      INTEGER(C_INT) :: istatus(*), ierr(*)
+      INTEGER(C_INT) :: fatode_erk_integrate_batch
+    END FUNCTION
+    FUNCTION fatode_erk_integrate_tlm_batch(model, ncells, nvar, ntlm, y, y_tlm, tin, tout, atol_tlm, rtol_tlm, atol, rtol, &
+                                            icntrl_u, rcntrl_u, istatus, rstatus, ierr, model_params, mem, stream) &
+                                            BIND(C, NAME='fatode_erk_integrate_tlm_batch')
+      IMPORT :: C_INT, C_INT64_T, C_DOUBLE, C_PTR
+      INTEGER(C_INT), VALUE :: model, nvar, ntlm, mem
+      INTEGER(C_INT64_T), VALUE :: ncells
+      REAL(C_DOUBLE), VALUE :: tin, tout
+      REAL(C_DOUBLE) :: y(*), y_tlm(*), rstatus(*)
+      TYPE(C_PTR), VALUE :: atol_tlm, rtol_tlm, icntrl_u, rcntrl_u, model_params, stream
+      REAL(C_DOUBLE), INTENT(IN) :: atol(*), rtol(*)
+      INTEGER(C_INT) :: istatus(*), ierr(*)
+      INTEGER(C_INT) :: fatode_erk_integrate_tlm_batch
     END FUNCTION
     FUNCTION fatode_rk_integrate_batch(model, ncells, nvar, y, tin, tout, atol, rtol, icntrl_u, rcntrl_u, &
                                         istatus, rstatus, ierr, model_params, mem, stream) BIND(C, NAME='fatode_rk_integrate_batch')
@@ -173,6 +201,66 @@ CONTAINS
     IF (PRESENT(RSTATUS_U)) RSTATUS_U(:) = rst(:)
     IF (PRESENT(IERR_U)) IERR_U = ierr(1)
   END SUBROUTINE INTEGRATE
+
+  !~~~> FWD/ERK INTEGRATE, one system (FWD/ERK/ERK_f90_Integrator.F90:28-29: NVAR instead of N, no NNZERO, no JAC).  Its dummy
+  !     names differ from the implicit families', so it is a routine of its own; an application written against
+  !     ERK_f90_Integrator keeps its keyword call (swe2D_erk_dr.F90:112-114) with
+  !        USE fatode_b200_mod, ONLY: INTEGRATE => INTEGRATE_ERK, fatode_b200_set_model
+  SUBROUTINE INTEGRATE_ERK( TIN, TOUT, NVAR, VAR, RTOL, ATOL, FUN, ICNTRL_U, RCNTRL_U, ISTATUS_U, RSTATUS_U, Ierr_U )
+    INTEGER, INTENT(IN) :: NVAR
+    DOUBLE PRECISION, INTENT(INOUT) :: VAR(NVAR)
+    DOUBLE PRECISION, INTENT(IN) :: RTOL(NVAR), ATOL(NVAR), TIN, TOUT
+    EXTERNAL :: FUN
+    INTEGER, INTENT(IN), OPTIONAL, TARGET :: ICNTRL_U(20)
+    DOUBLE PRECISION, INTENT(IN), OPTIONAL, TARGET :: RCNTRL_U(20)
+    INTEGER, INTENT(OUT), OPTIONAL :: ISTATUS_U(20), Ierr_U
+    DOUBLE PRECISION, INTENT(OUT), OPTIONAL :: RSTATUS_U(20)
+    INTEGER(C_INT) :: ist(20), ierr(1), rc
+    REAL(C_DOUBLE) :: rst(20)
+    TYPE(C_PTR) :: pic, prc
+    pic = C_NULL_PTR; prc = C_NULL_PTR
+    IF (PRESENT(ICNTRL_U)) pic = C_LOC(ICNTRL_U)
+    IF (PRESENT(RCNTRL_U)) prc = C_LOC(RCNTRL_U)
+    ist = 0; rst = 0.0d0; ierr = 0
+    rc = fatode_erk_integrate_batch(current_model, 1_C_INT64_T, INT(NVAR, C_INT), VAR, TIN, TOUT, ATOL, RTOL, pic, prc, &
+                                    ist, rst, ierr, C_NULL_PTR, FATODE_MEM_HOST, C_NULL_PTR)
+    IF (rc /= 0) ierr(1) = rc
+    IF (ierr(1) < 0) PRINT *, 'ERK: Unsuccessful exit at T=', TIN, ' (Ierr=', ierr(1), ')'   ! as :75-77
+    IF (PRESENT(ISTATUS_U)) ISTATUS_U(:) = ist(:)
+    IF (PRESENT(RSTATUS_U)) RSTATUS_U(:) = rst(:)
+    IF (PRESENT(Ierr_U)) Ierr_U = ierr(1)
+  END SUBROUTINE INTEGRATE_ERK
+
+  !~~~> TLM/ERK_TLM INTEGRATE_TLM, one system (TLM/ERK_TLM/ERK_TLM_f90_Integrator.F90:28-30; argument order and names differ from
+  !     the ROS/SDIRK TLM families): USE fatode_b200_mod, ONLY: INTEGRATE_TLM => INTEGRATE_ERK_TLM keeps the keyword call of
+  !     swe2D_erk_tlm_dr.F90:131-135.  JAC is accepted and ignored (finite-difference Jacobian-vector products, ICNTRL(5) = 0).
+  SUBROUTINE INTEGRATE_ERK_TLM( TIN, TOUT, NVAR, NTLM, VAR, VAR_TLM, ATOL_TLM, RTOL_TLM, ATOL, RTOL, FUN, JAC, &
+                                ICNTRL_U, RCNTRL_U, ISTATUS_U, RSTATUS_U, IERR_U )
+    INTEGER, INTENT(IN) :: NVAR, NTLM
+    DOUBLE PRECISION, INTENT(INOUT) :: VAR(NVAR), VAR_TLM(NVAR,NTLM)
+    DOUBLE PRECISION, INTENT(INOUT), TARGET :: RTOL_TLM(NVAR,NTLM), ATOL_TLM(NVAR,NTLM)
+    DOUBLE PRECISION, INTENT(IN) :: RTOL(NVAR), ATOL(NVAR), TIN, TOUT
+    EXTERNAL :: FUN, JAC
+    INTEGER, INTENT(IN), OPTIONAL, TARGET :: ICNTRL_U(20)
+    DOUBLE PRECISION, INTENT(IN), OPTIONAL, TARGET :: RCNTRL_U(20)
+    INTEGER, INTENT(OUT), OPTIONAL :: ISTATUS_U(20), IERR_U
+    DOUBLE PRECISION, INTENT(OUT), OPTIONAL :: RSTATUS_U(20)
+    INTEGER(C_INT) :: ist(20), ierr(1), rc
+    REAL(C_DOUBLE) :: rst(20)
+    TYPE(C_PTR) :: pic, prc
+    pic = C_NULL_PTR; prc = C_NULL_PTR
+    IF (PRESENT(ICNTRL_U)) pic = C_LOC(ICNTRL_U)
+    IF (PRESENT(RCNTRL_U)) prc = C_LOC(RCNTRL_U)
+    ist = 0; rst = 0.0d0; ierr = 0
+    rc = fatode_erk_integrate_tlm_batch(current_model, 1_C_INT64_T, INT(NVAR, C_INT), INT(NTLM, C_INT), VAR, VAR_TLM, TIN, TOUT, &
+                                        C_LOC(ATOL_TLM), C_LOC(RTOL_TLM), ATOL, RTOL, pic, prc, ist, rst, ierr, C_NULL_PTR, &
+                                        FATODE_MEM_HOST, C_NULL_PTR)
+    IF (rc /= 0) ierr(1) = rc
+    IF (ierr(1) < 0) PRINT *, 'ERK-TLM: Unsuccessful exit at T=', TIN, ' (Ierr=', ierr(1), ')'   ! as :79-81
+    IF (PRESENT(ISTATUS_U)) ISTATUS_U(:) = ist(:)
+    IF (PRESENT(RSTATUS_U)) RSTATUS_U(:) = rst(:)
+    IF (PRESENT(IERR_U)) IERR_U = ierr(1)
+  END SUBROUTINE INTEGRATE_ERK_TLM
 
   !~~~> ADJ/ROS_ADJ INTEGRATE_ADJ, one system (ADJ/ROS_ADJ/ROS_ADJ_f90_Integrator.F90:34-37)
   !     With fatode_b200_set_family(FATODE_FAMILY_RK) the same routine stands in for ADJ/RK_ADJ's INTEGRATE_ADJ
