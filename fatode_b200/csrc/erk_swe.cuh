@@ -25,6 +25,7 @@ namespace fatode {
 
 constexpr int SWE_MX = 40, SWE_CELLS = 1600, SWE_N = 4800;
 constexpr int ERK_THREADS = 320, ERK_CPT = SWE_CELLS / ERK_THREADS;   // cells per thread
+constexpr int ERK_EPT = SWE_N / ERK_THREADS;                            // vector components per thread
 static_assert(ERK_CPT * ERK_THREADS == SWE_CELLS, "cells per thread");
 constexpr size_t ERK_SMEM = sizeof(double) * (2 * SWE_N + 8);
 
@@ -182,13 +183,20 @@ k_erk_swe(ErkParams p, ErkArgs a) {
 #pragma unroll 1
       for (int is = 0; is < S; ++is) {
         // TMP = sum_j (H a_ij) K_j + Y   (:411-421)
-        for (int v = tid; v < SWE_N; v += ERK_THREADS) {
-          double t = 0.0;
+        {   // stage-major so that the thread's 15 loads of one K_j are in flight together; per element the order is the DAXPYs'
+          double t[ERK_EPT];
+#pragma unroll
+          for (int q = 0; q < ERK_EPT; ++q) t[q] = 0.0;
           for (int j = 0; j < is; ++j) {
             const double c = H * p.A[is][j];
-            if (c != 0.0) t = t + c * K[(size_t)j * SWE_N + v];
+            if (c != 0.0) {
+              const double* Kj = K + (size_t)j * SWE_N + tid;
+#pragma unroll
+              for (int q = 0; q < ERK_EPT; ++q) t[q] = t[q] + c * Kj[q * ERK_THREADS];
+            }
           }
-          TMP[v] = t + Ys[v];
+#pragma unroll
+          for (int q = 0; q < ERK_EPT; ++q) TMP[tid + q * ERK_THREADS] = t[q] + Ys[tid + q * ERK_THREADS];
         }
         __syncthreads();
         double* Ki = K + (size_t)is * SWE_N;
@@ -215,17 +223,27 @@ k_erk_swe(ErkParams p, ErkArgs a) {
       }
       nstp++;
       // error estimate (:430-438): TMP <- (scaled error component)^2, then one sequential sum
-      for (int v = tid; v < SWE_N; v += ERK_THREADS) {
-        double t = 0.0;
+      {
+        double t[ERK_EPT];
+#pragma unroll
+        for (int q = 0; q < ERK_EPT; ++q) t[q] = 0.0;
         for (int i = 0; i < S; ++i)
           if (p.E[i] != 0.0) {
             const double c = H * p.E[i];
-            if (c != 0.0) t = t + c * K[(size_t)i * SWE_N + v];
+            if (c != 0.0) {
+              const double* Ki = K + (size_t)i * SWE_N + tid;
+#pragma unroll
+              for (int q = 0; q < ERK_EPT; ++q) t[q] = t[q] + c * Ki[q * ERK_THREADS];
+            }
           }
-        const int vt = p.vector_tol ? v : 0;
-        const double scal = 1.0 / (a.atol[vt] + a.rtol[vt] * fabs(Ys[v]));
-        const double q = t * scal;
-        TMP[v] = q * q;
+#pragma unroll
+        for (int q = 0; q < ERK_EPT; ++q) {
+          const int v = tid + q * ERK_THREADS;
+          const int vt = p.vector_tol ? v : 0;
+          const double scal = 1.0 / (a.atol[vt] + a.rtol[vt] * fabs(Ys[v]));
+          const double w = t[q] * scal;
+          TMP[v] = w * w;
+        }
       }
       __syncthreads();
       if (tid == 0) {
@@ -243,14 +261,23 @@ k_erk_swe(ErkParams p, ErkArgs a) {
         FirstStep = false;
         nacc++;
         T = T + H;
-        for (int v = tid; v < SWE_N; v += ERK_THREADS) {
-          double y = Ys[v];
+        {
+          double t[ERK_EPT];
+#pragma unroll
+          for (int q = 0; q < ERK_EPT; ++q) t[q] = Ys[tid + q * ERK_THREADS];
           for (int i = 0; i < S; ++i)
             if (p.B[i] != 0.0) {
               const double c = H * p.B[i];
-              if (c != 0.0) y = y + c * K[(size_t)i * SWE_N + v];
+              if (c != 0.0) {
+                const double* Ki = K + (size_t)i * SWE_N + tid;
+#pragma unroll
+                for (int q = 0; q < ERK_EPT; ++q) t[q] = t[q] + c * Ki[q * ERK_THREADS];
+              }
             }
-          Ys[v] = y;
+#pragma unroll
+          for (int q = 0; q < ERK_EPT; ++q) Ys[tid + q * ERK_THREADS] = t[q];
+        }
+        for (int v = tid; v < SWE_N; v += ERK_THREADS) {
           if constexpr (TLM) {
             for (int col = 0; col < ntlm; ++col) {
               double s = ytl[(size_t)col * SWE_N + v];

@@ -5,6 +5,7 @@
 // Lambda(N,NADJ) per cell), mu[cell][NADJ][NP], istatus[cell][20], rstatus[cell][20].
 #include <omp.h>
 #include <cstring>
+#include <vector>
 #include "models.hpp"
 #include "ros.hpp"
 #include "sdirk.hpp"
@@ -12,6 +13,7 @@
 #include "rk_adj.hpp"
 #include "sdirk_tlm.hpp"
 #include "erk.hpp"
+#include "sdirk_adj.hpp"
 
 using namespace oracle;
 
@@ -172,6 +174,26 @@ int oracle_erk_batch(int model, long ncells, int ntlm, double* y, double* y_tlm,
 // initializeGaussianGrid(A) + u = u0, v = v0 + grid2vec (EXAMPLES/swe/SWE_ERK/swe2D_erk_dr.F90:100-103)
 int oracle_swe_initial_state(double A, double u0, double v0, double* vec) { Swe::initial_state(A, u0, v0, vec); return 0; }
 int oracle_swe_fun(const double* y, double* p) { Swe m; m.fun(0.0, y, p); return 0; }
+
+// INTEGRATE_ADJ of ADJ/SDIRK_ADJ looped over cells (layouts as oracle_ros_adj_batch)
+int oracle_sdirk_adj_batch(int model, long ncells, int np, int nadj, double* y, double* lambda, double* mu, double tin, double tout,
+                           const double* atol, const double* rtol, const int* icntrl, const double* rcntrl, int* istatus,
+                           double* rstatus, int* ierr, int nthreads) {
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+  if (model != MODEL_CBM4) { for (long c = 0; c < ncells; ++c) ierr[c] = -100; return 0; }
+  const int N = Cbm4::N;
+  std::vector<double> tol_adj((size_t)2 * N * nadj);   // the drivers pass rtol_adj = rtol, atol_adj = atol per column
+  for (int m = 0; m < nadj; ++m)
+    for (int i = 0; i < N; ++i) { tol_adj[(size_t)m * N + i] = atol[i]; tol_adj[(size_t)(nadj + m) * N + i] = rtol[i]; }
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+  for (long c = 0; c < ncells; ++c) {
+    Cbm4 m;
+    ierr[c] = sdirk_adj_integrate<Cbm4>(m, np, nadj, y + c * N, lambda + c * (long)N * nadj, (np > 0 && mu) ? mu + c * (long)np * nadj : nullptr,
+                                        tin, tout, tol_adj.data(), tol_adj.data() + (size_t)N * nadj, atol, rtol, icntrl, rcntrl,
+                                        istatus + c * 20, rstatus + c * 20);
+  }
+  return 0;
+}
 
 // FWD/SDIRK INTEGRATE looped over cells
 int oracle_sdirk_fwd_batch(int model, long ncells, double* y, double tin, double tout, const double* atol, const double* rtol,

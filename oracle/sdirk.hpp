@@ -13,6 +13,7 @@
 #pragma once
 #include <cmath>
 #include <cstring>
+#include <vector>
 #include "ros.hpp"
 #include "gen/sdirk_tableau_gen.h"
 
@@ -95,6 +96,12 @@ struct Sdirk {
   int ISTATUS[20];
   double RSTATUS[20];
   LssDense<N> lss;
+  // hooks of the adjoint family's forward sweep (SDIRK_FwdInt, ADJ/SDIRK_ADJ/SDIRK_ADJ_f90_Integrator.F90:545-781): every
+  // accepted step is pushed as (T, H, Y, Z) before the update (SDIRK_Push :735), and its SDIRK_PrepareMatrix re-evaluates
+  // the Jacobian after a singular factorisation (SkipJac = .FALSE., :1239; the forward family keeps it, :780)
+  struct TapeEntry { double T, H, Y[N], Z[5][N]; };
+  std::vector<TapeEntry>* tape = nullptr;
+  bool sng_keeps_jac = true;
   explicit Sdirk(Model& m) : mdl(m) { std::memset(ISTATUS, 0, sizeof ISTATUS); std::memset(RSTATUS, 0, sizeof RSTATUS); }
 
   void error_scale(const double* AbsTol, const double* RelTol, const double* Y, double* SCAL) const {   // :661-676
@@ -119,7 +126,7 @@ struct Sdirk {
         ConsecutiveSng++;
         if (ConsecutiveSng >= 6) return ISING;
         H = 0.5 * H;
-        SkipJac = true; SkipLU = false; Reject = true;
+        SkipJac = sng_keeps_jac; SkipLU = false; Reject = true;
       }
     }
     return 0;
@@ -221,6 +228,13 @@ struct Sdirk {
       if (Err < 1.0) {
         FirstStep = false;
         ISTATUS[Nacc]++;
+        if (tape) {
+          tape->emplace_back();
+          TapeEntry& e = tape->back();
+          e.T = T; e.H = H;
+          std::memcpy(e.Y, Y, sizeof e.Y);
+          std::memcpy(e.Z, Z, sizeof e.Z);
+        }
         T = T + H;
         for (int s = 1; s <= S; ++s)
           if (tb.D[s - 1] != 0.0) for (int i = 0; i < N; ++i) Y[i] = Y[i] + tb.D[s - 1] * Z[s - 1][i];

@@ -9,11 +9,14 @@ copied here verbatim (they are run outputs committed upstream, not source code):
   EXAMPLES/cbm4/CBM4_SDIRK/cbm4_sdirk_sol.txt          Y(Tend), 32 x E24.16 (FWD/SDIRK, Sdirk4a, rtol 1e-6, atol 1e-8)
   EXAMPLES/cbm4/CBM4_RK/cbm4_rk_sol.txt                Y(Tend), 32 x E24.16 (FWD/RK, Radau-2A, rtol 1e-6, atol 1e-8)
   EXAMPLES/cbm4/CBM4_RK_ADJ/{cbm4_rk_sol.txt,cbm4_output_sens.txt}   ADJ/RK_ADJ Radau-2A: Y(Tend), Lambda(32,32), Mu(29,32)
+  EXAMPLES/cbm4/CBM4_SDIRK_ADJ/{cbm4_sdirk_sol.txt,cbm4_output_sens.txt}   ADJ/SDIRK_ADJ Sdirk4a, direct adjoint solve
+  EXAMPLES/swe/SWE_ERK/swe_lsode_sol.txt               Y(50 dt), 4800 x E24.16 (LSODE solution the ERK driver compares with)
 Usage: python tests/golden/make_golden.py [/root/reference]
 """
 import json
 import os
 import re
+import shutil
 import sys
 
 import numpy as np
@@ -52,6 +55,15 @@ def main():
     json.dump({"source": "EXAMPLES/cbm4/CBM4_RK_ADJ/{cbm4_rk_sol.txt,cbm4_output_sens.txt}",
                "y": y, "lambda": vals[:1024], "mu": vals[1024:]},
               open(os.path.join(HERE, "cbm4_rk_adj.json"), "w"))
+    d = os.path.join(REF, "EXAMPLES/cbm4/CBM4_SDIRK_ADJ")
+    ffloat = lambda t: float(re.sub(r"(\d)([+-]\d{3})\s*$", r"\1E\2", t.strip()))   # E24.16 drops the E for 3-digit exponents
+    y = [ffloat(l) for l in open(os.path.join(d, "cbm4_sdirk_sol.txt"))]
+    vals = [ffloat(l) for l in open(os.path.join(d, "cbm4_output_sens.txt")) if not l.startswith(("L", "M"))]
+    assert len(y) == 32 and len(vals) == 32 * 32 + 32 * 29
+    json.dump({"source": "EXAMPLES/cbm4/CBM4_SDIRK_ADJ/{cbm4_sdirk_sol.txt,cbm4_output_sens.txt}",
+               "y": y, "lambda": vals[:1024], "mu": vals[1024:]},
+              open(os.path.join(HERE, "cbm4_sdirk_adj.json"), "w"))
+    shutil.copy(os.path.join(REF, "EXAMPLES/swe/SWE_ERK/swe_lsode_sol.txt"), os.path.join(HERE, "swe_lsode_sol.txt"))
     print("wrote fixtures")
 
 

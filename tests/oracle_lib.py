@@ -25,6 +25,7 @@ def lib():
                                            ctypes.c_double, ctypes.c_double, _dp, _dp, _ip, _dp, _ip, _dp, _ip,
                                            ctypes.c_int]
         L.oracle_rk_adj_batch.argtypes = L.oracle_ros_adj_batch.argtypes
+        L.oracle_sdirk_adj_batch.argtypes = L.oracle_ros_adj_batch.argtypes
         L.oracle_rk_fwd_batch.argtypes = [ctypes.c_int, ctypes.c_long, _dp, ctypes.c_double, ctypes.c_double, _dp, _dp,
                                           _ip, _dp, _ip, _dp, _ip, ctypes.c_int, ctypes.c_int]
         L.oracle_sdirk_fwd_batch.argtypes = [ctypes.c_int, ctypes.c_long, _dp, ctypes.c_double, ctypes.c_double, _dp, _dp,
@@ -226,3 +227,22 @@ def erk(model, y, tin, tout, atol, rtol, icntrl=None, rcntrl=None, y_tlm=None, a
                                _i(ist), _d(rst), _i(ierr), nthreads)
     assert r == 0
     return dict(y=y, y_tlm=yt, istatus=ist, rstatus=rst, ierr=ierr)
+
+
+def sdirk_adj(model, y, nadj, tin, tout, atol, rtol, icntrl=None, rcntrl=None, with_mu=True, nthreads=0):
+    """INTEGRATE_ADJ of ADJ/SDIRK_ADJ looped over cells; lambda_: [ncells, NADJ, N], mu: [ncells, NADJ, NP]."""
+    y = np.atleast_2d(np.array(y, dtype=np.float64, order="C"))
+    nc, n = y.shape
+    _, npar = dims(model)
+    ic, rc = _ctrl(icntrl, rcntrl)
+    atol = np.ascontiguousarray(atol, dtype=np.float64)
+    rtol = np.ascontiguousarray(rtol, dtype=np.float64)
+    ist = np.zeros((nc, 20), dtype=np.int32)
+    rst = np.zeros((nc, 20))
+    ierr = np.zeros(nc, dtype=np.int32)
+    lam = np.zeros((nc, nadj, n))
+    use_mu = with_mu and npar > 0
+    mu = np.zeros((nc, nadj, max(npar, 1)))
+    lib().oracle_sdirk_adj_batch(MODEL[model], nc, npar if use_mu else 0, nadj, _d(y), _d(lam), _d(mu) if use_mu else None,
+                                 tin, tout, _d(atol), _d(rtol), _i(ic), _d(rc), _i(ist), _d(rst), _i(ierr), nthreads)
+    return dict(y=y, istatus=ist, rstatus=rst, ierr=ierr, lambda_=lam, mu=mu[:, :, :npar] if use_mu else None)
