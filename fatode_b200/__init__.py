@@ -74,6 +74,7 @@ def lib():
                                                    ctypes.c_double, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
         L.fatode_rk_integrate_batch.argtypes = L.fatode_sdirk_integrate_batch.argtypes
         L.fatode_rk_integrate_adj_batch.argtypes = L.fatode_ros_integrate_adj_batch.argtypes
+        L.fatode_sdirk_integrate_adj_batch.argtypes = L.fatode_ros_integrate_adj_batch.argtypes
         L.fatode_ros_integrate_tlm_batch.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, vp, vp,
                                                      ctypes.c_double, ctypes.c_double, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                                      ctypes.c_int, vp]
@@ -226,7 +227,8 @@ def swe_initial_state(amplitude=30.0, u0=2.0, v0=2.0) -> np.ndarray:
 def integrate_adj(model, tin, tout, y, nadj, rtol, atol, np_=None, icntrl_u=None, rcntrl_u=None, want_mu=True,
                   want_mu_sum=False, model_params=None, family="ros") -> Result:
     """Batched INTEGRATE_ADJ: family="ros" ADJ/ROS_ADJ (ADJ/ROS_ADJ/ROS_ADJ_f90_Integrator.F90:34), family="rk"
-    ADJ/RK_ADJ (ADJ/RK_ADJ/RK_ADJ_f90_Integrator.F90:20). y: [ncells, N] or [N]."""
+    ADJ/RK_ADJ (ADJ/RK_ADJ/RK_ADJ_f90_Integrator.F90:20), family="sdirk" ADJ/SDIRK_ADJ (ADJ/SDIRK_ADJ/SDIRK_ADJ_f90_Integrator.F90:29).
+    y: [ncells, N] or [N]."""
     mid = model_id(model)
     yy = np.atleast_2d(np.array(y, dtype=np.float64, order="C"))
     nc, n = yy.shape
@@ -243,7 +245,8 @@ def integrate_adj(model, tin, tout, y, nadj, rtol, atol, np_=None, icntrl_u=None
     mu = np.zeros((nc, nadj, npar)) if with_mu else None
     mus = np.zeros((nadj, npar)) if (with_mu and want_mu_sum) else None
     mp = None if model_params is None else np.ascontiguousarray(model_params, dtype=np.float64)
-    entry = lib().fatode_rk_integrate_adj_batch if family == "rk" else lib().fatode_ros_integrate_adj_batch
+    entry = {"rk": lib().fatode_rk_integrate_adj_batch, "sdirk": lib().fatode_sdirk_integrate_adj_batch}.get(
+        family, lib().fatode_ros_integrate_adj_batch)
     _check(entry(mid, nc, n, npar if with_mu else 0, nadj, _ptr(yy), _ptr(lam), _ptr(mu),
                                                 float(tin), float(tout), None, None, _ptr(atol), _ptr(rtol), _ptr(ic),
                                                 _ptr(rc), _ptr(ist), _ptr(rst), _ptr(ierr), _ptr(mus), _ptr(mp),

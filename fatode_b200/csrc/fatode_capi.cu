@@ -32,6 +32,7 @@
 #include "sdirk_cell_fwd.cuh"
 #include "sdirk_cell_tlm.cuh"
 #include "erk_swe.cuh"
+#include "sdirk_cell_adj.cuh"
 #include "rk_cell_fwd.cuh"
 #include "model_cbm4_dense_cell.cuh"
 #include "rk_cell_adj.cuh"
@@ -1630,9 +1631,12 @@ static void release_sdirk_workspace() { g_sd_tape.release(); g_sd_fat.release();
 
 // One group of systems (ids) through the state sweep and the column sweep.  Systems that overflow their tape slot are
 // appended to `overflow`.  A system whose state sweep fails keeps Y_tlm as of its last accepted step, like the reference.
+// adj != nullptr: the same organisation for ADJ/SDIRK_ADJ (forward sweep in SD_MODE_ADJ, sdirk_cell_adj.cuh backward); ntlm is then
+// NADJ and d_ytlm is Lambda.  A system whose forward sweep fails still gets its backward sweep and IERR = 1, as the reference.
+struct SdirkAdjHost { SdirkAdjCoef co; double* d_mu; int with_mu, np; };
 static int sdirk_tlm_group(const SdirkParams& sp, const Cbm4Const& mc, const std::vector<int>& ids, int cap, int ntlm, size_t fat_budget,
                            double* d_y, double* d_ytlm, const double* d_atol, const double* d_rtol, int* d_ist, double* d_rst,
-                           int* d_ierr, cudaStream_t st, int sms, std::vector<int>& overflow) {
+                           int* d_ierr, cudaStream_t st, int sms, std::vector<int>& overflow, const SdirkAdjHost* adj = nullptr) {
   const int n = (int)ids.size();
   if (n == 0) return 0;
   const size_t idx_bytes = sizeof(int) * (size_t)n * 3 + 16 + sizeof(long long) * (size_t)(n + 1);
@@ -1643,22 +1647,63 @@ static int sdirk_tlm_group(const SdirkParams& sp, const Cbm4Const& mc, const std
   long long* d_off = reinterpret_cast<long long*>(reinterpret_cast<char*>(g_sd_idx.p) + ((sizeof(int) * (size_t)n * 3 + 15) / 16) * 16);
   CUDA_TRY(cudaMemcpyAsync(d_ids, ids.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
   CUDA_TRY(g_sd_tape.ensure(sizeof(double) * (size_t)n * cap * SD_REC));
-  if (int e = cellfwd_launch<SdirkParams, Cbm4Const, double*, int, int>(k_sdirk_fwd_cell<Cbm4Cell, 32, true>, SdirkSmem<Cbm4Cell, 32>::BYTES, 32,
-                                                                       sp, mc, n, d_y, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, d_ids,
-                                                                       g_sd_tape.as<double>(), cap, ntlm))
-    return e;
+  if (adj) {
+    if (int e = cellfwd_launch<SdirkParams, Cbm4Const, double*, int, int>(k_sdirk_fwd_cell<Cbm4Cell, 32, SD_MODE_ADJ>, SdirkSmem<Cbm4Cell, 32>::BYTES, 32,
+                                                                         sp, mc, n, d_y, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, d_ids,
+                                                                         g_sd_tape.as<double>(), cap, ntlm))
+      return e;
+  } else {
+    if (int e = cellfwd_launch<SdirkParams, Cbm4Const, double*, int, int>(k_sdirk_fwd_cell<Cbm4Cell, 32, SD_MODE_TLM>, SdirkSmem<Cbm4Cell, 32>::BYTES, 32,
+                                                                         sp, mc, n, d_y, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, d_ids,
+                                                                         g_sd_tape.as<double>(), cap, ntlm))
+      return e;
+  }
   CUDA_TRY(g_sd_stat.ensure(sizeof(int) * 2 * (size_t)n));
   k_rk_gather_status<<<(n + 255) / 256, 256, 0, st>>>(n, d_ids, d_ierr, d_ist, g_sd_stat.as<int>());
   std::vector<int> h_stat(2 * (size_t)n);
   CUDA_TRY(cudaMemcpyAsync(h_stat.data(), g_sd_stat.p, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  const size_t rec_bytes = sizeof(double) * ST_REC;
+  const size_t rec_bytes = sizeof(double) * (adj ? SA_REC : ST_REC);
   std::vector<int> b_slot, b_cell;
   std::vector<long long> b_off;
   auto flush = [&]() -> int {
     const int nb = (int)b_slot.size();
     if (nb == 0) return 0;
     const long long nrec = b_off.back();
+    if (adj) {
+      CUDA_TRY(g_sd_fat.ensure((size_t)std::max<long long>(nrec, 1) * rec_bytes));
+      CUDA_TRY(cudaMemcpyAsync(d_slot, b_slot.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(d_cell, b_cell.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(d_off, b_off.data(), sizeof(long long) * (nb + 1), cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemsetAsync(g_ctr.p, 0, 16 * sizeof(unsigned long long), st));
+      PhaseTimer tm(st);
+      if (nrec > 0) {
+        SdirkAdjPrepArgs pa{(long)nrec, nb, d_off, d_slot, g_sd_tape.as<double>(), cap, g_sd_fat.as<double>()};
+        const size_t psm = sizeof(double) * (size_t)(cbm4_cell::NLU + 2 * 32) * SA_PREP_LANES;
+        CUDA_TRY(cudaFuncSetAttribute(k_sdirk_adj_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+        int per_sm = 1;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sdirk_adj_prep, 32, psm));
+        const long long nwork = nrec * sp.S;
+        const unsigned pblocks = (unsigned)std::min<long long>((nwork + SA_PREP_LANES - 1) / SA_PREP_LANES, (long long)sms * std::max(per_sm, 1));
+        tm.start();
+        k_sdirk_adj_prep<<<pblocks, 32, psm, st>>>(sp, mc, pa);
+        CUDA_TRY(cudaGetLastError());
+        g_stats.ms_forward_tape += tm.stop();
+        g_stats.launches++; g_stats.launches_expand++;
+      }
+      SdirkAdjArgs aa{nb, d_off, d_cell, g_sd_fat.as<double>(), d_ytlm, adj->d_mu, d_ist, d_ierr, g_ctr.as<unsigned long long>(), ntlm,
+                      adj->with_mu, adj->np};
+      CUDA_TRY(cudaFuncSetAttribute(k_sdirk_adj_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDIRK_ADJ_SMEM));
+      const unsigned ablocks = (unsigned)std::min<int>(nb, 3 * sms);
+      tm.start();
+      k_sdirk_adj_cell<<<ablocks, 32, SDIRK_ADJ_SMEM, st>>>(sp, adj->co, aa);
+      CUDA_TRY(cudaGetLastError());
+      g_stats.ms_adjoint += tm.stop();
+      g_stats.launches++; g_stats.launches_adjoint++;
+      CUDA_TRY(cudaStreamSynchronize(st));
+      b_slot.clear(); b_cell.clear(); b_off.clear();
+      return 0;
+    }
     CUDA_TRY(g_sd_fat.ensure((size_t)std::max<long long>(nrec, 1) * rec_bytes));
     CUDA_TRY(cudaMemcpyAsync(d_slot, b_slot.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_cell, b_cell.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, st));
@@ -1667,11 +1712,12 @@ static int sdirk_tlm_group(const SdirkParams& sp, const Cbm4Const& mc, const std
     PhaseTimer tm(st);
     if (nrec > 0) {
       SdirkTlmPrepArgs pa{(long)nrec, nb, d_off, d_slot, g_sd_tape.as<double>(), cap, g_sd_fat.as<double>()};
-      const size_t psm = sizeof(double) * (size_t)(cbm4_cell::NLU + 3 * 32) * ST_PREP_LANES;
+      const size_t psm = sizeof(double) * (size_t)(cbm4_cell::NLU + 2 * 32) * ST_PREP_LANES;
       CUDA_TRY(cudaFuncSetAttribute(k_sdirk_tlm_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
       int per_sm = 1;
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sdirk_tlm_prep, 32, psm));
-      const unsigned pblocks = (unsigned)std::min<long long>((nrec + ST_PREP_LANES - 1) / ST_PREP_LANES, (long long)sms * std::max(per_sm, 1));
+      const long long nwork = nrec * (sp.S + 1);
+      const unsigned pblocks = (unsigned)std::min<long long>((nwork + ST_PREP_LANES - 1) / ST_PREP_LANES, (long long)sms * std::max(per_sm, 1));
       tm.start();
       k_sdirk_tlm_prep<<<pblocks, 32, psm, st>>>(sp, mc, pa);
       CUDA_TRY(cudaGetLastError());
@@ -1693,7 +1739,7 @@ static int sdirk_tlm_group(const SdirkParams& sp, const Cbm4Const& mc, const std
   for (int i = 0; i < n; ++i) {
     const int code = h_stat[2 * (size_t)i], nacc = h_stat[2 * (size_t)i + 1];
     if (code == IERR_TAPE_OVERFLOW) { overflow.push_back(ids[i]); continue; }
-    if (code == SDIRK_IERR_IRREGULAR || nacc <= 0) continue;   // handed back / nothing accepted: the columns stay as given
+    if (code == SDIRK_IERR_IRREGULAR || (!adj && nacc <= 0)) continue;   // handed back / nothing accepted: the columns stay as given
     if (b_off.empty()) b_off.push_back(0);
     if (!b_slot.empty() && (size_t)(b_off.back() + nacc) * rec_bytes > fat_budget)
       if (int e = flush()) return e;
@@ -1707,7 +1753,8 @@ static int sdirk_tlm_group(const SdirkParams& sp, const Cbm4Const& mc, const std
 }
 
 static int sdirk_tlm_device(const SdirkParams& sp, const Cbm4Const& mc, int64_t ncells, int ntlm, double* d_y, double* d_ytlm,
-                            const double* d_atol, const double* d_rtol, int* d_ist, double* d_rst, int* d_ierr, cudaStream_t st) {
+                            const double* d_atol, const double* d_rtol, int* d_ist, double* d_rst, int* d_ierr, cudaStream_t st,
+                            const SdirkAdjHost* adj = nullptr) {
   std::memset(&g_stats, 0, sizeof g_stats);
   int dev = 0, sms = 0;
   CUDA_TRY(cudaGetDevice(&dev));
@@ -1725,7 +1772,7 @@ static int sdirk_tlm_device(const SdirkParams& sp, const Cbm4Const& mc, int64_t 
     const int64_t w1 = std::min(ncells, w0 + wave);
     ids.resize((size_t)(w1 - w0));
     for (int64_t c = w0; c < w1; ++c) ids[(size_t)(c - w0)] = (int)c;
-    if (int e = sdirk_tlm_group(sp, mc, ids, cap, ntlm, fat_budget, d_y, d_ytlm, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, sms, overflow))
+    if (int e = sdirk_tlm_group(sp, mc, ids, cap, ntlm, fat_budget, d_y, d_ytlm, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, sms, overflow, adj))
       return e;
     g_stats.waves++;
   }
@@ -1735,7 +1782,7 @@ static int sdirk_tlm_device(const SdirkParams& sp, const Cbm4Const& mc, int64_t 
     const size_t take = std::max<size_t>(1, std::min<size_t>(overflow.size(), (size_t)(0.35 * (double)budget) / per));
     std::vector<int> part(overflow.end() - (long)take, overflow.end()), again;
     overflow.resize(overflow.size() - take);
-    if (int e = sdirk_tlm_group(sp, mc, part, capx, ntlm, fat_budget, d_y, d_ytlm, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, sms, again))
+    if (int e = sdirk_tlm_group(sp, mc, part, capx, ntlm, fat_budget, d_y, d_ytlm, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, sms, again, adj))
       return e;
     if (!again.empty()) return fail(FATODE_ENOMEM, "SDIRK_TLM tape overflow with a Max_no_steps slot");
     g_stats.waves++;
@@ -1799,6 +1846,92 @@ extern "C" int fatode_sdirk_integrate_tlm_batch(int model, int64_t ncells, int n
     CUDA_TRY(cudaMemcpyAsync(istatus, d_ist, sizeof(int) * 20 * ncells, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(rstatus, d_rst, sizeof(double) * 20 * ncells, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(ierr, d_ierr, sizeof(int) * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+// INTEGRATE_ADJ of ADJ/SDIRK_ADJ for CBM-IV (direct adjoint solve): sdirk_cell_adj.cuh
+extern "C" int fatode_sdirk_integrate_adj_batch(int model, int64_t ncells, int nvar, int np, int nadj, double* y, double* lambda,
+                                                double* mu, double tin, double tout, const double* atol_adj, const double* rtol_adj,
+                                                const double* atol, const double* rtol, const int* icntrl_u, const double* rcntrl_u,
+                                                int* istatus, double* rstatus, int* ierr, double* mu_sum, const double* model_params,
+                                                int mem, void* stream) {
+  (void)atol_adj; (void)rtol_adj;   // only read by the Newton mode of the adjoint solve (ICNTRL(7) /= 1), which is not built
+  g_err.clear();
+  if (ncells < 0 || !y || !atol || !rtol || !istatus || !rstatus || !ierr) return fail(FATODE_EINVAL, "NULL required argument");
+  if (int e = check_model_dims(model, nvar, np)) return e;
+  if (!lambda || nadj < 1) return fail(FATODE_EINVAL, "lambda is NULL or nadj < 1");
+  if (model != FATODE_MODEL_CBM4) return fail(FATODE_EUNSUPPORTED, "the SDIRK discrete adjoint is available for the cbm4 model only in this build");
+  if (nadj > 32) return fail(FATODE_EUNSUPPORTED, "nadj > 32 per call is not supported yet");
+  if (int e = check_device()) return e;
+  if (ncells == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // INTEGRATE_ADJ presets ICNTRL(5) = 8, ICNTRL(7) = 1, ICNTRL(8) = 0 before the `> 0` override (:70-83)
+  int ic[20];
+  std::memset(ic, 0, sizeof ic);
+  ic[4] = 8; ic[6] = 1;
+  if (icntrl_u) for (int i = 0; i < 20; ++i) if (icntrl_u[i] > 0) ic[i] = icntrl_u[i];
+  const bool direct = (ic[6] == 1);
+  int icp[20];
+  std::memcpy(icp, ic, sizeof ic);
+  icp[5] = 0;                                      // starting values are always interpolated in this family (:623)
+  SdirkParams sp;
+  const int perr = sdirk_parse_options(nvar, icp, rcntrl_u, tin, tout, atol, rtol, sp);
+  if (ic[3] == 0) sp.max_no_steps = 10000;        // :375
+  if (perr < 0) return broadcast_ierr(ncells, perr, istatus, rstatus, ierr, mem, st);
+  if (!direct)
+    return fail(FATODE_EUNSUPPORTED, "SDIRK_ADJ with simplified-Newton adjoint stages (ICNTRL(7) /= 1) is not built; use the preset direct solve");
+  const bool with_mu = np > 0 && mu != nullptr;
+  SdirkAdjHost ah;
+  const int method = (ic[2] == 1 || ic[2] == 2 || ic[2] == 3 || ic[2] == 5) ? ic[2] : 4;
+  std::memcpy(ah.co.A, SDIRK_ADJ_AB[method - 1].A, sizeof ah.co.A);
+  std::memcpy(ah.co.B, SDIRK_ADJ_AB[method - 1].B, sizeof ah.co.B);
+  ah.with_mu = with_mu ? 1 : 0;
+  ah.np = np;
+  Cbm4Const mc;
+  cbm4_constants(model_params, mc);
+  DevBuf b_atol, b_rtol, b_y, b_lam, b_mu, b_ist, b_rst, b_ierr, b_musum;
+  CUDA_TRY(b_atol.alloc(sizeof(double) * nvar));
+  CUDA_TRY(b_rtol.alloc(sizeof(double) * nvar));
+  CUDA_TRY(cudaMemcpyAsync(b_atol.p, atol, sizeof(double) * nvar, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(b_rtol.p, rtol, sizeof(double) * nvar, cudaMemcpyHostToDevice, st));
+  double *d_y = y, *d_lam = lambda, *d_mu = mu, *d_rst = rstatus, *d_musum = mu_sum;
+  int *d_ist = istatus, *d_ierr = ierr;
+  const size_t ny = sizeof(double) * nvar * ncells, nl = sizeof(double) * (size_t)nvar * nadj * ncells,
+               nm = sizeof(double) * (size_t)np * nadj * ncells;
+  if (mem == FATODE_MEM_HOST) {
+    CUDA_TRY(b_y.alloc(ny));
+    CUDA_TRY(b_ist.alloc(sizeof(int) * 20 * ncells));
+    CUDA_TRY(b_rst.alloc(sizeof(double) * 20 * ncells));
+    CUDA_TRY(b_ierr.alloc(sizeof(int) * ncells));
+    CUDA_TRY(cudaMemcpyAsync(b_y.p, y, ny, cudaMemcpyHostToDevice, st));
+    d_y = b_y.as<double>(); d_ist = b_ist.as<int>(); d_rst = b_rst.as<double>(); d_ierr = b_ierr.as<int>();
+    CUDA_TRY(b_lam.alloc(nl));
+    d_lam = b_lam.as<double>();
+    CUDA_TRY(cudaMemcpyAsync(d_lam, lambda, nl, cudaMemcpyHostToDevice, st));
+    if (with_mu) {
+      CUDA_TRY(b_mu.alloc(nm));
+      d_mu = b_mu.as<double>();
+      CUDA_TRY(cudaMemcpyAsync(d_mu, mu, nm, cudaMemcpyHostToDevice, st));
+      if (mu_sum) { CUDA_TRY(b_musum.alloc(sizeof(double) * np * nadj)); d_musum = b_musum.as<double>(); }
+    }
+  }
+  ah.d_mu = d_mu;
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_cbm4_rc, mc.rc_base, sizeof(double) * 81, 0, cudaMemcpyHostToDevice, st));
+  if (int e = sdirk_tlm_device(sp, mc, ncells, nadj, d_y, d_lam, b_atol.as<double>(), b_rtol.as<double>(), d_ist, d_rst, d_ierr, st, &ah))
+    return e;
+  if (with_mu && d_musum)
+    if (int e = mu_sum_device(ncells, nadj * np, d_mu, d_ierr, d_musum, st)) return e;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (mem == FATODE_MEM_HOST) {
+    CUDA_TRY(cudaMemcpyAsync(y, d_y, ny, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(istatus, d_ist, sizeof(int) * 20 * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(rstatus, d_rst, sizeof(double) * 20 * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ierr, d_ierr, sizeof(int) * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(lambda, d_lam, nl, cudaMemcpyDeviceToHost, st));
+    if (with_mu) CUDA_TRY(cudaMemcpyAsync(mu, d_mu, nm, cudaMemcpyDeviceToHost, st));
+    if (with_mu && mu_sum) CUDA_TRY(cudaMemcpyAsync(mu_sum, d_musum, sizeof(double) * np * nadj, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
   }
   return 0;

@@ -57,8 +57,12 @@ __device__ __forceinline__ double sdirk_powi(double x, int m) {   // gfortran's 
 // (T, H, saveNiter of the stages, Y, Z_1..Z_S) to the system's tape slot: record r of queue slot s lives at
 // tape[(s * tape_cap + r) * SD_REC].  The columns themselves are propagated afterwards (sdirk_cell_tlm.cuh).
 constexpr int SD_REC = 196;   // T, H, packed saveNiter (4 bits per stage), pad, Y(32), Z(5 x 32)
+// MODE 0: FWD/SDIRK.  MODE 1 (TLM): as described above.  MODE 2 (ADJ): SDIRK_FwdInt of ADJ/SDIRK_ADJ
+// (ADJ/SDIRK_ADJ/SDIRK_ADJ_f90_Integrator.F90:545-781) = the forward family's loop with every accepted step pushed to the tape
+// (:735) and its own SDIRK_PrepareMatrix, which re-evaluates the Jacobian after a singular factorisation (:1239).
+constexpr int SD_MODE_FWD = 0, SD_MODE_TLM = 1, SD_MODE_ADJ = 2;
 
-template <class Model, int LANES, bool TLM = false>
+template <class Model, int LANES, int MODE = 0>
 __global__ void __launch_bounds__(32, 1)
 k_sdirk_fwd_cell(SdirkParams sp, typename Model::Const mc, long ncells, const double* __restrict__ y_in, double* __restrict__ y_out,
                  const double* __restrict__ atol_g, const double* __restrict__ rtol_g, int* __restrict__ istatus,
@@ -148,7 +152,7 @@ k_sdirk_fwd_cell(SdirkParams sp, typename Model::Const mc, long ncells, const do
           nsng++;
           if (++ConsecutiveSng >= 6) break;
           H = __dmul_rn(0.5, H);
-          SkipJac = true; SkipLU = false; Reject = true;
+          SkipJac = (MODE != SD_MODE_ADJ); SkipLU = false; Reject = true;
         }
         if (code == LU_IRREGULAR) { ierr = SDIRK_IERR_IRREGULAR; break; }
         if (code == LU_SINGULAR) { ierr = -8; break; }
@@ -209,7 +213,7 @@ k_sdirk_fwd_cell(SdirkParams sp, typename Model::Const mc, long ncells, const do
           for (int i = 0; i < N; ++i) Zi[i * SV] = __dadd_rn(Zi[i * SV], RHS[i * SV]);
           NewtonDone = (__dmul_rn(NewtonRate, NewtonIncrement) <= sp.newtontol);
           if (NewtonDone) {
-            if constexpr (TLM) {   // saveNiter = NewtonIter + 1 (:603); the TLM loop runs min(saveNiter, NewtonMaxit) iterations
+            if constexpr (MODE == SD_MODE_TLM) {   // saveNiter = NewtonIter + 1 (:603); the TLM loop runs min(saveNiter, NewtonMaxit) iterations
               const int it = min(NewtonIter + 1, sp.newton_maxit);
               save_pack |= (unsigned)it << (4 * istage);
               njac++;
@@ -244,7 +248,7 @@ k_sdirk_fwd_cell(SdirkParams sp, typename Model::Const mc, long ncells, const do
       F2 = fmax(sp.facmin, fmin(sp.facmax, F2));
       double Hnew = __dmul_rn(H, F2);
       if (Err < 1.0) {   // accept (:594-631)
-        if constexpr (TLM) if (tape) {
+        if constexpr (MODE != SD_MODE_FWD) if (tape) {
           if (nacc >= tape_cap) { ierr = IERR_TAPE_OVERFLOW; break; }
           double* rec = tape + ((size_t)slot * tape_cap + nacc) * SD_REC;
           st_global_256(rec, T, H, (double)save_pack, (double)S);
@@ -278,7 +282,7 @@ k_sdirk_fwd_cell(SdirkParams sp, typename Model::Const mc, long ncells, const do
           H = __dsub_rn(Tfinal, T);
         } else {
           const double Hratio = __ddiv_rn(Hnew, H);
-          SkipLU = !TLM && (Theta <= sp.thetamin) && (Hratio >= sp.qmin) && (Hratio <= sp.qmax);   // TLM: never (:879)
+          SkipLU = (MODE != SD_MODE_TLM) && (Theta <= sp.thetamin) && (Hratio >= sp.qmin) && (Hratio <= sp.qmax);   // TLM: never (:879)
           if (!SkipLU) H = Hnew;
         }
         SkipJac = false;

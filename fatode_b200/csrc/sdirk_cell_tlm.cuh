@@ -5,7 +5,7 @@
 // (saveNiter, :603, :769), no TLM influence on the step control (ICNTRL(9) = ICNTRL(12) = 0).  In that mode the columns
 // never feed back into the state, so the state sweep (k_sdirk_fwd_cell<.., TLM = true>) runs first and tapes every
 // accepted step; two kernels then propagate the columns:
-//   k_sdirk_tlm_prep   one THREAD per accepted step: the factorisation of 1/(H gamma) I - J(T,Y) (what the accepted attempt
+//   k_sdirk_tlm_prep   one THREAD per (accepted step, part): the factorisation of 1/(H gamma) I - J(T,Y) (what the accepted attempt
 //                      used: the LU is never carried across steps in this family and a rejected attempt leaves (T,Y)
 //                      unchanged) and the S stage Jacobians J(T + c_i H, Y + Z_i) (LSS_Jac1), one contiguous record.
 //   k_sdirk_tlm_cell   one WARP per system, lane = TLM column, walking the records forwards: per stage
@@ -36,6 +36,10 @@ struct SdirkTlmPrepArgs {
   double* fat;
 };
 
+// Work item = (accepted step, part): parts 0..S-1 are the stage Jacobians, part S the factorisation.  (One item per step with
+// the stages in a loop was miscompiled by ptxas 12.9 when a second kernel of the same shape joined the translation unit: the
+// 32-byte stores inside the looped jac_values call were narrowed to their first element.  tests/test_sass_guards.py watches
+// the store widths of the three preparation kernels.)
 __global__ void __launch_bounds__(32, 1)
 k_sdirk_tlm_prep(SdirkParams sp, Cbm4Const mc, SdirkTlmPrepArgs a) {
   extern __shared__ __align__(16) double cell_smem[];
@@ -43,10 +47,13 @@ k_sdirk_tlm_prep(SdirkParams sp, Cbm4Const mc, SdirkTlmPrepArgs a) {
   double* const base = cell_smem + threadIdx.x;
   double* const lu = base;
   double* const dinv = lu + NLU * SV;
-  double* const Yv = dinv + N * SV;
-  double* const Tv = Yv + N * SV;
+  double* const Tv = dinv + N * SV;
   double PH[Cbm4Cell::NPH];
-  for (long q = (long)blockIdx.x * SV + threadIdx.x; q < a.nrec; q += (long)gridDim.x * SV) {
+  const int S = sp.S, P = S + 1;
+  const long nwork = a.nrec * P;
+  for (long w = (long)blockIdx.x * SV + threadIdx.x; w < nwork; w += (long)gridDim.x * SV) {
+    const long q = w / P;
+    const int part = (int)(w - q * P);
     int lo = 0, hi = a.ncells;
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
@@ -56,28 +63,27 @@ k_sdirk_tlm_prep(SdirkParams sp, Cbm4Const mc, SdirkTlmPrepArgs a) {
     const double* rec = a.tape + ((size_t)a.slot[lo] * a.tape_cap + r) * SD_REC;
     double* out = a.fat + (size_t)q * ST_REC;
     const double T = rec[0], H = rec[1];
+    if (part < S) {
+      const double* Z = rec + 4 + N + part * N;
 #pragma unroll 4
-    for (int i = 0; i < N; ++i) Yv[i * SV] = rec[4 + i];
-    unsigned swaps = 0;
-    Cbm4Cell::photo(T, mc, PH);
-    Cbm4Cell::build_E<SV>(Yv, PH, mc, 1.0 / (H * sp.Gamma), lu);
-    cbm4_cell::lu_factor<SV>(lu, dinv, swaps);
-    st_global_256(out + ST_HDR, T, H, (double)((unsigned)rec[2] | (swaps << 24)), rec[3]);
+      for (int i = 0; i < N; ++i) Tv[i * SV] = rec[4 + i] + Z[i];          // TMP = Y + Z_i (:700)
+      Cbm4Cell::photo(T + sp.C[part] * H, mc, PH);
+      cbm4_cell::jac_values<SV>(Tv, mc.fix, PH, out + ST_J + part * 276);
+    } else {
+#pragma unroll 4
+      for (int i = 0; i < N; ++i) Tv[i * SV] = rec[4 + i];
+      unsigned swaps = 0;
+      Cbm4Cell::photo(T, mc, PH);
+      Cbm4Cell::build_E<SV>(Tv, PH, mc, 1.0 / (H * sp.Gamma), lu);
+      cbm4_cell::lu_factor<SV>(lu, dinv, swaps);
+      st_global_256(out + ST_HDR, T, H, (double)((unsigned)rec[2] | (swaps << 24)), rec[3]);
 #pragma unroll 2
-    for (int e = 0; e < 364; e += 4)
-      st_global_256(out + ST_LU + e, lu[e * SV], lu[(e + 1) * SV], lu[(e + 2) * SV], lu[(e + 3) * SV]);
-    st_global_256(out + ST_LU + 364, lu[364 * SV], lu[365 * SV], lu[366 * SV], 0.0);
+      for (int e = 0; e < 364; e += 4)
+        st_global_256(out + ST_LU + e, lu[e * SV], lu[(e + 1) * SV], lu[(e + 2) * SV], lu[(e + 3) * SV]);
+      st_global_256(out + ST_LU + 364, lu[364 * SV], lu[365 * SV], lu[366 * SV], 0.0);
 #pragma unroll 1
-    for (int k = 0; k < N; k += 4)
-      st_global_256(out + ST_DINV + k, dinv[k * SV], dinv[(k + 1) * SV], dinv[(k + 2) * SV], dinv[(k + 3) * SV]);
-    const int S = sp.S;
-#pragma unroll 1
-    for (int s = 0; s < S; ++s) {
-      const double* Z = rec + 4 + N + s * N;
-#pragma unroll 4
-      for (int i = 0; i < N; ++i) Tv[i * SV] = Yv[i * SV] + Z[i];          // TMP = Y + Z_i (:700)
-      Cbm4Cell::photo(T + sp.C[s] * H, mc, PH);
-      cbm4_cell::jac_values<SV>(Tv, mc.fix, PH, out + ST_J + s * 276);
+      for (int k = 0; k < N; k += 4)
+        st_global_256(out + ST_DINV + k, dinv[k * SV], dinv[(k + 1) * SV], dinv[(k + 2) * SV], dinv[(k + 3) * SV]);
     }
   }
 }

@@ -136,6 +136,22 @@ int fatode_sdirk_integrate_tlm_batch(int model, int64_t ncells, int nvar, int nt
                                      const double* rcntrl_u, int* istatus, double* rstatus, int* ierr,
                                      const double* model_params, int mem, void* stream);
 
+/* INTEGRATE_ADJ of ADJ/SDIRK_ADJ (ADJ/SDIRK_ADJ/SDIRK_ADJ_f90_Integrator.F90:29):
+ *   INTEGRATE_ADJ(NVAR,NP,NADJ,NNZERO,Y,Lambda,Mu,TIN,TOUT,ATOL_adj,RTOL_adj,ATOL,RTOL,FUN,JAC,ADJINIT,JACP,DRDY,DRDP,
+ *                 ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U,Ierr_U,Q,QFUN)
+ * Discrete adjoint of the five SDIRK methods.  Presets ICNTRL(5) = 8, ICNTRL(7) = 1 (direct adjoint solve: one factorisation per
+ * stage), user values override when > 0; Max_no_steps defaults to 10000 and Newton starting values are always interpolated in
+ * this family.  Built: the preset direct mode, NADJ <= 32, Mu for the model's NP parameters, ADJINIT of the drivers (Lambda = I,
+ * Mu = 0), cbm4 only; ICNTRL(7) /= 1 (simplified-Newton adjoint stages) and the quadrature terms return FATODE_EUNSUPPORTED.
+ * Reference behaviour kept: a system whose forward sweep fails still gets ADJINIT and the backward sweep over its accepted
+ * steps, and its IERR is the backward sweep's (1) — RSTATUS(1) < TOUT tells (:519-531).  Arguments as
+ * fatode_ros_integrate_adj_batch. */
+int fatode_sdirk_integrate_adj_batch(int model, int64_t ncells, int nvar, int np, int nadj, double* y, double* lambda,
+                                     double* mu, double tin, double tout, const double* atol_adj, const double* rtol_adj,
+                                     const double* atol, const double* rtol, const int* icntrl_u, const double* rcntrl_u,
+                                     int* istatus, double* rstatus, int* ierr, double* mu_sum, const double* model_params,
+                                     int mem, void* stream);
+
 /* INTEGRATE of FWD/ERK (FWD/ERK/ERK_f90_Integrator.F90:28):
  *   INTEGRATE(TIN,TOUT,NVAR,VAR,RTOL,ATOL,FUN,ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U,Ierr_U)   (no NNZERO, no JAC)
  * Explicit Runge-Kutta pairs, ICNTRL(3) = 1 Erk23, 2 Erk3_Heun, 3 Erk43, 0/4 Dopri5 (default), 5 Verner, 6 Dopri853; user
