@@ -242,6 +242,15 @@ def run_side_workload(args):
         desc = ("EXAMPLES/cbm4 ADJ/RK_ADJ: Radau-2A (ICNTRL(3)=1), NADJ=32, NP=29, fixed-sweep discrete adjoint, 12h..84h, "
                 "rtol 0.1f*1e-5, atol 0.1f*1e-7 (cbm4_rk_adj_dr.F90)")
         ncpu = 32
+    elif w == "cbm4_sdirk_adj":
+        nc = args.cells if args.cells != 131072 else 9472
+        rtol, atol = tolerances()
+        y0 = perturbed_states(F.initial_state("cbm4"), nc)
+        run = lambda y: F.integrate_adj("cbm4", T0, T1, y, 32, rtol, atol, family="sdirk")
+        cpu = lambda y: O.sdirk_adj("cbm4", y, 32, T0, T1, atol, rtol)
+        desc = ("EXAMPLES/cbm4 ADJ/SDIRK_ADJ: Sdirk4a, NADJ=32, NP=29, direct adjoint solve (presets), 12h..84h, driver tolerances "
+                "of ROS_ADJ")
+        ncpu = 32
     elif w == "cbm4_sdirk_tlm":
         nc = args.cells if args.cells != 131072 else 9472
         rtol, atol = tolerances()
@@ -335,7 +344,7 @@ def main():
     ap.add_argument("--impl", default="fatode_b200", choices=["fatode_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="cbm4_ros_adj", choices=["cbm4_ros_adj", "small_strato_fwd", "cbm4_ros_tlm", "cbm4_sdirk", "cbm4_rk", "cbm4_rk_adj", "cbm4_sdirk_tlm", "swe_erk", "swe_erk_tlm"],
+    ap.add_argument("--workload", default="cbm4_ros_adj", choices=["cbm4_ros_adj", "small_strato_fwd", "cbm4_ros_tlm", "cbm4_sdirk", "cbm4_rk", "cbm4_rk_adj", "cbm4_sdirk_tlm", "cbm4_sdirk_adj", "swe_erk", "swe_erk_tlm"],
                     help="cbm4_ros_adj = the headline metric (default); the others are side measurements of the other "
                          "BASELINE configs / entry points (single GPU, one JSON line each, not the driver's metric)")
     args = ap.parse_args()

@@ -1725,7 +1725,7 @@ static int sdirk_tlm_group(const SdirkParams& sp, const Cbm4Const& mc, const std
       g_stats.launches++; g_stats.launches_expand++;
       SdirkTlmArgs aa{nb, d_off, d_cell, g_sd_fat.as<double>(), d_ytlm, g_ctr.as<unsigned long long>(), ntlm};
       CUDA_TRY(cudaFuncSetAttribute(k_sdirk_tlm_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDIRK_TLM_SMEM));
-      const unsigned ablocks = (unsigned)std::min<int>(nb, 2 * sms);
+      const unsigned ablocks = (unsigned)std::min<int>(nb, 3 * sms);   // 71.6 KB of shared memory per warp: three per SM
       tm.start();
       k_sdirk_tlm_cell<<<ablocks, 32, SDIRK_TLM_SMEM, st>>>(sp, aa);
       CUDA_TRY(cudaGetLastError());

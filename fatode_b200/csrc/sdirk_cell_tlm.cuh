@@ -101,7 +101,7 @@ struct SdirkTlmArgs {
 constexpr int ST_VEC = 7;   // per-lane vectors: Y_tlm, Z_tlm(5), G
 constexpr size_t SDIRK_TLM_SMEM = sizeof(double) * ((size_t)ST_VEC * 32 * 32 + ST_REC);
 
-__global__ void __launch_bounds__(32, 2)
+__global__ void __launch_bounds__(32, 3)
 k_sdirk_tlm_cell(SdirkParams sp, SdirkTlmArgs a) {
   extern __shared__ __align__(16) double cell_smem[];
   constexpr int N = 32, SV = 32;

@@ -10,6 +10,7 @@
 !     MODULE SDIRK_f90_Integrator   :: INTEGRATE       (FWD/SDIRK/SDIRK_f90_Integrator.F90:25)   after fatode_b200_set_family(FATODE_FAMILY_SDIRK)
 !     MODULE RK_f90_Integrator      :: INTEGRATE       (FWD/RK/RK_f90_Integrator.F90:32)         after fatode_b200_set_family(FATODE_FAMILY_RK)
 !     MODULE RK_adj_f90_Integrator  :: INTEGRATE_ADJ   (ADJ/RK_ADJ/RK_ADJ_f90_Integrator.F90:20) after fatode_b200_set_family(FATODE_FAMILY_RK)
+!     MODULE SDIRK_ADJ_f90_Integrator :: INTEGRATE_ADJ (ADJ/SDIRK_ADJ/SDIRK_ADJ_f90_Integrator.F90:29) after fatode_b200_set_family(FATODE_FAMILY_SDIRK)
 !     MODULE SDIRK_TLM_f90_Integrator :: INTEGRATE_TLM (TLM/SDIRK_TLM/SDIRK_TLM_f90_Integrator.F90:31) after fatode_b200_set_family(FATODE_FAMILY_SDIRK)
 !     MODULE ERK_f90_Integrator     :: INTEGRATE       (FWD/ERK/ERK_f90_Integrator.F90:28)       as INTEGRATE_ERK (rename on the USE line)
 !     MODULE ERK_TLM_f90_Integrator :: INTEGRATE_TLM   (TLM/ERK_TLM/ERK_TLM_f90_Integrator.F90:28) as INTEGRATE_ERK_TLM
@@ -127,6 +128,19 @@ MODULE fatode_b200_mod
       REAL(C_DOUBLE), INTENT(IN) :: atol(*), rtol(*)
       INTEGER(C_INT) :: istatus(*), ierr(*)
       INTEGER(C_INT) :: fatode_rk_integrate_adj_batch
+    END FUNCTION
+    FUNCTION fatode_sdirk_integrate_adj_batch(model, ncells, nvar, np, nadj, y, lambda, mu, tin, tout, atol_adj, rtol_adj, &
+                                            atol, rtol, icntrl_u, rcntrl_u, istatus, rstatus, ierr, mu_sum, model_params, &
+                                            mem, stream) BIND(C, NAME='fatode_sdirk_integrate_adj_batch')
+      IMPORT :: C_INT, C_INT64_T, C_DOUBLE, C_PTR
+      INTEGER(C_INT), VALUE :: model, nvar, np, nadj, mem
+      INTEGER(C_INT64_T), VALUE :: ncells
+      REAL(C_DOUBLE), VALUE :: tin, tout
+      REAL(C_DOUBLE) :: y(*), lambda(*), rstatus(*)
+      TYPE(C_PTR), VALUE :: mu, atol_adj, rtol_adj, icntrl_u, rcntrl_u, mu_sum, model_params, stream
+      REAL(C_DOUBLE), INTENT(IN) :: atol(*), rtol(*)
+      INTEGER(C_INT) :: istatus(*), ierr(*)
+      INTEGER(C_INT) :: fatode_sdirk_integrate_adj_batch
     END FUNCTION
     FUNCTION fatode_ros_integrate_tlm_batch(model, ncells, nvar, ntlm, y, y_tlm, tin, tout, atol_tlm, rtol_tlm, atol, rtol, &
                                             icntrl_u, rcntrl_u, istatus, rstatus, ierr, model_params, mem, stream) &
@@ -289,7 +303,7 @@ CONTAINS
     IF (PRESENT(ICNTRL_U)) pic = C_LOC(ICNTRL_U)
     IF (PRESENT(RCNTRL_U)) prc = C_LOC(RCNTRL_U)
     ! mode selection of the reference (:100-144): Mu is propagated only with NP>0, Mu, JACP and HESSTR_VEC_F_PY present
-    IF (NP > 0 .AND. PRESENT(Mu) .AND. PRESENT(JACP) .AND. (PRESENT(HESSTR_VEC_F_PY) .OR. current_family == FATODE_FAMILY_RK)) THEN
+    IF (NP > 0 .AND. PRESENT(Mu) .AND. PRESENT(JACP) .AND. (PRESENT(HESSTR_VEC_F_PY) .OR. current_family /= FATODE_FAMILY_ROS)) THEN
       pmu = C_LOC(Mu); npc = INT(NP, C_INT)
     END IF
     IF (PRESENT(Q) .AND. PRESENT(QFUN)) THEN
@@ -303,6 +317,12 @@ CONTAINS
                                          C_NULL_PTR, C_NULL_PTR, FATODE_MEM_HOST, C_NULL_PTR)
       IF (rc /= 0) ierr(1) = rc
       IF (ierr(1) < 0) PRINT *, 'Runge-Kutta-ADJ: Unsuccessful exit at T=', TIN, ' (IERR=', ierr(1), ')'   ! RK_ADJ :135-137
+    ELSE IF (current_family == FATODE_FAMILY_SDIRK) THEN   ! ADJ/SDIRK_ADJ/SDIRK_ADJ_f90_Integrator.F90:29-31 (cbm4_sdirk_adj_dr.F90:230-234)
+      rc = fatode_sdirk_integrate_adj_batch(current_model, 1_C_INT64_T, INT(NVAR, C_INT), npc, INT(NADJ, C_INT), Y, Lambda, pmu, &
+                                            TIN, TOUT, C_NULL_PTR, C_NULL_PTR, ATOL, RTOL, pic, prc, ist, rst, ierr, &
+                                            C_NULL_PTR, C_NULL_PTR, FATODE_MEM_HOST, C_NULL_PTR)
+      IF (rc /= 0) ierr(1) = rc
+      IF (ierr(1) < 0) PRINT *, 'SDIRK: Unsuccessful exit at T=', TIN, ' (Ierr=', ierr(1), ')'
     ELSE
       rc = fatode_ros_integrate_adj_batch(current_model, 1_C_INT64_T, INT(NVAR, C_INT), npc, INT(NADJ, C_INT), Y, Lambda, pmu, &
                                           TIN, TOUT, C_NULL_PTR, C_NULL_PTR, ATOL, RTOL, pic, prc, ist, rst, ierr, &
