@@ -1302,7 +1302,12 @@ static int cellfwd_launch(CellFwdKernel<Params, Const, Extra...> kern, size_t sm
 }
 
 enum { IMPL_SDIRK = 0, IMPL_RK = 1 };
-constexpr int RK_LANES_CBM4 = 16;   // 13.4 KB of shared memory per system (three factor planes + 17 vectors)
+// Active lanes per one-warp block of the per-thread forward kernels: the shared-memory footprint per system (6 KB SDIRK, 13.4 KB
+// RK: three factor planes + 17 vectors) fixes the number of systems per SM (about 32 / 16).  Measured: spreading them over four
+// blocks of 8 / 4 lanes (four schedulers) is SLOWER (SDIRK 8.0 -> 7.2 k systems/s, RK 8.3 -> 3.2 k): the sweeps are bound by the
+// issue rate of their one warp, and narrower warps issue the same instruction stream four times.
+constexpr int SDIRK_LANES_CBM4 = 32;
+constexpr int RK_LANES_CBM4 = 16;
 constexpr int RK_LANES_DENSE = 7, SDIRK_LANES_DENSE = 16;   // general-pivoting second pass (dense 32 x 32 planes)
 
 static int implicit_integrate_batch(int family, int model, int64_t ncells, int nvar, double* y, double tin, double tout,
@@ -1346,7 +1351,7 @@ static int implicit_integrate_batch(int family, int model, int64_t ncells, int n
   int rc;
   if (family == IMPL_SDIRK) {
     if (model == FATODE_MODEL_CBM4)
-      rc = cellfwd_launch<SdirkParams, Cbm4Const, double*, int, int>(k_sdirk_fwd_cell<Cbm4Cell, 32>, SdirkSmem<Cbm4Cell, 32>::BYTES, 32, sp, mc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st, nullptr, (double*)nullptr, 0, 0);
+      rc = cellfwd_launch<SdirkParams, Cbm4Const, double*, int, int>(k_sdirk_fwd_cell<Cbm4Cell, SDIRK_LANES_CBM4>, SdirkSmem<Cbm4Cell, SDIRK_LANES_CBM4>::BYTES, SDIRK_LANES_CBM4, sp, mc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st, nullptr, (double*)nullptr, 0, 0);
     else if (model == FATODE_MODEL_SMALL_STRATO)
       rc = cellfwd_launch<SdirkParams, SmallConst, double*, int, int>(k_sdirk_fwd_cell<SmallStratoCell, 32>, SdirkSmem<SmallStratoCell, 32>::BYTES, 32, sp, sc, ncells, d_y, da, dr, d_ist, d_rst, d_ierr, st, nullptr, (double*)nullptr, 0, 0);
     else
@@ -1517,7 +1522,7 @@ static int rk_adj_device(const RkParams& rp, const Cbm4Const& mc, int64_t ncells
   free_b += g_rk_tape.cap + g_rk_fat.cap;
   const size_t budget = g_tape_budget ? (size_t)g_tape_budget : (size_t)(0.6 * (double)free_b);
   const int cap = std::min(rp.max_no_steps + 1, g_rk_tape_slot > 0 ? g_rk_tape_slot : 1024);   // Nstp > Max_no_steps stops: one more may be accepted
-  int64_t wave = g_wave_cells > 0 ? g_wave_cells : (int64_t)sms * RK_LANES_CBM4 * 2;
+  int64_t wave = g_wave_cells > 0 ? g_wave_cells : (int64_t)sms * 16 * 2;   // two resident rounds of 16 systems per SM
   wave = std::min<int64_t>(wave, std::max<int64_t>(1, (int64_t)(0.2 * (double)budget / ((double)cap * RK_REC * sizeof(double)))));
   const size_t fat_budget = (size_t)(0.75 * (double)budget);
   std::vector<int> ids, overflow;
@@ -1648,12 +1653,12 @@ static int sdirk_tlm_group(const SdirkParams& sp, const Cbm4Const& mc, const std
   CUDA_TRY(cudaMemcpyAsync(d_ids, ids.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
   CUDA_TRY(g_sd_tape.ensure(sizeof(double) * (size_t)n * cap * SD_REC));
   if (adj) {
-    if (int e = cellfwd_launch<SdirkParams, Cbm4Const, double*, int, int>(k_sdirk_fwd_cell<Cbm4Cell, 32, SD_MODE_ADJ>, SdirkSmem<Cbm4Cell, 32>::BYTES, 32,
+    if (int e = cellfwd_launch<SdirkParams, Cbm4Const, double*, int, int>(k_sdirk_fwd_cell<Cbm4Cell, SDIRK_LANES_CBM4, SD_MODE_ADJ>, SdirkSmem<Cbm4Cell, SDIRK_LANES_CBM4>::BYTES, SDIRK_LANES_CBM4,
                                                                          sp, mc, n, d_y, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, d_ids,
                                                                          g_sd_tape.as<double>(), cap, ntlm))
       return e;
   } else {
-    if (int e = cellfwd_launch<SdirkParams, Cbm4Const, double*, int, int>(k_sdirk_fwd_cell<Cbm4Cell, 32, SD_MODE_TLM>, SdirkSmem<Cbm4Cell, 32>::BYTES, 32,
+    if (int e = cellfwd_launch<SdirkParams, Cbm4Const, double*, int, int>(k_sdirk_fwd_cell<Cbm4Cell, SDIRK_LANES_CBM4, SD_MODE_TLM>, SdirkSmem<Cbm4Cell, SDIRK_LANES_CBM4>::BYTES, SDIRK_LANES_CBM4,
                                                                          sp, mc, n, d_y, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, d_ids,
                                                                          g_sd_tape.as<double>(), cap, ntlm))
       return e;

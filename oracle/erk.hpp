@@ -13,6 +13,10 @@
 //                                             vec2grid :292-315, compute_F :318-567 (third-order upwind flux splitting,
 //                                             periodic halo); FUN = vec2grid -> compute_F -> grid2vec
 //                                             (EXAMPLES/swe/SWE_ERK/swe2D_erk_dr.F90:2-14)
+// Pinned: FWD/ERK + the SWE model against the reference's golden file EXAMPLES/swe/SWE_ERK/swe_lsode_sol.txt (tests/golden/
+// swe_lsode_sol.txt; relative L2 error 7e-3 / 2e-4 / 1e-6 at tolerances 1e-2 / 1e-4 / 1e-6, tests/test_oracle_erk.py).
+// PARITY UNPINNED by reference artefacts for the ERK_TLM part (the TLM driver only prints): checked against finite
+// differences of the pinned state sweep.
 // Not restated: the dense-Jacobian TLM mode (ICNTRL(5) /= 0: a full 4800 x 4800 JAC + MATMUL per stage, compute_JacF
 // :570-2128) returns -100.
 // Statement order and BLAS call order follow the Fortran (DAXPY with a zero factor returns at once, as netlib's does);

@@ -12,6 +12,10 @@
 // Differences from FWD/SDIRK that matter for ISTATUS: the LU is never reused across steps (:879), every stage of every
 // attempt evaluates one more Jacobian (:701-702) and runs the TLM iterations of all NTLM columns — rejected attempts
 // included — each iteration counting one Nsol (:727).
+// PARITY UNPINNED by reference artefacts: the reference ships no CBM-IV driver and no golden file for this family (its TLM
+// drivers exist for the shallow-water example only and write nothing).  The restatement is cross-validated against the ROS_TLM
+// restatement, finite differences of its own state sweep and exact linearity in Y_tlm(t0) (tests/test_oracle_sdirk_tlm.py); its
+// state sweep shares every routine with the golden-pinned FWD/SDIRK restatement (sdirk.hpp).
 #pragma once
 #include <vector>
 #include "sdirk.hpp"
