@@ -36,6 +36,7 @@
 #include "rk_cell_fwd.cuh"
 #include "model_cbm4_dense_cell.cuh"
 #include "rk_cell_adj.cuh"
+#include "sdirk_dense_sens.cuh"
 
 using namespace fatode;
 
@@ -1641,7 +1642,8 @@ static void release_sdirk_workspace() { g_sd_tape.release(); g_sd_fat.release();
 struct SdirkAdjHost { SdirkAdjCoef co; double* d_mu; int with_mu, np; };
 static int sdirk_tlm_group(const SdirkParams& sp, const Cbm4Const& mc, const std::vector<int>& ids, int cap, int ntlm, size_t fat_budget,
                            double* d_y, double* d_ytlm, const double* d_atol, const double* d_rtol, int* d_ist, double* d_rst,
-                           int* d_ierr, cudaStream_t st, int sms, std::vector<int>& overflow, const SdirkAdjHost* adj = nullptr) {
+                           int* d_ierr, cudaStream_t st, int sms, std::vector<int>& overflow, const SdirkAdjHost* adj = nullptr,
+                           bool dense = false) {
   const int n = (int)ids.size();
   if (n == 0) return 0;
   const size_t idx_bytes = sizeof(int) * (size_t)n * 3 + 16 + sizeof(long long) * (size_t)(n + 1);
@@ -1652,15 +1654,22 @@ static int sdirk_tlm_group(const SdirkParams& sp, const Cbm4Const& mc, const std
   long long* d_off = reinterpret_cast<long long*>(reinterpret_cast<char*>(g_sd_idx.p) + ((sizeof(int) * (size_t)n * 3 + 15) / 16) * 16);
   CUDA_TRY(cudaMemcpyAsync(d_ids, ids.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
   CUDA_TRY(g_sd_tape.ensure(sizeof(double) * (size_t)n * cap * SD_REC));
-  if (adj) {
-    if (int e = cellfwd_launch<SdirkParams, Cbm4Const, double*, int, int>(k_sdirk_fwd_cell<Cbm4Cell, SDIRK_LANES_CBM4, SD_MODE_ADJ>, SdirkSmem<Cbm4Cell, SDIRK_LANES_CBM4>::BYTES, SDIRK_LANES_CBM4,
-                                                                         sp, mc, n, d_y, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, d_ids,
-                                                                         g_sd_tape.as<double>(), cap, ntlm))
-      return e;
-  } else {
-    if (int e = cellfwd_launch<SdirkParams, Cbm4Const, double*, int, int>(k_sdirk_fwd_cell<Cbm4Cell, SDIRK_LANES_CBM4, SD_MODE_TLM>, SdirkSmem<Cbm4Cell, SDIRK_LANES_CBM4>::BYTES, SDIRK_LANES_CBM4,
-                                                                         sp, mc, n, d_y, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, d_ids,
-                                                                         g_sd_tape.as<double>(), cap, ntlm))
+  {
+    typedef CellFwdKernel<SdirkParams, Cbm4Const, double*, int, int> Kern;
+    Kern kern;
+    size_t smem;
+    int lanes;
+    if (dense) {   // general partial pivoting (systems the static-pattern pass handed back)
+      kern = adj ? (Kern)k_sdirk_fwd_cell<Cbm4DenseCell, SDIRK_LANES_DENSE, SD_MODE_ADJ> : (Kern)k_sdirk_fwd_cell<Cbm4DenseCell, SDIRK_LANES_DENSE, SD_MODE_TLM>;
+      smem = SdirkSmem<Cbm4DenseCell, SDIRK_LANES_DENSE>::BYTES;
+      lanes = SDIRK_LANES_DENSE;
+    } else {
+      kern = adj ? (Kern)k_sdirk_fwd_cell<Cbm4Cell, SDIRK_LANES_CBM4, SD_MODE_ADJ> : (Kern)k_sdirk_fwd_cell<Cbm4Cell, SDIRK_LANES_CBM4, SD_MODE_TLM>;
+      smem = SdirkSmem<Cbm4Cell, SDIRK_LANES_CBM4>::BYTES;
+      lanes = SDIRK_LANES_CBM4;
+    }
+    if (int e = cellfwd_launch<SdirkParams, Cbm4Const, double*, int, int>(kern, smem, lanes, sp, mc, n, d_y, d_atol, d_rtol, d_ist, d_rst, d_ierr,
+                                                                         st, d_ids, g_sd_tape.as<double>(), cap, ntlm))
       return e;
   }
   CUDA_TRY(g_sd_stat.ensure(sizeof(int) * 2 * (size_t)n));
@@ -1668,7 +1677,7 @@ static int sdirk_tlm_group(const SdirkParams& sp, const Cbm4Const& mc, const std
   std::vector<int> h_stat(2 * (size_t)n);
   CUDA_TRY(cudaMemcpyAsync(h_stat.data(), g_sd_stat.p, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  const size_t rec_bytes = sizeof(double) * (adj ? SA_REC : ST_REC);
+  const size_t rec_bytes = sizeof(double) * (adj ? (dense ? DA_REC : SA_REC) : (dense ? DT_REC : ST_REC));
   std::vector<int> b_slot, b_cell;
   std::vector<long long> b_off;
   auto flush = [&]() -> int {
@@ -1684,24 +1693,28 @@ static int sdirk_tlm_group(const SdirkParams& sp, const Cbm4Const& mc, const std
       PhaseTimer tm(st);
       if (nrec > 0) {
         SdirkAdjPrepArgs pa{(long)nrec, nb, d_off, d_slot, g_sd_tape.as<double>(), cap, g_sd_fat.as<double>()};
-        const size_t psm = sizeof(double) * (size_t)(cbm4_cell::NLU + 2 * 32) * SA_PREP_LANES;
-        CUDA_TRY(cudaFuncSetAttribute(k_sdirk_adj_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+        auto pk = dense ? k_sdirk_adj_prep_dense : k_sdirk_adj_prep;
+        const int plan = dense ? DA_PREP_LANES : SA_PREP_LANES;
+        const size_t psm = sizeof(double) * (size_t)((dense ? DN_LU + 32 : cbm4_cell::NLU + 2 * 32)) * plan;
+        CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
         int per_sm = 1;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sdirk_adj_prep, 32, psm));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk, 32, psm));
         const long long nwork = nrec * sp.S;
-        const unsigned pblocks = (unsigned)std::min<long long>((nwork + SA_PREP_LANES - 1) / SA_PREP_LANES, (long long)sms * std::max(per_sm, 1));
+        const unsigned pblocks = (unsigned)std::min<long long>((nwork + plan - 1) / plan, (long long)sms * std::max(per_sm, 1));
         tm.start();
-        k_sdirk_adj_prep<<<pblocks, 32, psm, st>>>(sp, mc, pa);
+        pk<<<pblocks, 32, psm, st>>>(sp, mc, pa);
         CUDA_TRY(cudaGetLastError());
         g_stats.ms_forward_tape += tm.stop();
         g_stats.launches++; g_stats.launches_expand++;
       }
       SdirkAdjArgs aa{nb, d_off, d_cell, g_sd_fat.as<double>(), d_ytlm, adj->d_mu, d_ist, d_ierr, g_ctr.as<unsigned long long>(), ntlm,
                       adj->with_mu, adj->np};
-      CUDA_TRY(cudaFuncSetAttribute(k_sdirk_adj_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDIRK_ADJ_SMEM));
+      auto ck = dense ? k_sdirk_adj_cell_dense : k_sdirk_adj_cell;
+      const size_t csm = dense ? SDIRK_ADJ_DENSE_SMEM : SDIRK_ADJ_SMEM;
+      CUDA_TRY(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
       const unsigned ablocks = (unsigned)std::min<int>(nb, 3 * sms);
       tm.start();
-      k_sdirk_adj_cell<<<ablocks, 32, SDIRK_ADJ_SMEM, st>>>(sp, adj->co, aa);
+      ck<<<ablocks, 32, csm, st>>>(sp, adj->co, aa);
       CUDA_TRY(cudaGetLastError());
       g_stats.ms_adjoint += tm.stop();
       g_stats.launches++; g_stats.launches_adjoint++;
@@ -1717,22 +1730,26 @@ static int sdirk_tlm_group(const SdirkParams& sp, const Cbm4Const& mc, const std
     PhaseTimer tm(st);
     if (nrec > 0) {
       SdirkTlmPrepArgs pa{(long)nrec, nb, d_off, d_slot, g_sd_tape.as<double>(), cap, g_sd_fat.as<double>()};
-      const size_t psm = sizeof(double) * (size_t)(cbm4_cell::NLU + 2 * 32) * ST_PREP_LANES;
-      CUDA_TRY(cudaFuncSetAttribute(k_sdirk_tlm_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+      auto pk = dense ? k_sdirk_tlm_prep_dense : k_sdirk_tlm_prep;
+      const int plan = dense ? DT_PREP_LANES : ST_PREP_LANES;
+      const size_t psm = sizeof(double) * (size_t)((dense ? DN_LU + 32 : cbm4_cell::NLU + 2 * 32)) * plan;
+      CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
       int per_sm = 1;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sdirk_tlm_prep, 32, psm));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk, 32, psm));
       const long long nwork = nrec * (sp.S + 1);
-      const unsigned pblocks = (unsigned)std::min<long long>((nwork + ST_PREP_LANES - 1) / ST_PREP_LANES, (long long)sms * std::max(per_sm, 1));
+      const unsigned pblocks = (unsigned)std::min<long long>((nwork + plan - 1) / plan, (long long)sms * std::max(per_sm, 1));
       tm.start();
-      k_sdirk_tlm_prep<<<pblocks, 32, psm, st>>>(sp, mc, pa);
+      pk<<<pblocks, 32, psm, st>>>(sp, mc, pa);
       CUDA_TRY(cudaGetLastError());
       g_stats.ms_forward_tape += tm.stop();
       g_stats.launches++; g_stats.launches_expand++;
       SdirkTlmArgs aa{nb, d_off, d_cell, g_sd_fat.as<double>(), d_ytlm, g_ctr.as<unsigned long long>(), ntlm};
-      CUDA_TRY(cudaFuncSetAttribute(k_sdirk_tlm_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDIRK_TLM_SMEM));
-      const unsigned ablocks = (unsigned)std::min<int>(nb, 3 * sms);   // 71.6 KB of shared memory per warp: three per SM
+      auto ck = dense ? k_sdirk_tlm_cell_dense : k_sdirk_tlm_cell;
+      const size_t csm = dense ? SDIRK_TLM_DENSE_SMEM : SDIRK_TLM_SMEM;
+      CUDA_TRY(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+      const unsigned ablocks = (unsigned)std::min<int>(nb, (dense ? 2 : 3) * sms);   // 71.6 KB (dense: 85 KB) of shared memory per warp
       tm.start();
-      k_sdirk_tlm_cell<<<ablocks, 32, SDIRK_TLM_SMEM, st>>>(sp, aa);
+      ck<<<ablocks, 32, csm, st>>>(sp, aa);
       CUDA_TRY(cudaGetLastError());
       g_stats.ms_adjoint += tm.stop();
       g_stats.launches++; g_stats.launches_adjoint++;
@@ -1772,25 +1789,41 @@ static int sdirk_tlm_device(const SdirkParams& sp, const Cbm4Const& mc, int64_t 
   int64_t wave = g_wave_cells > 0 ? g_wave_cells : (int64_t)sms * 32 * 2;
   wave = std::min<int64_t>(wave, std::max<int64_t>(1, (int64_t)(0.35 * (double)budget / ((double)cap * SD_REC * sizeof(double)))));
   const size_t fat_budget = (size_t)(0.6 * (double)budget);
-  std::vector<int> ids, overflow;
-  for (int64_t w0 = 0; w0 < ncells; w0 += wave) {
-    const int64_t w1 = std::min(ncells, w0 + wave);
-    ids.resize((size_t)(w1 - w0));
-    for (int64_t c = w0; c < w1; ++c) ids[(size_t)(c - w0)] = (int)c;
-    if (int e = sdirk_tlm_group(sp, mc, ids, cap, ntlm, fat_budget, d_y, d_ytlm, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, sms, overflow, adj))
-      return e;
-    g_stats.waves++;
-  }
-  while (!overflow.empty()) {   // more accepted steps than the default slot: again with room for Max_no_steps
-    const int capx = sp.max_no_steps + 1;
-    const size_t per = (size_t)capx * SD_REC * sizeof(double);
-    const size_t take = std::max<size_t>(1, std::min<size_t>(overflow.size(), (size_t)(0.35 * (double)budget) / per));
-    std::vector<int> part(overflow.end() - (long)take, overflow.end()), again;
-    overflow.resize(overflow.size() - take);
-    if (int e = sdirk_tlm_group(sp, mc, part, capx, ntlm, fat_budget, d_y, d_ytlm, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, sms, again, adj))
-      return e;
-    if (!again.empty()) return fail(FATODE_ENOMEM, "SDIRK_TLM tape overflow with a Max_no_steps slot");
-    g_stats.waves++;
+  auto run_all = [&](const std::vector<int>& all, bool dense) -> int {
+    std::vector<int> ids, overflow;
+    for (size_t w0 = 0; w0 < all.size(); w0 += (size_t)wave) {
+      const size_t w1 = std::min(all.size(), w0 + (size_t)wave);
+      ids.assign(all.begin() + (long)w0, all.begin() + (long)w1);
+      if (int e = sdirk_tlm_group(sp, mc, ids, cap, ntlm, fat_budget, d_y, d_ytlm, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, sms, overflow, adj, dense))
+        return e;
+      g_stats.waves++;
+    }
+    while (!overflow.empty()) {   // more accepted steps than the default slot: again with room for Max_no_steps
+      const int capx = sp.max_no_steps + 1;
+      const size_t per = (size_t)capx * SD_REC * sizeof(double);
+      const size_t take = std::max<size_t>(1, std::min<size_t>(overflow.size(), (size_t)(0.35 * (double)budget) / per));
+      std::vector<int> part(overflow.end() - (long)take, overflow.end()), again;
+      overflow.resize(overflow.size() - take);
+      if (int e = sdirk_tlm_group(sp, mc, part, capx, ntlm, fat_budget, d_y, d_ytlm, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, sms, again, adj, dense))
+        return e;
+      if (!again.empty()) return fail(FATODE_ENOMEM, "SDIRK tape overflow with a Max_no_steps slot");
+      g_stats.waves++;
+    }
+    return 0;
+  };
+  std::vector<int> all((size_t)ncells);
+  for (int64_t c = 0; c < ncells; ++c) all[(size_t)c] = (int)c;
+  if (int e = run_all(all, false)) return e;
+  {   // second pass: systems that left the static pivot pattern kept their initial state; general partial pivoting throughout
+    std::vector<int> h_ierr((size_t)ncells), irregular;
+    CUDA_TRY(cudaMemcpyAsync(h_ierr.data(), d_ierr, sizeof(int) * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int64_t c = 0; c < ncells; ++c)
+      if (h_ierr[(size_t)c] == SDIRK_IERR_IRREGULAR) irregular.push_back((int)c);
+    if (!irregular.empty()) {
+      if (int e = run_all(irregular, true)) return e;
+      g_stats.cells_general = (int64_t)irregular.size();
+    }
   }
   CUDA_TRY(cudaStreamSynchronize(st));
   return 0;

@@ -198,6 +198,59 @@ __device__ __noinline__ void dense32_zlu_solve(const double* ar, const double* a
   }
 }
 
+// DGETRS('N') / DGETRS('T') for the lane-per-column sweeps of the general-pivoting pass: ONE dense factorisation per warp in
+// shared memory (a: column-major 32 x 32, pivot rows as doubles at a[1024 + j], warp-uniform reads), the lane's right-hand side
+// in its shared-memory slot (b[i * SB]).  Loop order and exact-zero skips of netlib (oracle/ref_lapack.hpp::dgetrs).
+template <int SB>
+__device__ __noinline__ void dense32_solve_n_shared(const double* __restrict__ a, double* b) {
+  constexpr int N = 32;
+#pragma unroll 1
+  for (int i = 0; i < N; ++i) {
+    const int ip = (int)a[N * N + i];
+    if (ip != i) { const double t = b[i * SB]; b[i * SB] = b[ip * SB]; b[ip * SB] = t; }
+  }
+#pragma unroll 1
+  for (int k = 0; k < N; ++k) {
+    const double bk = b[k * SB];
+    if (bk != 0.0) {
+#pragma unroll 4
+      for (int i = k + 1; i < N; ++i) b[i * SB] = __dsub_rn(b[i * SB], __dmul_rn(bk, a[i + N * k]));
+    }
+  }
+#pragma unroll 1
+  for (int k = N - 1; k >= 0; --k) {
+    if (b[k * SB] != 0.0) {
+      const double bk = __ddiv_rn(b[k * SB], a[k + N * k]);
+      b[k * SB] = bk;
+#pragma unroll 4
+      for (int i = 0; i < k; ++i) b[i * SB] = __dsub_rn(b[i * SB], __dmul_rn(bk, a[i + N * k]));
+    }
+  }
+}
+template <int SB>
+__device__ __noinline__ void dense32_solve_t_shared(const double* __restrict__ a, double* b) {
+  constexpr int N = 32;
+#pragma unroll 1
+  for (int i = 0; i < N; ++i) {            // U^T x = b, dot-product form
+    double temp = b[i * SB];
+#pragma unroll 4
+    for (int k = 0; k < i; ++k) temp = __dsub_rn(temp, __dmul_rn(a[k + N * i], b[k * SB]));
+    b[i * SB] = __ddiv_rn(temp, a[i + N * i]);
+  }
+#pragma unroll 1
+  for (int i = N - 1; i >= 0; --i) {       // L^T x = b (unit diagonal)
+    double temp = b[i * SB];
+#pragma unroll 4
+    for (int k = i + 1; k < N; ++k) temp = __dsub_rn(temp, __dmul_rn(a[k + N * i], b[k * SB]));
+    b[i * SB] = temp;
+  }
+#pragma unroll 1
+  for (int i = N - 1; i >= 0; --i) {       // DLASWP backward
+    const int ip = (int)a[N * N + i];
+    if (ip != i) { const double t = b[i * SB]; b[i * SB] = b[ip * SB]; b[ip * SB] = t; }
+  }
+}
+
 struct Cbm4DenseCell : Cbm4Cell {
   static constexpr int NLU = 32 * 32 + 32;   // dense matrix + pivot rows
   static constexpr bool HAS_GENERAL_PATH = false;

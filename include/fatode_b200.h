@@ -127,9 +127,11 @@ int fatode_sdirk_integrate_batch(int model, int64_t ncells, int nvar, double* y,
  * override when > 0 (:60-77); an ICNTRL(3) outside 0..5 selects Sdirk2a in this family (:262-275).  Built: the preset
  * mode — modified-Newton TLM (ICNTRL(7) = 0) with the iteration count of the state stage, columns outside the step
  * control (ICNTRL(9) = ICNTRL(12) = 0); ICNTRL(7) = 1, ICNTRL(9) != 0 and ICNTRL(12) != 0 return FATODE_EUNSUPPORTED.
- * ntlm <= 32, cbm4 only.  Per-cell IERR: 1, the reference's -1..-8, or -20 for a system whose factorisations leave the
- * static pivot pattern (its Y and Y_tlm are returned unchanged).  A cell whose state sweep fails returns Y and Y_tlm as of
- * its last accepted step, as the reference. */
+ * ntlm <= 32, cbm4 only.  Per-cell IERR: 1 or the reference's -1..-8.  Systems whose factorisations leave the static pivot
+ * pattern (all of them at rtol >= 1e-3) are integrated a second time with general partial pivoting in the state sweep, the
+ * preparation and the column sweep (fatode_stats.cells_general counts them); results are bit-identical to the reference's
+ * operation order on both paths.  A cell whose state sweep fails returns Y and Y_tlm as of its last accepted step, as the
+ * reference. */
 int fatode_sdirk_integrate_tlm_batch(int model, int64_t ncells, int nvar, int ntlm, double* y, double* y_tlm,
                                      double tin, double tout, const double* atol_tlm, const double* rtol_tlm,
                                      const double* atol, const double* rtol, const int* icntrl_u,
@@ -144,8 +146,8 @@ int fatode_sdirk_integrate_tlm_batch(int model, int64_t ncells, int nvar, int nt
  * this family.  Built: the preset direct mode, NADJ <= 32, Mu for the model's NP parameters, ADJINIT of the drivers (Lambda = I,
  * Mu = 0), cbm4 only; ICNTRL(7) /= 1 (simplified-Newton adjoint stages) and the quadrature terms return FATODE_EUNSUPPORTED.
  * Reference behaviour kept: a system whose forward sweep fails still gets ADJINIT and the backward sweep over its accepted
- * steps, and its IERR is the backward sweep's (1) — RSTATUS(1) < TOUT tells (:519-531).  Arguments as
- * fatode_ros_integrate_adj_batch. */
+ * steps, and its IERR is the backward sweep's (1) — RSTATUS(1) < TOUT tells (:519-531).  Systems that leave the static pivot
+ * pattern take a second pass with general partial pivoting, as for SDIRK_TLM.  Arguments as fatode_ros_integrate_adj_batch. */
 int fatode_sdirk_integrate_adj_batch(int model, int64_t ncells, int nvar, int np, int nadj, double* y, double* lambda,
                                      double* mu, double tin, double tout, const double* atol_adj, const double* rtol_adj,
                                      const double* atol, const double* rtol, const int* icntrl_u, const double* rcntrl_u,

@@ -150,3 +150,22 @@ def test_sdirk_adj_variants():
     ic[6] = 2                                    # Newton mode of the adjoint solve: not built
     with pytest.raises(F.FatodeError):
         F.integrate_adj("cbm4", T0, t1, y0, 4, rtol, atol, icntrl_u=ic, family="sdirk")
+
+
+@pytest.mark.gpu
+def test_sdirk_adj_general_pivoting_pass_at_loose_tolerances():
+    """rtol 1e-3: every system leaves the static pivot pattern and takes the second pass with general partial pivoting."""
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    rtol, atol = np.full(32, F01 * 1.0e-2), np.full(32, F01 * 1.0e-4)
+    y0 = perturbed_states(F.initial_state("cbm4"), 20)
+    t1 = T0 + 30 * 3600.0
+    res = F.integrate_adj("cbm4", T0, t1, y0, 32, rtol, atol, family="sdirk")
+    ref = O.sdirk_adj("cbm4", y0, 32, T0, t1, atol, rtol)
+    assert (res.ierr == 1).all() and F.last_stats().cells_general > 0
+    check(res, ref)
+    assert np.array_equal(res.lambda_, ref["lambda_"])
+    rtol, atol = np.full(32, F01 * 3.0e-3), np.full(32, F01 * 3.0e-5)
+    res = F.integrate_adj("cbm4", T0, t1, y0, 7, rtol, atol, family="sdirk", want_mu=False)
+    ref = O.sdirk_adj("cbm4", y0, 7, T0, t1, atol, rtol, with_mu=False)
+    check(res, ref)

@@ -129,3 +129,23 @@ def test_sdirk_tlm_unsupported_modes_and_option_errors():
     assert res.ierr[0] == ref["ierr"][0]
     if ref["ierr"][0] < 0:
         assert np.array_equal(res.y[0], y0)
+
+
+def test_sdirk_tlm_general_pivoting_pass_at_loose_tolerances():
+    """rtol 1e-3: every system leaves the static pivot pattern in its forward factorisations and takes the second pass with
+    netlib's general partial pivoting (dense DGETF2 / DGETRS in the state sweep, the preparation and the column sweep)."""
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    rtol, atol = tols(1.0e-2)
+    y0 = perturbed_states(F.initial_state("cbm4"), 20)
+    yt = np.tile(np.eye(32)[:9], (20, 1, 1))
+    t1 = T0 + 30 * 3600.0
+    res = F.integrate_tlm("cbm4", T0, t1, y0, yt, rtol, atol, family="sdirk")
+    ref = O.sdirk_tlm("cbm4", y0, yt, T0, t1, atol, rtol)
+    assert (res.ierr == 1).all() and F.last_stats().cells_general > 0
+    check(res, ref)
+    # a mixed batch: intermediate tolerance, some systems on each path
+    rtol, atol = tols(3.0e-3)
+    res = F.integrate_tlm("cbm4", T0, t1, y0, yt, rtol, atol, family="sdirk")
+    ref = O.sdirk_tlm("cbm4", y0, yt, T0, t1, atol, rtol)
+    check(res, ref)

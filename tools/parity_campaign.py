@@ -1,0 +1,61 @@
+"""Wider GPU-vs-oracle parity sweep of the implicit-family sensitivity entry points and the explicit family (more systems and
+tolerances than tests/ can afford): prints one line per case; exits non-zero on any mismatch."""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import fatode_b200 as F
+import oracle_lib as O
+from fatode_b200.inputs import perturbed_states, swe_members
+F01 = float(np.float32(0.1)); T0 = 43200.0
+bad = 0
+
+
+def sens_err(a, b):
+    sc = np.max(np.abs(b), axis=2); er = np.max(np.abs(a - b), axis=2)
+    fl = 1e-10 * np.max(sc, axis=1, keepdims=True)
+    return float(np.max(er / np.maximum(sc, fl)))
+
+
+def report(name, res, ref, sens=None):
+    global bad
+    ok = (np.array_equal(res.ierr, ref["ierr"]) and np.array_equal(res.istatus, ref["istatus"]) and np.array_equal(res.rstatus, ref["rstatus"])
+          and np.array_equal(res.y, ref["y"]))
+    msg = f"{name}: state/ISTATUS/RSTATUS bitwise {ok}; ierr codes {dict(zip(*np.unique(res.ierr, return_counts=True)))}"
+    for label, a, b in (sens or []):
+        e = sens_err(a, b)
+        msg += f"; {label} max col err {e:.2e} bitwise {np.array_equal(a, b)}"
+        ok = ok and e <= 1e-9
+    print(msg, flush=True)
+    if not ok:
+        bad += 1
+
+
+nc = int(sys.argv[1]) if len(sys.argv) > 1 else 192
+first = 1000
+for k in (1e-2, 1e-3, 1e-4, 1e-5):
+    rtol, atol = np.full(32, F01 * k), np.full(32, F01 * k * 1e-2)
+    y0 = perturbed_states(F.initial_state("cbm4"), nc, first_cell=first)
+    first += nc
+    t1 = T0 + 30 * 3600.0
+    yt = np.tile(np.eye(32), (nc, 1, 1))
+    r = F.integrate_tlm("cbm4", T0, t1, y0, yt, rtol, atol, family="sdirk")
+    o = O.sdirk_tlm("cbm4", y0, yt, T0, t1, atol, rtol)
+    report(f"SDIRK_TLM rtol {F01*k:.0e} n {nc}", r, o, [("Y_tlm", r.y_tlm, o["y_tlm"])])
+    r = F.integrate_adj("cbm4", T0, t1, y0, 32, rtol, atol, family="sdirk")
+    o = O.sdirk_adj("cbm4", y0, 32, T0, t1, atol, rtol)
+    report(f"SDIRK_ADJ rtol {F01*k:.0e} n {nc}", r, o, [("Lambda", r.lambda_, o["lambda_"]), ("Mu", r.mu, o["mu"])])
+DT = float(np.float32(2.1573758800627289e-003))
+for tol, method in ((1e-2, 0), (1e-3, 5), (1e-5, 0), (1e-6, 6)):
+    ic = np.zeros(20, dtype=np.int32); ic[2] = method
+    y0 = swe_members(48, first_member=first); first += 48
+    tv = np.full(4800, tol)
+    r = F.integrate_erk("swe", 0.0, 50 * DT, y0, tv, tv, icntrl_u=ic)
+    o = O.erk("swe", y0, 0.0, 50 * DT, tv, tv, ic)
+    report(f"ERK method {method} tol {tol:.0e} n 48 (attempts/member {r.istatus[:,2].mean():.1f})", r, o)
+    v = np.random.default_rng(int(1e6 * tol) + method).standard_normal((48, 2, 4800))
+    r = F.integrate_erk("swe", 0.0, 5 * DT, y0, tv, tv, icntrl_u=ic, var_tlm=v)
+    o = O.erk("swe", y0, 0.0, 5 * DT, tv, tv, ic, y_tlm=v)
+    report(f"ERK_TLM method {method} tol {tol:.0e} n 48 ntlm 2", r, o, [("Y_tlm", r.y_tlm, o["y_tlm"])])
+print("MISMATCHES", bad)
+sys.exit(1 if bad else 0)
