@@ -37,6 +37,7 @@
 #include "model_cbm4_dense_cell.cuh"
 #include "rk_cell_adj.cuh"
 #include "sdirk_dense_sens.cuh"
+#include "rk_dense_adj.cuh"
 
 using namespace fatode;
 
@@ -1436,7 +1437,7 @@ __global__ void k_rk_gather_status(int n, const int* __restrict__ ids, const int
 static int rk_adj_group(const RkParams& rp, const Cbm4Const& mc, const std::vector<int>& ids, int cap, int nadj, bool with_mu,
                         int np, bool do_adjoint, size_t fat_budget, double* d_y, double* d_lam, double* d_mu, const double* d_atol,
                         const double* d_rtol, int* d_ist, double* d_rst, int* d_ierr, cudaStream_t st, int sms,
-                        std::vector<int>& overflow) {
+                        std::vector<int>& overflow, bool dense = false) {
   const int n = (int)ids.size();
   if (n == 0) return 0;
   // index buffer: [ids n][slot n][cell n] ints, then [rec_off n + 1] long long
@@ -1448,10 +1449,17 @@ static int rk_adj_group(const RkParams& rp, const Cbm4Const& mc, const std::vect
   long long* d_off = reinterpret_cast<long long*>(reinterpret_cast<char*>(g_rk_idx.p) + ((sizeof(int) * (size_t)n * 3 + 15) / 16) * 16);
   CUDA_TRY(cudaMemcpyAsync(d_ids, ids.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
   if (do_adjoint) CUDA_TRY(g_rk_tape.ensure(sizeof(double) * (size_t)n * cap * RK_REC));
-  if (int e = cellfwd_launch<RkParams, Cbm4Const, double*, int>(k_rk_fwd_cell<Cbm4Cell, RK_LANES_CBM4, true>, RkSmem<Cbm4Cell, RK_LANES_CBM4>::BYTES,
-                                                               RK_LANES_CBM4, rp, mc, n, d_y, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, d_ids,
-                                                               do_adjoint ? g_rk_tape.as<double>() : (double*)nullptr, cap))
-    return e;
+  if (dense) {   // general partial pivoting (systems the static-pattern pass handed back)
+    if (int e = cellfwd_launch<RkParams, Cbm4Const, double*, int>(k_rk_fwd_cell<Cbm4DenseCell, RK_LANES_DENSE, true>, RkSmem<Cbm4DenseCell, RK_LANES_DENSE>::BYTES,
+                                                                 RK_LANES_DENSE, rp, mc, n, d_y, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, d_ids,
+                                                                 do_adjoint ? g_rk_tape.as<double>() : (double*)nullptr, cap))
+      return e;
+  } else {
+    if (int e = cellfwd_launch<RkParams, Cbm4Const, double*, int>(k_rk_fwd_cell<Cbm4Cell, RK_LANES_CBM4, true>, RkSmem<Cbm4Cell, RK_LANES_CBM4>::BYTES,
+                                                                 RK_LANES_CBM4, rp, mc, n, d_y, d_atol, d_rtol, d_ist, d_rst, d_ierr, st, d_ids,
+                                                                 do_adjoint ? g_rk_tape.as<double>() : (double*)nullptr, cap))
+      return e;
+  }
   if (!do_adjoint) return 0;
   CUDA_TRY(g_rk_stat.ensure(sizeof(int) * 2 * (size_t)n));
   k_rk_gather_status<<<(n + 255) / 256, 256, 0, st>>>(n, d_ids, d_ierr, d_ist, g_rk_stat.as<int>());
@@ -1459,7 +1467,7 @@ static int rk_adj_group(const RkParams& rp, const Cbm4Const& mc, const std::vect
   CUDA_TRY(cudaMemcpyAsync(h_stat.data(), g_rk_stat.p, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   // backward sweep in batches that fit the record budget
-  const size_t rec_bytes = sizeof(double) * RA_REC;
+  const size_t rec_bytes = sizeof(double) * (dense ? DR_REC : RA_REC);
   std::vector<int> b_slot, b_cell;
   std::vector<long long> b_off;
   auto flush = [&]() -> int {
@@ -1474,20 +1482,24 @@ static int rk_adj_group(const RkParams& rp, const Cbm4Const& mc, const std::vect
     PhaseTimer tm(st);
     if (nrec > 0) {
       RkAdjPrepArgs pa{(long)nrec, nb, d_off, d_slot, g_rk_tape.as<double>(), cap, g_rk_fat.as<double>()};
-      const size_t psm = sizeof(double) * (size_t)(3 * cbm4_cell::NLU + 3 * 32) * RA_PREP_LANES;
-      CUDA_TRY(cudaFuncSetAttribute(k_rk_adj_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-      const unsigned pblocks = (unsigned)std::min<long long>((nrec + RA_PREP_LANES - 1) / RA_PREP_LANES, (long long)sms);
+      auto pk = dense ? k_rk_adj_prep_dense : k_rk_adj_prep;
+      const int plan = dense ? DR_PREP_LANES : RA_PREP_LANES;
+      const size_t psm = sizeof(double) * (size_t)(dense ? 2 * DR_LUN + 1024 + 2 * 32 : 3 * cbm4_cell::NLU + 3 * 32) * plan;
+      CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+      const unsigned pblocks = (unsigned)std::min<long long>((nrec + plan - 1) / plan, (long long)sms);
       tm.start();
-      k_rk_adj_prep<<<pblocks, 32, psm, st>>>(rp, mc, pa);
+      pk<<<pblocks, 32, psm, st>>>(rp, mc, pa);
       CUDA_TRY(cudaGetLastError());
       g_stats.ms_forward_tape += tm.stop();
       g_stats.launches++; g_stats.launches_expand++;
     }
     RkAdjArgs aa{nb, d_off, d_cell, g_rk_fat.as<double>(), d_lam, d_mu, d_ist, g_ctr.as<unsigned long long>(), nadj, with_mu ? 1 : 0, np};
-    CUDA_TRY(cudaFuncSetAttribute(k_rk_adj_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RK_ADJ_SMEM));
-    const unsigned ablocks = (unsigned)std::min<int>(nb, 2 * sms);
+    auto ck = dense ? k_rk_adj_cell_dense : k_rk_adj_cell;
+    const size_t csm = dense ? RK_ADJ_DENSE_SMEM : RK_ADJ_SMEM;
+    CUDA_TRY(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+    const unsigned ablocks = (unsigned)std::min<int>(nb, (dense ? 1 : 2) * sms);
     tm.start();
-    k_rk_adj_cell<<<ablocks, 32, RK_ADJ_SMEM, st>>>(rp, aa);
+    ck<<<ablocks, 32, csm, st>>>(rp, aa);
     CUDA_TRY(cudaGetLastError());
     g_stats.ms_adjoint += tm.stop();
     g_stats.launches++; g_stats.launches_adjoint++;
@@ -1526,28 +1538,44 @@ static int rk_adj_device(const RkParams& rp, const Cbm4Const& mc, int64_t ncells
   int64_t wave = g_wave_cells > 0 ? g_wave_cells : (int64_t)sms * 16 * 2;   // two resident rounds of 16 systems per SM
   wave = std::min<int64_t>(wave, std::max<int64_t>(1, (int64_t)(0.2 * (double)budget / ((double)cap * RK_REC * sizeof(double)))));
   const size_t fat_budget = (size_t)(0.75 * (double)budget);
-  std::vector<int> ids, overflow;
-  for (int64_t w0 = 0; w0 < ncells; w0 += wave) {
-    const int64_t w1 = std::min(ncells, w0 + wave);
-    ids.resize((size_t)(w1 - w0));
-    for (int64_t c = w0; c < w1; ++c) ids[(size_t)(c - w0)] = (int)c;
-    if (int e = rk_adj_group(rp, mc, ids, cap, nadj, with_mu, np, do_adjoint, fat_budget, d_y, d_lam, d_mu, d_atol, d_rtol, d_ist, d_rst,
-                             d_ierr, st, sms, overflow))
-      return e;
-    g_stats.waves++;
-  }
-  // systems with more accepted steps than the default slot: again, a few at a time, with room for Max_no_steps
-  while (!overflow.empty()) {
-    const int capx = rp.max_no_steps + 1;
-    const size_t per = (size_t)capx * RK_REC * sizeof(double);
-    const size_t take = std::max<size_t>(1, std::min<size_t>(overflow.size(), (size_t)(0.2 * (double)budget) / per));
-    std::vector<int> part(overflow.end() - (long)take, overflow.end()), again;
-    overflow.resize(overflow.size() - take);
-    if (int e = rk_adj_group(rp, mc, part, capx, nadj, with_mu, np, do_adjoint, fat_budget, d_y, d_lam, d_mu, d_atol, d_rtol, d_ist,
-                             d_rst, d_ierr, st, sms, again))
-      return e;
-    if (!again.empty()) return fail(FATODE_ENOMEM, "RK_ADJ tape overflow with a Max_no_steps slot");
-    g_stats.waves++;
+  auto run_all = [&](const std::vector<int>& all, bool dense) -> int {
+    std::vector<int> ids, overflow;
+    for (size_t w0 = 0; w0 < all.size(); w0 += (size_t)wave) {
+      const size_t w1 = std::min(all.size(), w0 + (size_t)wave);
+      ids.assign(all.begin() + (long)w0, all.begin() + (long)w1);
+      if (int e = rk_adj_group(rp, mc, ids, cap, nadj, with_mu, np, do_adjoint, fat_budget, d_y, d_lam, d_mu, d_atol, d_rtol, d_ist, d_rst,
+                               d_ierr, st, sms, overflow, dense))
+        return e;
+      g_stats.waves++;
+    }
+    // systems with more accepted steps than the default slot: again, a few at a time, with room for Max_no_steps
+    while (!overflow.empty()) {
+      const int capx = rp.max_no_steps + 1;
+      const size_t per = (size_t)capx * RK_REC * sizeof(double);
+      const size_t take = std::max<size_t>(1, std::min<size_t>(overflow.size(), (size_t)(0.2 * (double)budget) / per));
+      std::vector<int> part(overflow.end() - (long)take, overflow.end()), again;
+      overflow.resize(overflow.size() - take);
+      if (int e = rk_adj_group(rp, mc, part, capx, nadj, with_mu, np, do_adjoint, fat_budget, d_y, d_lam, d_mu, d_atol, d_rtol, d_ist,
+                               d_rst, d_ierr, st, sms, again, dense))
+        return e;
+      if (!again.empty()) return fail(FATODE_ENOMEM, "RK_ADJ tape overflow with a Max_no_steps slot");
+      g_stats.waves++;
+    }
+    return 0;
+  };
+  std::vector<int> all((size_t)ncells);
+  for (int64_t c = 0; c < ncells; ++c) all[(size_t)c] = (int)c;
+  if (int e = run_all(all, false)) return e;
+  {   // second pass: systems that left the static pivot pattern kept their initial state; general partial pivoting throughout
+    std::vector<int> h_ierr((size_t)ncells), irregular;
+    CUDA_TRY(cudaMemcpyAsync(h_ierr.data(), d_ierr, sizeof(int) * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int64_t c = 0; c < ncells; ++c)
+      if (h_ierr[(size_t)c] == RK_IERR_IRREGULAR) irregular.push_back((int)c);
+    if (!irregular.empty()) {
+      if (int e = run_all(irregular, true)) return e;
+      g_stats.cells_general = (int64_t)irregular.size();
+    }
   }
   if (with_mu && d_mu_sum && do_adjoint)
     if (int e = mu_sum_device(ncells, nadj * np, d_mu, d_ierr, d_mu_sum, st)) return e;

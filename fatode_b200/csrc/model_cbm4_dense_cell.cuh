@@ -251,6 +251,48 @@ __device__ __noinline__ void dense32_solve_t_shared(const double* __restrict__ a
   }
 }
 
+// ZGETRS('T') (plain transpose) for the lane-per-column sweep of the general-pivoting pass: the dense complex factors of the warp
+// in shared memory (zr / zi column-major 32 x 32, pivot rows as doubles at zr[1024 + j]), the lane's right-hand side (br, bi) in
+// its shared-memory slots.  Loop order, four-multiplication products and Smith quotients of oracle/ref_lapack.hpp::zgetrs_t.
+template <int SB>
+__device__ __noinline__ void dense32_zsolve_t_shared(const double* __restrict__ zr, const double* __restrict__ zi, double* br, double* bi) {
+  constexpr int N = 32;
+#pragma unroll 1
+  for (int i = 0; i < N; ++i) {
+    const double b0r = br[i * SB], b0i = bi[i * SB];
+    double tr = __dsub_rn(__dmul_rn(1.0, b0r), __dmul_rn(0.0, b0i)), ti = __dadd_rn(__dmul_rn(1.0, b0i), __dmul_rn(0.0, b0r));
+#pragma unroll 2
+    for (int k = 0; k < i; ++k) {
+      const double ar = zr[k + N * i], ai = zi[k + N * i], xr = br[k * SB], xi = bi[k * SB];
+      tr = __dsub_rn(tr, __dsub_rn(__dmul_rn(ar, xr), __dmul_rn(ai, xi)));
+      ti = __dsub_rn(ti, __dadd_rn(__dmul_rn(ar, xi), __dmul_rn(ai, xr)));
+    }
+    double qr, qi;
+    zdiv_dev(tr, ti, zr[i + N * i], zi[i + N * i], qr, qi);
+    br[i * SB] = qr; bi[i * SB] = qi;
+  }
+#pragma unroll 1
+  for (int i = N - 1; i >= 0; --i) {
+    const double b0r = br[i * SB], b0i = bi[i * SB];
+    double tr = __dsub_rn(__dmul_rn(1.0, b0r), __dmul_rn(0.0, b0i)), ti = __dadd_rn(__dmul_rn(1.0, b0i), __dmul_rn(0.0, b0r));
+#pragma unroll 2
+    for (int k = i + 1; k < N; ++k) {
+      const double ar = zr[k + N * i], ai = zi[k + N * i], xr = br[k * SB], xi = bi[k * SB];
+      tr = __dsub_rn(tr, __dsub_rn(__dmul_rn(ar, xr), __dmul_rn(ai, xi)));
+      ti = __dsub_rn(ti, __dadd_rn(__dmul_rn(ar, xi), __dmul_rn(ai, xr)));
+    }
+    br[i * SB] = tr; bi[i * SB] = ti;
+  }
+#pragma unroll 1
+  for (int i = N - 1; i >= 0; --i) {
+    const int ip = (int)zr[N * N + i];
+    if (ip != i) {
+      double t = br[i * SB]; br[i * SB] = br[ip * SB]; br[ip * SB] = t;
+      t = bi[i * SB]; bi[i * SB] = bi[ip * SB]; bi[ip * SB] = t;
+    }
+  }
+}
+
 struct Cbm4DenseCell : Cbm4Cell {
   static constexpr int NLU = 32 * 32 + 32;   // dense matrix + pivot rows
   static constexpr bool HAS_GENERAL_PATH = false;

@@ -207,8 +207,9 @@ int fatode_rk_integrate_batch(int model, int64_t ncells, int nvar, double* y, do
  * Same argument layout as fatode_ros_integrate_adj_batch; ADJINIT of the example drivers (Lambda = I, Mu = 0) is applied
  * after the forward sweep, systems whose forward sweep fails keep the caller's Lambda/Mu.  cbm4 only.  The direct and the
  * adaptive adjoint solves (ICNTRL(7) = 2, 3) and the quadrature terms return FATODE_EUNSUPPORTED.  Per-cell IERR: 1, or
- * the reference's -1..-13, or -20 for a system whose forward factorisations leave the static pivot pattern (no
- * general-pivoting pass for this family yet). */
+ * the reference's -1..-13.  Systems whose real or complex factorisations leave the static pivot pattern (none at rtol 1e-6,
+ * all at rtol >= 1e-4) are integrated a second time with general partial pivoting (fatode_stats.cells_general counts them);
+ * the forward sweep, the counters and Lambda are bit-identical to the reference's operation order on both paths. */
 int fatode_rk_integrate_adj_batch(int model, int64_t ncells, int nvar, int np, int nadj, double* y, double* lambda,
                                   double* mu, double tin, double tout, const double* atol_adj,
                                   const double* rtol_adj, const double* atol, const double* rtol,

@@ -163,3 +163,23 @@ def test_rk_adj_waves_batches_and_tape_overflow_are_invisible():
     for a, b in ((res.y, base.y), (res.istatus, base.istatus), (res.rstatus, base.rstatus), (res.lambda_, base.lambda_),
                  (res.mu, base.mu), (res.ierr, base.ierr)):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+def test_rk_adj_general_pivoting_pass_at_loose_tolerances():
+    """rtol 1e-4: every system leaves the static pivot pattern in its real or complex factorisations and takes the second pass
+    with netlib's general partial pivoting (dense DGETF2/ZGETF2 forward, dense DGETRS('T')/ZGETRS('T') in the backward sweep)."""
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    rtol, atol = np.full(32, F01 * 1.0e-3), np.full(32, F01 * 1.0e-5)
+    y0 = perturbed_states(F.initial_state("cbm4"), 12)
+    t1 = T0 + 20 * 3600.0
+    res = F.integrate_adj("cbm4", T0, t1, y0, 32, rtol, atol, icntrl_u=radau(), family="rk")
+    ref = O.rk_adj("cbm4", y0, 32, T0, t1, atol, rtol, radau())
+    assert (res.ierr == 1).all() and F.last_stats().cells_general > 0
+    assert np.array_equal(res.ierr, ref["ierr"]) and np.array_equal(res.istatus, ref["istatus"]) and np.array_equal(res.rstatus, ref["rstatus"])
+    assert np.array_equal(res.y, ref["y"])
+    assert np.array_equal(res.lambda_, ref["lambda_"]), "the backward sweep follows the reference's operation order"
+    sc = np.max(np.abs(ref["mu"]), axis=2)
+    er = np.max(np.abs(res.mu - ref["mu"]), axis=2)
+    assert np.all(er <= 1e-7 * np.maximum(sc, 1e-10 * sc.max(axis=1, keepdims=True)))

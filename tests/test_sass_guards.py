@@ -12,8 +12,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "fatode_b200", "lib", "libfatode_b200.so")
 # kernel -> minimum number of 256-bit global stores in its SASS (generated jac_values / hess / LU record writers)
-KERNELS = {"k_sdirk_tlm_prepE": 75, "k_sdirk_adj_prepE": 84, "k_rk_adj_prep": 115, "k_expand_tape": 150,
-           "k_sdirk_tlm_prep_dense": 70, "k_sdirk_adj_prep_dense": 75}
+KERNELS = {"k_sdirk_tlm_prepE": 75, "k_sdirk_adj_prepE": 84, "k_rk_adj_prepE": 115, "k_expand_tape": 150,
+           "k_sdirk_tlm_prep_dense": 70, "k_sdirk_adj_prep_dense": 75, "k_rk_adj_prep_dense": 70}
 
 
 @pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not available")

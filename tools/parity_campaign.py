@@ -17,7 +17,7 @@ def sens_err(a, b):
     return float(np.max(er / np.maximum(sc, fl)))
 
 
-def report(name, res, ref, sens=None):
+def report(name, res, ref, sens=None, tol=1e-9):
     global bad
     ok = (np.array_equal(res.ierr, ref["ierr"]) and np.array_equal(res.istatus, ref["istatus"]) and np.array_equal(res.rstatus, ref["rstatus"])
           and np.array_equal(res.y, ref["y"]))
@@ -25,7 +25,7 @@ def report(name, res, ref, sens=None):
     for label, a, b in (sens or []):
         e = sens_err(a, b)
         msg += f"; {label} max col err {e:.2e} bitwise {np.array_equal(a, b)}"
-        ok = ok and e <= 1e-9
+        ok = ok and e <= tol
     print(msg, flush=True)
     if not ok:
         bad += 1
@@ -45,6 +45,30 @@ for k in (1e-2, 1e-3, 1e-4, 1e-5):
     r = F.integrate_adj("cbm4", T0, t1, y0, 32, rtol, atol, family="sdirk")
     o = O.sdirk_adj("cbm4", y0, 32, T0, t1, atol, rtol)
     report(f"SDIRK_ADJ rtol {F01*k:.0e} n {nc}", r, o, [("Lambda", r.lambda_, o["lambda_"]), ("Mu", r.mu, o["mu"])])
+for k in (1e-2, 1e-3, 1e-4):
+    rtol, atol = np.full(32, F01 * k), np.full(32, F01 * k * 1e-2)
+    y0 = perturbed_states(F.initial_state("cbm4"), nc, first_cell=first)
+    first += nc
+    t1 = T0 + 30 * 3600.0
+    ic = np.zeros(20, dtype=np.int32); ic[2] = 5
+    r = F.integrate_adj("cbm4", T0, t1, y0, 32, rtol, atol, icntrl_u=ic)
+    o = O.ros_adj("cbm4", y0, 32, T0, t1, atol, rtol, ic)
+    loose = 1e-9 if k <= 1e-5 else 1e-6   # the 1e-9 contract is stated at RTOL = 1e-6; big steps amplify rounding differences
+    report(f"ROS_ADJ rtol {F01*k:.0e} n {nc} (general path cells {F.last_stats().cells_general})", r, o, [("Lambda", r.lambda_, o["lambda_"]), ("Mu", r.mu, o["mu"])], loose)
+    yt = np.tile(np.eye(32), (nc, 1, 1))
+    r = F.integrate_tlm("cbm4", T0, t1, y0, yt, rtol, atol, icntrl_u=ic)
+    o = O.ros_tlm("cbm4", y0, yt, T0, t1, atol, rtol, ic)
+    report(f"ROS_TLM rtol {F01*k:.0e} n {nc}", r, o, [("Y_tlm", r.y_tlm, o["y_tlm"])], loose)
+    ic = np.zeros(20, dtype=np.int32); ic[2] = 1
+    r = F.integrate_rk("cbm4", T0, t1, y0, rtol, atol, icntrl_u=ic)
+    o = O.rk_fwd("cbm4", y0, T0, t1, atol, rtol, ic)
+    report(f"FWD/RK rtol {F01*k:.0e} n {nc} (general pass cells {F.last_stats().cells_general})", r, o)
+    r = F.integrate_sdirk("cbm4", T0, t1, y0, rtol, atol)
+    o = O.sdirk_fwd("cbm4", y0, T0, t1, atol, rtol)
+    report(f"FWD/SDIRK rtol {F01*k:.0e} n {nc} (general pass cells {F.last_stats().cells_general})", r, o)
+    r = F.integrate_adj("cbm4", T0, t1, y0, 32, rtol, atol, icntrl_u=ic, family="rk")
+    o = O.rk_adj("cbm4", y0, 32, T0, t1, atol, rtol, ic)
+    report(f"RK_ADJ rtol {F01*k:.0e} n {nc} (general pass cells {F.last_stats().cells_general})", r, o, [("Lambda", r.lambda_, o["lambda_"]), ("Mu", r.mu, o["mu"])], loose)
 DT = float(np.float32(2.1573758800627289e-003))
 for tol, method in ((1e-2, 0), (1e-3, 5), (1e-5, 0), (1e-6, 6)):
     ic = np.zeros(20, dtype=np.int32); ic[2] = method
