@@ -143,6 +143,9 @@ struct ErkArgs {
   unsigned long long* queue;
   double* scratch;             // per CTA: S * N (+ ntlm * S * N) doubles
   int ntlm;
+  int tlm_trunc;               // ICNTRL(12) /= 0: the columns' truncation errors enter the step control
+  const double* atol_tlm;      // [ntlm][N] (read with tlm_trunc only)
+  const double* rtol_tlm;
 };
 
 template <bool TLM>
@@ -253,6 +256,40 @@ k_erk_swe(ErkParams p, ErkArgs a) {
         red[0] = fmax(sqrt(e / (double)SWE_N), 1.0e-10);
       }
       __syncthreads();
+      if constexpr (TLM) {
+        if (a.tlm_trunc) {   // ERK_ErrorNorm_TLM (TLM/ERK_TLM/ERK_TLM_f90_Integrator.F90:493-501, 613-626): scaled by the error vector itself
+          for (int col = 0; col < ntlm; ++col) {
+            double t[ERK_EPT];
+#pragma unroll
+            for (int q = 0; q < ERK_EPT; ++q) t[q] = 0.0;
+            for (int i = 0; i < S; ++i)
+              if (p.E[i] != 0.0) {
+                const double c = H * p.E[i];
+                if (c != 0.0) {
+                  const double* Ki = KT + ((size_t)col * S + i) * SWE_N + tid;
+#pragma unroll
+                  for (int q = 0; q < ERK_EPT; ++q) t[q] = t[q] + c * Ki[q * ERK_THREADS];
+                }
+              }
+#pragma unroll
+            for (int q = 0; q < ERK_EPT; ++q) {
+              const int v = tid + q * ERK_THREADS;
+              const size_t vt = (size_t)col * SWE_N + (p.vector_tol ? v : 0);
+              const double scal = 1.0 / (a.atol_tlm[vt] + a.rtol_tlm[vt] * fabs(t[q]));
+              const double w = t[q] * scal;
+              TMP[v] = w * w;
+            }
+            __syncthreads();
+            if (tid == 0) {
+              double e = 0.0;
+#pragma unroll 8
+              for (int v = 0; v < SWE_N; ++v) e = e + TMP[v];
+              red[0] = fmax(red[0], fmax(sqrt(e / (double)SWE_N), 1.0e-10));
+            }
+            __syncthreads();
+          }
+        }
+      }
       const double Err = red[0];
       double Fac = p.facsafe * fpm::pow_neg_inv(Err, p.ELO);
       Fac = fmax(p.facmin, fmin(p.facmax, Fac));

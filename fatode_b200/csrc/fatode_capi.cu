@@ -2009,7 +2009,7 @@ static thread_local CachedBuf g_erk_scratch;
 static void release_erk_workspace() { g_erk_scratch.release(); }
 
 static int erk_batch_impl(bool tlm, int model, int64_t ncells, int nvar, int ntlm, double* y, double* y_tlm, double tin, double tout,
-                          const double* atol, const double* rtol, const int* icntrl_u, const double* rcntrl_u, int* istatus,
+                          const double* atol_tlm, const double* rtol_tlm, const double* atol, const double* rtol, const int* icntrl_u, const double* rcntrl_u, int* istatus,
                           double* rstatus, int* ierr, int mem, void* stream) {
   g_err.clear();
   if (ncells < 0 || !y || !atol || !rtol || !istatus || !rstatus || !ierr) return fail(FATODE_EINVAL, "NULL required argument");
@@ -2025,14 +2025,22 @@ static int erk_batch_impl(bool tlm, int model, int64_t ncells, int nvar, int ntl
   if (tlm && tlm_opt[0] != 0)
     return fail(FATODE_EUNSUPPORTED, "ERK_TLM with a dense Jacobian (ICNTRL(5) /= 0: a 4800 x 4800 JAC + MATMUL per stage) is not built; "
                                      "use the preset finite-difference Jacobian-vector products");
-  if (tlm && tlm_opt[1] != 0) return fail(FATODE_EUNSUPPORTED, "ERK_TLM truncation-error control (ICNTRL(12) /= 0) is not built");
+  const bool trunc = tlm && tlm_opt[1] != 0;
+  if (trunc && (!atol_tlm || !rtol_tlm)) return fail(FATODE_EINVAL, "ERK_TLM with ICNTRL(12) /= 0 needs ATOL_TLM and RTOL_TLM");
   const int ntl = tlm ? ntlm : 0;
   const int ntol = ep.vector_tol ? nvar : 1;
-  DevBuf b_atol, b_rtol, b_y, b_yt, b_ist, b_rst, b_ierr;
+  DevBuf b_atol, b_rtol, b_y, b_yt, b_ist, b_rst, b_ierr, b_atl, b_rtl;
   CUDA_TRY(b_atol.alloc(sizeof(double) * ntol));
   CUDA_TRY(b_rtol.alloc(sizeof(double) * ntol));
   CUDA_TRY(cudaMemcpyAsync(b_atol.p, atol, sizeof(double) * ntol, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(b_rtol.p, rtol, sizeof(double) * ntol, cudaMemcpyHostToDevice, st));
+  if (trunc) {   // ATOL_TLM / RTOL_TLM (NVAR, NTLM): host arrays like ATOL / RTOL, shared by all members
+    const size_t nb = sizeof(double) * (size_t)nvar * ntl;
+    CUDA_TRY(b_atl.alloc(nb));
+    CUDA_TRY(b_rtl.alloc(nb));
+    CUDA_TRY(cudaMemcpyAsync(b_atl.p, atol_tlm, nb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b_rtl.p, rtol_tlm, nb, cudaMemcpyHostToDevice, st));
+  }
   double *d_y = y, *d_yt = y_tlm, *d_rst = rstatus;
   int *d_ist = istatus, *d_ierr = ierr;
   const size_t ny = sizeof(double) * (size_t)nvar * ncells, nt = ny * (size_t)ntl;
@@ -2061,7 +2069,7 @@ static int erk_batch_impl(bool tlm, int model, int64_t ncells, int nvar, int ntl
   CUDA_TRY(g_ctr.ensure(16 * sizeof(unsigned long long)));
   CUDA_TRY(cudaMemsetAsync(g_ctr.p, 0, 16 * sizeof(unsigned long long), st));
   ErkArgs ea{(long)ncells, d_y, d_y, d_yt, b_atol.as<double>(), b_rtol.as<double>(), d_ist, d_rst, d_ierr,
-             g_ctr.as<unsigned long long>(), g_erk_scratch.as<double>(), ntl};
+             g_ctr.as<unsigned long long>(), g_erk_scratch.as<double>(), ntl, trunc ? 1 : 0, b_atl.as<double>(), b_rtl.as<double>()};
   PhaseTimer tm(st);
   tm.start();
   kern<<<blocks, ERK_THREADS, ERK_SMEM, st>>>(ep, ea);
@@ -2086,7 +2094,7 @@ extern "C" int fatode_erk_integrate_batch(int model, int64_t ncells, int nvar, d
                                           const double* rtol, const int* icntrl_u, const double* rcntrl_u, int* istatus,
                                           double* rstatus, int* ierr, const double* model_params, int mem, void* stream) {
   (void)model_params;
-  return erk_batch_impl(false, model, ncells, nvar, 0, y, nullptr, tin, tout, atol, rtol, icntrl_u, rcntrl_u, istatus, rstatus, ierr,
+  return erk_batch_impl(false, model, ncells, nvar, 0, y, nullptr, tin, tout, nullptr, nullptr, atol, rtol, icntrl_u, rcntrl_u, istatus, rstatus, ierr,
                         mem, stream);
 }
 
@@ -2094,8 +2102,8 @@ extern "C" int fatode_erk_integrate_tlm_batch(int model, int64_t ncells, int nva
                                               double tout, const double* atol_tlm, const double* rtol_tlm, const double* atol,
                                               const double* rtol, const int* icntrl_u, const double* rcntrl_u, int* istatus,
                                               double* rstatus, int* ierr, const double* model_params, int mem, void* stream) {
-  (void)atol_tlm; (void)rtol_tlm; (void)model_params;   // the TLM tolerances are only read with ICNTRL(12) /= 0
-  return erk_batch_impl(true, model, ncells, nvar, ntlm, y, y_tlm, tin, tout, atol, rtol, icntrl_u, rcntrl_u, istatus, rstatus, ierr,
+  (void)model_params;   // the TLM tolerances (host arrays [ntlm][nvar], shared by all members) are only read with ICNTRL(12) /= 0
+  return erk_batch_impl(true, model, ncells, nvar, ntlm, y, y_tlm, tin, tout, atol_tlm, rtol_tlm, atol, rtol, icntrl_u, rcntrl_u, istatus, rstatus, ierr,
                         mem, stream);
 }
 

@@ -172,8 +172,9 @@ int fatode_erk_integrate_batch(int model, int64_t ncells, int nvar, double* y, d
  *                 ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U,IERR_U)
  * (the C ABI keeps the argument order of the other TLM entry points).  Built: the preset mode, ICNTRL(5) = 0 — Jacobian-vector
  * products by forward finite differences (FDJACV :1071-1097, increment RCNTRL(12) or sqrt(max(RTOL(1), eps))), one extra
- * FUN per column per stage, Nfun = S * (1 + NTLM) * Nstp — and ICNTRL(12) = 0; the dense-Jacobian mode and the TLM
- * truncation-error control return FATODE_EUNSUPPORTED.  y_tlm [ncells][ntlm][4800]. */
+ * FUN per column per stage, Nfun = S * (1 + NTLM) * Nstp — with or without the TLM truncation-error control (ICNTRL(12) /= 0:
+ * the columns' error norms, scaled with ATOL_TLM / RTOL_TLM [ntlm][nvar] — host arrays shared by all members — enter the step
+ * control, :493-501); the dense-Jacobian mode returns FATODE_EUNSUPPORTED.  y_tlm [ncells][ntlm][4800]. */
 int fatode_erk_integrate_tlm_batch(int model, int64_t ncells, int nvar, int ntlm, double* y, double* y_tlm,
                                    double tin, double tout, const double* atol_tlm, const double* rtol_tlm,
                                    const double* atol, const double* rtol, const int* icntrl_u,

@@ -97,11 +97,35 @@ def test_erk_tlm_matches_oracle():
     res = F.integrate_erk("swe", 0.0, 5 * DT, y0, tol, tol, icntrl_u=ic, rcntrl_u=rc, var_tlm=v3)
     ref = O.erk("swe", y0, 0.0, 5 * DT, tol, tol, ic, rc, y_tlm=v3)
     check(res, ref)
-    for k in (4, 11):                                         # dense-Jacobian mode, TLM truncation-error control
-        ic2 = np.zeros(20, dtype=np.int32)
-        ic2[k] = 1
-        with pytest.raises(F.FatodeError):
-            F.integrate_erk("swe", 0.0, 5 * DT, y0, tol, tol, icntrl_u=ic2, var_tlm=v)
+    ic2 = np.zeros(20, dtype=np.int32)
+    ic2[4] = 1                                                # dense-Jacobian mode (4800 x 4800 JAC + MATMUL per stage)
+    with pytest.raises(F.FatodeError):
+        F.integrate_erk("swe", 0.0, 5 * DT, y0, tol, tol, icntrl_u=ic2, var_tlm=v)
+
+
+def test_erk_tlm_truncation_error_control():
+    """ICNTRL(12) /= 0: the columns' error norms (scaled with ATOL_TLM / RTOL_TLM and the error vector itself) enter the step
+    control, so the step sequence changes with the columns; state, counters and Y_tlm still match the oracle bit for bit."""
+    import fatode_b200 as F
+    from fatode_b200.inputs import swe_members
+    y0 = swe_members(5)
+    tol = np.full(4800, 1e-3)
+    rng = np.random.default_rng(9)
+    v = 50.0 * rng.standard_normal((5, 2, 4800))
+    at, rt = np.full((2, 4800), 1e-5), np.full((2, 4800), 1e-4)
+    for method, scalar in ((0, 0), (3, 1)):
+        ic = np.zeros(20, dtype=np.int32)
+        ic[1], ic[2], ic[11] = scalar, method, 1
+        res = F.integrate_erk("swe", 0.0, 10 * DT, y0, tol, tol, icntrl_u=ic, var_tlm=v, atol_tlm=at, rtol_tlm=rt)
+        ref = O.erk("swe", y0, 0.0, 10 * DT, tol, tol, ic, y_tlm=v, atol_tlm=at, rtol_tlm=rt)
+        check(res, ref)
+        ic[11] = 0
+        free = F.integrate_erk("swe", 0.0, 10 * DT, y0, tol, tol, icntrl_u=ic, var_tlm=v)
+        assert (res.istatus[:, 2] > free.istatus[:, 2]).all()      # the columns' error does bind here
+    with pytest.raises(F.FatodeError):                        # ICNTRL(12) without the TLM tolerances
+        ic = np.zeros(20, dtype=np.int32)
+        ic[11] = 1
+        F.integrate_erk("swe", 0.0, 10 * DT, y0, tol, tol, icntrl_u=ic, var_tlm=v)
 
 
 def test_swe_is_rejected_by_the_implicit_families_and_erk_rejects_the_chemistry_models():
