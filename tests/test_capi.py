@@ -55,3 +55,18 @@ def test_inputs_generator_is_counter_based():
     assert np.array_equal(a[0], base)
     assert np.all(a[:, 6] == 0.0) and np.all(np.abs(a[1:, 0] / base[0] - 1.0) <= 0.1)
     assert len({tuple(r) for r in a}) == 64
+
+
+def test_swe_ensemble_inputs_shard_consistently_and_match_the_oracle():
+    """Host-side input generation of the shallow-water ensemble (no GPU): any rank can regenerate its members from the global
+    member index, and the library's initial state equals the oracle's bit for bit."""
+    import numpy as np
+    import fatode_b200 as F
+    from fatode_b200.inputs import swe_members
+    import oracle_lib as O
+    whole = swe_members(6)
+    parts = np.concatenate([swe_members(2, first_member=0), swe_members(4, first_member=2)])
+    assert np.array_equal(whole, parts)
+    assert np.array_equal(whole[0], O.swe_initial_state())          # member 0 is the driver's problem
+    assert np.array_equal(F.swe_initial_state(33.0, 1.5, -2.0), O.swe_initial_state(33.0, 1.5, -2.0))
+    assert len({float(m[:1600].max()) for m in whole}) == 6         # distinct amplitudes
