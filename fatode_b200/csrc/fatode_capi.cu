@@ -1737,12 +1737,21 @@ static int sdirk_tlm_group(const SdirkParams& sp, const Cbm4Const& mc, const std
       }
       SdirkAdjArgs aa{nb, d_off, d_cell, g_sd_fat.as<double>(), d_ytlm, adj->d_mu, d_ist, d_ierr, g_ctr.as<unsigned long long>(), ntlm,
                       adj->with_mu, adj->np};
-      auto ck = dense ? k_sdirk_adj_cell_dense : k_sdirk_adj_cell;
-      const size_t csm = dense ? SDIRK_ADJ_DENSE_SMEM : SDIRK_ADJ_SMEM;
-      CUDA_TRY(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
-      const unsigned ablocks = (unsigned)std::min<int>(nb, 3 * sms);
+      // static path: tensor-memory variant (one CTA of four sweep warps per SM; FATODE_SDIRK_ADJ_SMEM=1 selects the shared-memory
+      // variant with three one-warp CTAs per SM); general-pivoting pass: shared-memory variant with dense factors
+      static const bool use_tm = !(getenv("FATODE_SDIRK_ADJ_SMEM") && atoi(getenv("FATODE_SDIRK_ADJ_SMEM")) != 0);
       tm.start();
-      ck<<<ablocks, 32, csm, st>>>(sp, adj->co, aa);
+      if (!dense && use_tm) {
+        CUDA_TRY(cudaFuncSetAttribute(k_sdirk_adj_cell_tm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDIRK_ADJ_TM_SMEM));
+        const unsigned ablocks = (unsigned)std::min<int>((nb + SA_TM_WARPS - 1) / SA_TM_WARPS, sms);
+        k_sdirk_adj_cell_tm<<<ablocks, SA_TM_WARPS * 32, SDIRK_ADJ_TM_SMEM, st>>>(sp, adj->co, aa);
+      } else {
+        auto ck = dense ? k_sdirk_adj_cell_dense : k_sdirk_adj_cell;
+        const size_t csm = dense ? SDIRK_ADJ_DENSE_SMEM : SDIRK_ADJ_SMEM;
+        CUDA_TRY(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+        const unsigned ablocks = (unsigned)std::min<int>(nb, 3 * sms);
+        ck<<<ablocks, 32, csm, st>>>(sp, adj->co, aa);
+      }
       CUDA_TRY(cudaGetLastError());
       g_stats.ms_adjoint += tm.stop();
       g_stats.launches++; g_stats.launches_adjoint++;

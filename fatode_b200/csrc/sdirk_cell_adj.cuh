@@ -21,6 +21,7 @@
 #pragma once
 #include "sdirk_cell_fwd.cuh"
 #include "rk_cell_adj.cuh"
+#include "tmem.cuh"
 #include "gen/sdirk_adj_tableau_gen.h"
 
 namespace fatode {
@@ -230,6 +231,173 @@ k_sdirk_adj_cell(SdirkParams sp, SdirkAdjCoef co, SdirkAdjArgs a) {
       a.ierr[cell] = 1;
     }
   }
+}
+
+
+// ---- tensor-memory variant of the backward sweep (the shipped one for the static-pattern path).
+// The lane's seven vectors (Lambda, Mu, U_1..U_5 = 224 doubles) fit the 256 doubles of tensor memory a lane owns, the way the
+// Rosenbrock sweeps keep their running sums (tmem.cuh): shared memory then only stages the records (6.75 KB per warp), and an
+// SM runs FOUR sweep warps — one CTA of four warps, each with its quarter of the tensor memory and its own system — instead
+// of three.  tcgen05.ld/st are warp-wide, so idle lanes (column >= NADJ) run along and are dropped at the output.  Same
+// floating-point operations in the same order as k_sdirk_adj_cell: Lambda stays bit-identical.
+constexpr uint32_t SA_TM_LAM = 0, SA_TM_MU = 64, SA_TM_U = 128;       // 32-bit columns; U_s at SA_TM_U + 64 s
+constexpr int SA_TM_WARPS = 4;
+constexpr size_t SDIRK_ADJ_TM_SMEM = sizeof(double) * (size_t)SA_TM_WARPS * (SA_STAGE + SA_CHUNK);
+
+__global__ void __launch_bounds__(SA_TM_WARPS * 32, 1)
+k_sdirk_adj_cell_tm(SdirkParams sp, SdirkAdjCoef co, SdirkAdjArgs a) {
+  extern __shared__ __align__(16) double cell_smem[];
+  __shared__ uint32_t tmem_base_s;
+  constexpr int N = 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* const hdr = cell_smem + (size_t)warp * (SA_STAGE + SA_CHUNK);
+  double* const ch = hdr + SA_STAGE;
+  if (warp == 0) tmem::alloc512(&tmem_base_s);
+  tmem::fence_before_sync();
+  __syncthreads();
+  tmem::fence_after_sync();
+  const uint32_t tm = tmem_base_s + ((uint32_t)(warp * 32) << 16);
+  const bool active = lane < a.nadj;
+  const int S = sp.S;
+  for (;;) {
+    unsigned long long slot = 0;
+    if (lane == 0) slot = atomicAdd(a.queue, 1ull);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot >= (unsigned long long)a.ncells) break;
+    const long long r0 = a.rec_off[slot], r1 = a.rec_off[slot + 1];
+    const int cell = a.cell[slot];
+    double x[32], o[32];
+    // ADJINIT of the example drivers: Lambda = I, Mu = 0
+#pragma unroll
+    for (int i = 0; i < N; ++i) { x[i] = (i == lane) ? 1.0 : 0.0; o[i] = 0.0; }
+    tmem::st32(tm + SA_TM_LAM, x);
+    tmem::st32(tm + SA_TM_MU, o);
+    tmem::wait_st();
+    for (long long q = r1 - 1; q >= r0; --q) {
+      const double* rec = a.fat + (size_t)q * SA_REC;
+      __syncwarp();
+      {
+        const double2* src = reinterpret_cast<const double2*>(rec);
+        double2* dst = reinterpret_cast<double2*>(hdr);
+        for (int e = lane; e < SA_STAGE / 2; e += 32) dst[e] = __ldg(src + e);
+      }
+      double H = 0.0;
+#pragma unroll 1
+      for (int s = S - 1; s >= 0; --s) {
+        __syncwarp();
+        {
+          const double2* src = reinterpret_cast<const double2*>(rec + SA_STAGE + s * SA_CHUNK);
+          double2* dst = reinterpret_cast<double2*>(ch);
+          for (int e = lane; e < SA_CHUNK / 2; e += 32) dst[e] = __ldg(src + e);
+        }
+        __syncwarp();
+        H = hdr[SA_HDR + 1];
+        const double hgi = 1.0 / (H * sp.Gamma);
+        const unsigned swaps = (unsigned)ch[SA_SW];
+        tmem::ld32(tm + SA_TM_LAM, x);
+        {
+          const double b = co.B[s];
+#pragma unroll
+          for (int i = 0; i < N; ++i) x[i] = b * x[i];
+        }
+        for (int j = s + 1; j < S; ++j) {
+          const double c = co.A[j][s];
+          if (c != 0.0) {
+            double t[16];
+            tmem::ld16(tm + SA_TM_U + 64 * j, t);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = x[i] + c * t[i];
+            tmem::ld16(tm + SA_TM_U + 64 * j + 32, t);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[16 + i] = x[16 + i] + c * t[i];
+          }
+        }
+        asm volatile("" ::: "memory");
+        cbm4_cell::jt_vec_seq(ch + SA_J, x, o);
+#pragma unroll
+        for (int i = 0; i < N; ++i) o[i] = hgi * (H * o[i]);
+        asm volatile("" ::: "memory");
+        cbm4_cell::lut_solve_seq(ch + SA_LU, ch + SA_DINV, swaps, o);
+        tmem::st32(tm + SA_TM_U + 64 * s, o);
+        tmem::wait_st();
+      }
+      // Mu += V_1 + .. + V_S   (:961-983)
+      if (a.with_mu) {
+        tmem::ld32(tm + SA_TM_MU, o);
+#pragma unroll 1
+        for (int s = 0; s < S; ++s) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) x[i] = 0.0;
+          for (int j = s; j < S; ++j) {
+            const double c = H * co.A[j][s];
+            if (c != 0.0) {
+              double t[16];
+              tmem::ld16(tm + SA_TM_U + 64 * j, t);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) x[i] = x[i] + c * t[i];
+              tmem::ld16(tm + SA_TM_U + 64 * j + 32, t);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) x[16 + i] = x[16 + i] + c * t[i];
+            }
+          }
+          {
+            const double c = H * co.B[s];
+            if (c != 0.0) {
+              double t[16];
+              tmem::ld16(tm + SA_TM_LAM, t);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) x[i] = x[i] + c * t[i];
+              tmem::ld16(tm + SA_TM_LAM + 32, t);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) x[16 + i] = x[16 + i] + c * t[i];
+            }
+          }
+          const double* AP = hdr + SA_P + s * 32;
+          Cbm4Warp::stoich_cols(x, [&](auto pc, double spv) {
+            constexpr int p = decltype(pc)::value;
+            o[p] = fma(AP[p], spv, o[p]);
+          });
+        }
+        tmem::st32(tm + SA_TM_MU, o);
+      }
+      tmem::ld32(tm + SA_TM_LAM, x);
+      for (int s = 0; s < S; ++s) {
+        double t[16];
+        tmem::ld16(tm + SA_TM_U + 64 * s, t);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = x[i] + t[i];
+        tmem::ld16(tm + SA_TM_U + 64 * s + 32, t);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[16 + i] = x[16 + i] + t[i];
+      }
+      tmem::st32(tm + SA_TM_LAM, x);
+      tmem::wait_st();
+    }
+    tmem::ld32(tm + SA_TM_LAM, x);
+    tmem::ld32(tm + SA_TM_MU, o);
+    if (active) {
+      double* lo = a.lambda + ((size_t)cell * a.nadj + lane) * N;
+#pragma unroll
+      for (int i = 0; i < N; ++i) lo[i] = x[i];
+      if (a.with_mu) {
+        double* mo = a.mu + ((size_t)cell * a.nadj + lane) * a.np;
+#pragma unroll
+        for (int p = 0; p < 32; ++p) if (p < a.np) mo[p] = o[p];
+      }
+    }
+    if (lane == 0) {
+      const int A = (int)(r1 - r0);
+      int* is_ = a.istatus + (size_t)cell * 20;
+      is_[Nstp] += A;
+      is_[Njac] += (1 + S) * A;
+      is_[Ndec] += (1 + S) * A;
+      is_[Nsol] += S * a.nadj * A;
+      a.ierr[cell] = 1;
+    }
+  }
+  tmem::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem::dealloc512(tmem_base_s);
 }
 
 }  // namespace fatode
