@@ -1781,12 +1781,21 @@ static int sdirk_tlm_group(const SdirkParams& sp, const Cbm4Const& mc, const std
       g_stats.ms_forward_tape += tm.stop();
       g_stats.launches++; g_stats.launches_expand++;
       SdirkTlmArgs aa{nb, d_off, d_cell, g_sd_fat.as<double>(), d_ytlm, g_ctr.as<unsigned long long>(), ntlm};
-      auto ck = dense ? k_sdirk_tlm_cell_dense : k_sdirk_tlm_cell;
-      const size_t csm = dense ? SDIRK_TLM_DENSE_SMEM : SDIRK_TLM_SMEM;
-      CUDA_TRY(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
-      const unsigned ablocks = (unsigned)std::min<int>(nb, (dense ? 2 : 3) * sms);   // 71.6 KB (dense: 85 KB) of shared memory per warp
+      // static path: tensor-memory variant (one CTA of four sweep warps per SM; FATODE_SDIRK_TLM_SMEM=1 selects the shared-memory
+      // variant with three one-warp CTAs per SM); general-pivoting pass: shared-memory variant with dense factors
+      static const bool use_tm = !(getenv("FATODE_SDIRK_TLM_SMEM") && atoi(getenv("FATODE_SDIRK_TLM_SMEM")) != 0);
       tm.start();
-      ck<<<ablocks, 32, csm, st>>>(sp, aa);
+      if (!dense && use_tm) {
+        CUDA_TRY(cudaFuncSetAttribute(k_sdirk_tlm_cell_tm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDIRK_TLM_TM_SMEM));
+        const unsigned ablocks = (unsigned)std::min<int>((nb + ST_TM_WARPS - 1) / ST_TM_WARPS, sms);
+        k_sdirk_tlm_cell_tm<<<ablocks, ST_TM_WARPS * 32, SDIRK_TLM_TM_SMEM, st>>>(sp, aa);
+      } else {
+        auto ck = dense ? k_sdirk_tlm_cell_dense : k_sdirk_tlm_cell;
+        const size_t csm = dense ? SDIRK_TLM_DENSE_SMEM : SDIRK_TLM_SMEM;
+        CUDA_TRY(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+        const unsigned ablocks = (unsigned)std::min<int>(nb, (dense ? 2 : 3) * sms);   // 71.6 KB (dense: 85 KB) of shared memory per warp
+        ck<<<ablocks, 32, csm, st>>>(sp, aa);
+      }
       CUDA_TRY(cudaGetLastError());
       g_stats.ms_adjoint += tm.stop();
       g_stats.launches++; g_stats.launches_adjoint++;

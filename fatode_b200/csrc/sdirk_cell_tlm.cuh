@@ -16,6 +16,7 @@
 #pragma once
 #include "sdirk_cell_fwd.cuh"
 #include "rk_cell_adj.cuh"
+#include "tmem.cuh"
 
 namespace fatode {
 
@@ -189,6 +190,125 @@ k_sdirk_tlm_cell(SdirkParams sp, SdirkTlmArgs a) {
       for (int i = 0; i < N; ++i) ycol[i] = YT[i * SV];
     }
   }
+}
+
+
+// ---- tensor-memory variant of the column sweep (the shipped one for the static-pattern path): the lane's seven vectors
+// (Y_tlm, Z_tlm_1..5, G = 224 doubles) live in the lane's 256 doubles of tensor memory, shared memory only stages the records
+// (14.3 KB per warp), one CTA of four sweep warps per SM.  Same operations in the same order as k_sdirk_tlm_cell.
+constexpr uint32_t ST_TM_Y = 0, ST_TM_G = 64, ST_TM_Z = 128;          // 32-bit columns; Z_tlm_s at ST_TM_Z + 64 s
+constexpr int ST_TM_WARPS = 4;
+constexpr size_t SDIRK_TLM_TM_SMEM = sizeof(double) * (size_t)ST_TM_WARPS * ST_REC;
+
+__global__ void __launch_bounds__(ST_TM_WARPS * 32, 1)
+k_sdirk_tlm_cell_tm(SdirkParams sp, SdirkTlmArgs a) {
+  extern __shared__ __align__(16) double cell_smem[];
+  __shared__ uint32_t tmem_base_s;
+  constexpr int N = 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* const rec = cell_smem + (size_t)warp * ST_REC;
+  if (warp == 0) tmem::alloc512(&tmem_base_s);
+  tmem::fence_before_sync();
+  __syncthreads();
+  tmem::fence_after_sync();
+  const uint32_t tm = tmem_base_s + ((uint32_t)(warp * 32) << 16);
+  const bool active = lane < a.ntlm;
+  const int S = sp.S;
+  for (;;) {
+    unsigned long long slot = 0;
+    if (lane == 0) slot = atomicAdd(a.queue, 1ull);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot >= (unsigned long long)a.ncells) break;
+    const long long r0 = a.rec_off[slot], r1 = a.rec_off[slot + 1];
+    const int cell = a.cell[slot];
+    double* const ycol = a.y_tlm + ((size_t)cell * a.ntlm + (active ? lane : 0)) * N;
+    double x[32], o[32];
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = ycol[i];
+    tmem::st32(tm + ST_TM_Y, x);
+    tmem::wait_st();
+    for (long long q = r0; q < r1; ++q) {
+      __syncwarp();
+      {
+        const double2* src = reinterpret_cast<const double2*>(a.fat + (size_t)q * ST_REC);
+        double2* dst = reinterpret_cast<double2*>(rec);
+        for (int e = lane; e < ST_REC / 2; e += 32) dst[e] = __ldg(src + e);
+      }
+      __syncwarp();
+      const double H = rec[ST_HDR + 1];
+      const unsigned hw = (unsigned)rec[ST_HDR + 2];
+      const unsigned swaps = hw >> 24;
+      const double hg = H * sp.Gamma;
+      const double hgi = 1.0 / (H * sp.Gamma);
+#pragma unroll 1
+      for (int s = 0; s < S; ++s) {
+        const double* Jv = rec + ST_J + s * 276;
+        const int iters = (int)((hw >> (4 * s)) & 15u);
+        // G = (H gamma) J_i Y_tlm + sum_j theta_ij Z_tlm_j   (:706-716)
+        tmem::ld32(tm + ST_TM_Y, x);
+        cbm4_cell::j_vec_seq(Jv, x, o);
+#pragma unroll
+        for (int i = 0; i < N; ++i) { o[i] = hg * o[i]; x[i] = 0.0; }
+        for (int j = 0; j < s; ++j) {
+          const double th = sp.Theta[s][j];
+          double t[16];
+          tmem::ld16(tm + ST_TM_Z + 64 * j, t);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = o[i] + th * t[i];
+          tmem::ld16(tm + ST_TM_Z + 64 * j + 32, t);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[16 + i] = o[16 + i] + th * t[i];
+        }
+        tmem::st32(tm + ST_TM_G, o);
+        tmem::wait_st();
+        // fixed number of modified-Newton iterations on Z_tlm (x), :724-775
+#pragma unroll 1
+        for (int it = 0; it < iters; ++it) {
+          asm volatile("" ::: "memory");
+          cbm4_cell::j_vec_seq(Jv, x, o);
+          {
+            double t[16];
+            tmem::ld16(tm + ST_TM_G, t);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = hgi * ((hg * o[i] + t[i]) - x[i]);
+            tmem::ld16(tm + ST_TM_G + 32, t);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[16 + i] = hgi * ((hg * o[16 + i] + t[i]) - x[16 + i]);
+          }
+          asm volatile("" ::: "memory");
+          cbm4_cell::lun_solve_seq(rec + ST_LU, rec + ST_DINV, swaps, o);
+#pragma unroll
+          for (int i = 0; i < N; ++i) x[i] = x[i] + o[i];
+        }
+        tmem::st32(tm + ST_TM_Z + 64 * s, x);
+        tmem::wait_st();
+      }
+      // Y_tlm += sum_i d_i Z_tlm_i   (:851-862)
+      tmem::ld32(tm + ST_TM_Y, x);
+      for (int s = 0; s < S; ++s) {
+        const double d = sp.D[s];
+        if (d != 0.0) {
+          double t[16];
+          tmem::ld16(tm + ST_TM_Z + 64 * s, t);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] = x[i] + d * t[i];
+          tmem::ld16(tm + ST_TM_Z + 64 * s + 32, t);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[16 + i] = x[16 + i] + d * t[i];
+        }
+      }
+      tmem::st32(tm + ST_TM_Y, x);
+      tmem::wait_st();
+    }
+    tmem::ld32(tm + ST_TM_Y, x);
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) ycol[i] = x[i];
+    }
+  }
+  tmem::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem::dealloc512(tmem_base_s);
 }
 
 }  // namespace fatode
