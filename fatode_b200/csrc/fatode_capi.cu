@@ -1494,12 +1494,21 @@ static int rk_adj_group(const RkParams& rp, const Cbm4Const& mc, const std::vect
       g_stats.launches++; g_stats.launches_expand++;
     }
     RkAdjArgs aa{nb, d_off, d_cell, g_rk_fat.as<double>(), d_lam, d_mu, d_ist, g_ctr.as<unsigned long long>(), nadj, with_mu ? 1 : 0, np};
-    auto ck = dense ? k_rk_adj_cell_dense : k_rk_adj_cell;
-    const size_t csm = dense ? RK_ADJ_DENSE_SMEM : RK_ADJ_SMEM;
-    CUDA_TRY(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
-    const unsigned ablocks = (unsigned)std::min<int>(nb, (dense ? 1 : 2) * sms);
+    // static path: tensor-memory variant (one CTA of four sweep warps per SM; FATODE_RK_ADJ_SMEM=1 selects the shared-memory variant
+    // with two one-warp CTAs per SM); general-pivoting pass: shared-memory variant with dense factors, one warp per SM
+    static const bool use_tm = !(getenv("FATODE_RK_ADJ_SMEM") && atoi(getenv("FATODE_RK_ADJ_SMEM")) != 0);
     tm.start();
-    ck<<<ablocks, 32, csm, st>>>(rp, aa);
+    if (!dense && use_tm) {
+      CUDA_TRY(cudaFuncSetAttribute(k_rk_adj_cell_tm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RK_ADJ_TM_SMEM));
+      const unsigned ablocks = (unsigned)std::min<int>((nb + RA_TM_WARPS - 1) / RA_TM_WARPS, sms);
+      k_rk_adj_cell_tm<<<ablocks, RA_TM_WARPS * 32, RK_ADJ_TM_SMEM, st>>>(rp, aa);
+    } else {
+      auto ck = dense ? k_rk_adj_cell_dense : k_rk_adj_cell;
+      const size_t csm = dense ? RK_ADJ_DENSE_SMEM : RK_ADJ_SMEM;
+      CUDA_TRY(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+      const unsigned ablocks = (unsigned)std::min<int>(nb, (dense ? 1 : 2) * sms);
+      ck<<<ablocks, 32, csm, st>>>(rp, aa);
+    }
     CUDA_TRY(cudaGetLastError());
     g_stats.ms_adjoint += tm.stop();
     g_stats.launches++; g_stats.launches_adjoint++;

@@ -24,6 +24,7 @@
 #pragma once
 #include "rk_cell_fwd.cuh"
 #include "ros_cell_adj.cuh"
+#include "tmem.cuh"
 
 namespace fatode {
 
@@ -261,6 +262,214 @@ k_rk_adj_cell(RkParams rp, RkAdjArgs a) {
       is_[Nsol] += (int)nsol;
     }
   }
+}
+
+
+// ---- tensor-memory variant of the backward sweep (the shipped one for the static-pattern path): Lambda, Mu, U1..3 and G1..3
+// (8 x 32 = 256 doubles, exactly a lane's share of tensor memory) live in tensor memory, the right-hand sides R1..3 and the
+// staged record in shared memory (41 KB per warp): one CTA of four sweep warps per SM instead of two one-warp CTAs.
+// Same floating-point operations in the same order as k_rk_adj_cell (sums accumulated term by term): Lambda stays bit-identical.
+constexpr uint32_t RA_TM_LAM = 0, RA_TM_MU = 64, RA_TM_U = 128, RA_TM_G = 320;   // 32-bit columns; U_s / G_s at +64 s
+constexpr int RA_TM_WARPS = 4;
+constexpr int RA_TM_WARP_DOUBLES = RA_REC + 3 * 32 * 32;
+constexpr size_t RK_ADJ_TM_SMEM = sizeof(double) * (size_t)RA_TM_WARPS * RA_TM_WARP_DOUBLES;
+
+__global__ void __launch_bounds__(RA_TM_WARPS * 32, 1)
+k_rk_adj_cell_tm(RkParams rp, RkAdjArgs a) {
+  extern __shared__ __align__(16) double cell_smem[];
+  __shared__ uint32_t tmem_base_s;
+  constexpr int N = 32, SV = 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* const rec = cell_smem + (size_t)warp * RA_TM_WARP_DOUBLES;
+  double* const pv = rec + RA_REC + lane;
+  double* const R1 = pv;
+  double* const R2 = pv + 1 * N * SV;
+  double* const R3 = pv + 2 * N * SV;
+  double* const Rs[3] = {R1, R2, R3};
+  if (warp == 0) tmem::alloc512(&tmem_base_s);
+  tmem::fence_before_sync();
+  __syncthreads();
+  tmem::fence_after_sync();
+  const uint32_t tm = tmem_base_s + ((uint32_t)(warp * 32) << 16);
+  const bool active = lane < a.nadj;
+  for (;;) {
+    unsigned long long slot = 0;
+    if (lane == 0) slot = atomicAdd(a.queue, 1ull);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot >= (unsigned long long)a.ncells) break;
+    const long long r0 = a.rec_off[slot], r1 = a.rec_off[slot + 1];
+    const int cell = a.cell[slot];
+    double x[32], o[32];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { x[i] = (i == lane) ? 1.0 : 0.0; o[i] = 0.0; }
+    tmem::st32(tm + RA_TM_LAM, x);
+    tmem::st32(tm + RA_TM_MU, o);
+    tmem::wait_st();
+    long nsol = 0;
+    for (long long q = r1 - 1; q >= r0; --q) {
+      __syncwarp();
+      {
+        const double2* src = reinterpret_cast<const double2*>(a.fat + (size_t)q * RA_REC);
+        double2* dst = reinterpret_cast<double2*>(rec);
+        for (int e = lane; e < RA_REC / 2; e += 32) dst[e] = __ldg(src + e);
+      }
+      __syncwarp();
+      const double H = rec[RA_HDR + 1];
+      const unsigned hw = (unsigned)rec[RA_HDR + 2];
+      const int NewIt = (int)(hw & 0xffu);
+      const unsigned swaps = (hw >> 8) & 0xffu, zswaps = hw >> 16;
+      const unsigned zmask = (unsigned)rec[RA_HDR + 3];
+      const double rH = 1.0 / H;
+      const int sweeps = min(rp.newton_maxit, max(NewIt + 1, 6) + 1);
+      nsol += 2L * sweeps * a.nadj;
+      // G_s = -H b_s J_s^T Lambda, U_s = 0   (:1337-1347)
+      tmem::ld32(tm + RA_TM_LAM, x);
+#pragma unroll 1
+      for (int s = 0; s < 3; ++s) {
+        cbm4_cell::jt_vec_seq(rec + RA_J + s * 276, x, o);
+        const double c = -H * rp.B[s + 1];
+#pragma unroll
+        for (int i = 0; i < N; ++i) o[i] = c * o[i];
+        tmem::st32(tm + RA_TM_G + 64 * s, o);
+#pragma unroll
+        for (int i = 0; i < N; ++i) o[i] = 0.0;
+        tmem::st32(tm + RA_TM_U + 64 * s, o);
+      }
+      tmem::wait_st();
+#pragma unroll 1
+      for (int it = 0; it < sweeps; ++it) {
+        // RK_PrepareRHS_Adj: R_s = G_s + (U_s + J_s^T (-H sum_j a_js U_j))
+#pragma unroll 1
+        for (int s = 0; s < 3; ++s) {
+          const double c1 = -H * rp.A[1][s + 1], c2 = -H * rp.A[2][s + 1], c3 = -H * rp.A[3][s + 1];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            double t[16];
+            tmem::ld16(tm + RA_TM_U + 32 * h, t);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[16 * h + i] = c1 * t[i];
+            tmem::ld16(tm + RA_TM_U + 64 + 32 * h, t);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[16 * h + i] = x[16 * h + i] + c2 * t[i];
+            tmem::ld16(tm + RA_TM_U + 128 + 32 * h, t);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[16 * h + i] = x[16 * h + i] + c3 * t[i];
+          }
+          cbm4_cell::jt_vec_seq(rec + RA_J + s * 276, x, o);
+          double* R = Rs[s];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            double g[16], u[16];
+            tmem::ld16(tm + RA_TM_G + 64 * s + 32 * h, g);
+            tmem::ld16(tm + RA_TM_U + 64 * s + 32 * h, u);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) R[(16 * h + i) * SV] = g[i] + (u[i] + o[16 * h + i]);
+          }
+        }
+        // RK_SolveTR
+#pragma unroll 4
+        for (int i = 0; i < N; ++i) {
+          const double x1 = cbm4_cell::exact_div(R1[i * SV], H, rH), x2 = cbm4_cell::exact_div(R2[i * SV], H, rH),
+                       x3 = cbm4_cell::exact_div(R3[i * SV], H, rH);
+          R1[i * SV] = rp.AinvT[0][0] * x1 + rp.AinvT[1][0] * x2 + rp.AinvT[2][0] * x3;
+          R2[i * SV] = rp.AinvT[0][1] * x1 + rp.AinvT[1][1] * x2 + rp.AinvT[2][1] * x3;
+          R3[i * SV] = rp.AinvT[0][2] * x1 + rp.AinvT[1][2] * x2 + rp.AinvT[2][2] * x3;
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = R1[i * SV];
+        cbm4_cell::lut_solve_seq(rec + RA_LU, rec + RA_DINV, swaps, x);
+#pragma unroll
+        for (int i = 0; i < N; ++i) { R1[i * SV] = x[i]; x[i] = R2[i * SV]; o[i] = -R3[i * SV]; }
+        cbm4_cell::zlut_solve_seq(rec + RA_ZR, rec + RA_ZI, rec + RA_ZRATIO, rec + RA_ZDIV, rec + RA_ZRDIV, zmask, zswaps, x, o);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          double u1[16], u2[16], u3[16];
+          tmem::ld16(tm + RA_TM_U + 32 * h, u1);
+          tmem::ld16(tm + RA_TM_U + 64 + 32 * h, u2);
+          tmem::ld16(tm + RA_TM_U + 128 + 32 * h, u3);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int e = 16 * h + i;
+            const double x1 = R1[e * SV], x2 = x[e], x3 = -o[e];
+            const double d1 = rp.Tinv[0][0] * x1 + rp.Tinv[1][0] * x2 + rp.Tinv[2][0] * x3;
+            const double d2 = rp.Tinv[0][1] * x1 + rp.Tinv[1][1] * x2 + rp.Tinv[2][1] * x3;
+            const double d3 = rp.Tinv[0][2] * x1 + rp.Tinv[1][2] * x2 + rp.Tinv[2][2] * x3;
+            u1[i] -= d1; u2[i] -= d2; u3[i] -= d3;
+          }
+          tmem::st16(tm + RA_TM_U + 32 * h, u1);
+          tmem::st16(tm + RA_TM_U + 64 + 32 * h, u2);
+          tmem::st16(tm + RA_TM_U + 128 + 32 * h, u3);
+        }
+        tmem::wait_st();
+      }
+      // Mu += sum_s JACP_s^T (H sum_j a_js U_j + H b_s Lambda)   (:1424-1464)
+      if (a.with_mu) {
+        tmem::ld32(tm + RA_TM_MU, o);
+#pragma unroll 1
+        for (int s = 0; s < 3; ++s) {
+          const double c1 = H * rp.A[1][s + 1], c2 = H * rp.A[2][s + 1], c3 = H * rp.A[3][s + 1], cb = H * rp.B[s + 1];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            double t[16];
+            tmem::ld16(tm + RA_TM_U + 32 * h, t);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[16 * h + i] = c1 * t[i];
+            tmem::ld16(tm + RA_TM_U + 64 + 32 * h, t);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[16 * h + i] = x[16 * h + i] + c2 * t[i];
+            tmem::ld16(tm + RA_TM_U + 128 + 32 * h, t);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[16 * h + i] = x[16 * h + i] + c3 * t[i];
+            tmem::ld16(tm + RA_TM_LAM + 32 * h, t);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[16 * h + i] = x[16 * h + i] + cb * t[i];
+          }
+          const double* AP = rec + RA_P + s * 32;
+          Cbm4Warp::stoich_cols(x, [&](auto pc, double sp) {
+            constexpr int p = decltype(pc)::value;
+            o[p] = fma(AP[p], sp, o[p]);
+          });
+        }
+        tmem::st32(tm + RA_TM_MU, o);
+      }
+      tmem::ld32(tm + RA_TM_LAM, x);
+#pragma unroll 1
+      for (int s = 0; s < 3; ++s) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          double t[16];
+          tmem::ld16(tm + RA_TM_U + 64 * s + 32 * h, t);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[16 * h + i] = x[16 * h + i] + t[i];
+        }
+      }
+      tmem::st32(tm + RA_TM_LAM, x);
+      tmem::wait_st();
+    }
+    tmem::ld32(tm + RA_TM_LAM, x);
+    tmem::ld32(tm + RA_TM_MU, o);
+    if (active) {
+      double* lo = a.lambda + ((size_t)cell * a.nadj + lane) * N;
+#pragma unroll
+      for (int i = 0; i < N; ++i) lo[i] = x[i];
+      if (a.with_mu) {
+        double* mo = a.mu + ((size_t)cell * a.nadj + lane) * a.np;
+#pragma unroll
+        for (int p = 0; p < 32; ++p) if (p < a.np) mo[p] = o[p];
+      }
+    }
+    if (lane == 0) {   // backward counters (:1290-1299, 1511, RK_Decomp, RK_SolveTR)
+      const int A = (int)(r1 - r0);
+      int* is_ = a.istatus + (size_t)cell * 20;
+      is_[Njac] += 4 * A;
+      is_[Ndec] += A;
+      is_[Nstp] += A;
+      is_[Nsol] += (int)nsol;
+    }
+  }
+  tmem::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem::dealloc512(tmem_base_s);
 }
 
 }  // namespace fatode
