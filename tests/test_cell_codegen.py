@@ -42,5 +42,9 @@ def test_generated_header_is_current():
         pytest.skip("reference tree not present")
     path = os.path.join(ROOT, "fatode_b200", "csrc", "gen", "cbm4_cell_gen.h")
     before = open(path).read()
+    st = os.stat(path)
     subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_cbm4_cell.py")], check=True, capture_output=True)
-    assert open(path).read() == before
+    same = open(path).read() == before
+    if same:
+        os.utime(path, (st.st_atime, st.st_mtime))   # identical content: keep the time stamp so that the library is not rebuilt
+    assert same
