@@ -1053,6 +1053,10 @@ static int ros_tlm_device(const RosParams& rp, const typename Warp::Const& mc, i
     CUDA_TRY(cudaStreamSynchronize(st));
     for (int c : general) h[c] = -20;
     CUDA_TRY(cudaMemcpyAsync(d_ierr, h.data(), sizeof(int) * ncells, cudaMemcpyHostToDevice, st));
+    // not an error of the call (rc stays 0), but worth a message: fatode_last_error() reports it
+    g_err = std::to_string(general.size()) + " of " + std::to_string((long long)ncells) +
+            " systems left the static pivot pattern of the per-thread kernels and were handed back with IERR -20 (Y, Y_tlm untouched): "
+            "ROS_TLM has no general-pivoting pass yet; tighten RTOL (none are handed back at RTOL <= 1e-5 for the CBM-IV driver problem)";
   }
   CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
