@@ -52,9 +52,10 @@ k_sdirk_tlm_prep(SdirkParams sp, Cbm4Const mc, SdirkTlmPrepArgs a) {
   double PH[Cbm4Cell::NPH];
   const int S = sp.S, P = S + 1;
   const long nwork = a.nrec * P;
+  // items 0 .. nrec-1 are the factorisations, the rest the stage Jacobians: the lanes of a warp do the same kind of work
   for (long w = (long)blockIdx.x * SV + threadIdx.x; w < nwork; w += (long)gridDim.x * SV) {
-    const long q = w / P;
-    const int part = (int)(w - q * P);
+    const long q = (w < a.nrec) ? w : (w - a.nrec) / S;
+    const int part = (w < a.nrec) ? S : (int)((w - a.nrec) - q * S);
     int lo = 0, hi = a.ncells;
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
