@@ -19,3 +19,17 @@ r = F.integrate_sdirk("cbm4", T0, T1, y, rtol, atol); print("sdirk", (r.ierr == 
 ys = perturbed_states(F.initial_state("small_strato"), 70)
 r = F.integrate("small_strato", T0, T0 + 86400.0, ys, np.full(5, 1e-4), np.full(5, 1e-2)); print("strato", (r.ierr == 1).all())
 r = F.integrate_sdirk("roberts", 0.0, 40.0, np.array([[1.0, 0, 0]] * 5), np.full(3, 1e-4), np.full(3, 1e-8)); print("roberts sdirk", (r.ierr == 1).all())
+icr = np.zeros(20, dtype=np.int32); icr[2] = 1
+r = F.integrate_rk("cbm4", T0, T1, y, rtol, atol, icntrl_u=icr); print("rk", (r.ierr == 1).all(), F.last_stats().cells_general)
+r = F.integrate_adj("cbm4", T0, T1, y[:12], 32, rtol, atol, icntrl_u=icr, family="rk"); print("rk_adj", (r.ierr == 1).all(), F.last_stats().cells_general)
+r = F.integrate_adj("cbm4", T0, T1, y[:12], 32, rtol, atol, family="sdirk"); print("sdirk_adj", (r.ierr == 1).all(), F.last_stats().cells_general)
+r = F.integrate_tlm("cbm4", T0, T1, y[:12], np.tile(np.eye(32), (12, 1, 1)), rtol, atol, family="sdirk"); print("sdirk_tlm", (r.ierr == 1).all())
+loose_r, loose_a = np.full(32, F01 * 1e-2), np.full(32, F01 * 1e-4)      # general-pivoting passes
+r = F.integrate_adj("cbm4", T0, T1, y[:12], 8, loose_r, loose_a, family="sdirk"); print("sdirk_adj general pass", (r.ierr == 1).all(), F.last_stats().cells_general)
+r = F.integrate_adj("cbm4", T0, T1, y[:12], 8, loose_r, loose_a, icntrl_u=icr, family="rk"); print("rk_adj general pass", (r.ierr == 1).all(), F.last_stats().cells_general)
+from fatode_b200.inputs import swe_members
+DT = float(np.float32(2.1573758800627289e-003)); tol = np.full(4800, 1e-3)
+m = swe_members(9)
+r = F.integrate_erk("swe", 0.0, 10 * DT, m, tol, tol); print("swe erk", (r.ierr == 1).all(), r.istatus[:, 2].mean())
+v = np.zeros((9, 1, 4800)); v[:, 0, 0] = 1.0
+r = F.integrate_erk("swe", 0.0, 5 * DT, m, tol, tol, var_tlm=v); print("swe erk_tlm", (r.ierr == 1).all())
