@@ -275,9 +275,6 @@ def integrate_tlm(model, tin, tout, y, y_tlm, rtol, atol, icntrl_u=None, rcntrl_
     entry = lib().fatode_sdirk_integrate_tlm_batch if family == "sdirk" else lib().fatode_ros_integrate_tlm_batch
     _check(entry(mid, nc, n, ntlm, _ptr(yy), _ptr(yt), float(tin), float(tout), _ptr(at), _ptr(rt),
                  _ptr(atol), _ptr(rtol), _ptr(ic), _ptr(rc), _ptr(ist), _ptr(rst), _ptr(ierr), _ptr(mp), MEM_HOST, None))
-    if (ierr == -20).any():      # ROS_TLM hand-back (no general-pivoting pass for that family yet): say so, loudly
-        import warnings
-        warnings.warn(lib().fatode_last_error().decode(), RuntimeWarning, stacklevel=2)
     return Result(yy, ist, rst, ierr, y_tlm=yt)
 
 

@@ -38,6 +38,7 @@
 #include "rk_cell_adj.cuh"
 #include "sdirk_dense_sens.cuh"
 #include "rk_dense_adj.cuh"
+#include "units_internal.h"
 
 using namespace fatode;
 
@@ -1035,28 +1036,40 @@ static int ros_device_small(const RosParams& rp, const typename Cell::Const& mc,
   return 0;
 }
 
-// INTEGRATE_TLM (forward error control): state sweep + tangent-linear sweep on the per-thread path.  There is no general
-// TLM kernel yet: a cell the static-pattern LU cannot take keeps IERR = FATODE_IERR_TLM_IRREGULAR (-20) and its Y / Y_tlm
-// untouched (never observed for the shipped inputs).
+// INTEGRATE_TLM.  Forward error control (ICNTRL(12) = 0): state sweep + tangent-linear sweep on the per-thread path; systems the
+// static-pattern LU cannot take are integrated by the lock-step kernel (general partial pivoting, ros_tlm_lock.cu).  TLM
+// truncation-error control (ICNTRL(12) /= 0, the preset of INTEGRATE_TLM): every system goes through the lock-step kernel.
 template <class Cell, class Warp>
-static int ros_tlm_device(const RosParams& rp, const typename Warp::Const& mc, int64_t ncells, int ntlm, double* d_y, double* d_ytlm,
-                          const double* d_atol, const double* d_rtol, int* d_istatus, double* d_rstatus, int* d_ierr,
-                          cudaStream_t st) {
+static int ros_tlm_device(const RosParams& rp, const typename Warp::Const& mc, int64_t ncells, int ntlm, bool trunc, double* d_y,
+                          double* d_ytlm, const double* d_atol, const double* d_rtol, const double* d_atol_tlm,
+                          const double* d_rtol_tlm, int* d_istatus, double* d_rstatus, int* d_ierr, cudaStream_t st) {
   std::memset(&g_stats, 0, sizeof g_stats);
+  UnitTiming ut;
+  std::string uerr;
+  if (trunc || g_path == 1) {
+    if (int e = ros_tlm_lock_device(rp, mc, ncells, nullptr, ntlm, trunc, d_y, d_ytlm, d_atol, d_rtol, d_atol_tlm, d_rtol_tlm, d_istatus,
+                                    d_rstatus, d_ierr, st, ut, uerr)) return fail(e, uerr);
+    g_stats.ms_forward += ut.ms;
+    g_stats.launches += ut.launches;
+    g_stats.launches_forward += 1;
+    g_stats.waves = 1;
+    g_stats.cells_general = ncells;
+    return 0;
+  }
   std::vector<int> general;
   if (int e = ros_device_fast<Cell, Warp>(rp, mc, ncells, ntlm, false, true, d_y, d_ytlm, nullptr, d_atol, d_rtol, d_istatus,
                                           d_rstatus, d_ierr, st, general, /*tlm_sweep=*/true)) return e;
   g_stats.cells_general = (int64_t)general.size();
-  if (!general.empty()) {
-    std::vector<int> h(ncells);
-    CUDA_TRY(cudaMemcpyAsync(h.data(), d_ierr, sizeof(int) * ncells, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    for (int c : general) h[c] = -20;
-    CUDA_TRY(cudaMemcpyAsync(d_ierr, h.data(), sizeof(int) * ncells, cudaMemcpyHostToDevice, st));
-    // not an error of the call (rc stays 0), but worth a message: fatode_last_error() reports it
-    g_err = std::to_string(general.size()) + " of " + std::to_string((long long)ncells) +
-            " systems left the static pivot pattern of the per-thread kernels and were handed back with IERR -20 (Y, Y_tlm untouched): "
-            "ROS_TLM has no general-pivoting pass yet; tighten RTOL (none are handed back at RTOL <= 1e-5 for the CBM-IV driver problem)";
+  if (!general.empty()) {   // these systems kept Y / Y_tlm untouched: integrate them in lock-step with general pivoting
+    std::sort(general.begin(), general.end());
+    DevBuf b_ids;
+    CUDA_TRY(b_ids.alloc(sizeof(int) * general.size()));
+    CUDA_TRY(cudaMemcpyAsync(b_ids.p, general.data(), sizeof(int) * general.size(), cudaMemcpyHostToDevice, st));
+    if (int e = ros_tlm_lock_device(rp, mc, (long)general.size(), b_ids.as<int>(), ntlm, false, d_y, d_ytlm, d_atol, d_rtol, nullptr,
+                                    nullptr, d_istatus, d_rstatus, d_ierr, st, ut, uerr)) return fail(e, uerr);
+    g_stats.ms_forward += ut.ms;
+    g_stats.launches += ut.launches;
+    g_stats.launches_forward += 1;
   }
   CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
@@ -1151,7 +1164,8 @@ static int broadcast_ierr(int64_t ncells, int code, int* istatus, double* rstatu
 static int ros_batch_impl(int family, int model, int64_t ncells, int nvar, int np, int nadj, double* y, double* lambda,
                           double* mu, double tin, double tout, const double* atol, const double* rtol, const int* icntrl_u,
                           const double* rcntrl_u, int* istatus, double* rstatus, int* ierr, double* mu_sum,
-                          const double* model_params, int mem, void* stream) {
+                          const double* model_params, int mem, void* stream, const double* atol_tlm = nullptr,
+                          const double* rtol_tlm = nullptr) {
   g_err.clear();
   if (ncells < 0 || !y || !atol || !rtol || !istatus || !rstatus || !ierr) return fail(FATODE_EINVAL, "NULL required argument");
   if (int e = check_model_dims(model, nvar, np)) return e;
@@ -1174,9 +1188,9 @@ static int ros_batch_impl(int family, int model, int64_t ncells, int nvar, int n
   }
   const bool do_tlm = (family == FAM_TLM);
   if (do_tlm) {
-    if (perr == 1 && ic[11] != 0)
-      return fail(FATODE_EUNSUPPORTED, "ROS_TLM with TLM truncation-error control (ICNTRL(12) != 0, the preset when ICNTRL_U is "
-                                       "absent) is not built yet: pass ICNTRL_U with ICNTRL_U(12) = 0");
+    if (perr == 1 && ic[11] != 0 && (!atol_tlm || !rtol_tlm))
+      return fail(FATODE_EINVAL, "ROS_TLM with TLM truncation-error control (ICNTRL(12) /= 0, the preset of INTEGRATE_TLM) needs "
+                                 "ATOL_TLM and RTOL_TLM");
     if (nadj > 32) return fail(FATODE_EUNSUPPORTED, "ntlm > 32 per call is not supported yet");
     if (model != FATODE_MODEL_CBM4) return fail(FATODE_EUNSUPPORTED, "INTEGRATE_TLM is available for the cbm4 model only in this build");
   }
@@ -1221,9 +1235,19 @@ static int ros_batch_impl(int family, int model, int64_t ncells, int nvar, int n
     }
   }
   int rc;
-  if (do_tlm)
-    rc = ros_tlm_device<Cbm4Cell, Cbm4Warp>(rp, mc, ncells, nadj, d_y, d_lam, b_atol.as<double>(), b_rtol.as<double>(), d_ist, d_rst,
-                                            d_ierr, st);
+  if (do_tlm) {
+    const bool trunc = ic[11] != 0;
+    DevBuf b_atl, b_rtl;          // ATOL_tlm / RTOL_tlm (N, NTLM), shared by the batch like ATOL / RTOL
+    if (trunc) {
+      const size_t nb = sizeof(double) * (size_t)nvar * nadj;
+      CUDA_TRY(b_atl.alloc(nb));
+      CUDA_TRY(b_rtl.alloc(nb));
+      CUDA_TRY(cudaMemcpyAsync(b_atl.p, atol_tlm, nb, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(b_rtl.p, rtol_tlm, nb, cudaMemcpyHostToDevice, st));
+    }
+    rc = ros_tlm_device<Cbm4Cell, Cbm4Warp>(rp, mc, ncells, nadj, trunc, d_y, d_lam, b_atol.as<double>(), b_rtol.as<double>(),
+                                            b_atl.as<double>(), b_rtl.as<double>(), d_ist, d_rst, d_ierr, st);
+  }
   else if (model == FATODE_MODEL_CBM4)
     rc = ros_device<Cbm4Cell, Cbm4Warp>(rp, mc, ncells, nadj, with_mu, do_adjoint, d_y, d_lam, d_mu, b_atol.as<double>(),
                                         b_rtol.as<double>(), d_ist, d_rst, d_ierr, d_musum, st);
@@ -1270,9 +1294,9 @@ extern "C" int fatode_ros_integrate_tlm_batch(int model, int64_t ncells, int nva
                                               double tout, const double* atol_tlm, const double* rtol_tlm, const double* atol,
                                               const double* rtol, const int* icntrl_u, const double* rcntrl_u, int* istatus,
                                               double* rstatus, int* ierr, const double* model_params, int mem, void* stream) {
-  (void)atol_tlm; (void)rtol_tlm;   // used by the reference only when ICNTRL(12) != 0 (TLM truncation-error control)
+  // ATOL_tlm / RTOL_tlm are read only when ICNTRL(12) /= 0 (TLM truncation-error control, the preset)
   return ros_batch_impl(FAM_TLM, model, ncells, nvar, 0, ntlm, y, y_tlm, nullptr, tin, tout, atol, rtol, icntrl_u, rcntrl_u,
-                        istatus, rstatus, ierr, nullptr, model_params, mem, stream);
+                        istatus, rstatus, ierr, nullptr, model_params, mem, stream, atol_tlm, rtol_tlm);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,0 +1,32 @@
+// Host-side declarations shared by the translation units of libfatode_b200.so (not part of the C ABI).
+// Each family added after round 1 lives in its own .cu (compiled in parallel by fatode_b200/build.py); fatode_capi.cu keeps the
+// C entry points, argument checks and host<->device staging and calls the unit's device-level driver declared here.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include "fatode_common.cuh"
+#include "model_cbm4.cuh"
+
+namespace fatode {
+
+// CUDA call guard for the units: the message goes to `err`, the return value is the C ABI's error code
+#define UNIT_TRY(x)                                                                                           \
+  do {                                                                                                        \
+    cudaError_t e_ = (x);                                                                                     \
+    if (e_ != cudaSuccess) {                                                                                  \
+      err = std::string(#x) + ": " + cudaGetErrorString(e_);                                                  \
+      return (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? -102 /*FATODE_ENODEVICE*/ : -103 /*FATODE_ECUDA*/; \
+    }                                                                                                         \
+  } while (0)
+
+struct UnitTiming { double ms = 0.0; long launches = 0; };
+
+// ros_tlm_lock.cu — ros_TLM_Int (TLM/ROS_TLM/ROS_TLM_f90_Integrator.F90:462-707) with state and columns in lock-step and
+// general partial pivoting.  ids == nullptr: cells 0..ncells-1; otherwise the listed cells (device array).
+// trunc: TLM truncation-error control (ICNTRL(12) != 0), d_atol_tlm / d_rtol_tlm [ntlm][32] device arrays then required.
+int ros_tlm_lock_device(const RosParams& rp, const Cbm4Const& mc, long ncells, const int* d_ids, int ntlm, bool trunc,
+                        double* d_y, double* d_ytlm, const double* d_atol, const double* d_rtol, const double* d_atol_tlm,
+                        const double* d_rtol_tlm, int* d_istatus, double* d_rstatus, int* d_ierr, cudaStream_t st,
+                        UnitTiming& tm, std::string& err);
+
+}  // namespace fatode

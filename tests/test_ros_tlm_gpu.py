@@ -88,34 +88,71 @@ def test_tlm_is_the_transpose_of_the_discrete_adjoint_when_autonomous():
     assert err.max() < 1e-9, err.max()
 
 
-def test_tlm_truncation_error_control_is_reported_unsupported():
-    import fatode_b200 as F
-    rtol, atol = tols()
-    y0 = F.initial_state("cbm4")
-    with pytest.raises(F.FatodeError):                     # ICNTRL_U absent -> preset ICNTRL(12) = 1
-        F.integrate_tlm("cbm4", T0, T0 + 3600.0, y0, np.eye(32)[None], rtol, atol)
-    ic = np.zeros(20, dtype=np.int32)
-    ic[2] = 9                                              # unknown method: the reference's IERR -2 for every cell
-    r = F.integrate_tlm("cbm4", T0, T0 + 3600.0, y0, np.eye(32)[None], rtol, atol, icntrl_u=ic)
-    assert r.ierr[0] == -2 and np.array_equal(r.y[0], y0)
-
-
-def test_tlm_hand_back_at_loose_tolerances_is_reported():
-    """Known gap: ROS_TLM has no general-pivoting pass, so systems whose factorisations leave the static pivot
-    pattern (almost all at rtol 1e-3) come back with IERR -20 and untouched Y / Y_tlm — reported through fatode_last_error() and
-    a Python warning; the other systems of the batch are unaffected and still match the oracle."""
+def test_tlm_default_call_runs_with_truncation_error_control():
+    """INTEGRATE_TLM with ICNTRL_U absent presets ICNTRL(12) = 1 (TLM/ROS_TLM/ROS_TLM_f90_Integrator.F90:70-72): the columns'
+    error norms (ros_ErrorNorm_tlm :745-769) enter accept/reject, so state and columns advance in lock-step; the lock-step kernel
+    follows the reference's operation order, so Y_tlm is compared bit for bit too."""
     import fatode_b200 as F
     from fatode_b200.inputs import perturbed_states
-    rtol, atol = np.full(32, F01 * 1.0e-2), np.full(32, F01 * 1.0e-4)
+    rtol, atol = tols()
+    y0 = perturbed_states(F.initial_state("cbm4"), 12)
+    yt = np.tile(np.eye(32)[:6], (12, 1, 1))
+    at = np.full((6, 32), 1.0e-6)
+    rt = np.full((6, 32), 1.0e-4)
+    t1 = T0 + 24 * 3600.0
+    res = F.integrate_tlm("cbm4", T0, t1, y0, yt, rtol, atol, atol_tlm=at, rtol_tlm=rt)      # the reference's default call
+    ref = O.ros_tlm("cbm4", y0, yt, T0, t1, atol, rtol, None, atol_tlm=at, rtol_tlm=rt)
+    assert (res.ierr == 1).all()
+    check(res, ref)
+    assert np.array_equal(res.y_tlm, ref["y_tlm"])
+    # the columns really decide: with forward-only control the step counts differ
+    ic = np.zeros(20, dtype=np.int32)
+    ic[1], ic[2] = 1, 5
+    fwd = F.integrate_tlm("cbm4", T0, t1, y0, yt, rtol, atol, icntrl_u=ic)
+    assert (res.istatus[:, 2] > fwd.istatus[:, 2]).any()
+    with pytest.raises(F.FatodeError):                     # the preset needs the column tolerances
+        F.integrate_tlm("cbm4", T0, t1, y0, yt, rtol, atol)
+    ic = np.zeros(20, dtype=np.int32)
+    ic[2] = 9                                              # unknown method: the reference's IERR -2 for every cell
+    r = F.integrate_tlm("cbm4", T0, T0 + 3600.0, y0[:1], np.eye(32)[None], rtol, atol, icntrl_u=ic)
+    assert r.ierr[0] == -2 and np.array_equal(r.y[0], y0[0])
+
+
+def test_tlm_truncation_error_control_methods_and_tolerance_kinds():
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    rtol, atol = tols()
+    y0 = perturbed_states(F.initial_state("cbm4"), 6)
+    rng = np.random.default_rng(11)
+    yt = rng.standard_normal((6, 32, 32))                  # NTLM = 32: every lane carries a column
+    at = 1.0e-6 * (1.0 + rng.random((32, 32)))
+    rt = 1.0e-4 * (1.0 + rng.random((32, 32)))
+    t1 = T0 + 6 * 3600.0
+    for method, auto, scalar in ((1, 0, 0), (2, 0, 0), (3, 0, 1), (4, 1, 0), (5, 1, 1), (5, 0, 0)):
+        ic = np.zeros(20, dtype=np.int32)
+        ic[0], ic[1], ic[2], ic[11] = auto, scalar, method, 1
+        res = F.integrate_tlm("cbm4", T0, t1, y0, yt, rtol, atol, icntrl_u=ic, atol_tlm=at, rtol_tlm=rt)
+        ref = O.ros_tlm("cbm4", y0, yt, T0, t1, atol, rtol, ic, atol_tlm=at, rtol_tlm=rt)
+        check(res, ref)
+        assert np.array_equal(res.y_tlm, ref["y_tlm"]), (method, auto, scalar)
+
+
+def test_tlm_general_pivoting_pass_at_loose_tolerances():
+    """Systems whose factorisations leave the static pivot pattern of the per-thread kernels (almost all at rtol 1e-3) are
+    integrated by the lock-step kernel with netlib's partial pivoting: no IERR -20 hand-backs any more."""
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
     y0 = perturbed_states(F.initial_state("cbm4"), 24)
     yt = np.tile(np.eye(32)[:4], (24, 1, 1))
     ic = np.zeros(20, dtype=np.int32)
     ic[2] = 5
     t1 = T0 + 24 * 3600.0
-    with pytest.warns(RuntimeWarning, match="handed back"):
+    general = 0
+    for rt_ in (1.0e-2, 1.0e-3):
+        rtol, atol = np.full(32, F01 * rt_), np.full(32, F01 * rt_ * 1.0e-2)
         res = F.integrate_tlm("cbm4", T0, t1, y0, yt, rtol, atol, icntrl_u=ic)
-    back = res.ierr == -20
-    assert back.any() and np.array_equal(res.y[back], y0[back]) and np.array_equal(res.y_tlm[back], yt[back])
-    if (~back).any():
-        ref = O.ros_tlm("cbm4", y0[~back], yt[~back], T0, t1, atol, rtol, ic)
-        assert np.array_equal(res.y[~back], ref["y"]) and np.array_equal(res.istatus[~back], ref["istatus"])
+        ref = O.ros_tlm("cbm4", y0, yt, T0, t1, atol, rtol, ic)
+        assert not (res.ierr == -20).any()
+        check(res, ref)
+        general += F.last_stats().cells_general
+    assert general > 0

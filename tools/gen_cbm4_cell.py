@@ -712,9 +712,43 @@ def main():
             w(f"    x[{i}] = fma(-lu[{idx[(i, k)]}], bk, x[{i}]);")
         w("  }")
     w("}")
+    # ------------------------------------------------------------------ reference-order variants (ROS_TLM lock-step kernel)
+    w("// ---- reference-order operators of the lock-step Rosenbrock tangent-linear kernel (ICNTRL(12) = 1: the columns' error")
+    w("// norms decide accept/reject, so their arithmetic follows ros_TLM_Int operation by operation, no fma):")
+    w("// tmp = (dJ/dt) x as matmul's column sweep restricted to the NJT time-dependent entries (LSS_Mul_Jac2, :620), then the")
+    w("// DAXPY out = out + hg * tmp on the rows that have such entries (the others would add hg * 0)")
+    w("CBM4_CELL_INL void dj_vec_seq(const double* __restrict__ Dj, const double hg, const double (&x)[32], double (&out)[32]) {")
+    for r, ents in sorted(byrow.items()):
+        w("  { double a = 0.0;")
+        for (n, c) in sorted(ents, key=lambda nc: nc[1]):
+            w(f"    a = a + Dj[{n}] * x[{c}];")
+        w(f"    out[{r}] = out[{r}] + hg * a; }}")
+    w("}")
+    w("// out = Hess_Vec(U1, x) = (f_yy x U1) . x: the term list of CBM4_HessTR_Vec (:1869-2023) contracted the other way, terms")
+    w("// of output k in the order of that routine (by HTU row, then textual order) — the order the CPU restatement uses")
+    w("CBM4_CELL_INL void hess_vec_seq(const double* __restrict__ U1, const double (&x)[32], double (&out)[32]) {")
+    hv = {}
+    for a in body("CBM4_HessTR_Vec"):
+        r = a.lhs.idx[0] - 1
+
+        def hterms(e):
+            if isinstance(e, fx.Bin) and e.op == "+":
+                return hterms(e.a) + [e.b]
+            if isinstance(e, fx.Num):
+                return []
+            return [e]
+        for t in hterms(a.rhs):
+            hv.setdefault(t.b.a.idx[0] - 1, []).append((t.a.idx[0] - 1, r, t.b.b.idx[0] - 1))
+    for k in range(N):
+        e = None
+        for (h, r, c) in hv.get(k, []):
+            t = f"CBM4_CELL_HESS({h}) * (U1[{r}] * x[{c}])"
+            e = t if e is None else f"({e} + {t})"
+        w(f"  out[{k}] = {e if e else '0.0'};")
+    w("}")
     w("}  // namespace cbm4_cell")
 
-    outdir = os.path.join(HERE, "..", "fatode_b200", "csrc", "gen")
+    outdir =os.path.join(HERE, "..", "fatode_b200", "csrc", "gen")
     open(os.path.join(outdir, "cbm4_cell_gen.h"), "w").write("\n".join(o) + "\n")
     nl = sum(1 for (i, c) in idx if c < i)
     print(f"NLU={NLU} (L {nl}, U {NLU - nl - N}) updates={nupd} lines={len(o)}")
