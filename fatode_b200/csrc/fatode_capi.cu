@@ -27,6 +27,7 @@
 #include "ros_warp_adj.cuh"
 #include "ros_warp_adj2.cuh"
 #include "ros_cell_fwd.cuh"
+#include "ros_cell_fwd_tm.cuh"
 #include "ros_cell_adj.cuh"
 #include "model_small_cell.cuh"
 #include "sdirk_cell_fwd.cuh"
@@ -667,8 +668,10 @@ struct StreamSet {
   cudaStream_t sF = nullptr, sX = nullptr, sA = nullptr;
   cudaEvent_t comp_free[2] = {nullptr, nullptr}, fat_free[2] = {nullptr, nullptr}, expand_done[2] = {nullptr, nullptr};
   cudaEvent_t join = nullptr, doneF = nullptr, doneX = nullptr, doneA = nullptr, tables_ready = nullptr;
+  void destroy();
   cudaError_t init() {
-    if (sF) return cudaSuccess;
+    if (sF && tables_ready) return cudaSuccess;
+    destroy();   // a half-built set (an earlier init failed) starts over
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&sF, cudaStreamNonBlocking)) != cudaSuccess) return e;
     if ((e = cudaStreamCreateWithFlags(&sX, cudaStreamNonBlocking)) != cudaSuccess) return e;
@@ -679,7 +682,19 @@ struct StreamSet {
       if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return e;
     return cudaSuccess;
   }
+  // streams and events belong to the device they were created on: released with the workspace (fatode_release_workspace,
+  // and check_device() when the host thread moves to another GPU), re-created by the next init()
+  void destroy_impl() {
+    cudaEvent_t* all[] = {&comp_free[0], &comp_free[1], &fat_free[0], &fat_free[1], &expand_done[0], &expand_done[1],
+                          &join, &doneF, &doneX, &doneA, &tables_ready};
+    for (cudaEvent_t* ev : all)
+      if (*ev) { cudaEventDestroy(*ev); *ev = nullptr; }
+    cudaStream_t* str[] = {&sF, &sX, &sA};
+    for (cudaStream_t* q : str)
+      if (*q) { cudaStreamDestroy(*q); *q = nullptr; }
+  }
 };
+inline void StreamSet::destroy() { destroy_impl(); }
 static thread_local StreamSet g_ss;
 static thread_local CachedBuf g_comp[2], g_fat[2], g_cprev[2], g_cowner[2], g_cseq[2], g_wids[2], g_wnacc2[2], g_wlast2[2],
     g_border[2], g_bfatoff[2], g_wbatch[2], g_cnext[2], g_wfirst[2], g_ctr;
@@ -691,9 +706,31 @@ static void release_pipeline_workspace() {
     g_wbatch[i].release(); g_cnext[i].release(); g_wfirst[i].release();
   }
   g_ctr.release();
+  g_ss.destroy();
 }
 
 struct TimedLaunch { cudaEvent_t a, b; int phase; };
+// the timing events of one call; whatever is still in the list when the call leaves (error exits included) is destroyed
+struct TimedList : std::vector<TimedLaunch> {
+  ~TimedList() {
+    for (TimedLaunch& t : *this) {
+      if (t.a) cudaEventDestroy(t.a);
+      if (t.b) cudaEventDestroy(t.b);
+    }
+  }
+};
+// error exits of the pipeline: the caller's stream still waits for the side streams, so nothing of this call is in flight
+// on them when the next call (or the caller's next kernel) starts
+struct StreamJoin {
+  cudaStream_t st, s[3];
+  cudaEvent_t ev[3];
+  bool armed = true;
+  ~StreamJoin() {
+    if (!armed) return;
+    for (int i = 0; i < 3; ++i)
+      if (s[i] && s[i] != st && cudaEventRecord(ev[i], s[i]) == cudaSuccess) cudaStreamWaitEvent(st, ev[i], 0);
+  }
+};
 
 template <class Cell, class Warp>
 static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, int64_t ncells, int nadj, bool with_mu,
@@ -709,18 +746,31 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
   CUDA_TRY(g_ctr.ensure(16 * sizeof(unsigned long long)));
   unsigned long long* d_ctr = g_ctr.as<unsigned long long>();   // [0,1] forward queues, [2,3] pool heads, [4,5] backward queues
   CellTape tape{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0u, nullptr};
+  // forward kernel: the tensor-memory variant (two warps = 58 cells per SM) unless FATODE_FWD_TM=0 (A/B runs) selects the
+  // shared-memory one (one warp = 32 cells per SM); identical bits
+  static const bool fwd_tm = !(getenv("FATODE_FWD_TM") && atoi(getenv("FATODE_FWD_TM")) == 0);
   if (!do_adjoint) {
     constexpr int LANES = CELL_LANES_SOLO;
     const size_t cell_smem = CellSmem<Cell, LANES>::BYTES;
     CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd_cell<Cell, 0, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cell_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd_cell_tm<Cell, 0, FWD_TM_LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)CellSmemTM<Cell, FWD_TM_LANES>::BYTES));
     CUDA_TRY(g_wnacc.ensure(sizeof(int) * ncells));
     CUDA_TRY(cudaMemsetAsync(d_ctr, 0, 16 * sizeof(unsigned long long), st));
     PhaseTimer tm(st);
     tm.start();
-    const unsigned blocks = (unsigned)std::min<int64_t>((ncells + LANES - 1) / LANES, (int64_t)sms);
-    k_ros_fwd_cell<Cell, 0, LANES><<<blocks, 32, cell_smem, st>>>(rp, mc, ncells, nullptr, d_y, d_y, d_atol, d_rtol, d_istatus,
-                                                                  d_rstatus, d_ierr, g_wnacc.as<int>(), tape, 0,
-                                                                  g_debug_irregular_every, d_ctr);
+    if (fwd_tm) {
+      constexpr int PER_CTA = FWD_TM_LANES * FWD_TM_WARPS;
+      const unsigned blocks = (unsigned)std::min<int64_t>((ncells + PER_CTA - 1) / PER_CTA, (int64_t)sms);
+      k_ros_fwd_cell_tm<Cell, 0, FWD_TM_LANES><<<blocks, 32 * FWD_TM_WARPS, CellSmemTM<Cell, FWD_TM_LANES>::BYTES, st>>>(
+          rp, mc, ncells, nullptr, d_y, d_y, d_atol, d_rtol, d_istatus, d_rstatus, d_ierr, g_wnacc.as<int>(), tape, 0,
+          g_debug_irregular_every, d_ctr);
+    } else {
+      const unsigned blocks = (unsigned)std::min<int64_t>((ncells + LANES - 1) / LANES, (int64_t)sms);
+      k_ros_fwd_cell<Cell, 0, LANES><<<blocks, 32, cell_smem, st>>>(rp, mc, ncells, nullptr, d_y, d_y, d_atol, d_rtol, d_istatus,
+                                                                    d_rstatus, d_ierr, g_wnacc.as<int>(), tape, 0,
+                                                                    g_debug_irregular_every, d_ctr);
+    }
     CUDA_TRY(cudaGetLastError());
     g_stats.ms_forward += tm.stop();
     g_stats.launches++;
@@ -743,7 +793,8 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
   // kept as an option (fatode_set_pipeline) rather than the default.
   const int pmode = getenv("FATODE_PIPELINE") ? atoi(getenv("FATODE_PIPELINE")) : g_pipeline;
   const int nbuf = pmode > 0 ? 2 : 1;
-  const int LANES = pmode > 0 ? CELL_LANES_SHARED : CELL_LANES_SOLO;
+  const bool use_tm = fwd_tm && pmode <= 0;
+  const int LANES = pmode > 0 ? CELL_LANES_SHARED : (use_tm ? FWD_TM_LANES * FWD_TM_WARPS : CELL_LANES_SOLO);   // cells per SM
   const int S = rp.S;
   const size_t cell_smem = pmode > 0 ? CellSmem<Cell, CELL_LANES_SHARED>::BYTES : CellSmem<Cell, CELL_LANES_SOLO>::BYTES;
   const size_t adj_smem = sizeof(double) * ((size_t)ADJ3_WARP_DOUBLES * ADJ3_WARPS + (size_t)ADJ3_PRIV_DOUBLES * (ADJ3_WARPS - 4));
@@ -751,6 +802,8 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
                                 (int)CellSmem<Cell, CELL_LANES_SHARED>::BYTES));
   CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd_cell<Cell, 1, CELL_LANES_SOLO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)CellSmem<Cell, CELL_LANES_SOLO>::BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd_cell_tm<Cell, 1, FWD_TM_LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)CellSmemTM<Cell, FWD_TM_LANES>::BYTES));
   CUDA_TRY(cudaFuncSetAttribute(k_ros_adj_cell<Warp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem));
   CUDA_TRY(cudaFuncSetAttribute(k_ros_tlm_cell<Warp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem));
   CUDA_TRY(g_ss.init());
@@ -778,8 +831,10 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
     free_b += g_comp[0].cap + g_comp[1].cap + g_fat[0].cap + g_fat[1].cap;
     budget = (size_t)(0.6 * (double)free_b);
   }
-  const size_t comp_bytes = budget ? (size_t)((nbuf == 2 ? 0.14 : 0.22) * (double)budget) : g_comp[0].cap;
-  const size_t fat_bytes = budget ? (size_t)((nbuf == 2 ? 0.36 : 0.78) * (double)budget) : g_fat[0].cap;
+  // (the tensor-memory forward kernel holds 58 cells per SM: a wave of 148 x 58 cells wants a larger pool)
+  const double comp_frac = nbuf == 2 ? 0.14 : (use_tm ? 0.36 : 0.22);
+  const size_t comp_bytes = budget ? (size_t)(comp_frac * (double)budget) : g_comp[0].cap;
+  const size_t fat_bytes = budget ? (size_t)((nbuf == 2 ? 0.36 : 1.0 - comp_frac) * (double)budget) : g_fat[0].cap;
   const unsigned pool_chunks = (unsigned)std::min<size_t>(comp_bytes / chunk_bytes, 0x7fffffffu);
   const long long fat_steps_cap = (long long)(fat_bytes / fat_step_bytes);
   if (pool_chunks < 1 || fat_steps_cap < 1) return fail(FATODE_ENOMEM, "tape budget smaller than one chunk of the trajectory tape");
@@ -812,7 +867,8 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
   CUDA_TRY(cudaStreamWaitEvent(ss.sX, ss.join, 0));
   CUDA_TRY(cudaStreamWaitEvent(ss.sA, ss.join, 0));
 
-  std::vector<TimedLaunch> timed;
+  TimedList timed;
+  StreamJoin join_guard{st, {ss.sF, ss.sX, ss.sA}, {ss.doneF, ss.doneX, ss.doneA}};
   auto t_begin = [&](cudaStream_t s, int phase) -> int {
     TimedLaunch t{nullptr, nullptr, phase};
     CUDA_TRY(cudaEventCreate(&t.a));
@@ -828,7 +884,19 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
   std::vector<long long> h_fatoff;
   std::vector<int> h_batch;
   for (int64_t c = 0; c < ncells; ++c) pending[c] = (int)c;
-  double chunks_per_cell = 0.0;   // running estimate (0 = unknown)
+  // running estimate of the tape chunks a cell needs (0 = unknown: the first wave is then a small probing one — if the pool
+  // ran dry every cell still integrating would be deferred together).  A wave costs the same time whether its lanes are all
+  // busy or not, so the estimate of the previous call is reused when the call describes the same problem.
+  struct TapeHint { double tstart, tend, rtol0, atol0, hstart; int method, family; double chunks_per_cell; };
+  static thread_local TapeHint hint = {0, 0, 0, 0, 0, -1, -1, 0.0};
+  double h_tol[2] = {0.0, 0.0};
+  CUDA_TRY(cudaMemcpyAsync(&h_tol[0], d_rtol, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(&h_tol[1], d_atol, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const bool hint_ok = hint.chunks_per_cell > 0.0 && hint.tstart == rp.tstart && hint.tend == rp.tend && hint.rtol0 == h_tol[0] &&
+                       hint.atol0 == h_tol[1] && hint.hstart == rp.hstart && hint.method == rp.S * 100 + (int)(rp.ELO * 10) &&
+                       hint.family == rp.family;
+  double chunks_per_cell = hint_ok ? hint.chunks_per_cell * 1.05 : 0.0, measured_cpc = 0.0;
   size_t pos = 0;
   int k = 0, g = 0;
   bool comp_used[2] = {false, false}, fat_used[2] = {false, false};
@@ -869,7 +937,11 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
     tape.last_chunk = g_wlast2[p].as<int>();
     if (int e = t_begin(ss.sF, 0)) return e;
     const unsigned fblocks = (unsigned)std::min<int64_t>((n + LANES - 1) / LANES, (int64_t)sms);
-    if (pmode > 0)
+    if (use_tm)
+      k_ros_fwd_cell_tm<Cell, 1, FWD_TM_LANES><<<fblocks, 32 * FWD_TM_WARPS, CellSmemTM<Cell, FWD_TM_LANES>::BYTES, ss.sF>>>(
+          rp, mc, n, g_wids[p].as<int>(), d_y, d_y, d_atol, d_rtol, d_istatus, d_rstatus, d_ierr, g_wnacc2[p].as<int>(), tape,
+          with_mu ? 1 : 0, g_debug_irregular_every, d_ctr + p);
+    else if (pmode > 0)
       k_ros_fwd_cell<Cell, 1, CELL_LANES_SHARED><<<fblocks, 32, cell_smem, ss.sF>>>(
           rp, mc, n, g_wids[p].as<int>(), d_y, d_y, d_atol, d_rtol, d_istatus, d_rstatus, d_ierr, g_wnacc2[p].as<int>(), tape,
           with_mu ? 1 : 0, g_debug_irregular_every, d_ctr + p);
@@ -907,7 +979,8 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
       chunks_per_cell = std::max(2.0 * chunks_per_cell, (double)pool_chunks / std::max<int64_t>(1, n / 2));
     }
     if (n_ok > 0) {
-      chunks_per_cell = std::max(chunks_per_cell, ((double)steps / (double)n_ok) / FT_CHUNK + 0.5);
+      measured_cpc = std::max(measured_cpc, ((double)steps / (double)n_ok) / FT_CHUNK + 0.5);
+      chunks_per_cell = std::max(chunks_per_cell, measured_cpc);
       g_stats.accepted_steps += steps;
       g_stats.tape_bytes_peak = std::max<uint64_t>(g_stats.tape_bytes_peak, (uint64_t)chunks_used * chunk_bytes + (uint64_t)std::min<long long>(steps, fat_steps_cap) * fat_step_bytes);
       std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h_nacc[a] > h_nacc[b]; });   // longest first
@@ -945,7 +1018,8 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
         const int64_t nb = (int64_t)(bt.o1 - bt.o0);
         if (fat_used[f]) CUDA_TRY(cudaStreamWaitEvent(ss.sX, ss.fat_free[f], 0));
         if (int e = t_begin(ss.sX, 1)) return e;
-        k_expand_tape<Cell><<<chunks_used, FT_CHUNK * S, 0, ss.sX>>>(
+        if (chunks_used > 0)   // no accepted step in the whole wave (TIN == TOUT): nothing to expand, Lambda = ADJINIT
+          k_expand_tape<Cell><<<chunks_used, FT_CHUNK * S, 0, ss.sX>>>(
             rp, mc, chunks_used, g_cowner[p].as<int>(), g_cseq[p].as<int>(), g_wids[p].as<int>(), d_ierr, g_wnacc2[p].as<int>(),
             g_wlast2[p].as<int>(), g_comp[p].as<double>(), g_fat[f].as<double>(), g_bfatoff[p].as<long long>(),
             g_wbatch[p].as<int>(), (int)bi, tlm_sweep ? 2 : (with_mu ? 1 : 0));
@@ -983,6 +1057,8 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
     comp_used[p] = true;
     ++k;
   }
+  if (measured_cpc > 0.0 && !rc_fail)
+    hint = TapeHint{rp.tstart, rp.tend, h_tol[0], h_tol[1], rp.hstart, rp.S * 100 + (int)(rp.ELO * 10), rp.family, measured_cpc};
   // join: the caller's stream continues after all three side streams
   CUDA_TRY(cudaEventRecord(ss.doneF, ss.sF));
   CUDA_TRY(cudaEventRecord(ss.doneX, ss.sX));
@@ -990,6 +1066,7 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
   CUDA_TRY(cudaStreamWaitEvent(st, ss.doneF, 0));
   CUDA_TRY(cudaStreamWaitEvent(st, ss.doneX, 0));
   CUDA_TRY(cudaStreamWaitEvent(st, ss.doneA, 0));
+  join_guard.armed = false;
   CUDA_TRY(cudaStreamSynchronize(st));
   for (TimedLaunch& t : timed) {   // device time per phase (the phases overlap; their sum exceeds the elapsed time)
     float ms = 0.f;
@@ -997,8 +1074,6 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
       if (t.phase == 0) g_stats.ms_forward += ms; else if (t.phase == 1) g_stats.ms_forward_tape += ms; else g_stats.ms_adjoint += ms;
       if (dbg) fprintf(stderr, "[timing] phase %d %.2f ms\n", t.phase, ms);
     }
-    cudaEventDestroy(t.a);
-    if (t.b) cudaEventDestroy(t.b);
   }
   return rc_fail;
 }

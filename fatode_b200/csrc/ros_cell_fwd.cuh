@@ -95,6 +95,10 @@ struct Cbm4Cell {
   }
   template <int SV>
   __device__ static void lu_solve(const double* lu, unsigned swaps, double* b) { cbm4_cell::lu_solve<SV>(lu, swaps, b); }
+  template <int SV>   // the same solve with the right-hand side in registers (k_ros_fwd_cell_tm)
+  __device__ __forceinline__ static void lu_solve_reg(const double* lu, const double* dinv, unsigned swaps, double (&b)[32]) {
+    cbm4_cell::lu_solve_reg<SV>(lu, dinv, swaps, b);
+  }
   // complex matrix -J + (a + i b) I of the implicit Runge-Kutta families in two planes (FWD/RK/LS_Solver.F90:22-32)
   template <int SV>
   __device__ static void build_EZ(const double* y, const double* PH, const Const& mc, double a, double b, double* zr, double* zi) {

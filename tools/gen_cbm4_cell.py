@@ -746,9 +746,40 @@ def main():
             e = t if e is None else f"({e} + {t})"
         w(f"  out[{k}] = {e if e else '0.0'};")
     w("}")
+    # ------------------------------------------------------------------ forward sweep with the right-hand side in registers
+    w("// DGETRS('N') with the right-hand side in REGISTERS and the thread's own factors in its strided slots (lu[e * SV],")
+    w("// dinv[k * SV] = RN(1/U(k,k)) as lu_factor leaves it): same operations in the same order as lu_solve, the quotient by")
+    w("// U(k,k) through exact_div (the correctly rounded quotient in three operations instead of a division sequence)")
+    w("// exact_div with a guard: outside the range where Markstein's correction is proven (tiny, huge or non-finite quotients)")
+    w("// the true division is used")
+    w("CBM4_CELL_INL double exact_div_safe(const double a, const double b, const double rb) {")
+    w("  const double q = a * rb;")
+    w("  const double aq = fabs(q);")
+    w("  if (aq != 0.0 && !(aq > 1.0e-280 && aq < 1.0e280)) return a / b;")
+    w("  return fma(fma(-q, b, a), rb, q);")
+    w("}")
+    w("template <int SV> CBM4_CELL_INL void lu_solve_reg(const double* __restrict__ lu, const double* __restrict__ dinv, "
+      "const unsigned swaps, double (&b)[32]) {")
+    for bi, (k, p_) in enumerate(SWAPS):
+        w(f"  if (swaps & {1 << bi}u) {{ const double t = b[{k}]; b[{k}] = b[{p_}]; b[{p_}] = t; }}")
+    for k in range(N - 1):
+        rows = [i for i in range(k + 1, N) if P[i][k]]
+        if not rows:
+            continue
+        w(f"  {{ const double bk = b[{k}];")
+        for i in rows:
+            w(f"    b[{i}] = b[{i}] - bk * lu[{idx[(i, k)]} * SV];")
+        w("  }")
+    for k in range(N - 1, -1, -1):
+        rows = [i for i in range(k) if P[i][k]]
+        w(f"  {{ const double bk = exact_div_safe(b[{k}], lu[{idx[(k, k)]} * SV], dinv[{k} * SV]); b[{k}] = bk;")
+        for i in rows:
+            w(f"    b[{i}] = b[{i}] - bk * lu[{idx[(i, k)]} * SV];")
+        w("  }")
+    w("}")
     w("}  // namespace cbm4_cell")
 
-    outdir =os.path.join(HERE, "..", "fatode_b200", "csrc", "gen")
+    outdir = os.path.join(HERE, "..", "fatode_b200", "csrc", "gen")
     open(os.path.join(outdir, "cbm4_cell_gen.h"), "w").write("\n".join(o) + "\n")
     nl = sum(1 for (i, c) in idx if c < i)
     print(f"NLU={NLU} (L {nl}, U {NLU - nl - N}) updates={nupd} lines={len(o)}")
