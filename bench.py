@@ -7,18 +7,23 @@ Rodas4 sweep 12h -> 84h with trajectory tape, ADJINIT, discrete adjoint sweep fo
 functionals and NP = 29 rate-coefficient parameters (the reference driver's problem,
 EXAMPLES/cbm4/CBM4_ROS_ADJ/cbm4_ros_adj_dr.F90:167-292), on synthetic per-cell initial states.
 
-A "step" is one pass of the hot path over one batch of `--cells` cells per GPU (default 2^17: the >= 1 M-cell
-workload of BASELINE.json is processed in waves of ~4.7 k cells whatever the batch size, so throughput does not depend
-on it; `--cells 1048576` runs the full-size batch in ~80 s per step).
+A "step" is one pass of the hot path over one batch of cells per GPU: one C-ABI call.  Default batch: 2^18 cells when the
+whole run (warm-up + timed steps + the e2e pass) fits ten minutes, else 2^17 (default_cells(); the >= 1 M-cell workload of
+BASELINE.json is processed in waves of ~8.3 k cells whatever the batch size, so throughput does not depend on it;
+`--cells 1048576` runs the full-size batch in about a minute per step; `--scaling strong` splits a fixed 2^20 cells over N GPUs).
   value : cells/s with y0 and all outputs resident in HBM (device pointers through the C ABI)
   e2e   : cells/s through the same C-ABI call with pinned HOST buffers (H2D of y0, D2H of y, Lambda,
           Mu, ISTATUS, RSTATUS, IERR inside the timed region)
-  roofline    : dominant kernel (k_ros_adj_cell, the backward sweep): algorithmic FP64 flops of
-                SURVEY.md §8d evaluated on the returned counters / its CUDA-event time, against the
-                DFMA peak measured on this GPU in this run (MEASURED_PEAKS.json has no FP64 figure)
+  roofline    : dominant kernel (k_ros_adj_cell, the backward sweep): ALGORITHMIC FP64 flops of SURVEY.md 8d (the dense
+                FULL_ALGEBRA count, evaluated on the returned counters) / its CUDA-event time, against the DFMA peak
+                measured on this GPU in this run (MEASURED_PEAKS.json has no FP64 figure); the same for the forward
+                kernel; EXECUTED fractions (the kernels run the sparse patterns) only from an ncu capture of the very
+                library this run loads (profiles/executed_counts.json, matched by SHA-256) -- nothing is hard-coded
   cpu_baseline: the CPU oracle (C++ restatement of the reference, OpenMP over cells) on a bounded sample
-`--impl reference` times that CPU restatement alone (the reference Fortran cannot be built: no Fortran
-compiler in the image) and prints the same JSON line with "impl": "reference".
+  side        : (N = 1) one timed call each of the other BASELINE configs (small_strato FWD/ROS 2^20 cells, cbm4 RK_ADJ and
+                SDIRK_TLM, the shallow-water ensemble) with algorithmic roofline fraction and an oracle bit check
+`--impl reference` times that CPU restatement alone (the reference Fortran cannot be built: no Fortran compiler in the
+image) on every host thread and prints the same JSON line with "impl": "reference"; it loads oracle/liboracle.so only.
 Multi-GPU (torchrun, one rank per GPU): cells are sharded, no data-path collective; one NCCL
 all-reduce of the 29x32 Mu sums per step.  Time = max over ranks, barrier on both sides.
 """
@@ -120,6 +125,31 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def _load_inputs():
+    """fatode_b200/inputs.py loaded BY PATH: the reference arm and the CPU baseline must not import the product package
+    (its __init__ dlopens libfatode_b200.so)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_fatode_inputs", os.path.join(ROOT, "fatode_b200", "inputs.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def host_threads():
+    """threads the CPU arm uses: every core this process may run on (torchrun exports OMP_NUM_THREADS=1, which only changes
+    OpenMP's default; the oracle takes the count explicitly)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def oracle_initial_state(L, model=3, n=N):
+    y = np.zeros(n)
+    L.oracle_initial_state(model, y.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    return y
+
+
 def oracle_lib():
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
     L = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
@@ -149,32 +179,38 @@ def cpu_run(L, y0, nthreads):
 
 
 def cpu_baseline(sample_cells=None):
-    from fatode_b200.inputs import perturbed_states
-    import fatode_b200 as F
+    """the CPU oracle on a bounded sample of the GPU arm's own first cells (about 20-30 s of CPU work)"""
+    perturbed_states = _load_inputs().perturbed_states
     L = oracle_lib()
-    cores = L.oracle_max_threads()
-    nc = sample_cells or max(16, 12 * cores)
-    y0 = perturbed_states(F.initial_state("cbm4"), nc)
+    cores = host_threads()
+    nc = sample_cells or max(64, 48 * cores)
+    y0 = perturbed_states(oracle_initial_state(L), nc)
     dt = cpu_run(L, y0, cores)
     return {"value": nc / dt, "unit": "cells/s", "cores": cores, "kind": "port",
-            "sample": f"{nc} cells of the same workload (perturbed driver states, cells 0..{nc-1}), {dt:.1f} s wall, "
-                      f"OpenMP schedule(dynamic) over cells, C++ restatement of ADJ/ROS_ADJ (oracle/), strict IEEE"}
+            "sample": f"{nc} cells of the same workload (perturbed driver states, cells 0..{nc-1} = the first cells of the GPU "
+                      f"arm's first step), {dt:.1f} s wall, OpenMP schedule(dynamic) over cells on {cores} threads, C++ "
+                      f"restatement of ADJ/ROS_ADJ (oracle/), strict IEEE"}
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU algorithm (C++ restatement; no Fortran compiler in this image)."""
+    """--impl reference: the reference's CPU algorithm (C++ restatement; no Fortran compiler in this image) on all host
+    threads.  Loads oracle/liboracle.so only — never the product package or library."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from fatode_b200.inputs import perturbed_states
-    import fatode_b200 as F
+    perturbed_states = _load_inputs().perturbed_states
     L = oracle_lib()
-    cores = L.oracle_max_threads()
-    nc = max(8, 4 * cores)       # bounded sample per step: ~4 cells per core, ~5 s
-    base = F.initial_state("cbm4")
+    cores = host_threads()
+    nsteps = args.warmup + args.steps
+    # bounded sample per step: >= 4096 cells over the timed steps when that fits ~5 minutes of CPU time (1.1 - 1.9 cells/s
+    # per thread measured for this workload on the hosts seen so far), never fewer than 4 cells per thread
+    budget_cells = int(300.0 * 1.5 * cores / max(nsteps, 1))
+    nc = max(4 * cores, min(max(-(-4096 // max(args.steps, 1)), 4 * cores), budget_cells))
+    gpu_cells = default_cells(args)
+    base = oracle_initial_state(L)
     times = []
-    for s in range(args.warmup + args.steps):
-        y0 = perturbed_states(base, nc, first_cell=s * nc)
+    for s in range(nsteps):
+        y0 = perturbed_states(base, nc, first_cell=s * gpu_cells * args.gpus)     # the first cells of the GPU arm's step s
         dt = cpu_run(L, y0, cores)
         if s >= args.warmup:
             times.append(dt)
@@ -182,13 +218,29 @@ def run_reference_arm(args):
     v = nc * len(times) / tot
     line = {"impl": "reference", "metric": "cell-integrations/sec (fwd + adjoint), CBM-IV ROS_ADJ", "value": v, "unit": "cells/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(nc, 1, note="CPU arm: bounded sample per step"),
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(gpu_cells, args.gpus,
+                                      note=f"CPU arm: same per-cell workload; each step integrates the first {nc} cells of the "
+                                           f"GPU arm's step (a bounded sample: the full {gpu_cells * args.gpus}-cell step would "
+                                           f"take {gpu_cells * args.gpus / max(v, 1e-9) / 3600.0:.1f} h on this host)"),
             "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port",
-                             "sample": f"{nc} cells per step x {len(times)} steps, OpenMP over cells on {cores} host threads"},
+                             "sample": f"{nc} cells per step x {len(times)} timed steps, OpenMP over cells on {cores} host threads"},
             "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def default_cells(args):
+    """cells per GPU per step.  Default: 2^18 when the whole run (warm-up + timed device steps + the e2e pass) fits ten
+    minutes at the measured ~16 k cells/s, else 2^17 (the driver's 25-step runs must end inside its 870 s limit);
+    --scaling strong splits a fixed 2^20 cells over the GPUs."""
+    if args.scaling == "strong":
+        total = args.cells if args.cells > 0 else (1 << 20)
+        return max(1, total // max(args.gpus, 1))
+    if args.cells > 0:
+        return args.cells
+    calls = args.warmup + args.steps + (0 if args.no_e2e else args.steps + 1)
+    return (1 << 18) if calls * (1 << 18) / 16000.0 <= 600.0 else (1 << 17)
 
 
 def workload_config(cells, ngpus, note=None):
@@ -201,17 +253,37 @@ def workload_config(cells, ngpus, note=None):
     return c
 
 
-def run_side_workload(args):
-    """Side measurements (1 GPU, host buffers through the C ABI): BASELINE config 1 (small_strato FWD/ROS, 2^20 cells) and the
-    ROS_TLM / FWD/SDIRK / FWD/RK entry points on CBM-IV, each next to the CPU oracle on a bounded sample."""
+SIDE_DEFAULT_CELLS = {"small_strato_fwd": 1 << 20, "cbm4_ros_tlm": 32768, "cbm4_rk_adj": 9472, "cbm4_sdirk_adj": 9472,
+                      "cbm4_sdirk_tlm": 9472, "swe_erk": 65536, "swe_erk_tlm": 16384, "cbm4_rk": 18944, "cbm4_sdirk": 18944}
+
+
+def dense_flops_from_counters(ist, n, f_fun, f_jac, complex_pairs=False, sens_cols=0):
+    """ALGORITHMIC flops of a run from its returned ISTATUS counters, with the dense FULL_ALGEBRA costs the reference pays
+    (SURVEY.md section 8d): LU = 2/3 n^3 + n^2, solve = 2 n^2; an implicit Runge-Kutta 'decomposition' is a real + a complex
+    LU (4 x the real cost) and its Nsol counts real and complex solves alike (average 5 n^2); every sensitivity solve comes
+    with at least one dense Jacobian mat-vec (2 n^2)."""
+    I = ist.astype(np.float64)
+    nfun, njac, ndec, nsol = I[:, 0].sum(), I[:, 1].sum(), I[:, 5].sum(), I[:, 6].sum()
+    lu = 2.0 * n ** 3 / 3.0 + n * n
+    sol = 2.0 * n * n
+    if complex_pairs:
+        lu, sol = 5.0 * lu, 5.0 * n * n
+    f = nfun * f_fun + njac * f_jac + ndec * lu + nsol * sol
+    if sens_cols:
+        f += nsol * (sens_cols / (sens_cols + 1.0)) * 2.0 * n * n
+    return float(f)
+
+
+def side_measure(w, nc, steps, warmup, fp64_peak=None, hbm_peak=None):
+    """One side measurement (1 GPU, host buffers through the C ABI) of another BASELINE config / entry point, next to the CPU
+    oracle on a bounded sample with a bit-for-bit check of state and counters.  Returns the JSON-able line."""
     import torch  # noqa: F401  (initialises CUDA the same way the main arm does)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import fatode_b200 as F
     import oracle_lib as O
     from fatode_b200.inputs import perturbed_states
-    w = args.workload
+    flops = None
     if w == "small_strato_fwd":
-        nc = args.cells if args.cells != 131072 else (1 << 20)
         rtol, atol = np.full(5, 1.0e-1), np.full(5, 1.0)
         for _ in range(5):                      # tolerances of the driver's fifth sweep (small_strato_dr.F90:27-38)
             rtol, atol = F01 * rtol, F01 * atol
@@ -219,10 +291,12 @@ def run_side_workload(args):
         y0 = perturbed_states(F.initial_state("small_strato"), nc)
         run = lambda y: F.integrate("small_strato", t0, t1, y, rtol, atol)
         cpu = lambda y: O.ros_fwd("small_strato", y, t0, t1, atol, rtol)
-        desc = "EXAMPLES/small_strato FWD/ROS (Ros4, REAL(4) tableau), N=5, 12h..30d, rtol 1e-6 atol 1e-5 (REAL(4) 0.1 products)"
+        desc = "EXAMPLES/small_strato FWD/ROS (Ros4, REAL(4) tableau), N=5, 12h..30d, rtol 1e-6 atol 1e-5 (REAL(4) 0.1 products) (BASELINE config 2)"
         ncpu = 256
+        # FWD/ROS does not count Ndec/Nsol: one LU + S = 4 solves per attempt (Nstp), 3 new-function stages
+        flops = lambda r: float((r.istatus[:, 2].astype(np.float64) * (2 * 125 / 3.0 + 25 + 4 * 50 + 2 * 5 * 4 * 3 + 4 * 5 * 4 + 7 * 5)
+                                 + r.istatus[:, 0].astype(np.float64) * 42 + r.istatus[:, 1].astype(np.float64) * 52).sum())
     elif w == "cbm4_ros_tlm":
-        nc = args.cells if args.cells != 131072 else 32768
         rtol, atol = tolerances()
         ic = icntrl_rodas4()
         y0 = perturbed_states(F.initial_state("cbm4"), nc)
@@ -231,8 +305,8 @@ def run_side_workload(args):
         cpu = lambda y: O.ros_tlm("cbm4", y, np.broadcast_to(eye, (y.shape[0], 32, 32)).copy(), T0, T1, atol, rtol, ic)
         desc = "EXAMPLES/cbm4 TLM/ROS_TLM: Rodas4, NTLM=32, Y_tlm(t0)=I, ICNTRL(12)=0, 12h..84h, driver tolerances of ROS_ADJ"
         ncpu = 32
+        flops = lambda r: dense_flops_from_counters(r.istatus, 32, 573, 636, sens_cols=32)
     elif w == "cbm4_rk_adj":
-        nc = args.cells if args.cells != 131072 else 9472
         rtol, atol = np.full(N, F01 * 1.0e-5), np.full(N, F01 * 1.0e-7)
         ic = np.zeros(20, dtype=np.int32)
         ic[2] = 1
@@ -240,10 +314,10 @@ def run_side_workload(args):
         run = lambda y: F.integrate_adj("cbm4", T0, T1, y, 32, rtol, atol, icntrl_u=ic, family="rk")
         cpu = lambda y: O.rk_adj("cbm4", y, 32, T0, T1, atol, rtol, ic)
         desc = ("EXAMPLES/cbm4 ADJ/RK_ADJ: Radau-2A (ICNTRL(3)=1), NADJ=32, NP=29, fixed-sweep discrete adjoint, 12h..84h, "
-                "rtol 0.1f*1e-5, atol 0.1f*1e-7 (cbm4_rk_adj_dr.F90)")
+                "rtol 0.1f*1e-5, atol 0.1f*1e-7 (cbm4_rk_adj_dr.F90) (BASELINE config 4)")
         ncpu = 32
+        flops = lambda r: dense_flops_from_counters(r.istatus, 32, 573, 636, complex_pairs=True, sens_cols=32)
     elif w == "cbm4_sdirk_adj":
-        nc = args.cells if args.cells != 131072 else 9472
         rtol, atol = tolerances()
         y0 = perturbed_states(F.initial_state("cbm4"), nc)
         run = lambda y: F.integrate_adj("cbm4", T0, T1, y, 32, rtol, atol, family="sdirk")
@@ -251,8 +325,8 @@ def run_side_workload(args):
         desc = ("EXAMPLES/cbm4 ADJ/SDIRK_ADJ: Sdirk4a, NADJ=32, NP=29, direct adjoint solve (presets), 12h..84h, driver tolerances "
                 "of ROS_ADJ")
         ncpu = 32
+        flops = lambda r: dense_flops_from_counters(r.istatus, 32, 573, 636, sens_cols=32)
     elif w == "cbm4_sdirk_tlm":
-        nc = args.cells if args.cells != 131072 else 9472
         rtol, atol = tolerances()
         y0 = perturbed_states(F.initial_state("cbm4"), nc)
         eye = np.eye(32)
@@ -261,10 +335,10 @@ def run_side_workload(args):
         desc = ("EXAMPLES/cbm4 TLM/SDIRK_TLM: Sdirk4a, NTLM=32, Y_tlm(t0)=I, modified-Newton TLM (presets), 12h..84h, "
                 "driver tolerances of ROS_ADJ (BASELINE config 4)")
         ncpu = 32
+        flops = lambda r: dense_flops_from_counters(r.istatus, 32, 573, 636, sens_cols=32)
     elif w in ("swe_erk", "swe_erk_tlm"):
         from fatode_b200.inputs import swe_members
         tlm = w == "swe_erk_tlm"
-        nc = args.cells if args.cells != 131072 else (16384 if tlm else 65536)
         dt = float(np.float32(2.1573758800627289e-003))
         tol = np.full(4800, 1.0e-4)
         t1 = (5 if tlm else 50) * dt
@@ -282,8 +356,9 @@ def run_side_workload(args):
             desc = ("EXAMPLES/swe FWD/ERK: Dopri5, 40x40 grid (N=4800), t=0..50 dt, rtol=atol=1e-4, Gaussian bump a=30(1+0.1u) per "
                     "member (BASELINE config 5)")
         ncpu = 128
+        # ~0.51 Mflop per FUN (1600 grid cells x ~320 flop)
+        flops = lambda r: float(r.istatus[:, 0].astype(np.float64).sum()) * 0.51e6
     elif w == "cbm4_rk":
-        nc = args.cells if args.cells != 131072 else 18944
         rtol, atol = np.full(N, F01 * 1.0e-5), np.full(N, F01 * 1.0e-7)
         ic = np.zeros(20, dtype=np.int32)
         ic[2] = 1
@@ -292,18 +367,20 @@ def run_side_workload(args):
         cpu = lambda y: O.rk_fwd("cbm4", y, T0, T1, atol, rtol, ic)
         desc = "EXAMPLES/cbm4 FWD/RK: Radau-2A (ICNTRL(3)=1), 12h..84h, rtol 0.1f*1e-5, atol 0.1f*1e-7 (cbm4_rk_dr.F90)"
         ncpu = 256
+        flops = lambda r: dense_flops_from_counters(r.istatus, 32, 573, 636, complex_pairs=True)
     else:
-        nc = args.cells if args.cells != 131072 else 18944
         rtol, atol = np.full(N, F01 * 1.0e-5), np.full(N, F01 * 1.0e-7)
         y0 = perturbed_states(F.initial_state("cbm4"), nc)
         run = lambda y: F.integrate_sdirk("cbm4", T0, T1, y, rtol, atol)
         cpu = lambda y: O.sdirk_fwd("cbm4", y, T0, T1, atol, rtol)
         desc = "EXAMPLES/cbm4 FWD/SDIRK: Sdirk4a, 12h..84h, rtol 0.1f*1e-5, atol 0.1f*1e-7 (cbm4_sdirk_dr.F90)"
         ncpu = 128
-    for _ in range(max(args.warmup, 1)):
-        run(y0[: max(nc // 8, 64)])
+        flops = lambda r: dense_flops_from_counters(r.istatus, 32, 573, 636)
+    ncpu = min(ncpu, nc)
+    for _ in range(max(warmup, 1)):
+        run(y0[: max(nc // 8, min(64, nc))])
     times, dev_ms = [], []
-    for _ in range(args.steps):
+    for _ in range(steps):
         t = time.perf_counter()
         r = run(y0)
         times.append(time.perf_counter() - t)
@@ -311,12 +388,13 @@ def run_side_workload(args):
         dev_ms.append(st.ms_forward + st.ms_forward_tape + st.ms_adjoint)
         assert (r.ierr == 1).all()
     t = time.perf_counter()
+    cores = host_threads()
     ref = cpu(y0[:ncpu])
     tc = time.perf_counter() - t
     same = bool(np.array_equal(ref["y"], r.y[:ncpu]) and np.array_equal(ref["istatus"], r.istatus[:ncpu]))
-    cores = O.lib().oracle_max_threads()
-    line = {"metric": "cell-integrations/sec, " + w, "value": nc / (np.mean(dev_ms) * 1e-3), "unit": "cells/s", "n_gpus": 1,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(dev_ms)), "higher_is_better": True,
+    sec = float(np.mean(dev_ms)) * 1e-3
+    line = {"metric": "cell-integrations/sec, " + w, "value": nc / sec, "unit": "cells/s", "n_gpus": 1,
+            "steps": steps, "warmup": warmup, "ms_per_step": float(np.mean(dev_ms)), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "cells_per_gpu_per_step": int(nc), "note": "side measurement, not the driver's metric; "
                        "value = CUDA-event kernel time, e2e = wall clock of the C-ABI call with pageable host buffers"},
@@ -324,15 +402,59 @@ def run_side_workload(args):
             "cpu_baseline": {"value": ncpu / tc, "unit": "cells/s", "cores": cores, "kind": "port",
                              "sample": f"{ncpu} cells, {tc:.1f} s, OpenMP over cells"},
             "bitwise_equal_to_oracle_on_sample": same}
+    if flops is not None:
+        f = flops(r)
+        roof = {"bound": "fp64", "achieved": f / sec / 1e12, "unit": "TFLOP/s", "peak": fp64_peak,
+                "frac": (f / sec / 1e12 / fp64_peak) if fp64_peak else None,
+                "note": "ALGORITHMIC flops (dense FULL_ALGEBRA costs of the reference, SURVEY.md 8d) from the returned ISTATUS "
+                        "counters / summed CUDA-event kernel time; the kernels execute the sparse pattern"}
+        line["roofline"] = roof
     if w.startswith("swe_"):
-        # ~0.51 Mflop per FUN (1600 grid cells x ~320 flop) + 2 flop per component per stage-sum term
         nfun = float(r.istatus[:, 0].sum())
         line["unit"] = line["e2e"]["unit"] = line["cpu_baseline"]["unit"] = "members/s"
-        line["fun_evaluations_per_s"] = nfun / (np.mean(dev_ms) * 1e-3)
-        line["algorithmic_tflops"] = nfun * 0.51e6 / (np.mean(dev_ms) * 1e-3) / 1e12
+        line["fun_evaluations_per_s"] = nfun / sec
         line["config"]["layout"] = ("one member per CTA: Y and the stage vector in shared memory, K_1..K_S in an L2-resident per-CTA "
                                     "scratch; HBM traffic = Y in + Y out (76.8 kB per member)")
-    print(json.dumps(line), flush=True)
+        if hbm_peak:
+            line["roofline"]["hbm"] = {"achieved_GBs": nc * 76.8e3 / sec / 1e9, "peak_GBs": hbm_peak,
+                                       "note": "mandatory traffic only (Y in + Y out): the stage vectors stay in L2"}
+    return line
+
+
+def run_side_workload(args):
+    import fatode_b200 as F
+    nc = args.cells if args.cells > 0 else SIDE_DEFAULT_CELLS[args.workload]
+    peak = F.measure_fp64_peak(20000)
+    print(json.dumps(side_measure(args.workload, nc, args.steps, args.warmup, peak, measured_hbm_peak())), flush=True)
+
+
+def executed_counts():
+    """profiles/executed_counts.json: executed FP64 work per unit from an ncu capture (tools/ncu_executed.py), valid only for
+    the build it names -- compared by the SHA-256 of the library this process uses."""
+    import hashlib
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "executed_counts.json")))
+        h = hashlib.sha256(open(os.path.join(ROOT, "fatode_b200", "lib", "libfatode_b200.so"), "rb").read()).hexdigest()
+        if d.get("library_sha256") != h:
+            return None
+        d["source"] = f"profiles/executed_counts.json (ncu capture {d.get('capture', '?')} of library sha256 {h[:16]})"
+        return d
+    except Exception:
+        return None
+
+
+def measured_hbm_peak():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        for k in ("hbm_gbs_burst", "hbm_GBs", "hbm_gbs", "hbm_copy_gbs"):
+            if k in d:
+                return float(d[k])
+        for k, v in d.items():
+            if "hbm" in k.lower() and isinstance(v, (int, float)):
+                return float(v)
+    except Exception:
+        pass
+    return None
 
 
 def main():
@@ -340,11 +462,15 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--cells", type=int, default=131072, help="cells per GPU per step")
+    ap.add_argument("--cells", type=int, default=0,
+                    help="cells per GPU per step (weak scaling) or in total (--scaling strong); 0 = default, see default_cells()")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --cells per GPU (default); strong: a fixed total (default 2^20) split over the GPUs")
     ap.add_argument("--impl", default="fatode_b200", choices=["fatode_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="cbm4_ros_adj", choices=["cbm4_ros_adj", "small_strato_fwd", "cbm4_ros_tlm", "cbm4_sdirk", "cbm4_rk", "cbm4_rk_adj", "cbm4_sdirk_tlm", "cbm4_sdirk_adj", "swe_erk", "swe_erk_tlm"],
+    ap.add_argument("--no-side", action="store_true", help="skip the side block (other BASELINE configs, ~2 minutes, N=1 only)")
+    ap.add_argument("--workload", default="cbm4_ros_adj", choices=["cbm4_ros_adj"] + sorted(SIDE_DEFAULT_CELLS),
                     help="cbm4_ros_adj = the headline metric (default); the others are side measurements of the other "
                          "BASELINE configs / entry points (single GPU, one JSON line each, not the driver's metric)")
     args = ap.parse_args()
@@ -368,7 +494,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = F.lib()
     dev = torch.device("cuda", local)
-    nc = args.cells
+    nc = default_cells(args)
     rtol, atol = tolerances()
     ic, rc = icntrl_rodas4(), np.zeros(20)
     base = F.initial_state("cbm4")
@@ -492,37 +618,72 @@ def main():
         acc_t, att_t, ms_adj_t, ms_fwd_t, ms_tape_t, n_adj_t, general_t = [float(x) for x in tot.tolist()]
         f_adj = acc_t * flops_adjoint_per_step()
         f_fwd = flops_forward(att_t, acc_t)
-        # dominant kernel: k_ros_adj; per-rank kernel time = sum of its launches on that rank (ranks run concurrently)
-        adj_tflops = f_adj / (ms_adj_t / world * 1e-3) / 1e12
-        # DRAM traffic of the backward kernel: measured with ncu (profiles/, dram__bytes_read.sum + dram__bytes_write.sum of
-        # k_ros_adj_cell) = 28.4 kB per accepted step (the step entry 3.3 kB + six stage blocks of 4.5 kB, streamed once
-        # by TMA, plus the Lambda/Mu write-back); scaled here to the steps one launch of this run processes
-        traffic_per_step = 28.4e3
+        # dominant kernel: k_ros_adj_cell; per-rank kernel time = sum of its launches on that rank (ranks run concurrently)
+        adj_s = ms_adj_t / world * 1e-3
+        fwd_s = ms_fwd_t / world * 1e-3
+        adj_tflops = f_adj / adj_s / 1e12
+        peak = fp64_peak * world
+        ex = executed_counts()       # ncu-measured executed FP64 work per unit, only if captured from THIS binary
         roof = {"bound": "fp64", "kernel": "k_ros_adj_cell<Cbm4Warp> (discrete adjoint sweep, lane = adjoint column)",
-                "achieved": adj_tflops, "peak": fp64_peak * world, "unit": "TFLOP/s", "frac": adj_tflops / (fp64_peak * world),
+                "achieved": adj_tflops, "peak": peak, "unit": "TFLOP/s", "frac": adj_tflops / peak,
+                "achieved_is": "ALGORITHMIC flops (SURVEY.md 8d: the dense FULL_ALGEBRA count of the reference, evaluated on the "
+                               "returned counters) / CUDA-event time of the kernel's launches in this run; the kernel executes "
+                               "the 276/367/128-nnz sparse patterns, so this can exceed 1 -- see executed_*",
                 "peak_source": "DFMA micro-benchmark run by this bench on this GPU (fatode_measure_fp64_peak); "
                                "MEASURED_PEAKS.json carries no FP64 figure",
                 "algorithmic_flops_per_accepted_step": flops_adjoint_per_step(),
                 "launches": int(n_adj_t), "avg_launch_ms": ms_adj_t / max(n_adj_t, 1.0),
                 "share_of_step_time": (ms_adj_t / world) / ms,
-                "traffic": traffic_per_step * acc_t / max(n_adj_t, 1.0),
-                "traffic_note": "bytes per launch = ncu-measured DRAM bytes per accepted step x steps per launch",
+                "traffic": (ex["adjoint"]["dram_bytes_per_accepted_step"] * acc_t / max(n_adj_t, 1.0)) if ex else None,
                 "whole_job_algorithmic_tflops": (f_adj + f_fwd) / (ms * 1e-3) / 1e12,
-                "whole_job_frac_of_fp64_peak": (f_adj + f_fwd) / (ms * 1e-3) / 1e12 / (fp64_peak * world),
+                "whole_job_frac_of_fp64_peak": (f_adj + f_fwd) / (ms * 1e-3) / 1e12 / peak,
                 "forward_ms_per_step": ms_fwd_t / (args.steps * world), "expand_ms_per_step": ms_tape_t / (args.steps * world),
                 "adjoint_ms_per_step": ms_adj_t / (args.steps * world),
-                "cells_on_general_path": int(general_t),
-                # executed (not algorithmic) work of the same kernel from the ncu capture in profiles/r1i_cellpath_raw.csv:
-                # the kernel exploits the sparsity, so it executes ~0.65 Mflop per accepted step of the 2.05 Mflop dense count
-                "executed_fp64_pipe_busy_ncu": 0.30, "executed_dfma_frac_of_peak_ncu": 0.206, "issue_slots_busy_ncu": 0.285}
+                "forward_kernel": {"kernel": "k_ros_fwd_cell_tm<Cbm4Cell> (forward sweep + tape, one cell per thread, two warps per SM)",
+                                   "achieved": f_fwd / fwd_s / 1e12, "peak": peak, "unit": "TFLOP/s",
+                                   "frac": f_fwd / fwd_s / 1e12 / peak, "share_of_step_time": (ms_fwd_t / world) / ms},
+                "cells_on_general_path": int(general_t)}
+        if ex:
+            e_adj = ex["adjoint"]["fp64_flops_per_accepted_step"] * acc_t
+            e_fwd = ex["forward"]["fp64_flops_per_attempt"] * att_t
+            roof["executed_tflops"] = e_adj / adj_s / 1e12
+            roof["executed_frac"] = e_adj / adj_s / 1e12 / peak
+            roof["forward_kernel"]["executed_tflops"] = e_fwd / fwd_s / 1e12
+            roof["forward_kernel"]["executed_frac"] = e_fwd / fwd_s / 1e12 / peak
+            roof["executed_source"] = ex["source"]
+        else:
+            roof["executed_source"] = ("not reported: profiles/executed_counts.json is absent or was captured from another build of "
+                                       "libfatode_b200.so than the one this run loaded")
         line = {"metric": "cell-integrations/sec (fwd + adjoint), CBM-IV ROS_ADJ", "value": value, "unit": "cells/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(nc, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roof,
                 "accepted_steps_per_cell": acc_t / (nc * world * args.steps)}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()
+        if not args.no_side and world == 1:
+            # the other BASELINE configs, one timed call each (config 2: small_strato 2^20 cells; config 4: RK_ADJ and
+            # SDIRK_TLM; config 5: the shallow-water ensemble), each with its algorithmic roofline fraction and a bit check
+            # against the CPU oracle on a sample
+            del y0_all, y, lam, mu
+            torch.cuda.empty_cache()
+            L.fatode_release_workspace()
+            side = {}
+            hbm = measured_hbm_peak()
+            for w_, n_ in (("small_strato_fwd", 1 << 20), ("cbm4_rk_adj", 9472), ("cbm4_sdirk_tlm", 9472), ("swe_erk", 32768)):
+                t_ = time.perf_counter()
+                try:
+                    sl = side_measure(w_, n_, 1, 1, fp64_peak, hbm)
+                    side[w_] = {k: sl[k] for k in ("value", "unit", "ms_per_step", "e2e", "cpu_baseline", "roofline",
+                                                   "bitwise_equal_to_oracle_on_sample") if k in sl}
+                    side[w_]["workload"] = sl["config"]["workload"]
+                    side[w_]["cells"] = n_
+                except Exception as exc:       # a side case must never cost the headline line
+                    side[w_] = {"error": repr(exc)}
+                side[w_]["wall_s"] = time.perf_counter() - t_
+                L.fatode_release_workspace()
+            line["side"] = side
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

@@ -792,11 +792,16 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
   // forward kernel's 190 KB of straight-line code evicts the backward kernel's from the instruction cache), so it is
   // kept as an option (fatode_set_pipeline) rather than the default.
   const int pmode = getenv("FATODE_PIPELINE") ? atoi(getenv("FATODE_PIPELINE")) : g_pipeline;
-  const int nbuf = pmode > 0 ? 2 : 1;
-  const bool use_tm = fwd_tm && pmode <= 0;
-  const int LANES = pmode > 0 ? CELL_LANES_SHARED : (use_tm ? FWD_TM_LANES * FWD_TM_WARPS : CELL_LANES_SOLO);   // cells per SM
+  // Mode 3 (default): forward sweep alone on the GPU (it needs the whole shared memory and tensor memory of an SM), then
+  // the batches of the wave with k_expand_tape of batch g+1 (HBM bound, 75 % of the bandwidth when it runs alone) beside
+  // the backward sweep of batch g (FP64-latency bound, 8 % of the bandwidth): two fat buffers, one pool.
+  const int nbuf = (pmode == 1 || pmode == 2) ? 2 : 1;        // chunk pools
+  const int nfat = (pmode >= 1) ? 2 : 1;                      // fat buffers
+  const bool fwd_shared = (pmode == 1 || pmode == 2);          // forward sweep co-resident with the backward sweep
+  const bool use_tm = fwd_tm && !fwd_shared;
+  const int LANES = fwd_shared ? CELL_LANES_SHARED : (use_tm ? FWD_TM_LANES * FWD_TM_WARPS : CELL_LANES_SOLO);   // cells per SM
   const int S = rp.S;
-  const size_t cell_smem = pmode > 0 ? CellSmem<Cell, CELL_LANES_SHARED>::BYTES : CellSmem<Cell, CELL_LANES_SOLO>::BYTES;
+  const size_t cell_smem = fwd_shared ? CellSmem<Cell, CELL_LANES_SHARED>::BYTES : CellSmem<Cell, CELL_LANES_SOLO>::BYTES;
   const size_t adj_smem = sizeof(double) * ((size_t)ADJ3_WARP_DOUBLES * ADJ3_WARPS + (size_t)ADJ3_PRIV_DOUBLES * (ADJ3_WARPS - 4));
   CUDA_TRY(cudaFuncSetAttribute(k_ros_fwd_cell<Cell, 1, CELL_LANES_SHARED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)CellSmem<Cell, CELL_LANES_SHARED>::BYTES));
@@ -810,6 +815,7 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
   StreamSet ss = g_ss;
   if (pmode <= 1) ss.sX = ss.sF;
   if (pmode <= 0) ss.sA = ss.sF;
+  if (pmode == 3) ss.sA = ss.sF;       // forward and backward sweeps alternate on one stream, the expansion runs beside them
   {   // constant Hessian values of the mechanism for k_expand_tape
     CUDA_TRY(g_part.ensure(sizeof(double) * 512));
     k_cbm4_hess<<<1, 1, 0, st>>>(mc.fix, g_part.as<double>());
@@ -823,7 +829,7 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
   size_t budget;
   if (g_tape_budget) budget = (size_t)g_tape_budget;
   else if (g_comp[0].cap >= chunk_bytes * 64 && g_fat[0].cap >= fat_step_bytes * 64 && (nbuf == 1 || g_comp[1].cap == g_comp[0].cap) &&
-           (nbuf == 2 || g_comp[1].cap == 0))
+           (nbuf == 2 || g_comp[1].cap == 0) && (nfat == 1 || g_fat[1].cap == g_fat[0].cap) && (nfat == 2 || g_fat[1].cap == 0))
     budget = 0;   // reuse the cached buffers
   else {
     size_t free_b = 0, total_b = 0;
@@ -834,7 +840,7 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
   // (the tensor-memory forward kernel holds 58 cells per SM: a wave of 148 x 58 cells wants a larger pool)
   const double comp_frac = nbuf == 2 ? 0.14 : (use_tm ? 0.36 : 0.22);
   const size_t comp_bytes = budget ? (size_t)(comp_frac * (double)budget) : g_comp[0].cap;
-  const size_t fat_bytes = budget ? (size_t)((nbuf == 2 ? 0.36 : 1.0 - comp_frac) * (double)budget) : g_fat[0].cap;
+  const size_t fat_bytes = budget ? (size_t)((1.0 - nbuf * comp_frac) / nfat * (double)budget) : g_fat[0].cap;
   const unsigned pool_chunks = (unsigned)std::min<size_t>(comp_bytes / chunk_bytes, 0x7fffffffu);
   const long long fat_steps_cap = (long long)(fat_bytes / fat_step_bytes);
   if (pool_chunks < 1 || fat_steps_cap < 1) return fail(FATODE_ENOMEM, "tape budget smaller than one chunk of the trajectory tape");
@@ -842,9 +848,9 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
     for (int i = 0; i < 2; ++i) { g_comp[i].release(); g_fat[i].release(); }   // re-plan (budget or mode changed)
   }
   const int64_t wave_max = std::min<int64_t>(g_wave_cells > 0 ? g_wave_cells : (int64_t)sms * LANES, ncells);
+  for (int i = 0; i < nfat; ++i) CUDA_TRY(g_fat[i].ensure((size_t)fat_steps_cap * fat_step_bytes));
   for (int i = 0; i < nbuf; ++i) {
     CUDA_TRY(g_comp[i].ensure((size_t)pool_chunks * chunk_bytes));
-    CUDA_TRY(g_fat[i].ensure((size_t)fat_steps_cap * fat_step_bytes));
     CUDA_TRY(g_cprev[i].ensure(sizeof(int) * (size_t)pool_chunks));
     CUDA_TRY(g_cowner[i].ensure(sizeof(int) * (size_t)pool_chunks));
     CUDA_TRY(g_cseq[i].ensure(sizeof(int) * (size_t)pool_chunks));
@@ -941,7 +947,7 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
       k_ros_fwd_cell_tm<Cell, 1, FWD_TM_LANES><<<fblocks, 32 * FWD_TM_WARPS, CellSmemTM<Cell, FWD_TM_LANES>::BYTES, ss.sF>>>(
           rp, mc, n, g_wids[p].as<int>(), d_y, d_y, d_atol, d_rtol, d_istatus, d_rstatus, d_ierr, g_wnacc2[p].as<int>(), tape,
           with_mu ? 1 : 0, g_debug_irregular_every, d_ctr + p);
-    else if (pmode > 0)
+    else if (fwd_shared)
       k_ros_fwd_cell<Cell, 1, CELL_LANES_SHARED><<<fblocks, 32, cell_smem, ss.sF>>>(
           rp, mc, n, g_wids[p].as<int>(), d_y, d_y, d_atol, d_rtol, d_istatus, d_rstatus, d_ierr, g_wnacc2[p].as<int>(), tape,
           with_mu ? 1 : 0, g_debug_irregular_every, d_ctr + p);
@@ -1014,7 +1020,7 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
       CUDA_TRY(cudaStreamWaitEvent(ss.sX, ss.tables_ready, 0));
       for (size_t bi = 0; bi < batches.size(); ++bi) {
         const Batch& bt = batches[bi];
-        const int f = (nbuf == 2) ? (g & 1) : 0;
+        const int f = (nfat == 2) ? (g & 1) : 0;
         const int64_t nb = (int64_t)(bt.o1 - bt.o0);
         if (fat_used[f]) CUDA_TRY(cudaStreamWaitEvent(ss.sX, ss.fat_free[f], 0));
         if (int e = t_begin(ss.sX, 1)) return e;

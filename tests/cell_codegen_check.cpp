@@ -19,6 +19,7 @@ static double g_rc[81], g_hess[258];
 
 static long n_lu = 0, n_lu_bad = 0, n_irregular = 0, n_solve = 0, n_solve_bad = 0, n_swaps[4] = {0, 0, 0, 0};
 static double cur_lu[cbm4_cell::NLU];
+static double cur_dinv[32];
 static unsigned cur_swaps = 0;
 static bool cur_ok = false;
 static double max_terr = 0.0;
@@ -54,7 +55,7 @@ static inline int dgetf2(int n, double* a, int* ipiv) {
     for (int c = 0; c < 32; ++c)
       if (!inpat[i][c] && a[i + 32 * c] != 0.0) { std::printf("E has an entry outside the pattern (%d,%d)\n", i, c); std::exit(2); }
   int info = dgetf2_oracle(n, a, ipiv);
-  double dinv[32];
+  double* const dinv = cur_dinv;
   int bad = lu_factor<1>(cur_lu, dinv, cur_swaps);
   ++n_lu;
   // expected verdict: regular iff every interchange is one of the allowed ones
@@ -125,9 +126,14 @@ static inline void dgetrs(bool trans, int n, const double* a, const int* ipiv, d
   double x[32];
   std::memcpy(x, b, sizeof x);
   dgetrs_oracle(trans, n, a, ipiv, b);
+  double xr[32];
+  std::memcpy(xr, x, sizeof xr);
   cbm4_cell::lu_solve<1>(cur_lu, cur_swaps, x);
   ++n_solve;
   for (int i = 0; i < 32; ++i) if (!same(x[i], b[i])) { ++n_solve_bad; break; }
+  // the register form of the tensor-memory forward kernel (quotients through exact_div_safe): every solve of the trajectory
+  cbm4_cell::lu_solve_reg<1>(cur_lu, cur_dinv, cur_swaps, xr);
+  for (int i = 0; i < 32; ++i) if (!same(xr[i], b[i])) { ++n_solve_bad; break; }
 }
 // ZGETF2 / ZGETRS('N') of the implicit Runge-Kutta families through cbm4_cell::zlu_factor / zlu_solve
 static inline int zgetf2(int n, cplx* a, int* ipiv) {

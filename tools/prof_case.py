@@ -15,4 +15,8 @@ if os.environ.get("PROF_TAPE_GB"):
     F.lib().fatode_set_tape_budget(int(float(os.environ["PROF_TAPE_GB"]) * 2**30))
 r = F.integrate_adj("cbm4", T0, T1, y, 32, rtol, atol, icntrl_u=ic)
 s = F.last_stats()
+if os.environ.get("PROF_COUNTS"):
+    import json
+    json.dump({"cells": nc, "hours": hours, "accepted_steps": int(s.accepted_steps), "attempts": int(r.istatus[:, 2].sum() - r.istatus[:, 3].sum())},
+              open(os.environ["PROF_COUNTS"], "w"))
 print(f"ncells {nc}: fwd {s.ms_forward:.1f} fwd_tape {s.ms_forward_tape:.1f} adj {s.ms_adjoint:.1f} ms steps {s.accepted_steps} ok {(r.ierr==1).all()}")
