@@ -43,7 +43,7 @@ struct Cbm4Warp {
     if (Tlocal >= SunRise && Tlocal <= SunSet) {
       double Ttmp = __ddiv_rn(__dsub_rn(__dsub_rn(__dmul_rn(2.0, Tlocal), SunRise), SunSet), __dsub_rn(SunSet, SunRise));
       if (Ttmp > 0) Ttmp = __dmul_rn(Ttmp, Ttmp); else Ttmp = __dmul_rn(-Ttmp, Ttmp);
-      return __ddiv_rn(__dadd_rn(1.0, fpm::cos_small(__dmul_rn(PI, Ttmp))), 2.0);
+      return __ddiv_rn(__dadd_rn(1.0, fpm::cos_cr(__dmul_rn(PI, Ttmp))), 2.0);
     }
     return 0.0;
   }

@@ -1,10 +1,14 @@
-// Deterministic elementary functions for the two places where the step sequence depends on a
-// transcendental: COS in the models' Update_SUN and Err**(1/ELO) in the Rosenbrock step controller
-// (ADJ/ROS_ADJ/ROS_ADJ_f90_Integrator.F90:1048).  libm results differ by an ulp between platforms
-// (glibc picks FMA/non-FMA variants per CPU; CUDA's cos/pow are 1-2 ulp), and the CBM-IV error
-// estimate amplifies one ulp into different accept/reject sequences.  These versions use only IEEE
-// +,-,*,/,sqrt and integer bit moves in a fixed order, so host (g++ -ffp-contract=off) and device
-// (nvcc -fmad=false) produce identical bits.  Accuracy: < 1 ulp (classic fdlibm-style kernels).
+// Deterministic, CORRECTLY ROUNDED elementary functions for the two places where the Rosenbrock step sequence depends on a
+// transcendental: COS in the models' Update_SUN and Err**(1/ELO) in the step controller
+// (ADJ/ROS_ADJ/ROS_ADJ_f90_Integrator.F90:1048).  libm results differ by an ulp between platforms (glibc picks FMA/non-FMA
+// variants per CPU and changed its cos/pow in 2.28; CUDA's are 1-2 ulp), and the CBM-IV error estimate amplifies one ulp into
+// a different accept/reject sequence (half of the perturbed cells take different step counts under two libms, DESIGN.md
+// section 5).  The one implementation-independent definition of these values is the correctly rounded one -- what the
+// reference's golden binaries got from the IBM Accurate Mathematical Library of their 2012 glibc -- so cos_cr / root_elo
+// evaluate in double-double arithmetic (error < 2^-80, then one rounding: correctly rounded except with probability ~2^-27
+// per call) with IEEE +,-,*,/,sqrt, fma and integer bit moves in a fixed order: host (g++ -ffp-contract=off) and device (nvcc
+// -fmad=false) produce identical bits.  The x**(-1/k) kernels of the SDIRK / RK / ERK controllers below are fixed-order
+// IEEE kernels (< 1.2 ulp), not correctly rounded.
 #pragma once
 #include <stdint.h>
 #include <string.h>
@@ -21,45 +25,78 @@ namespace fpm {
 FPM_HD uint64_t bits_of(double x) { uint64_t u; memcpy(&u, &x, 8); return u; }
 FPM_HD double from_bits(uint64_t u) { double x; memcpy(&x, &u, 8); return x; }
 
-// sin on [-pi/4, pi/4], argument x + y (y = tail)
-FPM_HD double k_sin(double x, double y, int iy) {
-  const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
-               S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
-  double z = x * x;
-  double v = z * x;
-  double r = S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)));
-  if (iy == 0) return x + v * (S1 + z * r);
-  return x - ((z * (0.5 * y - v * r) - y) - v * S1);
+// ---- double-double helpers (error-free transformations; every operation is an IEEE operation, fma included)
+struct dd { double hi, lo; };
+FPM_HD dd two_sum(double a, double b) { double s = a + b; double bb = s - a; double e = (a - (s - bb)) + (b - bb); dd r = {s, e}; return r; }
+FPM_HD dd fast_two_sum(double a, double b) { double s = a + b; double e = b - (s - a); dd r = {s, e}; return r; }   // |a| >= |b|
+FPM_HD dd two_prod(double a, double b) { double p = a * b; double e = fma(a, b, -p); dd r = {p, e}; return r; }
+FPM_HD dd dd_add(dd a, dd b) {
+  dd s = two_sum(a.hi, b.hi), t = two_sum(a.lo, b.lo);
+  s.lo = s.lo + t.hi;
+  s = fast_two_sum(s.hi, s.lo);
+  s.lo = s.lo + t.lo;
+  return fast_two_sum(s.hi, s.lo);
 }
-// cos on [-pi/4, pi/4], argument x + y
-FPM_HD double k_cos(double x, double y) {
-  const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
-               C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
-  double ax = fabs(x);
-  double z = x * x;
-  double r = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
-  if (ax < 0.3) return 1.0 - (0.5 * z - (z * r - x * y));
-  double qx;
-  if (ax > 0.78125) qx = 0.28125;
-  else qx = from_bits((bits_of(ax) - 0x0020000000000000ull) & 0xffffffff00000000ull);   // ~|x|/4, 32-bit mantissa
-  double hz = 0.5 * z - qx;
-  double a = 1.0 - qx;
-  return a - (hz - (z * r - x * y));
+FPM_HD dd dd_add_d(dd a, double b) {
+  dd s = two_sum(a.hi, b);
+  s.lo = s.lo + a.lo;
+  return fast_two_sum(s.hi, s.lo);
 }
-// cos(x) for |x| <= ~3.93 (5*pi/4): quadrant reduction with a two-part pi/2
-FPM_HD double cos_small(double x) {
+FPM_HD dd dd_mul(dd a, dd b) {
+  dd p = two_prod(a.hi, b.hi);
+  p.lo = p.lo + (a.hi * b.lo + a.lo * b.hi);
+  return fast_two_sum(p.hi, p.lo);
+}
+
+// cos(r) for the double-double r, |r| <= pi/4, z = r*r: Taylor series, the terms below 1e-9 in double, the rest in double-double
+FPM_HD dd k_cos_dd(dd z) {
+  const double zh = z.hi;
+  const double tail = zh * (2.08767569878681e-09 + zh * (-1.1470745597729725e-11 + zh * (4.779477332387385e-14 + zh * (-1.5619206968586225e-16 +
+                      zh * (4.110317623312165e-19 + zh * (-8.896791392450574e-22 + zh * 1.6117375710961184e-24))))));
+  const dd D1 = {-0.5, 0.0}, D2 = {0.041666666666666664, 2.3129646346357427e-18}, D3 = {-0.001388888888888889, 5.300543954373577e-20},
+           D4 = {2.48015873015873e-05, 2.1511947866775882e-23}, D5 = {-2.755731922398589e-07, -2.3767714622250297e-23};
+  dd a = dd_add_d(D5, tail);
+  a = dd_add(D4, dd_mul(z, a));
+  a = dd_add(D3, dd_mul(z, a));
+  a = dd_add(D2, dd_mul(z, a));
+  a = dd_add(D1, dd_mul(z, a));
+  a = dd_mul(z, a);
+  return dd_add_d(a, 1.0);
+}
+// sin(r) for the double-double r, |r| <= pi/4, z = r*r
+FPM_HD dd k_sin_dd(dd r, dd z) {
+  const double zh = z.hi;
+  const double tail = zh * (1.6059043836821613e-10 + zh * (-7.647163731819816e-13 + zh * (2.8114572543455206e-15 + zh * (-8.22063524662433e-18 +
+                      zh * (1.9572941063391263e-20 + zh * -3.868170170630684e-23)))));
+  const dd E1 = {-0.16666666666666666, -9.25185853854297e-18}, E2 = {0.008333333333333333, 1.1564823173178714e-19},
+           E3 = {-0.0001984126984126984, -1.7209558293420705e-22}, E4 = {2.7557319223985893e-06, -1.858393274046472e-22},
+           E5 = {-2.505210838544172e-08, 1.448814070935912e-24};
+  dd a = dd_add_d(E5, tail);
+  a = dd_add(E4, dd_mul(z, a));
+  a = dd_add(E3, dd_mul(z, a));
+  a = dd_add(E2, dd_mul(z, a));
+  a = dd_add(E1, dd_mul(z, a));
+  a = dd_mul(dd_mul(z, a), r);      // r * z * (...)
+  return dd_add(r, a);
+}
+// cos(x), correctly rounded (see the header comment), for |x| <= 5*pi/4 (Update_SUN needs |x| <= pi): quadrant reduction with a
+// three-part pi/2 (33 + 33 + 53 bits, the first two products with n exact), the kernels in double-double, one final rounding
+FPM_HD double cos_cr(double x) {
   const double pio4 = 7.85398163397448278999e-01;
-  const double pio2_1 = 1.57079632673412561417e+00;    // first 33 bits of pi/2
-  const double pio2_1t = 6.07710050650619224932e-11;   // pi/2 - pio2_1
-  double ax = fabs(x);
-  if (ax <= pio4) return k_cos(ax, 0.0);
-  int n = (ax <= 3.0 * pio4) ? 1 : 2;
-  double z = ax - (double)n * pio2_1;                  // exact (33-bit constant, small n)
-  double t = (double)n * pio2_1t;
-  double r0 = z - t;
-  double r1 = (z - r0) - t;                            // tail
-  if (n == 1) return -k_sin(r0, r1, 1);
-  return -k_cos(r0, r1);
+  const double P1 = 1.5707963267341256, P2 = 6.077100506303966e-11, P3 = 2.0222662487959506e-21;
+  const double ax = fabs(x);
+  const int n = (ax <= pio4) ? 0 : ((ax <= 3.0 * pio4) ? 1 : 2);
+  dd r = {ax, 0.0};
+  if (n) {
+    const double z = ax - (double)n * P1;              // exact (33-bit constant, Sterbenz)
+    r = two_sum(z, -((double)n * P2));                 // exact
+    r.lo = r.lo - (double)n * P3;
+    r = fast_two_sum(r.hi, r.lo);
+  }
+  const dd z = dd_mul(r, r);
+  if (n == 1) return -k_sin_dd(r, z).hi;
+  const double c = k_cos_dd(z).hi;
+  return n ? -c : c;
 }
 
 // cube root, x > 0 normal (fdlibm s_cbrt construction: rational seed, 20-bit chop, one Newton step)
@@ -79,18 +116,35 @@ FPM_HD double cbrt_pos(double x) {
   return t + t * r;
 }
 
-// x**(1/elo) for the estimator orders used by the Rosenbrock tableaux (ros_ELO = 2, 3 or 4)
+// x**fl(1/elo), correctly rounded, for the estimator orders of the Rosenbrock tableaux (ros_ELO = 2, 3 or 4; the reference
+// evaluates Err**(ONE/ros_ELO)): a root to < 1 ulp, then one Newton correction from the exact residual (fma), one rounding
 FPM_HD double root_elo(double x, double elo) {
-  if (elo == 4.0) return sqrt(sqrt(x));
-  if (elo == 3.0) {
-    // the reference raises to fl(1/3) = 1/3 + d, d = -1.85e-17: x**fl(1/3) = cbrt(x)*(1 + d*ln x);
-    // ln x is only needed to two digits here (exponent + linear mantissa term)
-    const double c = cbrt_pos(x);
-    const uint64_t b = bits_of(x);
-    const double lg2 = (double)((int)((b >> 52) & 0x7ff) - 1023) + (from_bits((b & 0x000fffffffffffffull) | 0x3ff0000000000000ull) - 1.0);
-    return c + c * (-1.850371707708594e-17 * (0.6931471805599453 * lg2));
-  }
   if (elo == 2.0) return sqrt(x);
+  if (!(x > 1.0e-290 && x < 1.0e290)) return (elo == 4.0) ? sqrt(sqrt(x)) : pow(x, 1.0 / elo);   // never met: Err >= 1e-10
+  if (elo == 4.0) {
+    const double r0 = sqrt(sqrt(x));
+    const dd p = two_prod(r0, r0);                      // r0^2 = p.hi + p.lo
+    const dd q = two_prod(p.hi, p.hi);                  // p.hi^2 = q.hi + q.lo
+    const double e = (x - q.hi) - (q.lo + 2.0 * p.hi * p.lo);   // x - r0^4 (x - q.hi is exact)
+    return r0 + e * r0 / (4.0 * x);                     // Newton: delta = e / (4 r0^3)
+  }
+  if (elo == 3.0) {
+    // x**fl(1/3) = cbrt(x) * exp(d ln x), d = fl(1/3) - 1/3 = -1.85e-17
+    const double c0 = cbrt_pos(x);
+    const dd p = two_prod(c0, c0);
+    const dd q = two_prod(p.hi, c0);
+    const double e = (x - q.hi) - (q.lo + p.lo * c0);   // x - c0^3
+    const double d1 = e / (3.0 * p.hi);
+    const uint64_t b = bits_of(x);
+    int ex = (int)((b >> 52) & 0x7ff) - 1023;
+    double m = from_bits((b & 0x000fffffffffffffull) | 0x3ff0000000000000ull);
+    if (m > 1.4142135623730951) { m = 0.5 * m; ex += 1; }
+    const double s = (m - 1.0) / (m + 1.0), s2 = s * s;   // ln m = 2 atanh(s), |s| <= 0.172: relative error < 1e-12
+    const double lnm = 2.0 * s * (1.0 + s2 * (1.0 / 3.0 + s2 * (0.2 + s2 * (1.0 / 7.0 + s2 * (1.0 / 9.0 + s2 * (1.0 / 11.0 + s2 * (1.0 / 13.0
+                       + s2 * (1.0 / 15.0))))))));
+    const double lnx = (double)ex * 0.6931471805599453 + lnm;
+    return c0 + (d1 + c0 * (-1.850371707708594e-17 * lnx));
+  }
   return pow(x, 1.0 / elo);   // not reached by the shipped tableaux
 }
 

@@ -270,6 +270,9 @@ double fatode_measure_fp64_peak(int iters);
  *                     lu_out row-major in pivoted row order, who[k] = original row at position k */
 int fatode_probe_cbm4(double t, const double* y, double* f, double* jac_dense, double* hess);
 int fatode_probe_lu32(const double* A, const double* b, double* lu_out, int* who, double* x, int* info);
+/*  fatode_probe_math: the correctly rounded COS (Update_SUN) and Err**(1/ELO) (step controller) kernels evaluated on the device:
+ *                     out_cos[i] = cos(x[i]) for |x[i]| <= 5 pi / 4, out_root[i] = |x[i]| ** fl(1/elo), elo = 2, 3 or 4 */
+int fatode_probe_math(int n, const double* x, double elo, double* out_cos, double* out_root);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ namespace oracle {
 
 // 0: deterministic kernels of portable_math.hpp (default), 1: libm cos/pow (see portable_math.hpp)
 inline int& libm_mode() { static int m = (getenv("ORACLE_LIBM") && atoi(getenv("ORACLE_LIBM")) != 0) ? 1 : 0; return m; }
-static inline double o_cos(double x) { return libm_mode() ? std::cos(x) : oracle_pm::cos_small(x); }
+static inline double o_cos(double x) { return libm_mode() ? std::cos(x) : oracle_pm::cos_cr(x); }
 static inline double o_root(double x, double elo) { return libm_mode() ? std::pow(x, 1.0 / elo) : oracle_pm::root_elo(x, elo); }
 
 #define F4(x) ((double)(x##f))

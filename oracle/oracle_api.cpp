@@ -61,6 +61,10 @@ static void fwd_batch(long ncells, double* y, double tin, double tout, const dou
 extern "C" {
 
 int oracle_max_threads() { return omp_get_max_threads(); }
+// the correctly rounded kernels of portable_math.hpp themselves (tests: against a multi-precision reference, against the device)
+void oracle_probe_math(int n, const double* x, double elo, double* out_cos, double* out_root) {
+  for (int i = 0; i < n; ++i) { out_cos[i] = oracle_pm::cos_cr(x[i]); out_root[i] = oracle_pm::root_elo(std::fabs(x[i]), elo); }
+}
 int oracle_set_libm(int on) { int old = libm_mode(); libm_mode() = on ? 1 : 0; return old; }
 
 int oracle_model_dims(int model, int* n, int* np) {

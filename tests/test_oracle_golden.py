@@ -63,23 +63,30 @@ def test_cbm4_ros_adj_matches_reference_golden_files():
     assert att >= A + R
 
 
-def test_cbm4_default_mode_agrees_with_golden_at_integration_level():
-    """Default (deterministic cos/root kernels): one ulp in SUN(t) or Err**(1/4) changes the
-    accept/reject sequence of this problem (the error estimate is dominated by cancellation), so the
-    run is a different but equally valid Rodas4 trajectory: Nacc 799 vs 797, state within 1e-8,
-    sensitivities within the integration tolerance."""
+def test_cbm4_default_mode_reproduces_the_golden_files_to_print_precision():
+    """Default mode = correctly rounded COS and Err**(1/4) (oracle/portable_math.hpp): what the IBM Accurate Mathematical Library
+    of the golden binaries' glibc returned.  The restatement then reproduces the reference's own run to the 17 digits the golden
+    files print: same 797 accepted / 47 rejected steps, state and Lambda at the 1e-15 level.  (The host libm of this image, whose
+    cos/pow are no longer correctly rounded, gives 4e-12 / 5e-9 on the same step sequence: the test above.  With 1-ulp kernels the
+    run even takes 799 steps — the step sequence of this problem is that sensitive)"""
     g = json.load(open(os.path.join(G, "cbm4_ros_adj.json")))
     c = cbm4_driver_case()
     assert O.lib().oracle_set_libm(0) == 0
     r = O.ros_adj("cbm4", O.initial_state("cbm4"), 32, c["tin"], c["tout"], c["atol"], c["rtol"], c["icntrl"], nthreads=1)
+    ist = r["istatus"][0]
+    assert (ist[3], ist[4], ist[2] - ist[3]) == (797, 47, 844)
     gy = np.array(g["y"])
-    assert np.max(np.abs(r["y"][0] - gy)) <= 1e-8 * np.max(np.abs(gy))
+    assert np.max(np.abs(r["y"][0] - gy)) <= 1e-14 * np.max(np.abs(gy))
     glam = np.array(g["lambda"]).reshape(32, 32)
     cs = np.max(np.abs(glam), axis=1)
     ok = cs > 1e-30
     err = (np.max(np.abs(r["lambda_"][0] - glam), axis=1) / np.maximum(cs, 1e-300))[ok]
-    assert np.all(err <= 1e-4) and np.median(err) <= 1e-6, err
-    assert abs(int(r["istatus"][0][3]) - 797) <= 5
+    assert np.all(err <= 1e-13), err
+    gmu = np.array(g["mu"]).reshape(32, 29)
+    rowscale = np.max(np.abs(gmu), axis=0)
+    rerr = np.max(np.abs(r["mu"][0] - gmu), axis=0) / rowscale
+    good = [p for p in range(29) if p not in {15, 22, 23, 24, 25, 26}]
+    assert np.all(rerr[good] <= 1e-12), rerr
 
 
 def test_small_strato_forward_matches_ANS():

@@ -71,18 +71,24 @@ def test_driver_cell_matches_oracle_and_reference_golden():
     res = F.integrate_adj("cbm4", T0, T1, y0, 32, rtol, atol, icntrl_u=rodas4())
     ref = O.ros_adj("cbm4", y0, 32, T0, T1, atol, rtol, rodas4(), nthreads=1)
     check_against_oracle(res, ref, 32)
-    # Reference golden files: produced upstream with glibc's cos/pow.  The engine (and the oracle's
-    # default mode) use fixed-order cos/root kernels, which moves the accept/reject sequence
-    # (Nacc 799 instead of 797 for this cell), so agreement is at the level of two valid runs of
-    # the same integrator at rtol 1e-5, not at round-off level (tests/test_oracle_golden.py pins
-    # the libm mode of the oracle to 4e-12).
+    # Reference golden files (EXAMPLES/cbm4/CBM4_ROS_ADJ/cbm4_ros_sol.txt, cbm4_output_sens.txt).  COS and Err**(1/4) are
+    # correctly rounded in the engine (csrc/portable_math.h), like the IBM libm of the golden binaries, so the GPU takes the
+    # reference's own 797 + 47 steps and meets north_star's 1e-9 against the reference's vectors directly — the forward state
+    # at the 1e-15 level (bit-identical to the oracle, which reproduces the golden state to print precision), Lambda and Mu
+    # within the 1e-9 of the contract (the backward sweep regroups sums and uses fma).
+    assert (res.istatus[0][3], res.istatus[0][4]) == (797, 47)
     g = json.load(open(os.path.join(G, "cbm4_ros_adj.json")))
     gy = np.array(g["y"])
-    assert np.max(np.abs(res.y[0] - gy)) <= 1e-8 * np.max(np.abs(gy))
+    assert np.max(np.abs(res.y[0] - gy)) <= 1e-14 * np.max(np.abs(gy))
     glam = np.array(g["lambda"]).reshape(32, 32)
     cs = np.max(np.abs(glam), axis=1)
     ok = cs > 1e-30
-    assert np.all((np.max(np.abs(res.lambda_[0] - glam), axis=1) / np.maximum(cs, 1e-300))[ok] <= 1e-4)
+    assert np.all((np.max(np.abs(res.lambda_[0] - glam), axis=1) / np.maximum(cs, 1e-300))[ok] <= 1e-9)
+    gmu = np.array(g["mu"]).reshape(32, 29)
+    rowscale = np.max(np.abs(gmu), axis=0)
+    rerr = np.max(np.abs(res.mu[0] - gmu), axis=0) / rowscale
+    good = [p for p in range(29) if p not in {15, 22, 23, 24, 25, 26}]   # parameters of identically-zero species: round-off noise
+    assert np.all(rerr[good] <= 1e-9), rerr
 
 
 def test_batch_of_perturbed_cells_matches_oracle():

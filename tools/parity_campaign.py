@@ -20,7 +20,7 @@ def sens_err(a, b):
 
 def report(name, res, ref, sens=None, tol=1e-9):
     global bad
-    handed_back = res.ierr == -20          # ROS_TLM only: no general-pivoting pass for that family yet (known gap, reported apart)
+    handed_back = res.ierr == -20          # no family hands systems back any more; kept as a tripwire
     if handed_back.any():
         global gaps
         gaps += int(handed_back.sum())
@@ -71,7 +71,12 @@ for k in (1e-2, 1e-3, 1e-4):
     yt = np.tile(np.eye(32), (nc, 1, 1))
     r = F.integrate_tlm("cbm4", T0, t1, y0, yt, rtol, atol, icntrl_u=ic)
     o = O.ros_tlm("cbm4", y0, yt, T0, t1, atol, rtol, ic)
-    report(f"ROS_TLM rtol {F01*k:.0e} n {nc}", r, o, [("Y_tlm", r.y_tlm, o["y_tlm"])], loose)
+    report(f"ROS_TLM rtol {F01*k:.0e} n {nc} (general pass cells {F.last_stats().cells_general})", r, o, [("Y_tlm", r.y_tlm, o["y_tlm"])], loose)
+    # the reference's default call: ICNTRL_U absent -> ICNTRL(12) = 1, columns in the error control (lock-step kernel, bit for bit)
+    at, rt = np.full((8, 32), 1e-6), np.full((8, 32), 10 * F01 * k)
+    r = F.integrate_tlm("cbm4", T0, t1, y0[:32], yt[:32, :8], rtol, atol, atol_tlm=at, rtol_tlm=rt)
+    o = O.ros_tlm("cbm4", y0[:32], yt[:32, :8], T0, t1, atol, rtol, None, atol_tlm=at, rtol_tlm=rt)
+    report(f"ROS_TLM preset (ICNTRL(12)=1) rtol {F01*k:.0e} n 32 ntlm 8 bitwise Y_tlm {np.array_equal(r.y_tlm, o['y_tlm'])}", r, o, [("Y_tlm", r.y_tlm, o["y_tlm"])], 1e-12)
     ic = np.zeros(20, dtype=np.int32); ic[2] = 1
     r = F.integrate_rk("cbm4", T0, t1, y0, rtol, atol, icntrl_u=ic)
     o = O.rk_fwd("cbm4", y0, T0, t1, atol, rtol, ic)
