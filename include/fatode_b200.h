@@ -264,6 +264,25 @@ void fatode_free_pinned(void* p);
 /* FP64 DFMA micro-benchmark on the current device: returns achieved TFLOP/s (<0 on error). */
 double fatode_measure_fp64_peak(int iters);
 
+/* ---- Batched structure-of-arrays container "FATODEB1" (on disk / on the wire) and the reference's text files.
+ * The reference writes one system's result as text, one E24.16 number per line (cbm4_ros_adj_dr.F90:134-164); the container
+ * holds the arrays of a whole batch exactly in the layouts this header uses, so a section can be passed to the *_batch entry
+ * points without re-layout (format: fatode_b200/csrc/fatode_io.cu).  Host code only, no GPU needed.
+ *  fatode_file_write : any of y, lambda, mu, istatus, rstatus, ierr may be NULL (left out)
+ *  fatode_file_info  : header fields (any pointer may be NULL); has[6] = presence of the six arrays in that order
+ *  fatode_file_read  : cells [first_cell, first_cell + ncells) of one named array into dst
+ *  fatode_text_*     : cbm4_ros_sol.txt / cbm4_output_sens.txt of ONE system (lambda[nadj][nvar], mu[nadj][np]) */
+int fatode_file_write(const char* path, int model, int64_t ncells, int nvar, int np, int nadj, double tin, double tout,
+                      const double* y, const double* lambda, const double* mu, const int* istatus, const double* rstatus,
+                      const int* ierr);
+int fatode_file_info(const char* path, int* model, int64_t* ncells, int* nvar, int* np, int* nadj, double* tin, double* tout,
+                     int* has);
+int fatode_file_read(const char* path, const char* name, int64_t first_cell, int64_t ncells, void* dst);
+int fatode_text_write_solution(const char* path, int nvar, const double* y);
+int fatode_text_write_sens(const char* path, int nvar, int np, int nadj, const double* lambda, const double* mu);
+int fatode_text_read_solution(const char* path, int nvar, double* y);
+int fatode_text_read_sens(const char* path, int nvar, int np, int nadj, double* lambda, double* mu);
+
 /* Unit-level probes used by the parity tests (one warp, one system).
  *  fatode_probe_cbm4: f[32] = fun(t,y); jac_dense[32*32] column-major = jac(t,y); hess[258] = Hessian(t)
  *  fatode_probe_lu32: DGETF2 + DGETRS('N') of a column-major 32x32 matrix on the warp LU;
