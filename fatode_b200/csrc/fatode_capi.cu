@@ -625,6 +625,11 @@ static int mu_sum_device(int64_t ncells, int len, const double* d_mu, const int*
   CUDA_TRY(cudaGetLastError());
   g_stats.ms_other += tm.stop();
   g_stats.launches += 2;
+  if (comm_active()) {   // the path's one collective: Mu summed over the cells of every rank (fatode_comm.cu)
+    std::string cerr;
+    if (int e = comm_allreduce_device(d_mu_sum, (size_t)len, st, cerr)) return fail(e, cerr);
+    g_stats.launches += 1;
+  }
   return 0;
 }
 

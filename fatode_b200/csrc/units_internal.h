@@ -29,4 +29,8 @@ int ros_tlm_lock_device(const RosParams& rp, const Cbm4Const& mc, long ncells, c
                         const double* d_rtol_tlm, int* d_istatus, double* d_rstatus, int* d_ierr, cudaStream_t st,
                         UnitTiming& tm, std::string& err);
 
+// fatode_comm.cu — the library's NCCL communicator (optional): sum of a device buffer over the ranks, stream-ordered
+bool comm_active();
+int comm_allreduce_device(double* d_buf, size_t count, cudaStream_t st, std::string& err);
+
 }  // namespace fatode

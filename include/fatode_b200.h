@@ -264,6 +264,20 @@ void fatode_free_pinned(void* p);
 /* FP64 DFMA micro-benchmark on the current device: returns achieved TFLOP/s (<0 on error). */
 double fatode_measure_fp64_peak(int iters);
 
+/* ---- Multi-GPU (one process per GPU).  Cells are sharded by the host; the path's one collective — the sum of
+ * the parameter sensitivities Mu over all cells — is done inside the library over NCCL once a communicator exists: every
+ * *_integrate_adj_batch call then returns mu_sum summed over ALL ranks' cells.  NCCL is resolved at run time (dlopen).
+ *  fatode_comm_unique_id : rank 0 creates the 128-byte NCCL id; the host hands it to the other ranks (file, MPI, socket)
+ *  fatode_comm_init      : every rank, after selecting its GPU (cudaSetDevice)
+ *  fatode_comm_allreduce_sum : in-place sum of a host or device buffer over the ranks (no-op without a communicator) */
+int fatode_comm_unique_id(void* id128);
+int fatode_comm_init(int nranks, int rank, const void* id128);
+int fatode_comm_size(void);
+int fatode_comm_rank(void);
+int fatode_comm_allreduce_sum(double* buf, int64_t count, int mem, void* stream);
+int fatode_comm_finalize(void);
+const char* fatode_comm_last_error(void);
+
 /* ---- Batched structure-of-arrays container "FATODEB1" (on disk / on the wire) and the reference's text files.
  * The reference writes one system's result as text, one E24.16 number per line (cbm4_ros_adj_dr.F90:134-164); the container
  * holds the arrays of a whole batch exactly in the layouts this header uses, so a section can be passed to the *_batch entry
