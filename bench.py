@@ -494,6 +494,25 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = F.lib()
     dev = torch.device("cuda", local)
+    # multi-GPU: the Mu sum over all cells is all-reduced INSIDE the library (fatode_comm_*, NCCL resolved by dlopen); torch's
+    # process group only carries the 128-byte NCCL id and the benchmark's own barriers / timing reduction
+    lib_comm = False
+    if dist is not None:
+        idbuf = (ctypes.c_ubyte * 128)()
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        if rank == 0 and L.fatode_comm_unique_id(idbuf) != 0:
+            ok.zero_()
+        idt = torch.tensor(list(idbuf), dtype=torch.uint8, device=dev)
+        dist.broadcast(idt, 0)
+        dist.broadcast(ok, 0)
+        if int(ok.item()) == 1:
+            idbuf = (ctypes.c_ubyte * 128)(*idt.cpu().tolist())
+            rc_comm = L.fatode_comm_init(world, rank, idbuf)
+            ok.fill_(1 if rc_comm == 0 else 0)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        lib_comm = int(ok.item()) == 1
+        if not lib_comm:
+            L.fatode_comm_finalize()
     nc = default_cells(args)
     rtol, atol = tolerances()
     ic, rc = icntrl_rodas4(), np.zeros(20)
@@ -522,8 +541,8 @@ def main():
                                              None, F.MEM_DEVICE, vp(stream.cuda_stream))
         if r != 0:
             raise RuntimeError(L.fatode_last_error().decode())
-        if dist is not None:
-            dist.all_reduce(musum)      # the path's only exchange: 29x32 parameter sensitivities summed over cells
+        if dist is not None and not lib_comm:
+            dist.all_reduce(musum)      # fall-back: the path's only exchange (29x32 Mu sums) through torch's communicator
         return F.last_stats()
 
     def sync_all():
@@ -546,7 +565,7 @@ def main():
     acc_steps = attempts = 0
     for s in range(args.warmup, args.warmup + args.steps):
         st = step_device(s)
-        launches += st.launches + 1 + (1 if dist is not None else 0)     # + the y0 copy (+ NCCL kernel)
+        launches += st.launches + 1 + (1 if (dist is not None and not lib_comm) else 0)   # + the y0 copy (+ torch's NCCL kernel; the library counts its own)
         n_adj_launches += st.launches_adjoint
         general_cells += st.cells_general
         ms_adj += st.ms_adjoint
@@ -590,7 +609,7 @@ def main():
                                                  vp(hmusum.data_ptr()), None, F.MEM_HOST, vp(stream.cuda_stream))
             if r != 0:
                 raise RuntimeError(L.fatode_last_error().decode())
-            if dist is not None:
+            if dist is not None and not lib_comm:
                 g = hmusum.to(dev, non_blocking=True)
                 dist.all_reduce(g)
                 hmusum.copy_(g)
@@ -658,6 +677,8 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(nc, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "allreduce": (None if dist is None else ("in-library NCCL (fatode_comm_*): mu_sum returned already summed over ranks"
+                                                         if lib_comm else "torch.distributed all_reduce of mu_sum (library communicator unavailable)")),
                 "roofline": roof,
                 "accepted_steps_per_cell": acc_t / (nc * world * args.steps)}
         if not args.no_cpu_baseline and world == 1:
@@ -687,6 +708,8 @@ def main():
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
+        if lib_comm:
+            L.fatode_comm_finalize()
         dist.destroy_process_group()
 
 
