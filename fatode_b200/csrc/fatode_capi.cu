@@ -1282,8 +1282,8 @@ static int ros_batch_impl(int family, int model, int64_t ncells, int nvar, int n
   }
   if (perr != 1) return broadcast_ierr(ncells, perr, istatus, rstatus, ierr, mem, st);
   const bool with_mu = (family == FAM_ADJ) && np > 0 && mu != nullptr;
-  if (model != FATODE_MODEL_CBM4 && do_adjoint)
-    return fail(FATODE_EUNSUPPORTED, "the discrete adjoint is available for the cbm4 model only in this build");
+  if (model != FATODE_MODEL_CBM4 && do_adjoint && nadj > 8)
+    return fail(FATODE_EUNSUPPORTED, "the small models take at most 8 adjoint columns per call");
   Cbm4Const mc;
   cbm4_constants(model_params, mc);
   SmallConst sc;
@@ -1337,6 +1337,19 @@ static int ros_batch_impl(int family, int model, int64_t ncells, int nvar, int n
   else if (model == FATODE_MODEL_CBM4)
     rc = ros_device<Cbm4Cell, Cbm4Warp>(rp, mc, ncells, nadj, with_mu, do_adjoint, d_y, d_lam, d_mu, b_atol.as<double>(),
                                         b_rtol.as<double>(), d_ist, d_rst, d_ierr, d_musum, st);
+  else if (do_adjoint) {   // small_strato / roberts: forward sweep, tape and discrete adjoint of a system in one thread
+    std::memset(&g_stats, 0, sizeof g_stats);
+    UnitTiming ut;
+    std::string uerr;
+    rc = ros_small_adj_device(model, rp, sc.fix, (long)ncells, nadj, with_mu, d_y, d_lam, d_mu, b_atol.as<double>(),
+                              b_rtol.as<double>(), d_ist, d_rst, d_ierr, (size_t)g_tape_budget, st, ut, uerr);
+    if (rc != 0) return fail(rc, uerr);
+    g_stats.ms_forward = ut.ms;
+    g_stats.launches = ut.launches;
+    if (with_mu && d_musum)
+      if (int e = mu_sum_device(ncells, nadj * np, d_mu, d_ierr, d_musum, st)) return e;
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
   else if (model == FATODE_MODEL_SMALL_STRATO)
     rc = ros_device_small<SmallStratoCell>(rp, sc, ncells, d_y, b_atol.as<double>(), b_rtol.as<double>(), d_ist, d_rst, d_ierr, st);
   else

@@ -335,8 +335,9 @@ CONTAINS
     IF (PRESENT(RSTATUS_U)) RSTATUS_U(:) = rst(:)
   END SUBROUTINE INTEGRATE_ADJ
 
-  !~~~> TLM/ROS_TLM INTEGRATE_TLM, one system (TLM/ROS_TLM/ROS_TLM_f90_Integrator.F90:35-36).  The engine implements the
-  !     forward-error-control mode, ICNTRL_U(12) = 0; ROS_TLM has no IERR_U (failures are printed, :86-89).
+  !~~~> TLM/ROS_TLM INTEGRATE_TLM, one system (TLM/ROS_TLM/ROS_TLM_f90_Integrator.F90:35-36): both error-control modes,
+  !     including the preset ICNTRL(12) = 1 of a call without ICNTRL_U (ATOL_tlm / RTOL_tlm are then required, as upstream);
+  !     ROS_TLM has no IERR_U (failures are printed, :86-89).
   !     With fatode_b200_set_family(FATODE_FAMILY_SDIRK) the same routine stands in for TLM/SDIRK_TLM's INTEGRATE_TLM
   !     (TLM/SDIRK_TLM/SDIRK_TLM_f90_Integrator.F90:31-32: no HESS_VEC, IERR_U last); both keyword sets compile unchanged.
   SUBROUTINE INTEGRATE_TLM( N, NTLM, NNZERO, Y, Y_tlm, TIN, TOUT, ATOL_tlm, RTOL_tlm, ATOL, RTOL, FUN, JAC, HESS_VEC, &

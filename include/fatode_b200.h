@@ -82,9 +82,11 @@ int fatode_ros_integrate_batch(int model, int64_t ncells, int nvar, double* y, d
  * reference uses them only for the continuous adjoint).  Quadrature arguments (Q, QFUN, DRDY, DRDP,
  * HESSTR_VEC_R*) and the continuous adjoints (ICNTRL(7) = 3,4) are outside the engine's scope
  * (FATODE_EUNSUPPORTED).
+ * Models: cbm4 (nadj <= 32; the headline path), small_strato (RosenbrockADJ2, EXAMPLES/small_strato/small_ros_adj) and
+ * roberts (NP = 3, EXAMPLES/roberts/ROBERTS_ROS_ADJ without its quadrature terms), nadj <= 8 for the two small models.
  * mu_sum (may be NULL): [nadj][np] sum over all cells of this call with ierr == 1, reduced in a
- * fixed order on the device (host pointer unless mem == FATODE_MEM_DEVICE); a multi-GPU caller
- * all-reduces it across ranks. */
+ * fixed order on the device (host pointer unless mem == FATODE_MEM_DEVICE); with a communicator
+ * (fatode_comm_init) it is additionally summed over the cells of all ranks. */
 int fatode_ros_integrate_adj_batch(int model, int64_t ncells, int nvar, int np, int nadj, double* y,
                                    double* lambda, double* mu, double tin, double tout,
                                    const double* atol_adj, const double* rtol_adj, const double* atol,
@@ -96,14 +98,17 @@ int fatode_ros_integrate_adj_batch(int model, int64_t ncells, int nvar, int np, 
  *   INTEGRATE_TLM(N,NTLM,NNZERO,Y,Y_tlm,TIN,TOUT,ATOL_tlm,RTOL_tlm,ATOL,RTOL,FUN,JAC,HESS_VEC,
  *                 ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U)
  * y_tlm [ncells][ntlm][nvar] = Y_tlm(1:N,1:NTLM) of cell c, column-major (in: sensitivities at TIN, out: at TOUT).
- * ICNTRL_U/RCNTRL_U override the presets (ICNTRL(2)=1, (3)=5, (12)=1) when >= 0 (:77-82).  Built: forward error
- * control, ICNTRL(12) = 0, i.e. any call that passes ICNTRL_U with entry 12 zero; the TLM truncation-error control
- * (ICNTRL(12) != 0, the preset when icntrl_u == NULL) returns FATODE_EUNSUPPORTED.  ATOL_tlm/RTOL_tlm are used by the
- * reference only in that mode.  RCNTRL(3) = STEPMIN (a SAVEd variable of the reference that carries the last step size
- * over to the next call) is 0 for every cell.  ntlm <= 32, cbm4 only; HESS_VEC is the model's registered routine.
- * A cell whose state sweep ends with an error code returns Y and Y_tlm as of its last accepted step, as the reference.
- * Known gap: a system whose factorisations leave the static pivot pattern (almost all at rtol >= 1e-3, 1 in 100 at 1e-4, none
- * at rtol <= 1e-5) returns IERR -20 with Y, Y_tlm untouched — this family has no general-pivoting pass yet. */
+ * ICNTRL_U/RCNTRL_U override the presets (ICNTRL(2)=1, (3)=5, (12)=1) when >= 0 (:77-82).  Both error-control modes are
+ * built: ICNTRL(12) = 0 (forward error control: state sweep + column sweep over the tape) and ICNTRL(12) != 0 — the PRESET
+ * when icntrl_u == NULL — where the columns' error norms (ros_ErrorNorm_tlm, scaled with ATOL_tlm/RTOL_tlm [ntlm][nvar], then
+ * required) enter the accept/reject decision: state and columns advance in lock-step in one kernel whose column arithmetic
+ * follows the reference operation by operation (csrc/ros_tlm_lock.cu).  RCNTRL(3) = STEPMIN — a SAVEd variable of the
+ * reference that leaks the last step size of one call into the next one as Hstart — is 0 for every cell (every system of a
+ * batch is a first call); pass RCNTRL_U(3) = RSTATUS(Nhexit) of the previous call to reproduce the carry-over.
+ * ntlm <= 32, cbm4 only; HESS_VEC is the model's registered routine.  A cell whose state sweep ends with an error code
+ * returns Y and Y_tlm as of its last accepted step, as the reference.  Systems whose factorisations leave the static pivot
+ * pattern of the per-thread kernels (almost all at rtol >= 1e-3, none at rtol <= 1e-5) are integrated by the lock-step kernel
+ * with netlib's partial pivoting (fatode_stats.cells_general counts them). */
 int fatode_ros_integrate_tlm_batch(int model, int64_t ncells, int nvar, int ntlm, double* y, double* y_tlm,
                                    double tin, double tout, const double* atol_tlm, const double* rtol_tlm,
                                    const double* atol, const double* rtol, const int* icntrl_u,
