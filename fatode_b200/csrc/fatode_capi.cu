@@ -29,6 +29,7 @@
 #include "ros_cell_fwd.cuh"
 #include "ros_cell_fwd_tm.cuh"
 #include "ros_cell_adj.cuh"
+#include "ros_cell_adj_pair.cuh"
 #include "model_small_cell.cuh"
 #include "sdirk_cell_fwd.cuh"
 #include "sdirk_cell_tlm.cuh"
@@ -816,6 +817,10 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
                                 (int)CellSmemTM<Cell, FWD_TM_LANES>::BYTES));
   CUDA_TRY(cudaFuncSetAttribute(k_ros_adj_cell<Warp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem));
   CUDA_TRY(cudaFuncSetAttribute(k_ros_tlm_cell<Warp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem));
+  // backward sweep: two warps per cell (solver + accumulator, ros_cell_adj_pair.cuh) unless FATODE_ADJ_PAIR=0 (A/B runs)
+  static const bool adj_pair = !(getenv("FATODE_ADJ_PAIR") && atoi(getenv("FATODE_ADJ_PAIR")) == 0);
+  const size_t adjp_smem = sizeof(double) * (size_t)ADJP_PAIR_DOUBLES * ADJP_PAIRS;
+  CUDA_TRY(cudaFuncSetAttribute(k_ros_adj_pair<Warp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adjp_smem));
   CUDA_TRY(g_ss.init());
   StreamSet ss = g_ss;
   if (pmode <= 1) ss.sX = ss.sF;
@@ -1050,7 +1055,8 @@ static int ros_device_fast(const RosParams& rp, const typename Cell::Const& mc, 
           AdjArgs aa{nb, g_wids[p].as<int>(), g_wnacc2[p].as<int>(), g_wlast2[p].as<int>(), g_comp[p].as<double>(), g_cprev[p].as<int>(),
                      g_fat[f].as<double>(), g_bfatoff[p].as<long long>(), d_ierr, d_y, d_lambda, with_mu ? d_mu : nullptr, d_istatus,
                      d_ctr + 4 + f, g_border[p].as<int>() + bt.o0, nadj, with_mu ? 1 : 0};
-          k_ros_adj_cell<Warp><<<ablocks, ADJ3_WARPS * 32, adj_smem, ss.sA>>>(rp, aa);
+          if (adj_pair) k_ros_adj_pair<Warp><<<ablocks, ADJP_PAIRS * 64, adjp_smem, ss.sA>>>(rp, aa);
+          else k_ros_adj_cell<Warp><<<ablocks, ADJ3_WARPS * 32, adj_smem, ss.sA>>>(rp, aa);
         }
         CUDA_TRY(cudaGetLastError());
         if (int e = t_end(ss.sA)) return e;

@@ -206,6 +206,17 @@ __device__ __forceinline__ void adj3_lambda_half(const double* __restrict__ MV, 
   }
 }
 
+template <class Model, int HALF, class Priv>
+__device__ __forceinline__ void adj3_mu_half(const double* __restrict__ AP, const double (&x)[32], const Priv& pv) {
+  double mu[16];
+  pv.ld16(TM_MU + 32 * HALF, mu);
+  Model::stoich_cols(x, [&](auto pc, double s) {
+    constexpr int p = decltype(pc)::value;
+    if constexpr (p / 16 == HALF) mu[p - 16 * HALF] = fma(AP[p], s, mu[p - 16 * HALF]);
+  });
+  pv.st16(TM_MU + 32 * HALF, mu);
+}
+
 // one work item: stage `is` of the step whose per-step block is `SB`, stage block `STG`
 template <class Model, class Priv>
 __device__ __forceinline__ void adj3_consume(const RosParams& rp, const double* __restrict__ SB, const double* __restrict__ STG,
@@ -265,14 +276,9 @@ __device__ __forceinline__ void adj3_consume(const RosParams& rp, const double* 
   // the step Lambda += increment (:1324-1339 run after the stage loop).  Two halves of 16 rows bound the register use.
   adj3_lambda_half<Model, 0>(MV, x, v, first, is == 0, pv);
   adj3_lambda_half<Model, 1>(MV, x, v, first, is == 0, pv);
-  if (with_mu) {   // Mu += a_p * (S^T U_i)_p     (:1352-1365)
-    double mu[32];
-    pv.ld32(TM_MU, mu);
-    Model::stoich_cols(x, [&](auto pc, double s) {
-      constexpr int p = decltype(pc)::value;
-      mu[p] = fma(AP[p], s, mu[p]);
-    });
-    pv.st32(TM_MU, mu);
+  if (with_mu) {   // Mu += a_p * (S^T U_i)_p     (:1352-1365); two halves of 16 parameters bound the register use
+    adj3_mu_half<Model, 0>(AP, x, pv);
+    adj3_mu_half<Model, 1>(AP, x, pv);
   }
 }
 
