@@ -145,7 +145,9 @@ __device__ __forceinline__ void adjp_solver(const RosParams& rp, const AdjArgs& 
         }
       }
     }
-    cbm4_cell::lut_solve(SB + FT_HDR, SB + FT_HDR + FT_LU, swaps, x);   // LSS_Solve(Transp, U_i(m)) (:1301-1304)
+    // LSS_Solve(Transp, U_i(m)) (:1301-1304); the dominant interchange outcome has its own (shorter, bit-identical) code
+    if (swaps == cbm4_cell::LUT_DOM_SWAPS) cbm4_cell::lut_solve_dom(SB + FT_HDR, SB + FT_HDR + FT_LU, x);
+    else cbm4_cell::lut_solve(SB + FT_HDR, SB + FT_HDR + FT_LU, swaps, x);
     Model::jt_vec(s.JBUF + (t & 1) * FT_MV, x, v);                       // V_i = J(T_i,Y_i)^T U_i (:1315)
     double* XB = s.XBUF + (t & 1) * ADJP_XB;
 #pragma unroll
@@ -161,34 +163,35 @@ __device__ __forceinline__ void adjp_solver(const RosParams& rp, const AdjArgs& 
 }
 
 // ---- accumulator warp ----------------------------------------------------------------------------------------------
-template <class Model, int HALF>
-__device__ __forceinline__ void adjp_acc_half(const RosParams& rp, const double* __restrict__ MV, const double* __restrict__ XB,
-                                              const double (&u)[32], double inv_dH, int is, bool first, uint32_t tm, int lane) {
-  double v[16];
-#pragma unroll
-  for (int r = 0; r < 16; ++r) v[r] = XB[(32 + 16 * HALF + r) * 32 + lane];
+// Lambda increment and the running sums of one work item (accumulator warp).  One instantiation of the generated sparse
+// rows per kernel: the code of the two warps of a pair has to share the instruction caches of one scheduler.
+template <class Model>
+__device__ __forceinline__ void adjp_accumulate(const RosParams& rp, const double* __restrict__ MV, const double (&u)[32],
+                                                const double* __restrict__ vs, double inv_dH, int is, bool first, uint32_t tm) {
+  // vs: V_i of this lane in the exchange block, row r at vs[r * 32] (read where it is used: u and the 32 sums fill the registers)
   {   // Lambda increment: LACC (+)= V_i + M'^T U_i; at the last stage of the step Lambda += increment   (:1324-1339, :1402)
-    double acc[16];
-    if (!first) tmem::ld16(tm + TM_LACC + 32 * HALF, acc);
+    double acc[32];
     if (first) {
-      Model::mt_rows(MV, u, [&](auto rc, double h) {
-        constexpr int r = decltype(rc)::value;
-        if constexpr (r / 16 == HALF) acc[r - 16 * HALF] = v[r - 16 * HALF] + h;
-      });
-    } else {
-      Model::mt_rows(MV, u, [&](auto rc, double h) {
-        constexpr int r = decltype(rc)::value;
-        if constexpr (r / 16 == HALF) acc[r - 16 * HALF] += v[r - 16 * HALF] + h;
-      });
-    }
-    if (is == 0) {
-      double lam[16];
-      tmem::ld16(tm + TM_LAM + 32 * HALF, lam);
 #pragma unroll
-      for (int r = 0; r < 16; ++r) lam[r] += acc[r];
-      tmem::st16(tm + TM_LAM + 32 * HALF, lam);
+      for (int r = 0; r < 32; ++r) acc[r] = 0.0;
     } else {
-      tmem::st16(tm + TM_LACC + 32 * HALF, acc);
+      tmem::ld32(tm + TM_LACC, acc);
+    }
+    Model::mt_rows(MV, u, [&](auto rc, double h) {
+      constexpr int r = decltype(rc)::value;
+      acc[r] += vs[r * 32] + h;
+    });
+    if (is == 0) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        double lam[16];
+        tmem::ld16(tm + TM_LAM + 32 * c, lam);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) lam[r] += acc[16 * c + r];
+        tmem::st16(tm + TM_LAM + 32 * c, lam);
+      }
+    } else {
+      tmem::st32(tm + TM_LACC, acc);
     }
   }
   // running sums of the earlier stages except the next one (the solver adds that contribution itself):
@@ -196,28 +199,31 @@ __device__ __forceinline__ void adjp_acc_half(const RosParams& rp, const double*
   for (int j = 0; j + 1 < is; ++j) {
     const double ca = rp.A[is * (is - 1) / 2 + j];
     const double cc = rp.C[is * (is - 1) / 2 + j] * inv_dH;
-    double w[16];
-    if (first) {
 #pragma unroll
-      for (int r = 0; r < 16; ++r) w[r] = fma(ca, v[r], cc * u[16 * HALF + r]);
-    } else {
-      tmem::ld16(tm + TM_W + 64 * j + 32 * HALF, w);
+    for (int c = 0; c < 2; ++c) {
+      double w[16];
+      if (first) {
 #pragma unroll
-      for (int r = 0; r < 16; ++r) w[r] += fma(ca, v[r], cc * u[16 * HALF + r]);
+        for (int r = 0; r < 16; ++r) w[r] = 0.0;
+      } else {
+        tmem::ld16(tm + TM_W + 64 * j + 32 * c, w);
+      }
+#pragma unroll
+      for (int r = 0; r < 16; ++r) w[r] += fma(ca, vs[(16 * c + r) * 32], cc * u[16 * c + r]);
+      tmem::st16(tm + TM_W + 64 * j + 32 * c, w);
     }
-    tmem::st16(tm + TM_W + 64 * j + 32 * HALF, w);
   }
 }
 
-template <class Model, int HALF>
-__device__ __forceinline__ void adjp_mu_half(const double* __restrict__ AP, const double (&u)[32], uint32_t tm) {
-  double mu[16];
-  tmem::ld16(tm + TM_MU + 32 * HALF, mu);
+template <class Model>
+__device__ __forceinline__ void adjp_mu(const double* __restrict__ AP, const double (&u)[32], uint32_t tm) {
+  double mu[32];
+  tmem::ld32(tm + TM_MU, mu);
   Model::stoich_cols(u, [&](auto pc, double sp) {
     constexpr int p = decltype(pc)::value;
-    if constexpr (p / 16 == HALF) mu[p - 16 * HALF] = fma(AP[p], sp, mu[p - 16 * HALF]);
+    mu[p] = fma(AP[p], sp, mu[p]);
   });
-  tmem::st16(tm + TM_MU + 32 * HALF, mu);
+  tmem::st32(tm + TM_MU, mu);
 }
 
 template <class Model>
@@ -251,15 +257,13 @@ __device__ __forceinline__ void adjp_accumulator(const RosParams& rp, const AdjA
 #pragma unroll
     for (int r = 0; r < 32; ++r) u[r] = XB[r * 32 + lane];
     tmem::wait_st();                             // this warp's stores of the previous item are in place
-    adjp_acc_half<Model, 0>(rp, MV, XB, u, inv_dH, is, first, tm, lane);
-    adjp_acc_half<Model, 1>(rp, MV, XB, u, inv_dH, is, first, tm, lane);
+    adjp_accumulate<Model>(rp, MV, u, XB + 32 * 32 + lane, inv_dH, is, first, tm);
     tmem::wait_st();
     tmem::fence_before_sync();
     if (is == 0) mbar::arrive(s.lam);            // Lambda of this step is complete
     mbar::arrive(s.bdone + (t & 1));             // XBUF[t&1] consumed, W_j up to date
     if (with_mu) {   // Mu += a_p * (S^T U_i)_p     (:1352-1365)
-      adjp_mu_half<Model, 0>(AP, u, tm);
-      adjp_mu_half<Model, 1>(AP, u, tm);
+      adjp_mu<Model>(AP, u, tm);
     }
   }
   // results: column m of Lambda / Mu is this lane's private vector

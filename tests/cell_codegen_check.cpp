@@ -17,7 +17,7 @@ static double g_rc[81], g_hess[258];
 #define CBM4_CELL_ST4(p, a, b, c, d) do { (p)[0] = (a); (p)[1] = (b); (p)[2] = (c); (p)[3] = (d); } while (0)
 #include "../fatode_b200/csrc/gen/cbm4_cell_gen.h"
 
-static long n_lu = 0, n_lu_bad = 0, n_irregular = 0, n_solve = 0, n_solve_bad = 0, n_swaps[4] = {0, 0, 0, 0};
+static long n_dom = 0, n_lu = 0, n_lu_bad = 0, n_irregular = 0, n_solve = 0, n_solve_bad = 0, n_swaps[4] = {0, 0, 0, 0};
 static double cur_lu[cbm4_cell::NLU];
 static double cur_dinv[32];
 static unsigned cur_swaps = 0;
@@ -94,6 +94,13 @@ static inline int dgetf2(int n, double* a, int* ipiv) {
     for (int i = 0; i < 32; ++i) xr[i] = xn[i] = std::sin(1.0 + i * 0.37 + (double)(n_lu % 97));
     dgetrs_oracle(true, n, a, ipiv, xr);
     lut_solve(cur_lu, dinv, cur_swaps, xn);
+    if (cur_swaps == LUT_DOM_SWAPS) {   // the dominant-outcome code must give the very same bits
+      double xd[32];
+      for (int i = 0; i < 32; ++i) xd[i] = std::sin(1.0 + i * 0.37 + (double)(n_lu % 97));
+      lut_solve_dom(cur_lu, dinv, xd);
+      ++n_dom;
+      for (int i = 0; i < 32; ++i) if (!same(xd[i], xn[i])) { ++n_solve_bad; break; }
+    }
     double sc = 0.0, er = 0.0;
     for (int i = 0; i < 32; ++i) { sc = std::fmax(sc, std::fabs(xr[i])); er = std::fmax(er, std::fabs(xr[i] - xn[i])); }
     max_terr = std::fmax(max_terr, er / sc);
