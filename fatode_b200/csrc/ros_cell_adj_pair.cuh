@@ -163,20 +163,26 @@ __device__ __forceinline__ void adjp_solver(const RosParams& rp, const AdjArgs& 
 }
 
 // ---- accumulator warp ----------------------------------------------------------------------------------------------
+// zero the Lambda increment and the running sums W_0..W_{S-3} of a lane (start of a step)
+__device__ __forceinline__ void adjp_clear_sums(uint32_t tm, int S) {
+  double z[32];
+#pragma unroll
+  for (int r = 0; r < 32; ++r) z[r] = 0.0;
+  tmem::st32(tm + TM_LACC, z);
+  for (int j = 0; j + 2 < S; ++j) tmem::st32(tm + TM_W + 64 * j, z);
+}
+
 // Lambda increment and the running sums of one work item (accumulator warp).  One instantiation of the generated sparse
 // rows per kernel: the code of the two warps of a pair has to share the instruction caches of one scheduler.
 template <class Model>
 __device__ __forceinline__ void adjp_accumulate(const RosParams& rp, const double* __restrict__ MV, const double (&u)[32],
-                                                const double* __restrict__ vs, double inv_dH, int is, bool first, uint32_t tm) {
+                                                const double* __restrict__ vs, double inv_dH, int is, uint32_t tm) {
   // vs: V_i of this lane in the exchange block, row r at vs[r * 32] (read where it is used: u and the 32 sums fill the registers)
-  {   // Lambda increment: LACC (+)= V_i + M'^T U_i; at the last stage of the step Lambda += increment   (:1324-1339, :1402)
+  {   // Lambda increment: LACC += V_i + M'^T U_i; at the last stage of the step Lambda += increment   (:1324-1339, :1402)
+    // No first-stage special case: LACC and the W_j are ZERO when a step begins (cleared below and at ADJINIT with
+    // register-free stores of RZ), so every item runs the same straight-line code.
     double acc[32];
-    if (first) {
-#pragma unroll
-      for (int r = 0; r < 32; ++r) acc[r] = 0.0;
-    } else {
-      tmem::ld32(tm + TM_LACC, acc);
-    }
+    tmem::ld32(tm + TM_LACC, acc);
     Model::mt_rows(MV, u, [&](auto rc, double h) {
       constexpr int r = decltype(rc)::value;
       acc[r] += vs[r * 32] + h;
@@ -190,24 +196,20 @@ __device__ __forceinline__ void adjp_accumulate(const RosParams& rp, const doubl
         for (int r = 0; r < 16; ++r) lam[r] += acc[16 * c + r];
         tmem::st16(tm + TM_LAM + 32 * c, lam);
       }
+      adjp_clear_sums(tm, rp.S);
     } else {
       tmem::st32(tm + TM_LACC, acc);
     }
   }
   // running sums of the earlier stages except the next one (the solver adds that contribution itself):
-  // W_j (+)= a_ij V_i + c_ij/h U_i, j < i - 1     (:1292-1300)
+  // W_j += a_ij V_i + c_ij/h U_i, j < i - 1     (:1292-1300)
   for (int j = 0; j + 1 < is; ++j) {
     const double ca = rp.A[is * (is - 1) / 2 + j];
     const double cc = rp.C[is * (is - 1) / 2 + j] * inv_dH;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       double w[16];
-      if (first) {
-#pragma unroll
-        for (int r = 0; r < 16; ++r) w[r] = 0.0;
-      } else {
-        tmem::ld16(tm + TM_W + 64 * j + 32 * c, w);
-      }
+      tmem::ld16(tm + TM_W + 64 * j + 32 * c, w);
 #pragma unroll
       for (int r = 0; r < 16; ++r) w[r] += fma(ca, vs[(16 * c + r) * 32], cc * u[16 * c + r]);
       tmem::st16(tm + TM_W + 64 * j + 32 * c, w);
@@ -252,12 +254,11 @@ __device__ __forceinline__ void adjp_accumulator(const RosParams& rp, const AdjA
     const double* MV = s.MBUF + (t & 1) * FT_MAP;
     const double* AP = MV + (FT_AP - FT_MV);
     const double inv_dH = XB[64 * 32];
-    const bool first = (is == S - 1);
     double u[32];
 #pragma unroll
     for (int r = 0; r < 32; ++r) u[r] = XB[r * 32 + lane];
     tmem::wait_st();                             // this warp's stores of the previous item are in place
-    adjp_accumulate<Model>(rp, MV, u, XB + 32 * 32 + lane, inv_dH, is, first, tm);
+    adjp_accumulate<Model>(rp, MV, u, XB + 32 * 32 + lane, inv_dH, is, tm);
     tmem::wait_st();
     tmem::fence_before_sync();
     if (is == 0) mbar::arrive(s.lam);            // Lambda of this step is complete
@@ -335,6 +336,7 @@ k_ros_adj_pair(RosParams rp, AdjArgs a) {
       for (int p = 0; p < 32; ++p) m0[p] = 0.0;
       tmem::st32(tm + TM_LAM, lam);
       tmem::st32(tm + TM_MU, m0);
+      adjp_clear_sums(tm, rp.S);
       tmem::wait_st();
       tmem::fence_before_sync();
     }
