@@ -14,7 +14,7 @@ BASELINE.json is processed in waves of ~8.3 k cells whatever the batch size, so 
   value : cells/s with y0 and all outputs resident in HBM (device pointers through the C ABI)
   e2e   : cells/s through the same C-ABI call with pinned HOST buffers (H2D of y0, D2H of y, Lambda,
           Mu, ISTATUS, RSTATUS, IERR inside the timed region)
-  roofline    : dominant kernel (k_ros_adj_cell, the backward sweep): ALGORITHMIC FP64 flops of SURVEY.md 8d (the dense
+  roofline    : dominant kernel (k_ros_adj_pair, the backward sweep): ALGORITHMIC FP64 flops of SURVEY.md 8d (the dense
                 FULL_ALGEBRA count, evaluated on the returned counters) / its CUDA-event time, against the DFMA peak
                 measured on this GPU in this run (MEASURED_PEAKS.json has no FP64 figure); the same for the forward
                 kernel; EXECUTED fractions (the kernels run the sparse patterns) only from an ncu capture of the very
@@ -637,13 +637,13 @@ def main():
         acc_t, att_t, ms_adj_t, ms_fwd_t, ms_tape_t, n_adj_t, general_t = [float(x) for x in tot.tolist()]
         f_adj = acc_t * flops_adjoint_per_step()
         f_fwd = flops_forward(att_t, acc_t)
-        # dominant kernel: k_ros_adj_cell; per-rank kernel time = sum of its launches on that rank (ranks run concurrently)
+        # dominant kernel: k_ros_adj_pair; per-rank kernel time = sum of its launches on that rank (ranks run concurrently)
         adj_s = ms_adj_t / world * 1e-3
         fwd_s = ms_fwd_t / world * 1e-3
         adj_tflops = f_adj / adj_s / 1e12
         peak = fp64_peak * world
         ex = executed_counts()       # ncu-measured executed FP64 work per unit, only if captured from THIS binary
-        roof = {"bound": "fp64", "kernel": "k_ros_adj_cell<Cbm4Warp> (discrete adjoint sweep, lane = adjoint column)",
+        roof = {"bound": "fp64", "kernel": "k_ros_adj_pair<Cbm4Warp> (discrete adjoint sweep: solver + accumulator warp per cell, lane = adjoint column)",
                 "achieved": adj_tflops, "peak": peak, "unit": "TFLOP/s", "frac": adj_tflops / peak,
                 "achieved_is": "ALGORITHMIC flops (SURVEY.md 8d: the dense FULL_ALGEBRA count of the reference, evaluated on the "
                                "returned counters) / CUDA-event time of the kernel's launches in this run; the kernel executes "

@@ -148,7 +148,7 @@ __device__ __forceinline__ void adjp_solver(const RosParams& rp, const AdjArgs& 
     // LSS_Solve(Transp, U_i(m)) (:1301-1304); the dominant interchange outcome has its own (shorter, bit-identical) code
     if (swaps == cbm4_cell::LUT_DOM_SWAPS) cbm4_cell::lut_solve_dom(SB + FT_HDR, SB + FT_HDR + FT_LU, x);
     else cbm4_cell::lut_solve(SB + FT_HDR, SB + FT_HDR + FT_LU, swaps, x);
-    Model::jt_vec(s.JBUF + (t & 1) * FT_MV, x, v);                       // V_i = J(T_i,Y_i)^T U_i (:1315)
+    Model::jt_vec1(s.JBUF + (t & 1) * FT_MV, x, v);                       // V_i = J(T_i,Y_i)^T U_i (:1315)
     double* XB = s.XBUF + (t & 1) * ADJP_XB;
 #pragma unroll
     for (int r = 0; r < 32; ++r) { XB[r * 32 + lane] = x[r]; XB[(32 + r) * 32 + lane] = v[r]; }
@@ -211,7 +211,7 @@ __device__ __forceinline__ void adjp_accumulate(const RosParams& rp, const doubl
       double w[16];
       tmem::ld16(tm + TM_W + 64 * j + 32 * c, w);
 #pragma unroll
-      for (int r = 0; r < 16; ++r) w[r] += fma(ca, vs[(16 * c + r) * 32], cc * u[16 * c + r]);
+      for (int r = 0; r < 16; ++r) w[r] = fma(ca, vs[(16 * c + r) * 32], fma(cc, u[16 * c + r], w[r]));
       tmem::st16(tm + TM_W + 64 * j + 32 * c, w);
     }
   }

@@ -468,6 +468,41 @@ def main():
             w(f"    a{t % 2} = fma(Mv[{e}], x[{k}], a{t % 2});")
         w(f"    f(IC<{r}>(), a0 + a1); }}")
     w("}")
+    # ---- variants for the two-warps-per-cell backward sweep (ros_cell_adj_pair.cuh): fewer instructions per row
+    w("// v = J^T x with one product + multiply-add chain per row (no 0.0 seeds, no final add of partial sums)")
+    w("__device__ __forceinline__ void jt_vec1(const double* __restrict__ Jv, const double (&x)[32], double (&v)[32]) {")
+    je = 0
+    for r in range(N):
+        terms = []
+        while je < NJ and jent[je][1] == r:
+            terms.append((je, jent[je][0]))
+            je += 1
+        assert terms
+        if len(terms) <= 4:
+            (e0, k0) = terms[0]
+            expr = f"Jv[{e0}] * x[{k0}]"
+            for (e, k) in terms[1:]:
+                expr = f"fma(Jv[{e}], x[{k}], {expr})"
+            w(f"  v[{r}] = {expr};")
+        else:   # long rows: two chains seeded with products
+            w(f"  {{ double a0 = Jv[{terms[0][0]}] * x[{terms[0][1]}], a1 = Jv[{terms[1][0]}] * x[{terms[1][1]}];")
+            for t, (e, k) in enumerate(terms[2:]):
+                w(f"    a{t % 2} = fma(Jv[{e}], x[{k}], a{t % 2});")
+            w(f"    v[{r}] = a0 + a1; }}")
+    w("}")
+    w("// acc[r] += vs[r * 32] + (M'^T x)_r: the running sum and the V_i entry seed the two multiply-add chains of the row")
+    w("__device__ __forceinline__ void mt_rows_acc(const double* __restrict__ Mv, const double (&x)[32], const double* __restrict__ vs, double (&acc)[32]) {")
+    me = 0
+    for r in range(N):
+        terms = []
+        while me < NM and mpat[me][1] == r:
+            terms.append((me, mpat[me][0]))
+            me += 1
+        w(f"  {{ double a0 = acc[{r}], a1 = vs[{r} * 32];")
+        for t, (e, k) in enumerate(terms):
+            w(f"    a{t % 2} = fma(Mv[{e}], x[{k}], a{t % 2});")
+        w(f"    acc[{r}] = a0 + a1; }}")
+    w("}")
     w("// s_p = sum_r STOICM(r, JCOEFF[p]) * x_r  (column p of the stoichiometric matrix; REAL(4) literals)")
     w("template <class F> __device__ __forceinline__ void stoich_cols(const double (&x)[32], F&& f) {")
     nst = 0

@@ -28,7 +28,7 @@ def num(r, key):
 agg = {}
 for r in rows[2:]:
     k = r[hdr["Kernel Name"]]
-    key = "forward" if "k_ros_fwd_cell" in k else "expand" if "k_expand_tape" in k else "adjoint" if "k_ros_adj_cell" in k else None
+    key = "forward" if "k_ros_fwd_cell" in k else "expand" if "k_expand_tape" in k else "adjoint" if "k_ros_adj_" in k else None
     if key is None:
         continue
     a = agg.setdefault(key, dict(kernel=k.split("(")[0], launches=0, dfma=0.0, dmul=0.0, dadd=0.0, dram=0.0, ns=0.0, inst=0.0))
