@@ -504,14 +504,6 @@ def main():
     for a in body("Hessian"):
         w(f"  {ref(a.lhs.name, a.lhs.idx)} = {fx.emit_c(a.rhs, ref)};")
     w("}")
-    w("// the 59 second derivatives of the reaction rates alone (the D2A temporaries of Hessian): per-call constants of this")
-    w("// at most bimolecular mechanism; the two-warps-per-cell backward sweep applies (Hess x K)^T U reaction by reaction")
-    w("template <int SV> CBM4_CELL_FN void d2a_values(const double* __restrict__ V, const double F, const double* __restrict__ PH, "
-      "double* __restrict__ D2A) {")
-    for a in body("Hessian"):
-        if a.lhs.name == "D2A":
-            w(f"  {ref(a.lhs.name, a.lhs.idx)} = {fx.emit_c(a.rhs, ref)};")
-    w("}")
     w("// M'[e] = sum_t HESS[h]*K[c] (CBM4_HessTR_Vec :1869-2023 regrouped as the sparse matrix (Hess x K))")
     w("//         + hg * dJdt[n] on the time-dependent Jacobian entries; entry order = cbm4_dev's MV order.")
     w("// CBM-IV is at most bimolecular: HESS depends on the rate coefficients only (no V, no SUN), i.e. it is a per-call")

@@ -503,57 +503,6 @@ def main():
             w(f"    a{t % 2} = fma(Mv[{e}], x[{k}], a{t % 2});")
         w(f"    acc[{r}] = a0 + a1; }}")
     w("}")
-    # (Hess x K)^T u reaction by reaction: HESS(h) = sum coef * D2A(d) and HessTR_Vec's terms HESS(h) U1(k) U2(c) -> HTU(r) group, for
-    # every second derivative d, into  D2A(d) * (sum_k coef_k u_k) * K_c  added to row r: the inner sum is the stoichiometric
-    # column of the reaction applied to u, shared by all (r, c) of that reaction
-    import collections
-    grp = collections.defaultdict(lambda: collections.defaultdict(float))
-    for (k, r), lst in M.items():
-        for (h, c) in lst:
-            for (coef, d) in HE[h]:
-                grp[(d, r, c)][k] += coef
-    byd = collections.defaultdict(list)
-    for (d, r, c), vec in sorted(grp.items()):
-        byd[d].append((r, c, dict(vec)))
-    w("// acc += (Hess x K)^T u, one block per second derivative D2A(d) = d2a(IC<d>()) of a reaction rate (HessTR_Vec :1869-2023")
-    w("// regrouped: s = stoichiometric column of the reaction applied to u, then acc[r] += D2A(d) * s * K[c])")
-    w("template <class D2> __device__ __forceinline__ void hessk_acc(D2&& d2a, const double (&K)[32], const double (&u)[32], double (&acc)[32]) {")
-    n_add = n_fma = 0
-    for d, lst in sorted(byd.items()):
-        base = lst[0][2]
-        ks = sorted(base)
-        w("  {")
-        first = True
-        for k in ks:
-            cf = base[k]
-            if first:
-                w(f"    double s = {'u[%d]' % k if cf == 1.0 else ('-u[%d]' % k if cf == -1.0 else '%s * u[%d]' % (fx.c_double(cf), k))};")
-                first = False
-            elif cf == 1.0:
-                w(f"    s = s + u[{k}];")
-            elif cf == -1.0:
-                w(f"    s = s - u[{k}];")
-            else:
-                w(f"    s = fma({fx.c_double(cf)}, u[{k}], s);")
-            n_add += 1
-        w(f"    const double w = d2a(IC<{d}>()) * s;")
-        for (r, c, vec) in lst:
-            assert sorted(vec) == ks
-            ratio = {vec[k] / base[k] for k in ks}
-            assert len(ratio) == 1
-            ratio = ratio.pop()
-            wx = "w" if ratio == 1.0 else f"({fx.c_double(ratio)} * w)"
-            w(f"    acc[{r}] = fma({wx}, K[{c}], acc[{r}]);")
-            n_fma += 1
-        w("  }")
-    w("}")
-    w(f"constexpr int HESSK_ADDS = {n_add}, HESSK_FMAS = {n_fma}, ND2A = {len(D2A)};")
-    w("// acc += (hg * dJ/dt)^T u on the NJT time-dependent Jacobian entries; Gdj[n] = hg * d/dt of entry JAC_TIME[n]")
-    w("__device__ __forceinline__ void djt_acc(const double* __restrict__ Gdj, const double (&u)[32], double (&acc)[32]) {")
-    for n, i in enumerate(jtime):
-        (rj, cj) = jent[i]
-        w(f"  acc[{cj}] = fma(Gdj[{n}], u[{rj}], acc[{cj}]);")
-    w("}")
     w("// s_p = sum_r STOICM(r, JCOEFF[p]) * x_r  (column p of the stoichiometric matrix; REAL(4) literals)")
     w("template <class F> __device__ __forceinline__ void stoich_cols(const double (&x)[32], F&& f) {")
     nst = 0
