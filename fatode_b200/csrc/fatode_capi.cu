@@ -40,6 +40,7 @@
 #include "rk_cell_adj.cuh"
 #include "sdirk_dense_sens.cuh"
 #include "rk_dense_adj.cuh"
+#include "rk_big_adj.cuh"
 #include "units_internal.h"
 
 using namespace fatode;
@@ -1567,6 +1568,7 @@ __global__ void k_rk_gather_status(int n, const int* __restrict__ ids, const int
 }
 
 // One group of systems (ids) through forward + backward.  Systems that overflow their tape slot are appended to `overflow`.
+static thread_local bool g_rk_adj_direct = false;   // ICNTRL(7) = 2 of the current call: one 3N x 3N factorisation per step (rk_big_adj.cuh)
 static int rk_adj_group(const RkParams& rp, const Cbm4Const& mc, const std::vector<int>& ids, int cap, int nadj, bool with_mu,
                         int np, bool do_adjoint, size_t fat_budget, double* d_y, double* d_lam, double* d_mu, const double* d_atol,
                         const double* d_rtol, int* d_ist, double* d_rst, int* d_ierr, cudaStream_t st, int sms,
@@ -1631,7 +1633,12 @@ static int rk_adj_group(const RkParams& rp, const Cbm4Const& mc, const std::vect
     // with two one-warp CTAs per SM); general-pivoting pass: shared-memory variant with dense factors, one warp per SM
     static const bool use_tm = !(getenv("FATODE_RK_ADJ_SMEM") && atoi(getenv("FATODE_RK_ADJ_SMEM")) != 0);
     tm.start();
-    if (!dense && use_tm) {
+    if (g_rk_adj_direct) {
+      CUDA_TRY(cudaFuncSetAttribute(k_rk_adj_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RK_ADJ_BIG_SMEM));
+      const RkBigRecord rl = dense ? RkBigRecord{DR_REC, DR_J} : RkBigRecord{RA_REC, RA_J};
+      const unsigned ablocks = (unsigned)std::min<int>(nb, 2 * sms);
+      k_rk_adj_big<<<ablocks, RB_THREADS, RK_ADJ_BIG_SMEM, st>>>(rp, aa, rl);
+    } else if (!dense && use_tm) {
       CUDA_TRY(cudaFuncSetAttribute(k_rk_adj_cell_tm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RK_ADJ_TM_SMEM));
       const unsigned ablocks = (unsigned)std::min<int>((nb + RA_TM_WARPS - 1) / RA_TM_WARPS, sms);
       k_rk_adj_cell_tm<<<ablocks, RA_TM_WARPS * 32, RK_ADJ_TM_SMEM, st>>>(rp, aa);
@@ -1745,9 +1752,10 @@ extern "C" int fatode_rk_integrate_adj_batch(int model, int64_t ncells, int nvar
   const int perr = rk_parse_options(nvar, icntrl_u, rcntrl_u, tin, tout, atol, rtol, rp, &ao);
   if (perr < 0) return broadcast_ierr(ncells, perr, istatus, rstatus, ierr, mem, st);
   const bool do_adjoint = (ao.type == 0 || ao.type == 2);
-  if (do_adjoint && ao.solve >= 2)
-    return fail(FATODE_EUNSUPPORTED, "RK_ADJ direct / adaptive adjoint solves (ICNTRL(7) = 2, 3: 3N x 3N factorisation) are not built; "
-                                     "use the preset fixed-sweep solve");
+  if (do_adjoint && ao.solve >= 3)
+    return fail(FATODE_EUNSUPPORTED, "RK_ADJ adaptive adjoint solve (ICNTRL(7) = 3) is not built; use the preset fixed-sweep solve or "
+                                     "the direct solve (ICNTRL(7) = 2)");
+  g_rk_adj_direct = do_adjoint && ao.solve == 2;
   const bool with_mu = np > 0 && mu != nullptr;
   Cbm4Const mc;
   cbm4_constants(model_params, mc);

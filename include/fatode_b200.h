@@ -213,8 +213,10 @@ int fatode_rk_integrate_batch(int model, int64_t ncells, int nvar, double* y, do
  * 4 Radau-1A) with the presets of the reference (ICNTRL(5) = 8, (7) = 1 fixed-sweep adjoint solve, (9) = 2 discrete,
  * (10) = 1 SDIRK error estimator, (11) = 1 classic controller, Max_no_steps = 10000); ICNTRL(9) = 1: forward sweep only.
  * Same argument layout as fatode_ros_integrate_adj_batch; ADJINIT of the example drivers (Lambda = I, Mu = 0) is applied
- * after the forward sweep, systems whose forward sweep fails keep the caller's Lambda/Mu.  cbm4 only.  The direct and the
- * adaptive adjoint solves (ICNTRL(7) = 2, 3) and the quadrature terms return FATODE_EUNSUPPORTED.  Per-cell IERR: 1, or
+ * after the forward sweep, systems whose forward sweep fails keep the caller's Lambda/Mu.  cbm4 only.  ICNTRL(7) = 2 selects
+ * the direct adjoint solve (LSS_Decomp_Big / LSS_Solve_Big, ADJ/RK_ADJ/LS_Solver.F90:59-80,115-124: one factorisation of the
+ * 3N x 3N system per accepted step, one DGETRS('T') per column; block-cooperative 96 x 96 LU on the GPU).  The adaptive
+ * adjoint solve (ICNTRL(7) = 3) and the quadrature terms return FATODE_EUNSUPPORTED.  Per-cell IERR: 1, or
  * the reference's -1..-13.  Systems whose real or complex factorisations leave the static pivot pattern (none at rtol 1e-6,
  * all at rtol >= 1e-4) are integrated a second time with general partial pivoting (fatode_stats.cells_general counts them);
  * the forward sweep, the counters and Lambda are bit-identical to the reference's operation order on both paths. */

@@ -13,8 +13,9 @@
 //                                          lapack_solve_cmp :95-113 (ZGETRS 'n'/'t' — plain transpose),
 //                                          lss_jac1..3 :704-720, lss_mul_jactr1..3 :835-848
 // Built: the discrete adjoint with the fixed number of transposed simplified-Newton sweeps (ICNTRL(7) = 0/1, the preset
-// and what cbm4_rk_adj_dr.F90 runs) and ICNTRL(9) = 1 (forward only).  The direct / adaptive solves (ICNTRL(7) = 2, 3:
-// one blocked DGETRF of the 3N x 3N system) and the quadrature terms are not restated: rk_adj_integrate returns -100.
+// and what cbm4_rk_adj_dr.F90 runs), ICNTRL(9) = 1 (forward only), and the direct solve (ICNTRL(7) = 2: lapack_decomp_big /
+// lapack_solve_big :59-80,115-124, one DGETRF of the 3N x 3N system per step and one DGETRS('T') per column).  The adaptive
+// solve (ICNTRL(7) = 3) and the quadrature terms are not restated: rk_adj_integrate returns -100.
 // Differences from FWD/RK's forward sweep that matter for ISTATUS: no FUN(T,Y) at the top of the time loop; the SDIRK
 // error stage evaluates and counts its own FUN(T,Y); ICNTRL(11) is preset to 1, i.e. the classic controller; default
 // Max_no_steps = 10000 (= tape capacity); no Lobatto-3A.
@@ -32,7 +33,9 @@ struct RungeKuttaAdj : RungeKutta<Model> {
   using Base::cfg; using Base::ISTATUS; using Base::RSTATUS; using Base::lss; using Base::mdl; using Base::e2; using Base::ip2;
   struct TapeEntry { double T, H, Y[N], Z[3 * N]; int NewIt; };
   std::vector<TapeEntry> tape;            // chk_T, chk_H, chk_Y, chk_Z, chk_NiT
-  std::vector<double> fjac1, fjac2, fjac3;
+  std::vector<double> fjac1, fjac2, fjac3, e_big;
+  std::vector<int> ip_big;
+  bool direct_solve = false;               // AdjointSolve == Solve_direct (ICNTRL(7) = 2): one 3N x 3N factorisation per step
   explicit RungeKuttaAdj(Model& m) : Base(m), fjac1(N * N, 0.0), fjac2(N * N, 0.0), fjac3(N * N, 0.0) {}
 
   // RK_PrepareRHS :1707-1739 (no F0 argument, no Lobatto-3A)
@@ -281,12 +284,51 @@ struct RungeKuttaAdj : RungeKutta<Model> {
       if (NP > 0) mdl.jacp(T + tb.C[3] * H, TMP, FPJAC3.data());
       const double* FJ[3] = {fjac1.data(), fjac2.data(), fjac3.data()};
       const double* FP[3] = {FPJAC1.data(), FPJAC2.data(), FPJAC3.data()};
+      if (direct_solve) {   // LSS_Decomp_Big -> lapack_decomp_big (ADJ/RK_ADJ/LS_Solver.F90:59-80); its ISING is never looked at (:1330)
+        constexpr int NB = 3 * N;
+        e_big.resize((size_t)NB * NB);
+        ip_big.resize(NB);
+        for (int j = 0; j < N; ++j)
+          for (int i = 0; i < N; ++i)
+            for (int b = 0; b < 3; ++b)
+              for (int a = 0; a < 3; ++a)
+                e_big[(size_t)(a * N + i) + (size_t)NB * (b * N + j)] = -H * tb.A[a + 1][b + 1] * FJ[b][i + N * j];
+        for (int i = 0; i < NB; ++i) e_big[(size_t)i + (size_t)NB * i] = e_big[(size_t)i + (size_t)NB * i] + 1;
+        dgetf2(NB, e_big.data(), ip_big.data());   // DGETRF: blocked (NB = 64 < 96) in netlib, same operations per element in the same order
+        ISTATUS[Ndec]++;
+      }
       for (int iadj = 0; iadj < NADJ; ++iadj) {
         double* lam = Lambda + (size_t)iadj * N;
         for (int i = 0; i < N; ++i) { U1[i] = 0.0; U2[i] = 0.0; U3[i] = 0.0; G1[i] = 0.0; G2[i] = 0.0; G3[i] = 0.0; }
         mul_jactr(fjac1.data(), TMP, lam); axpy(N, -H * tb.B[1], TMP, G1);
         mul_jactr(fjac2.data(), TMP, lam); axpy(N, -H * tb.B[2], TMP, G2);
         mul_jactr(fjac3.data(), TMP, lam); axpy(N, -H * tb.B[3], TMP, G3);
+        if (direct_solve) {   // :1466-1499: X = -G, one transposed solve with the big factors, U_s = X_s
+          double X[3 * N];
+          for (int i = 0; i < N; ++i) { X[i] = -G1[i]; X[N + i] = -G2[i]; X[2 * N + i] = -G3[i]; }
+          dgetrs(true, 3 * N, e_big.data(), ip_big.data(), X);
+          ISTATUS[Nsol]++;
+          const double* Xs[3] = {X, X + N, X + 2 * N};
+          if (NP > 0 && Mu) {
+            double* mu = Mu + (size_t)iadj * NP;
+            double* V[3] = {V1.data(), V2.data(), V3.data()};
+            for (int s = 1; s <= 3; ++s) {
+              for (int i = 0; i < N; ++i) TMP[i] = 0.0;
+              axpy(N, H * tb.A[1][s], Xs[0], TMP); axpy(N, H * tb.A[2][s], Xs[1], TMP); axpy(N, H * tb.A[3][s], Xs[2], TMP);
+              axpy(N, H * tb.B[s], lam, TMP);
+              for (int j = 0; j < NP; ++j) {
+                double t = 0.0;
+                for (int i = 0; i < N; ++i) t = t + FP[s - 1][i + (size_t)N * j] * TMP[i];
+                V[s - 1][j] = 1.0 * t;
+              }
+            }
+            for (int i = 0; i < N; ++i) lam[i] = lam[i] + Xs[0][i] + Xs[1][i] + Xs[2][i];
+            for (int j = 0; j < NP; ++j) mu[j] = mu[j] + V1[j] + V2[j] + V3[j];
+          } else {
+            for (int i = 0; i < N; ++i) lam[i] = lam[i] + Xs[0][i] + Xs[1][i] + Xs[2][i];
+          }
+          continue;
+        }
         for (int NewtonIter = 1; NewtonIter <= NewtonMaxit; ++NewtonIter) {
           // RK_PrepareRHS_Adj :1742-1784
           double* U[3] = {U1, U2, U3};
@@ -358,7 +400,8 @@ int rk_adj_integrate(Model& mdl, int NP, int NADJ, double* Y, double* Lambda, do
   else if (ICNTRL[8] == 1) discrete = false;            // ICNTRL(9) = 1: no adjoint
   else if (ICNTRL[8] != 0 && ICNTRL[8] != 2) IERR = -9;
   const bool with_mu = (NP > 0 && Mu != nullptr);
-  if (IERR >= 0 && discrete && ICNTRL[6] >= 2) IERR = -100;   // direct / adaptive adjoint solves: not restated
+  s.direct_solve = (ICNTRL[6] == 2);                       // Solve_direct (:458-459)
+  if (IERR >= 0 && discrete && ICNTRL[6] == 3) IERR = -100;   // adaptive adjoint solve: not restated
   if (IERR >= 0) {
     IERR = s.fwd_integrate(Y, TIN, TOUT, ATOL, RTOL, discrete);
     if (IERR >= 0) {

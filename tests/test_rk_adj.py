@@ -70,7 +70,7 @@ def test_oracle_options():
     rtol, atol = driver_tols()
     y0 = O.initial_state("cbm4")
     ic = radau()
-    ic[6] = 2                                     # direct 3N x 3N solve: not restated
+    ic[6] = 3                                     # adaptive adjoint solve: not restated
     assert O.rk_adj("cbm4", y0, 2, T0, T0 + 600.0, atol, rtol, ic)["ierr"][0] == -100
     ic = radau()
     ic[2] = 5                                     # no Lobatto-3A in RK_ADJ
@@ -78,6 +78,51 @@ def test_oracle_options():
     ic = radau()
     ic[8] = 3                                     # continuous adjoints are not implemented upstream either
     assert O.rk_adj("cbm4", y0, 2, T0, T0 + 600.0, atol, rtol, ic)["ierr"][0] == -9
+
+
+def test_oracle_direct_adjoint_solve_agrees_with_the_fixed_sweeps():
+    """ICNTRL(7) = 2 (lapack_decomp_big / lapack_solve_big: one 3N x 3N DGETRF per step, one DGETRS('T') per column) and the
+    preset fixed number of transposed Newton sweeps solve the same linear systems: two independent code paths of the
+    restatement agree to the sweeps' convergence level; the counters follow ADJ/RK_ADJ :1331, :1472."""
+    rtol, atol = driver_tols()
+    y0 = O.initial_state("cbm4")
+    t1 = T0 + 6 * 3600.0
+    fx = O.rk_adj("cbm4", y0, 32, T0, t1, atol, rtol, radau(), nthreads=1)
+    ic = radau()
+    ic[6] = 2
+    dr = O.rk_adj("cbm4", y0, 32, T0, t1, atol, rtol, ic, nthreads=1)
+    assert dr["ierr"][0] == 1 and np.array_equal(dr["y"], fx["y"])
+    sc = np.max(np.abs(fx["lambda_"][0]))
+    assert np.max(np.abs(dr["lambda_"][0] - fx["lambda_"][0])) <= 1e-8 * sc            # observed 1.9e-10
+    assert np.max(np.abs(dr["mu"][0] - fx["mu"][0])) <= 1e-8 * np.max(np.abs(fx["mu"][0]))
+    A = fx["istatus"][0][3]
+    assert dr["istatus"][0][5] == fx["istatus"][0][5] + A                             # one more decomposition per step
+    fwd_ic = radau()
+    fwd_ic[8] = 1
+    fwd = O.rk_adj("cbm4", y0, 32, T0, t1, atol, rtol, fwd_ic, nthreads=1)
+    assert dr["istatus"][0][6] == fwd["istatus"][0][6] + 32 * A                       # one big solve per column and step
+
+
+@pytest.mark.gpu
+def test_rk_adj_direct_solve_matches_oracle():
+    """ICNTRL(7) = 2 on the GPU (k_rk_adj_big: block-cooperative 96 x 96 DGETF2 + DGETRS('T') per column): state, counters and
+    Lambda bit-identical to the restatement, Mu to rounding; static-pattern and general-pivoting records."""
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    from test_ros_adj_gpu import check_against_oracle
+    y0 = perturbed_states(F.initial_state("cbm4"), 12)
+    t1 = T0 + 10 * 3600.0
+    for (rt, at, nadj, with_mu) in ((1.0e-5, 1.0e-7, 32, True), (1.0e-5, 1.0e-7, 5, False), (1.0e-3, 1.0e-5, 32, True)):
+        rtol, atol = np.full(32, F01 * rt), np.full(32, F01 * at)
+        ic = radau()
+        ic[6] = 2
+        res = F.integrate_adj("cbm4", T0, t1, y0, nadj, rtol, atol, icntrl_u=ic, want_mu=with_mu, family="rk")
+        ref = O.rk_adj("cbm4", y0, nadj, T0, t1, atol, rtol, ic, with_mu=with_mu)
+        assert (res.ierr == 1).all() and np.array_equal(res.y, ref["y"])
+        assert np.array_equal(res.istatus, ref["istatus"]) and np.array_equal(res.rstatus, ref["rstatus"])
+        assert np.array_equal(res.lambda_, ref["lambda_"]), "same operations in the same order as DGETF2 / DGETRS('T')"
+        check_against_oracle(res, ref, nadj)
+    assert F.last_stats().cells_general > 0          # the loose-tolerance case went through the dense preparation records
 
 
 @pytest.mark.gpu
@@ -129,7 +174,7 @@ def test_rk_adj_variants():
     ref = O.rk_adj("cbm4", y0, 4, T0, T1, atol, rtol, ic)
     assert np.array_equal(res.ierr, ref["ierr"]) and (res.ierr == -9).all()
     ic = radau()
-    ic[6] = 2
+    ic[6] = 3                                                     # adaptive adjoint solve: not built
     with pytest.raises(Exception):
         F.integrate_adj("cbm4", T0, t1, y0, 4, rtol, atol, icntrl_u=ic, family="rk")
 
