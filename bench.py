@@ -253,7 +253,8 @@ def workload_config(cells, ngpus, note=None):
     return c
 
 
-SIDE_DEFAULT_CELLS = {"small_strato_fwd": 1 << 20, "cbm4_ros_tlm": 32768, "cbm4_rk_adj": 9472, "cbm4_sdirk_adj": 9472,
+SIDE_DEFAULT_CELLS = {"small_strato_fwd": 1 << 20, "cbm4_ros_tlm": 32768, "cbm4_rk_adj": 9472, "cbm4_rk_adj_direct": 9472,
+                      "cbm4_rk_adj_rtol1e-5": 4736, "cbm4_rk_adj_rtol1e-4": 4736, "cbm4_sdirk_adj": 9472,
                       "cbm4_sdirk_tlm": 9472, "swe_erk": 65536, "swe_erk_tlm": 16384, "cbm4_rk": 18944, "cbm4_sdirk": 18944}
 
 
@@ -306,17 +307,29 @@ def side_measure(w, nc, steps, warmup, fp64_peak=None, hbm_peak=None):
         desc = "EXAMPLES/cbm4 TLM/ROS_TLM: Rodas4, NTLM=32, Y_tlm(t0)=I, ICNTRL(12)=0, 12h..84h, driver tolerances of ROS_ADJ"
         ncpu = 32
         flops = lambda r: dense_flops_from_counters(r.istatus, 32, 573, 636, sens_cols=32)
-    elif w == "cbm4_rk_adj":
-        rtol, atol = np.full(N, F01 * 1.0e-5), np.full(N, F01 * 1.0e-7)
+    elif w in ("cbm4_rk_adj", "cbm4_rk_adj_direct", "cbm4_rk_adj_rtol1e-5", "cbm4_rk_adj_rtol1e-4"):
+        # the two looser-tolerance variants measure the general-pivoting second pass (systems that leave the static pivot
+        # pattern are integrated again from t0 with dense factors): rtol 0.1f*1e-4 -> about half of the systems, 0.1f*1e-3 -> all
+        scale = {"cbm4_rk_adj_rtol1e-5": 10.0, "cbm4_rk_adj_rtol1e-4": 100.0}.get(w, 1.0)
+        rtol, atol = np.full(N, F01 * 1.0e-5 * scale), np.full(N, F01 * 1.0e-7 * scale)
         ic = np.zeros(20, dtype=np.int32)
         ic[2] = 1
+        if w == "cbm4_rk_adj_direct":
+            ic[6] = 2                           # LSS_Decomp_Big / LSS_Solve_Big: one 96 x 96 factorisation per accepted step
         y0 = perturbed_states(F.initial_state("cbm4"), nc)
         run = lambda y: F.integrate_adj("cbm4", T0, T1, y, 32, rtol, atol, icntrl_u=ic, family="rk")
         cpu = lambda y: O.rk_adj("cbm4", y, 32, T0, T1, atol, rtol, ic)
-        desc = ("EXAMPLES/cbm4 ADJ/RK_ADJ: Radau-2A (ICNTRL(3)=1), NADJ=32, NP=29, fixed-sweep discrete adjoint, 12h..84h, "
-                "rtol 0.1f*1e-5, atol 0.1f*1e-7 (cbm4_rk_adj_dr.F90) (BASELINE config 4)")
+        desc = ("EXAMPLES/cbm4 ADJ/RK_ADJ: Radau-2A (ICNTRL(3)=1), NADJ=32, NP=29, "
+                + ("direct adjoint solve (ICNTRL(7)=2, 3N x 3N DGETRF per step)" if w == "cbm4_rk_adj_direct" else "fixed-sweep discrete adjoint")
+                + f", 12h..84h, rtol 0.1f*{1.0e-5 * scale:g}, atol 0.1f*{1.0e-7 * scale:g} (cbm4_rk_adj_dr.F90"
+                + (") (BASELINE config 4)" if scale == 1.0 else "; looser tolerances: general-pivoting second pass)"))
         ncpu = 32
-        flops = lambda r: dense_flops_from_counters(r.istatus, 32, 573, 636, complex_pairs=True, sens_cols=32)
+        if w == "cbm4_rk_adj_direct":           # + one (2/3 (3n)^3 + (3n)^2) factorisation and NADJ x 2 (3n)^2 solves per accepted step
+            flops = lambda r: (dense_flops_from_counters(r.istatus, 32, 573, 636, complex_pairs=True)
+                               + float(r.istatus[:, 3].astype(np.float64).sum()) * (2.0 * 96 ** 3 / 3.0 + 96 ** 2 - 5.0 * (2.0 * 32 ** 3 / 3.0 + 32 ** 2)
+                                                                                     + 32 * (2.0 * 96 ** 2 - 5.0 * 32 ** 2)))
+        else:
+            flops = lambda r: dense_flops_from_counters(r.istatus, 32, 573, 636, complex_pairs=True, sens_cols=32)
     elif w == "cbm4_sdirk_adj":
         rtol, atol = tolerances()
         y0 = perturbed_states(F.initial_state("cbm4"), nc)
@@ -386,6 +399,8 @@ def side_measure(w, nc, steps, warmup, fp64_peak=None, hbm_peak=None):
         times.append(time.perf_counter() - t)
         st = F.last_stats()
         dev_ms.append(st.ms_forward + st.ms_forward_tape + st.ms_adjoint)
+        phases = {"forward_ms": float(st.ms_forward), "preparation_ms": float(st.ms_forward_tape), "sensitivity_ms": float(st.ms_adjoint),
+                  "cells_general": int(st.cells_general)}
         assert (r.ierr == 1).all()
     t = time.perf_counter()
     cores = host_threads()
@@ -401,7 +416,7 @@ def side_measure(w, nc, steps, warmup, fp64_peak=None, hbm_peak=None):
             "e2e": {"value": nc / float(np.mean(times)), "unit": "cells/s"},
             "cpu_baseline": {"value": ncpu / tc, "unit": "cells/s", "cores": cores, "kind": "port",
                              "sample": f"{ncpu} cells, {tc:.1f} s, OpenMP over cells"},
-            "bitwise_equal_to_oracle_on_sample": same}
+            "bitwise_equal_to_oracle_on_sample": same, "phases_last_step": phases}
     if flops is not None:
         f = flops(r)
         roof = {"bound": "fp64", "achieved": f / sec / 1e12, "unit": "TFLOP/s", "peak": fp64_peak,

@@ -120,13 +120,18 @@ k_rk_adj_big(RkParams rp, RkAdjArgs a, RkBigRecord rl) {
           }
         }
         __syncthreads();
-        if (k < NB - 1) {   // DGER: rows of the trailing block on the lanes, its columns dealt to the warps
+        if (k < NB - 1) {   // DGER: rows of the trailing block on the lanes (three per lane), its columns dealt to the warps
+          const double l0 = E[lane + NB * k], l1 = E[lane + 32 + NB * k], l2 = E[lane + 64 + NB * k];   // x = column k of L
+          const bool r0 = lane > k, r1 = lane + 32 > k, r2 = lane + 64 > k;
           for (int c = k + 1 + warp; c < NB; c += 3) {
             const double yc = E[k + NB * c];
             if (yc != 0.0) {
               const double temp = -1.0 * yc;
-              for (int i = lane; i < NB; i += 32)
-                if (i > k) E[i + NB * c] = E[i + NB * c] + E[i + NB * k] * temp;
+              double* col = E + NB * c;
+              const double a0 = col[lane], a1 = col[lane + 32], a2 = col[lane + 64];
+              if (r0) col[lane] = a0 + l0 * temp;
+              if (r1) col[lane + 32] = a1 + l1 * temp;
+              if (r2) col[lane + 64] = a2 + l2 * temp;
             }
           }
         }
@@ -144,16 +149,19 @@ k_rk_adj_big(RkParams rp, RkAdjArgs a, RkBigRecord rl) {
           for (int i = 0; i < N; ++i) X[(s * N + i) * 32] = -(0.0 + c * o[i]);   // G = 0 + c J^T Lambda (SET2ZERO, DAXPY), X = -G
         }
       }
-      // DGETRS('T'): DTRSM(L,U,T,N), DTRSM(L,L,T,U), DLASWP(-1)
+      // DGETRS('T'): DTRSM(L,U,T,N), DTRSM(L,L,T,U), DLASWP(-1) in netlib's dot-product loops (an update-as-you-go U^T solve has the
+      // same operations per element in the same order and was measured 20 % slower: one more shared-memory store per term)
       for (int i = 0; i < NB; ++i) {
         double temp = X[i * 32];
         const double* col = E + NB * i;
+#pragma unroll 8
         for (int k = 0; k < i; ++k) temp = temp - col[k] * X[k * 32];
         X[i * 32] = temp / col[i];
       }
-      for (int i = NB - 1; i >= 0; --i) {
+      for (int i = NB - 1; i >= 0; --i) {            // L^T: element i takes its products in ascending k, only the dot form has that order
         double temp = X[i * 32];
         const double* col = E + NB * i;
+#pragma unroll 8
         for (int k = i + 1; k < NB; ++k) temp = temp - col[k] * X[k * 32];
         X[i * 32] = temp;
       }
