@@ -79,6 +79,7 @@ def lib():
                                                      ctypes.c_double, ctypes.c_double, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                                      ctypes.c_int, vp]
         L.fatode_sdirk_integrate_tlm_batch.argtypes = L.fatode_ros_integrate_tlm_batch.argtypes
+        L.fatode_rk_integrate_tlm_batch.argtypes = L.fatode_ros_integrate_tlm_batch.argtypes
         L.fatode_set_sdirk_tape_slot.argtypes = [ctypes.c_int]
         L.fatode_erk_integrate_batch.argtypes = L.fatode_sdirk_integrate_batch.argtypes
         L.fatode_erk_integrate_tlm_batch.argtypes = L.fatode_ros_integrate_tlm_batch.argtypes
@@ -257,7 +258,8 @@ def integrate_adj(model, tin, tout, y, nadj, rtol, atol, np_=None, icntrl_u=None
 def integrate_tlm(model, tin, tout, y, y_tlm, rtol, atol, icntrl_u=None, rcntrl_u=None, atol_tlm=None, rtol_tlm=None,
                   model_params=None, family="ros") -> Result:
     """Batched INTEGRATE_TLM: family="ros" TLM/ROS_TLM (TLM/ROS_TLM/ROS_TLM_f90_Integrator.F90:35), family="sdirk"
-    TLM/SDIRK_TLM (TLM/SDIRK_TLM/SDIRK_TLM_f90_Integrator.F90:31). y: [ncells, N]; y_tlm: [ncells, NTLM, N]."""
+    TLM/SDIRK_TLM (TLM/SDIRK_TLM/SDIRK_TLM_f90_Integrator.F90:31), family="rk" TLM/RK_TLM (TLM/RK_TLM/RK_TLM_f90_Integrator.F90:33,
+    preset direct TLM solve). y: [ncells, N]; y_tlm: [ncells, NTLM, N]."""
     mid = model_id(model)
     yy = np.atleast_2d(np.array(y, dtype=np.float64, order="C"))
     nc, n = yy.shape
@@ -272,7 +274,8 @@ def integrate_tlm(model, tin, tout, y, y_tlm, rtol, atol, icntrl_u=None, rcntrl_
     rst = np.zeros((nc, 20))
     ierr = np.zeros(nc, dtype=np.int32)
     mp = None if model_params is None else np.ascontiguousarray(model_params, dtype=np.float64)
-    entry = lib().fatode_sdirk_integrate_tlm_batch if family == "sdirk" else lib().fatode_ros_integrate_tlm_batch
+    entry = {"sdirk": lib().fatode_sdirk_integrate_tlm_batch, "rk": lib().fatode_rk_integrate_tlm_batch}.get(
+        family, lib().fatode_ros_integrate_tlm_batch)
     _check(entry(mid, nc, n, ntlm, _ptr(yy), _ptr(yt), float(tin), float(tout), _ptr(at), _ptr(rt),
                  _ptr(atol), _ptr(rtol), _ptr(ic), _ptr(rc), _ptr(ist), _ptr(rst), _ptr(ierr), _ptr(mp), MEM_HOST, None))
     return Result(yy, ist, rst, ierr, y_tlm=yt)

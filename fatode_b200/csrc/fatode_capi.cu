@@ -1568,6 +1568,7 @@ __global__ void k_rk_gather_status(int n, const int* __restrict__ ids, const int
 }
 
 // One group of systems (ids) through forward + backward.  Systems that overflow their tape slot are appended to `overflow`.
+static thread_local bool g_rk_tlm = false;          // the current call is INTEGRATE_TLM of TLM/RK_TLM: forward-order big-solve column pass
 static thread_local bool g_rk_adj_direct = false;   // ICNTRL(7) = 2 of the current call: one 3N x 3N factorisation per step (rk_big_adj.cuh)
 static int rk_adj_group(const RkParams& rp, const Cbm4Const& mc, const std::vector<int>& ids, int cap, int nadj, bool with_mu,
                         int np, bool do_adjoint, size_t fat_budget, double* d_y, double* d_lam, double* d_mu, const double* d_atol,
@@ -1628,12 +1629,17 @@ static int rk_adj_group(const RkParams& rp, const Cbm4Const& mc, const std::vect
       g_stats.ms_forward_tape += tm.stop();
       g_stats.launches++; g_stats.launches_expand++;
     }
-    RkAdjArgs aa{nb, d_off, d_cell, g_rk_fat.as<double>(), d_lam, d_mu, d_ist, g_ctr.as<unsigned long long>(), nadj, with_mu ? 1 : 0, np};
+    RkAdjArgs aa{nb, d_off, d_cell, g_rk_fat.as<double>(), d_lam, d_mu, d_ist, g_ctr.as<unsigned long long>(), nadj, with_mu ? 1 : 0, np, d_ierr};
     // static path: tensor-memory variant (one CTA of four sweep warps per SM; FATODE_RK_ADJ_SMEM=1 selects the shared-memory variant
     // with two one-warp CTAs per SM); general-pivoting pass: shared-memory variant with dense factors, one warp per SM
     static const bool use_tm = !(getenv("FATODE_RK_ADJ_SMEM") && atoi(getenv("FATODE_RK_ADJ_SMEM")) != 0);
     tm.start();
-    if (g_rk_adj_direct) {
+    if (g_rk_tlm) {
+      CUDA_TRY(cudaFuncSetAttribute(k_rk_tlm_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RK_ADJ_BIG_SMEM));
+      const RkBigRecord rl = dense ? RkBigRecord{DR_REC, DR_J} : RkBigRecord{RA_REC, RA_J};
+      const unsigned ablocks = (unsigned)std::min<int>(nb, 2 * sms);
+      k_rk_tlm_big<<<ablocks, RB_THREADS, RK_ADJ_BIG_SMEM, st>>>(rp, aa, rl);
+    } else if (g_rk_adj_direct) {
       CUDA_TRY(cudaFuncSetAttribute(k_rk_adj_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RK_ADJ_BIG_SMEM));
       const RkBigRecord rl = dense ? RkBigRecord{DR_REC, DR_J} : RkBigRecord{RA_REC, RA_J};
       const unsigned ablocks = (unsigned)std::min<int>(nb, 2 * sms);
@@ -1659,7 +1665,8 @@ static int rk_adj_group(const RkParams& rp, const Cbm4Const& mc, const std::vect
   for (int i = 0; i < n; ++i) {
     const int code = h_stat[2 * (size_t)i], nacc = h_stat[2 * (size_t)i + 1];
     if (code == IERR_TAPE_OVERFLOW) { overflow.push_back(ids[i]); continue; }
-    if (code != 1) continue;                       // failed forward sweep: no adjoint (the reference returns)
+    // failed forward sweep: no adjoint (the reference returns); the tangent-linear columns were advanced inside every accepted step
+    if (code != 1 && !(g_rk_tlm && code < 0 && code >= -13)) continue;   // -1..-13: the reference's codes (not the internal hand-backs)
     if (b_off.empty()) b_off.push_back(0);
     if (!b_slot.empty() && (size_t)(b_off.back() + nacc) * rec_bytes > fat_budget)
       if (int e = flush()) return e;
@@ -1756,6 +1763,7 @@ extern "C" int fatode_rk_integrate_adj_batch(int model, int64_t ncells, int nvar
     return fail(FATODE_EUNSUPPORTED, "RK_ADJ adaptive adjoint solve (ICNTRL(7) = 3) is not built; use the preset fixed-sweep solve or "
                                      "the direct solve (ICNTRL(7) = 2)");
   g_rk_adj_direct = do_adjoint && ao.solve == 2;
+  g_rk_tlm = false;
   const bool with_mu = np > 0 && mu != nullptr;
   Cbm4Const mc;
   cbm4_constants(model_params, mc);
@@ -1800,6 +1808,70 @@ extern "C" int fatode_rk_integrate_adj_batch(int model, int64_t ncells, int nvar
       if (with_mu) CUDA_TRY(cudaMemcpyAsync(mu, d_mu, nm, cudaMemcpyDeviceToHost, st));
       if (with_mu && mu_sum) CUDA_TRY(cudaMemcpyAsync(mu_sum, d_musum, sizeof(double) * np * nadj, cudaMemcpyDeviceToHost, st));
     }
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TLM/RK_TLM INTEGRATE_TLM for CBM-IV in the reference's preset mode (direct TLM solve, ICNTRL(7) = 1; state-only error control):
+// the RK_IntegratorTLM flavour of the taping forward sweep, the preparation records of the RK adjoint, then k_rk_tlm_big
+// (rk_big_adj.cuh) over the records in forward order.
+extern "C" int fatode_rk_integrate_tlm_batch(int model, int64_t ncells, int nvar, int ntlm, double* y, double* y_tlm, double tin,
+                                             double tout, const double* atol_tlm, const double* rtol_tlm, const double* atol,
+                                             const double* rtol, const int* icntrl_u, const double* rcntrl_u, int* istatus,
+                                             double* rstatus, int* ierr, const double* model_params, int mem, void* stream) {
+  (void)atol_tlm; (void)rtol_tlm;   // only read with ICNTRL(9) / ICNTRL(12), which are not built
+  g_err.clear();
+  if (ncells < 0 || !y || !y_tlm || !atol || !rtol || !istatus || !rstatus || !ierr) return fail(FATODE_EINVAL, "NULL required argument");
+  if (int e = check_model_dims(model, nvar, 0)) return e;
+  if (ntlm < 1) return fail(FATODE_EINVAL, "ntlm < 1");
+  if (model != FATODE_MODEL_CBM4) return fail(FATODE_EUNSUPPORTED, "the Runge-Kutta tangent linear model is available for the cbm4 model only in this build");
+  if (ntlm > 32) return fail(FATODE_EUNSUPPORTED, "ntlm > 32 per call is not supported yet");
+  if (int e = check_device()) return e;
+  if (ncells == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  RkParams rp;
+  RkTlmOptions to;
+  const int perr = rk_parse_options(nvar, icntrl_u, rcntrl_u, tin, tout, atol, rtol, rp, nullptr, &to);
+  if (perr < 0) return broadcast_ierr(ncells, perr, istatus, rstatus, ierr, mem, st);
+  if (to.trunc_err)
+    return fail(FATODE_EUNSUPPORTED, "RK_TLM with the columns in the truncation error control (ICNTRL(12)) is not built");
+  // ICNTRL(7) = 0 (modified-Newton TLM) cannot be selected through INTEGRATE_TLM: the preset 1 survives the `> 0` override rule;
+  // ICNTRL(9) only matters in that mode
+  Cbm4Const mc;
+  cbm4_constants(model_params, mc);
+  DevBuf b_atol, b_rtol, b_y, b_yt, b_ist, b_rst, b_ierr;
+  CUDA_TRY(b_atol.alloc(sizeof(double) * nvar));
+  CUDA_TRY(b_rtol.alloc(sizeof(double) * nvar));
+  CUDA_TRY(cudaMemcpyAsync(b_atol.p, atol, sizeof(double) * nvar, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(b_rtol.p, rtol, sizeof(double) * nvar, cudaMemcpyHostToDevice, st));
+  double *d_y = y, *d_yt = y_tlm, *d_rst = rstatus;
+  int *d_ist = istatus, *d_ierr = ierr;
+  const size_t ny = sizeof(double) * nvar * ncells, nl = sizeof(double) * (size_t)nvar * ntlm * ncells;
+  if (mem == FATODE_MEM_HOST) {
+    CUDA_TRY(b_y.alloc(ny));
+    CUDA_TRY(b_yt.alloc(nl));
+    CUDA_TRY(b_ist.alloc(sizeof(int) * 20 * ncells));
+    CUDA_TRY(b_rst.alloc(sizeof(double) * 20 * ncells));
+    CUDA_TRY(b_ierr.alloc(sizeof(int) * ncells));
+    CUDA_TRY(cudaMemcpyAsync(b_y.p, y, ny, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b_yt.p, y_tlm, nl, cudaMemcpyHostToDevice, st));
+    d_y = b_y.as<double>(); d_yt = b_yt.as<double>(); d_ist = b_ist.as<int>(); d_rst = b_rst.as<double>(); d_ierr = b_ierr.as<int>();
+  }
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_cbm4_rc, mc.rc_base, sizeof(double) * 81, 0, cudaMemcpyHostToDevice, st));
+  g_rk_tlm = true;
+  g_rk_adj_direct = false;
+  const int e = rk_adj_device(rp, mc, ncells, ntlm, /*with_mu=*/false, 0, /*do_adjoint=*/true, d_y, d_yt, nullptr, b_atol.as<double>(),
+                              b_rtol.as<double>(), d_ist, d_rst, d_ierr, nullptr, st);
+  g_rk_tlm = false;
+  if (e) return e;
+  if (mem == FATODE_MEM_HOST) {
+    CUDA_TRY(cudaMemcpyAsync(y, d_y, ny, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(y_tlm, d_yt, nl, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(istatus, d_ist, sizeof(int) * 20 * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(rstatus, d_rst, sizeof(double) * 20 * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ierr, d_ierr, sizeof(int) * ncells, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
   }
   return 0;

@@ -35,6 +35,88 @@ constexpr size_t RK_ADJ_BIG_SMEM = sizeof(double) * (size_t)RB_DOUBLES;   // 106
 
 struct RkBigRecord { int stride, off_tail; };             // doubles per preparation record, offset of its J | P tail
 
+// lapack_decomp_big for the step whose header and J | P tail sit in REC: assembles e_big = I - H (A x J_b) in E (96 x 96, column
+// major) and factorises it in place like DGETF2, block-cooperatively (all 96 threads).  Returns netlib's INFO (0, or k + 1 of the
+// first exactly zero pivot); the interchanges go to PIV (0-based).
+__device__ __forceinline__ int rb_decomp_big(const RkParams& rp, double* __restrict__ E, const double* __restrict__ REC,
+                                             int* __restrict__ PIV, double* __restrict__ RED, double H, int tid, int warp, int lane) {
+  constexpr int N = 32, NB = RB_N;
+  const double sfmin = 2.2250738585072014e-308;           // DLAMCH('S')
+  int info = 0;
+  // lapack_decomp_big: e_big = -H rkA(a,b) fjac_b + I.  Entries outside the Jacobian pattern are the signed zeros of the product.
+  for (int idx = tid; idx < NB * NB; idx += RB_THREADS) {
+    const int i = idx % NB, j = idx / NB;
+    E[idx] = (-H * rp.A[i / N + 1][j / N + 1]) * 0.0;
+  }
+  __syncthreads();
+  for (int e = tid; e < 3 * 276; e += RB_THREADS) {
+    const int b = e / 276, ee = e - b * 276;
+    const int r = cbm4_dev::JAC_ROW[ee], c = cbm4_dev::JAC_COL[ee];
+    const double v = REC[4 + e];
+#pragma unroll
+    for (int ab = 0; ab < 3; ++ab) E[(ab * N + r) + NB * (b * N + c)] = (-H * rp.A[ab + 1][b + 1]) * v;
+  }
+  __syncthreads();
+  E[tid + NB * tid] = E[tid + NB * tid] + 1;
+  __syncthreads();
+  // DGETF2 (oracle/ref_lapack.hpp::dgetf2 operation by operation)
+  for (int k = 0; k < NB; ++k) {
+    {   // IDAMAX over rows k..95 of column k: first index of the maximum modulus
+      double v = (tid >= k) ? fabs(E[tid + NB * k]) : -1.0;
+      int row = tid;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, v, off);
+        const int orow = __shfl_down_sync(0xffffffffu, row, off);
+        if (ov > v || (ov == v && orow < row)) { v = ov; row = orow; }
+      }
+      if (lane == 0) { RED[warp] = v; RED[3 + warp] = (double)row; }
+    }
+    __syncthreads();
+    int jp;
+    {
+      double v = RED[0]; jp = (int)RED[3];
+      if (RED[1] > v) { v = RED[1]; jp = (int)RED[4]; }
+      if (RED[2] > v) { v = RED[2]; jp = (int)RED[5]; }
+    }
+    const double pv = E[jp + NB * k];
+    if (tid == 0) PIV[k] = jp;
+    __syncthreads();                                   // every thread has read RED and the pivot before rows move
+    if (pv == 0.0 && info == 0) info = k + 1;
+    if (pv != 0.0) {
+      if (jp != k) {                                   // DSWAP of the two full rows: thread = column
+        const double t = E[k + NB * tid];
+        E[k + NB * tid] = E[jp + NB * tid];
+        E[jp + NB * tid] = t;
+      }
+      __syncthreads();
+      if (k < NB - 1 && tid > k) {                     // DSCAL by the reciprocal, or the division below sfmin
+        const double d = E[k + NB * k];
+        if (fabs(d) >= sfmin) { const double r = 1.0 / d; E[tid + NB * k] = r * E[tid + NB * k]; }
+        else E[tid + NB * k] = E[tid + NB * k] / d;
+      }
+    }
+    __syncthreads();
+    if (k < NB - 1) {   // DGER: rows of the trailing block on the lanes (three per lane), its columns dealt to the warps
+      const double l0 = E[lane + NB * k], l1 = E[lane + 32 + NB * k], l2 = E[lane + 64 + NB * k];   // x = column k of L
+      const bool r0 = lane > k, r1 = lane + 32 > k, r2 = lane + 64 > k;
+      for (int c = k + 1 + warp; c < NB; c += 3) {
+        const double yc = E[k + NB * c];
+        if (yc != 0.0) {
+          const double temp = -1.0 * yc;
+          double* col = E + NB * c;
+          const double a0 = col[lane], a1 = col[lane + 32], a2 = col[lane + 64];
+          if (r0) col[lane] = a0 + l0 * temp;
+          if (r1) col[lane + 32] = a1 + l1 * temp;
+          if (r2) col[lane + 64] = a2 + l2 * temp;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  return info;
+}
+
 __global__ void __launch_bounds__(RB_THREADS, 2)
 k_rk_adj_big(RkParams rp, RkAdjArgs a, RkBigRecord rl) {
   extern __shared__ __align__(16) double cell_smem[];
@@ -45,7 +127,6 @@ k_rk_adj_big(RkParams rp, RkAdjArgs a, RkBigRecord rl) {
   double* const REC = cell_smem + RB_OFF_REC;             // [0..3] header, then J_1..3 (276 each), then the reactant products (32 each)
   int* const PIV = reinterpret_cast<int*>(cell_smem + RB_OFF_PIV);
   double* const RED = cell_smem + RB_OFF_RED;             // [0..2] warp maxima, [3..5] their rows (as doubles), [6] queue slot
-  const double sfmin = 2.2250738585072014e-308;           // DLAMCH('S')
   const bool active = (warp == 0) && lane < a.nadj;
   for (;;) {
     __syncthreads();
@@ -67,76 +148,7 @@ k_rk_adj_big(RkParams rp, RkAdjArgs a, RkBigRecord rl) {
       }
       __syncthreads();
       const double H = REC[1];
-      // lapack_decomp_big: e_big = -H rkA(a,b) fjac_b + I.  Entries outside the Jacobian pattern are the signed zeros of the product.
-      for (int idx = tid; idx < NB * NB; idx += RB_THREADS) {
-        const int i = idx % NB, j = idx / NB;
-        E[idx] = (-H * rp.A[i / N + 1][j / N + 1]) * 0.0;
-      }
-      __syncthreads();
-      for (int e = tid; e < 3 * 276; e += RB_THREADS) {
-        const int b = e / 276, ee = e - b * 276;
-        const int r = cbm4_dev::JAC_ROW[ee], c = cbm4_dev::JAC_COL[ee];
-        const double v = REC[4 + e];
-#pragma unroll
-        for (int ab = 0; ab < 3; ++ab) E[(ab * N + r) + NB * (b * N + c)] = (-H * rp.A[ab + 1][b + 1]) * v;
-      }
-      __syncthreads();
-      E[tid + NB * tid] = E[tid + NB * tid] + 1;
-      __syncthreads();
-      // DGETF2 (oracle/ref_lapack.hpp::dgetf2 operation by operation)
-      for (int k = 0; k < NB; ++k) {
-        {   // IDAMAX over rows k..95 of column k: first index of the maximum modulus
-          double v = (tid >= k) ? fabs(E[tid + NB * k]) : -1.0;
-          int row = tid;
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) {
-            const double ov = __shfl_down_sync(0xffffffffu, v, off);
-            const int orow = __shfl_down_sync(0xffffffffu, row, off);
-            if (ov > v || (ov == v && orow < row)) { v = ov; row = orow; }
-          }
-          if (lane == 0) { RED[warp] = v; RED[3 + warp] = (double)row; }
-        }
-        __syncthreads();
-        int jp;
-        {
-          double v = RED[0]; jp = (int)RED[3];
-          if (RED[1] > v) { v = RED[1]; jp = (int)RED[4]; }
-          if (RED[2] > v) { v = RED[2]; jp = (int)RED[5]; }
-        }
-        const double pv = E[jp + NB * k];
-        if (tid == 0) PIV[k] = jp;
-        __syncthreads();                                   // every thread has read RED and the pivot before rows move
-        if (pv != 0.0) {
-          if (jp != k) {                                   // DSWAP of the two full rows: thread = column
-            const double t = E[k + NB * tid];
-            E[k + NB * tid] = E[jp + NB * tid];
-            E[jp + NB * tid] = t;
-          }
-          __syncthreads();
-          if (k < NB - 1 && tid > k) {                     // DSCAL by the reciprocal, or the division below sfmin
-            const double d = E[k + NB * k];
-            if (fabs(d) >= sfmin) { const double r = 1.0 / d; E[tid + NB * k] = r * E[tid + NB * k]; }
-            else E[tid + NB * k] = E[tid + NB * k] / d;
-          }
-        }
-        __syncthreads();
-        if (k < NB - 1) {   // DGER: rows of the trailing block on the lanes (three per lane), its columns dealt to the warps
-          const double l0 = E[lane + NB * k], l1 = E[lane + 32 + NB * k], l2 = E[lane + 64 + NB * k];   // x = column k of L
-          const bool r0 = lane > k, r1 = lane + 32 > k, r2 = lane + 64 > k;
-          for (int c = k + 1 + warp; c < NB; c += 3) {
-            const double yc = E[k + NB * c];
-            if (yc != 0.0) {
-              const double temp = -1.0 * yc;
-              double* col = E + NB * c;
-              const double a0 = col[lane], a1 = col[lane + 32], a2 = col[lane + 64];
-              if (r0) col[lane] = a0 + l0 * temp;
-              if (r1) col[lane + 32] = a1 + l1 * temp;
-              if (r2) col[lane + 64] = a2 + l2 * temp;
-            }
-          }
-        }
-        __syncthreads();
-      }
+      rb_decomp_big(rp, E, REC, PIV, RED, H, tid, warp, lane);   // ISING of LSS_Decomp_Big is never looked at (:1330)
       if (!active) continue;
       // G_s = -H b_s J_s^T Lambda (:1337-1347), X = -G (:1468-1470)
       {
@@ -204,6 +216,124 @@ k_rk_adj_big(RkParams rp, RkAdjArgs a, RkBigRecord rl) {
       is_[Ndec] += 2 * A;
       is_[Nstp] += A;
       is_[Nsol] += A * a.nadj;
+    }
+  }
+}
+
+// =====================================================================================================================
+// Tangent linear model of the 3-stage implicit Runge-Kutta methods, the reference's preset DIRECT TLM solve (TLM/RK_TLM
+// INTEGRATE_TLM, ICNTRL(7) = 1; RK_IntegratorTLM, TLM/RK_TLM/RK_TLM_f90_Integrator.F90:761-793, 909-914).
+// On every accepted step the reference evaluates the three stage Jacobians, factorises e_big = I - H (A x J_b)
+// (LSS_Decomp_Big) and solves, per column, e_big Zbig = H (A x J_b) Y_tlm (RK_PrepareRHS_TLMdirect :1185-1227, LSS_Solve_Big
+// with Transp = .FALSE.); then Y_tlm += sum_i d_i Z_i.  With the state's error control only (ICNTRL(12) = 0, the preset) the
+// columns never influence the step sequence, so the state sweep (k_rk_fwd_cell<.., ADJ = true> with RkParams::tlm set: the
+// RK_IntegratorTLM flavour) tapes the accepted steps and this kernel walks the preparation records FORWARDS.
+// Same mapping as k_rk_adj_big: one system per CTA of three warps, block-cooperative DGETF2, lane m of warp 0 = column m of
+// Y_tlm (in registers), its 96-vector Zbig in shared-memory slots.  matmul(fjac_b, Y_tlm) as the sequential row sums of
+// j_vec_seq, DGETRS('N') as DLASWP + netlib's two column-sweep DTRSMs (zero right-hand-side entries skipped like netlib; they only
+// skip exact zeros), no fma: Y_tlm is bit-identical to the CPU restatement (oracle/rk_tlm.hpp).  A singular e_big (the
+// reference STOPs: "Big big guy is singular") ends the system with IERR -12.
+__global__ void __launch_bounds__(RB_THREADS, 2)
+k_rk_tlm_big(RkParams rp, RkAdjArgs a, RkBigRecord rl) {
+  extern __shared__ __align__(16) double cell_smem[];
+  constexpr int N = 32, NB = RB_N;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  double* const E = cell_smem + RB_OFF_E;
+  double* const REC = cell_smem + RB_OFF_REC;
+  int* const PIV = reinterpret_cast<int*>(cell_smem + RB_OFF_PIV);
+  double* const RED = cell_smem + RB_OFF_RED;
+  const int ntlm = a.nadj;
+  const bool active = (warp == 0) && lane < ntlm;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) RED[6] = (double)atomicAdd(a.queue, 1ull);
+    __syncthreads();
+    const unsigned long long slot = (unsigned long long)RED[6];
+    if (slot >= (unsigned long long)a.ncells) break;
+    const long long r0 = a.rec_off[slot], r1 = a.rec_off[slot + 1];
+    const int cell = a.cell[slot];
+    double* const ycol = a.lambda + ((size_t)cell * ntlm + (lane < ntlm ? lane : 0)) * N;   // Y_tlm(:, m) of the caller
+    double yt[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) yt[i] = active ? ycol[i] : 0.0;
+    long long done = 0;
+    int info = 0;
+    for (long long q = r0; q < r1; ++q) {
+      __syncthreads();
+      {
+        const double* src = a.fat + (size_t)q * rl.stride;
+        if (tid < 4) REC[tid] = src[tid];
+        for (int e = tid; e < RB_TAIL; e += RB_THREADS) REC[4 + e] = __ldg(src + rl.off_tail + e);
+      }
+      __syncthreads();
+      const double H = REC[1];
+      info = rb_decomp_big(rp, E, REC, PIV, RED, H, tid, warp, lane);
+      ++done;
+      if (info != 0) break;                               // uniform: every thread computed the same INFO
+      if (!active) continue;
+      double* __restrict__ const X = cell_smem + RB_OFF_X + lane;   // Zbig of this lane: row r at X[r * 32]
+      const double* __restrict__ const Ef = E;
+      {   // RK_PrepareRHS_TLMdirect: Zbig_a = sum_b (H rkA(a,b)) (J_b Y_tlm), b = 1, 2, 3 in this order
+        double o[N];
+#pragma unroll 1
+        for (int b = 0; b < 3; ++b) {
+          cbm4_cell::j_vec_seq(REC + 4 + b * 276, yt, o);
+          const double c1 = H * rp.A[1][b + 1], c2 = H * rp.A[2][b + 1], c3 = H * rp.A[3][b + 1];
+          if (b == 0) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) { X[i * 32] = c1 * o[i]; X[(N + i) * 32] = c2 * o[i]; X[(2 * N + i) * 32] = c3 * o[i]; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              X[i * 32] = X[i * 32] + c1 * o[i];
+              X[(N + i) * 32] = X[(N + i) * 32] + c2 * o[i];
+              X[(2 * N + i) * 32] = X[(2 * N + i) * 32] + c3 * o[i];
+            }
+          }
+        }
+      }
+      // DGETRS('N'): DLASWP, DTRSM(L,L,N,U), DTRSM(L,U,N,N)
+      for (int i = 0; i < NB; ++i) {
+        const int ip = PIV[i];
+        if (ip != i) { const double t = X[i * 32]; X[i * 32] = X[ip * 32]; X[ip * 32] = t; }
+      }
+      for (int k = 0; k < NB; ++k) {
+        const double bk = X[k * 32];
+        if (bk != 0.0) {
+          const double* __restrict__ col = Ef + NB * k;
+#pragma unroll 4
+          for (int i = k + 1; i < NB; ++i) X[i * 32] = X[i * 32] - bk * col[i];
+        }
+      }
+      for (int k = NB - 1; k >= 0; --k) {
+        if (X[k * 32] != 0.0) {
+          const double* __restrict__ col = Ef + NB * k;
+          const double bk = X[k * 32] / col[k];
+          X[k * 32] = bk;
+#pragma unroll 4
+          for (int i = 0; i < k; ++i) X[i * 32] = X[i * 32] - bk * col[i];
+        }
+      }
+      // Y_tlm <- Y_tlm + sum_i d_i Z_i   (:909-914)
+#pragma unroll 1
+      for (int s = 1; s <= 3; ++s) {
+        const double d = rp.D[s];
+        if (d != 0.0) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) yt[i] = yt[i] + d * X[((s - 1) * N + i) * 32];
+        }
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) ycol[i] = yt[i];
+    }
+    if (tid == 0) {   // counters of the TLM block (:768, 773, 782): per accepted step Njac 3, Ndec 1, Nsol NTLM
+      int* is_ = a.istatus + (size_t)cell * 20;
+      is_[Njac] += 3 * (int)done;
+      is_[Ndec] += (int)done;
+      is_[Nsol] += (int)(info != 0 ? done - 1 : done) * ntlm;
+      if (info != 0 && a.ierr && a.ierr[cell] == 1) a.ierr[cell] = -12;
     }
   }
 }

@@ -119,6 +119,7 @@ struct RkAdjArgs {
   double* lambda; double* mu; int* istatus;
   unsigned long long* queue;
   int nadj, with_mu, np;
+  int* ierr = nullptr;        // per-system IERR (only the tangent-linear big-solve kernel writes it)
 };
 
 constexpr int RA_VEC = 11;   // per-lane vectors: LAM, MU, U1..3, G1..3, R1..3

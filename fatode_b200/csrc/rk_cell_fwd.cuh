@@ -35,6 +35,7 @@ struct RkParams {
   int method;
   double T[3][3], TinvAinv[3][3], Tinv[3][3], AinvT[3][3], A[4][4], B[4], C[4], D[4], Bgam[5], Theta[4], F[5], Gamma, Alpha, Beta, ELO;
   int vector_tol, max_no_steps, newton_maxit, start_newton, gustafsson;
+  int tlm;   // RK_IntegratorTLM flavour of the ADJ forward sweep: RK_PrepareRHS counts its FUN calls, the LU is never reused (TLM/RK_TLM :934-935, 1120-1134)
   double roundoff, hmin, hmax, hstart, facmin, facmax, facrej, facsafe, thetamin, newtontol, qmin, qmax;
   double tstart, tend;
 };
@@ -191,7 +192,8 @@ k_rk_fwd_cell(RkParams rp, typename Model::Const mc, long ncells, const double* 
       double Fac = 0.5;
       int NewtonIter;
       for (NewtonIter = 1; NewtonIter <= NewtonMaxit; ++NewtonIter) {
-        // RK_PrepareRHS :917-955 (its FUN calls are not counted)
+        // RK_PrepareRHS :917-955 (its FUN calls are not counted, except by the RK_TLM copy of the routine)
+        if (rp.tlm) nfun += 3;
 #pragma unroll 4
         for (int i = 0; i < N; ++i) { R1[i * SV] = Z1[i * SV]; R2[i * SV] = Z2[i * SV]; R3[i * SV] = Z3[i * SV]; }
         if (rp.method == RK_L3A) {
@@ -431,6 +433,7 @@ k_rk_fwd_cell(RkParams rp, typename Model::Const mc, long ncells, const double* 
         } else {
           const double Hratio = __ddiv_rn(Hnew, H);
           SkipLU = (Theta <= rp.thetamin) && (Hratio >= rp.qmin) && (Hratio <= rp.qmax);
+          if (rp.tlm) SkipLU = false;   // "For TLM: do not skip LU"
           if (!SkipLU) H = Hnew;
         }
         SkipJac = false;
@@ -462,8 +465,11 @@ k_rk_fwd_cell(RkParams rp, typename Model::Const mc, long ncells, const double* 
 // adj != nullptr: INTEGRATE_ADJ of ADJ/RK_ADJ instead (presets :63-70, no Lobatto-3A :411-423, Max_no_steps 10000 :426,
 // ICNTRL(7) adjoint solve and ICNTRL(9) adjoint type :456-487); *adj receives ICNTRL(7) (0..3) and ICNTRL(9) (0..2).
 struct RkAdjOptions { int solve, type; };
+struct RkTlmOptions { int direct, newton_est, trunc_err; };   // ICNTRL(7), (9), (12) of TLM/RK_TLM
+// tlm != nullptr: INTEGRATE_TLM of TLM/RK_TLM (presets :62-73: ICNTRL(5) = 8, (7) = 1 direct TLM solve, (10) = 1, (11) = 1 i.e. the
+// classic controller; no Lobatto-3A :321-334; Max_no_steps 200000 :336).
 inline int rk_parse_options(int N, const int* icntrl_u, const double* rcntrl_u, double tin, double tout, const double* atol,
-                            const double* rtol, RkParams& rp, RkAdjOptions* adj = nullptr) {
+                            const double* rtol, RkParams& rp, RkAdjOptions* adj = nullptr, RkTlmOptions* tlm = nullptr) {
   int ic[20];
   double rc[20];
   std::memset(ic, 0, sizeof ic);
@@ -471,6 +477,7 @@ inline int rk_parse_options(int N, const int* icntrl_u, const double* rcntrl_u, 
   ic[4] = 8;    // ICNTRL(5): max no. of Newton iterations
   ic[9] = 1;    // ICNTRL(10): SDIRK error estimation
   if (adj) { ic[6] = 1; ic[8] = 2; ic[10] = 1; }   // fixed-sweep adjoint solve, discrete adjoint, classic controller
+  if (tlm) { ic[6] = 1; ic[10] = 1; }              // direct TLM solve, classic controller
   for (int i = 0; i < 20; ++i) {
     if (icntrl_u && icntrl_u[i] > 0) ic[i] = icntrl_u[i];
     if (rcntrl_u && rcntrl_u[i] > 0) rc[i] = rcntrl_u[i];
@@ -484,7 +491,7 @@ inline int rk_parse_options(int N, const int* icntrl_u, const double* rcntrl_u, 
     case 0: case 2: method = RK_L3C; break;   // the actual default
     case 3: method = RK_GAU; break;
     case 4: method = RK_R1A; break;
-    case 5: if (adj) ierr = -13; else method = RK_L3A; break;
+    case 5: if (adj || tlm) ierr = -13; else method = RK_L3A; break;
     default: ierr = -13;
   }
   if (method) {
@@ -528,6 +535,7 @@ inline int rk_parse_options(int N, const int* icntrl_u, const double* rcntrl_u, 
     if (atol[i] <= 0.0 || rtol[i] <= 10.0 * rp.roundoff) ierr = -8;
   rp.tstart = tin;
   rp.tend = tout;
+  if (tlm) { tlm->direct = (ic[6] != 0); tlm->newton_est = (ic[8] != 0); tlm->trunc_err = (ic[11] != 0); rp.tlm = 1; }
   if (adj) {
     adj->solve = ic[6];
     adj->type = ic[8];

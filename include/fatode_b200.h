@@ -127,6 +127,23 @@ int fatode_sdirk_integrate_batch(int model, int64_t ncells, int nvar, double* y,
                                  const double* rcntrl_u, int* istatus, double* rstatus, int* ierr,
                                  const double* model_params, int mem, void* stream);
 
+/* INTEGRATE_TLM of TLM/RK_TLM (TLM/RK_TLM/RK_TLM_f90_Integrator.F90:33):
+ *   INTEGRATE_TLM(N,NTLM,NNZERO,Y,Y_TLM,TIN,TOUT,ATOL_TLM,RTOL_TLM,ATOL,RTOL,FUN,JAC,ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U)
+ * Tangent linear model of the 3-stage implicit Runge-Kutta methods (ICNTRL(3) = 1 Radau-2A, 0/2 Lobatto-3C, 3 Gauss, 4 Radau-1A)
+ * in the reference's preset mode: ICNTRL(5) = 8, (7) = 1 DIRECT TLM solve (one factorisation of the 3N x 3N system
+ * I - H (A x J_b) per accepted step and one solve per column, :761-793 — the modified-Newton TLM, ICNTRL(7) = 0, cannot be
+ * selected through INTEGRATE_TLM because of the `> 0` override rule), (10) = 1 SDIRK error estimator, (11) = 1 classic
+ * controller, (12) = 0 state-only truncation error; ICNTRL(12) != 0 returns FATODE_EUNSUPPORTED.  y_tlm [ncells][ntlm][nvar],
+ * ntlm <= 32, cbm4 only.  Per-cell IERR: 1, the reference's -1..-13, or -12 when the big matrix is singular (the reference
+ * STOPs there).  A cell whose state sweep fails returns Y and Y_tlm as of its last accepted step, as the reference.  Systems
+ * whose step factorisations leave the static pivot pattern take the general-pivoting second pass of the RK family.  State,
+ * counters and Y_tlm are bit-identical to the reference's operation order (oracle/rk_tlm.hpp). */
+int fatode_rk_integrate_tlm_batch(int model, int64_t ncells, int nvar, int ntlm, double* y, double* y_tlm,
+                                  double tin, double tout, const double* atol_tlm, const double* rtol_tlm,
+                                  const double* atol, const double* rtol, const int* icntrl_u,
+                                  const double* rcntrl_u, int* istatus, double* rstatus, int* ierr,
+                                  const double* model_params, int mem, void* stream);
+
 /* INTEGRATE_TLM of TLM/SDIRK_TLM (TLM/SDIRK_TLM/SDIRK_TLM_f90_Integrator.F90:31):
  *   INTEGRATE_TLM(N,NTLM,NNZERO,Y,Y_TLM,TIN,TOUT,ATOL_TLM,RTOL_TLM,ATOL,RTOL,FUN,JAC,
  *                 ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U,IERR_U)

@@ -12,6 +12,7 @@
 #include "rk.hpp"
 #include "rk_adj.hpp"
 #include "sdirk_tlm.hpp"
+#include "rk_tlm.hpp"
 #include "erk.hpp"
 #include "sdirk_adj.hpp"
 
@@ -153,6 +154,24 @@ int oracle_sdirk_tlm_batch(int model, long ncells, int ntlm, double* y, double* 
       case MODEL_ROBERTS: { Roberts m; ierr[c] = sdirk_tlm_integrate<Roberts>(m, ntlm, y + c * Roberts::N, y_tlm + c * (long)Roberts::N * ntlm, tin, tout, atol_tlm, rtol_tlm, atol, rtol, icntrl, rcntrl, istatus + c * 20, rstatus + c * 20); break; }
       case MODEL_SMALL_STRATO: { SmallStrato m; ierr[c] = sdirk_tlm_integrate<SmallStrato>(m, ntlm, y + c * SmallStrato::N, y_tlm + c * (long)SmallStrato::N * ntlm, tin, tout, atol_tlm, rtol_tlm, atol, rtol, icntrl, rcntrl, istatus + c * 20, rstatus + c * 20); break; }
       case MODEL_CBM4: { Cbm4 m; ierr[c] = sdirk_tlm_integrate<Cbm4>(m, ntlm, y + c * Cbm4::N, y_tlm + c * (long)Cbm4::N * ntlm, tin, tout, atol_tlm, rtol_tlm, atol, rtol, icntrl, rcntrl, istatus + c * 20, rstatus + c * 20); break; }
+      default: ierr[c] = -100;
+    }
+  }
+  return 0;
+}
+
+// INTEGRATE_TLM of TLM/RK_TLM looped over cells (preset direct TLM solve); y_tlm[cell][NTLM][N]
+int oracle_rk_tlm_batch(int model, long ncells, int ntlm, double* y, double* y_tlm, double tin, double tout, const double* atol_tlm,
+                        const double* rtol_tlm, const double* atol, const double* rtol, const int* icntrl, const double* rcntrl,
+                        int* istatus, double* rstatus, int* ierr, int nthreads) {
+  (void)atol_tlm; (void)rtol_tlm;
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+  for (long c = 0; c < ncells; ++c) {
+    switch (model) {
+      case MODEL_ROBERTS: { Roberts m; ierr[c] = rk_tlm_integrate<Roberts>(m, ntlm, y + c * Roberts::N, y_tlm + c * (long)Roberts::N * ntlm, tin, tout, atol, rtol, icntrl, rcntrl, istatus + c * 20, rstatus + c * 20); break; }
+      case MODEL_SMALL_STRATO: { SmallStrato m; ierr[c] = rk_tlm_integrate<SmallStrato>(m, ntlm, y + c * SmallStrato::N, y_tlm + c * (long)SmallStrato::N * ntlm, tin, tout, atol, rtol, icntrl, rcntrl, istatus + c * 20, rstatus + c * 20); break; }
+      case MODEL_CBM4: { Cbm4 m; ierr[c] = rk_tlm_integrate<Cbm4>(m, ntlm, y + c * Cbm4::N, y_tlm + c * (long)Cbm4::N * ntlm, tin, tout, atol, rtol, icntrl, rcntrl, istatus + c * 20, rstatus + c * 20); break; }
       default: ierr[c] = -100;
     }
   }

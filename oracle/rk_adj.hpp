@@ -36,6 +36,8 @@ struct RungeKuttaAdj : RungeKutta<Model> {
   std::vector<double> fjac1, fjac2, fjac3, e_big;
   std::vector<int> ip_big;
   bool direct_solve = false;               // AdjointSolve == Solve_direct (ICNTRL(7) = 2): one 3N x 3N factorisation per step
+  bool tlm_flavour = false;                // forward sweep as RK_IntegratorTLM runs it (rk_tlm.hpp): RK_PrepareRHS counts its three FUN
+                                           // calls (TLM/RK_TLM :1120-1134) and the LU is never reused across steps (:934-935)
   explicit RungeKuttaAdj(Model& m) : Base(m), fjac1(N * N, 0.0), fjac2(N * N, 0.0), fjac3(N * N, 0.0) {}
 
   // RK_PrepareRHS :1707-1739 (no F0 argument, no Lobatto-3A)
@@ -49,6 +51,7 @@ struct RungeKuttaAdj : RungeKutta<Model> {
     for (int s = 1; s <= 3; ++s) {
       for (int i = 0; i < N; ++i) TMP[i] = Y[i] + Z[s - 1][i];
       mdl.fun(T + tb.C[s] * H, TMP, F);
+      if (tlm_flavour) ISTATUS[Nfun]++;
       axpy(-H * tb.A[1][s], F, R1); axpy(-H * tb.A[2][s], F, R2); axpy(-H * tb.A[3][s], F, R3);
     }
   }
@@ -217,6 +220,7 @@ struct RungeKuttaAdj : RungeKutta<Model> {
         } else {
           Hratio = Hnew / H;
           SkipLU = (Theta <= cfg.ThetaMin) && (Hratio >= cfg.Qmin) && (Hratio <= cfg.Qmax);
+          if (tlm_flavour) SkipLU = false;   // "For TLM: do not skip LU"
           if (!SkipLU) H = Hnew;
         }
         SkipJac = false;

@@ -33,6 +33,7 @@ def lib():
         L.oracle_ros_tlm_batch.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_int, _dp, _dp, ctypes.c_double, ctypes.c_double,
                                            _dp, _dp, _dp, _dp, _ip, _dp, _ip, _dp, _ip, ctypes.c_int]
         L.oracle_sdirk_tlm_batch.argtypes = L.oracle_ros_tlm_batch.argtypes
+        L.oracle_rk_tlm_batch.argtypes = L.oracle_ros_tlm_batch.argtypes
         L.oracle_erk_batch.argtypes = L.oracle_ros_tlm_batch.argtypes
         L.oracle_swe_initial_state.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_double, _dp]
         L.oracle_swe_fun.argtypes = [_dp, _dp]
@@ -187,6 +188,24 @@ def sdirk_tlm(model, y, y_tlm, tin, tout, atol, rtol, icntrl=None, rcntrl=None, 
     r = lib().oracle_sdirk_tlm_batch(MODEL[model], nc, ntlm, _d(y), _d(yt), tin, tout, None if at is None else _d(at),
                                      None if rt is None else _d(rt), _d(atol), _d(rtol), _i(ic), _d(rc), _i(ist), _d(rst),
                                      _i(ierr), nthreads)
+    assert r == 0
+    return dict(y=y, y_tlm=yt, istatus=ist, rstatus=rst, ierr=ierr)
+
+
+def rk_tlm(model, y, y_tlm, tin, tout, atol, rtol, icntrl=None, rcntrl=None, nthreads=0):
+    """INTEGRATE_TLM (TLM/RK_TLM, preset direct TLM solve); y_tlm: [ncells, NTLM, N]."""
+    y = np.atleast_2d(np.array(y, dtype=np.float64, order="C"))
+    nc, n = y.shape
+    yt = np.array(y_tlm, dtype=np.float64, order="C").reshape(nc, -1, n)
+    ntlm = yt.shape[1]
+    ic, rc = _ctrl(icntrl, rcntrl)
+    atol = np.ascontiguousarray(atol, dtype=np.float64)
+    rtol = np.ascontiguousarray(rtol, dtype=np.float64)
+    ist = np.zeros((nc, 20), dtype=np.int32)
+    rst = np.zeros((nc, 20))
+    ierr = np.zeros(nc, dtype=np.int32)
+    r = lib().oracle_rk_tlm_batch(MODEL[model], nc, ntlm, _d(y), _d(yt), tin, tout, None, None, _d(atol), _d(rtol), _i(ic), _d(rc),
+                                  _i(ist), _d(rst), _i(ierr), nthreads)
     assert r == 0
     return dict(y=y, y_tlm=yt, istatus=ist, rstatus=rst, ierr=ierr)
 
