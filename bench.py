@@ -254,7 +254,7 @@ def workload_config(cells, ngpus, note=None):
 
 
 SIDE_DEFAULT_CELLS = {"small_strato_fwd": 1 << 20, "cbm4_ros_tlm": 32768, "cbm4_rk_adj": 9472, "cbm4_rk_adj_direct": 9472,
-                      "cbm4_rk_adj_rtol1e-5": 4736, "cbm4_rk_adj_rtol1e-4": 4736, "cbm4_sdirk_adj": 9472,
+                      "cbm4_rk_adj_rtol1e-5": 4736, "cbm4_rk_adj_rtol1e-4": 4736, "cbm4_rk_tlm": 9472, "cbm4_sdirk_adj": 9472,
                       "cbm4_sdirk_tlm": 9472, "swe_erk": 65536, "swe_erk_tlm": 16384, "cbm4_rk": 18944, "cbm4_sdirk": 18944}
 
 
@@ -330,6 +330,23 @@ def side_measure(w, nc, steps, warmup, fp64_peak=None, hbm_peak=None):
                                                                                      + 32 * (2.0 * 96 ** 2 - 5.0 * 32 ** 2)))
         else:
             flops = lambda r: dense_flops_from_counters(r.istatus, 32, 573, 636, complex_pairs=True, sens_cols=32)
+    elif w == "cbm4_rk_tlm":
+        rtol, atol = np.full(N, F01 * 1.0e-5), np.full(N, F01 * 1.0e-7)
+        ic = np.zeros(20, dtype=np.int32)
+        ic[2] = 1
+        y0 = perturbed_states(F.initial_state("cbm4"), nc)
+        eye = np.eye(32)
+        run = lambda y: F.integrate_tlm("cbm4", T0, T1, y, np.broadcast_to(eye, (y.shape[0], 32, 32)).copy(), rtol, atol, icntrl_u=ic, family="rk")
+        cpu = lambda y: O.rk_tlm("cbm4", y, np.broadcast_to(eye, (y.shape[0], 32, 32)).copy(), T0, T1, atol, rtol, ic)
+        desc = ("EXAMPLES/cbm4 TLM/RK_TLM: Radau-2A (ICNTRL(3)=1), NTLM=32, Y_tlm(t0)=I, preset direct TLM solve (3N x 3N DGETRF per accepted "
+                "step), 12h..84h, rtol 0.1f*1e-5, atol 0.1f*1e-7")
+        ncpu = 32
+        # state sweep (real + complex factorisations) + per accepted step one (2/3 (3n)^3 + (3n)^2) factorisation, 3 Jacobians and
+        # NTLM x (3 dense mat-vecs + 2 (3n)^2 solve)
+        flops = lambda r: (float(r.istatus[:, 0].astype(np.float64).sum()) * 573 + float((r.istatus[:, 1] - 3 * r.istatus[:, 3]).astype(np.float64).sum()) * 636
+                           + float((r.istatus[:, 5] - r.istatus[:, 3]).astype(np.float64).sum()) * 5.0 * (2.0 * 32 ** 3 / 3.0 + 32 ** 2)
+                           + float((r.istatus[:, 6] - 32 * r.istatus[:, 3]).astype(np.float64).sum()) * 5.0 * 32 ** 2
+                           + float(r.istatus[:, 3].astype(np.float64).sum()) * (2.0 * 96 ** 3 / 3.0 + 96 ** 2 + 3 * 636 + 32 * (3 * 2.0 * 32 ** 2 + 2.0 * 96 ** 2)))
     elif w == "cbm4_sdirk_adj":
         rtol, atol = tolerances()
         y0 = perturbed_states(F.initial_state("cbm4"), nc)

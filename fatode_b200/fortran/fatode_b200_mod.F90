@@ -10,6 +10,7 @@
 !     MODULE SDIRK_f90_Integrator   :: INTEGRATE       (FWD/SDIRK/SDIRK_f90_Integrator.F90:25)   after fatode_b200_set_family(FATODE_FAMILY_SDIRK)
 !     MODULE RK_f90_Integrator      :: INTEGRATE       (FWD/RK/RK_f90_Integrator.F90:32)         after fatode_b200_set_family(FATODE_FAMILY_RK)
 !     MODULE RK_adj_f90_Integrator  :: INTEGRATE_ADJ   (ADJ/RK_ADJ/RK_ADJ_f90_Integrator.F90:20) after fatode_b200_set_family(FATODE_FAMILY_RK)
+!     MODULE RK_tlm_f90_Integrator  :: INTEGRATE_TLM   (TLM/RK_TLM/RK_TLM_f90_Integrator.F90:33) after fatode_b200_set_family(FATODE_FAMILY_RK)
 !     MODULE SDIRK_ADJ_f90_Integrator :: INTEGRATE_ADJ (ADJ/SDIRK_ADJ/SDIRK_ADJ_f90_Integrator.F90:29) after fatode_b200_set_family(FATODE_FAMILY_SDIRK)
 !     MODULE SDIRK_TLM_f90_Integrator :: INTEGRATE_TLM (TLM/SDIRK_TLM/SDIRK_TLM_f90_Integrator.F90:31) after fatode_b200_set_family(FATODE_FAMILY_SDIRK)
 !     MODULE ERK_f90_Integrator     :: INTEGRATE       (FWD/ERK/ERK_f90_Integrator.F90:28)       as INTEGRATE_ERK (rename on the USE line)
@@ -167,6 +168,19 @@ MODULE fatode_b200_mod
       REAL(C_DOUBLE), INTENT(IN) :: atol(*), rtol(*)
       INTEGER(C_INT) :: istatus(*), ierr(*)
       INTEGER(C_INT) :: fatode_sdirk_integrate_tlm_batch
+    END FUNCTION
+    FUNCTION fatode_rk_integrate_tlm_batch(model, ncells, nvar, ntlm, y, y_tlm, tin, tout, atol_tlm, rtol_tlm, atol, rtol, &
+                                           icntrl_u, rcntrl_u, istatus, rstatus, ierr, model_params, mem, stream) &
+                                           BIND(C, NAME='fatode_rk_integrate_tlm_batch')
+      IMPORT :: C_INT, C_INT64_T, C_DOUBLE, C_PTR
+      INTEGER(C_INT), VALUE :: model, nvar, ntlm, mem
+      INTEGER(C_INT64_T), VALUE :: ncells
+      REAL(C_DOUBLE), VALUE :: tin, tout
+      REAL(C_DOUBLE) :: y(*), y_tlm(*), rstatus(*)
+      TYPE(C_PTR), VALUE :: atol_tlm, rtol_tlm, icntrl_u, rcntrl_u, model_params, stream
+      REAL(C_DOUBLE), INTENT(IN) :: atol(*), rtol(*)
+      INTEGER(C_INT) :: istatus(*), ierr(*)
+      INTEGER(C_INT) :: fatode_rk_integrate_tlm_batch
     END FUNCTION
   END INTERFACE
 
@@ -369,6 +383,11 @@ CONTAINS
                                             pat, prt, ATOL, RTOL, pic, prc, ist, rst, ierr, C_NULL_PTR, FATODE_MEM_HOST, C_NULL_PTR)
       IF (rc /= 0) ierr(1) = rc
       IF (ierr(1) < 0) PRINT *, 'SDIRK-TLM: Unsuccessful exit at T=', TIN, ' (IERR=', ierr(1), ')'   ! as :94-96
+    ELSE IF (current_family == FATODE_FAMILY_RK) THEN   ! TLM/RK_TLM INTEGRATE_TLM (RK_TLM_f90_Integrator.F90:33)
+      rc = fatode_rk_integrate_tlm_batch(current_model, 1_C_INT64_T, INT(N, C_INT), INT(NTLM, C_INT), Y, Y_tlm, TIN, TOUT, &
+                                         pat, prt, ATOL, RTOL, pic, prc, ist, rst, ierr, C_NULL_PTR, FATODE_MEM_HOST, C_NULL_PTR)
+      IF (rc /= 0) ierr(1) = rc
+      IF (ierr(1) < 0) PRINT *, 'Runge-Kutta-TLM: Unsuccessful exit at T=', TIN, ' (IERR=', ierr(1), ')'   ! as :95-97
     ELSE
       rc = fatode_ros_integrate_tlm_batch(current_model, 1_C_INT64_T, INT(N, C_INT), INT(NTLM, C_INT), Y, Y_tlm, TIN, TOUT, &
                                           pat, prt, ATOL, RTOL, pic, prc, ist, rst, ierr, C_NULL_PTR, FATODE_MEM_HOST, C_NULL_PTR)

@@ -24,6 +24,9 @@ r = F.integrate_rk("cbm4", T0, T1, y, rtol, atol, icntrl_u=icr); print("rk", (r.
 r = F.integrate_adj("cbm4", T0, T1, y[:12], 32, rtol, atol, icntrl_u=icr, family="rk"); print("rk_adj", (r.ierr == 1).all(), F.last_stats().cells_general)
 r = F.integrate_adj("cbm4", T0, T1, y[:12], 32, rtol, atol, family="sdirk"); print("sdirk_adj", (r.ierr == 1).all(), F.last_stats().cells_general)
 r = F.integrate_tlm("cbm4", T0, T1, y[:12], np.tile(np.eye(32), (12, 1, 1)), rtol, atol, family="sdirk"); print("sdirk_tlm", (r.ierr == 1).all())
+r = F.integrate_tlm("cbm4", T0, T1, y[:12], np.tile(np.eye(32), (12, 1, 1)), rtol, atol, icntrl_u=icr, family="rk"); print("rk_tlm (direct)", (r.ierr == 1).all())
+icd = icr.copy(); icd[6] = 2
+r = F.integrate_adj("cbm4", T0, T1, y[:12], 32, rtol, atol, icntrl_u=icd, family="rk"); print("rk_adj direct", (r.ierr == 1).all())
 loose_r, loose_a = np.full(32, F01 * 1e-2), np.full(32, F01 * 1e-4)      # general-pivoting passes
 r = F.integrate_adj("cbm4", T0, T1, y[:12], 8, loose_r, loose_a, family="sdirk"); print("sdirk_adj general pass", (r.ierr == 1).all(), F.last_stats().cells_general)
 r = F.integrate_adj("cbm4", T0, T1, y[:12], 8, loose_r, loose_a, icntrl_u=icr, family="rk"); print("rk_adj general pass", (r.ierr == 1).all(), F.last_stats().cells_general)

@@ -58,6 +58,21 @@ for k in (1e-2, 1e-3, 1e-4, 1e-5):
     r = F.integrate_adj("cbm4", T0, t1, y0, 32, rtol, atol, family="sdirk")
     o = O.sdirk_adj("cbm4", y0, 32, T0, t1, atol, rtol)
     report(f"SDIRK_ADJ rtol {F01*k:.0e} n {nc}", r, o, [("Lambda", r.lambda_, o["lambda_"]), ("Mu", r.mu, o["mu"])])
+for k in (1e-2, 1e-3, 1e-4, 1e-5):   # Runge-Kutta big-system modes: TLM/RK_TLM (preset direct solve) and RK_ADJ with ICNTRL(7) = 2
+    rtol, atol = np.full(32, F01 * k), np.full(32, F01 * k * 1e-2)
+    nb = max(16, nc // 4)
+    y0 = perturbed_states(F.initial_state("cbm4"), nb, first_cell=first)
+    first += nb
+    t1 = T0 + 20 * 3600.0
+    ic = np.zeros(20, dtype=np.int32); ic[2] = 1
+    yt = np.tile(np.eye(32), (nb, 1, 1))
+    r = F.integrate_tlm("cbm4", T0, t1, y0, yt, rtol, atol, icntrl_u=ic, family="rk")
+    o = O.rk_tlm("cbm4", y0, yt, T0, t1, atol, rtol, ic)
+    report(f"RK_TLM rtol {F01*k:.0e} n {nb} (general path cells {F.last_stats().cells_general})", r, o, [("Y_tlm", r.y_tlm, o["y_tlm"])])
+    ic[6] = 2
+    r = F.integrate_adj("cbm4", T0, t1, y0, 32, rtol, atol, icntrl_u=ic, family="rk")
+    o = O.rk_adj("cbm4", y0, 32, T0, t1, atol, rtol, ic)
+    report(f"RK_ADJ direct rtol {F01*k:.0e} n {nb} (general path cells {F.last_stats().cells_general})", r, o, [("Lambda", r.lambda_, o["lambda_"]), ("Mu", r.mu, o["mu"])], 1e-7)
 for k in (1e-2, 1e-3, 1e-4):
     rtol, atol = np.full(32, F01 * k), np.full(32, F01 * k * 1e-2)
     y0 = perturbed_states(F.initial_state("cbm4"), nc, first_cell=first)
