@@ -1254,6 +1254,24 @@ static int broadcast_ierr(int64_t ncells, int code, int* istatus, double* rstatu
   return 0;
 }
 
+// Continuous Rosenbrock adjoint (ICNTRL(7) = 3) for cbm4, on top of a forward-only sweep: the extra FUN / JAC (/ time derivative)
+// of the last checkpoint (ADJ/ROS_ADJ/ROS_ADJ_f90_Integrator.F90:1143-1157), ADJINIT of the driver (Lambda = I, Mu = 0), and the
+// IERR -7 (-6) with which ros_CadjInt leaves its time loop before the first step (:1511-1519; H is negative there).
+__global__ void k_ros_cadj_epilogue_cbm4(int64_t ncells, int nadj, int np, int autonomous, int max_no_steps, const double* y, double* lambda,
+                                         double* mu, int* istatus, double* rstatus, int* ierr) {
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= ncells || ierr[cell] != 1) return;
+  for (int m = 0; m < nadj; ++m)
+    for (int i = 0; i < 32; ++i) lambda[((size_t)cell * nadj + m) * 32 + i] = Cbm4Warp::adjinit_lambda(i, m, y[cell * 32 + i]);
+  if (mu && np > 0)
+    for (int q = 0; q < nadj * np; ++q) mu[(size_t)cell * nadj * np + q] = 0.0;
+  int* is_ = istatus + cell * 20;
+  is_[Nfun] += autonomous ? 1 : 2;
+  is_[Njac] += 1;
+  rstatus[cell * 20 + Nhexit] = 0.0;
+  ierr[cell] = (is_[Nstp] > max_no_steps) ? -6 : -7;
+}
+
 static int ros_batch_impl(int family, int model, int64_t ncells, int nvar, int np, int nadj, double* y, double* lambda,
                           double* mu, double tin, double tout, const double* atol, const double* rtol, const int* icntrl_u,
                           const double* rcntrl_u, int* istatus, double* rstatus, int* ierr, double* mu_sum,
@@ -1270,11 +1288,18 @@ static int ros_batch_impl(int family, int model, int64_t ncells, int nvar, int n
   RosParams rp;
   int ic[20];
   const int perr = ros_parse_options(family, nvar, icntrl_u, rcntrl_u, tin, tout, atol, rtol, rp, ic);
-  bool do_adjoint = false;
+  bool do_adjoint = false, cadj3 = false;
   if (family == FAM_ADJ) {
     const int adjtype = ic[6] == 0 ? 2 : ic[6];
-    if (perr == 1 && (adjtype == 3 || adjtype == 4))
-      return fail(FATODE_EUNSUPPORTED, "continuous adjoints (ICNTRL(7)=3,4) are outside this engine's scope");
+    // ICNTRL(7) = 3 (continuous adjoint): reproduced as the reference behaves — forward sweep, ADJINIT, then IERR -7 at the first
+    // statement of ros_CadjInt's time loop (negative H against `H <= Roundoff`, ADJ/ROS_ADJ :1517), see cadj_epilogue below.
+    // ICNTRL(7) = 4 (simplified continuous adjoint): ros_SimpleCadjInt multiplies its first stage by the Jacobian instead of its
+    // transpose (LSS_Mul_Jac :1741 vs LSS_Mul_Jactr1 :1781) and overflows within tens of steps (oracle/ros.hpp restates it,
+    // tests/test_oracle_cadj.py shows it): nothing a caller could want bit for bit.
+    if (perr == 1 && adjtype == 4)
+      return fail(FATODE_EUNSUPPORTED, "the simplified continuous adjoint (ICNTRL(7)=4) is not built: the reference routine "
+                                       "multiplies its first stage by J instead of J^T and overflows (see DESIGN.md section 8)");
+    cadj3 = (perr == 1 && adjtype == 3);
     if (perr == 1 && ic[7] != 0) return fail(FATODE_EUNSUPPORTED, "ICNTRL(8) (SaveLU) is not implemented by the reference either");
     do_adjoint = (adjtype == 2);
     if (do_adjoint && nadj > 32) return fail(FATODE_EUNSUPPORTED, "nadj > 32 per call is not supported yet");
@@ -1362,13 +1387,24 @@ static int ros_batch_impl(int family, int model, int64_t ncells, int nvar, int n
   else
     rc = ros_device_small<RobertsCell>(rp, sc, ncells, d_y, b_atol.as<double>(), b_rtol.as<double>(), d_ist, d_rst, d_ierr, st);
   if (rc != 0) return rc;
+  if (cadj3) {   // continuous adjoint: ADJINIT and the immediate IERR -7 of ros_CadjInt on top of the forward-only sweep
+    if (model == FATODE_MODEL_CBM4) {
+      k_ros_cadj_epilogue_cbm4<<<(unsigned)((ncells + 127) / 128), 128, 0, st>>>(ncells, nadj, with_mu ? np : 0, rp.autonomous ? 1 : 0,
+                                                                                rp.max_no_steps, d_y, d_lam, d_mu, d_ist, d_rst, d_ierr);
+      CUDA_TRY(cudaGetLastError());
+    } else {
+      if (int e = ros_small_cadj_epilogue_device(model, rp, sc.fix, (long)ncells, nadj, with_mu, d_y, d_lam, d_mu, d_ist, d_rst, d_ierr, st))
+        return fail(e, "continuous-adjoint epilogue of the small models failed (nadj must be 1..8)");
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
   if (mem == FATODE_MEM_HOST) {
     CUDA_TRY(cudaMemcpyAsync(y, d_y, ny, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(istatus, d_ist, sizeof(int) * 20 * ncells, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(rstatus, d_rst, sizeof(double) * 20 * ncells, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(ierr, d_ierr, sizeof(int) * ncells, cudaMemcpyDeviceToHost, st));
     if (do_tlm) CUDA_TRY(cudaMemcpyAsync(lambda, d_lam, nl, cudaMemcpyDeviceToHost, st));
-    if (family == FAM_ADJ && do_adjoint) {
+    if (family == FAM_ADJ && (do_adjoint || cadj3)) {
       CUDA_TRY(cudaMemcpyAsync(lambda, d_lam, nl, cudaMemcpyDeviceToHost, st));
       if (with_mu) CUDA_TRY(cudaMemcpyAsync(mu, d_mu, nm, cudaMemcpyDeviceToHost, st));
       if (with_mu && mu_sum) CUDA_TRY(cudaMemcpyAsync(mu_sum, d_musum, sizeof(double) * np * nadj, cudaMemcpyDeviceToHost, st));

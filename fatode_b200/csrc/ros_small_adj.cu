@@ -657,6 +657,49 @@ int small_adj_run(const RosParams& rp, const double* fix, long ncells, int nadj,
 
 }  // namespace
 
+// Continuous adjoint (ICNTRL(7) = 3) after a forward-only sweep: what RosenbrockADJ1/2 leave behind.  The forward sweep in this
+// mode evaluates FUN, JAC (and the time derivative) once more at TOUT for its last checkpoint (:1143-1157); ADJINIT runs; then
+// ros_CadjInt is entered as ros_CadjInt(NADJ, Lambda, Tend, Tstart, ...) (:588-592), i.e. backwards in time with a NEGATIVE H, and
+// its first statement inside the time loop, IF (((T+0.1d0*H) == T).OR.(H <= Roundoff)) (:1517), returns IERR = -7 (-6 when the
+// forward sweep used up Max_no_steps) before anything is integrated: Lambda = ADJINIT, RSTATUS(Nhexit) = 0.
+template <class Model>
+__global__ void k_ros_small_cadj_epilogue(long ncells, int nadj, int with_mu, int autonomous, int max_no_steps, const double* y,
+                                          double* lambda, double* mu, int* istatus, double* rstatus, int* ierr, double fix0, double fix1) {
+  constexpr int N = Model::N, NP = Model::NP;
+  const long cell = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= ncells || ierr[cell] != 1) return;
+  Model mdl;
+  const double fix[2] = {fix0, fix1};
+  mdl.init(fix);
+  double Y[N], Lambda[N * SA_MAXADJ], Mu[(NP > 0 ? NP : 1) * SA_MAXADJ];
+  for (int i = 0; i < N; ++i) Y[i] = y[cell * N + i];
+  const bool wm = with_mu != 0 && NP > 0;
+  mdl.adjinit(nadj, Y, Lambda, wm ? Mu : nullptr);
+  for (int m = 0; m < nadj; ++m)
+    for (int i = 0; i < N; ++i) lambda[((size_t)cell * nadj + m) * N + i] = Lambda[i + N * m];
+  if (wm && mu)
+    for (int m = 0; m < nadj; ++m)
+      for (int p = 0; p < NP; ++p) mu[((size_t)cell * nadj + m) * NP + p] = Mu[p + NP * m];
+  int* is_ = istatus + cell * 20;
+  is_[Nfun] += autonomous ? 1 : 2;
+  is_[Njac] += 1;
+  rstatus[cell * 20 + Nhexit] = 0.0;
+  ierr[cell] = (is_[Nstp] > max_no_steps) ? -6 : -7;
+}
+
+int ros_small_cadj_epilogue_device(int model, const RosParams& rp, const double* fix, long ncells, int nadj, bool with_mu, const double* d_y,
+                                   double* d_lambda, double* d_mu, int* d_istatus, double* d_rstatus, int* d_ierr, cudaStream_t st) {
+  if (nadj < 1 || nadj > SA_MAXADJ) return -105;
+  const unsigned blocks = (unsigned)((ncells + 63) / 64);
+  if (model == FATODE_MODEL_SMALL_STRATO)
+    k_ros_small_cadj_epilogue<SmallStratoAdj><<<blocks, 64, 0, st>>>(ncells, nadj, 0, rp.autonomous, rp.max_no_steps, d_y, d_lambda, d_mu,
+                                                                     d_istatus, d_rstatus, d_ierr, fix[0], fix[1]);
+  else
+    k_ros_small_cadj_epilogue<RobertsAdj><<<blocks, 64, 0, st>>>(ncells, nadj, with_mu ? 1 : 0, rp.autonomous, rp.max_no_steps, d_y, d_lambda,
+                                                                 d_mu, d_istatus, d_rstatus, d_ierr, fix[0], fix[1]);
+  return cudaGetLastError() == cudaSuccess ? 0 : -103;
+}
+
 // model: FATODE_MODEL_SMALL_STRATO or FATODE_MODEL_ROBERTS; device arrays; y is read as y0 and overwritten with y(TOUT)
 int ros_small_adj_device(int model, const RosParams& rp, const double* fix, long ncells, int nadj, bool with_mu, double* d_y,
                          double* d_lambda, double* d_mu, const double* d_atol, const double* d_rtol, int* d_istatus,

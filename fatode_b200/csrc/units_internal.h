@@ -30,6 +30,8 @@ int ros_tlm_lock_device(const RosParams& rp, const Cbm4Const& mc, long ncells, c
                         UnitTiming& tm, std::string& err);
 
 // ros_small_adj.cu — INTEGRATE_ADJ (ADJ/ROS_ADJ, discrete adjoint) for small_strato / roberts, one system per thread; device arrays
+int ros_small_cadj_epilogue_device(int model, const RosParams& rp, const double* fix, long ncells, int nadj, bool with_mu, const double* d_y,
+                                   double* d_lambda, double* d_mu, int* d_istatus, double* d_rstatus, int* d_ierr, cudaStream_t st);
 int ros_small_adj_device(int model, const RosParams& rp, const double* fix, long ncells, int nadj, bool with_mu, double* d_y,
                          double* d_lambda, double* d_mu, const double* d_atol, const double* d_rtol, int* d_istatus,
                          double* d_rstatus, int* d_ierr, size_t tape_budget, cudaStream_t st, UnitTiming& tm, std::string& err);

@@ -79,9 +79,14 @@ int fatode_ros_integrate_batch(int model, int64_t ncells, int nvar, double* y, d
  * Discrete adjoint (ICNTRL(7) = 0 or 2) or forward only (1).  ICNTRL_U/RCNTRL_U override when >= 0
  * (:91-96).  mu == NULL or np == 0 selects the Lambda-only mode (RosenbrockADJ2).  ADJINIT is the
  * model's registered routine.  ATOL_adj/RTOL_adj are accepted for signature parity and unused (the
- * reference uses them only for the continuous adjoint).  Quadrature arguments (Q, QFUN, DRDY, DRDP,
- * HESSTR_VEC_R*) and the continuous adjoints (ICNTRL(7) = 3,4) are outside the engine's scope
- * (FATODE_EUNSUPPORTED).
+ * reference reads them only in the continuous adjoint, which never gets that far).  ICNTRL(7) = 3 (continuous adjoint) behaves
+ * as the reference does: INTEGRATE_ADJ enters ros_CadjInt backwards in time with a negative H, whose first test
+ * `H <= Roundoff` (:1517) returns IERR -7 at once — per cell: the forward solution, ADJINIT's Lambda / Mu, the forward
+ * counters plus the last checkpoint's FUN / JAC, RSTATUS(Nhexit) = 0, IERR -7 (-6 if the forward sweep used up Max_no_steps).
+ * ICNTRL(7) = 4 (simplified continuous adjoint) returns FATODE_EUNSUPPORTED: ros_SimpleCadjInt multiplies its first stage by J
+ * instead of J^T (:1741) and overflows within tens of steps (restated and shown in oracle/ros.hpp, tests/test_ros_cadj.py).
+ * Quadrature arguments (Q, QFUN, DRDY, DRDP, HESSTR_VEC_R*) are not accepted: the reference's quadrature weights ros_W come
+ * from a loop that never executes (:1241-1248).
  * Models: cbm4 (nadj <= 32; the headline path), small_strato (RosenbrockADJ2, EXAMPLES/small_strato/small_ros_adj) and
  * roberts (NP = 3, EXAMPLES/roberts/ROBERTS_ROS_ADJ without its quadrature terms), nadj <= 8 for the two small models.
  * mu_sum (may be NULL): [nadj][np] sum over all cells of this call with ierr == 1, reduced in a

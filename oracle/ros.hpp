@@ -14,7 +14,8 @@
 // Deliberate decisions on reference defects:
 //  * `ELSEIF (Max_no_steps > 0)` (ADJ :417) reads an uninitialised variable; restated as the
 //    evident intent `ICNTRL(4) > 0`.
-//  * quadrature-cost path (Q/QFUN, ros_W) and continuous adjoints (ICNTRL(7)=3,4) are out of scope.
+//  * quadrature-cost path (Q/QFUN, ros_W) is out of scope (its ros_W weights come from a loop that never runs);
+//    the continuous adjoints (ICNTRL(7) = 3, 4) are restated with their quirks (cadjoint, simple_cadjoint below).
 //  * SaveLU (ICNTRL(8)) is honoured on read but never implemented upstream; only 0 is accepted.
 #pragma once
 #include <cmath>
@@ -102,6 +103,7 @@ static inline double ros_error_norm(int N, const double* Y, const double* Ynew, 
 }
 
 struct RosTapeEntry { double T, H; std::vector<double> Ystage, K; };
+struct RosCTapeEntry { double T, H; std::vector<double> Y, dY; };   // ros_CPush :785-805 (chk_d2Y is only read by ros_Hermite5, never reached)
 
 // Per-call linear-solver state (module ls_solver/lapack in the reference)
 template <int N>
@@ -152,6 +154,7 @@ struct Rosenbrock {
   double RSTATUS[20];
   LssDense<N> lss;
   std::vector<RosTapeEntry> tape;   // chk_T, chk_H, chk_Y, chk_K
+  std::vector<RosCTapeEntry> ctape;  // continuous adjoints: chk_T, chk_H, chk_Y, chk_dY
   explicit Rosenbrock(Model& m) : mdl(m) { std::memset(ISTATUS, 0, sizeof ISTATUS); std::memset(RSTATUS, 0, sizeof RSTATUS); }
 
   // ros_FunTimeDerivative: ADJ :1870-1890 / FWD :667-688
@@ -187,7 +190,7 @@ struct Rosenbrock {
   // ros_Integrator (FWD :433-629) and ros_FwdInt (ADJ :877-1173); `adj` selects the family quirks:
   // tape push, Ndec/Nsol counting, RSTATUS(Nhexit)=H at loop top (ADJ :963).
   int forward(double* Y, double Tstart, double Tend, const double* AbsTol, const double* RelTol, bool adj,
-              bool count_la) {
+              bool count_la, bool cadj = false) {   // cadj: AdjointType continuous / simple continuous (checkpoints :1058-1065, 1143-1157)
     const RosTableauData& tb = cfg.tab;
     const int S = tb.S;
     double Ynew[N], Fcn0[N], Fcn[N], dFdT[N], Yerr[N];
@@ -207,7 +210,7 @@ struct Rosenbrock {
     while ((Direction > 0 && (T - Tend) + Roundoff <= 0.0) || (Direction < 0 && (Tend - T) + Roundoff <= 0.0)) {
       if (ISTATUS[Nstp] > cfg.Max_no_steps) return -6;
       if ((T + cfg.tenth * H) == T || H <= Roundoff) return -7;
-      if (adj) RSTATUS[Nhexit] = H;
+      if (adj || cadj) RSTATUS[Nhexit] = H;   // ros_FwdInt :963
       H = std::fmin(H, std::fabs(Tend - T));
       mdl.fun(T, Y, Fcn0);
       ISTATUS[Nfun]++;
@@ -261,6 +264,7 @@ struct Rosenbrock {
         if (Err <= 1.0 || H <= cfg.Hmin) {
           ISTATUS[Nacc]++;
           if (adj) { tape.push_back(RosTapeEntry{T, H, Ystage, K}); }   // ros_DPush :735-755
+          if (cadj) ctape.push_back(RosCTapeEntry{T, H, std::vector<double>(Y, Y + N), std::vector<double>(Fcn0, Fcn0 + N)});
           for (int i = 0; i < N; ++i) Y[i] = Ynew[i];
           T = T + Direction * H;
           Hnew = std::fmax(cfg.Hmin, std::fmin(Hnew, cfg.Hmax));
@@ -281,7 +285,141 @@ struct Rosenbrock {
         }
       }
     }
+    if (cadj) {   // "Save last state: only needed for continuous adjoint" (:1143-1157)
+      mdl.fun(T, Y, Fcn0);
+      ISTATUS[Nfun]++;
+      mdl.jac(T, Y, lss.fjac);
+      ISTATUS[Njac]++;
+      if (!cfg.Autonomous) fun_time_derivative(T, Y, Fcn0, dFdT);   // feeds chk_d2Y only; its FUN call is counted
+      ctape.push_back(RosCTapeEntry{T, H, std::vector<double>(Y, Y + N), std::vector<double>(Fcn0, Fcn0 + N)});
+    }
     return 1;
+  }
+
+  // ros_CadjInt :1447-1671, called as ros_CadjInt(NADJ, Lambda, Tend, Tstart, ...) (:588-592): the adjoint runs backwards in
+  // time, so Direction = -1 and H = Direction*H is negative — and the first pass through the time loop stops at
+  // `IF ( ((T+0.1d0*H) == T).OR.(H <= Roundoff) )` (:1517) with IERR = -7 before anything is computed.  The continuous adjoint of
+  // the reference therefore returns ADJINIT's Lambda and "Step size too small" for every forward-in-time problem; restated as is.
+  int cadjoint(double Tstart, double Tend) {
+    RSTATUS[Nhexit] = 0.0;
+    double H = std::fmin(std::fmax(std::fabs(cfg.Hmin), std::fabs(cfg.Hstart)), std::fabs(cfg.Hmax));
+    if (std::fabs(H) <= 10.0 * cfg.Roundoff) H = 1.0e-5;
+    const int Direction = (Tend >= Tstart) ? +1 : -1;
+    H = Direction * H;
+    const double T = Tstart;
+    if (!((Direction > 0 && (T - Tend) + cfg.Roundoff <= 0.0) || (Direction < 0 && (Tend - T) + cfg.Roundoff <= 0.0))) return 1;
+    if (ISTATUS[Nstp] > cfg.Max_no_steps) return -6;
+    if ((T + 0.1 * H) == T || H <= cfg.Roundoff) return -7;
+    return -100;   // a backward-in-time forward problem (Direction = +1 here): not restated
+  }
+
+  // ros_SimpleCadjInt :1675-1834: the adjoint ODE on the forward sweep's step sequence, no error control, with the method
+  // CadjMethod selected by ICNTRL(6).  Restated with its quirks: the first stage multiplies by the (negated) Jacobian itself,
+  // LSS_Mul_Jac (:1741), the later stages by its transpose (:1781); the stage Jacobians are taken at Hermite-interpolated states.
+  int simple_cadjoint(int NADJ, double* Lambda, double Tstart, double Tend) {
+    const RosTableauData& tb = cfg.tab;
+    const int S = tb.S;
+    const int Direction = (Tend >= Tstart) ? -1 : +1;
+    std::vector<double> Ynew((size_t)N * NADJ), Fcn0((size_t)N * NADJ), Fcn((size_t)N * NADJ), K((size_t)N * S * NADJ), dFdT((size_t)N * NADJ);
+    double Y0[N];
+    const int LD = N * S;
+    for (int istack = (int)ctape.size(); istack >= 2; --istack) {
+      const RosCTapeEntry& hi = ctape[istack - 1];
+      const RosCTapeEntry& lo = ctape[istack - 2];
+      const double T = hi.T, H = lo.H;
+      for (int i = 0; i < N; ++i) Y0[i] = hi.Y[i];
+      mdl.jac(T, Y0, lss.fjac);
+      ISTATUS[Njac]++;
+      if (!cfg.Autonomous) {
+        const double Delta = std::sqrt(cfg.Roundoff) * std::fmax(1.0e-5, std::fabs(T));
+        mdl.jac(T + Delta, Y0, lss.djdt);
+        ISTATUS[Njac]++;
+        lss.jac_time_derivative(Delta);
+        for (int m = 0; m < NADJ; ++m) {
+          lss.mul_djdttr(&dFdT[(size_t)N * m], Lambda + (size_t)N * m);
+          for (int i = 0; i < N; ++i) dFdT[(size_t)N * m + i] = (-1.0) * dFdT[(size_t)N * m + i];
+        }
+      }
+      for (int i = 0; i < N * N; ++i) lss.fjac[i] = -lss.fjac[i];                    // LSS_Rev_Jac
+      for (int m = 0; m < NADJ; ++m) lss.mul_jac(&Fcn0[(size_t)N * m], Lambda + (size_t)N * m);
+      const double ghinv = 1.0 / (Direction * H * tb.Gamma[0]);
+      const int j = lss.decomp(ghinv);
+      ISTATUS[Ndec]++;
+      if (j != 0) return -8;                                                            // the reference STOPs
+      for (int istage = 1; istage <= S; ++istage) {
+        const int ioffset = N * (istage - 1);
+        if (istage == 1) {
+          for (size_t q = 0; q < (size_t)N * NADJ; ++q) Fcn[q] = Fcn0[q];
+        } else if (tb.NewF[istage - 1]) {
+          for (size_t q = 0; q < (size_t)N * NADJ; ++q) Ynew[q] = Lambda[q];
+          for (int jj = 1; jj <= istage - 1; ++jj) {
+            const double a = tb.A[(istage - 1) * (istage - 2) / 2 + jj - 1];
+            for (int m = 0; m < NADJ; ++m)
+              for (int i = 0; i < N; ++i) Ynew[(size_t)N * m + i] = Ynew[(size_t)N * m + i] + a * K[(size_t)LD * m + N * (jj - 1) + i];
+          }
+          const double Tau = T + tb.Alpha[istage - 1] * Direction * H;
+          hermite3(lo.T, hi.T, Tau, lo.Y.data(), hi.Y.data(), lo.dY.data(), hi.dY.data(), Y0);
+          mdl.jac(Tau, Y0, lss.fjac1);
+          ISTATUS[Njac]++;
+          for (int i = 0; i < N * N; ++i) lss.fjac1[i] = -lss.fjac1[i];                // LSS_Rev_Jac1
+          for (int m = 0; m < NADJ; ++m) {                                            // LSS_Mul_Jactr1
+            const double* g = &Ynew[(size_t)N * m];
+            double* z = &Fcn[(size_t)N * m];
+            for (int i = 0; i < N; ++i) { double sm = 0.0; for (int k = 0; k < N; ++k) sm += lss.fjac1[k + N * i] * g[k]; z[i] = sm; }
+          }
+        }
+        for (int m = 0; m < NADJ; ++m)
+          for (int i = 0; i < N; ++i) K[(size_t)LD * m + ioffset + i] = Fcn[(size_t)N * m + i];
+        for (int jj = 1; jj <= istage - 1; ++jj) {
+          const double HC = tb.C[(istage - 1) * (istage - 2) / 2 + jj - 1] / (Direction * H);
+          for (int m = 0; m < NADJ; ++m)
+            for (int i = 0; i < N; ++i) K[(size_t)LD * m + ioffset + i] = K[(size_t)LD * m + ioffset + i] + HC * K[(size_t)LD * m + N * (jj - 1) + i];
+        }
+        if (!cfg.Autonomous && tb.Gamma[istage - 1] != 0.0) {
+          const double HG = Direction * H * tb.Gamma[istage - 1];
+          for (int m = 0; m < NADJ; ++m)
+            for (int i = 0; i < N; ++i) K[(size_t)LD * m + ioffset + i] = K[(size_t)LD * m + ioffset + i] + HG * dFdT[(size_t)N * m + i];
+        }
+        for (int m = 0; m < NADJ; ++m) {
+          lss.solve(true, &K[(size_t)LD * m + ioffset]);
+          ISTATUS[Nsol]++;
+        }
+      }
+      for (int m = 0; m < NADJ; ++m)
+        for (int jj = 1; jj <= S; ++jj) {
+          const double mj = tb.M[jj - 1];
+          for (int i = 0; i < N; ++i) Lambda[(size_t)N * m + i] = Lambda[(size_t)N * m + i] + mj * K[(size_t)LD * m + N * (jj - 1) + i];
+        }
+    }
+    return 1;
+  }
+
+  // ros_Hermite3 :1999-2042: cubic Hermite interpolant, coefficients assembled with DCOPY/DSCAL/DAXPY in the reference's order
+  static void hermite3(double a, double b, double T, const double* Ya, const double* Yb, const double* Ja, const double* Jb, double* Y) {
+    double amb[3];
+    amb[0] = 1.0 / (a - b);
+    for (int i = 1; i < 3; ++i) amb[i] = amb[i - 1] * amb[0];
+    double C3[N], C4[N];
+    // REAL(4) literals times DOUBLE PRECISION: the literal is converted exactly, the product is double
+    const double m3 = -3.0 * amb[1], p3 = 3.0 * amb[1], p2a = 2.0 * amb[0];
+    for (int i = 0; i < N; ++i) C3[i] = Ya[i];
+    for (int i = 0; i < N; ++i) C3[i] = m3 * C3[i];
+    for (int i = 0; i < N; ++i) C3[i] = C3[i] + p3 * Yb[i];
+    for (int i = 0; i < N; ++i) C3[i] = C3[i] + p2a * Ja[i];
+    for (int i = 0; i < N; ++i) C3[i] = C3[i] + amb[0] * Jb[i];
+    const double m2 = -2.0 * amb[2], p2 = 2.0 * amb[2];
+    for (int i = 0; i < N; ++i) C4[i] = Ya[i];
+    for (int i = 0; i < N; ++i) C4[i] = m2 * C4[i];
+    for (int i = 0; i < N; ++i) C4[i] = C4[i] + p2 * Yb[i];
+    for (int i = 0; i < N; ++i) C4[i] = C4[i] + amb[1] * Ja[i];
+    for (int i = 0; i < N; ++i) C4[i] = C4[i] + amb[1] * Jb[i];
+    const double Tau = T - a;
+    const double t3 = Tau * Tau * Tau, t2 = Tau * Tau;     // Tau**3, TAU**(j-1) with integer exponents: repeated products
+    for (int i = 0; i < N; ++i) Y[i] = C4[i];
+    for (int i = 0; i < N; ++i) Y[i] = t3 * Y[i];
+    for (int i = 0; i < N; ++i) Y[i] = Y[i] + t2 * C3[i];
+    for (int i = 0; i < N; ++i) Y[i] = Y[i] + Tau * Ja[i];
+    for (int i = 0; i < N; ++i) Y[i] = Y[i] + 1.0 * Ya[i];
   }
 
   // ros_DadjInt: ADJ1 :1177-1441 (with Mu) / ADJ2 :3508-3700 (Lambda only), GetQuad = false
@@ -585,13 +723,19 @@ int ros_integrate_adj(Model& mdl, int NP, int NADJ, double* Y, double* Lambda, d
   Rosenbrock<Model> r(mdl);
   int IERR = ros_parse(ROS_ADJ, Model::N, ICNTRL, RCNTRL, TIN, TOUT, ATOL, RTOL, r.cfg);
   const int AdjointType = (ICNTRL[6] == 0) ? 2 : ICNTRL[6];
-  if (IERR == 1 && (AdjointType == 3 || AdjointType == 4)) IERR = -9;   // continuous adjoints: out of scope
+  const bool cadj = (AdjointType == 3 || AdjointType == 4);
   if (IERR == 1 && ICNTRL[7] != 0) IERR = -9;                            // SaveLU never implemented upstream
   const bool with_mu = (NP > 0 && Mu != nullptr);
-  if (IERR == 1) IERR = r.forward(Y, TIN, TOUT, ATOL, RTOL, /*adj=*/AdjointType == 2, /*count_la=*/true);
+  if (IERR == 1) IERR = r.forward(Y, TIN, TOUT, ATOL, RTOL, /*adj=*/AdjointType == 2, /*count_la=*/true, cadj);
   if (IERR == 1) {
+    if (cadj) {   // the method that integrates the continuous adjoint: ICNTRL(6), default Ros4 (:426-435, 559-577)
+      const int CadjMethod = (ICNTRL[5] == 0) ? 3 : ICNTRL[5];
+      r.cfg.tab = ROS_TABLEAU_D[CadjMethod - 1];
+    }
     mdl.adjinit(NADJ, TOUT, Y, Lambda, with_mu ? Mu : nullptr);          // :579
     if (AdjointType == 2) IERR = r.adjoint(NADJ, NP, Lambda, with_mu ? Mu : nullptr, TIN, TOUT);
+    else if (AdjointType == 3) IERR = r.cadjoint(TOUT, TIN);             // called with (Tend, Tstart) (:588-592)
+    else if (AdjointType == 4) IERR = r.simple_cadjoint(NADJ, Lambda, TIN, TOUT);
   }
   if (ISTATUS_U) for (int i = 0; i < 20; ++i) ISTATUS_U[i] = r.ISTATUS[i];
   if (RSTATUS_U) for (int i = 0; i < 20; ++i) RSTATUS_U[i] = r.RSTATUS[i];
