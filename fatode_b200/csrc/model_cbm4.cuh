@@ -228,9 +228,6 @@ struct Cbm4Warp {
   template <class F>
   __device__ __forceinline__ static void mt_rows(const double* Mv, const double (&x)[32], F&& f) { cbm4_dev::mt_rows(Mv, x, f); }
   __device__ __forceinline__ static void jt_vec1(const double* Jv, const double (&x)[32], double (&v)[32]) { cbm4_dev::jt_vec1(Jv, x, v); }
-  __device__ __forceinline__ static void mt_rows_acc(const double* Mv, const double (&x)[32], const double* vs, double (&acc)[32]) {
-    cbm4_dev::mt_rows_acc(Mv, x, vs, acc);
-  }
   template <class F>
   __device__ __forceinline__ static void stoich_cols(const double (&x)[32], F&& f) { cbm4_dev::stoich_cols(x, f); }
   // adjinit (dr.F90:101-117): Lambda = I, Mu = 0

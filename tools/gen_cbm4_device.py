@@ -490,19 +490,6 @@ def main():
                 w(f"    a{t % 2} = fma(Jv[{e}], x[{k}], a{t % 2});")
             w(f"    v[{r}] = a0 + a1; }}")
     w("}")
-    w("// acc[r] += vs[r * 32] + (M'^T x)_r: the running sum and the V_i entry seed the two multiply-add chains of the row")
-    w("__device__ __forceinline__ void mt_rows_acc(const double* __restrict__ Mv, const double (&x)[32], const double* __restrict__ vs, double (&acc)[32]) {")
-    me = 0
-    for r in range(N):
-        terms = []
-        while me < NM and mpat[me][1] == r:
-            terms.append((me, mpat[me][0]))
-            me += 1
-        w(f"  {{ double a0 = acc[{r}], a1 = vs[{r} * 32];")
-        for t, (e, k) in enumerate(terms):
-            w(f"    a{t % 2} = fma(Mv[{e}], x[{k}], a{t % 2});")
-        w(f"    acc[{r}] = a0 + a1; }}")
-    w("}")
     w("// s_p = sum_r STOICM(r, JCOEFF[p]) * x_r  (column p of the stoichiometric matrix; REAL(4) literals)")
     w("template <class F> __device__ __forceinline__ void stoich_cols(const double (&x)[32], F&& f) {")
     nst = 0
