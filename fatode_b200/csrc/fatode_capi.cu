@@ -1857,7 +1857,6 @@ extern "C" int fatode_rk_integrate_tlm_batch(int model, int64_t ncells, int nvar
                                              double tout, const double* atol_tlm, const double* rtol_tlm, const double* atol,
                                              const double* rtol, const int* icntrl_u, const double* rcntrl_u, int* istatus,
                                              double* rstatus, int* ierr, const double* model_params, int mem, void* stream) {
-  (void)atol_tlm; (void)rtol_tlm;   // only read with ICNTRL(9) / ICNTRL(12), which are not built
   g_err.clear();
   if (ncells < 0 || !y || !y_tlm || !atol || !rtol || !istatus || !rstatus || !ierr) return fail(FATODE_EINVAL, "NULL required argument");
   if (int e = check_model_dims(model, nvar, 0)) return e;
@@ -2137,7 +2136,6 @@ extern "C" int fatode_sdirk_integrate_tlm_batch(int model, int64_t ncells, int n
                                                 double tout, const double* atol_tlm, const double* rtol_tlm, const double* atol,
                                                 const double* rtol, const int* icntrl_u, const double* rcntrl_u, int* istatus,
                                                 double* rstatus, int* ierr, const double* model_params, int mem, void* stream) {
-  (void)atol_tlm; (void)rtol_tlm;   // only read with ICNTRL(9) / ICNTRL(12), which are not built
   g_err.clear();
   if (ncells < 0 || !y || !y_tlm || !atol || !rtol || !istatus || !rstatus || !ierr) return fail(FATODE_EINVAL, "NULL required argument");
   if (int e = check_model_dims(model, nvar, 0)) return e;
@@ -2156,9 +2154,11 @@ extern "C" int fatode_sdirk_integrate_tlm_batch(int model, int64_t ncells, int n
   int tlm_opt[3] = {0, 0, 0};
   const int perr = sdirk_parse_options(nvar, ic, rcntrl_u, tin, tout, atol, rtol, sp, tlm_opt);
   if (perr < 0) return broadcast_ierr(ncells, perr, istatus, rstatus, ierr, mem, st);
-  if (tlm_opt[0] == 1) return fail(FATODE_EUNSUPPORTED, "SDIRK_TLM direct TLM solve (ICNTRL(7) = 1) is not built; use the preset modified Newton");
-  if (tlm_opt[1] != 0 || tlm_opt[2] != 0)
-    return fail(FATODE_EUNSUPPORTED, "SDIRK_TLM with the columns in the Newton / truncation error control (ICNTRL(9), ICNTRL(12)) is not built");
+  // the modes in which the columns feed back into the step sequence run in the lock-step kernel (sdirk_tlm_lock.cu)
+  const bool direct = (tlm_opt[0] == 1), newton_est = (tlm_opt[1] != 0), trunc = (tlm_opt[2] != 0);
+  const bool lock = direct || newton_est || trunc;
+  if ((newton_est || trunc) && (!atol_tlm || !rtol_tlm))
+    return fail(FATODE_EINVAL, "ICNTRL(9) / ICNTRL(12) need atol_tlm and rtol_tlm");
   Cbm4Const mc;
   cbm4_constants(model_params, mc);
   DevBuf b_atol, b_rtol, b_y, b_yt, b_ist, b_rst, b_ierr;
@@ -2180,8 +2180,28 @@ extern "C" int fatode_sdirk_integrate_tlm_batch(int model, int64_t ncells, int n
     d_y = b_y.as<double>(); d_yt = b_yt.as<double>(); d_ist = b_ist.as<int>(); d_rst = b_rst.as<double>(); d_ierr = b_ierr.as<int>();
   }
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_cbm4_rc, mc.rc_base, sizeof(double) * 81, 0, cudaMemcpyHostToDevice, st));
-  if (int e = sdirk_tlm_device(sp, mc, ncells, ntlm, d_y, d_yt, b_atol.as<double>(), b_rtol.as<double>(), d_ist, d_rst, d_ierr, st))
+  if (lock) {
+    DevBuf b_at, b_rt;
+    if (newton_est || trunc) {   // (N, NTLM) column-major, one set per call
+      CUDA_TRY(b_at.alloc(sizeof(double) * nvar * ntlm));
+      CUDA_TRY(b_rt.alloc(sizeof(double) * nvar * ntlm));
+      CUDA_TRY(cudaMemcpyAsync(b_at.p, atol_tlm, sizeof(double) * nvar * ntlm, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(b_rt.p, rtol_tlm, sizeof(double) * nvar * ntlm, cudaMemcpyHostToDevice, st));
+    }
+    std::memset(&g_stats, 0, sizeof g_stats);
+    UnitTiming ut;
+    std::string uerr;
+    if (int e = sdirk_tlm_lock_device(sp, mc, (long)ncells, nullptr, ntlm, direct, newton_est, trunc, d_y, d_yt, b_atol.as<double>(),
+                                      b_rtol.as<double>(), b_at.as<double>(), b_rt.as<double>(), d_ist, d_rst, d_ierr, st, ut, uerr))
+      return fail(e, uerr);
+    g_stats.ms_forward += ut.ms;
+    g_stats.launches += ut.launches;
+    g_stats.launches_forward += 1;
+    g_stats.waves = 1;
+    g_stats.cells_general = ncells;
+  } else if (int e = sdirk_tlm_device(sp, mc, ncells, ntlm, d_y, d_yt, b_atol.as<double>(), b_rtol.as<double>(), d_ist, d_rst, d_ierr, st)) {
     return e;
+  }
   if (mem == FATODE_MEM_HOST) {
     CUDA_TRY(cudaMemcpyAsync(y, d_y, ny, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(y_tlm, d_yt, nt, cudaMemcpyDeviceToHost, st));

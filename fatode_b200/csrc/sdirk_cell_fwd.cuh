@@ -19,18 +19,11 @@
 #include "ros_cell_fwd.cuh"
 #include "portable_math.h"
 #include "gen/sdirk_tableau_gen.h"
+#include "sdirk_params.h"
 
 namespace fatode {
 
 constexpr int SDIRK_IERR_IRREGULAR = -20;
-
-struct SdirkParams {
-  int S;
-  double Gamma, ELO, C[5], D[5], E[5], Theta[5][5], Alpha[5][5];
-  int vector_tol, max_no_steps, newton_maxit, start_newton;
-  double roundoff, hmin, hmax, hstart, facmin, facmax, facrej, facsafe, thetamin, newtontol, qmin, qmax;
-  double tstart, tend;
-};
 
 template <class Model, int LANES>
 struct SdirkSmem {
@@ -39,16 +32,6 @@ struct SdirkSmem {
                        OFF_YJ = 11 * N_, OFF_LU = 12 * N_, DOUBLES = OFF_LU + Model::NLU;
   static constexpr size_t BYTES = sizeof(double) * DOUBLES * LANES;
 };
-
-__device__ __forceinline__ double sdirk_powi(double x, int m) {   // gfortran's x**m for INTEGER m: libgcc __powidf2
-  unsigned n = m < 0 ? 0u - (unsigned)m : (unsigned)m;
-  double y = (n % 2) ? x : 1.0;
-  while (n >>= 1) {
-    x = __dmul_rn(x, x);
-    if (n % 2) y = __dmul_rn(y, x);
-  }
-  return m < 0 ? __ddiv_rn(1.0, y) : y;
-}
 
 // TLM = true: the state part of TLM/SDIRK_TLM (SDIRK_IntegratorTLM, TLM/SDIRK_TLM/SDIRK_TLM_f90_Integrator.F90:474-911) in
 // its preset mode, where the tangent-linear columns do not influence the step control: the LU is never reused across

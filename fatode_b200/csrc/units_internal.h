@@ -6,6 +6,7 @@
 #include <string>
 #include "fatode_common.cuh"
 #include "model_cbm4.cuh"
+#include "sdirk_params.h"
 
 namespace fatode {
 
@@ -28,6 +29,13 @@ int ros_tlm_lock_device(const RosParams& rp, const Cbm4Const& mc, long ncells, c
                         double* d_y, double* d_ytlm, const double* d_atol, const double* d_rtol, const double* d_atol_tlm,
                         const double* d_rtol_tlm, int* d_istatus, double* d_rstatus, int* d_ierr, cudaStream_t st,
                         UnitTiming& tm, std::string& err);
+
+// sdirk_tlm_lock.cu — SDIRK_IntegratorTLM (TLM/SDIRK_TLM/SDIRK_TLM_f90_Integrator.F90:474-911) with state and columns in
+// lock-step: direct TLM solve (ICNTRL(7) = 1), TLM Newton control (ICNTRL(9)), TLM truncation-error control (ICNTRL(12)).
+int sdirk_tlm_lock_device(const SdirkParams& sp, const Cbm4Const& mc, long ncells, const int* d_ids, int ntlm, bool direct,
+                          bool newton_est, bool trunc, double* d_y, double* d_ytlm, const double* d_atol, const double* d_rtol,
+                          const double* d_atol_tlm, const double* d_rtol_tlm, int* d_istatus, double* d_rstatus, int* d_ierr,
+                          cudaStream_t st, UnitTiming& tm, std::string& err);
 
 // ros_small_adj.cu — INTEGRATE_ADJ (ADJ/ROS_ADJ, discrete adjoint) for small_strato / roberts, one system per thread; device arrays
 int ros_small_cadj_epilogue_device(int model, const RosParams& rp, const double* fix, long ncells, int nadj, bool with_mu, const double* d_y,

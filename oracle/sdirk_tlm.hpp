@@ -8,7 +8,8 @@
 //                                                SDIRK_ErrorNorm_TLM :947-960; coefficient sets identical to FWD/SDIRK's
 //   TLM/SDIRK_TLM/LS_Solver.F90                  lss_jac1 :566-570, lss_mul_jac1 :555-558 (matmul(fjac1, g))
 // Restated: the modified-Newton TLM (ICNTRL(7) = 0) with and without the TLM Newton estimate (ICNTRL(9)) and the TLM
-// truncation error (ICNTRL(12)).  The direct TLM solve (ICNTRL(7) = 1: a second factorisation per stage) returns -100.
+// truncation error (ICNTRL(12)), and the direct TLM solve (ICNTRL(7) = 1, :332, :659-705: a second factorisation per stage at the
+// stage point, LSS_Decomp_TLM / LSS_Solve_TLM).
 // Differences from FWD/SDIRK that matter for ISTATUS: the LU is never reused across steps (:879), every stage of every
 // attempt evaluates one more Jacobian (:701-702) and runs the TLM iterations of all NTLM columns — rejected attempts
 // included — each iteration counting one Nsol (:727).
@@ -27,7 +28,9 @@ struct SdirkTlm : Sdirk<Model> {
   typedef Sdirk<Model> Base;
   static constexpr int N = Model::N;
   using Base::cfg; using Base::ISTATUS; using Base::RSTATUS; using Base::lss; using Base::mdl;
-  bool TLMNewtonEst = false, TLMtruncErr = false;
+  bool TLMNewtonEst = false, TLMtruncErr = false, DirectTLM = false;
+  double e_tlm[Model::N * Model::N];
+  int ip_tlm[Model::N];
   explicit SdirkTlm(Model& m) : Base(m) {}
 
   void scale_tlm(const double* AbsTol, const double* RelTol, const double* Y, double* SCAL) const {   // SDIRK_ErrorScale
@@ -111,6 +114,44 @@ struct SdirkTlm : Sdirk<Model> {
           H = Fac * H; Reject = true; SkipJac = true; SkipLU = false;
           cycle = true;
           break;
+        }
+        if (DirectTLM) {   // direct solution for the TLM variables (:659-697): a second factorisation, at the stage point
+          for (int i = 0; i < N; ++i) TMP[i] = Y[i] + Zi[i];
+          bool SkipJacT = false;
+          int ConsecutiveSng = 0, IER = 1;
+          double HGammaInv = 0.0;
+          while (IER != 0) {
+            HGammaInv = 1.0 / (H * tb.Gamma);
+            if (!SkipJacT) { mdl.jac(T + tb.C[istage - 1] * H, TMP, lss.fjac1); ISTATUS[Njac]++; }
+            for (int j = 0; j < N; ++j) {          // LSS_Decomp_TLM: e_tlm = HGammaInv I - fjac1, DGETRF
+              for (int i = 0; i < N; ++i) e_tlm[i + N * j] = -lss.fjac1[i + N * j];
+              e_tlm[j + N * j] = e_tlm[j + N * j] + HGammaInv;
+            }
+            IER = dgetf2(N, e_tlm, ip_tlm);
+            ISTATUS[Ndec]++;
+            if (IER != 0) {
+              ISTATUS[Nsng]++;
+              ConsecutiveSng++;
+              if (ConsecutiveSng >= 6) return -8;   // "RETURN ! Failure" (the reference leaves IERR as it is)
+              H = 0.5 * H; SkipJacT = true; SkipLU = false; Reject = true;
+            }
+          }
+          for (int itlm = 0; itlm < NTLM; ++itlm) {
+            double* Zt = ztlm(istage - 1, itlm);
+            const double* Yt = Y_TLM + (size_t)itlm * N;
+            for (int i = 0; i < N; ++i) G[i] = Yt[i];
+            for (int j = 1; j <= istage - 1; ++j) {
+              const double th = tb.Theta[istage - 1][j - 1];
+              const double* Zj = ztlm(j - 1, itlm);
+              for (int i = 0; i < N; ++i) G[i] = G[i] + th * Zj[i];
+            }
+            HGammaInv = 1.0 / (H * tb.Gamma);
+            for (int i = 0; i < N; ++i) G[i] = HGammaInv * G[i];
+            dgetrs(false, N, e_tlm, ip_tlm, G);
+            ISTATUS[Nsol]++;
+            for (int i = 0; i < N; ++i) Zt[i] = G[i] - Yt[i];
+          }
+          continue;
         }
         // modified-Newton TLM of this stage (:699-783)
         for (int i = 0; i < N; ++i) TMP[i] = Y[i] + Zi[i];
@@ -251,7 +292,7 @@ int sdirk_tlm_integrate(Model& mdl, int NTLM, double* Y, double* Y_TLM, double T
   if (ICNTRL[2] < 0 || ICNTRL[2] > 5) s.cfg.tab = SDIRK_TABLEAU[0];   // CASE DEFAULT: Sdirk2a (:262-275 of the TLM file)
   s.TLMNewtonEst = (ICNTRL[8] != 0);
   s.TLMtruncErr = (ICNTRL[11] != 0);
-  if (Ierr >= 0 && ICNTRL[6] == 1) Ierr = -100;                        // direct TLM solve: not restated
+  s.DirectTLM = (ICNTRL[6] == 1);                                      // :332
   if (Ierr >= 0 && (s.TLMNewtonEst || s.TLMtruncErr) && (!ATOL_TLM || !RTOL_TLM)) Ierr = -100;
   if (Ierr >= 0) Ierr = s.integrate_tlm(NTLM, Y, Y_TLM, TIN, TOUT, ATOL, RTOL, ATOL_TLM, RTOL_TLM);
   if (ISTATUS_U) for (int i = 0; i < 20; ++i) ISTATUS_U[i] = s.ISTATUS[i];

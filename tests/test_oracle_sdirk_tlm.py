@@ -78,3 +78,39 @@ def test_sdirk_tlm_counters_all_methods():
     ic[2] = 1
     c = O.sdirk_tlm("cbm4", y0, np.eye(32)[None, :3], T0, t1, atol, rtol, ic)
     assert np.array_equal(c["y"], a["y"]) and np.array_equal(c["y_tlm"], a["y_tlm"])
+
+
+def test_sdirk_tlm_direct_solve_and_controlled_modes():
+    """ICNTRL(7) = 1 (:659-705): the same state sweep, one more factorisation and NTLM solves per stage, Y_tlm equal to the
+    modified-Newton columns within their Newton tolerance and closer to finite differences; ICNTRL(9) / ICNTRL(12) change
+    the step sequence only through the columns."""
+    y0 = O.initial_state("cbm4")
+    t1 = T0 + 6 * 3600.0
+    rtol, atol = np.full(32, F01 * 1e-6), np.full(32, F01 * 1e-8)
+    for method in (0, 2, 5):
+        ic = np.zeros(20, dtype=np.int32)
+        ic[2] = method
+        a = O.sdirk_tlm("cbm4", y0, np.eye(32)[None], T0, t1, atol, rtol, ic)
+        ic[6] = 1
+        b = O.sdirk_tlm("cbm4", y0, np.eye(32)[None], T0, t1, atol, rtol, ic)
+        assert a["ierr"][0] == 1 and b["ierr"][0] == 1
+        assert np.array_equal(a["y"], b["y"]) and np.array_equal(a["rstatus"], b["rstatus"])
+        Ia, Ib = a["istatus"][0].astype(np.int64), b["istatus"][0].astype(np.int64)
+        assert np.array_equal(Ia[[0, 1, 2, 3, 4, 7]], Ib[[0, 1, 2, 3, 4, 7]])
+        stages = Ib[5] - Ia[5]                       # one LSS_Decomp_TLM per completed stage in the direct flavour
+        assert stages >= (Ia[1] - Ia[5]) and stages <= Ia[1] - Ia[3]   # one LSS_Jac1 each; the rest of Njac: PrepareMatrix
+        assert Ib[6] == Ia[0] + Ia[2] + 32 * stages  # Nsol: state iterations + error solves + one solve per column and stage
+        assert col_err(b["y_tlm"][0], a["y_tlm"][0]) < 1e-7
+        ic[6] = 2                                    # only the value 1 selects the direct solve (:332)
+        c = O.sdirk_tlm("cbm4", y0, np.eye(32)[None], T0, t1, atol, rtol, ic)
+        assert np.array_equal(c["y_tlm"], a["y_tlm"]) and np.array_equal(c["istatus"], a["istatus"])
+    # columns in the error control: unit columns, tolerances in their scale
+    rtol, atol = np.full(32, F01 * 1e-3), np.full(32, F01 * 1e-5)
+    at, rt = np.full((32, 32), 1e-4), np.full((32, 32), 1e-4)
+    ic = np.zeros(20, dtype=np.int32)
+    base = O.sdirk_tlm("cbm4", y0, np.eye(32)[None], T0, t1, atol, rtol, ic)
+    ic[11] = 1
+    tr = O.sdirk_tlm("cbm4", y0, np.eye(32)[None], T0, t1, atol, rtol, ic, atol_tlm=at, rtol_tlm=rt)
+    assert tr["ierr"][0] == 1 and tr["istatus"][0][3] > base["istatus"][0][3]     # smaller steps for the columns' sake
+    fine = O.sdirk_tlm("cbm4", y0, np.eye(32)[None], T0, t1, atol * 1e-4, rtol * 1e-4, np.zeros(20, dtype=np.int32))
+    assert col_err(tr["y_tlm"][0], fine["y_tlm"][0]) < col_err(base["y_tlm"][0], fine["y_tlm"][0])

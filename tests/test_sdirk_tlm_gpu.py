@@ -112,11 +112,11 @@ def test_sdirk_tlm_tape_slot_overflow_takes_the_second_pass():
     assert F.last_stats().waves > 3
 
 
-def test_sdirk_tlm_unsupported_modes_and_option_errors():
+def test_sdirk_tlm_option_errors():
     import fatode_b200 as F
     rtol, atol = tols()
     y0 = F.initial_state("cbm4")
-    for k in (6, 8, 11):                                  # ICNTRL(7) direct solve, ICNTRL(9), ICNTRL(12)
+    for k in (8, 11):                                     # ICNTRL(9), ICNTRL(12) read ATOL_TLM / RTOL_TLM
         ic = np.zeros(20, dtype=np.int32)
         ic[k] = 1
         with pytest.raises(F.FatodeError):
@@ -148,4 +148,81 @@ def test_sdirk_tlm_general_pivoting_pass_at_loose_tolerances():
     rtol, atol = tols(3.0e-3)
     res = F.integrate_tlm("cbm4", T0, t1, y0, yt, rtol, atol, family="sdirk")
     ref = O.sdirk_tlm("cbm4", y0, yt, T0, t1, atol, rtol)
+    check(res, ref)
+
+
+def column_tols(ntlm, k):
+    """(N, NTLM) tolerances of the columns, different per column and per component"""
+    j = np.arange(ntlm)[:, None]
+    i = np.arange(32)[None, :]
+    return F01 * k * (1.0 + 0.25 * ((i + j) % 3)), F01 * k * 1e-2 * (1.0 + 0.5 * ((i + 2 * j) % 2))
+
+
+@pytest.mark.parametrize("direct,est,trunc", [(1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (0, 1, 1), (1, 1, 1)])
+def test_sdirk_tlm_lock_step_modes_match_oracle(direct, est, trunc):
+    """ICNTRL(7) = 1 (direct TLM solve, a second factorisation per stage), ICNTRL(9) (column Newton control), ICNTRL(12)
+    (column truncation errors in the step control) and their combinations: lock-step kernel, everything bit-identical."""
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    rtol, atol = tols(1.0e-3)
+    ncell = 6
+    y0 = perturbed_states(F.initial_state("cbm4"), ncell)
+    rng = np.random.default_rng(11)
+    yt = np.repeat(np.eye(32)[None], ncell, axis=0) + 0.01 * rng.standard_normal((ncell, 32, 32))
+    t1 = T0 + 4 * 3600.0
+    rt, at = column_tols(32, 1.0e-3)
+    at = at * 1.0e4                                       # unit-sized columns: absolute tolerances in their scale
+    for method in ((0, 2, 5) if (direct, est, trunc) in ((1, 0, 0), (0, 1, 1)) else (0,)):
+        ic = np.zeros(20, dtype=np.int32)
+        ic[2], ic[6], ic[8], ic[11] = method, direct, est, trunc
+        ref = O.sdirk_tlm("cbm4", y0, yt, T0, t1, atol, rtol, ic, atol_tlm=at, rtol_tlm=rt)
+        res = F.integrate_tlm("cbm4", T0, t1, y0, yt, rtol, atol, icntrl_u=ic, atol_tlm=at, rtol_tlm=rt, family="sdirk")
+        assert (ref["ierr"] == 1).all()
+        check(res, ref)
+    if trunc or est:                                      # the columns do change the step sequence
+        ic0 = np.zeros(20, dtype=np.int32)
+        ic0[6] = direct
+        base = O.sdirk_tlm("cbm4", y0, yt, T0, t1, atol, rtol, ic0)
+        assert not np.array_equal(base["istatus"], ref["istatus"])
+
+
+def test_sdirk_tlm_lock_step_fewer_columns_scalar_tolerances_failures():
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    rtol, atol = tols(1.0e-4)
+    ncell = 5
+    y0 = perturbed_states(F.initial_state("cbm4"), ncell)
+    yt = np.repeat(np.eye(32)[None, :7], ncell, axis=0)
+    t1 = T0 + 2 * 3600.0
+    rt, at = column_tols(7, 1.0e-4)
+    ic = np.zeros(20, dtype=np.int32)
+    ic[1], ic[2], ic[8], ic[11] = 1, 3, 1, 1              # scalar tolerances: the first entry of every column's set
+    ref = O.sdirk_tlm("cbm4", y0, yt, T0, t1, atol, rtol, ic, atol_tlm=at * 1e4, rtol_tlm=rt)
+    res = F.integrate_tlm("cbm4", T0, t1, y0, yt, rtol, atol, icntrl_u=ic, atol_tlm=at * 1e4, rtol_tlm=rt, family="sdirk")
+    check(res, ref)
+    # columns whose Newton iterations fail end the attempt (:795-800): few iterations allowed, tight column tolerances
+    for maxit, sc in ((3, 1.0e-6), (4, 1.0e-10)):
+        ic = np.zeros(20, dtype=np.int32)
+        ic[4], ic[8] = maxit, 1
+        tt = np.full((7, 32), sc)
+        ref = O.sdirk_tlm("cbm4", y0, yt, T0, t1, atol, rtol, ic, atol_tlm=tt, rtol_tlm=tt)
+        ic[8] = 0
+        base = O.sdirk_tlm("cbm4", y0, yt, T0, t1, atol, rtol, ic)
+        assert (ref["istatus"][:, 5] > base["istatus"][:, 5]).all()          # more factorisations: rejected attempts
+        ic[8] = 1
+        res = F.integrate_tlm("cbm4", T0, t1, y0, yt, rtol, atol, icntrl_u=ic, atol_tlm=tt, rtol_tlm=tt, family="sdirk")
+        check(res, ref)
+    # column tolerances no step can meet: the step size collapses, IERR -7 with the columns of the last accepted step
+    ic = np.zeros(20, dtype=np.int32)
+    ic[6], ic[11] = 1, 1
+    ref = O.sdirk_tlm("cbm4", y0, yt, T0, t1, atol, rtol, ic, atol_tlm=at * 1e-12, rtol_tlm=rt * 1e-9)
+    res = F.integrate_tlm("cbm4", T0, t1, y0, yt, rtol, atol, icntrl_u=ic, atol_tlm=at * 1e-12, rtol_tlm=rt * 1e-9, family="sdirk")
+    assert (ref["ierr"] < 0).all()
+    check(res, ref)
+    # Max_no_steps reached in the direct mode
+    ic = np.zeros(20, dtype=np.int32)
+    ic[3], ic[6] = 12, 1
+    ref = O.sdirk_tlm("cbm4", y0, yt, T0, t1, atol, rtol, ic)
+    res = F.integrate_tlm("cbm4", T0, t1, y0, yt, rtol, atol, icntrl_u=ic, family="sdirk")
+    assert (ref["ierr"] == -6).all()
     check(res, ref)
