@@ -255,7 +255,7 @@ def workload_config(cells, ngpus, note=None):
 
 SIDE_DEFAULT_CELLS = {"small_strato_fwd": 1 << 20, "cbm4_ros_tlm": 32768, "cbm4_rk_adj": 9472, "cbm4_rk_adj_direct": 9472,
                       "cbm4_rk_adj_rtol1e-5": 4736, "cbm4_rk_adj_rtol1e-4": 4736, "cbm4_rk_tlm": 9472, "cbm4_sdirk_adj": 9472,
-                      "cbm4_sdirk_tlm": 9472, "swe_erk": 65536, "swe_erk_tlm": 16384, "cbm4_rk": 18944, "cbm4_sdirk": 18944}
+                      "cbm4_sdirk_tlm": 9472, "cbm4_sdirk_tlm_direct": 2368, "cbm4_sdirk_tlm_trunc": 2368, "swe_erk": 65536, "swe_erk_tlm": 16384, "cbm4_rk": 18944, "cbm4_sdirk": 18944}
 
 
 def dense_flops_from_counters(ist, n, f_fun, f_jac, complex_pairs=False, sens_cols=0):
@@ -364,6 +364,24 @@ def side_measure(w, nc, steps, warmup, fp64_peak=None, hbm_peak=None):
         cpu = lambda y: O.sdirk_tlm("cbm4", y, np.broadcast_to(eye, (y.shape[0], 32, 32)).copy(), T0, T1, atol, rtol)
         desc = ("EXAMPLES/cbm4 TLM/SDIRK_TLM: Sdirk4a, NTLM=32, Y_tlm(t0)=I, modified-Newton TLM (presets), 12h..84h, "
                 "driver tolerances of ROS_ADJ (BASELINE config 4)")
+        ncpu = 32
+        flops = lambda r: dense_flops_from_counters(r.istatus, 32, 573, 636, sens_cols=32)
+    elif w in ("cbm4_sdirk_tlm_direct", "cbm4_sdirk_tlm_trunc"):
+        # the modes in which the columns feed back into the step sequence: lock-step kernel (sdirk_tlm_lock.cu), one system per warp
+        rtol, atol = tolerances()
+        y0 = perturbed_states(F.initial_state("cbm4"), nc)
+        eye = np.eye(32)
+        ic = np.zeros(20, dtype=np.int32)
+        direct = w.endswith("direct")
+        ic[6 if direct else 11] = 1
+        tt = np.full((32, 32), 1.0e-5)     # unit-sized columns: ATOL_TLM = RTOL_TLM = 1e-5
+        run = lambda y: F.integrate_tlm("cbm4", T0, T1, y, np.broadcast_to(eye, (y.shape[0], 32, 32)).copy(), rtol, atol, icntrl_u=ic,
+                                        atol_tlm=tt, rtol_tlm=tt, family="sdirk")
+        cpu = lambda y: O.sdirk_tlm("cbm4", y, np.broadcast_to(eye, (y.shape[0], 32, 32)).copy(), T0, T1, atol, rtol, ic, atol_tlm=tt, rtol_tlm=tt)
+        desc = ("EXAMPLES/cbm4 TLM/SDIRK_TLM: Sdirk4a, NTLM=32, Y_tlm(t0)=I, " +
+                ("direct TLM solve (ICNTRL(7)=1: a second factorisation per stage)" if direct else
+                 "column truncation errors in the step control (ICNTRL(12)=1, ATOL_TLM=RTOL_TLM=1e-5)") +
+                ", 12h..84h, driver tolerances of ROS_ADJ; state and columns in lock-step, general pivoting")
         ncpu = 32
         flops = lambda r: dense_flops_from_counters(r.istatus, 32, 573, 636, sens_cols=32)
     elif w in ("swe_erk", "swe_erk_tlm"):

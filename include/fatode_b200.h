@@ -153,14 +153,19 @@ int fatode_rk_integrate_tlm_batch(int model, int64_t ncells, int nvar, int ntlm,
  *   INTEGRATE_TLM(N,NTLM,NNZERO,Y,Y_TLM,TIN,TOUT,ATOL_TLM,RTOL_TLM,ATOL,RTOL,FUN,JAC,
  *                 ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U,IERR_U)
  * y_tlm [ncells][ntlm][nvar] as for ROS_TLM.  Presets: ICNTRL(5) = 8 Newton iterations, everything else 0; user values
- * override when > 0 (:60-77); an ICNTRL(3) outside 0..5 selects Sdirk2a in this family (:262-275).  Built: the preset
- * mode — modified-Newton TLM (ICNTRL(7) = 0) with the iteration count of the state stage, columns outside the step
- * control (ICNTRL(9) = ICNTRL(12) = 0); ICNTRL(7) = 1, ICNTRL(9) != 0 and ICNTRL(12) != 0 return FATODE_EUNSUPPORTED.
- * ntlm <= 32, cbm4 only.  Per-cell IERR: 1 or the reference's -1..-8.  Systems whose factorisations leave the static pivot
- * pattern (all of them at rtol >= 1e-3) are integrated a second time with general partial pivoting in the state sweep, the
- * preparation and the column sweep (fatode_stats.cells_general counts them); results are bit-identical to the reference's
- * operation order on both paths.  A cell whose state sweep fails returns Y and Y_tlm as of its last accepted step, as the
- * reference. */
+ * override when > 0 (:60-77); an ICNTRL(3) outside 0..5 selects Sdirk2a in this family (:262-275).  Every mode of the
+ * reference is built.  Preset mode — modified-Newton TLM (ICNTRL(7) = 0) with the iteration count of the state stage, columns
+ * outside the step control (ICNTRL(9) = ICNTRL(12) = 0): state sweep + preparation + column sweep over a tape; systems whose
+ * factorisations leave the static pivot pattern (all of them at rtol >= 1e-3) are integrated a second time with general
+ * partial pivoting (fatode_stats.cells_general counts them).  ICNTRL(7) = 1 (direct TLM solve: a second factorisation per
+ * stage, :659-705), ICNTRL(9) /= 0 (the columns' Newton iterations are convergence-controlled with ATOL_TLM / RTOL_TLM and
+ * can reject the attempt, :735-800) and ICNTRL(12) /= 0 (the columns' error estimates enter the step control, :825-837), in
+ * any combination: one lock-step kernel advances the state and the columns of a system together with general pivoting
+ * (cells_general = ncells).  atol_tlm / rtol_tlm [ntlm][nvar] (the Fortran (N, NTLM) arrays, one set per call) are read
+ * when ICNTRL(9) or ICNTRL(12) is set and may be NULL otherwise (FATODE_EINVAL if they are needed and NULL).
+ * ntlm <= 32, cbm4 only.  Per-cell IERR: 1 or the reference's -1..-8.  State, ISTATUS, RSTATUS and Y_tlm are bit-identical
+ * to the reference's operation order in every mode.  A cell whose integration fails returns Y and Y_tlm as of its last
+ * accepted step, as the reference. */
 int fatode_sdirk_integrate_tlm_batch(int model, int64_t ncells, int nvar, int ntlm, double* y, double* y_tlm,
                                      double tin, double tout, const double* atol_tlm, const double* rtol_tlm,
                                      const double* atol, const double* rtol, const int* icntrl_u,

@@ -55,6 +55,13 @@ for k in (1e-2, 1e-3, 1e-4, 1e-5):
     r = F.integrate_tlm("cbm4", T0, t1, y0, yt, rtol, atol, family="sdirk")
     o = O.sdirk_tlm("cbm4", y0, yt, T0, t1, atol, rtol)
     report(f"SDIRK_TLM rtol {F01*k:.0e} n {nc}", r, o, [("Y_tlm", r.y_tlm, o["y_tlm"])])
+    nl = max(16, nc // 4)                                  # lock-step modes: direct solve, column Newton / truncation control
+    tt = np.full((32, 32), 10.0 * F01 * k)
+    for d7, e9, t12 in ((1, 0, 0), (0, 1, 1), (1, 0, 1)):
+        ic = np.zeros(20, dtype=np.int32); ic[6], ic[8], ic[11] = d7, e9, t12
+        r = F.integrate_tlm("cbm4", T0, t1, y0[:nl], yt[:nl], rtol, atol, icntrl_u=ic, atol_tlm=tt, rtol_tlm=tt, family="sdirk")
+        o = O.sdirk_tlm("cbm4", y0[:nl], yt[:nl], T0, t1, atol, rtol, ic, atol_tlm=tt, rtol_tlm=tt)
+        report(f"SDIRK_TLM lock-step ICNTRL(7,9,12)=({d7},{e9},{t12}) rtol {F01*k:.0e} n {nl}", r, o, [("Y_tlm", r.y_tlm, o["y_tlm"])])
     r = F.integrate_adj("cbm4", T0, t1, y0, 32, rtol, atol, family="sdirk")
     o = O.sdirk_adj("cbm4", y0, 32, T0, t1, atol, rtol)
     report(f"SDIRK_ADJ rtol {F01*k:.0e} n {nc}", r, o, [("Lambda", r.lambda_, o["lambda_"]), ("Mu", r.mu, o["mu"])])
