@@ -226,7 +226,7 @@ def swe_initial_state(amplitude=30.0, u0=2.0, v0=2.0) -> np.ndarray:
 
 
 def integrate_adj(model, tin, tout, y, nadj, rtol, atol, np_=None, icntrl_u=None, rcntrl_u=None, want_mu=True,
-                  want_mu_sum=False, model_params=None, family="ros") -> Result:
+                  want_mu_sum=False, model_params=None, family="ros", atol_adj=None, rtol_adj=None) -> Result:
     """Batched INTEGRATE_ADJ: family="ros" ADJ/ROS_ADJ (ADJ/ROS_ADJ/ROS_ADJ_f90_Integrator.F90:34), family="rk"
     ADJ/RK_ADJ (ADJ/RK_ADJ/RK_ADJ_f90_Integrator.F90:20), family="sdirk" ADJ/SDIRK_ADJ (ADJ/SDIRK_ADJ/SDIRK_ADJ_f90_Integrator.F90:29).
     y: [ncells, N] or [N]."""
@@ -246,10 +246,13 @@ def integrate_adj(model, tin, tout, y, nadj, rtol, atol, np_=None, icntrl_u=None
     mu = np.zeros((nc, nadj, npar)) if with_mu else None
     mus = np.zeros((nadj, npar)) if (with_mu and want_mu_sum) else None
     mp = None if model_params is None else np.ascontiguousarray(model_params, dtype=np.float64)
+    # ATOL_adj / RTOL_adj (N, NADJ): read by ADJ/SDIRK_ADJ's simplified-Newton adjoint stages (ICNTRL(7) /= 1) only
+    ata = None if atol_adj is None else np.ascontiguousarray(atol_adj, dtype=np.float64).reshape(nadj, n)
+    rta = None if rtol_adj is None else np.ascontiguousarray(rtol_adj, dtype=np.float64).reshape(nadj, n)
     entry = {"rk": lib().fatode_rk_integrate_adj_batch, "sdirk": lib().fatode_sdirk_integrate_adj_batch}.get(
         family, lib().fatode_ros_integrate_adj_batch)
     _check(entry(mid, nc, n, npar if with_mu else 0, nadj, _ptr(yy), _ptr(lam), _ptr(mu),
-                                                float(tin), float(tout), None, None, _ptr(atol), _ptr(rtol), _ptr(ic),
+                                                float(tin), float(tout), _ptr(ata), _ptr(rta), _ptr(atol), _ptr(rtol), _ptr(ic),
                                                 _ptr(rc), _ptr(ist), _ptr(rst), _ptr(ierr), _ptr(mus), _ptr(mp),
                                                 MEM_HOST, None))
     return Result(yy, ist, rst, ierr, lam, mu, mus)

@@ -1924,7 +1924,7 @@ static void release_sdirk_workspace() { g_sd_tape.release(); g_sd_fat.release();
 // appended to `overflow`.  A system whose state sweep fails keeps Y_tlm as of its last accepted step, like the reference.
 // adj != nullptr: the same organisation for ADJ/SDIRK_ADJ (forward sweep in SD_MODE_ADJ, sdirk_cell_adj.cuh backward); ntlm is then
 // NADJ and d_ytlm is Lambda.  A system whose forward sweep fails still gets its backward sweep and IERR = 1, as the reference.
-struct SdirkAdjHost { SdirkAdjCoef co; double* d_mu; int with_mu, np; };
+struct SdirkAdjHost { SdirkAdjCoef co; double* d_mu; int with_mu, np; int newton = 0; const double* d_atol_adj = nullptr; const double* d_rtol_adj = nullptr; };
 static int sdirk_tlm_group(const SdirkParams& sp, const Cbm4Const& mc, const std::vector<int>& ids, int cap, int ntlm, size_t fat_budget,
                            double* d_y, double* d_ytlm, const double* d_atol, const double* d_rtol, int* d_ist, double* d_rst,
                            int* d_ierr, cudaStream_t st, int sms, std::vector<int>& overflow, const SdirkAdjHost* adj = nullptr,
@@ -1969,6 +1969,21 @@ static int sdirk_tlm_group(const SdirkParams& sp, const Cbm4Const& mc, const std
     const int nb = (int)b_slot.size();
     if (nb == 0) return 0;
     const long long nrec = b_off.back();
+    if (adj && adj->newton) {   // simplified-Newton adjoint stages: one warp per system straight from the tape (sdirk_adj_newton.cu)
+      CUDA_TRY(cudaMemcpyAsync(d_slot, b_slot.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(d_cell, b_cell.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(d_off, b_off.data(), sizeof(long long) * (nb + 1), cudaMemcpyHostToDevice, st));
+      UnitTiming ut;
+      std::string uerr;
+      if (int e = sdirk_adj_newton_device(sp, mc, adj->co, nb, d_off, d_slot, d_cell, g_sd_tape.as<double>(), cap, ntlm, adj->with_mu,
+                                          adj->np, d_ytlm, adj->d_mu, adj->d_atol_adj, adj->d_rtol_adj, d_ist, d_ierr,
+                                          g_ctr.as<unsigned long long>(), st, ut, uerr))
+        return fail(e, uerr);
+      g_stats.ms_adjoint += ut.ms;
+      g_stats.launches += ut.launches; g_stats.launches_adjoint++;
+      b_slot.clear(); b_cell.clear(); b_off.clear();
+      return 0;
+    }
     if (adj) {
       CUDA_TRY(g_sd_fat.ensure((size_t)std::max<long long>(nrec, 1) * rec_bytes));
       CUDA_TRY(cudaMemcpyAsync(d_slot, b_slot.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, st));
@@ -2219,7 +2234,6 @@ extern "C" int fatode_sdirk_integrate_adj_batch(int model, int64_t ncells, int n
                                                 const double* atol, const double* rtol, const int* icntrl_u, const double* rcntrl_u,
                                                 int* istatus, double* rstatus, int* ierr, double* mu_sum, const double* model_params,
                                                 int mem, void* stream) {
-  (void)atol_adj; (void)rtol_adj;   // only read by the Newton mode of the adjoint solve (ICNTRL(7) /= 1), which is not built
   g_err.clear();
   if (ncells < 0 || !y || !atol || !rtol || !istatus || !rstatus || !ierr) return fail(FATODE_EINVAL, "NULL required argument");
   if (int e = check_model_dims(model, nvar, np)) return e;
@@ -2242,8 +2256,8 @@ extern "C" int fatode_sdirk_integrate_adj_batch(int model, int64_t ncells, int n
   const int perr = sdirk_parse_options(nvar, icp, rcntrl_u, tin, tout, atol, rtol, sp);
   if (ic[3] == 0) sp.max_no_steps = 10000;        // :375
   if (perr < 0) return broadcast_ierr(ncells, perr, istatus, rstatus, ierr, mem, st);
-  if (!direct)
-    return fail(FATODE_EUNSUPPORTED, "SDIRK_ADJ with simplified-Newton adjoint stages (ICNTRL(7) /= 1) is not built; use the preset direct solve");
+  if (!direct && (!atol_adj || !rtol_adj))
+    return fail(FATODE_EINVAL, "the simplified-Newton adjoint stages (ICNTRL(7) /= 1) need atol_adj and rtol_adj");
   const bool with_mu = np > 0 && mu != nullptr;
   SdirkAdjHost ah;
   const int method = (ic[2] == 1 || ic[2] == 2 || ic[2] == 3 || ic[2] == 5) ? ic[2] : 4;
@@ -2280,6 +2294,16 @@ extern "C" int fatode_sdirk_integrate_adj_batch(int model, int64_t ncells, int n
     }
   }
   ah.d_mu = d_mu;
+  DevBuf b_ata, b_rta;
+  if (!direct) {   // (N, NADJ) column-major, one set per call
+    CUDA_TRY(b_ata.alloc(sizeof(double) * nvar * nadj));
+    CUDA_TRY(b_rta.alloc(sizeof(double) * nvar * nadj));
+    CUDA_TRY(cudaMemcpyAsync(b_ata.p, atol_adj, sizeof(double) * nvar * nadj, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b_rta.p, rtol_adj, sizeof(double) * nvar * nadj, cudaMemcpyHostToDevice, st));
+    ah.newton = 1;
+    ah.d_atol_adj = b_ata.as<double>();
+    ah.d_rtol_adj = b_rta.as<double>();
+  }
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_cbm4_rc, mc.rc_base, sizeof(double) * 81, 0, cudaMemcpyHostToDevice, st));
   if (int e = sdirk_tlm_device(sp, mc, ncells, nadj, d_y, d_lam, b_atol.as<double>(), b_rtol.as<double>(), d_ist, d_rst, d_ierr, st, &ah))
     return e;

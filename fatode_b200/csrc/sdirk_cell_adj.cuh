@@ -37,7 +37,6 @@ static_assert(SA_REC % 4 == 0 && SA_CHUNK % 4 == 0 && cbm4_cell::NLU == 367 && c
 // 32-byte stores of jac_values<32> in k_sdirk_tlm_prep once a second kernel shared that instantiation; tests/test_sass_guards.py)
 constexpr int SA_PREP_LANES = 30;
 
-struct SdirkAdjCoef { double A[5][5], B[5]; };
 
 struct SdirkAdjPrepArgs {
   long nrec;                 // records (accepted steps) in this batch

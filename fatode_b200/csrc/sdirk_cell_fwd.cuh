@@ -39,7 +39,6 @@ struct SdirkSmem {
 // of its fixed-count TLM iterations (:727, :769 — rejected attempts included), and every accepted step pushes
 // (T, H, saveNiter of the stages, Y, Z_1..Z_S) to the system's tape slot: record r of queue slot s lives at
 // tape[(s * tape_cap + r) * SD_REC].  The columns themselves are propagated afterwards (sdirk_cell_tlm.cuh).
-constexpr int SD_REC = 196;   // T, H, packed saveNiter (4 bits per stage), pad, Y(32), Z(5 x 32)
 // MODE 0: FWD/SDIRK.  MODE 1 (TLM): as described above.  MODE 2 (ADJ): SDIRK_FwdInt of ADJ/SDIRK_ADJ
 // (ADJ/SDIRK_ADJ/SDIRK_ADJ_f90_Integrator.F90:545-781) = the forward family's loop with every accepted step pushed to the tape
 // (:735) and its own SDIRK_PrepareMatrix, which re-evaluates the Jacobian after a singular factorisation (:1239).

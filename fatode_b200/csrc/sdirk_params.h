@@ -13,6 +13,12 @@ struct SdirkParams {
   double tstart, tend;
 };
 
+// tape record of one accepted step written by k_sdirk_fwd_cell in its TLM / ADJ modes (sdirk_cell_fwd.cuh)
+constexpr int SD_REC = 196;   // T, H, packed saveNiter (4 bits per stage), pad, Y(32), Z(5 x 32)
+
+// coefficients of the discrete adjoint (ADJ/SDIRK_ADJ: rkA, rkB of the transposed scheme)
+struct SdirkAdjCoef { double A[5][5], B[5]; };
+
 __device__ __forceinline__ double sdirk_powi(double x, int m) {   // gfortran's x**m for INTEGER m: libgcc __powidf2
   unsigned n = m < 0 ? 0u - (unsigned)m : (unsigned)m;
   double y = (n % 2) ? x : 1.0;

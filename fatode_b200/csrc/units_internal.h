@@ -37,6 +37,13 @@ int sdirk_tlm_lock_device(const SdirkParams& sp, const Cbm4Const& mc, long ncell
                           const double* d_atol_tlm, const double* d_rtol_tlm, int* d_istatus, double* d_rstatus, int* d_ierr,
                           cudaStream_t st, UnitTiming& tm, std::string& err);
 
+// sdirk_adj_newton.cu — backward sweep of ADJ/SDIRK_ADJ with simplified-Newton adjoint stages (ICNTRL(7) /= 1,
+// ADJ/SDIRK_ADJ/SDIRK_ADJ_f90_Integrator.F90:786-995), one warp per system over the forward sweep's tape records; all device arrays
+int sdirk_adj_newton_device(const SdirkParams& sp, const Cbm4Const& mc, const SdirkAdjCoef& co, int nsys, const long long* d_rec_off,
+                            const int* d_slot, const int* d_cell, const double* d_tape, int tape_cap, int nadj, int with_mu, int np,
+                            double* d_lambda, double* d_mu, const double* d_atol_adj, const double* d_rtol_adj, int* d_istatus,
+                            int* d_ierr, unsigned long long* d_queue, cudaStream_t st, UnitTiming& tm, std::string& err);
+
 // ros_small_adj.cu — INTEGRATE_ADJ (ADJ/ROS_ADJ, discrete adjoint) for small_strato / roberts, one system per thread; device arrays
 int ros_small_cadj_epilogue_device(int model, const RosParams& rp, const double* fix, long ncells, int nadj, bool with_mu, const double* d_y,
                                    double* d_lambda, double* d_mu, int* d_istatus, double* d_rstatus, int* d_ierr, cudaStream_t st);

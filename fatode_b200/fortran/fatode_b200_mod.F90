@@ -302,7 +302,8 @@ CONTAINS
     DOUBLE PRECISION, INTENT(INOUT) :: Y(NVAR), Lambda(NVAR,NADJ)
     DOUBLE PRECISION, INTENT(INOUT), OPTIONAL, TARGET :: Mu(NP,NADJ)
     DOUBLE PRECISION, INTENT(INOUT), OPTIONAL :: Q(NADJ)
-    DOUBLE PRECISION, INTENT(IN) :: TIN, TOUT, ATOL_adj(NVAR,NADJ), RTOL_adj(NVAR,NADJ), ATOL(NVAR), RTOL(NVAR)
+    DOUBLE PRECISION, INTENT(IN) :: TIN, TOUT, ATOL(NVAR), RTOL(NVAR)
+    DOUBLE PRECISION, INTENT(IN), TARGET :: ATOL_adj(NVAR,NADJ), RTOL_adj(NVAR,NADJ)
     INTEGER, INTENT(IN), OPTIONAL, TARGET :: ICNTRL_U(20)
     DOUBLE PRECISION, INTENT(IN), OPTIONAL, TARGET :: RCNTRL_U(20)
     INTEGER, INTENT(OUT), OPTIONAL :: ISTATUS_U(20), IERR_U
@@ -332,8 +333,9 @@ CONTAINS
       IF (rc /= 0) ierr(1) = rc
       IF (ierr(1) < 0) PRINT *, 'Runge-Kutta-ADJ: Unsuccessful exit at T=', TIN, ' (IERR=', ierr(1), ')'   ! RK_ADJ :135-137
     ELSE IF (current_family == FATODE_FAMILY_SDIRK) THEN   ! ADJ/SDIRK_ADJ/SDIRK_ADJ_f90_Integrator.F90:29-31 (cbm4_sdirk_adj_dr.F90:230-234)
+      ! ATOL_adj / RTOL_adj are read by the simplified-Newton adjoint stages (ICNTRL(7) /= 1, :869-871)
       rc = fatode_sdirk_integrate_adj_batch(current_model, 1_C_INT64_T, INT(NVAR, C_INT), npc, INT(NADJ, C_INT), Y, Lambda, pmu, &
-                                            TIN, TOUT, C_NULL_PTR, C_NULL_PTR, ATOL, RTOL, pic, prc, ist, rst, ierr, &
+                                            TIN, TOUT, C_LOC(ATOL_adj), C_LOC(RTOL_adj), ATOL, RTOL, pic, prc, ist, rst, ierr, &
                                             C_NULL_PTR, C_NULL_PTR, FATODE_MEM_HOST, C_NULL_PTR)
       IF (rc /= 0) ierr(1) = rc
       IF (ierr(1) < 0) PRINT *, 'SDIRK: Unsuccessful exit at T=', TIN, ' (Ierr=', ierr(1), ')'

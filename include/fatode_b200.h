@@ -177,8 +177,14 @@ int fatode_sdirk_integrate_tlm_batch(int model, int64_t ncells, int nvar, int nt
  *                 ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U,Ierr_U,Q,QFUN)
  * Discrete adjoint of the five SDIRK methods.  Presets ICNTRL(5) = 8, ICNTRL(7) = 1 (direct adjoint solve: one factorisation per
  * stage), user values override when > 0; Max_no_steps defaults to 10000 and Newton starting values are always interpolated in
- * this family.  Built: the preset direct mode, NADJ <= 32, Mu for the model's NP parameters, ADJINIT of the drivers (Lambda = I,
- * Mu = 0), cbm4 only; ICNTRL(7) /= 1 (simplified-Newton adjoint stages) and the quadrature terms return FATODE_EUNSUPPORTED.
+ * this family.  Built: both adjoint solution modes, NADJ <= 32, Mu for the model's NP parameters, ADJINIT of the drivers
+ * (Lambda = I, Mu = 0), cbm4 only; the quadrature terms return FATODE_EUNSUPPORTED.  ICNTRL(7) /= 1 selects the
+ * simplified-Newton adjoint stages (:890-951): one factorisation per step, the columns iterated until they converge in their own
+ * scale 1 / (ATOL_adj + RTOL_adj |Lambda|) — atol_adj / rtol_adj [nadj][nvar] (the Fortran (N, NADJ) arrays, one set per call) are
+ * then required (FATODE_EINVAL if NULL).  A column that does not converge takes the reference's fall-back, LSS_Decomp(HGamma)
+ * with a HGamma this mode never assigns upstream (:804, :855, :941): reproduced with HGamma = 0, the value a zero-initialised stack
+ * gives — the results of such columns, and of the columns after them (they iterate with the new factors), are as meaningless as
+ * the reference's, and fall-backs are frequent; use the preset direct mode for sensitivities.
  * Reference behaviour kept: a system whose forward sweep fails still gets ADJINIT and the backward sweep over its accepted
  * steps, and its IERR is the backward sweep's (1) — RSTATUS(1) < TOUT tells (:519-531).  Systems that leave the static pivot
  * pattern take a second pass with general partial pivoting, as for SDIRK_TLM.  Arguments as fatode_ros_integrate_adj_batch. */

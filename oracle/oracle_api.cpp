@@ -218,6 +218,22 @@ int oracle_sdirk_adj_batch(int model, long ncells, int np, int nadj, double* y, 
   return 0;
 }
 
+// the same with the caller's ATOL_adj / RTOL_adj (N, NADJ) — read by the simplified-Newton adjoint stages (ICNTRL(7) /= 1)
+int oracle_sdirk_adj_batch_tol(int model, long ncells, int np, int nadj, double* y, double* lambda, double* mu, double tin, double tout,
+                               const double* atol_adj, const double* rtol_adj, const double* atol, const double* rtol, const int* icntrl,
+                               const double* rcntrl, int* istatus, double* rstatus, int* ierr, int nthreads) {
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+  if (model != MODEL_CBM4) { for (long c = 0; c < ncells; ++c) ierr[c] = -100; return 0; }
+  const int N = Cbm4::N;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+  for (long c = 0; c < ncells; ++c) {
+    Cbm4 m;
+    ierr[c] = sdirk_adj_integrate<Cbm4>(m, np, nadj, y + c * N, lambda + c * (long)N * nadj, (np > 0 && mu) ? mu + c * (long)np * nadj : nullptr,
+                                        tin, tout, atol_adj, rtol_adj, atol, rtol, icntrl, rcntrl, istatus + c * 20, rstatus + c * 20);
+  }
+  return 0;
+}
+
 // FWD/SDIRK INTEGRATE looped over cells
 int oracle_sdirk_fwd_batch(int model, long ncells, double* y, double tin, double tout, const double* atol, const double* rtol,
                            const int* icntrl, const double* rcntrl, int* istatus, double* rstatus, int* ierr, int nthreads) {

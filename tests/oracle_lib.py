@@ -248,8 +248,9 @@ def erk(model, y, tin, tout, atol, rtol, icntrl=None, rcntrl=None, y_tlm=None, a
     return dict(y=y, y_tlm=yt, istatus=ist, rstatus=rst, ierr=ierr)
 
 
-def sdirk_adj(model, y, nadj, tin, tout, atol, rtol, icntrl=None, rcntrl=None, with_mu=True, nthreads=0):
-    """INTEGRATE_ADJ of ADJ/SDIRK_ADJ looped over cells; lambda_: [ncells, NADJ, N], mu: [ncells, NADJ, NP]."""
+def sdirk_adj(model, y, nadj, tin, tout, atol, rtol, icntrl=None, rcntrl=None, with_mu=True, nthreads=0, atol_adj=None, rtol_adj=None):
+    """INTEGRATE_ADJ of ADJ/SDIRK_ADJ looped over cells; lambda_: [ncells, NADJ, N], mu: [ncells, NADJ, NP].
+    atol_adj / rtol_adj [NADJ, N]: read by the simplified-Newton adjoint stages (default: atol / rtol for every column, as the drivers)."""
     y = np.atleast_2d(np.array(y, dtype=np.float64, order="C"))
     nc, n = y.shape
     _, npar = dims(model)
@@ -262,6 +263,16 @@ def sdirk_adj(model, y, nadj, tin, tout, atol, rtol, icntrl=None, rcntrl=None, w
     lam = np.zeros((nc, nadj, n))
     use_mu = with_mu and npar > 0
     mu = np.zeros((nc, nadj, max(npar, 1)))
+    if atol_adj is not None:
+        ata = np.ascontiguousarray(atol_adj, dtype=np.float64).reshape(nadj, n)
+        rta = np.ascontiguousarray(rtol_adj, dtype=np.float64).reshape(nadj, n)
+        L = lib()
+        L.oracle_sdirk_adj_batch_tol.restype = ctypes.c_int
+        L.oracle_sdirk_adj_batch_tol.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 3 + \
+            [ctypes.c_double, ctypes.c_double] + [ctypes.c_void_p] * 9 + [ctypes.c_int]
+        L.oracle_sdirk_adj_batch_tol(MODEL[model], nc, npar if use_mu else 0, nadj, _d(y), _d(lam), _d(mu) if use_mu else None,
+                                     tin, tout, _d(ata), _d(rta), _d(atol), _d(rtol), _i(ic), _d(rc), _i(ist), _d(rst), _i(ierr), nthreads)
+        return dict(y=y, istatus=ist, rstatus=rst, ierr=ierr, lambda_=lam, mu=mu[:, :, :npar] if use_mu else None)
     lib().oracle_sdirk_adj_batch(MODEL[model], nc, npar if use_mu else 0, nadj, _d(y), _d(lam), _d(mu) if use_mu else None,
                                  tin, tout, _d(atol), _d(rtol), _i(ic), _d(rc), _i(ist), _d(rst), _i(ierr), nthreads)
     return dict(y=y, istatus=ist, rstatus=rst, ierr=ierr, lambda_=lam, mu=mu[:, :, :npar] if use_mu else None)

@@ -147,9 +147,61 @@ def test_sdirk_adj_variants():
     assert (ref["ierr"] == 1).all() and (ref["rstatus"][:, 0] < t1).all()
     check(res, ref)
     ic = np.zeros(20, dtype=np.int32)
-    ic[6] = 2                                    # Newton mode of the adjoint solve: not built
+    ic[6] = 2                                    # Newton mode of the adjoint solve reads ATOL_adj / RTOL_adj
     with pytest.raises(F.FatodeError):
         F.integrate_adj("cbm4", T0, t1, y0, 4, rtol, atol, icntrl_u=ic, family="sdirk")
+
+
+def newton_check(res, ref):
+    assert np.array_equal(res.ierr, ref["ierr"])
+    assert np.array_equal(res.istatus, ref["istatus"]), "ISTATUS must be bit-exact"
+    assert np.array_equal(res.rstatus, ref["rstatus"]) and np.array_equal(res.y, ref["y"])
+    assert np.array_equal(res.lambda_, ref["lambda_"]), "the sweep follows the reference's operation order"
+    if ref["mu"] is not None:
+        sc = np.max(np.abs(ref["mu"]), axis=2, keepdims=True)
+        floor = 1e-10 * np.max(sc, axis=1, keepdims=True)
+        assert np.all(np.abs(res.mu - ref["mu"]) <= 1e-9 * np.maximum(sc, floor))
+
+
+@pytest.mark.gpu
+def test_sdirk_adj_simplified_newton_adjoint_stages_match_oracle():
+    """ICNTRL(7) /= 1 (:890-951): one factorisation per step, the adjoint stages by simplified Newton iterations measured in the
+    columns' own tolerances; columns that do not converge take the fall-back (new shared factors for the columns after them)."""
+    import fatode_b200 as F
+    from fatode_b200.inputs import perturbed_states
+    y0 = perturbed_states(F.initial_state("cbm4"), 6)
+    t1 = T0 + 5 * 3600.0
+    j = np.arange(32)[:, None]
+    i = np.arange(32)[None, :]
+    for k, method, nadj, with_mu, scalar in ((1.0e-4, 0, 32, True, 0), (1.0e-5, 2, 7, True, 0), (1.0e-3, 5, 32, False, 1), (1.0e-4, 3, 5, True, 1),
+                                              (1.0e-2, 0, 32, True, 0)):   # the last one: forward sweep on the general-pivoting pass
+        rtol, atol = np.full(32, F01 * k), np.full(32, F01 * k * 1e-2)
+        ata = (F01 * k * 1e-2 * (1.0 + 0.5 * ((i + j) % 3)))[:nadj]
+        rta = (F01 * k * (1.0 + 0.25 * ((i + 2 * j) % 2)))[:nadj]
+        ic = np.zeros(20, dtype=np.int32)
+        ic[1], ic[2], ic[6] = scalar, method, 2
+        ref = O.sdirk_adj("cbm4", y0, nadj, T0, t1, atol, rtol, ic, with_mu=with_mu, atol_adj=ata, rtol_adj=rta)
+        res = F.integrate_adj("cbm4", T0, t1, y0, nadj, rtol, atol, icntrl_u=ic, want_mu=with_mu, family="sdirk", atol_adj=ata, rtol_adj=rta)
+        assert (ref["ierr"] == 1).all()
+        newton_check(res, ref)
+        icd = ic.copy()
+        icd[6] = 1
+        d = O.sdirk_adj("cbm4", y0, nadj, T0, t1, atol, rtol, icd, with_mu=with_mu)
+        assert not np.array_equal(d["istatus"], ref["istatus"])        # fewer factorisations, more solves than the direct mode
+    # few iterations allowed: columns fail and take the fall-back path (more factorisations than one per step)
+    rtol, atol = np.full(32, F01 * 1.0e-4), np.full(32, F01 * 1.0e-6)
+    ic = np.zeros(20, dtype=np.int32)
+    ic[4], ic[6] = 4, 2
+    tt = np.full((32, 32), 1.0e-12)
+    ref = O.sdirk_adj("cbm4", y0, 32, T0, t1, atol, rtol, ic, atol_adj=tt, rtol_adj=tt)
+    icf = ic.copy()
+    icf[8] = 1                                    # forward sweep only (ICNTRL(9)): its counters
+    res = F.integrate_adj("cbm4", T0, t1, y0, 32, rtol, atol, icntrl_u=ic, family="sdirk", atol_adj=tt, rtol_adj=tt)
+    assert np.array_equal(res.ierr, ref["ierr"]) and np.array_equal(res.istatus, ref["istatus"])
+    steps = ref["istatus"][:, 3]
+    assert (ref["istatus"][:, 5] > 2 * steps + ref["istatus"][:, 4]).any(), "no fall-back factorisation happened: the case does not test it"
+    ok = ref["ierr"] == 1
+    assert np.array_equal(res.lambda_[ok], ref["lambda_"][ok])
 
 
 @pytest.mark.gpu
