@@ -39,6 +39,8 @@ struct Swe {
   static double dx() { return (3.0 - (-3.0)) / (Mx - 1.0); }
   static double dy() { return (3.0 - (-3.0)) / (My - 1.0); }
   std::vector<double> U, F;   // (3, Mx+4, My+4) column-major: U(k,i,j) at k + 3*(i + GX*j), 0-based
+  std::vector<double> feig, geig;   // feigvalues / geigvalues of compute_F, kept when the JAC callback asks (keep_eig)
+  bool keep_eig = false;
   Swe() : U((size_t)3 * GX * GY, 0.0), F((size_t)3 * GX * GY, 0.0) {}
   static inline int at(int k, int i, int j) { return k + 3 * (i + GX * j); }   // 0-based k, i, j
 
@@ -94,6 +96,7 @@ struct Swe {
       }
     }
     const double g = gAcc, ddx = dx(), ddy = dy();
+    if (keep_eig && feig.empty()) { feig.assign((size_t)3 * GX * GY, 0.0); geig.assign((size_t)3 * GX * GY, 0.0); }
     for (int j = 3; j <= My + 2; ++j)
       for (int i = 3; i <= Mx + 2; ++i) {
         double eigf[3], eigg[3], Fu1[3][3] = {{0}}, Fu2[3][3] = {{0}}, Fu3[3][3] = {{0}}, Gu1[3][3] = {{0}}, Gu2[3][3] = {{0}},
@@ -157,6 +160,7 @@ struct Swe {
         mv3(Gu3, eigg[2] >= 0.0 ? dUdyPlus : dUdyMinus, tmpMV);
         for (int k = 0; k < 3; ++k) tmpG[k] = tmpG[k] + eigg[2] * tmpMV[k];
         for (int k = 0; k < 3; ++k) F[at(k, i - 1, j - 1)] = -tmpF[k] - tmpG[k];
+        if (keep_eig) for (int k = 0; k < 3; ++k) { feig[at(k, i - 1, j - 1)] = eigf[k]; geig[at(k, i - 1, j - 1)] = eigg[k]; }
       }
   }
   void fun(double /*t*/, const double* y, double* p) {   // swe2D_erk_dr.F90:2-14

@@ -14,6 +14,7 @@
 #include "sdirk_tlm.hpp"
 #include "rk_tlm.hpp"
 #include "erk.hpp"
+#include "erk_adj.hpp"
 #include "sdirk_adj.hpp"
 
 using namespace oracle;
@@ -192,6 +193,28 @@ int oracle_erk_batch(int model, long ncells, int ntlm, double* y, double* y_tlm,
       default: ierr[c] = -100;
     }
   }
+  return 0;
+}
+// INTEGRATE_ADJ of ADJ/ERK_ADJ (no parameters: ERKADJ2) for the shallow-water example; lambda[member][NADJ][N]
+int oracle_erk_adj_batch(int model, long ncells, int nadj, double* y, double* lambda, double tin, double tout, const double* atol,
+                         const double* rtol, const int* icntrl, const double* rcntrl, int* istatus, double* rstatus, int* ierr,
+                         int nthreads) {
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+  for (long c = 0; c < ncells; ++c) {
+    if (model != MODEL_SWE) { ierr[c] = -100; continue; }
+    Swe m;
+    ierr[c] = erk_adj_integrate_swe(m, nadj, y + c * Swe::N, lambda + c * (long)Swe::N * nadj, tin, tout, atol, rtol, icntrl, rcntrl,
+                                    istatus + c * 20, rstatus + c * 20);
+  }
+  return 0;
+}
+// the JAC callback of the shallow-water drivers as a matrix-free product: out = JAC(y)^T x (trans != 0) or JAC(y) x
+int oracle_swe_jac_mul(const double* y, const double* x, int trans, double* out) {
+  Swe m;
+  SweJac J;
+  J.build(m, y);
+  if (trans) J.mul_t(x, out); else J.mul_n(x, out);
   return 0;
 }
 // initializeGaussianGrid(A) + u = u0, v = v0 + grid2vec (EXAMPLES/swe/SWE_ERK/swe2D_erk_dr.F90:100-103)

@@ -37,6 +37,10 @@ def lib():
         L.oracle_erk_batch.argtypes = L.oracle_ros_tlm_batch.argtypes
         L.oracle_swe_initial_state.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_double, _dp]
         L.oracle_swe_fun.argtypes = [_dp, _dp]
+        L.oracle_swe_jac_mul.argtypes = [_dp, _dp, ctypes.c_int, _dp]
+        L.oracle_erk_adj_batch.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_int, _dp, _dp, ctypes.c_double, ctypes.c_double,
+                                           _dp, _dp, ctypes.POINTER(ctypes.c_int), _dp, ctypes.POINTER(ctypes.c_int), _dp,
+                                           ctypes.POINTER(ctypes.c_int), ctypes.c_int]
         _lib = L
     return _lib
 
@@ -225,6 +229,32 @@ def swe_fun(y):
     p = np.zeros(SWE_N)
     lib().oracle_swe_fun(_d(y), _d(p))
     return p
+
+
+def swe_jac_mul(y, x, trans=False):
+    """JAC(y) x or JAC(y)^T x with the JAC callback of the shallow-water drivers (compute_JacF, swe2D_erk_adj_dr.F90:2-13)."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    o = np.zeros(SWE_N)
+    lib().oracle_swe_jac_mul(_d(y), _d(x), 1 if trans else 0, _d(o))
+    return o
+
+
+def erk_adj(model, y, nadj, tin, tout, atol, rtol, icntrl=None, rcntrl=None, nthreads=0):
+    """INTEGRATE_ADJ of ADJ/ERK_ADJ (no parameters) looped over members; lambda_: [ncells, NADJ, N], ADJINIT: Lambda(k,k) = 1."""
+    y = np.atleast_2d(np.array(y, dtype=np.float64, order="C"))
+    nc, n = y.shape
+    ic, rc = _ctrl(icntrl, rcntrl)
+    atol = np.ascontiguousarray(atol, dtype=np.float64)
+    rtol = np.ascontiguousarray(rtol, dtype=np.float64)
+    ist = np.zeros((nc, 20), dtype=np.int32)
+    rst = np.zeros((nc, 20))
+    ierr = np.zeros(nc, dtype=np.int32)
+    lam = np.zeros((nc, nadj, n))
+    r = lib().oracle_erk_adj_batch(MODEL[model], nc, nadj, _d(y), _d(lam), tin, tout, _d(atol), _d(rtol), _i(ic), _d(rc), _i(ist),
+                                   _d(rst), _i(ierr), nthreads)
+    assert r == 0
+    return dict(y=y, lambda_=lam, istatus=ist, rstatus=rst, ierr=ierr)
 
 
 def erk(model, y, tin, tout, atol, rtol, icntrl=None, rcntrl=None, y_tlm=None, atol_tlm=None, rtol_tlm=None, nthreads=0):
