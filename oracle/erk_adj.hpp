@@ -169,7 +169,7 @@ struct ErkAdjSwe : Erk<Swe> {
       if (Err < 1.0) {
         FirstStep = false;
         ISTATUS[Nacc]++;
-        if ((int)stack.size() + 1 > cfg.Max_no_steps) return -100;   // "Push failed: buffer overflow", STOP
+        if ((int)stack.size() + 1 > cfg.Max_no_steps) return -106;   // ERK_Push: "Push failed: buffer overflow", STOP (:766-770)
         stack.push_back(Entry{T, H, std::vector<double>(Y, Y + N), Z});
         T = T + H;
         for (int i = 1; i <= S; ++i)
@@ -232,7 +232,9 @@ static inline int erk_adj_integrate_swe(Swe& mdl, int NADJ, double* Y, double* L
   int Ierr = erk_parse(Swe::N, ICNTRL, RCNTRL, TIN, TOUT, ATOL, RTOL, false, s.cfg);
   if (Ierr >= 0) {
     Ierr = s.fwd(Y, TIN, TOUT, ATOL, RTOL);
-    if (Ierr != -100) {   // a failed forward sweep still runs ADJINIT and the backward sweep over its accepted steps (:1563-1576)
+    if (Ierr == -106) {   // the reference program STOPs in ERK_Push; restated as IERR -6 with Lambda untouched
+      Ierr = -6;
+    } else {              // a failed forward sweep still runs ADJINIT and the backward sweep over its accepted steps (:1563-1576)
       for (size_t q = 0; q < (size_t)Swe::N * NADJ; ++q) Lambda[q] = 0.0;
       for (int k = 0; k < NADJ; ++k) Lambda[(size_t)k * Swe::N + k] = 1.0;
       Ierr = s.dadj(NADJ, Lambda);

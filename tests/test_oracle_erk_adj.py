@@ -60,8 +60,8 @@ def test_erk_adj_forward_sweep_counters_and_sensitivities():
     for k in range(3):
         assert abs(lam[k] @ v - fd[k]) < 1e-4 * np.max(np.abs(fd[:3]))
         assert abs(lam[k] @ v - tl[k]) < 1e-3 * np.max(np.abs(tl[:3]))   # the TLM's own finite-difference increment is sqrt(rtol) = 1e-2
-    # Max_no_steps: the forward sweep stops with -6, ADJINIT and the backward sweep still run over the accepted steps (return 1)
+    # more accepted steps than Max_no_steps checkpoints: the reference STOPs in ERK_Push (:766-770); restated as IERR -6, Lambda untouched
     ic = np.zeros(20, dtype=np.int32)
     ic[3] = 3
     b = O.erk_adj("swe", y0, 1, 0.0, t1, tol, tol, ic)
-    assert b["ierr"][0] == 1 and b["rstatus"][0][0] < t1 and b["istatus"][0][1] == 7 * b["istatus"][0][3]
+    assert b["ierr"][0] == -6 and b["rstatus"][0][0] < t1 and b["istatus"][0][3] == 4 and not b["lambda_"].any()   # the fourth accepted step finds the buffer full
