@@ -81,6 +81,10 @@ def lib():
         L.fatode_sdirk_integrate_tlm_batch.argtypes = L.fatode_ros_integrate_tlm_batch.argtypes
         L.fatode_rk_integrate_tlm_batch.argtypes = L.fatode_ros_integrate_tlm_batch.argtypes
         L.fatode_set_sdirk_tape_slot.argtypes = [ctypes.c_int]
+        L.fatode_set_erk_tape_slot.argtypes = [ctypes.c_int]
+        L.fatode_erk_integrate_adj_batch.restype = ctypes.c_int
+        L.fatode_erk_integrate_adj_batch.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int] + \
+            [ctypes.c_void_p] * 3 + [ctypes.c_double, ctypes.c_double] + [ctypes.c_void_p] * 8 + [ctypes.c_int, ctypes.c_void_p]
         L.fatode_erk_integrate_batch.argtypes = L.fatode_sdirk_integrate_batch.argtypes
         L.fatode_erk_integrate_tlm_batch.argtypes = L.fatode_ros_integrate_tlm_batch.argtypes
         L.fatode_swe_initial_state.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_double, _dp]
@@ -256,6 +260,24 @@ def integrate_adj(model, tin, tout, y, nadj, rtol, atol, np_=None, icntrl_u=None
                                                 _ptr(rc), _ptr(ist), _ptr(rst), _ptr(ierr), _ptr(mus), _ptr(mp),
                                                 MEM_HOST, None))
     return Result(yy, ist, rst, ierr, lam, mu, mus)
+
+
+def integrate_erk_adj(model, tin, tout, y, nadj, rtol, atol, icntrl_u=None, rcntrl_u=None) -> Result:
+    """Batched INTEGRATE_ADJ of ADJ/ERK_ADJ (ADJ/ERK_ADJ/ERK_ADJ_f90_Integrator.F90:33) on the shallow-water ensemble, no parameters;
+    y: [members, 4800]; result.lambda_: [members, nadj, 4800] (ADJINIT: Lambda(k,k) = 1)."""
+    mid = model_id(model)
+    yy = np.atleast_2d(np.array(y, dtype=np.float64, order="C"))
+    nc, n = yy.shape
+    rtol = np.ascontiguousarray(rtol, dtype=np.float64)
+    atol = np.ascontiguousarray(atol, dtype=np.float64)
+    ic, rc = _ctrl(icntrl_u, rcntrl_u)
+    ist = np.zeros((nc, 20), dtype=np.int32)
+    rst = np.zeros((nc, 20))
+    ierr = np.zeros(nc, dtype=np.int32)
+    lam = np.zeros((nc, nadj, n))
+    _check(lib().fatode_erk_integrate_adj_batch(mid, nc, n, 0, nadj, _ptr(yy), _ptr(lam), None, float(tin), float(tout), _ptr(atol),
+                                                _ptr(rtol), _ptr(ic), _ptr(rc), _ptr(ist), _ptr(rst), _ptr(ierr), None, MEM_HOST, None))
+    return Result(yy, ist, rst, ierr, lam, None, None)
 
 
 def integrate_tlm(model, tin, tout, y, y_tlm, rtol, atol, icntrl_u=None, rcntrl_u=None, atol_tlm=None, rtol_tlm=None,

@@ -2427,6 +2427,71 @@ extern "C" int fatode_erk_integrate_tlm_batch(int model, int64_t ncells, int nva
                         mem, stream);
 }
 
+// INTEGRATE_ADJ of ADJ/ERK_ADJ on the shallow-water ensemble (erk_adj_swe.cu)
+static int g_erk_tape_slot = 0;
+extern "C" int fatode_set_erk_tape_slot(int checkpoints) { g_erk_tape_slot = checkpoints > 0 ? checkpoints : 0; return 0; }
+extern "C" int fatode_erk_integrate_adj_batch(int model, int64_t ncells, int nvar, int np, int nadj, double* y, double* lambda, double* mu,
+                                              double tin, double tout, const double* atol, const double* rtol, const int* icntrl_u,
+                                              const double* rcntrl_u, int* istatus, double* rstatus, int* ierr,
+                                              const double* model_params, int mem, void* stream) {
+  (void)model_params;
+  g_err.clear();
+  if (ncells < 0 || !y || !lambda || !atol || !rtol || !istatus || !rstatus || !ierr) return fail(FATODE_EINVAL, "NULL required argument");
+  if (nadj < 1) return fail(FATODE_EINVAL, "nadj < 1");
+  if (int e = check_model_dims(model, nvar, 0, true)) return e;
+  if (np > 0 && mu) return fail(FATODE_EUNSUPPORTED, "ERK_ADJ with parameter sensitivities (NP > 0, Mu, JACP): the shallow-water example has no parameters");
+  if (nadj > nvar) return fail(FATODE_EINVAL, "nadj > nvar (ADJINIT sets Lambda(k,k) = 1)");
+  if (int e = check_device()) return e;
+  if (ncells == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ErkParams ep;
+  const int perr = erk_parse_options(nvar, icntrl_u, rcntrl_u, tin, tout, atol, rtol, ep, nullptr);
+  if (perr < 0) return broadcast_ierr(ncells, perr, istatus, rstatus, ierr, mem, st);
+  const int ntol = ep.vector_tol ? nvar : 1;
+  DevBuf b_atol, b_rtol, b_y, b_lam, b_ist, b_rst, b_ierr;
+  CUDA_TRY(b_atol.alloc(sizeof(double) * ntol));
+  CUDA_TRY(b_rtol.alloc(sizeof(double) * ntol));
+  CUDA_TRY(cudaMemcpyAsync(b_atol.p, atol, sizeof(double) * ntol, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(b_rtol.p, rtol, sizeof(double) * ntol, cudaMemcpyHostToDevice, st));
+  double *d_y = y, *d_lam = lambda, *d_rst = rstatus;
+  int *d_ist = istatus, *d_ierr = ierr;
+  const size_t ny = sizeof(double) * (size_t)nvar * ncells, nl = ny * (size_t)nadj;
+  if (mem == FATODE_MEM_HOST) {
+    CUDA_TRY(b_y.alloc(ny));
+    CUDA_TRY(b_lam.alloc(nl));
+    CUDA_TRY(b_ist.alloc(sizeof(int) * 20 * ncells));
+    CUDA_TRY(b_rst.alloc(sizeof(double) * 20 * ncells));
+    CUDA_TRY(b_ierr.alloc(sizeof(int) * ncells));
+    CUDA_TRY(cudaMemcpyAsync(b_y.p, y, ny, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b_lam.p, lambda, nl, cudaMemcpyHostToDevice, st));   // members that stop in ERK_Push keep the caller's Lambda
+    d_y = b_y.as<double>(); d_lam = b_lam.as<double>(); d_ist = b_ist.as<int>(); d_rst = b_rst.as<double>(); d_ierr = b_ierr.as<int>();
+  }
+  std::memset(&g_stats, 0, sizeof g_stats);
+  size_t free_b = 0, total_b = 0;
+  CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+  const size_t budget = g_tape_budget ? (size_t)g_tape_budget : (size_t)(0.6 * (double)free_b);
+  UnitTiming ut;
+  std::string uerr;
+  long retried = 0;
+  if (int e = erk_adj_swe_device(ep, (long)ncells, nadj, d_y, d_lam, b_atol.as<double>(), b_rtol.as<double>(), d_ist, d_rst, d_ierr,
+                                 g_erk_tape_slot, budget, st, ut, retried, uerr))
+    return fail(e, uerr);
+  g_stats.ms_forward += ut.ms;
+  g_stats.launches += ut.launches;
+  g_stats.launches_forward += ut.launches;
+  g_stats.waves = (int)ut.launches;
+  g_stats.cells_deferred = retried;
+  if (mem == FATODE_MEM_HOST) {
+    CUDA_TRY(cudaMemcpyAsync(y, d_y, ny, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(lambda, d_lam, nl, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(istatus, d_ist, sizeof(int) * 20 * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(rstatus, d_rst, sizeof(double) * 20 * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ierr, d_ierr, sizeof(int) * ncells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Unit-level probes (used by tests/): evaluate the device model / warp LU on explicit inputs.
 template <class Model>

@@ -7,6 +7,7 @@
 #include "fatode_common.cuh"
 #include "model_cbm4.cuh"
 #include "sdirk_params.h"
+#include "erk_swe.cuh"
 
 namespace fatode {
 
@@ -43,6 +44,13 @@ int sdirk_adj_newton_device(const SdirkParams& sp, const Cbm4Const& mc, const Sd
                             const int* d_slot, const int* d_cell, const double* d_tape, int tape_cap, int nadj, int with_mu, int np,
                             double* d_lambda, double* d_mu, const double* d_atol_adj, const double* d_rtol_adj, int* d_istatus,
                             int* d_ierr, unsigned long long* d_queue, cudaStream_t st, UnitTiming& tm, std::string& err);
+
+// erk_adj_swe.cu — INTEGRATE_ADJ of ADJ/ERK_ADJ (no parameters) on the shallow-water ensemble: forward sweep with checkpoints,
+// ADJINIT (Lambda(k,k) = 1) and ERK_DadjInt with the matrix-free JAC^T of the example; one member per CTA.  Device arrays.
+// tape_slot: checkpoints per CTA in the first pass (0: 128); members that need more are integrated again with Max_no_steps.
+int erk_adj_swe_device(const ErkParams& ep, long nmembers, int nadj, double* d_y, double* d_lambda, const double* d_atol,
+                       const double* d_rtol, int* d_istatus, double* d_rstatus, int* d_ierr, int tape_slot, size_t budget,
+                       cudaStream_t st, UnitTiming& tm, long& retried, std::string& err);
 
 // ros_small_adj.cu — INTEGRATE_ADJ (ADJ/ROS_ADJ, discrete adjoint) for small_strato / roberts, one system per thread; device arrays
 int ros_small_cadj_epilogue_device(int model, const RosParams& rp, const double* fix, long ncells, int nadj, bool with_mu, const double* d_y,

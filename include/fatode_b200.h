@@ -205,6 +205,28 @@ int fatode_erk_integrate_batch(int model, int64_t ncells, int nvar, double* y, d
                                const double* rcntrl_u, int* istatus, double* rstatus, int* ierr,
                                const double* model_params, int mem, void* stream);
 
+/* INTEGRATE_ADJ of ADJ/ERK_ADJ (ADJ/ERK_ADJ/ERK_ADJ_f90_Integrator.F90:33):
+ *   INTEGRATE_ADJ(NVAR,NP,NADJ,NNZ,Y,Lambda,TIN,TOUT,ATOL,RTOL,FUN,JAC,AdjInit,ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U,Ierr_U,
+ *                 Mu,JACP,DRDY,DRDP,QFUN,Q)
+ * Discrete adjoint of the six explicit pairs on the shallow-water ensemble (model FATODE_MODEL_SWE, the family's only example,
+ * EXAMPLES/swe/SWE_ERK_ADJ): forward sweep with the checkpoint of every accepted step (ERK_FwdInt :1600-1740), ADJINIT of the
+ * driver (Lambda(k,k) = 1, swe2D_erk_adj_dr.F90:31-43) and ERK_DadjInt, U_i = JAC^T (h sum a_ji U_j + h b_i Lambda) per stage with
+ * the example's JAC callback (compute_JacF, swe2D_upwind.F90:483-2023) applied matrix-free.  Options as fatode_erk_integrate_batch
+ * (ICNTRL(2), (3), (4), RCNTRL(1..7), (10)); the call without parameters (ERKADJ2) is built: np > 0 with mu != NULL and the
+ * quadrature terms return FATODE_EUNSUPPORTED (the example has no parameters).  lambda [ncells][nadj][nvar] (column k of the
+ * Fortran Lambda(NVAR,NADJ) at lambda[cell][k][:]), nadj <= nvar.  Per-member IERR: 1 (as upstream, also after a forward sweep that
+ * stopped with -6 / -7: ADJINIT and the backward sweep still run over the accepted steps, RSTATUS(1) < TOUT tells), or -6 when
+ * more than Max_no_steps steps are accepted (the reference program STOPs in ERK_Push, :766-770; Lambda is then left as given).
+ * ISTATUS: Nfun = S * attempts, Njac = S * Nacc, Nstp = attempts + Nacc.  State, ISTATUS, RSTATUS bit-identical to the reference's
+ * operation order, Lambda within 1e-9 (rounding level observed).  fatode_set_erk_tape_slot: checkpoints a CTA reserves in the first
+ * pass (default 128); members with more accepted steps are integrated again with Max_no_steps checkpoints
+ * (fatode_stats.cells_deferred counts them). */
+int fatode_erk_integrate_adj_batch(int model, int64_t ncells, int nvar, int np, int nadj, double* y, double* lambda,
+                                   double* mu, double tin, double tout, const double* atol, const double* rtol,
+                                   const int* icntrl_u, const double* rcntrl_u, int* istatus, double* rstatus,
+                                   int* ierr, const double* model_params, int mem, void* stream);
+int fatode_set_erk_tape_slot(int checkpoints);
+
 /* INTEGRATE_TLM of TLM/ERK_TLM (TLM/ERK_TLM/ERK_TLM_f90_Integrator.F90:28):
  *   INTEGRATE_TLM(TIN,TOUT,NVAR,NTLM,VAR,VAR_TLM,ATOL_TLM,RTOL_TLM,ATOL,RTOL,FUN,JAC,
  *                 ICNTRL_U,RCNTRL_U,ISTATUS_U,RSTATUS_U,IERR_U)
