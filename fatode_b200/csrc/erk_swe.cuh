@@ -29,6 +29,10 @@ constexpr int ERK_EPT = SWE_N / ERK_THREADS;                            // vecto
 static_assert(ERK_CPT * ERK_THREADS == SWE_CELLS, "cells per thread");
 constexpr size_t ERK_SMEM = sizeof(double) * (2 * SWE_N + 8);
 
+}  // namespace fatode
+#include "swe_jac_dev.cuh"   // the example's JAC callback, matrix-free (dense-Jacobian TLM mode here, ERK_ADJ in erk_adj_swe.cu)
+namespace fatode {
+
 struct ErkParams {
   int S;
   double ELO, A[12][12], B[12], C[12], E[12];
@@ -146,6 +150,7 @@ struct ErkArgs {
   int tlm_trunc;               // ICNTRL(12) /= 0: the columns' truncation errors enter the step control
   const double* atol_tlm;      // [ntlm][N] (read with tlm_trunc only)
   const double* rtol_tlm;
+  int tlm_dense;               // ICNTRL(5) /= 0: K_tlm = MATMUL(JAC, S_tlm) with the example's JAC callback (scratch: + 27 * N)
 };
 
 template <bool TLM>
@@ -158,8 +163,12 @@ k_erk_swe(ErkParams p, ErkArgs a) {
   const int tid = threadIdx.x;
   const int S = p.S;
   const int ntlm = TLM ? a.ntlm : 0;
-  double* const K = a.scratch + (size_t)blockIdx.x * ((size_t)S * SWE_N * (1 + ntlm));
+  double* const K = a.scratch + (size_t)blockIdx.x * ((size_t)S * SWE_N * (1 + ntlm) + (size_t)((TLM && a.tlm_dense) ? SWE_NNZR * SWE_N : 0));
   double* const KT = K + (size_t)S * SWE_N;       // K_tlm[col][stage][N]
+  double* const JV = KT + (size_t)ntlm * S * SWE_N;   // [27][N] rows of JAC at the stage state (dense-Jacobian TLM mode)
+  const bool dense = TLM && a.tlm_dense;
+  const double dxg = p.c6x / 6.0;
+  int njac = 0;
   const double Roundoff = p.roundoff;
   const double Tdirection = (p.tout - p.tin) >= 0.0 ? 1.0 : -1.0;
   const double rinc = TLM ? 1.0 / p.fdinc : 0.0;
@@ -173,6 +182,7 @@ k_erk_swe(ErkParams p, ErkArgs a) {
     double* const ytl = TLM ? a.y_tlm + (size_t)member * SWE_N * ntlm : nullptr;
     for (int v = tid; v < SWE_N; v += ERK_THREADS) Ys[v] = yin[v];
     int nfun = 0, nstp = 0, nacc = 0, nrej = 0, ierr = 1;
+    njac = 0;
     double T = p.tin, texit = 0.0, hexit = 0.0, hnew_out = 0.0;
     double H = fmax(fabs(p.hmin), fabs(p.hstart));
     if (fabs(H) <= 10.0 * Roundoff) H = 1.0e-6;
@@ -206,6 +216,23 @@ k_erk_swe(ErkParams p, ErkArgs a) {
         swe_fun_cells<false>(TMP, p, Ki, nullptr, 0.0);
         nfun++;
         if constexpr (TLM) {
+          if (dense) {   // FJAC = JAC(T + c H, TMP); K_TLM(:, istage, itlm) = MATMUL(FJAC, S_TLM)  (:460-474)
+            swe_jac_rows(TMP, JV, dxg);
+            njac++;
+            for (int col = 0; col < ntlm; ++col) {
+              __syncthreads();   // every thread has finished reading TMP (the rows, the previous column's product)
+              for (int v = tid; v < SWE_N; v += ERK_THREADS) {
+                double s = ytl[(size_t)col * SWE_N + v];
+                for (int j = 0; j < is; ++j) {
+                  const double c = H * p.A[is][j];
+                  if (c != 0.0) s = s + c * KT[((size_t)col * S + j) * SWE_N + v];
+                }
+                TMP[v] = s;
+              }
+              __syncthreads();
+              swe_jac_n_gather(JV, TMP, KT + ((size_t)col * S + is) * SWE_N);
+            }
+          } else
           for (int col = 0; col < ntlm; ++col) {
             __syncthreads();   // every thread has finished reading TMP
             double* Kc = KT + ((size_t)col * S + is) * SWE_N;
@@ -346,7 +373,7 @@ k_erk_swe(ErkParams p, ErkArgs a) {
       a.ierr[member] = ierr;
       int* ist = a.istatus + member * 20;
       for (int i = 0; i < 20; ++i) ist[i] = 0;
-      ist[0] = nfun; ist[2] = nstp; ist[3] = nacc; ist[4] = nrej;
+      ist[0] = nfun; ist[1] = njac; ist[2] = nstp; ist[3] = nacc; ist[4] = nrej;
       double* rst = a.rstatus + member * 20;
       for (int i = 0; i < 20; ++i) rst[i] = 0.0;
       rst[0] = texit; rst[1] = hexit; rst[2] = hnew_out;

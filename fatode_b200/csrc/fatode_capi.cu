@@ -2342,9 +2342,7 @@ static int erk_batch_impl(bool tlm, int model, int64_t ncells, int nvar, int ntl
   int tlm_opt[2] = {0, 0};
   const int perr = erk_parse_options(nvar, icntrl_u, rcntrl_u, tin, tout, atol, rtol, ep, tlm ? tlm_opt : nullptr);
   if (perr < 0) return broadcast_ierr(ncells, perr, istatus, rstatus, ierr, mem, st);
-  if (tlm && tlm_opt[0] != 0)
-    return fail(FATODE_EUNSUPPORTED, "ERK_TLM with a dense Jacobian (ICNTRL(5) /= 0: a 4800 x 4800 JAC + MATMUL per stage) is not built; "
-                                     "use the preset finite-difference Jacobian-vector products");
+  const bool dense = tlm && tlm_opt[0] != 0;   // ICNTRL(5) /= 0: JAC + MATMUL per stage, the example's JAC callback applied matrix-free
   const bool trunc = tlm && tlm_opt[1] != 0;
   if (trunc && (!atol_tlm || !rtol_tlm)) return fail(FATODE_EINVAL, "ERK_TLM with ICNTRL(12) /= 0 needs ATOL_TLM and RTOL_TLM");
   const int ntl = tlm ? ntlm : 0;
@@ -2385,11 +2383,11 @@ static int erk_batch_impl(bool tlm, int model, int64_t ncells, int nvar, int ntl
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ERK_SMEM));
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ERK_THREADS, ERK_SMEM));
   const unsigned blocks = (unsigned)std::min<int64_t>(ncells, (int64_t)sms * std::max(per_sm, 1));
-  CUDA_TRY(g_erk_scratch.ensure(sizeof(double) * (size_t)blocks * ep.S * SWE_N * (1 + ntl)));
+  CUDA_TRY(g_erk_scratch.ensure(sizeof(double) * (size_t)blocks * ((size_t)ep.S * SWE_N * (1 + ntl) + (dense ? (size_t)SWE_NNZR * SWE_N : 0))));
   CUDA_TRY(g_ctr.ensure(16 * sizeof(unsigned long long)));
   CUDA_TRY(cudaMemsetAsync(g_ctr.p, 0, 16 * sizeof(unsigned long long), st));
   ErkArgs ea{(long)ncells, d_y, d_y, d_yt, b_atol.as<double>(), b_rtol.as<double>(), d_ist, d_rst, d_ierr,
-             g_ctr.as<unsigned long long>(), g_erk_scratch.as<double>(), ntl, trunc ? 1 : 0, b_atl.as<double>(), b_rtl.as<double>()};
+             g_ctr.as<unsigned long long>(), g_erk_scratch.as<double>(), ntl, trunc ? 1 : 0, b_atl.as<double>(), b_rtl.as<double>(), dense ? 1 : 0};
   PhaseTimer tm(st);
   tm.start();
   kern<<<blocks, ERK_THREADS, ERK_SMEM, st>>>(ep, ea);

@@ -17,17 +17,22 @@
 // swe_lsode_sol.txt; relative L2 error 7e-3 / 2e-4 / 1e-6 at tolerances 1e-2 / 1e-4 / 1e-6, tests/test_oracle_erk.py).
 // PARITY UNPINNED by reference artefacts for the ERK_TLM part (the TLM driver only prints): checked against finite
 // differences of the pinned state sweep.
-// Not restated: the dense-Jacobian TLM mode (ICNTRL(5) /= 0: a full 4800 x 4800 JAC + MATMUL per stage, compute_JacF
-// :570-2128) returns -100.
+// The dense-Jacobian TLM mode (ICNTRL(5) /= 0: JAC + MATMUL(FJAC, S_TLM) per stage, :460-474) is restated for the shallow-water
+// model with its JAC callback kept as sparse rows (SweJac below; MATMUL's column sweep = per row the columns ascending).
 // Statement order and BLAS call order follow the Fortran (DAXPY with a zero factor returns at once, as netlib's does);
 // compile with -ffp-contract=off.  Err**(-1/rkELO) goes through o_pow_neg_inv (portable kernel by default, libm pow in
 // ORACLE_LIBM mode).
 #pragma once
 #include <cmath>
 #include <cstring>
+#include <memory>
+#include <type_traits>
 #include <vector>
+#include <algorithm>
+#include <utility>
 #include "sdirk.hpp"
 #include "gen/erk_tableau_gen.h"
+#include "gen/swe_jac_gen.h"
 
 namespace oracle {
 
@@ -170,6 +175,107 @@ struct Swe {
   }
 };
 
+// ---- the JAC callback of the shallow-water drivers (EXAMPLES/swe/SWE_ERK_TLM/swe2D_erk_tlm_dr.F90:2-14, SWE_ERK_ADJ/
+// swe2D_erk_adj_dr.F90:2-13: vec2grid, compute_F for the eigenvalue signs, compute_JacF, fjac = JF; the two examples carry the same
+// compute_JacF) kept as the 27 structural entries of each row instead of the dense 4800 x 4800 matrix; gen/swe_jac_gen.h
+// (tools/gen_swe_jac.py) holds the formula export statement by statement
+struct SweJac {
+  static constexpr int N = Swe::N, NNZR = 27, Mx = Swe::Mx, My = Swe::My;
+  std::vector<int> col;       // [N][27]
+  std::vector<double> val;    // [N][27]  JAC(p, col) = -JF - JG
+  SweJac() : col((size_t)N * NNZR), val((size_t)N * NNZR) {}
+
+  static void mapgrinv(int p, int& k, int& i, int& j) {   // 1-based p -> 1-based field, grid indices with the halo of two
+    k = (p - 1) / (Mx * My) + 1;
+    const int aux = (p - 1) % (Mx * My);
+    i = aux / Mx + 1 + 2;
+    j = aux % Mx + 1 + 2;
+  }
+  static int mapgr(int p, int dk, int di, int dj) {       // 1-based index of the periodic neighbour
+    int z, x, y;
+    mapgrinv(p, z, x, y);
+    z += dk;
+    x += di;
+    if (x == 2) x = Mx + 2;
+    if (x == 1) x = Mx + 1;
+    if (x == Mx + 3) x = 3;
+    if (x == Mx + 4) x = 4;
+    y += dj;
+    if (y == 2) y = My + 2;
+    if (y == 1) y = My + 1;
+    if (y == My + 3) y = 3;
+    if (y == My + 4) y = 4;
+    return (z - 1) * Mx * My + (x - 3) * Mx + y - 2;
+  }
+  // jac(n, t, y, fjac) of the driver
+  void build(Swe& m, const double* y) {
+    m.vec2grid(y, m.U.data());
+    m.keep_eig = true;
+    m.compute_F();
+    const double* Ug = m.U.data();
+    auto u = [&](int k, int i, int j) { return Ug[Swe::at(k - 1, i - 1, j - 1)]; };
+    const double dx = Swe::dx(), dy = Swe::dy(), g = Swe::gAcc;
+    for (int p = 1; p <= N; ++p) {
+      int kf, i, j;
+      mapgrinv(p, kf, i, j);
+      double V[3][9], JF[3][5], JG[3][5];
+      bool fe[3], ge[3];
+      for (int f = 1; f <= 3; ++f) {
+        for (int d = -2; d <= 2; ++d) V[f - 1][d + 2] = u(f, i + d, j);
+        V[f - 1][5] = u(f, i, j - 2);
+        V[f - 1][6] = u(f, i, j - 1);
+        V[f - 1][7] = u(f, i, j + 1);
+        V[f - 1][8] = u(f, i, j + 2);
+      }
+      for (int q = 0; q < 3; ++q) {
+        fe[q] = m.feig[Swe::at(q, i - 1, j - 1)] >= 0.0;
+        ge[q] = m.geig[Swe::at(q, i - 1, j - 1)] >= 0.0;
+      }
+      if (kf == 1) swe_jac::row0(V, fe, ge, dx, dy, g, JF, JG);
+      else if (kf == 2) swe_jac::row1(V, fe, ge, dx, dy, g, JF, JG);
+      else swe_jac::row2(V, fe, ge, dx, dy, g, JF, JG);
+      int* c = col.data() + (size_t)(p - 1) * NNZR;
+      double* v = val.data() + (size_t)(p - 1) * NNZR;
+      int e = 0;
+      for (int cf = 1; cf <= 3; ++cf) {
+        for (int d = -2; d <= 2; ++d) {          // JF(p, ind) [+ JG at the centre]
+          c[e] = mapgr(p, cf - kf, d, 0) - 1;
+          v[e] = -JF[cf - 1][d + 2] - (d == 0 ? JG[cf - 1][2] : 0.0);
+          ++e;
+        }
+        for (int d = -2; d <= 2; ++d) {
+          if (d == 0) continue;
+          c[e] = mapgr(p, cf - kf, 0, d) - 1;
+          v[e] = -0.0 - JG[cf - 1][d + 2];
+          ++e;
+        }
+      }
+    }
+  }
+  // DGEMV('T', N, N, 1, FJAC, N, x, 1, 0, out, 1)
+  void mul_t(const double* x, double* out) const {
+    for (int i = 0; i < N; ++i) out[i] = 0.0;
+    for (int r = 0; r < N; ++r) {
+      const int* c = col.data() + (size_t)r * NNZR;
+      const double* v = val.data() + (size_t)r * NNZR;
+      for (int e = 0; e < NNZR; ++e) out[c[e]] = out[c[e]] + v[e] * x[r];
+    }
+  }
+  // y = FJAC x (MATMUL / DGEMV('N') of the dense-Jacobian tangent linear mode): column sweep, i.e. per row ascending columns
+  void mul_n(const double* x, double* out) const {
+    std::vector<std::pair<int, double>> t(NNZR);
+    for (int r = 0; r < N; ++r) {
+      const int* c = col.data() + (size_t)r * NNZR;
+      const double* v = val.data() + (size_t)r * NNZR;
+      for (int e = 0; e < NNZR; ++e) t[e] = {c[e], v[e]};
+      std::sort(t.begin(), t.end());
+      double s = 0.0;
+      for (int e = 0; e < NNZR; ++e) s = s + t[e].second * x[t[e].first];
+      out[r] = s;
+    }
+  }
+};
+
 struct ErkConfig {
   ErkTableauData tab;
   int ITOL, Max_no_steps;
@@ -229,6 +335,7 @@ struct Erk {
   ErkConfig cfg;
   int ISTATUS[20];
   double RSTATUS[20];
+  std::unique_ptr<SweJac> jac;   // dense-Jacobian tangent linear mode (shallow-water model only)
   explicit Erk(Model& m) : mdl(m) { std::memset(ISTATUS, 0, sizeof ISTATUS); std::memset(RSTATUS, 0, sizeof RSTATUS); }
 
   static void daxpy(int n, double a, const double* x, double* y) {
@@ -273,9 +380,17 @@ struct Erk {
         daxpy(N, 1.0, Y, TMP.data());
         mdl.fun(T + tb.C[istage - 1] * H, TMP.data(), Ki);
         ISTATUS[Nfun]++;
+        if (NTLM > 0 && !cfg.FDAprox) {   // FJAC = 0; CALL JAC(NVAR, T + c H, TMP, FJAC)  (:460-464)
+          if constexpr (std::is_same<Model, Swe>::value) { if (!jac) jac.reset(new SweJac); jac->build(mdl, TMP.data()); }
+          ISTATUS[Njac]++;
+        }
         for (int itlm = 0; itlm < NTLM; ++itlm) {
           for (int i = 0; i < N; ++i) S_TLM[i] = Y_TLM[(size_t)itlm * N + i];
           for (int j = 1; j <= istage - 1; ++j) daxpy(N, H * tb.A[istage - 1][j - 1], Kt(j - 1, itlm), S_TLM.data());
+          if (!cfg.FDAprox) {             // K_TLM(:, istage, itlm) = MATMUL(FJAC, S_TLM)  (:473-474)
+            if constexpr (std::is_same<Model, Swe>::value) jac->mul_n(S_TLM.data(), Kt(istage - 1, itlm));
+            continue;
+          }
           // FDJACV(N, T + c H, TMP, S_TLM, K(:,istage), K_TLM(:,istage,itlm)) :1071-1097
           double* Kc = Kt(istage - 1, itlm);
           daxpy(N, cfg.FDincrement, S_TLM.data(), TMP.data());
@@ -344,7 +459,7 @@ int erk_integrate(Model& mdl, int NTLM, double* Y, double* Y_TLM, double TIN, do
   Erk<Model> s(mdl);
   const bool tlm = NTLM > 0;
   int Ierr = erk_parse(Model::N, ICNTRL, RCNTRL, TIN, TOUT, ATOL, RTOL, tlm, s.cfg);
-  if (Ierr >= 0 && tlm && !s.cfg.FDAprox) Ierr = -100;   // dense-Jacobian TLM mode: not restated
+  if (Ierr >= 0 && tlm && !s.cfg.FDAprox && !std::is_same<Model, Swe>::value) Ierr = -100;   // dense-Jacobian TLM mode: shallow-water model only
   if (Ierr >= 0 && tlm && s.cfg.TLMtruncErr && (!ATOL_TLM || !RTOL_TLM)) Ierr = -100;
   if (Ierr >= 0) Ierr = s.integrate(NTLM, Y, Y_TLM, TIN, TOUT, ATOL, RTOL, ATOL_TLM, RTOL_TLM);
   if (ISTATUS_U) for (int i = 0; i < 20; ++i) ISTATUS_U[i] = s.ISTATUS[i];

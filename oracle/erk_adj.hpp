@@ -23,106 +23,8 @@
 #include <utility>
 #include <vector>
 #include "erk.hpp"
-#include "gen/swe_jac_gen.h"
 
 namespace oracle {
-
-struct SweJac {
-  static constexpr int N = Swe::N, NNZR = 27, Mx = Swe::Mx, My = Swe::My;
-  std::vector<int> col;       // [N][27]
-  std::vector<double> val;    // [N][27]  JAC(p, col) = -JF - JG
-  SweJac() : col((size_t)N * NNZR), val((size_t)N * NNZR) {}
-
-  static void mapgrinv(int p, int& k, int& i, int& j) {   // 1-based p -> 1-based field, grid indices with the halo of two
-    k = (p - 1) / (Mx * My) + 1;
-    const int aux = (p - 1) % (Mx * My);
-    i = aux / Mx + 1 + 2;
-    j = aux % Mx + 1 + 2;
-  }
-  static int mapgr(int p, int dk, int di, int dj) {       // 1-based index of the periodic neighbour
-    int z, x, y;
-    mapgrinv(p, z, x, y);
-    z += dk;
-    x += di;
-    if (x == 2) x = Mx + 2;
-    if (x == 1) x = Mx + 1;
-    if (x == Mx + 3) x = 3;
-    if (x == Mx + 4) x = 4;
-    y += dj;
-    if (y == 2) y = My + 2;
-    if (y == 1) y = My + 1;
-    if (y == My + 3) y = 3;
-    if (y == My + 4) y = 4;
-    return (z - 1) * Mx * My + (x - 3) * Mx + y - 2;
-  }
-  // jac(n, t, y, fjac) of the driver
-  void build(Swe& m, const double* y) {
-    m.vec2grid(y, m.U.data());
-    m.keep_eig = true;
-    m.compute_F();
-    const double* Ug = m.U.data();
-    auto u = [&](int k, int i, int j) { return Ug[Swe::at(k - 1, i - 1, j - 1)]; };
-    const double dx = Swe::dx(), dy = Swe::dy(), g = Swe::gAcc;
-    for (int p = 1; p <= N; ++p) {
-      int kf, i, j;
-      mapgrinv(p, kf, i, j);
-      double V[3][9], JF[3][5], JG[3][5];
-      bool fe[3], ge[3];
-      for (int f = 1; f <= 3; ++f) {
-        for (int d = -2; d <= 2; ++d) V[f - 1][d + 2] = u(f, i + d, j);
-        V[f - 1][5] = u(f, i, j - 2);
-        V[f - 1][6] = u(f, i, j - 1);
-        V[f - 1][7] = u(f, i, j + 1);
-        V[f - 1][8] = u(f, i, j + 2);
-      }
-      for (int q = 0; q < 3; ++q) {
-        fe[q] = m.feig[Swe::at(q, i - 1, j - 1)] >= 0.0;
-        ge[q] = m.geig[Swe::at(q, i - 1, j - 1)] >= 0.0;
-      }
-      if (kf == 1) swe_jac::row0(V, fe, ge, dx, dy, g, JF, JG);
-      else if (kf == 2) swe_jac::row1(V, fe, ge, dx, dy, g, JF, JG);
-      else swe_jac::row2(V, fe, ge, dx, dy, g, JF, JG);
-      int* c = col.data() + (size_t)(p - 1) * NNZR;
-      double* v = val.data() + (size_t)(p - 1) * NNZR;
-      int e = 0;
-      for (int cf = 1; cf <= 3; ++cf) {
-        for (int d = -2; d <= 2; ++d) {          // JF(p, ind) [+ JG at the centre]
-          c[e] = mapgr(p, cf - kf, d, 0) - 1;
-          v[e] = -JF[cf - 1][d + 2] - (d == 0 ? JG[cf - 1][2] : 0.0);
-          ++e;
-        }
-        for (int d = -2; d <= 2; ++d) {
-          if (d == 0) continue;
-          c[e] = mapgr(p, cf - kf, 0, d) - 1;
-          v[e] = -0.0 - JG[cf - 1][d + 2];
-          ++e;
-        }
-      }
-    }
-  }
-  // DGEMV('T', N, N, 1, FJAC, N, x, 1, 0, out, 1)
-  void mul_t(const double* x, double* out) const {
-    for (int i = 0; i < N; ++i) out[i] = 0.0;
-    for (int r = 0; r < N; ++r) {
-      const int* c = col.data() + (size_t)r * NNZR;
-      const double* v = val.data() + (size_t)r * NNZR;
-      for (int e = 0; e < NNZR; ++e) out[c[e]] = out[c[e]] + v[e] * x[r];
-    }
-  }
-  // y = FJAC x (MATMUL / DGEMV('N') of the dense-Jacobian tangent linear mode): column sweep, i.e. per row ascending columns
-  void mul_n(const double* x, double* out) const {
-    std::vector<std::pair<int, double>> t(NNZR);
-    for (int r = 0; r < N; ++r) {
-      const int* c = col.data() + (size_t)r * NNZR;
-      const double* v = val.data() + (size_t)r * NNZR;
-      for (int e = 0; e < NNZR; ++e) t[e] = {c[e], v[e]};
-      std::sort(t.begin(), t.end());
-      double s = 0.0;
-      for (int e = 0; e < NNZR; ++e) s = s + t[e].second * x[t[e].first];
-      out[r] = s;
-    }
-  }
-};
 
 struct ErkAdjSwe : Erk<Swe> {
   typedef Erk<Swe> Base;

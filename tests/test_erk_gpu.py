@@ -97,10 +97,43 @@ def test_erk_tlm_matches_oracle():
     res = F.integrate_erk("swe", 0.0, 5 * DT, y0, tol, tol, icntrl_u=ic, rcntrl_u=rc, var_tlm=v3)
     ref = O.erk("swe", y0, 0.0, 5 * DT, tol, tol, ic, rc, y_tlm=v3)
     check(res, ref)
-    ic2 = np.zeros(20, dtype=np.int32)
-    ic2[4] = 1                                                # dense-Jacobian mode (4800 x 4800 JAC + MATMUL per stage)
-    with pytest.raises(F.FatodeError):
-        F.integrate_erk("swe", 0.0, 5 * DT, y0, tol, tol, icntrl_u=ic2, var_tlm=v)
+
+
+def test_erk_tlm_dense_jacobian_mode_matches_oracle():
+    """ICNTRL(5) /= 0 (TLM/ERK_TLM :460-474): K_tlm = MATMUL(JAC, S_tlm) with the example's JAC callback (compute_JacF), applied
+    matrix-free on the GPU; the state sweep is bit-identical, Y_tlm within 1e-9 (row sums ordered by column except at the
+    periodic seams, pow(x, 1.5) from CUDA's libm); the columns are the exact duals of ERK_ADJ's Lambda."""
+    import fatode_b200 as F
+    from fatode_b200.inputs import swe_members
+    y0 = swe_members(6)
+    tol = np.full(4800, 1.0e-4)
+    rng = np.random.default_rng(7)
+    v3 = rng.standard_normal((6, 3, 4800))
+    for method in (0, 1, 5):
+        ic = np.zeros(20, dtype=np.int32)
+        ic[2], ic[4] = method, 1
+        res = F.integrate_erk("swe", 0.0, 5 * DT, y0, tol, tol, icntrl_u=ic, var_tlm=v3)
+        ref = O.erk("swe", y0, 0.0, 5 * DT, tol, tol, ic, y_tlm=v3)
+        assert (ref["ierr"] == 1).all() and np.array_equal(res.ierr, ref["ierr"])
+        assert np.array_equal(res.istatus, ref["istatus"]) and np.array_equal(res.rstatus, ref["rstatus"]) and np.array_equal(res.y, ref["y"])
+        assert np.all(res.istatus[:, 1] == res.istatus[:, 0])          # one JAC per FUN, no extra FUN per column
+        sc = np.max(np.abs(ref["y_tlm"]), axis=2)
+        er = np.max(np.abs(res.y_tlm - ref["y_tlm"]), axis=2)
+        assert np.all(er <= 1e-9 * sc), np.max(er / sc)
+    adj = F.integrate_erk_adj("swe", 0.0, 5 * DT, y0, 2, tol, tol, icntrl_u=ic)
+    for k in range(2):
+        d = np.einsum("mn,mcn->mc", adj.lambda_[:, k, :], v3)
+        assert np.all(np.abs(d - res.y_tlm[:, :, k]) <= 1e-11 * np.max(np.abs(res.y_tlm[:, :, k])))
+    # with the columns in the step control (ICNTRL(12)): the step sequence follows the columns' error norms
+    ic = np.zeros(20, dtype=np.int32)
+    ic[4], ic[11] = 1, 1
+    tt = np.full((3, 4800), 1.0e-4)
+    res = F.integrate_erk("swe", 0.0, 5 * DT, y0, tol, tol, icntrl_u=ic, var_tlm=v3, atol_tlm=tt, rtol_tlm=tt)
+    ref = O.erk("swe", y0, 0.0, 5 * DT, tol, tol, ic, y_tlm=v3, atol_tlm=tt, rtol_tlm=tt)
+    assert np.array_equal(res.istatus, ref["istatus"]) and np.array_equal(res.ierr, ref["ierr"])
+    assert np.max(np.abs(res.y - ref["y"])) <= 1e-9 * np.max(np.abs(ref["y"]))
+    sc = np.max(np.abs(ref["y_tlm"]), axis=2)
+    assert np.all(np.max(np.abs(res.y_tlm - ref["y_tlm"]), axis=2) <= 1e-9 * sc)
 
 
 def test_erk_tlm_truncation_error_control():
