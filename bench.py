@@ -255,7 +255,7 @@ def workload_config(cells, ngpus, note=None):
 
 SIDE_DEFAULT_CELLS = {"small_strato_fwd": 1 << 20, "cbm4_ros_tlm": 32768, "cbm4_rk_adj": 9472, "cbm4_rk_adj_direct": 9472,
                       "cbm4_rk_adj_rtol1e-5": 4736, "cbm4_rk_adj_rtol1e-4": 4736, "cbm4_rk_tlm": 9472, "cbm4_sdirk_adj": 9472,
-                      "cbm4_sdirk_tlm": 9472, "cbm4_sdirk_tlm_direct": 2368, "cbm4_sdirk_tlm_trunc": 2368, "swe_erk": 65536, "swe_erk_tlm": 16384, "cbm4_rk": 18944, "cbm4_sdirk": 18944}
+                      "cbm4_sdirk_tlm": 9472, "cbm4_sdirk_tlm_direct": 2368, "cbm4_sdirk_tlm_trunc": 2368, "swe_erk": 65536, "swe_erk_tlm": 16384, "swe_erk_tlm_dense": 16384, "swe_erk_adj": 16384, "cbm4_rk": 18944, "cbm4_sdirk": 18944}
 
 
 def dense_flops_from_counters(ist, n, f_fun, f_jac, complex_pairs=False, sens_cols=0):
@@ -384,6 +384,30 @@ def side_measure(w, nc, steps, warmup, fp64_peak=None, hbm_peak=None):
                 ", 12h..84h, driver tolerances of ROS_ADJ; state and columns in lock-step, general pivoting")
         ncpu = 32
         flops = lambda r: dense_flops_from_counters(r.istatus, 32, 573, 636, sens_cols=32)
+    elif w in ("swe_erk_tlm_dense", "swe_erk_adj"):
+        from fatode_b200.inputs import swe_members
+        dt = float(np.float32(2.1573758800627289e-003))
+        tol = np.full(4800, 1.0e-4)
+        t1 = 5 * dt
+        y0 = swe_members(nc)
+        e1 = np.zeros((1, 4800))
+        e1[0, 0] = 1.0
+        icd = np.zeros(20, dtype=np.int32)
+        icd[4] = 1
+        if w == "swe_erk_adj":
+            run = lambda y: F.integrate_erk_adj("swe", 0.0, t1, y, 1, tol, tol)
+            cpu = lambda y: O.erk_adj("swe", y, 1, 0.0, t1, tol, tol)
+            desc = ("EXAMPLES/swe ADJ/ERK_ADJ: Dopri5, NADJ=1 (Lambda(1,1)=1), discrete adjoint with the example's JAC callback (compute_JacF) "
+                    "applied matrix-free, t=0..5 dt, rtol=atol=1e-4, Gaussian bump a=30(1+0.1u) per member (swe2D_erk_adj_dr.F90)")
+        else:
+            run = lambda y: F.integrate_erk("swe", 0.0, t1, y, tol, tol, icntrl_u=icd, var_tlm=np.broadcast_to(e1, (y.shape[0], 1, 4800)).copy())
+            cpu = lambda y: O.erk("swe", y, 0.0, t1, tol, tol, icd, y_tlm=np.broadcast_to(e1, (y.shape[0], 1, 4800)).copy())
+            desc = ("EXAMPLES/swe TLM/ERK_TLM: Dopri5, NTLM=1, Y_tlm=e_1, dense-Jacobian mode (ICNTRL(5)=1: JAC + MATMUL per stage) with the "
+                    "example's JAC callback applied matrix-free, t=0..5 dt, rtol=atol=1e-4, Gaussian bump a=30(1+0.1u) per member")
+        ncpu = 128
+        # per stage: FUN (~0.51 Mflop) + the 27 x 4800 entries of JAC (~3 Mflop as the formula export writes them) + one
+        # 27-entry product per column (0.26 Mflop); the dense MATMUL / DGEMV of the reference would be 46 Mflop per product
+        flops = lambda r: float(r.istatus[:, 0].astype(np.float64).sum()) * 0.51e6 + float(r.istatus[:, 1].astype(np.float64).sum()) * 3.3e6
     elif w in ("swe_erk", "swe_erk_tlm"):
         from fatode_b200.inputs import swe_members
         tlm = w == "swe_erk_tlm"

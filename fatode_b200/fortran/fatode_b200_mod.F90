@@ -15,6 +15,7 @@
 !     MODULE SDIRK_TLM_f90_Integrator :: INTEGRATE_TLM (TLM/SDIRK_TLM/SDIRK_TLM_f90_Integrator.F90:31) after fatode_b200_set_family(FATODE_FAMILY_SDIRK)
 !     MODULE ERK_f90_Integrator     :: INTEGRATE       (FWD/ERK/ERK_f90_Integrator.F90:28)       as INTEGRATE_ERK (rename on the USE line)
 !     MODULE ERK_TLM_f90_Integrator :: INTEGRATE_TLM   (TLM/ERK_TLM/ERK_TLM_f90_Integrator.F90:28) as INTEGRATE_ERK_TLM
+!     MODULE ERK_ADJ_f90_Integrator :: INTEGRATE_ADJ   (ADJ/ERK_ADJ/ERK_ADJ_f90_Integrator.F90:33) as INTEGRATE_ERK_ADJ
 !  (upstream the forward families are separate modules that all export INTEGRATE with the same argument list; the
 !  application picks one with its USE line, here with fatode_b200_set_family)
 !  Dummy-argument names and order are the reference's, so keyword calls such as
@@ -32,7 +33,7 @@ MODULE fatode_b200_mod
   IMPLICIT NONE
   PRIVATE
   PUBLIC :: INTEGRATE, INTEGRATE_ADJ, INTEGRATE_TLM, INTEGRATE_BATCH, INTEGRATE_ADJ_BATCH, fatode_b200_set_model
-  PUBLIC :: INTEGRATE_ERK, INTEGRATE_ERK_TLM
+  PUBLIC :: INTEGRATE_ERK, INTEGRATE_ERK_TLM, INTEGRATE_ERK_ADJ
   PUBLIC :: fatode_b200_set_family, FATODE_FAMILY_ROS, FATODE_FAMILY_SDIRK, FATODE_FAMILY_RK
   PUBLIC :: FATODE_MODEL_ROBERTS, FATODE_MODEL_SMALL_STRATO, FATODE_MODEL_CBM4, FATODE_MODEL_SWE
 
@@ -91,6 +92,19 @@ MODULE fatode_b200_mod
       REAL(C_DOUBLE), INTENT(IN) :: atol(*), rtol(*)
       INTEGER(C_INT) :: istatus(*), ierr(*)
       INTEGER(C_INT) :: fatode_erk_integrate_tlm_batch
+    END FUNCTION
+    FUNCTION fatode_erk_integrate_adj_batch(model, ncells, nvar, np, nadj, y, lambda, mu, tin, tout, atol, rtol, icntrl_u, rcntrl_u, &
+                                            istatus, rstatus, ierr, model_params, mem, stream) &
+                                            BIND(C, NAME='fatode_erk_integrate_adj_batch')
+      IMPORT :: C_INT, C_INT64_T, C_DOUBLE, C_PTR
+      INTEGER(C_INT), VALUE :: model, nvar, np, nadj, mem
+      INTEGER(C_INT64_T), VALUE :: ncells
+      REAL(C_DOUBLE), VALUE :: tin, tout
+      REAL(C_DOUBLE) :: y(*), lambda(*), rstatus(*)
+      TYPE(C_PTR), VALUE :: mu, icntrl_u, rcntrl_u, model_params, stream
+      REAL(C_DOUBLE), INTENT(IN) :: atol(*), rtol(*)
+      INTEGER(C_INT) :: istatus(*), ierr(*)
+      INTEGER(C_INT) :: fatode_erk_integrate_adj_batch
     END FUNCTION
     FUNCTION fatode_rk_integrate_batch(model, ncells, nvar, y, tin, tout, atol, rtol, icntrl_u, rcntrl_u, &
                                         istatus, rstatus, ierr, model_params, mem, stream) BIND(C, NAME='fatode_rk_integrate_batch')
@@ -261,7 +275,8 @@ CONTAINS
 
   !~~~> TLM/ERK_TLM INTEGRATE_TLM, one system (TLM/ERK_TLM/ERK_TLM_f90_Integrator.F90:28-30; argument order and names differ from
   !     the ROS/SDIRK TLM families): USE fatode_b200_mod, ONLY: INTEGRATE_TLM => INTEGRATE_ERK_TLM keeps the keyword call of
-  !     swe2D_erk_tlm_dr.F90:131-135.  JAC is accepted and ignored (finite-difference Jacobian-vector products, ICNTRL(5) = 0).
+  !     swe2D_erk_tlm_dr.F90:131-135.  JAC is accepted and not called: with ICNTRL(5) /= 0 the
+  !     engine applies the shallow-water example's own JAC (compute_JacF), compiled as a device function.
   SUBROUTINE INTEGRATE_ERK_TLM( TIN, TOUT, NVAR, NTLM, VAR, VAR_TLM, ATOL_TLM, RTOL_TLM, ATOL, RTOL, FUN, JAC, &
                                 ICNTRL_U, RCNTRL_U, ISTATUS_U, RSTATUS_U, IERR_U )
     INTEGER, INTENT(IN) :: NVAR, NTLM
@@ -289,6 +304,45 @@ CONTAINS
     IF (PRESENT(RSTATUS_U)) RSTATUS_U(:) = rst(:)
     IF (PRESENT(IERR_U)) IERR_U = ierr(1)
   END SUBROUTINE INTEGRATE_ERK_TLM
+
+  !~~~> ADJ/ERK_ADJ INTEGRATE_ADJ, one system (ADJ/ERK_ADJ/ERK_ADJ_f90_Integrator.F90:33-35; argument order and names differ from
+  !     the implicit adjoint families): USE fatode_b200_mod, ONLY: INTEGRATE_ADJ => INTEGRATE_ERK_ADJ keeps the keyword call of
+  !     swe2D_erk_adj_dr.F90:164-167.  FUN, JAC, AdjInit are accepted and not called (model id: the example's callbacks are device
+  !     functions; ADJINIT sets Lambda(k,k) = 1).  The call without parameters (ERKADJ2) is served; Mu / JACP / quadrature: -105.
+  SUBROUTINE INTEGRATE_ERK_ADJ( NVAR, NP, NADJ, NNZ, Y, Lambda, TIN, TOUT, ATOL, RTOL, FUN, JAC, AdjInit, ICNTRL_U, RCNTRL_U, &
+                                ISTATUS_U, RSTATUS_U, Ierr_U, Mu, JACP, DRDY, DRDP, QFUN, Q )
+    INTEGER, INTENT(IN) :: NVAR, NP, NADJ
+    INTEGER, INTENT(IN), OPTIONAL :: NNZ
+    DOUBLE PRECISION, INTENT(INOUT) :: Y(NVAR), Lambda(NVAR,NADJ)
+    DOUBLE PRECISION, INTENT(INOUT), OPTIONAL :: Q(NADJ), Mu(NP,NADJ)
+    DOUBLE PRECISION, INTENT(IN) :: ATOL(NVAR), RTOL(NVAR), TIN, TOUT
+    EXTERNAL :: FUN, JAC, AdjInit
+    EXTERNAL :: QFUN, JACP, DRDY, DRDP
+    OPTIONAL :: QFUN, JACP, DRDY, DRDP
+    INTEGER, INTENT(IN), OPTIONAL, TARGET :: ICNTRL_U(20)
+    DOUBLE PRECISION, INTENT(IN), OPTIONAL, TARGET :: RCNTRL_U(20)
+    INTEGER, INTENT(OUT), OPTIONAL :: ISTATUS_U(20), Ierr_U
+    DOUBLE PRECISION, INTENT(OUT), OPTIONAL :: RSTATUS_U(20)
+    INTEGER(C_INT) :: ist(20), ierr(1), rc
+    REAL(C_DOUBLE) :: rst(20)
+    TYPE(C_PTR) :: pic, prc
+    pic = C_NULL_PTR; prc = C_NULL_PTR
+    IF (PRESENT(ICNTRL_U)) pic = C_LOC(ICNTRL_U)
+    IF (PRESENT(RCNTRL_U)) prc = C_LOC(RCNTRL_U)
+    ist = 0; rst = 0.0d0; ierr = 0
+    IF ((NP > 0 .AND. PRESENT(Mu) .AND. PRESENT(JACP)) .OR. (PRESENT(Q) .AND. PRESENT(QFUN))) THEN
+      ierr(1) = -105   ! FATODE_EUNSUPPORTED: parameter sensitivities / quadrature terms of ERKADJ1 (:100-117)
+    ELSE
+      rc = fatode_erk_integrate_adj_batch(current_model, 1_C_INT64_T, INT(NVAR, C_INT), 0_C_INT, INT(NADJ, C_INT), Y, Lambda, &
+                                          C_NULL_PTR, TIN, TOUT, ATOL, RTOL, pic, prc, ist, rst, ierr, C_NULL_PTR, &
+                                          FATODE_MEM_HOST, C_NULL_PTR)
+      IF (rc /= 0) ierr(1) = rc
+    END IF
+    IF (ierr(1) < 0) PRINT *, 'ERK: Unsuccessful exit at T=', TIN, ' (Ierr=', ierr(1), ')'   ! as :129-131
+    IF (PRESENT(ISTATUS_U)) ISTATUS_U(:) = ist(:)
+    IF (PRESENT(RSTATUS_U)) RSTATUS_U(:) = rst(:)
+    IF (PRESENT(Ierr_U)) Ierr_U = ierr(1)
+  END SUBROUTINE INTEGRATE_ERK_ADJ
 
   !~~~> ADJ/ROS_ADJ INTEGRATE_ADJ, one system (ADJ/ROS_ADJ/ROS_ADJ_f90_Integrator.F90:34-37)
   !     With fatode_b200_set_family(FATODE_FAMILY_RK) the same routine stands in for ADJ/RK_ADJ's INTEGRATE_ADJ

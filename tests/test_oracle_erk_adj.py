@@ -65,3 +65,31 @@ def test_erk_adj_forward_sweep_counters_and_sensitivities():
     ic[3] = 3
     b = O.erk_adj("swe", y0, 1, 0.0, t1, tol, tol, ic)
     assert b["ierr"][0] == -6 and b["rstatus"][0][0] < t1 and b["istatus"][0][3] == 4 and not b["lambda_"].any()   # the fourth accepted step finds the buffer full
+
+
+def test_erk_tlm_dense_jacobian_mode_is_the_dual_of_erk_adj():
+    """TLM/ERK_TLM with ICNTRL(5) /= 0 (:460-474): JAC + MATMUL per stage; same state sweep as the finite-difference mode, one JAC
+    per FUN and no FUN per column; its columns are the exact duals of ERK_ADJ's Lambda (same JAC, same tableau)."""
+    y0 = O.swe_initial_state()
+    t1 = 5 * DT
+    tol = np.full(N, 1.0e-4)
+    rng = np.random.default_rng(2)
+    v = rng.standard_normal((2, N))
+    fdm = O.erk("swe", y0, 0.0, t1, tol, tol, y_tlm=v[None])
+    ic = np.zeros(20, dtype=np.int32)
+    ic[4] = 1
+    den = O.erk("swe", y0, 0.0, t1, tol, tol, ic, y_tlm=v[None])
+    assert den["ierr"][0] == 1 and np.array_equal(den["y"], fdm["y"]) and np.array_equal(den["rstatus"], fdm["rstatus"])
+    Id, If = den["istatus"][0], fdm["istatus"][0]
+    assert Id[0] == Id[1] == 7 * Id[2] and If[0] == 3 * Id[0] and np.array_equal(Id[2:5], If[2:5])
+    adj = O.erk_adj("swe", y0, 3, 0.0, t1, tol, tol)
+    for k in range(3):
+        for c in range(2):
+            assert abs(adj["lambda_"][0][k] @ v[c] - den["y_tlm"][0][c][k]) <= 1e-12 * np.max(np.abs(den["y_tlm"][0][c]))
+    # first column against the finite-difference mode (its increment is sqrt(rtol) = 1e-2; later columns of that mode carry the
+    # earlier columns' perturbations, fact kept from the reference) and against central differences of the state sweep
+    assert np.max(np.abs(den["y_tlm"][0][0] - fdm["y_tlm"][0][0])) < 2e-2 * np.max(np.abs(den["y_tlm"][0][0]))
+    eps = 1e-6
+    yp = O.erk("swe", y0 + eps * v[0], 0.0, t1, tol, tol)["y"][0]
+    ym = O.erk("swe", y0 - eps * v[0], 0.0, t1, tol, tol)["y"][0]
+    assert np.max(np.abs((yp - ym) / (2 * eps) - den["y_tlm"][0][0])) < 1e-2 * np.max(np.abs(den["y_tlm"][0][0]))

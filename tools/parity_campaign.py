@@ -121,5 +121,12 @@ for tol, method in ((1e-2, 0), (1e-3, 5), (1e-5, 0), (1e-6, 6)):
     r = F.integrate_erk("swe", 0.0, 5 * DT, y0, tv, tv, icntrl_u=ic, var_tlm=v)
     o = O.erk("swe", y0, 0.0, 5 * DT, tv, tv, ic, y_tlm=v)
     report(f"ERK_TLM method {method} tol {tol:.0e} n 48 ntlm 2", r, o, [("Y_tlm", r.y_tlm, o["y_tlm"])])
+    icd = ic.copy(); icd[4] = 1                                # dense-Jacobian mode: MATMUL(JAC, S_tlm) with the example's compute_JacF
+    r = F.integrate_erk("swe", 0.0, 5 * DT, y0, tv, tv, icntrl_u=icd, var_tlm=v)
+    o = O.erk("swe", y0, 0.0, 5 * DT, tv, tv, icd, y_tlm=v)
+    report(f"ERK_TLM dense-Jacobian method {method} tol {tol:.0e} n 48 ntlm 2", r, o, [("Y_tlm", r.y_tlm, o["y_tlm"])])
+    r = F.integrate_erk_adj("swe", 0.0, 20 * DT, y0, 2, tv, tv, icntrl_u=ic)
+    o = O.erk_adj("swe", y0, 2, 0.0, 20 * DT, tv, tv, ic)
+    report(f"ERK_ADJ method {method} tol {tol:.0e} n 48 nadj 2 (steps/member {r.istatus[:,3].mean():.1f})", r, o, [("Lambda", r.lambda_, o["lambda_"])])
 print("MISMATCHES", bad, "| systems handed back (known gap):", gaps)
 sys.exit(1 if bad else 0)
