@@ -234,7 +234,11 @@ int fatode_set_erk_tape_slot(int checkpoints);
  * products by forward finite differences (FDJACV :1071-1097, increment RCNTRL(12) or sqrt(max(RTOL(1), eps))), one extra
  * FUN per column per stage, Nfun = S * (1 + NTLM) * Nstp — with or without the TLM truncation-error control (ICNTRL(12) /= 0:
  * the columns' error norms, scaled with ATOL_TLM / RTOL_TLM [ntlm][nvar] — host arrays shared by all members — enter the step
- * control, :493-501); the dense-Jacobian mode returns FATODE_EUNSUPPORTED.  y_tlm [ncells][ntlm][4800]. */
+ * control, :493-501).  ICNTRL(5) /= 0 selects the dense-Jacobian mode (:460-474): one JAC per stage and
+ * K_tlm = MATMUL(FJAC, S_tlm) per column — the example's JAC callback (compute_JacF, EXAMPLES/swe/SWE_ERK_TLM/swe2D_upwind.F90:
+ * 483-2007) is compiled as a device function and applied matrix-free (27 structural entries per row); Nfun = S * Nstp = Njac;
+ * state bit-identical, Y_tlm within 1e-9 of the reference's operation order (pow(x, 1.5) is CUDA's).
+ * y_tlm [ncells][ntlm][4800]. */
 int fatode_erk_integrate_tlm_batch(int model, int64_t ncells, int nvar, int ntlm, double* y, double* y_tlm,
                                    double tin, double tout, const double* atol_tlm, const double* rtol_tlm,
                                    const double* atol, const double* rtol, const int* icntrl_u,

@@ -93,3 +93,25 @@ def test_erk_tlm_dense_jacobian_mode_is_the_dual_of_erk_adj():
     yp = O.erk("swe", y0 + eps * v[0], 0.0, t1, tol, tol)["y"][0]
     ym = O.erk("swe", y0 - eps * v[0], 0.0, t1, tol, tol)["y"][0]
     assert np.max(np.abs((yp - ym) / (2 * eps) - den["y_tlm"][0][0])) < 1e-2 * np.max(np.abs(den["y_tlm"][0][0]))
+
+
+def test_generated_swe_jacobian_headers_are_current():
+    """The committed headers are what tools/gen_swe_jac.py produces from the reference (skipped on boxes without it), and the
+    product's copy equals the oracle's."""
+    import os
+    import subprocess
+    import sys
+    import pytest
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    paths = [os.path.join(root, "oracle", "gen", "swe_jac_gen.h"), os.path.join(root, "fatode_b200", "csrc", "gen", "swe_jac_gen.h")]
+    before = [open(p).read() for p in paths]
+    assert before[0] == before[1]
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("reference tree not present")
+    stats = [os.stat(p) for p in paths]
+    subprocess.run([sys.executable, os.path.join(root, "tools", "gen_swe_jac.py")], check=True, capture_output=True)
+    same = [open(p).read() == b for p, b in zip(paths, before)]
+    for p, st, ok in zip(paths, stats, same):
+        if ok:
+            os.utime(p, (st.st_atime, st.st_mtime))      # identical content: keep the time stamps (no needless rebuild)
+    assert all(same)
