@@ -766,7 +766,7 @@ def main():
             L.fatode_release_workspace()
             side = {}
             hbm = measured_hbm_peak()
-            for w_, n_ in (("small_strato_fwd", 1 << 20), ("cbm4_rk_adj", 9472), ("cbm4_sdirk_tlm", 9472), ("swe_erk", 32768)):
+            for w_, n_ in (("small_strato_fwd", 1 << 20), ("cbm4_rk_adj", 9472), ("cbm4_sdirk_tlm", 9472), ("swe_erk", 32768), ("swe_erk_adj", 8192)):
                 t_ = time.perf_counter()
                 try:
                     sl = side_measure(w_, n_, 1, 1, fp64_peak, hbm)

@@ -36,3 +36,14 @@ m = swe_members(9)
 r = F.integrate_erk("swe", 0.0, 10 * DT, m, tol, tol); print("swe erk", (r.ierr == 1).all(), r.istatus[:, 2].mean())
 v = np.zeros((9, 1, 4800)); v[:, 0, 0] = 1.0
 r = F.integrate_erk("swe", 0.0, 5 * DT, m, tol, tol, var_tlm=v); print("swe erk_tlm", (r.ierr == 1).all())
+icd5 = np.zeros(20, dtype=np.int32); icd5[4] = 1
+r = F.integrate_erk("swe", 0.0, 5 * DT, m, tol, tol, icntrl_u=icd5, var_tlm=v); print("swe erk_tlm dense Jacobian", (r.ierr == 1).all(), r.istatus[:, 1].mean())
+r = F.integrate_erk_adj("swe", 0.0, 5 * DT, m, 2, tol, tol); print("swe erk_adj", (r.ierr == 1).all(), r.istatus[:, 1].mean())
+tt = np.full((32, 32), 1.0e-4)
+for name, k in (("direct", 6), ("column Newton control", 8), ("column truncation control", 11)):
+    icl = np.zeros(20, dtype=np.int32); icl[k] = 1
+    r = F.integrate_tlm("cbm4", T0, T1, y[:12], np.tile(np.eye(32), (12, 1, 1)), rtol, atol, icntrl_u=icl, atol_tlm=tt, rtol_tlm=tt, family="sdirk")
+    print("sdirk_tlm lock-step:", name, (r.ierr == 1).all(), F.last_stats().cells_general)
+icn = np.zeros(20, dtype=np.int32); icn[6] = 2
+r = F.integrate_adj("cbm4", T0, T1, y[:12], 8, rtol, atol, icntrl_u=icn, family="sdirk", atol_adj=np.tile(atol, (8, 1)), rtol_adj=np.tile(rtol, (8, 1)))
+print("sdirk_adj simplified-Newton adjoint stages", (r.ierr == 1).all(), r.istatus[:, 5].mean())
