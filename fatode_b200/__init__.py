@@ -288,7 +288,8 @@ def integrate_tlm(model, tin, tout, y, y_tlm, rtol, atol, icntrl_u=None, rcntrl_
     mid = model_id(model)
     yy = np.atleast_2d(np.array(y, dtype=np.float64, order="C"))
     nc, n = yy.shape
-    yt = np.array(y_tlm, dtype=np.float64, order="C").reshape(nc, -1, n)
+    yt = np.array(y_tlm, dtype=np.float64, order="C")
+    yt = yt if yt.ndim == 3 else yt.reshape(nc, -1, n)      # (an empty batch cannot infer NTLM from a flat array)
     ntlm = yt.shape[1]
     rtol = np.ascontiguousarray(rtol, dtype=np.float64)
     atol = np.ascontiguousarray(atol, dtype=np.float64)
