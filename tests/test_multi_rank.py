@@ -73,3 +73,50 @@ def test_sharded_mu_sum_equals_single_process_sum():
     absum = np.abs(ref["mu"]).sum(axis=0)
     assert nacc == int(ref["istatus"][:, 3].sum())
     assert np.all(np.abs(musum - s) <= 1e-12 * absum + 1e-300)
+
+
+def _erk_worker(rank, world, port, per_rank, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from fatode_b200.inputs import swe_members
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dt = float(np.float32(2.1573758800627289e-003))
+    tol = np.full(4800, 1.0e-3)
+    # rank r owns ensemble members [r*n, (r+1)*n): counter-based generator, no data path collective for this family
+    y0 = swe_members(per_rank, first_member=rank * per_rank)
+    r = O.erk_adj("swe", y0, 1, 0.0, 3 * dt, tol, tol, nthreads=2)
+    mine = torch.from_numpy(np.concatenate([r["lambda_"][:, 0, :8].ravel(), r["y"][:, :8].ravel(), r["istatus"][:, :5].ravel().astype(np.float64)]))
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)                 # only to compare in the test: the path itself exchanges nothing
+    if rank == 0:
+        out.put(np.stack([p.numpy() for p in parts]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_shallow_water_adjoint_equals_single_process():
+    """ERK_ADJ over an ensemble split across two ranks (no collective on the data path): the union of the shards equals one run."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from fatode_b200.inputs import swe_members
+    world, n = 2, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_erk_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    parts = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    dt = float(np.float32(2.1573758800627289e-003))
+    tol = np.full(4800, 1.0e-3)
+    ref = O.erk_adj("swe", swe_members(world * n), 1, 0.0, 3 * dt, tol, tol)
+    for r in range(world):
+        sl = slice(r * n, (r + 1) * n)
+        want = np.concatenate([ref["lambda_"][sl, 0, :8].ravel(), ref["y"][sl, :8].ravel(), ref["istatus"][sl, :5].ravel().astype(np.float64)])
+        assert np.array_equal(parts[r], want)
