@@ -23,7 +23,7 @@
 !                        lambda=lambda, mu=mu, ..., fun=fun, jac=jac, ..., icntrl_u=icntrl)
 !  (EXAMPLES/cbm4/CBM4_ROS_ADJ/cbm4_ros_adj_dr.F90:282-287) compile unchanged.  The EXTERNAL callback
 !  arguments are accepted and ignored: the model is selected with fatode_b200_set_model(); the
-!  shipped models (roberts, small_strato, cbm4) run as device functions.
+!  shipped models (roberts, small_strato, cbm4, swe) run as device functions.
 !  Batched entry points (INTEGRATE_ADJ_BATCH / INTEGRATE_BATCH) take NCELLS systems at once:
 !  Y(NVAR,NCELLS), Lambda(NVAR,NADJ,NCELLS), Mu(NP,NADJ,NCELLS), ISTATUS(20,NCELLS), ... — the
 !  column-major Fortran layout is exactly the C ABI's [cell][nadj][nvar] layout.
